@@ -1,0 +1,174 @@
+"""ctypes front of the CPU oracle (oracle/rt_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module;
+the product package (raytracer.jl_b200) never does.  Parity status: "parity unpinned" (no golden vectors exist
+in the reference and Julia is unavailable) -- see the header of rt_oracle.cpp for what pins the oracle instead.
+
+All ids are 1-based int64 as in the Julia reference.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+I64 = C.c_int64
+F64P = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+I64P = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+I8P = np.ctypeslib.ndpointer(dtype=np.int8, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "librt_oracle.so")
+    src = os.path.join(_HERE, "rt_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "librt_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.ora_annulus_build.restype = C.c_void_p
+        L.ora_annulus_build.argtypes = [I64, I64, C.c_double]
+        L.ora_mesh_sizes.argtypes = [C.c_void_p, I64P]
+        L.ora_mesh_export.argtypes = [C.c_void_p, F64P, F64P, F64P, F64P, I64P, I64P, I64P, I64P, I64P, I64P,
+                                      I64P, I8P]
+        L.ora_mesh_free.argtypes = [C.c_void_p]
+        L.ora_interp_velocity.argtypes = [F64P, F64P, I64, F64P, I64, C.c_double, F64P]
+        L.ora_closest_point.restype = I64
+        L.ora_closest_point.argtypes = [F64P, F64P, I64, C.c_double, C.c_double]
+        L.ora_bfm.argtypes = [I64, I64, I64P, I64P, I64P, I64P, I64P, I64, F64P, F64P, F64P, I64, C.c_int, I64,
+                              F64P, I64P, I64P]
+        L.ora_dijkstra.argtypes = [I64, I64, I64P, I64P, I64P, I64P, I64P, I64, F64P, F64P, F64P, I64, F64P]
+        L.ora_reconstruct_path.restype = I64
+        L.ora_reconstruct_path.argtypes = [I64P, I64, I64, I64, I64P, I64]
+        L.ora_grid3d_coords.argtypes = [F64P, F64P, I64P, C.c_int, F64P, F64P, F64P]
+        L.ora_bfm3d.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, C.c_int, I64, F64P, I64P, I64P]
+        L.ora_dijkstra3d.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, F64P]
+        L.ora_num_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+class Annulus:
+    """Arrays of `gr, G, halo = init_annulus(ntheta, nr; spacing)` (src/GridAnnulus.jl:57-70)."""
+
+    def __init__(self, ntheta, nr, spacing):
+        L = lib()
+        h = L.ora_annulus_build(int(ntheta), int(nr), float(spacing))
+        sz = np.zeros(8, np.int64)
+        L.ora_mesh_sizes(h, sz)
+        n, nel, se, nnz, hr, sn, nth, nrr = (int(v) for v in sz)
+        self.n, self.nel, self.ntheta, self.nr = n, nel, nth, nrr
+        self.x, self.z, self.theta, self.r = (np.zeros(n) for _ in range(4))
+        self.e2n_off = np.zeros(nel + 1, np.int64)
+        self.e2n_idx = np.zeros(se, np.int64)
+        self.G_colptr = np.zeros(n + 1, np.int64)
+        self.G_rowval = np.zeros(nnz, np.int64)
+        self.halo = np.zeros(max(2 * hr, 1), np.int64)
+        self.nbr_off = np.zeros(nel + 1, np.int64)
+        self.nbr_idx = np.zeros(max(sn, 1), np.int64)
+        self.el_type = np.zeros(nel, np.int8)
+        L.ora_mesh_export(h, self.x, self.z, self.theta, self.r, self.e2n_off, self.e2n_idx, self.G_colptr,
+                          self.G_rowval, self.halo, self.nbr_off, self.nbr_idx, self.el_type)
+        L.ora_mesh_free(h)
+        self.halo = self.halo[:2 * hr]
+        self.nbr_idx = self.nbr_idx[:sn]
+        self.halo_rows = hr
+
+    def halo_matrix(self):
+        """(2H, 2) like the Julia Matrix{Int64} (column-major storage)."""
+        return self.halo.reshape(2, self.halo_rows).T
+
+
+def interp_velocity(knots_r, knots_v, r, buffer=-1.0):
+    r = np.ascontiguousarray(r, np.float64)
+    out = np.zeros_like(r)
+    rc = lib().ora_interp_velocity(np.ascontiguousarray(knots_r, np.float64),
+                                   np.ascontiguousarray(knots_v, np.float64), len(knots_r), r, len(r),
+                                   float(buffer), out)
+    if rc:
+        raise ValueError("interpolation point outside the knots (BoundsError in the reference)")
+    return out
+
+
+def closest_point(a, b, pa, pb):
+    return int(lib().ora_closest_point(np.ascontiguousarray(a), np.ascontiguousarray(b), len(a), float(pa),
+                                       float(pb)))
+
+
+def bfm(mesh, U, source, nthreads=1, max_sweeps=0):
+    """bfm(G, halo, source, gr, U) (src/SSSP/bfm.jl:1-52). Returns dist, prev (1-based, 0 = never set), stats."""
+    n = mesh.n
+    dist = np.zeros(n)
+    prev = np.zeros(n, np.int64)
+    stats = np.zeros(4, np.int64)
+    halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
+    rc = lib().ora_bfm(n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.G_colptr, mesh.G_rowval, halo,
+                       mesh.halo_rows, mesh.x, mesh.z, np.ascontiguousarray(U, np.float64), int(source),
+                       int(nthreads), int(max_sweeps), dist, prev, stats)
+    if rc:
+        raise ValueError("bad source")
+    return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
+                            graph_edges=int(stats[3]))
+
+
+def dijkstra(mesh, U, source):
+    dist = np.zeros(mesh.n)
+    halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
+    lib().ora_dijkstra(mesh.n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.G_colptr, mesh.G_rowval, halo,
+                       mesh.halo_rows, mesh.x, mesh.z, np.ascontiguousarray(U, np.float64), int(source), dist)
+    return dist
+
+
+def reconstruct_path(prev, source, receiver):
+    prev = np.ascontiguousarray(prev, np.int64)
+    cap = 1024
+    while True:
+        out = np.zeros(cap, np.int64)
+        ln = int(lib().ora_reconstruct_path(prev, len(prev), int(source), int(receiver), out, cap))
+        if ln == -1:
+            raise RuntimeError("path does not reach the source")
+        if ln < 0:
+            cap = -ln
+            continue
+        return out[:ln].copy()
+
+
+def grid3d_coords(c0, c1, nn, coord_system=0):
+    nn = np.asarray(nn, np.int64)
+    n = int(np.prod(nn))
+    X, Y, Z = np.zeros(n), np.zeros(n), np.zeros(n)
+    lib().ora_grid3d_coords(np.asarray(c0, np.float64), np.asarray(c1, np.float64), nn, int(coord_system), X, Y,
+                            Z)
+    return X, Y, Z
+
+
+def bfm3d(nn, star_levels, X, Y, Z, U, source, nthreads=1, max_sweeps=0):
+    nn = np.asarray(nn, np.int64)
+    n = int(np.prod(nn))
+    dist = np.zeros(n)
+    prev = np.zeros(n, np.int64)
+    stats = np.zeros(4, np.int64)
+    rc = lib().ora_bfm3d(nn, int(star_levels), X, Y, Z, np.ascontiguousarray(U, np.float64), int(source),
+                         int(nthreads), int(max_sweeps), dist, prev, stats)
+    if rc:
+        raise ValueError("bad source")
+    return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
+                            graph_edges=int(stats[3]))
+
+
+def dijkstra3d(nn, star_levels, X, Y, Z, U, source):
+    nn = np.asarray(nn, np.int64)
+    dist = np.zeros(int(np.prod(nn)))
+    lib().ora_dijkstra3d(nn, int(star_levels), X, Y, Z, np.ascontiguousarray(U, np.float64), int(source), dist)
+    return dist
+
+
+def num_threads():
+    return int(lib().ora_num_threads())

@@ -1,0 +1,770 @@
+// rt_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE ONLY, never shipped, never measured as product).
+//
+// A plain C++ restatement of the reference algorithm of albert-de-montserrat/RayTracer.jl for the
+// shortest-path-method hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// `--impl reference` legs may load this library.  The product (raytracer.jl_b200/csrc) never links it.
+//
+// PARITY STATUS: "parity unpinned" at the level of golden vectors -- the reference is pure Julia, ships no
+// tests / fixtures / known-answer vectors, and Julia is not installed here, so the reference cannot be run.
+// The oracle is pinned instead by (1) a line-by-line restatement with file:line citations below,
+// (2) the closed-form node/element/halo counts of SURVEY.md section 8 (tests/test_oracle_builder.py),
+// (3) algebraic invariants of SURVEY.md section 8c and (4) an independent binary-heap Dijkstra that must give
+// bit-identical travel times (ora_dijkstra*).
+//
+// Build: see oracle/Makefile  (g++ -O2 -ffp-contract=off -fopenmp; no FMA contraction anywhere, because
+// plain Julia never contracts a*b+c).
+//
+// All node / element ids crossing this API are 1-based int64 exactly as in Julia.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <queue>
+#include <string>
+#include <utility>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef int64_t i64;
+
+namespace {
+
+const double R_EARTH = 6371.0;  // src/utils.jl:2
+// src/GridAnnulus.jl:73 (Float32 literals, all exactly representable in binary)
+const double RL[7] = {6371.0 - 20.0, 6371.0 - 35.0, 6371.0 - 210.0, 6371.0 - 410.0,
+                      6371.0 - 660.0, 6371.0 - 2740.0, 6371.0 - 2891.5};
+const double PI = 3.141592653589793;  // Float64(pi)
+
+// Julia Base: lerpi(j, d, a, b) = (t = j/d; (1-t)*a + t*b)   (LinRange element j+1 of d+1)
+inline double lerpi(i64 j, i64 d, double a, double b) {
+  double t = (double)j / (double)d;
+  return (1.0 - t) * a + t * b;
+}
+
+// Julia float `div(x, y)` = round((x - rem(x, y)) / y), rem == C fmod (exact), round == ties-to-even.
+inline double julia_fdiv(double x, double y) { return std::nearbyint((x - std::fmod(x, y)) / y); }
+
+struct Mesh {
+  std::vector<double> x, z, theta, r;
+  std::vector<std::vector<i64>> e2n;  // [nel], 1-based node ids
+  std::vector<std::vector<i64>> nbr;  // [nel], 1-based element ids
+  std::vector<int8_t> el_type;        // 0 = :Quad, 1 = :Tri
+  i64 ntheta = 0, nr = 0, nel = 0, nnods = 0;
+  std::vector<i64> G_colptr, G_rowval;  // SparseMatrixCSC{Bool,Int64}(nel x nnods), 1-based
+  std::vector<i64> halo;                // (2H x 2) column-major, 1-based
+  i64 halo_rows = 0;
+  std::string err;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// src/GridAnnulus.jl:473-507  element_neighbours
+void element_neighbours(Mesh& m) {
+  const i64 nel = m.nel;
+  // incidence_matrix = sparse(J=element, I=node): column(node) = ascending element ids containing node
+  std::vector<std::vector<i64>> node2el(m.nnods + 1);
+  for (i64 e = 1; e <= nel; ++e)
+    for (i64 nd : m.e2n[e - 1]) node2el[nd].push_back(e);  // ascending because e ascends
+  m.nbr.assign(nel, {});
+  // NOTE reference quirk :490 -- `for node in 1:nel` (nel == number of ring nodes; the centre node is skipped)
+  for (i64 node = 1; node <= nel && node <= m.nnods; ++node) {
+    const auto& els = node2el[node];
+    for (i64 e1 : els) {
+      auto& cur = m.nbr[e1 - 1];
+      for (i64 e2 : els)
+        if (e1 != e2 && std::find(cur.begin(), cur.end(), e2) == cur.end()) cur.push_back(e2);
+    }
+  }
+}
+
+// src/GridAnnulus.jl:72-142  primary_grid
+void primary_grid(Mesh& m, i64 ntheta, i64 nr_in) {
+  i64 nr = nr_in + 7;  // :75
+  i64 nn = nr * ntheta;
+  i64 nels = (nr - 1) * ntheta;
+  m.ntheta = ntheta;
+  m.nr = nr;
+  m.r.assign(nn + 1, 0.0);
+  m.theta.assign(nn + 1, 0.0);
+  double dth = 2 * PI / (double)ntheta;  // :81
+  double r_in = 0.1, r_out = R_EARTH;    // :84
+  std::vector<double> rcol;
+  for (int k = 0; k < 7; ++k) rcol.push_back(RL[k]);
+  i64 nlin = nr - 7;
+  for (i64 j = 0; j < nlin; ++j) rcol.push_back(nlin > 1 ? lerpi(j, nlin - 1, r_in, r_out) : r_in);
+  std::sort(rcol.begin(), rcol.end());  // :87
+  for (i64 ii = 1; ii <= ntheta; ++ii)
+    for (i64 k = 1; k <= nr; ++k) {
+      i64 id = k + nr * (ii - 1);
+      m.r[id - 1] = rcol[k - 1];
+      m.theta[id - 1] = dth * (double)(ii - 1);  // :92
+    }
+  // centre :95 already 0,0
+  m.e2n.clear();
+  m.e2n.resize(nels + ntheta);
+  m.el_type.assign(nels + ntheta, 0);
+  for (i64 ii = 1; ii <= ntheta; ++ii)  // :99-111
+    for (i64 k = 1; k <= nr - 1; ++k) {
+      i64 idx = k + (nr - 1) * (ii - 1);
+      i64 idx1 = k + nr * (ii - 1);
+      i64 idx2 = (ii < ntheta) ? k + nr * ii : k;
+      m.e2n[idx - 1] = {idx1, idx2, idx2 + 1, idx1 + 1};
+    }
+  for (i64 ii = 1; ii <= ntheta; ++ii) {  // :114-121
+    i64 idx = 1 + nr * (ii - 1);
+    i64 third = (ii == ntheta) ? 1 : idx + nr;
+    m.e2n[nels + ii - 1] = {nn + 1, idx, third};
+    m.el_type[nels + ii - 1] = 1;
+  }
+  m.nel = nels + ntheta;
+  m.nnods = nn + 1;
+  element_neighbours(m);
+  m.x.resize(m.nnods);
+  m.z.resize(m.nnods);
+  for (i64 i = 0; i < m.nnods; ++i) {  // @cartesian :27-29
+    m.x[i] = m.r[i] * std::sin(m.theta[i]);
+    m.z[i] = m.r[i] * std::cos(m.theta[i]);
+  }
+}
+
+struct Edges {
+  std::vector<std::pair<i64, i64>> nodes;  // sorted (lo, hi)
+  std::vector<std::vector<i64>> els;       // edge2el (set semantics; insertion order irrelevant)
+};
+
+// src/GridAnnulus.jl:515-595  edge_connectivity (with the slot-1 quirk at :566-571)
+void edge_connectivity(const Mesh& m, Edges& E) {
+  const i64 nel = m.nel;
+  std::vector<i64> el2edge(4 * nel, 0);
+  auto has_node = [&](i64 el, i64 nd) {
+    const auto& v = m.e2n[el - 1];
+    return std::find(v.begin(), v.end(), nd) != v.end();
+  };
+  for (i64 iel = 1; iel <= nel; ++iel) {
+    const auto& el = m.e2n[iel - 1];
+    int nedge = (int)el.size();  // only primary nodes exist at this point
+    for (int ie = 0; ie < nedge; ++ie) {
+      if (el2edge[ie + 4 * (iel - 1)] != 0) continue;
+      i64 a = el[ie], b = el[(ie + 1) % nedge];  // map_rectangle / map_triangle :519-526
+      if (a > b) std::swap(a, b);                // sort!(edge; dims=1)
+      E.nodes.push_back({a, b});
+      E.els.push_back({iel});
+      i64 gid = (i64)E.nodes.size();
+      el2edge[ie + 4 * (iel - 1)] = gid;
+      for (i64 ieln : m.nbr[iel - 1]) {
+        // issubset(edge[:, iedge], edge_neighbour): both endpoints among the neighbour's nodes;
+        // the inner `for i in 1:nedge ... break` always lands on i = 1  (:566-571)
+        if (has_node(ieln, a) && has_node(ieln, b)) {
+          el2edge[0 + 4 * (ieln - 1)] = gid;
+          auto& s = E.els.back();
+          if (std::find(s.begin(), s.end(), ieln) == s.end()) s.push_back(ieln);
+        }
+      }
+    }
+  }
+}
+
+// src/GridAnnulus.jl:607-698 secondary_nodes, :700-708 edge_length, :710-725 correct_theta
+void secondary_nodes(Mesh& m, double spacing) {
+  Edges E;
+  edge_connectivity(m, E);
+  const i64 nedges = (i64)E.nodes.size();
+  const double eps = 2 * PI - (1.0 - 1.0 / (double)m.ntheta);  // :621
+  const i64 icenter = m.nr * m.ntheta + 1;                      // :622
+  const i64 nnods0 = (i64)m.r.size();
+  std::vector<double> thmid, rmid;
+  i64 gidx = 0;
+  for (i64 i = 0; i < nedges; ++i) {
+    i64 n1 = E.nodes[i].first, n2 = E.nodes[i].second;
+    double t1 = m.theta[n1 - 1], t2 = m.theta[n2 - 1];
+    double r1 = m.r[n1 - 1], r2 = m.r[n2 - 1];
+    if (n1 != icenter && n2 != icenter) {  // correct_theta
+      if (std::fabs(t1 - t2) >= eps) {
+        if (t1 < PI)
+          t1 = t1 + 2 * PI;
+        else if (t2 < PI)
+          t2 = t2 + 2 * PI;
+      }
+    } else {
+      double tm = std::max(t1, t2);
+      t1 = tm;
+      t2 = tm;
+    }
+    double L;
+    if (t1 == t2)
+      L = std::sqrt(r1 * r1 + r2 * r2 - 2 * r1 * r2 * std::cos(t1 - t2));  // polardistance :706
+    else
+      L = r1 * std::fabs(t2 - t1);  // arclength :708
+    i64 np = (i64)julia_fdiv(L, spacing);  // :642
+    if (np > 0) {
+      for (i64 j = 1; j <= np; ++j) {
+        ++gidx;
+        double Lt = t2 - t1, Lr = r2 - r1;
+        double dt = Lt * (double)j / (double)(np + 1);  // :653
+        double dr = Lr * (double)j / (double)(np + 1);
+        thmid.push_back(t1 + dt);
+        rmid.push_back(r1 + dr);
+        for (i64 iel : E.els[i]) m.e2n[iel - 1].push_back(gidx + nnods0);  // :661-663
+      }
+    }
+  }
+  m.theta.insert(m.theta.end(), thmid.begin(), thmid.end());
+  m.r.insert(m.r.end(), rmid.begin(), rmid.end());
+  m.nnods = (i64)m.r.size();
+  m.x.resize(m.nnods);
+  m.z.resize(m.nnods);
+  for (i64 i = 0; i < m.nnods; ++i) {  // :671
+    m.x[i] = m.r[i] * std::sin(m.theta[i]);
+    m.z[i] = m.r[i] * std::cos(m.theta[i]);
+  }
+}
+
+// src/GridAnnulus.jl:374-381
+int find_boundary(double ri, const double* rlayer /*8*/) {
+  if (ri < rlayer[7]) return 1;
+  for (int i = 0; i < 7; ++i)
+    if (rlayer[i] > ri && ri > rlayer[i + 1]) return i + 2;
+  return 0;  // Julia would return `nothing`
+}
+
+// src/GridAnnulus.jl:296-321
+void constrain2layers(Mesh& m) {
+  const double rlayer[8] = {R_EARTH,        R_EARTH - 20,  R_EARTH - 35,   R_EARTH - 210,
+                            R_EARTH - 410,  R_EARTH - 660, R_EARTH - 2740, R_EARTH - 2891.5};
+  std::vector<int> lay(m.nel);
+  for (i64 i = 0; i < m.nel; ++i) {
+    const auto& e = m.e2n[i];
+    double c;
+    if (m.el_type[i] == 0)
+      c = (m.r[e[0] - 1] + m.r[e[1] - 1] + m.r[e[2] - 1] + m.r[e[3] - 1]) * 0.25;
+    else
+      c = (m.r[e[0] - 1] + m.r[e[1] - 1] + m.r[e[2] - 1]) * 0.33;
+    lay[i] = find_boundary(c, rlayer);
+  }
+  for (i64 i = 0; i < m.nel; ++i) {
+    std::vector<i64> keep;
+    for (i64 nb : m.nbr[i])
+      if (lay[nb - 1] == lay[i]) keep.push_back(nb);
+    m.nbr[i].swap(keep);
+  }
+}
+
+// src/GridAnnulus.jl:910-968
+void discontinuous_boundaries(Mesh& m) {
+  std::vector<i64> idx;
+  i64 counter = m.nnods;
+  const i64 nnods = m.nnods;
+  for (i64 i = 0; i < m.nel; ++i) {
+    auto& e = m.e2n[i];
+    if (e.size() < 3) continue;
+    double r3 = m.r[e[2] - 1];
+    int ib = -1;
+    for (int k = 0; k < 7; ++k)
+      if (r3 == RL[k]) {
+        ib = k;
+        break;
+      }
+    if (ib < 0) continue;
+    for (size_t j = 0; j < e.size(); ++j) {
+      i64 node = e[j];
+      if (m.r[node - 1] == RL[ib]) {
+        ++counter;
+        e[j] = counter;
+        idx.push_back(node);
+      }
+    }
+  }
+  const i64 H = (i64)idx.size();
+  for (i64 k = 0; k < H; ++k) {
+    double th = m.theta[idx[k] - 1];
+    double rr = m.r[idx[k] - 1] - 0.05;  // :938
+    m.theta.push_back(th);
+    m.r.push_back(rr);
+    m.x.push_back(rr * std::sin(th));  // polar2cartesian :55
+    m.z.push_back(rr * std::cos(th));
+  }
+  m.halo_rows = 2 * H;
+  m.halo.assign(4 * H, 0);
+  for (i64 k = 0; k < H; ++k) {  // :945-950  (column-major 2H x 2)
+    m.halo[k] = idx[k];
+    m.halo[k + 2 * H] = k + 1 + nnods;
+    m.halo[k + H + 2 * H] = idx[k];
+    m.halo[k + H] = k + 1 + nnods;
+  }
+  m.nnods = (i64)m.r.size();
+}
+
+// src/GridAnnulus.jl:420-452  element_incidence; sparse(I,J,V) sorts rows within a column and ORs duplicates
+void element_incidence(Mesh& m) {
+  const i64 n = m.nnods;
+  std::vector<i64> cnt(n + 1, 0);
+  for (i64 e = 0; e < m.nel; ++e) cnt[0] += 0;
+  for (i64 e = 0; e < m.nel; ++e)
+    for (i64 nd : m.e2n[e]) cnt[nd] += 1 + (i64)m.nbr[e].size();
+  std::vector<i64> off(n + 2, 0);
+  for (i64 v = 1; v <= n; ++v) off[v + 1] = off[v] + cnt[v];
+  std::vector<i64> tmp(off[n + 1]);
+  std::vector<i64> fill(off.begin(), off.end());
+  for (i64 e = 0; e < m.nel; ++e)
+    for (i64 nd : m.e2n[e]) {
+      tmp[fill[nd]++] = e + 1;
+      for (i64 nb : m.nbr[e]) tmp[fill[nd]++] = nb;
+    }
+  m.G_colptr.assign(n + 1, 1);
+  m.G_rowval.clear();
+  for (i64 v = 1; v <= n; ++v) {
+    auto b = tmp.begin() + off[v], e = tmp.begin() + off[v + 1];
+    std::sort(b, e);
+    e = std::unique(b, e);
+    m.G_rowval.insert(m.G_rowval.end(), b, e);
+    m.G_colptr[v] = (i64)m.G_rowval.size() + 1;
+  }
+}
+
+// flat views used by the solvers -------------------------------------------------------------------------
+struct Graph2D {
+  i64 n, nel;
+  const i64 *e2n_off, *e2n_idx;  // e2n_off[nel+1] 0-based offsets; e2n_idx 1-based node ids
+  const i64 *colptr, *rowval;    // Julia CSC, 1-based
+  const i64* halo;
+  i64 halo_rows;
+  const double *x, *z, *U;
+};
+
+// src/SSSP/bfm.jl:186 + src/GridAnnulus.jl:808-815: dGi + 2.0 * sqrt(0 + dx^2 + dz^2) / (Ui + Uj)
+inline double cand2d(const Graph2D& g, double dj, i64 i0, i64 j0) {
+  double dx = g.x[i0] - g.x[j0], dz = g.z[i0] - g.z[j0];
+  double d = 0.0;
+  d += dx * dx;
+  d += dz * dz;
+  return dj + 2.0 * std::sqrt(d) / (g.U[i0] + g.U[j0]);
+}
+
+const double INF = std::numeric_limits<double>::infinity();
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ annulus builder (init_annulus :57-70)
+void* ora_annulus_build(i64 ntheta, i64 nr, double spacing) {
+  Mesh* m = new Mesh();
+  primary_grid(*m, ntheta, nr);
+  secondary_nodes(*m, spacing);
+  constrain2layers(*m);
+  discontinuous_boundaries(*m);
+  element_incidence(*m);
+  return m;
+}
+
+void ora_mesh_sizes(void* h, i64* out /*[8]: n, nel, sum_e2n, nnzG, halo_rows, sum_nbr, ntheta, nr*/) {
+  Mesh* m = (Mesh*)h;
+  i64 se = 0, sn = 0;
+  for (auto& e : m->e2n) se += (i64)e.size();
+  for (auto& e : m->nbr) sn += (i64)e.size();
+  out[0] = m->nnods;
+  out[1] = m->nel;
+  out[2] = se;
+  out[3] = (i64)m->G_rowval.size();
+  out[4] = m->halo_rows;
+  out[5] = sn;
+  out[6] = m->ntheta;
+  out[7] = m->nr;
+}
+
+void ora_mesh_export(void* h, double* x, double* z, double* th, double* r, i64* e2n_off, i64* e2n_idx,
+                     i64* colptr, i64* rowval, i64* halo, i64* nbr_off, i64* nbr_idx, int8_t* el_type) {
+  Mesh* m = (Mesh*)h;
+  std::memcpy(x, m->x.data(), sizeof(double) * m->nnods);
+  std::memcpy(z, m->z.data(), sizeof(double) * m->nnods);
+  std::memcpy(th, m->theta.data(), sizeof(double) * m->nnods);
+  std::memcpy(r, m->r.data(), sizeof(double) * m->nnods);
+  i64 o = 0, on = 0;
+  for (i64 e = 0; e < m->nel; ++e) {
+    e2n_off[e] = o;
+    for (i64 nd : m->e2n[e]) e2n_idx[o++] = nd;
+    nbr_off[e] = on;
+    for (i64 nb : m->nbr[e]) nbr_idx[on++] = nb;
+    el_type[e] = m->el_type[e];
+  }
+  e2n_off[m->nel] = o;
+  nbr_off[m->nel] = on;
+  std::memcpy(colptr, m->G_colptr.data(), sizeof(i64) * (m->nnods + 1));
+  std::memcpy(rowval, m->G_rowval.data(), sizeof(i64) * m->G_rowval.size());
+  if (m->halo_rows) std::memcpy(halo, m->halo.data(), sizeof(i64) * 2 * m->halo_rows);
+}
+
+void ora_mesh_free(void* h) { delete (Mesh*)h; }
+
+// --------------------------------------------------------------------------------- velocity interpolation
+// src/utils.jl:38-44 (buffer < 0) and src/ShortestPath.jl:74-90 (buffer >= 0).  Interpolations.jl
+// gridded linear (version unpinned -> "parity unpinned" at the ulp level): i = clamp(searchsortedlast(knots,x),
+// 1, nk-1); f = (x-k[i])/(k[i+1]-k[i]); v = (1-f)*y[i] + f*y[i+1]; outside the knots -> error (Throw()).
+int ora_interp_velocity(const double* kr, const double* kv, i64 nk, const double* r, i64 n, double buffer,
+                        double* out) {
+  for (i64 i = 0; i < n; ++i) {
+    double xq = r[i];
+    if (buffer >= 0.0) {
+      for (int k = 0; k < 7; ++k)
+        if (xq == RL[k]) {
+          xq = xq + buffer;
+          break;
+        }
+    }
+    if (!(xq >= kr[0] && xq <= kr[nk - 1])) return 1;  // BoundsError in the reference
+    i64 idx = (i64)(std::upper_bound(kr, kr + nk, xq) - kr);  // searchsortedlast (1-based)
+    if (idx < 1) idx = 1;
+    if (idx > nk - 1) idx = nk - 1;
+    double f = (xq - kr[idx - 1]) / (kr[idx] - kr[idx - 1]);
+    out[i] = (1.0 - f) * kv[idx - 1] + f * kv[idx];
+  }
+  return 0;
+}
+
+// src/GridAnnulus.jl:823-840 closest_point: first index minimising sqrt((a-pa)^2 + (b-pb)^2)
+i64 ora_closest_point(const double* a, const double* b, i64 n, double pa, double pb) {
+  double best = INF;
+  i64 index = -1;
+  for (i64 i = 0; i < n; ++i) {
+    double da = a[i] - pa, db = b[i] - pb;
+    double di = std::sqrt(da * da + db * db);
+    if (di < best) {
+      index = i + 1;
+      best = di;
+    }
+  }
+  return index;
+}
+
+// ------------------------------------------------------------------------------------ bfm (src/SSSP/bfm.jl)
+// stats[0] = sweeps, stats[1] = candidate evaluations (E_relaxed), stats[2] = active-vertex updates,
+// stats[3] = E_graph (sum over vertices of |scan list|)
+int ora_bfm(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
+            const i64* halo, i64 halo_rows, const double* x, const double* z, const double* U, i64 source,
+            int nthreads, i64 max_sweeps, double* dist, i64* prev, i64* stats) {
+  Graph2D g{n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U};
+  if (source < 1 || source > n) return 1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  std::vector<double> dist0(n);
+  std::vector<uint8_t> Q(n, 0);
+  for (i64 i = 0; i < n; ++i) prev[i] = 0;  // reference leaves p undefined (bfm.jl:12)
+  // init_halo_path! :64-70 (n = length(halo) / 2 == all 2H rows)
+  for (i64 k = 0; k < halo_rows; ++k) {
+    i64 h1 = halo[k], h2 = halo[k + halo_rows];
+    prev[h2 - 1] = h1;
+    prev[h1 - 1] = h2;
+  }
+  // init_Q! :74-80
+  for (i64 p = colptr[source - 1]; p < colptr[source]; ++p) {
+    i64 el = rowval[p - 1];
+    for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q) Q[e2n_idx[q] - 1] = 1;
+  }
+  for (i64 i = 0; i < n; ++i) dist[i] = INF;
+  dist[source - 1] = 0.0;
+  for (i64 i = 0; i < n; ++i) dist0[i] = dist[i];
+  i64 sweeps = 0, evals = 0, updates = 0;
+  std::vector<i64> active;
+  active.reserve(n);
+  while (true) {
+    active.clear();
+    for (i64 i = 0; i < n; ++i)
+      if (Q[i]) active.push_back(i);  // findall(Q) :107
+    if (active.empty()) break;        // sum(Q) != 0 :29
+    if (max_sweeps > 0 && sweeps >= max_sweeps) break;
+    i64 ev = 0;
+    const i64 na = (i64)active.size();
+    // relax! :100-111 -> _relax! :161-210
+#pragma omp parallel for schedule(static) reduction(+ : ev)
+    for (i64 a = 0; a < na; ++a) {
+      i64 i0 = active[a];
+      double di = dist0[i0];
+      for (i64 p = colptr[i0]; p < colptr[i0 + 1]; ++p) {
+        i64 el = rowval[p - 1];
+        for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q) {
+          i64 j0 = e2n_idx[q] - 1;
+          double dj = dist0[j0];
+          double delta = (dj == INF) ? INF : cand2d(g, dj, i0, j0);
+          if (di > delta) {
+            di = delta;
+            prev[i0] = j0 + 1;
+          }
+          ++ev;
+        }
+      }
+      dist[i0] = di;
+    }
+    evals += ev;
+    updates += na;
+    // update_halo! :54-62 (serial order == single-thread reference)
+    for (i64 k = 0; k < halo_rows; ++k) {
+      i64 h1 = halo[k] - 1, h2 = halo[k + halo_rows] - 1;
+      if (dist[h1] < dist0[h1] && dist[h2] > dist[h1]) {
+        dist[h2] = dist[h1];
+        prev[h2] = prev[h1];
+      }
+    }
+    std::fill(Q.begin(), Q.end(), 0);  // :37
+    // update_Q! :82-98 (byte flags: benign races only)
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < n; ++i) {
+      if (dist[i] < INF && dist[i] < dist0[i]) {
+        for (i64 p = colptr[i]; p < colptr[i + 1]; ++p) {
+          i64 el = rowval[p - 1];
+          for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q) {
+            i64 j0 = e2n_idx[q] - 1;
+            if (!Q[j0]) Q[j0] = 1;
+          }
+        }
+      }
+    }
+    std::memcpy(dist0.data(), dist, sizeof(double) * n);  // :43
+    ++sweeps;
+  }
+  if (stats) {
+    i64 eg = 0;
+    for (i64 i = 0; i < n; ++i)
+      for (i64 p = colptr[i]; p < colptr[i + 1]; ++p) {
+        i64 el = rowval[p - 1];
+        eg += e2n_off[el] - e2n_off[el - 1];
+      }
+    stats[0] = sweeps;
+    stats[1] = evals;
+    stats[2] = updates;
+    stats[3] = eg;
+  }
+  return 0;
+}
+
+// Independent check: binary-heap Dijkstra on the same (symmetric) scan lists + halo rows as 0-weight edges.
+// Must give bit-identical dist (fp `+` is monotone => least fixed point is schedule independent).
+int ora_dijkstra(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
+                 const i64* halo, i64 halo_rows, const double* x, const double* z, const double* U, i64 source,
+                 double* dist) {
+  Graph2D g{n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U};
+  std::vector<std::vector<i64>> twins(n);
+  for (i64 k = 0; k < halo_rows; ++k) twins[halo[k] - 1].push_back(halo[k + halo_rows] - 1);
+  for (i64 i = 0; i < n; ++i) dist[i] = INF;
+  dist[source - 1] = 0.0;
+  typedef std::pair<double, i64> PQE;
+  std::priority_queue<PQE, std::vector<PQE>, std::greater<PQE>> pq;
+  pq.push({0.0, source - 1});
+  std::vector<uint8_t> done(n, 0);
+  while (!pq.empty()) {
+    PQE t = pq.top();
+    pq.pop();
+    i64 u = t.second;
+    if (done[u]) continue;
+    done[u] = 1;
+    double du = dist[u];
+    for (i64 v : twins[u])
+      if (du < dist[v]) {
+        dist[v] = du;
+        pq.push({du, v});
+      }
+    for (i64 p = colptr[u]; p < colptr[u + 1]; ++p) {
+      i64 el = rowval[p - 1];
+      for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q) {
+        i64 v = e2n_idx[q] - 1;
+        if (done[v]) continue;
+        double c = cand2d(g, du, v, u);  // evaluated from v's side exactly as _relax! does
+        if (c < dist[v]) {
+          dist[v] = c;
+          pq.push({c, v});
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+// src/SSSP/ssspm.jl:30-40  recontruct_path(prev::Vector, source, receiver) -> [receiver ... source]
+// returns path length, or -1 if the chase does not reach `source` within n steps (the reference would
+// loop forever / throw), or -(needed) if cap is too small.
+i64 ora_reconstruct_path(const i64* prev, i64 n, i64 source, i64 receiver, i64* out, i64 cap) {
+  i64 len = 0;
+  if (receiver < 1 || receiver > n) return -1;
+  if (len < cap) out[len] = receiver;
+  ++len;
+  i64 ip = (receiver == source) ? source : prev[receiver - 1];
+  i64 steps = 0;
+  while (ip != source) {
+    if (ip < 1 || ip > n || ++steps > n) return -1;
+    if (len < cap) out[len] = ip;
+    ++len;
+    ip = prev[ip - 1];
+  }
+  if (len < cap) out[len] = source;
+  ++len;
+  return len <= cap ? len : -len;
+}
+
+// ------------------------------------------------------------------------------------------ 3-D grid
+// src/StructuredGrid.jl:35-45 grid (LinRange axes), :90-96 CartesianIndex (x fastest), :225-235 spherical2cart
+// coord_system 0: Cartesian axes as they are; 1: axes are (theta, phi, r) -> spherical2cart.
+void ora_grid3d_coords(const double* c0, const double* c1, const i64* nn, int coord_system, double* X,
+                       double* Y, double* Z) {
+  std::vector<double> ax[3];
+  for (int d = 0; d < 3; ++d) {
+    ax[d].resize(nn[d]);
+    for (i64 i = 0; i < nn[d]; ++i) ax[d][i] = nn[d] > 1 ? lerpi(i, nn[d] - 1, c0[d], c1[d]) : c0[d];
+  }
+  i64 I = 0;
+  for (i64 k = 0; k < nn[2]; ++k)
+    for (i64 j = 0; j < nn[1]; ++j)
+      for (i64 i = 0; i < nn[0]; ++i, ++I) {
+        double a = ax[0][i], b = ax[1][j], c = ax[2][k];
+        if (coord_system == 0) {
+          X[I] = a;
+          Y[I] = b;
+          Z[I] = c;
+        } else {
+          X[I] = c * std::cos(b) * std::sin(a);
+          Y[I] = c * std::sin(b) * std::sin(a);
+          Z[I] = c * std::cos(a);
+        }
+      }
+}
+
+// src/SSSP/weights.jl:20  edge_weight = distance3D(p1,p2) * (1/abs(U1+U2)) * 2 ; distance3D StructuredGrid.jl:239
+static inline double cand3d(const double* X, const double* Y, const double* Z, const double* U, double dj,
+                            i64 i, i64 j) {
+  double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
+  double d = std::sqrt(dx * dx + dy * dy + dz * dz);
+  double w = d * (1.0 / std::fabs(U[i] + U[j])) * 2.0;
+  return dj + w;
+}
+
+// star-L adjacency of nodal_incidence (StructuredGrid.jl:177-223): L = 0 -> 26-neighbourhood without self;
+// L >= 1 -> clipped (2L+3)^3 window INCLUDING self.  Canonical scan order = ascending linear id (the
+// reference iterates a Julia Set, whose order is not reproducible).  Control flow = BFM/foo!/goo!
+// (src/Dijsktra.jl:294-343, 376-403).
+int ora_bfm3d(const i64* nn, int star_levels, const double* X, const double* Y, const double* Z,
+              const double* U, i64 source, int nthreads, i64 max_sweeps, double* dist, i64* prev, i64* stats) {
+  const i64 nx = nn[0], ny = nn[1], nz = nn[2], n = nx * ny * nz;
+  const i64 w = star_levels + 1;
+  const bool self = star_levels >= 1;
+  if (source < 1 || source > n) return 1;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  std::vector<double> dist0(n);
+  std::vector<uint8_t> act(n, 0), imp(n, 0);
+  for (i64 i = 0; i < n; ++i) {
+    dist[i] = INF;
+    prev[i] = 0;
+  }
+  dist[source - 1] = 0.0;
+  dist0.assign(dist, dist + n);
+  auto mark_window = [&](i64 I, std::vector<uint8_t>& flags) {
+    i64 i = I % nx, j = (I / nx) % ny, k = I / (nx * ny);
+    for (i64 kk = std::max<i64>(0, k - w); kk <= std::min(nz - 1, k + w); ++kk)
+      for (i64 jj = std::max<i64>(0, j - w); jj <= std::min(ny - 1, j + w); ++jj)
+        for (i64 ii = std::max<i64>(0, i - w); ii <= std::min(nx - 1, i + w); ++ii) {
+          i64 J = ii + nx * (jj + ny * kk);
+          if (J == I && !self) continue;
+          flags[J] = 1;
+        }
+  };
+  mark_window(source - 1, act);
+  i64 sweeps = 0, evals = 0, updates = 0;
+  std::vector<i64> active;
+  while (true) {
+    active.clear();
+    for (i64 i = 0; i < n; ++i)
+      if (act[i]) active.push_back(i);
+    if (active.empty()) break;
+    if (max_sweeps > 0 && sweeps >= max_sweeps) break;
+    i64 ev = 0;
+    const i64 na = (i64)active.size();
+#pragma omp parallel for schedule(static) reduction(+ : ev)
+    for (i64 a = 0; a < na; ++a) {
+      i64 I = active[a];
+      i64 i = I % nx, j = (I / nx) % ny, k = I / (nx * ny);
+      double di = dist0[I];
+      for (i64 kk = std::max<i64>(0, k - w); kk <= std::min(nz - 1, k + w); ++kk)
+        for (i64 jj = std::max<i64>(0, j - w); jj <= std::min(ny - 1, j + w); ++jj)
+          for (i64 ii = std::max<i64>(0, i - w); ii <= std::min(nx - 1, i + w); ++ii) {
+            i64 J = ii + nx * (jj + ny * kk);
+            if (J == I && !self) continue;
+            double dj = dist0[J];
+            double t = (dj == INF) ? INF : cand3d(X, Y, Z, U, dj, I, J);
+            if (di > t) {
+              di = t;
+              prev[I] = J + 1;
+            }
+            ++ev;
+          }
+      dist[I] = di;
+    }
+    evals += ev;
+    updates += na;
+    std::fill(act.begin(), act.end(), 0);
+    for (i64 I = 0; I < n; ++I)
+      if (dist[I] < dist0[I]) mark_window(I, act);  // goo!
+    std::memcpy(dist0.data(), dist, sizeof(double) * n);
+    ++sweeps;
+  }
+  if (stats) {
+    i64 eg = 0;
+    for (i64 k = 0; k < nz; ++k)
+      for (i64 j = 0; j < ny; ++j)
+        for (i64 i = 0; i < nx; ++i) {
+          i64 cx = std::min(nx - 1, i + w) - std::max<i64>(0, i - w) + 1;
+          i64 cy = std::min(ny - 1, j + w) - std::max<i64>(0, j - w) + 1;
+          i64 cz = std::min(nz - 1, k + w) - std::max<i64>(0, k - w) + 1;
+          eg += cx * cy * cz - (self ? 0 : 1);
+        }
+    stats[0] = sweeps;
+    stats[1] = evals;
+    stats[2] = updates;
+    stats[3] = eg;
+  }
+  return 0;
+}
+
+int ora_dijkstra3d(const i64* nn, int star_levels, const double* X, const double* Y, const double* Z,
+                   const double* U, i64 source, double* dist) {
+  const i64 nx = nn[0], ny = nn[1], nz = nn[2], n = nx * ny * nz;
+  const i64 w = star_levels + 1;
+  for (i64 i = 0; i < n; ++i) dist[i] = INF;
+  dist[source - 1] = 0.0;
+  typedef std::pair<double, i64> PQE;
+  std::priority_queue<PQE, std::vector<PQE>, std::greater<PQE>> pq;
+  pq.push({0.0, source - 1});
+  std::vector<uint8_t> done(n, 0);
+  while (!pq.empty()) {
+    PQE t = pq.top();
+    pq.pop();
+    i64 I = t.second;
+    if (done[I]) continue;
+    done[I] = 1;
+    i64 i = I % nx, j = (I / nx) % ny, k = I / (nx * ny);
+    for (i64 kk = std::max<i64>(0, k - w); kk <= std::min(nz - 1, k + w); ++kk)
+      for (i64 jj = std::max<i64>(0, j - w); jj <= std::min(ny - 1, j + w); ++jj)
+        for (i64 ii = std::max<i64>(0, i - w); ii <= std::min(nx - 1, i + w); ++ii) {
+          i64 J = ii + nx * (jj + ny * kk);
+          if (J == I || done[J]) continue;
+          double c = cand3d(X, Y, Z, U, dist[I], J, I);
+          if (c < dist[J]) {
+            dist[J] = c;
+            pq.push({c, J});
+          }
+        }
+  }
+  return 0;
+}
+
+int ora_num_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"
