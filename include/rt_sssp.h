@@ -1,0 +1,140 @@
+/* rt_sssp.h -- C ABI of librt_sssp.so: the B200-native (sm_100a) drop-in for the shortest-path-method hot
+ * path of albert-de-montserrat/RayTracer.jl.
+ *
+ * The reference has no FFI boundary of its own (it is pure Julia); the boundary replaced here is the set of
+ * exported Julia functions of src/RayTracer.jl:24-34.  Each entry point below names the reference function
+ * whose work it takes over.  julia/RayTracerB200.jl binds these with `ccall`; the Python package
+ * raytracer.jl_b200 binds them with ctypes.
+ *
+ * Conventions
+ *  - every node / element id crossing the ABI is a 1-based int64 exactly as in Julia; 0 in a `prev` table means
+ *    "never set" (the reference leaves those entries undefined, src/SSSP/bfm.jl:12);
+ *  - all pointers are HOST pointers unless the function name ends in `_dev`; outputs go into caller-allocated
+ *    buffers whose capacity is passed explicitly; the library never frees caller memory;
+ *  - every function returns an int status (RT_OK == 0); rt_last_error() returns a thread-local message;
+ *    nothing throws across the boundary;
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point returns RT_ERR_CUDA.
+ */
+#ifndef RT_SSSP_H
+#define RT_SSSP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_OK 0
+#define RT_ERR_ARG 1      /* invalid argument (bad id, null pointer, capacity too small) */
+#define RT_ERR_CUDA 2     /* CUDA runtime / no device */
+#define RT_ERR_RANGE 3    /* interpolation point outside the knots (BoundsError in the reference) */
+#define RT_ERR_NOPATH 4   /* recontruct_path would not terminate (receiver unreachable / cycle) */
+#define RT_ERR_UNSUPPORTED 5
+
+typedef struct rt_mesh rt_mesh; /* opaque: a graph resident in HBM (2-D annulus mesh or 3-D structured grid) */
+
+/* Counters of one rt_bfm_solve call (summed over its sources).  Replaces the reference's only log line,
+ * println("Converged in $it iterations") src/SSSP/bfm.jl:49 (it == sweeps + 1 there). */
+typedef struct rt_stats {
+  int64_t sweeps;          /* relaxation sweeps executed                                                    */
+  int64_t relaxed_edges;   /* E_relaxed: candidate (edge) evaluations executed by the relax kernels         */
+  int64_t vertex_updates;  /* active-vertex updates (vertices relaxed, summed over sweeps)                   */
+  int64_t graph_edges;     /* E_graph: sum over vertices of |scan list| (reference multiplicities, per source)*/
+  double kernel_ms;        /* device time of the solve loop(s), CUDA events on the solver stream            */
+  double relax_ms;         /* device time of the relax kernel alone (0 unless profiling timers are enabled)  */
+  int64_t relax_launches;  /* launches of the relax kernel                                                  */
+  int64_t total_launches;  /* all kernel launches issued by the solve(s)                                    */
+} rt_stats;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+const char* rt_last_error(void);
+const char* rt_version(void);
+int rt_device_count(int* count);
+int rt_set_device(int device); /* call before building meshes on this host thread */
+
+/* ---- 2-D annulus: init_annulus(ntheta, nr; spacing) src/GridAnnulus.jl:57-70 ---------------------------- */
+/* Runs primary_grid :72-142, secondary_nodes :607-698, constrain2layers! :296-321,
+ * discontinuous_boundaries :910-968 and element_incidence :420-452; the mesh stays resident on the device. */
+int rt_annulus_build(int64_t ntheta, int64_t nr, double spacing, rt_mesh** out);
+
+/* sizes[8] = { n, nel, sum|e2n|, nnz(G), halo_rows (2H), sum|neighbours|, ntheta, nr(+7) }.
+ * For a 3-D grid: { n, 0, 0, 0, 0, 0, 0, 0 }. */
+int rt_mesh_sizes(const rt_mesh* m, int64_t sizes[8]);
+
+/* Materialise Grid2D / SparseMatrixCSC{Bool,Int64} / halo::Matrix{Int64} for Julia (any pointer may be NULL).
+ * e2n_off has nel+1 0-based offsets into e2n_idx; G_colptr is the 1-based Julia colptr (n+1); halo is the
+ * (2H x 2) matrix in column-major order. */
+int rt_mesh_export(const rt_mesh* m, double* x, double* z, double* theta, double* r, int64_t* e2n_off,
+                   int64_t* e2n_idx, int64_t* G_colptr, int64_t* G_rowval, int64_t* halo, int64_t* nbr_off,
+                   int64_t* nbr_idx, int8_t* el_type);
+
+/* Adopt a graph that was built elsewhere (by the reference in Julia, or by a test):  the arrays that
+ * bfm(G, halo, source, gr, U) reads -- G.colptr/G.rowval, gr.e2n (flattened), gr.x, gr.z, halo.
+ * theta / r may be NULL (only needed by rt_mesh_export and rt_closest_point). */
+int rt_mesh_from_arrays(int64_t n, int64_t nel, const int64_t* e2n_off, const int64_t* e2n_idx,
+                        const int64_t* G_colptr, const int64_t* G_rowval, const int64_t* halo, int64_t halo_rows,
+                        const double* x, const double* z, const double* theta, const double* r, rt_mesh** out);
+
+/* ---- 3-D structured grid: grid(c0,c1,nnods) src/StructuredGrid.jl:35-45 + nodal_incidence :177-223 ------- */
+/* coord_system 0: Cartesian axes; 1: axes are (theta, phi, r) mapped through spherical2cart :225-235.
+ * star_levels = neighbour_levels (0: 26-neighbourhood; L>=1: clipped (2L+3)^3 window incl. self).
+ * Edge weight = distance3D(p1,p2) * (1/abs(U1+U2)) * 2  (src/SSSP/weights.jl:20). */
+int rt_grid3d_build(const double c0[3], const double c1[3], const int64_t nn[3], int star_levels,
+                    int coord_system, rt_mesh** out);
+int rt_grid3d_export(const rt_mesh* m, double* X, double* Y, double* Z); /* Cartesian node coordinates */
+
+int rt_mesh_free(rt_mesh* m);
+
+/* ---- velocity: interpolate_velocity(r, interpolant) src/utils.jl:38-44 ----------------------------------- */
+/* Gridded linear interpolation on (knots_r, knots_v), knots ascending.  buffer < 0: utils.jl semantics;
+ * buffer >= 0: src/ShortestPath.jl:74-90 (points exactly on a discontinuity radius are evaluated at r+buffer). */
+int rt_interp_velocity(const double* knots_r, const double* knots_v, int64_t nk, const double* r, int64_t n,
+                       double buffer, double* out);
+
+/* Same, r_dev / out_dev are DEVICE pointers (knots stay on the host: they are 6372 entries). */
+int rt_interp_velocity_dev(const double* knots_r, const double* knots_v, int64_t nk, const double* r_dev,
+                           int64_t n, double buffer, double* out_dev);
+
+/* Device pointers to the node coordinates of a resident mesh: 2-D -> (x, z, theta, r) i.e. gr.x, gr.z, gr.theta,
+ * gr.r (theta / r NULL if the mesh was adopted without them); 3-D -> (X, Y, Z, NULL). */
+int rt_mesh_coords_dev(const rt_mesh* m, const double** a, const double** b, const double** c, const double** d);
+
+/* ---- closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 ---------------------------------------- */
+/* system 0 = :cartesian (x,z), 1 = :polar ((theta, r) treated as Cartesian).  First index of the minimum. */
+int rt_closest_point(const rt_mesh* m, const double* pa, const double* pb, int64_t npts, int system,
+                     int64_t* index_out);
+
+/* ---- solver: bfm(G, halo, source, gr, U) src/SSSP/bfm.jl:1-52 -------------------------------------------- */
+/* Solves nsrc independent single-source problems on the same mesh and velocity.  dist_out / prev_out are
+ * [nsrc x n] row-major (source-major) host buffers == BellmanFordMoore(prev, dist) per source
+ * (src/SSSP/ssspm.jl:3-10).  Either output may be NULL.  precision: 64 (reference semantics; only this is
+ * implemented).  stats may be NULL. */
+int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t nsrc, int precision,
+                 double* dist_out, int64_t* prev_out, rt_stats* stats);
+
+/* Device-resident variant: U_dev [n] doubles and dist_dev [nsrc x n] doubles / prev_dev [nsrc x n] int32
+ * (0-based, -1 = never set) are DEVICE pointers on the mesh's device.  Used by benchmarks and by sharded
+ * multi-GPU drivers that gather tables with NCCL. */
+int rt_bfm_solve_dev(rt_mesh* m, const double* U_dev, const int64_t* sources, int64_t nsrc, int precision,
+                     double* dist_dev, int32_t* prev_dev, rt_stats* stats);
+
+/* Solver options: key/value, e.g. ("schedule", 0 = Jacobi sweeps exactly as the reference (default),
+ * 1 = work-efficient near-far ordering; dist identical, prev may differ on exact ties),
+ * ("profile_timers", 1) to fill rt_stats.relax_ms. */
+int rt_set_option(rt_mesh* m, const char* key, double value);
+
+/* ---- paths: recontruct_path(prev, source, receiver) src/SSSP/ssspm.jl:30-40 ------------------------------- */
+/* Two-call pattern: with path_idx == NULL only path_off[nrec+1] (0-based offsets) is written.  Each path is
+ * [receiver, ..., source].  Returns RT_ERR_NOPATH if a chase does not reach `source` within n steps. */
+int rt_reconstruct_paths(const int64_t* prev, int64_t n, int64_t source, const int64_t* receivers, int64_t nrec,
+                         int64_t* path_off, int64_t* path_idx, int64_t cap);
+
+/* Same with the predecessor table resident on the device (int32, 0-based, -1 = never set) as written by
+ * rt_bfm_solve_dev; receivers / outputs are host arrays with 1-based ids. */
+int rt_reconstruct_paths_dev(const int32_t* prev_dev, int64_t n, int64_t source, const int64_t* receivers,
+                             int64_t nrec, int64_t* path_off, int64_t* path_idx, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_SSSP_H */

@@ -1,0 +1,289 @@
+"""Host-side mirror of the reference's exported interface (src/RayTracer.jl:24-34) on top of the C ABI.
+
+Julia is not installed in the build/bench image, so this Python layer plays the part of julia/RayTracerB200.jl
+(which binds the same entry points with `ccall`): same function names, argument meaning, 1-based ids and error
+behaviour, so that tests read like the README example of the reference (README.md:15-53):
+
+    gr, G, halo = init_annulus(ntheta, nr, spacing=1)
+    source      = closest_point(gr, 0.0, R, system="polar")
+    profile     = velocity_profile()
+    Vp          = interpolate_velocity(gr.r, LinearInterpolation(profile.r, profile.Vp))
+    D           = bfm(G, halo, source, gr, Vp)          # D.dist, D.prev
+    path        = recontruct_path(D.prev, source, receiver)
+
+All computation happens in librt_sssp.so on the GPU; there is no CPU path here.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import RtError, RtStats, check, lib, ptr
+
+R = 6371.0  # src/utils.jl:2
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+# ------------------------------------------------------------------------------------------------ handles
+class _Handle:
+    """Owns an rt_mesh*."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().rt_mesh_free(self.h)
+        except Exception:
+            pass
+        self.h = None
+
+    def sizes(self):
+        s = np.zeros(8, np.int64)
+        check(lib().rt_mesh_sizes(self.h, s))
+        return s
+
+    def set_option(self, key, value):
+        check(lib().rt_set_option(self.h, key.encode(), float(value)))
+
+    def coords_dev(self):
+        p = [C.c_void_p() for _ in range(4)]
+        check(lib().rt_mesh_coords_dev(self.h, *[C.byref(q) for q in p]))
+        return [q.value for q in p]
+
+
+class SparseMatrixCSC:
+    """G::SparseMatrixCSC{Bool,Int64} (nel x n): colptr / rowval exactly as Julia stores them (1-based)."""
+
+    def __init__(self, m, n, colptr, rowval):
+        self.m, self.n, self.colptr, self.rowval = int(m), int(n), colptr, rowval
+
+    @property
+    def nnz(self):
+        return len(self.rowval)
+
+
+class Grid2D:
+    """Grid2D of src/GridAnnulus.jl:9-21.  e2n is kept flattened (e2n_off 0-based offsets, e2n_idx 1-based ids);
+    `gr.e2n[el]` (el 1-based) returns the node list of an element like the reference Dict."""
+
+    def __init__(self, x, z, theta, r, e2n_off, e2n_idx, ntheta, nr, nel, nnods, nbr_off=None, nbr_idx=None,
+                 element_type=None, handle=None):
+        self.x, self.z, self.theta, self.r = x, z, theta, r
+        self.e2n_off, self.e2n_idx = e2n_off, e2n_idx
+        self.ntheta, self.nr, self.nel, self.nnods = int(ntheta), int(nr), int(nel), int(nnods)
+        self.nbr_off, self.nbr_idx, self.element_type = nbr_off, nbr_idx, element_type
+        self._handle = handle
+        self._handle_key = None
+
+    def __len__(self):
+        return self.nnods
+
+    class _E2N:
+        def __init__(self, g):
+            self.g = g
+
+        def __getitem__(self, el):
+            return self.g.e2n_idx[self.g.e2n_off[el - 1]:self.g.e2n_off[el]]
+
+    @property
+    def e2n(self):
+        return Grid2D._E2N(self)
+
+    def neighbours(self, el):
+        return self.nbr_idx[self.nbr_off[el - 1]:self.nbr_off[el]]
+
+
+class BellmanFordMoore:
+    """BellmanFordMoore(prev, dist) of src/SSSP/ssspm.jl:3-10.  prev: int64 1-based (0 = never set)."""
+
+    def __init__(self, prev, dist, stats=None):
+        self.prev, self.dist, self.stats = prev, dist, stats
+
+
+class VelProfile:
+    def __init__(self, r, Vp, Vs):
+        self.r, self.Vp, self.Vs = r, Vp, Vs
+
+
+class LinearInterpolation:
+    """Stand-in for Interpolations.LinearInterpolation(knots, values) (README.md:32): holds the knots; evaluation
+    happens on the device in interpolate_velocity."""
+
+    def __init__(self, knots, values):
+        self.knots = np.ascontiguousarray(knots, np.float64)
+        self.values = np.ascontiguousarray(values, np.float64)
+        if self.knots.shape != self.values.shape or self.knots.ndim != 1 or len(self.knots) < 2:
+            raise ValueError("knots and values must be 1-D arrays of equal length >= 2")
+
+
+# ----------------------------------------------------------------------------------------------- builders
+def init_annulus(ntheta, nr, spacing=20, export=True):
+    """gr, G, halo = init_annulus(ntheta, nr; spacing) -- src/GridAnnulus.jl:57-70, built on the device.
+    With export=False the host arrays are not materialised (gr only carries the device handle and sizes)."""
+    h = C.c_void_p()
+    check(lib().rt_annulus_build(int(ntheta), int(nr), float(spacing), C.byref(h)))
+    handle = _Handle(h)
+    n, nel, se, nnz, hr, sn, nth, nrr = (int(v) for v in handle.sizes())
+    if not export:
+        gr = Grid2D(None, None, None, None, None, None, nth, nrr, nel, n, handle=handle)
+        return gr, SparseMatrixCSC(nel, n, None, None), None
+    x, z, th, r = (np.zeros(n) for _ in range(4))
+    e2n_off = np.zeros(nel + 1, np.int64)
+    e2n_idx = np.zeros(se, np.int64)
+    colptr = np.zeros(n + 1, np.int64)
+    rowval = np.zeros(nnz, np.int64)
+    halo = np.zeros(2 * hr, np.int64)
+    nbr_off = np.zeros(nel + 1, np.int64)
+    nbr_idx = np.zeros(sn, np.int64)
+    el_type = np.zeros(nel, np.int8)
+    check(lib().rt_mesh_export(h, ptr(x), ptr(z), ptr(th), ptr(r), ptr(e2n_off), ptr(e2n_idx), ptr(colptr),
+                               ptr(rowval), ptr(halo), ptr(nbr_off), ptr(nbr_idx), ptr(el_type)))
+    gr = Grid2D(x, z, th, r, e2n_off, e2n_idx, nth, nrr, nel, n, nbr_off, nbr_idx, el_type, handle=handle)
+    G = SparseMatrixCSC(nel, n, colptr, rowval)
+    return gr, G, halo.reshape(2, hr).T.copy()  # (2H, 2) like Matrix{Int64}
+
+
+def mesh_from_arrays(gr, G, halo):
+    """Adopt arrays built elsewhere (by the reference, or by a test) -> device handle (cached on gr)."""
+    key = (id(G.colptr), id(G.rowval), id(halo) if halo is not None else 0)
+    if gr._handle is not None and (gr._handle_key is None or gr._handle_key == key):
+        return gr._handle
+    n, nel = int(G.n), int(gr.nel)
+    if halo is None or len(halo) == 0:
+        halo_cm, hr = None, 0
+    else:
+        halo = np.asarray(halo, np.int64)
+        hr = halo.shape[0]
+        halo_cm = np.ascontiguousarray(halo.T).reshape(-1)  # column-major (2H x 2)
+    h = C.c_void_p()
+    c = lambda a, t: np.ascontiguousarray(a, t)
+    th = None if gr.theta is None else c(gr.theta, np.float64)
+    rr = None if gr.r is None else c(gr.r, np.float64)
+    check(lib().rt_mesh_from_arrays(n, nel, c(gr.e2n_off, np.int64), c(gr.e2n_idx, np.int64),
+                                    c(G.colptr, np.int64), c(G.rowval, np.int64), ptr(halo_cm), hr,
+                                    c(gr.x, np.float64), c(gr.z, np.float64), ptr(th), ptr(rr), C.byref(h)))
+    gr._handle = _Handle(h)
+    gr._handle_key = key
+    return gr._handle
+
+
+class Grid3D:
+    """grid(c0, c1, nnods) of src/StructuredGrid.jl:35-45 with its star-L adjacency (nodal_incidence :177-223)
+    kept implicit on the device."""
+
+    def __init__(self, c0, c1, nnods, neighbour_levels=1, coord_system="cartesian"):
+        self.c0 = np.asarray(c0, np.float64).copy()
+        self.c1 = np.asarray(c1, np.float64).copy()
+        self.nnods = tuple(int(v) for v in nnods)
+        self.n = int(np.prod(self.nnods))
+        self.neighbour_levels = int(neighbour_levels)
+        self.coord_system = coord_system
+        h = C.c_void_p()
+        cs = {"cartesian": 0, "spherical": 1}[coord_system]
+        check(lib().rt_grid3d_build(self.c0, self.c1, np.asarray(self.nnods, np.int64), self.neighbour_levels, cs,
+                                    C.byref(h)))
+        self._handle = _Handle(h)
+
+    def coordinates(self):
+        """Cartesian node coordinates (x fastest), i.e. spherical2cart(gr) for spherical grids."""
+        X, Y, Z = np.zeros(self.n), np.zeros(self.n), np.zeros(self.n)
+        check(lib().rt_grid3d_export(self._handle.h, X, Y, Z))
+        return X, Y, Z
+
+
+def grid(c0, c1, nnods, neighbour_levels=1, coord_system="cartesian"):
+    return Grid3D(c0, c1, nnods, neighbour_levels, coord_system)
+
+
+# ----------------------------------------------------------------------------------------------- velocity
+def velocity_profile():
+    """velocity_profile() of src/utils.jl:23-30 (AK135; the reference's IASP91 file is byte-identical).
+    The table is shipped as data/ak135_profile.npz (made by tools/make_ak135_fixture.py)."""
+    d = np.load(os.path.join(_DATA, "ak135_profile.npz"))
+    depth = d["depth_km"]
+    r = depth.max() - depth
+    return VelProfile(r[::-1].copy(), d["vp"][::-1].copy(), d["vs"][::-1].copy())
+
+
+def interpolate_velocity(r, interpolant, buffer=None):
+    """interpolate_velocity(r, interpolant) src/utils.jl:38-44; with `buffer` the variant of
+    src/ShortestPath.jl:74-90.  Raises (like the reference's BoundsError) if a point is outside the knots."""
+    r = np.ascontiguousarray(r, np.float64)
+    out = np.empty_like(r)
+    check(lib().rt_interp_velocity(interpolant.knots, interpolant.values, len(interpolant.knots), r.reshape(-1),
+                                   r.size, -1.0 if buffer is None else float(buffer), out.reshape(-1)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ closest_point
+def closest_point(gr, px, pz, system="cartesian"):
+    """closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 -> 1-based node id (scalar or array)."""
+    handle = gr._handle
+    if handle is None:
+        raise ValueError("grid has no device handle; call mesh_from_arrays(gr, G, halo) or bfm(...) first")
+    pa = np.atleast_1d(np.asarray(px, np.float64)).copy()
+    pb = np.atleast_1d(np.asarray(pz, np.float64)).copy()
+    pa, pb = np.broadcast_arrays(pa, pb)
+    pa, pb = np.ascontiguousarray(pa), np.ascontiguousarray(pb)
+    out = np.zeros(len(pa), np.int64)
+    sysid = {"cartesian": 0, "polar": 1}[system]
+    check(lib().rt_closest_point(handle.h, pa, pb, len(pa), sysid, out))
+    return int(out[0]) if np.ndim(px) == 0 and np.ndim(pz) == 0 else out
+
+
+# ------------------------------------------------------------------------------------------------- solver
+def _solve(handle, n, U, sources, want_prev=True):
+    U = np.ascontiguousarray(U, np.float64)
+    if U.shape != (n,):
+        raise ValueError("U must have one entry per node (%d), got %s" % (n, U.shape))
+    src = np.atleast_1d(np.asarray(sources, np.int64)).copy()
+    dist = np.empty((len(src), n), np.float64)
+    prev = np.empty((len(src), n), np.int64) if want_prev else None
+    st = RtStats()
+    check(lib().rt_bfm_solve(handle.h, U, src, len(src), 64, ptr(dist), ptr(prev), C.byref(st)))
+    return dist, prev, st.as_dict()
+
+
+def bfm(G, halo, source, gr, U):
+    """D = bfm(G, halo, source, gr, U) -- src/SSSP/bfm.jl:1-52.  `source` may be an array of sources, in which
+    case D.dist / D.prev are [nsrc x n] tables (the batch API); a scalar gives vectors as in the reference."""
+    handle = mesh_from_arrays(gr, G, halo)
+    dist, prev, st = _solve(handle, int(G.n), U, source)
+    if np.ndim(source) == 0:
+        return BellmanFordMoore(prev[0], dist[0], st)
+    return BellmanFordMoore(prev, dist, st)
+
+
+def bfm3d(gr3, source, U):
+    """BFM(G, source, gr, U, fw) of src/Dijsktra.jl:294-343 on the implicit star-L graph of a Grid3D with the
+    edge weight of src/SSSP/weights.jl:20."""
+    dist, prev, st = _solve(gr3._handle, gr3.n, U, source)
+    if np.ndim(source) == 0:
+        return BellmanFordMoore(prev[0], dist[0], st)
+    return BellmanFordMoore(prev, dist, st)
+
+
+# -------------------------------------------------------------------------------------------------- paths
+def recontruct_path(prev, source, receiver):
+    """recontruct_path(prev::Vector, source, receiver) src/SSSP/ssspm.jl:30-40 -> [receiver, ..., source].
+    (The misspelling is the reference's API.)  `receiver` may be an array -> list of paths."""
+    if isinstance(prev, BellmanFordMoore):
+        prev = prev.prev
+    prev = np.ascontiguousarray(prev, np.int64)
+    rec = np.atleast_1d(np.asarray(receiver, np.int64)).copy()
+    off = np.zeros(len(rec) + 1, np.int64)
+    check(lib().rt_reconstruct_paths(prev, len(prev), int(source), rec, len(rec), off, None, 0))
+    idx = np.zeros(int(off[-1]), np.int64)
+    check(lib().rt_reconstruct_paths(prev, len(prev), int(source), rec, len(rec), off, ptr(idx), len(idx)))
+    paths = [idx[off[k]:off[k + 1]].copy() for k in range(len(rec))]
+    return paths[0] if np.ndim(receiver) == 0 else paths
+
+
+def device_count():
+    c = C.c_int(0)
+    check(lib().rt_device_count(C.byref(c)))
+    return c.value

@@ -1,0 +1,244 @@
+// api.cu -- the extern "C" surface declared in include/rt_sssp.h: handle management, argument checks and
+// host <-> device staging around the kernels.  No compute happens on the host.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* receivers, i64 nrec, i64* path_off,
+                             i64* path_idx, i64 cap);
+int prev_host_to_device_i32(const i64* prev, i64 n, DevBuf<i32>& out);
+
+static thread_local char g_err[512] = "";
+
+void rt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int make_handle(rt_mesh** out) {
+  RT_ARG(out, "null output handle");
+  *out = nullptr;
+  int dev = 0;
+  RT_CUDA(cudaGetDevice(&dev));
+  rt_mesh* h = new rt_mesh();
+  h->device = dev;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    rt_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    return RT_ERR_CUDA;
+  }
+  *out = h;
+  return RT_OK;
+}
+
+static i64 mesh_n(const rt_mesh* m) {
+  i64 n = 0;
+  if (m->kind == 3) grid3d_n(m, &n);
+  if (m->kind == 2) {
+    i64 s[8];
+    mesh2d_sizes(m, s);
+    n = s[0];
+  }
+  return n;
+}
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_err; }
+const char* rt_version(void) { return "rt_sssp 0.1 (sm_100a)"; }
+
+int rt_device_count(int* count) {
+  RT_ARG(count, "null count");
+  *count = 0;
+  RT_CUDA(cudaGetDeviceCount(count));
+  return RT_OK;
+}
+
+int rt_set_device(int device) {
+  RT_CUDA(cudaSetDevice(device));
+  return RT_OK;
+}
+
+int rt_annulus_build(int64_t ntheta, int64_t nr, double spacing, rt_mesh** out) {
+  RT_ARG(ntheta >= 3 && nr >= 2 && spacing > 0.0, "init_annulus needs ntheta >= 3, nr >= 2, spacing > 0");
+  RT_TRY(make_handle(out));
+  int rc = annulus_build_device(*out, ntheta, nr, spacing);
+  if (rc != RT_OK) {
+    rt_mesh_free(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int rt_mesh_sizes(const rt_mesh* m, int64_t sizes[8]) {
+  RT_ARG(m && sizes, "null argument");
+  if (m->kind == 2) return mesh2d_sizes(m, sizes);
+  std::memset(sizes, 0, 8 * sizeof(int64_t));
+  sizes[0] = mesh_n(m);
+  return RT_OK;
+}
+
+int rt_mesh_export(const rt_mesh* m, double* x, double* z, double* theta, double* r, int64_t* e2n_off,
+                   int64_t* e2n_idx, int64_t* G_colptr, int64_t* G_rowval, int64_t* halo, int64_t* nbr_off,
+                   int64_t* nbr_idx, int8_t* el_type) {
+  RT_ARG(m && m->kind == 2, "rt_mesh_export needs a 2-D mesh");
+  RT_CUDA(cudaSetDevice(m->device));
+  return mesh2d_export(m, x, z, theta, r, e2n_off, e2n_idx, G_colptr, G_rowval, halo, nbr_off, nbr_idx, el_type);
+}
+
+int rt_mesh_from_arrays(int64_t n, int64_t nel, const int64_t* e2n_off, const int64_t* e2n_idx,
+                        const int64_t* G_colptr, const int64_t* G_rowval, const int64_t* halo, int64_t halo_rows,
+                        const double* x, const double* z, const double* theta, const double* r, rt_mesh** out) {
+  RT_TRY(make_handle(out));
+  int rc = mesh2d_from_host(*out, n, nel, e2n_off, e2n_idx, G_colptr, G_rowval, halo, halo_rows, x, z, theta, r);
+  if (rc != RT_OK) {
+    rt_mesh_free(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int rt_grid3d_build(const double c0[3], const double c1[3], const int64_t nn[3], int star_levels,
+                    int coord_system, rt_mesh** out) {
+  RT_TRY(make_handle(out));
+  int rc = grid3d_build(*out, c0, c1, nn, star_levels, coord_system);
+  if (rc != RT_OK) {
+    rt_mesh_free(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+int rt_grid3d_export(const rt_mesh* m, double* X, double* Y, double* Z) {
+  RT_ARG(m && m->kind == 3, "rt_grid3d_export needs a 3-D grid");
+  RT_CUDA(cudaSetDevice(m->device));
+  return grid3d_export(m, X, Y, Z);
+}
+
+int rt_mesh_free(rt_mesh* m) {
+  if (!m) return RT_OK;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  mesh2d_free(m);
+  grid3d_free(m);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return RT_OK;
+}
+
+int rt_interp_velocity(const double* knots_r, const double* knots_v, int64_t nk, const double* r, int64_t n,
+                       double buffer, double* out) {
+  RT_ARG(knots_r && knots_v && r && out && n >= 0 && nk >= 2, "bad interpolation arguments");
+  DevBuf<double> dr, dout;
+  RT_TRY(dr.upload(r, n));
+  RT_TRY(dout.alloc(n));
+  RT_TRY(interp_velocity_device(knots_r, knots_v, nk, dr.p, n, buffer, dout.p));
+  if (n) RT_CUDA(cudaMemcpy(out, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+int rt_interp_velocity_dev(const double* knots_r, const double* knots_v, int64_t nk, const double* r_dev,
+                           int64_t n, double buffer, double* out_dev) {
+  return interp_velocity_device(knots_r, knots_v, nk, r_dev, n, buffer, out_dev);
+}
+
+int rt_mesh_coords_dev(const rt_mesh* m, const double** a, const double** b, const double** c, const double** d) {
+  RT_ARG(m && a && b && c && d, "null argument");
+  if (m->kind == 2) return mesh2d_coords(m, a, b, c, d);
+  if (m->kind == 3) return grid3d_coords(m, a, b, c, d);
+  rt_set_error("mesh handle is empty");
+  return RT_ERR_ARG;
+}
+
+int rt_closest_point(const rt_mesh* m, const double* pa, const double* pb, int64_t npts, int system,
+                     int64_t* index_out) {
+  RT_ARG(m && m->kind == 2, "rt_closest_point needs a 2-D mesh");
+  RT_ARG(system == 0 || system == 1, "system must be 0 (:cartesian) or 1 (:polar)");
+  RT_CUDA(cudaSetDevice(m->device));
+  return mesh2d_closest(m, pa, pb, npts, system, index_out);
+}
+
+int rt_bfm_solve_dev(rt_mesh* m, const double* U_dev, const int64_t* sources, int64_t nsrc, int precision,
+                     double* dist_dev, int32_t* prev_dev, rt_stats* stats) {
+  RT_ARG(m && U_dev && sources && nsrc >= 0, "null argument");
+  if (precision != 64) {
+    rt_set_error("precision %d not implemented (only 64 = reference semantics)", precision);
+    return RT_ERR_UNSUPPORTED;
+  }
+  RT_CUDA(cudaSetDevice(m->device));
+  if (m->kind == 2) return bfm2d_solve(m, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
+  if (m->kind == 3) return bfm3d_solve(m, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
+  rt_set_error("mesh handle is empty");
+  return RT_ERR_ARG;
+}
+
+int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t nsrc, int precision,
+                 double* dist_out, int64_t* prev_out, rt_stats* stats) {
+  RT_ARG(m && U && sources && nsrc >= 0, "null argument");
+  RT_CUDA(cudaSetDevice(m->device));
+  const i64 n = mesh_n(m);
+  DevBuf<double> dU, dd;
+  DevBuf<i32> dp;
+  RT_TRY(dU.upload(U, n));
+  RT_CUDA(cudaDeviceSynchronize());
+  rt_stats total = {};
+  // one source at a time keeps the staging buffers at n entries regardless of the batch size
+  if (dist_out) RT_TRY(dd.alloc(n));
+  if (prev_out) RT_TRY(dp.alloc(n));
+  for (i64 s = 0; s < nsrc; ++s) {
+    rt_stats st = {};
+    RT_TRY(rt_bfm_solve_dev(m, dU.p, sources + s, 1, precision, dist_out ? dd.p : nullptr,
+                            prev_out ? dp.p : nullptr, &st));
+    if (dist_out) RT_CUDA(cudaMemcpy(dist_out + s * n, dd.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (prev_out) RT_TRY(prev_to_host_i64(dp.p, n, prev_out + s * n, m->stream));
+    total.sweeps += st.sweeps;
+    total.relaxed_edges += st.relaxed_edges;
+    total.vertex_updates += st.vertex_updates;
+    total.graph_edges = st.graph_edges;
+    total.kernel_ms += st.kernel_ms;
+    total.relax_ms += st.relax_ms;
+    total.relax_launches += st.relax_launches;
+    total.total_launches += st.total_launches;
+  }
+  if (stats) *stats = total;
+  return RT_OK;
+}
+
+int rt_set_option(rt_mesh* m, const char* key, double value) {
+  RT_ARG(m && key, "null argument");
+  if (!std::strcmp(key, "schedule")) {
+    RT_ARG(value == 0.0 || value == 1.0, "schedule must be 0 (jacobi) or 1 (near-far)");
+    m->opts.schedule = (int)value;
+  } else if (!std::strcmp(key, "profile_timers")) {
+    m->opts.profile_timers = value != 0.0;
+  } else if (!std::strcmp(key, "check_every")) {
+    RT_ARG(value >= 1.0 && value <= 1024.0, "check_every must be in 1..1024");
+    m->opts.check_every = (int)value;
+  } else if (!std::strcmp(key, "delta")) {
+    RT_ARG(value >= 0.0, "delta must be >= 0");
+    m->opts.delta = value;
+  } else {
+    rt_set_error("unknown option '%s'", key);
+    return RT_ERR_ARG;
+  }
+  return RT_OK;
+}
+
+int rt_reconstruct_paths(const int64_t* prev, int64_t n, int64_t source, const int64_t* receivers, int64_t nrec,
+                         int64_t* path_off, int64_t* path_idx, int64_t cap) {
+  RT_ARG(prev && n > 0, "null prev table");
+  DevBuf<i32> dprev;
+  RT_TRY(prev_host_to_device_i32(prev, n, dprev));
+  return reconstruct_paths_device(dprev.p, n, source, receivers, nrec, path_off, path_idx, cap);
+}
+
+int rt_reconstruct_paths_dev(const int32_t* prev_dev, int64_t n, int64_t source, const int64_t* receivers,
+                             int64_t nrec, int64_t* path_off, int64_t* path_idx, int64_t cap) {
+  return reconstruct_paths_device(prev_dev, n, source, receivers, nrec, path_off, path_idx, cap);
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// common.cuh -- shared plumbing of librt_sssp.so (error strings, RAII device buffers, the rt_mesh handle).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "rt_sssp.h"
+
+typedef int64_t i64;
+typedef int32_t i32;
+typedef unsigned long long u64;
+
+void rt_set_error(const char* fmt, ...);
+
+#define RT_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      rt_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, __LINE__, #call); \
+      return RT_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+#define RT_TRY(call)          \
+  do {                        \
+    int _s = (call);          \
+    if (_s != RT_OK) return _s; \
+  } while (0)
+
+#define RT_ARG(cond, msg)              \
+  do {                                 \
+    if (!(cond)) {                     \
+      rt_set_error("bad argument: %s", msg); \
+      return RT_ERR_ARG;               \
+    }                                  \
+  } while (0)
+
+// Owning device buffer.  alloc() returns a status instead of throwing.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      n = 0;
+      rt_set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      return RT_ERR_CUDA;
+    }
+    return RT_OK;
+  }
+  int upload(const T* host, size_t count, cudaStream_t s = 0) {
+    RT_TRY(alloc(count));
+    if (count) RT_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return RT_OK;
+  }
+  int zero(cudaStream_t s = 0) {
+    if (n) RT_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    return RT_OK;
+  }
+};
+
+inline unsigned grid_for(i64 work, int block) { return (unsigned)((work + block - 1) / block); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Solver options / workspace shared by the 2-D and 3-D solvers
+struct SolverOpts {
+  int schedule = 0;        // 0 = Jacobi sweeps (reference schedule), 1 = near-far work-efficient
+  int profile_timers = 0;  // 1: time the relax kernel with its own events (adds syncs)
+  int check_every = 1;     // sweeps between host convergence checks
+  double delta = 0.0;      // near-far bucket width [s]; 0 = automatic
+};
+
+struct Mesh2D;
+struct Grid3D;
+
+struct rt_mesh {
+  int kind = 0;  // 2 = two-level annulus graph, 3 = 3-D structured grid
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  SolverOpts opts;
+  Mesh2D* m2 = nullptr;
+  Grid3D* g3 = nullptr;
+};
+
+// 2-D (mesh2d.cu / bfm2d.cu)
+int mesh2d_from_host(rt_mesh* h, i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr,
+                     const i64* rowval, const i64* halo, i64 halo_rows, const double* x, const double* z,
+                     const double* theta, const double* r);
+int mesh2d_sizes(const rt_mesh* h, i64 sizes[8]);
+int mesh2d_export(const rt_mesh* h, double* x, double* z, double* theta, double* r, i64* e2n_off, i64* e2n_idx,
+                  i64* colptr, i64* rowval, i64* halo, i64* nbr_off, i64* nbr_idx, int8_t* el_type);
+void mesh2d_free(rt_mesh* h);
+int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                rt_stats* stats);
+int mesh2d_closest(const rt_mesh* h, const double* pa, const double* pb, i64 npts, int system, i64* out);
+int annulus_build_device(rt_mesh* h, i64 ntheta, i64 nr, double spacing);
+int mesh2d_coords(const rt_mesh* h, const double** x, const double** z, const double** theta, const double** r);
+int grid3d_coords(const rt_mesh* h, const double** X, const double** Y, const double** Z, const double** none);
+
+// 3-D (grid3d.cu)
+int grid3d_build(rt_mesh* h, const double c0[3], const double c1[3], const i64 nn[3], int star_levels,
+                 int coord_system);
+int grid3d_export(const rt_mesh* h, double* X, double* Y, double* Z);
+void grid3d_free(rt_mesh* h);
+int grid3d_n(const rt_mesh* h, i64* n);
+int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                rt_stats* stats);
+
+// misc.cu
+int interp_velocity_device(const double* kr, const double* kv, i64 nk, const double* r, i64 n, double buffer,
+                           double* out);
+int closest_point_device(const double* a_dev, const double* b_dev, i64 n, const double* pa, const double* pb,
+                         i64 npts, i64* out, cudaStream_t s);
+int prev_to_host_i64(const i32* prev_dev, i64 count, i64* out, cudaStream_t s);

@@ -1,0 +1,445 @@
+// grid3d.cu -- 3-D structured grid: coordinates, implicit star-L adjacency and the BFM relaxation (sm_100a).
+//
+// Takes over grid(c0,c1,nnods) src/StructuredGrid.jl:35-45, CartesianIndex :90-96 (x fastest),
+// spherical2cart :225-235, nodal_incidence(gr; neighbour_levels) :177-223, distance3D :239-243,
+// edge_weight src/SSSP/weights.jl:20 and the control flow of BFM / foo! / goo! src/Dijsktra.jl:294-343,376-403.
+//
+// The reference materialises Dict{Int,Set{Int}} with ~125 entries per node; here the adjacency is implicit:
+// star-L of a box grid is the clipped (2L+3)^3 window (self included once L >= 1), so no adjacency arrays
+// exist at all.  A CTA owns one 8x4x4 tile of nodes, stages the tile plus its halo of (X,Y,Z,U,dist0) in
+// shared memory once, and every thread scans its window in ascending linear id (the canonical scan order:
+// the reference iterates a Julia Set whose order is not reproducible).  Frontier = active tile list.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TX = 8, TY = 4, TZ = 4;
+constexpr int TILE_THREADS = TX * TY * TZ;
+constexpr unsigned FULL = 0xffffffffu;
+
+}  // namespace
+
+struct Grid3D {
+  i64 nn[3] = {0, 0, 0};
+  i64 n = 0;
+  int star_levels = 1;
+  int w = 2;  // window half width = star_levels + 1
+  int self = 1;
+  int coord_system = 0;
+  double c0[3], c1[3];
+  DevBuf<double> X, Y, Z;
+  i64 tn[3] = {0, 0, 0};
+  i64 n_tiles = 0;
+  i64 graph_edges = 0;
+  // workspace
+  DevBuf<double> dist, dist0;
+  DevBuf<i32> prev;
+  DevBuf<uint8_t> improved;  // per tile
+  DevBuf<i32> act[2];
+  DevBuf<u64> counters;
+  u64* counters_host = nullptr;
+  bool ws_ready = false;
+};
+
+namespace {
+
+struct P3 {
+  const double* __restrict__ X;
+  const double* __restrict__ Y;
+  const double* __restrict__ Z;
+  const double* __restrict__ U;
+  double* dist;
+  double* dist0;
+  i32* prev;
+  uint8_t* improved;
+  u64* counters;
+  int nx, ny, nz;
+  int tnx, tny, tnz;
+  int w, self;
+};
+
+// Julia Base lerpi (LinRange element): t = j/d; (1-t)*a + t*b
+__device__ __forceinline__ double lerpi_dev(i64 j, i64 d, double a, double b) {
+  if (d <= 0) return a;
+  const double t = __ddiv_rn((double)j, (double)d);
+  return __dadd_rn(__dmul_rn(__dsub_rn(1.0, t), a), __dmul_rn(t, b));
+}
+
+__global__ void coords3d_kernel(double c0x, double c0y, double c0z, double c1x, double c1y, double c1z, int nx,
+                                int ny, int nz, int coord_system, double* __restrict__ X, double* __restrict__ Y,
+                                double* __restrict__ Z) {
+  const i64 I = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 n = (i64)nx * ny * nz;
+  if (I >= n) return;
+  const int i = (int)(I % nx), j = (int)((I / nx) % ny), k = (int)(I / ((i64)nx * ny));
+  const double a = lerpi_dev(i, nx - 1, c0x, c1x);
+  const double b = lerpi_dev(j, ny - 1, c0y, c1y);
+  const double c = lerpi_dev(k, nz - 1, c0z, c1z);
+  if (coord_system == 0) {
+    X[I] = a;
+    Y[I] = b;
+    Z[I] = c;
+  } else {
+    // spherical2cart(theta=a, phi=b, r=c): x = r*cos(phi)*sin(theta), y = r*sin(phi)*sin(theta), z = r*cos(theta)
+    const double st = sin(a), ct = cos(a), sp = sin(b), cp = cos(b);
+    X[I] = __dmul_rn(__dmul_rn(c, cp), st);
+    Y[I] = __dmul_rn(__dmul_rn(c, sp), st);
+    Z[I] = __dmul_rn(c, ct);
+  }
+}
+
+// dist0[J] + distance3D(pI,pJ) * (1/abs(UI+UJ)) * 2   (weights.jl:20, StructuredGrid.jl:239-241)
+__device__ __forceinline__ double cand3(double dj, double xi, double yi, double zi, double ui, double xj,
+                                        double yj, double zj, double uj) {
+  const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
+  const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  const double d = __dsqrt_rn(s);
+  const double wgt = __dmul_rn(__dmul_rn(d, __drcp_rn(fabs(__dadd_rn(ui, uj)))), 2.0);
+  return __dadd_rn(dj, wgt);
+}
+
+// One CTA per active tile; dynamic smem = 5 * SX*SY*SZ doubles.
+__global__ void __launch_bounds__(TILE_THREADS) relax3d_kernel(P3 p, const i32* __restrict__ active, int cur) {
+  extern __shared__ double sm[];
+  const int w = p.w;
+  const int SX = TX + 2 * w, SY = TY + 2 * w, SZ = TZ + 2 * w;
+  const int SN = SX * SY * SZ;
+  double* sX = sm;
+  double* sY = sX + SN;
+  double* sZ = sY + SN;
+  double* sU = sZ + SN;
+  double* sD = sU + SN;
+  const i64 n_active = (i64)p.counters[cur];
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const int tid = threadIdx.x;
+  const int lx = tid % TX, ly = (tid / TX) % TY, lz = tid / (TX * TY);
+  u64 evals = 0, updates = 0;
+  for (i64 a = blockIdx.x; a < n_active; a += gridDim.x) {
+    const int tile = active[a];
+    const int tx = tile % p.tnx, ty = (tile / p.tnx) % p.tny, tz = tile / (p.tnx * p.tny);
+    const int ox = tx * TX - w, oy = ty * TY - w, oz = tz * TZ - w;  // global coords of smem cell (0,0,0)
+    __syncthreads();  // previous iteration's readers are done
+    for (int c = tid; c < SN; c += TILE_THREADS) {
+      const int cx = c % SX, cy = (c / SX) % SY, cz = c / (SX * SY);
+      const int gx = ox + cx, gy = oy + cy, gz = oz + cz;
+      if (gx >= 0 && gx < p.nx && gy >= 0 && gy < p.ny && gz >= 0 && gz < p.nz) {
+        const i64 J = (i64)gx + (i64)p.nx * ((i64)gy + (i64)p.ny * gz);
+        sX[c] = p.X[J];
+        sY[c] = p.Y[J];
+        sZ[c] = p.Z[J];
+        sU[c] = p.U[J];
+        sD[c] = p.dist0[J];
+      }
+    }
+    __syncthreads();
+    const int gx = tx * TX + lx, gy = ty * TY + ly, gz = tz * TZ + lz;
+    if (gx < p.nx && gy < p.ny && gz < p.nz) {
+      const i64 I = (i64)gx + (i64)p.nx * ((i64)gy + (i64)p.ny * gz);
+      const int ci = (lx + w) + SX * ((ly + w) + SY * (lz + w));
+      const double xi = sX[ci], yi = sY[ci], zi = sZ[ci], ui = sU[ci];
+      double best = sD[ci];
+      i64 bid = -1;
+      const int x0 = max(0, gx - w), x1 = min(p.nx - 1, gx + w);
+      const int y0 = max(0, gy - w), y1 = min(p.ny - 1, gy + w);
+      const int z0 = max(0, gz - w), z1 = min(p.nz - 1, gz + w);
+      for (int zz = z0; zz <= z1; ++zz)
+        for (int yy = y0; yy <= y1; ++yy) {
+          const int rowc = SX * ((yy - oy) + SY * (zz - oz)) - ox;
+          for (int xx = x0; xx <= x1; ++xx) {
+            const int c = rowc + xx;
+            if (!p.self && c == ci) continue;
+            const double dj = sD[c];
+            const double delta = (dj == INF) ? INF : cand3(dj, xi, yi, zi, ui, sX[c], sY[c], sZ[c], sU[c]);
+            if (delta < best) {
+              best = delta;
+              bid = (i64)xx + (i64)p.nx * ((i64)yy + (i64)p.ny * zz);
+            }
+          }
+        }
+      p.dist[I] = best;
+      if (bid >= 0) p.prev[I] = (i32)bid;
+      evals += (u64)(x1 - x0 + 1) * (u64)(y1 - y0 + 1) * (u64)(z1 - z0 + 1) - (p.self ? 0u : 1u);
+      updates += 1;
+    }
+  }
+  // block-level sum of the counters
+  for (int o = 16; o; o >>= 1) {
+    evals += __shfl_xor_sync(FULL, evals, o);
+    updates += __shfl_xor_sync(FULL, updates, o);
+  }
+  if ((tid & 31) == 0 && updates) {
+    atomicAdd(&p.counters[2], evals);
+    atomicAdd(&p.counters[3], updates);
+  }
+}
+
+// goo! + copyto!(dist0, dist) over the active tiles; flags tiles that hold an improved node.
+__global__ void __launch_bounds__(TILE_THREADS) commit3d_kernel(P3 p, const i32* __restrict__ active, int cur) {
+  const i64 n_active = (i64)p.counters[cur];
+  const int tid = threadIdx.x;
+  const int lx = tid % TX, ly = (tid / TX) % TY, lz = tid / (TX * TY);
+  for (i64 a = blockIdx.x; a < n_active; a += gridDim.x) {
+    const int tile = active[a];
+    const int tx = tile % p.tnx, ty = (tile / p.tnx) % p.tny, tz = tile / (p.tnx * p.tny);
+    const int gx = tx * TX + lx, gy = ty * TY + ly, gz = tz * TZ + lz;
+    bool imp = false;
+    if (gx < p.nx && gy < p.ny && gz < p.nz) {
+      const i64 I = (i64)gx + (i64)p.nx * ((i64)gy + (i64)p.ny * gz);
+      const double d = p.dist[I];
+      if (d < p.dist0[I]) {
+        p.dist0[I] = d;
+        imp = true;
+      }
+    }
+    if (__syncthreads_or(imp) && tid == 0) p.improved[tile] = 1;
+  }
+}
+
+// a tile joins the frontier iff a tile within reach of the window (ceil(w/T) tiles per axis) improved
+__global__ void activate3d_kernel(P3 p, i64 n_tiles, i32* __restrict__ next_active, int nxt) {
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  bool act = false;
+  if (t < n_tiles) {
+    const int tx = (int)(t % p.tnx), ty = (int)((t / p.tnx) % p.tny), tz = (int)(t / ((i64)p.tnx * p.tny));
+    const int rx = (p.w + TX - 1) / TX, ry = (p.w + TY - 1) / TY, rz = (p.w + TZ - 1) / TZ;
+    for (int zz = max(0, tz - rz); zz <= min(p.tnz - 1, tz + rz) && !act; ++zz)
+      for (int yy = max(0, ty - ry); yy <= min(p.tny - 1, ty + ry) && !act; ++yy)
+        for (int xx = max(0, tx - rx); xx <= min(p.tnx - 1, tx + rx); ++xx)
+          if (p.improved[(i64)xx + (i64)p.tnx * ((i64)yy + (i64)p.tny * zz)]) {
+            act = true;
+            break;
+          }
+  }
+  const unsigned ball = __ballot_sync(FULL, act);
+  if (ball) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(ball) - 1;
+    u64 base = 0;
+    if (lane == leader) base = atomicAdd(&p.counters[nxt], (u64)__popc(ball));
+    base = __shfl_sync(FULL, base, leader);
+    if (act) next_active[base + __popc(ball & ((1u << lane) - 1u))] = (i32)t;
+  }
+}
+
+__global__ void init3d_kernel(double* __restrict__ dist, double* __restrict__ dist0, i32* __restrict__ prev, i64 n,
+                              i64 source) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = (i == source) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+  dist[i] = v;
+  dist0[i] = v;
+  prev[i] = -1;
+}
+
+int ensure_ws3(rt_mesh* h) {
+  Grid3D& g = *h->g3;
+  if (g.ws_ready) return RT_OK;
+  RT_TRY(g.dist.alloc(g.n));
+  RT_TRY(g.dist0.alloc(g.n));
+  RT_TRY(g.prev.alloc(g.n));
+  RT_TRY(g.improved.alloc(g.n_tiles));
+  RT_TRY(g.act[0].alloc(g.n_tiles));
+  RT_TRY(g.act[1].alloc(g.n_tiles));
+  RT_TRY(g.counters.alloc(8));
+  RT_CUDA(cudaMallocHost((void**)&g.counters_host, 8 * sizeof(u64)));
+  g.ws_ready = true;
+  return RT_OK;
+}
+
+}  // namespace
+
+int grid3d_build(rt_mesh* h, const double c0[3], const double c1[3], const i64 nn[3], int star_levels,
+                 int coord_system) {
+  RT_ARG(c0 && c1 && nn, "null argument");
+  RT_ARG(nn[0] >= 1 && nn[1] >= 1 && nn[2] >= 1, "grid needs at least one node per axis");
+  RT_ARG(star_levels >= 0 && star_levels <= 3, "star_levels must be in 0..3");
+  RT_ARG(coord_system == 0 || coord_system == 1, "coord_system must be 0 or 1");
+  const i64 n = nn[0] * nn[1] * nn[2];
+  RT_ARG(n < (i64)2000000000 && nn[0] < 65536 * 16 && nn[1] < 65536 * 16 && nn[2] < 65536 * 16, "grid too large");
+  Grid3D* gp = new Grid3D();
+  h->g3 = gp;
+  h->kind = 3;
+  Grid3D& g = *gp;
+  for (int d = 0; d < 3; ++d) {
+    g.nn[d] = nn[d];
+    g.c0[d] = c0[d];
+    g.c1[d] = c1[d];
+  }
+  g.n = n;
+  g.star_levels = star_levels;
+  g.w = star_levels + 1;
+  g.self = star_levels >= 1 ? 1 : 0;
+  g.coord_system = coord_system;
+  g.tn[0] = (nn[0] + TX - 1) / TX;
+  g.tn[1] = (nn[1] + TY - 1) / TY;
+  g.tn[2] = (nn[2] + TZ - 1) / TZ;
+  g.n_tiles = g.tn[0] * g.tn[1] * g.tn[2];
+  RT_TRY(g.X.alloc(n));
+  RT_TRY(g.Y.alloc(n));
+  RT_TRY(g.Z.alloc(n));
+  coords3d_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(c0[0], c0[1], c0[2], c1[0], c1[1], c1[2], (int)nn[0],
+                                                          (int)nn[1], (int)nn[2], coord_system, g.X.p, g.Y.p, g.Z.p);
+  RT_CUDA(cudaGetLastError());
+  RT_CUDA(cudaStreamSynchronize(h->stream));
+  // E_graph = prod_d sum_i |clipped window_d(i)|  (- n when self is excluded)
+  i64 s[3];
+  for (int d = 0; d < 3; ++d) {
+    s[d] = 0;
+    for (i64 i = 0; i < nn[d]; ++i)
+      s[d] += std::min(nn[d] - 1, i + g.w) - std::max<i64>(0, i - g.w) + 1;
+  }
+  g.graph_edges = s[0] * s[1] * s[2] - (g.self ? 0 : n);
+  return RT_OK;
+}
+
+int grid3d_export(const rt_mesh* h, double* X, double* Y, double* Z) {
+  const Grid3D& g = *h->g3;
+  if (X) RT_CUDA(cudaMemcpy(X, g.X.p, g.n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (Y) RT_CUDA(cudaMemcpy(Y, g.Y.p, g.n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (Z) RT_CUDA(cudaMemcpy(Z, g.Z.p, g.n * sizeof(double), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+void grid3d_free(rt_mesh* h) {
+  if (h->g3) {
+    if (h->g3->counters_host) cudaFreeHost(h->g3->counters_host);
+    delete h->g3;
+  }
+  h->g3 = nullptr;
+}
+
+int grid3d_coords(const rt_mesh* h, const double** X, const double** Y, const double** Z, const double** none) {
+  *X = h->g3->X.p;
+  *Y = h->g3->Y.p;
+  *Z = h->g3->Z.p;
+  *none = nullptr;
+  return RT_OK;
+}
+
+int grid3d_n(const rt_mesh* h, i64* n) {
+  *n = h->g3->n;
+  return RT_OK;
+}
+
+int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                rt_stats* stats) {
+  Grid3D& g = *h->g3;
+  cudaStream_t s = h->stream;
+  RT_TRY(ensure_ws3(h));
+  const i64 n = g.n;
+  P3 p;
+  p.X = g.X.p;
+  p.Y = g.Y.p;
+  p.Z = g.Z.p;
+  p.U = U_dev;
+  p.dist = g.dist.p;
+  p.dist0 = g.dist0.p;
+  p.prev = g.prev.p;
+  p.improved = g.improved.p;
+  p.counters = g.counters.p;
+  p.nx = (int)g.nn[0];
+  p.ny = (int)g.nn[1];
+  p.nz = (int)g.nn[2];
+  p.tnx = (int)g.tn[0];
+  p.tny = (int)g.tn[1];
+  p.tnz = (int)g.tn[2];
+  p.w = g.w;
+  p.self = g.self;
+  const int w = g.w;
+  const size_t smem = (size_t)5 * (TX + 2 * w) * (TY + 2 * w) * (TZ + 2 * w) * sizeof(double);
+  RT_CUDA(cudaFuncSetAttribute(relax3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+  const i64 max_blocks = (i64)sm_count * 16;
+
+  cudaEvent_t ev0, ev1, evr0, evr1;
+  RT_CUDA(cudaEventCreate(&ev0));
+  RT_CUDA(cudaEventCreate(&ev1));
+  RT_CUDA(cudaEventCreate(&evr0));
+  RT_CUDA(cudaEventCreate(&evr1));
+  rt_stats st = {};
+  st.graph_edges = g.graph_edges;
+  int rc = RT_OK;
+  for (i64 si = 0; si < nsrc && rc == RT_OK; ++si) {
+    const i64 src1 = sources[si];
+    if (src1 < 1 || src1 > n) {
+      rt_set_error("source %lld out of range 1..%lld", (long long)src1, (long long)n);
+      rc = RT_ERR_ARG;
+      break;
+    }
+    const i64 src = src1 - 1;
+    cudaEventRecord(ev0, s);
+    init3d_kernel<<<grid_for(n, 256), 256, 0, s>>>(p.dist, p.dist0, p.prev, n, src);
+    cudaMemsetAsync(g.improved.p, 0, g.n_tiles, s);
+    cudaMemsetAsync(g.counters.p, 0, 8 * sizeof(u64), s);
+    // initial active set = window of the source (BFM: union!(active, G[source])) -> tiles around its tile
+    {
+      const i64 sx = src % g.nn[0], sy = (src / g.nn[0]) % g.nn[1], sz = src / (g.nn[0] * g.nn[1]);
+      const i64 st_tile = (sx / TX) + g.tn[0] * ((sy / TY) + g.tn[1] * (sz / TZ));
+      const uint8_t one = 1;
+      cudaMemcpyAsync(g.improved.p + st_tile, &one, 1, cudaMemcpyHostToDevice, s);
+    }
+    int cur = 0;
+    activate3d_kernel<<<grid_for(g.n_tiles, 256), 256, 0, s>>>(p, g.n_tiles, g.act[cur].p, cur);
+    cudaMemsetAsync(g.improved.p, 0, g.n_tiles, s);
+    cudaMemcpyAsync(g.counters_host, g.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+    st.total_launches += 2;
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      rc = RT_ERR_CUDA;
+      break;
+    }
+    i64 n_active = (i64)g.counters_host[cur];
+    while (n_active > 0) {
+      const int nxt = cur ^ 1;
+      const unsigned nb = (unsigned)std::min<i64>(n_active, max_blocks);
+      if (h->opts.profile_timers) cudaEventRecord(evr0, s);
+      relax3d_kernel<<<nb, TILE_THREADS, smem, s>>>(p, g.act[cur].p, cur);
+      if (h->opts.profile_timers) cudaEventRecord(evr1, s);
+      commit3d_kernel<<<nb, TILE_THREADS, 0, s>>>(p, g.act[cur].p, cur);
+      cudaMemsetAsync(g.counters.p + nxt, 0, sizeof(u64), s);
+      activate3d_kernel<<<grid_for(g.n_tiles, 256), 256, 0, s>>>(p, g.n_tiles, g.act[nxt].p, nxt);
+      cudaMemsetAsync(g.improved.p, 0, g.n_tiles, s);
+      cudaMemcpyAsync(g.counters_host, g.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+      st.total_launches += 3;
+      st.relax_launches += 1;
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        rc = RT_ERR_CUDA;
+        break;
+      }
+      if (h->opts.profile_timers) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evr0, evr1);
+        st.relax_ms += ms;
+      }
+      st.sweeps += 1;
+      cur = nxt;
+      n_active = (i64)g.counters_host[cur];
+    }
+    if (rc != RT_OK) break;
+    st.relaxed_edges += (i64)g.counters_host[2];
+    st.vertex_updates += (i64)g.counters_host[3];
+    cudaEventRecord(ev1, s);
+    if (dist_dev) cudaMemcpyAsync(dist_dev + si * n, g.dist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (prev_dev) cudaMemcpyAsync(prev_dev + si * n, g.prev.p, n * sizeof(i32), cudaMemcpyDeviceToDevice, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      rc = RT_ERR_CUDA;
+      break;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    st.kernel_ms += ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (rc == RT_ERR_CUDA || e != cudaSuccess) {
+    rt_set_error("CUDA failure in bfm3d_solve: %s", cudaGetErrorString(e));
+    rc = RT_ERR_CUDA;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  cudaEventDestroy(evr0);
+  cudaEventDestroy(evr1);
+  if (stats) *stats = st;
+  return rc;
+}

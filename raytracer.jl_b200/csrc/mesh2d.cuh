@@ -1,0 +1,48 @@
+// mesh2d.cuh -- device-resident two-level annulus graph (node -> elements -> nodes) and solver workspace.
+//
+// Data layout in HBM (all ids 0-based int32 internally; 1-based int64 only at the C ABI):
+//   x, z, theta, r        double[n]        node coordinates (gr.x, gr.z, gr.theta, gr.r)
+//   e2n_off / e2n_idx     int32[nel+1] / int32[sum|e2n|]   element -> nodes in the reference's list order
+//   g_off / g_idx         int64[n+1]  / int32[nnz(G)]      node -> elements, ascending (SparseMatrixCSC column)
+//   n2e_off / n2e_idx     int32[n+1]  / int32[sum|e2n|]    node -> elements that CONTAIN it (transpose of e2n)
+//   item_first            int32[n_items+1]  work items: runs of <= 32 consecutive node ids (32-aligned) whose
+//                         G columns are identical -> one warp relaxes one item and shares the candidate scan
+//   halo                  orig[H], twin[H] (+ CSR of twin rows grouped by orig for the second half of the rows)
+#pragma once
+#include "common.cuh"
+
+struct Mesh2D {
+  i64 n = 0, nel = 0, sum_e2n = 0, nnzG = 0, halo_rows = 0, sum_nbr = 0, ntheta = 0, nr = 0;
+  DevBuf<double> x, z, theta, r;
+  bool has_polar = false;
+  DevBuf<i32> e2n_off, e2n_idx;
+  DevBuf<i64> g_off;
+  DevBuf<i32> g_idx;
+  DevBuf<i32> n2e_off, n2e_idx;
+  i64 n_items = 0;
+  DevBuf<i32> item_first;
+  // halo
+  i64 H = 0;
+  bool halo_structured = true;
+  DevBuf<i32> halo_h1, halo_h2;  // all 2H rows (0-based), used by the generic serial path and by commit
+  DevBuf<i32> h2_orig, h2_off, h2_twin;  // second-half rows grouped by their target (orig) in row order
+  i64 n_h2_orig = 0;
+  DevBuf<i32> hinit_node, hinit_val;  // init_halo_path! result (last writer wins, serial order)
+  i64 n_hinit = 0;
+  i64 graph_edges = 0;
+  // extras kept on the host for rt_mesh_export of built meshes
+  std::vector<i64> nbr_off_h, nbr_idx_h;
+  std::vector<int8_t> el_type_h;
+  // solver workspace (allocated on first solve)
+  DevBuf<double> dist, dist0;
+  DevBuf<i32> prev;
+  DevBuf<uint8_t> dirty;
+  DevBuf<i32> act[2];
+  DevBuf<u64> counters;  // [0],[1]: active counts (ping-pong); [2]: evals; [3]: vertex updates; [4]: improved flag
+  u64* counters_host = nullptr;  // pinned
+  bool ws_ready = false;
+};
+
+// Finishes a Mesh2D whose primary arrays (x,z,e2n_*,g_*) are already on the device: builds n2e, work items,
+// halo tables, E_graph.  halo_host: (2H x 2) column-major 1-based (may be null if halo_rows == 0).
+int mesh2d_finalize(rt_mesh* h, const i64* halo_host);

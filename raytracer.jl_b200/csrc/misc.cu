@@ -1,0 +1,253 @@
+// misc.cu -- the small kernels either side of the solver: velocity interpolation, closest_point, id
+// conversion and recontruct_path.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+// src/GridAnnulus.jl:73 (also :262,:297,:912; src/ShortestPath.jl:77): the seven discontinuity radii
+__constant__ double RL_DEV[7] = {6371.0 - 20.0,  6371.0 - 35.0,   6371.0 - 210.0, 6371.0 - 410.0,
+                                 6371.0 - 660.0, 6371.0 - 2740.0, 6371.0 - 2891.5};
+
+// interpolate_velocity: src/utils.jl:38-44 (buffer < 0) / src/ShortestPath.jl:74-90 (buffer >= 0).
+// Interpolations.jl gridded linear: i = clamp(searchsortedlast(knots, x), 1, nk-1);
+// f = (x - k[i]) / (k[i+1] - k[i]);  v = (1 - f) * y[i] + f * y[i+1]   (no FMA)
+__global__ void interp_kernel(const double* __restrict__ kr, const double* __restrict__ kv, i64 nk,
+                              const double* __restrict__ r, i64 n, double buffer, double* __restrict__ out,
+                              int* __restrict__ bad) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double xq = r[i];
+  if (buffer >= 0.0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+      if (xq == RL_DEV[k]) {
+        xq = __dadd_rn(xq, buffer);
+        break;
+      }
+  }
+  if (!(xq >= kr[0] && xq <= kr[nk - 1])) {
+    *bad = 1;
+    out[i] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  // searchsortedlast: number of knots <= xq
+  i64 lo = 0, hi = nk;
+  while (lo < hi) {
+    const i64 mid = (lo + hi) >> 1;
+    if (kr[mid] <= xq)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  i64 idx = lo;  // 1-based index of the last knot <= xq
+  if (idx < 1) idx = 1;
+  if (idx > nk - 1) idx = nk - 1;
+  const double k0 = kr[idx - 1], k1 = kr[idx];
+  const double f = __ddiv_rn(__dsub_rn(xq, k0), __dsub_rn(k1, k0));
+  out[i] = __dadd_rn(__dmul_rn(__dsub_rn(1.0, f), kv[idx - 1]), __dmul_rn(f, kv[idx]));
+}
+
+// closest_point (src/GridAnnulus.jl:823-840): argmin_i sqrt((a_i-pa)^2 + (b_i-pb)^2), FIRST index on ties.
+// Pass 1: 64-bit atomicMin on the bit pattern of the (non-negative) distance; pass 2: atomicMin on the index
+// among the nodes that attain it.  One grid row (blockIdx.y) per query point.
+__device__ __forceinline__ double cp_dist(double a, double b, double pa, double pb) {
+  const double da = __dsub_rn(a, pa), db = __dsub_rn(b, pb);
+  return __dsqrt_rn(__dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db)));
+}
+__global__ void closest_pass1_kernel(const double* __restrict__ a, const double* __restrict__ b, i64 n,
+                                     const double* __restrict__ pa, const double* __restrict__ pb,
+                                     u64* __restrict__ best) {
+  const int q = blockIdx.y;
+  const double qa = pa[q], qb = pb[q];
+  u64 m = ~0ull;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const double d = cp_dist(a[i], b[i], qa, qb);
+    if (d == d) {  // NaN never wins (`di < dist` is false for NaN)
+      const u64 bits = (u64)__double_as_longlong(d);
+      m = bits < m ? bits : m;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 other = __shfl_xor_sync(0xffffffffu, m, o);
+    m = other < m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&best[q], m);
+}
+__global__ void closest_pass2_kernel(const double* __restrict__ a, const double* __restrict__ b, i64 n,
+                                     const double* __restrict__ pa, const double* __restrict__ pb,
+                                     const u64* __restrict__ best, u64* __restrict__ index) {
+  const int q = blockIdx.y;
+  const double qa = pa[q], qb = pb[q];
+  const u64 target = best[q];
+  u64 m = ~0ull;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const double d = cp_dist(a[i], b[i], qa, qb);
+    if (d == d && (u64)__double_as_longlong(d) == target) m = (u64)i < m ? (u64)i : m;
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 other = __shfl_xor_sync(0xffffffffu, m, o);
+    m = other < m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&index[q], m);
+}
+
+__global__ void prev_i32_to_i64_kernel(const i32* __restrict__ src, i64* __restrict__ dst, i64 count) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = (i64)src[i] + 1;  // -1 (never set) -> 0
+}
+__global__ void prev_i64_to_i32_kernel(const i64* __restrict__ src, i32* __restrict__ dst, i64 count) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = (i32)(src[i] - 1);
+}
+
+// recontruct_path(prev, source, receiver) src/SSSP/ssspm.jl:30-40: one thread per receiver, two passes
+// (count, then fill).  prev is 0-based int32, -1 = never set.  len = -1 if the chase fails.
+__global__ void path_len_kernel(const i32* __restrict__ prev, i64 n, i32 source, const i32* __restrict__ recv,
+                                i64 nrec, i64* __restrict__ len) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nrec) return;
+  const i32 rcv = recv[k];
+  if (rcv < 0 || rcv >= n) {
+    len[k] = -1;
+    return;
+  }
+  i64 l = 1;
+  i32 ip = (rcv == source) ? source : prev[rcv];
+  i64 steps = 0;
+  while (ip != source) {
+    if (ip < 0 || ip >= n || ++steps > n) {
+      len[k] = -1;
+      return;
+    }
+    ++l;
+    ip = prev[ip];
+  }
+  len[k] = l + 1;
+}
+__global__ void path_fill_kernel(const i32* __restrict__ prev, i32 source, const i32* __restrict__ recv, i64 nrec,
+                                 const i64* __restrict__ off, i64* __restrict__ out) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nrec) return;
+  i64 o = off[k];
+  const i64 end = off[k + 1];
+  const i32 rcv = recv[k];
+  out[o++] = (i64)rcv + 1;
+  i32 ip = (rcv == source) ? source : prev[rcv];
+  while (ip != source && o < end - 1) {
+    out[o++] = (i64)ip + 1;
+    ip = prev[ip];
+  }
+  out[o] = (i64)source + 1;
+}
+
+}  // namespace
+
+int interp_velocity_device(const double* kr_h, const double* kv_h, i64 nk, const double* r_dev, i64 n,
+                           double buffer, double* out_dev) {
+  RT_ARG(kr_h && kv_h && nk >= 2 && r_dev && out_dev && n >= 0, "bad interpolation arguments");
+  for (i64 k = 0; k + 1 < nk; ++k) RT_ARG(kr_h[k] < kr_h[k + 1], "knots must be strictly ascending");
+  DevBuf<double> kr, kv;
+  DevBuf<int> bad;
+  RT_TRY(kr.upload(kr_h, nk));
+  RT_TRY(kv.upload(kv_h, nk));
+  RT_TRY(bad.alloc(1));
+  RT_TRY(bad.zero());
+  if (n) interp_kernel<<<grid_for(n, 256), 256>>>(kr.p, kv.p, nk, r_dev, n, buffer, out_dev, bad.p);
+  RT_CUDA(cudaGetLastError());
+  int hb = 0;
+  RT_CUDA(cudaMemcpy(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (hb) {
+    rt_set_error("interpolation point outside the knots (BoundsError in the reference)");
+    return RT_ERR_RANGE;
+  }
+  return RT_OK;
+}
+
+int closest_point_device(const double* a_dev, const double* b_dev, i64 n, const double* pa, const double* pb,
+                         i64 npts, i64* out, cudaStream_t s) {
+  RT_ARG(pa && pb && out && npts >= 0 && npts < 65536, "bad closest_point arguments (npts < 65536)");
+  if (npts == 0) return RT_OK;
+  DevBuf<double> dpa, dpb;
+  DevBuf<u64> best, index;
+  RT_TRY(dpa.upload(pa, npts, s));
+  RT_TRY(dpb.upload(pb, npts, s));
+  RT_TRY(best.alloc(npts));
+  RT_TRY(index.alloc(npts));
+  RT_CUDA(cudaMemsetAsync(best.p, 0xff, npts * sizeof(u64), s));
+  RT_CUDA(cudaMemsetAsync(index.p, 0xff, npts * sizeof(u64), s));
+  const unsigned bx = (unsigned)std::min<i64>(grid_for(n, 256), 1184);
+  dim3 grid(bx, (unsigned)npts);
+  closest_pass1_kernel<<<grid, 256, 0, s>>>(a_dev, b_dev, n, dpa.p, dpb.p, best.p);
+  closest_pass2_kernel<<<grid, 256, 0, s>>>(a_dev, b_dev, n, dpa.p, dpb.p, best.p, index.p);
+  RT_CUDA(cudaGetLastError());
+  std::vector<u64> hi(npts);
+  RT_CUDA(cudaMemcpyAsync(hi.data(), index.p, npts * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  RT_CUDA(cudaStreamSynchronize(s));
+  for (i64 q = 0; q < npts; ++q) out[q] = hi[q] == ~0ull ? -1 : (i64)hi[q] + 1;  // -1 as in the reference
+  return RT_OK;
+}
+
+int prev_to_host_i64(const i32* prev_dev, i64 count, i64* out, cudaStream_t s) {
+  // convert in slabs so that the staging buffer stays small
+  const i64 slab = (i64)1 << 26;
+  DevBuf<i64> tmp;
+  RT_TRY(tmp.alloc(std::min(count, slab)));
+  for (i64 o = 0; o < count; o += slab) {
+    const i64 c = std::min(slab, count - o);
+    prev_i32_to_i64_kernel<<<grid_for(c, 256), 256, 0, s>>>(prev_dev + o, tmp.p, c);
+    RT_CUDA(cudaMemcpyAsync(out + o, tmp.p, c * sizeof(i64), cudaMemcpyDeviceToHost, s));
+    RT_CUDA(cudaStreamSynchronize(s));
+  }
+  return RT_OK;
+}
+
+// prev_dev: 0-based int32 table on the device.  receivers: host, 1-based.
+int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* receivers, i64 nrec,
+                             i64* path_off, i64* path_idx, i64 cap) {
+  RT_ARG(prev_dev && receivers && path_off && nrec >= 0, "bad path arguments");
+  RT_ARG(source >= 1 && source <= n, "source out of range");
+  std::vector<i32> r32(nrec);
+  for (i64 k = 0; k < nrec; ++k) {
+    RT_ARG(receivers[k] >= 1 && receivers[k] <= n, "receiver out of range");
+    r32[k] = (i32)(receivers[k] - 1);
+  }
+  DevBuf<i32> recv;
+  DevBuf<i64> len;
+  RT_TRY(recv.upload(r32.data(), nrec));
+  RT_TRY(len.alloc(nrec));
+  if (nrec) path_len_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, n, (i32)(source - 1), recv.p, nrec, len.p);
+  RT_CUDA(cudaGetLastError());
+  std::vector<i64> hl(nrec);
+  RT_CUDA(cudaMemcpy(hl.data(), len.p, nrec * sizeof(i64), cudaMemcpyDeviceToHost));
+  path_off[0] = 0;
+  for (i64 k = 0; k < nrec; ++k) {
+    if (hl[k] < 0) {
+      rt_set_error("recontruct_path: receiver %lld does not reach source %lld", (long long)receivers[k],
+                   (long long)source);
+      return RT_ERR_NOPATH;
+    }
+    path_off[k + 1] = path_off[k] + hl[k];
+  }
+  if (!path_idx) return RT_OK;
+  RT_ARG(cap >= path_off[nrec], "path_idx capacity too small");
+  if (nrec == 0) return RT_OK;
+  DevBuf<i64> off, out;
+  RT_TRY(off.upload(path_off, nrec + 1));
+  RT_TRY(out.alloc(path_off[nrec]));
+  path_fill_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, (i32)(source - 1), recv.p, nrec, off.p, out.p);
+  RT_CUDA(cudaGetLastError());
+  RT_CUDA(cudaMemcpy(path_idx, out.p, path_off[nrec] * sizeof(i64), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+int prev_host_to_device_i32(const i64* prev, i64 n, DevBuf<i32>& out) {
+  DevBuf<i64> tmp;
+  RT_TRY(tmp.upload(prev, n));
+  RT_TRY(out.alloc(n));
+  prev_i64_to_i32_kernel<<<grid_for(n, 256), 256>>>(tmp.p, out.p, n);
+  RT_CUDA(cudaGetLastError());
+  RT_CUDA(cudaDeviceSynchronize());
+  return RT_OK;
+}

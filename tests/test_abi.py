@@ -1,0 +1,56 @@
+"""CPU-side checks of the drop-in boundary: the shared library builds, loads and exports every symbol that
+include/rt_sssp.h declares; without a GPU the compute entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "rt_sssp.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree(rt):
+    assert header_symbols() == sorted(rt.SYMBOLS)
+
+
+def test_library_exports_every_symbol(rt):
+    L = C.CDLL(rt.SO_PATH)
+    for s in header_symbols():
+        assert hasattr(L, s), "librt_sssp.so does not export " + s
+
+
+def test_version_and_error_string(rt):
+    assert b"sm_100a" in rt.lib().rt_version()
+    assert isinstance(rt.lib().rt_last_error(), bytes)
+
+
+def test_product_does_not_reference_oracle():
+    pkg = os.path.join(ROOT, "raytracer.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower().replace("no oracle", ""), f + " mentions the oracle"
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="only meaningful without a GPU")
+def test_no_cpu_fallback_without_gpu(rt):
+    with pytest.raises(rt.RtError) as e:
+        rt.grid((0, 0, 0), (1, 1, 1), (4, 4, 4))
+    assert e.value.code == 2  # RT_ERR_CUDA
+    with pytest.raises(rt.RtError):
+        rt.interpolate_velocity(np.array([1.0, 2.0]), rt.LinearInterpolation([0.0, 10.0], [1.0, 2.0]))
+
+
+def test_velocity_profile_table(rt):
+    p = rt.velocity_profile()
+    assert len(p.r) == 6372 and p.r[0] == 0.0 and p.r[-1] == 6371.0
+    assert p.Vp[-1] == 5.8 and p.Vp[0] == 11.2409  # surface / centre of AK135
+    assert np.all(np.diff(p.r) == 1.0)

@@ -1,0 +1,214 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes front), against the CPU oracle on the
+same seeded inputs.  Bar (north star): travel times bit-exact in Float64 (stronger than the 1e-6 relative the
+north star allows), predecessors and reconstructed paths bit-exact in the reference (Jacobi) schedule."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import splitmix64
+from helpers import scan_pairs, ulp_diff, weight2d, weight3d
+
+pytestmark = pytest.mark.gpu
+R = 6371.0
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def adopt(rt, m):
+    """Oracle-built arrays -> Grid2D / G / halo objects of the product API (== what Julia would hand over)."""
+    gr = rt.Grid2D(m.x, m.z, m.theta, m.r, m.e2n_off, m.e2n_idx, m.ntheta, m.nr, m.nel, m.n)
+    G = rt.SparseMatrixCSC(m.nel, m.n, m.G_colptr, m.G_rowval)
+    halo = m.halo_matrix() if m.halo_rows else None
+    return gr, G, halo
+
+
+def test_library_loaded_and_device_present(rt):
+    assert rt.device_count() >= 1
+
+
+@pytest.mark.parametrize("nt,nr,sp", [(24, 6, 300.0), (36, 10, 100.0), (180, 50, 50.0), (90, 20, 20.0)])
+def test_bfm2d_ak135_bit_exact(rt, O, annulus, ak135, nt, nr, sp):
+    m = annulus(nt, nr, sp)
+    gr, G, halo = adopt(rt, m)
+    Vp = rt.interpolate_velocity(gr.r, rt.LinearInterpolation(*ak135))
+    assert np.array_equal(Vp, O.interp_velocity(ak135[0], ak135[1], m.r))  # velocity kernel is bit-exact
+    rt.mesh_from_arrays(gr, G, halo)
+    src = rt.closest_point(gr, 0.0, R, system="polar")
+    assert src == O.closest_point(m.theta, m.r, 0.0, R)
+    D = rt.bfm(G, halo, src, gr, Vp)
+    dist, prev, st = O.bfm(m, Vp, src)
+    assert np.array_equal(D.dist, dist)
+    assert np.array_equal(D.prev, prev)
+    assert D.stats["sweeps"] == st["sweeps"]
+    assert D.stats["graph_edges"] == st["graph_edges"]
+    assert D.stats["relaxed_edges"] >= st["relaxed_edges"]  # items relax supersets of the reference frontier
+    # README receivers -> identical paths
+    degs = np.concatenate([np.arange(10, 151, 10), 360 - np.arange(150, 9, -10)]).astype(np.float32)
+    recv = rt.closest_point(gr, np.deg2rad(degs).astype(np.float64), np.full(len(degs), R), system="polar")
+    paths = rt.recontruct_path(D.prev, src, recv)
+    for k, (rc, p) in enumerate(zip(recv, paths)):
+        assert rc == O.closest_point(m.theta, m.r, float(np.deg2rad(degs[k])), R)
+        assert np.array_equal(p, O.reconstruct_path(prev, src, int(rc)))
+
+
+def test_bfm2d_golden_vectors(rt):
+    g = np.load(os.path.join(GOLD, "annulus_24_6_300.npz"))
+    n, nel, hr = (int(v) for v in g["sizes"])
+    gr = rt.Grid2D(g["x"], g["z"], g["theta"], g["r"], g["e2n_off"], g["e2n_idx"], 24, 13, nel, n)
+    G = rt.SparseMatrixCSC(nel, n, g["G_colptr"], g["G_rowval"])
+    halo = g["halo"].reshape(2, hr).T
+    D = rt.bfm(G, halo, int(g["source"]), gr, g["U"])
+    assert np.array_equal(D.dist, g["dist"]) and np.array_equal(D.prev, g["prev"])
+    assert D.stats["sweeps"] == int(g["sweeps"])
+
+
+def test_bfm2d_random_velocity_and_interior_sources(rt, O, annulus):
+    m = annulus(36, 10, 100.0)
+    gr, G, halo = adopt(rt, m)
+    U = 4.0 + 6.0 * splitmix64(20261018, m.n)  # benchmarks/cpu.jl:19 style stress test
+    srcs = np.array([1, m.n, m.n // 2, int(m.halo_matrix()[0, 0]), int(m.halo_matrix()[0, 1]),
+                     m.nr * m.ntheta + 1], np.int64)  # first, last (a twin), middle, orig, twin, centre node
+    D = rt.bfm(G, halo, srcs, gr, U)
+    for k, s in enumerate(srcs):
+        dist, prev, st = O.bfm(m, U, int(s))
+        assert np.array_equal(D.dist[k], dist), "source %d" % s
+        assert np.array_equal(D.prev[k], prev), "source %d" % s
+    # size-independent properties on the GPU result itself
+    tgt, cand = scan_pairs(m)
+    w = weight2d(m.x, m.z, U, tgt, cand)
+    d = D.dist[2]
+    assert np.all(d[tgt] <= d[cand] + w) and d[srcs[2] - 1] == 0.0
+    hm = m.halo_matrix() - 1
+    assert np.array_equal(d[hm[:, 0]], d[hm[:, 1]])
+
+
+def test_bfm2d_no_halo_and_generic_halo(rt, O, annulus):
+    m = annulus(24, 6, 300.0)
+    # (a) no halo at all: layers stay disconnected below the first discontinuity -> unreached nodes stay Inf
+    import copy
+    m0 = copy.copy(m)
+    m0.halo = np.zeros(0, np.int64)
+    m0.halo_rows = 0
+    gr, G, _ = adopt(rt, m0)
+    U = np.full(m.n, 5.0)
+    D = rt.bfm(G, None, 1, gr, U)
+    dist, prev, st = O.bfm(m0, U, 1)
+    assert np.array_equal(D.dist, dist) and np.array_equal(D.prev, prev) and np.isinf(dist).any()
+    # (b) halo rows in a non-standard order -> generic serial halo path, still the reference's serial semantics
+    m1 = copy.copy(m)
+    hm = m.halo_matrix()[::-1].copy()
+    m1.halo = np.ascontiguousarray(hm.T).reshape(-1)
+    gr1, G1, halo1 = adopt(rt, m1)
+    D1 = rt.bfm(G1, halo1, 7, gr1, U)
+    d1, p1, s1 = O.bfm(m1, U, 7)
+    assert np.array_equal(D1.dist, d1) and np.array_equal(D1.prev, p1)
+
+
+def test_bfm_bad_arguments(rt, annulus):
+    m = annulus(24, 6, 300.0)
+    gr, G, halo = adopt(rt, m)
+    U = np.full(m.n, 5.0)
+    with pytest.raises(rt.RtError):
+        rt.bfm(G, halo, 0, gr, U)
+    with pytest.raises(rt.RtError):
+        rt.bfm(G, halo, m.n + 1, gr, U)
+    with pytest.raises(ValueError):
+        rt.bfm(G, halo, 1, gr, U[:-1])
+    bad = rt.SparseMatrixCSC(m.nel, m.n, m.G_colptr, m.G_rowval + 10 ** 6)
+    gr2 = rt.Grid2D(m.x, m.z, m.theta, m.r, m.e2n_off, m.e2n_idx, m.ntheta, m.nr, m.nel, m.n)
+    with pytest.raises(rt.RtError):
+        rt.bfm(bad, halo, 1, gr2, U)
+
+
+def test_interp_and_paths_errors(rt, ak135):
+    itp = rt.LinearInterpolation(*ak135)
+    v = rt.interpolate_velocity(np.array([0.0, 0.25, 3479.5, 6371.0]), itp)
+    assert v[0] == ak135[1][0] and v[3] == ak135[1][-1]
+    vb = rt.interpolate_velocity(np.array([3479.5]), itp, buffer=1)
+    assert vb[0] == rt.interpolate_velocity(np.array([3480.5]), itp)[0]
+    with pytest.raises(rt.RtError) as e:
+        rt.interpolate_velocity(np.array([6371.0001]), itp)
+    assert e.value.code == 3
+    prev = np.array([0, 1, 2, 3, 0], np.int64)  # chain 4->3->2->1, node 5 unreachable
+    assert list(rt.recontruct_path(prev, 1, 4)) == [4, 3, 2, 1]
+    assert list(rt.recontruct_path(prev, 1, 1)) == [1, 1]
+    with pytest.raises(rt.RtError) as e:
+        rt.recontruct_path(prev, 1, 5)
+    assert e.value.code == 4
+    assert [list(p) for p in rt.recontruct_path(prev, 1, [2, 4])] == [[2, 1], [4, 3, 2, 1]]
+
+
+# ------------------------------------------------------------------------------------------------- 3-D
+@pytest.mark.parametrize("nn,lv,cs", [((7, 6, 5), 1, "spherical"), ((11, 11, 11), 1, "cartesian"),
+                                      ((20, 9, 13), 0, "spherical"), ((33, 18, 10), 2, "cartesian"),
+                                      ((40, 40, 24), 1, "spherical")])
+def test_bfm3d_bit_exact(rt, O, nn, lv, cs):
+    if cs == "spherical":
+        c0 = (np.deg2rad(70.0), np.deg2rad(70.0), R - 2000.0)
+        c1 = (np.deg2rad(110.0), np.deg2rad(110.0), R)
+    else:
+        c0, c1 = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)
+    g = rt.grid(c0, c1, nn, neighbour_levels=lv, coord_system=cs)
+    X, Y, Z = g.coordinates()
+    Xo, Yo, Zo = O.grid3d_coords(c0, c1, nn, 0 if cs == "cartesian" else 1)
+    if cs == "cartesian":
+        assert np.array_equal(X, Xo) and np.array_equal(Y, Yo) and np.array_equal(Z, Zo)
+    else:  # device sin/cos vs glibc: <= 2 ulp; the solver contract is on identical arrays
+        assert max(ulp_diff(X, Xo), ulp_diff(Y, Yo), ulp_diff(Z, Zo)) <= 2
+    n = int(np.prod(nn))
+    U = 4.0 + 6.0 * splitmix64(7 + n, n)
+    srcs = np.array([1, n, n // 2 + 3], np.int64)
+    D = rt.bfm3d(g, srcs, U)
+    for k, s in enumerate(srcs):
+        dist, prev, st = O.bfm3d(nn, lv, X, Y, Z, U, int(s))
+        assert np.array_equal(D.dist[k], dist)
+        assert np.array_equal(D.prev[k], prev)
+    assert D.stats["graph_edges"] == st["graph_edges"]
+    # tightness of every predecessor, independent numpy arithmetic
+    d, p = D.dist[0], D.prev[0]
+    i = np.nonzero(p > 0)[0]
+    assert len(i) == n - 1
+    assert np.array_equal(d[p[i] - 1] + weight3d(X, Y, Z, U, i, p[i] - 1), d[i])
+    path = rt.recontruct_path(p, 1, n)
+    assert path[0] == n and path[-1] == 1 and np.all(np.diff(d[path - 1]) <= 0)
+
+
+def test_bfm3d_golden(rt):
+    g3 = np.load(os.path.join(GOLD, "grid3d_7_6_5.npz"))
+    g = rt.grid(g3["c0"], g3["c1"], (7, 6, 5), neighbour_levels=1, coord_system="spherical")
+    X, Y, Z = g.coordinates()
+    D = rt.bfm3d(g, int(g3["source"]), g3["U"])
+    if np.array_equal(X, g3["X"]) and np.array_equal(Y, g3["Y"]) and np.array_equal(Z, g3["Z"]):
+        assert np.array_equal(D.dist, g3["dist"]) and np.array_equal(D.prev, g3["prev"])
+    else:  # coordinates differ in the last ulp (device vs glibc sin/cos): travel times agree to ~1e-15
+        assert np.allclose(D.dist, g3["dist"], rtol=1e-13, atol=0)
+
+
+def test_bfm3d_full_size_properties(rt):
+    """At a BASELINE-like size the oracle is too slow: check size-independent properties instead."""
+    nn = (96, 96, 64)
+    c0 = (np.deg2rad(70.0), np.deg2rad(70.0), R - 2000.0)
+    c1 = (np.deg2rad(110.0), np.deg2rad(110.0), R)
+    g = rt.grid(c0, c1, nn, neighbour_levels=1, coord_system="spherical")
+    X, Y, Z = g.coordinates()
+    n = g.n
+    rr = np.sqrt(X * X + Y * Y + Z * Z)
+    prof = rt.velocity_profile()
+    U = rt.interpolate_velocity(np.minimum(rr, R), rt.LinearInterpolation(prof.r, prof.Vp))
+    src = 1 + 48 + 96 * (48 + 96 * 63)
+    D = rt.bfm3d(g, src, U)
+    d, p = D.dist, D.prev
+    assert d[src - 1] == 0.0 and not np.isinf(d).any()
+    i = np.nonzero(p > 0)[0]
+    assert len(i) == n - 1
+    assert np.array_equal(d[p[i] - 1] + weight3d(X, Y, Z, U, i, p[i] - 1), d[i])  # bit-exact tightness
+    # fixed point along the three axes (+-1, +-2 neighbours)
+    D3 = d.reshape(64, 96, 96)
+    idx = np.arange(n).reshape(64, 96, 96)
+    for ax in range(3):
+        for sft in (1, 2):
+            a = np.take(idx, np.arange(sft, idx.shape[ax]), axis=ax).ravel()
+            b = np.take(idx, np.arange(0, idx.shape[ax] - sft), axis=ax).ravel()
+            w = weight3d(X, Y, Z, U, a, b)
+            assert np.all(d[a] <= d[b] + w) and np.all(d[b] <= d[a] + w)
+    assert D.stats["relaxed_edges"] > D.stats["graph_edges"]
