@@ -153,8 +153,9 @@ def test_bfm3d_bit_exact(rt, O, nn, lv, cs):
     Xo, Yo, Zo = O.grid3d_coords(c0, c1, nn, 0 if cs == "cartesian" else 1)
     if cs == "cartesian":
         assert np.array_equal(X, Xo) and np.array_equal(Y, Yo) and np.array_equal(Z, Zo)
-    else:  # device sin/cos vs glibc: <= 2 ulp; the solver contract is on identical arrays
-        assert max(ulp_diff(X, Xo), ulp_diff(Y, Yo), ulp_diff(Z, Zo)) <= 2
+    else:  # device sin/cos vs glibc differ by <= 1 ulp each, x = r*cos(phi)*sin(theta) compounds them
+        # (builder parity is structural; the solver's bit-exact contract is on identical arrays)
+        assert max(ulp_diff(X, Xo), ulp_diff(Y, Yo), ulp_diff(Z, Zo)) <= 4
     n = int(np.prod(nn))
     U = 4.0 + 6.0 * splitmix64(7 + n, n)
     srcs = np.array([1, n, n // 2 + 3], np.int64)
