@@ -461,7 +461,6 @@ CF_HD i64 g_column_centre_entry(const Params& p, i64 i) {  // i-th (0-based) ent
 
 // -----------------------------------------------------------------------------------------------------------
 // Host-side O(nr) set-up of the parameter tables (ring radii, quad-row layers, discontinuity flags)
-#if !defined(__CUDA_ARCH__)
 #include <algorithm>
 #include <vector>
 namespace cf {
@@ -523,4 +522,3 @@ inline void make_params(i64 ntheta, i64 nr, double spacing, HostParams& hp) {
 }
 
 }  // namespace cf
-#endif

@@ -213,3 +213,50 @@ def test_bfm3d_full_size_properties(rt):
             w = weight3d(X, Y, Z, U, a, b)
             assert np.all(d[a] <= d[b] + w) and np.all(d[b] <= d[a] + w)
     assert D.stats["relaxed_edges"] > D.stats["graph_edges"]
+
+
+# --------------------------------------------------------------------------------- device annulus builder
+@pytest.mark.parametrize("nt,nr,sp", [(8, 2, 500.0), (24, 6, 300.0), (37, 11, 77.7), (180, 50, 20), (64, 3, 0.9)])
+def test_init_annulus_device_builder(rt, O, annulus, nt, nr, sp):
+    m = annulus(nt, nr, sp)
+    gr, G, halo = rt.init_annulus(nt, nr, spacing=sp)
+    assert (gr.nnods, gr.nel, gr.ntheta, gr.nr) == (m.n, m.nel, m.ntheta, m.nr)
+    assert np.array_equal(gr.theta, m.theta) and np.array_equal(gr.r, m.r)  # plain arithmetic: bit-identical
+    assert max(ulp_diff(gr.x, m.x), ulp_diff(gr.z, m.z)) <= 2 or np.allclose(gr.x, m.x, rtol=0, atol=2e-12)
+    assert np.array_equal(gr.e2n_off, m.e2n_off) and np.array_equal(gr.e2n_idx, m.e2n_idx)
+    assert np.array_equal(G.colptr, m.G_colptr) and np.array_equal(G.rowval, m.G_rowval)
+    assert np.array_equal(halo, m.halo_matrix())
+    assert np.array_equal(gr.nbr_off, m.nbr_off) and np.array_equal(gr.element_type, m.el_type)
+    for e in range(1, m.nel + 1, max(1, m.nel // 300)):
+        assert sorted(m.nbr_idx[m.nbr_off[e - 1]:m.nbr_off[e]]) == list(gr.neighbours(e))
+    assert np.array_equal(gr.e2n[m.nel], m.e2n_idx[m.e2n_off[m.nel - 1]:m.e2n_off[m.nel]])
+
+
+def test_readme_example_on_device_built_mesh(rt, O, ak135):
+    """README.md:15-53 end to end through the drop-in API, checked against the oracle on identical arrays."""
+    nt, nr, sp = 180, 50, 50
+    gr, G, halo = rt.init_annulus(nt, nr, spacing=sp)
+    source = rt.closest_point(gr, 0.0, R, system="polar")
+    profile = rt.velocity_profile()
+    Vp = rt.interpolate_velocity(gr.r, rt.LinearInterpolation(profile.r, profile.Vp))
+    D = rt.bfm(G, halo, source, gr, Vp)
+    # oracle on the arrays the device builder produced (x, z come from device sin/cos)
+    m = O.Annulus(nt, nr, sp)
+    m.x, m.z = gr.x, gr.z
+    dist, prev, st = O.bfm(m, Vp, source)
+    assert np.array_equal(D.dist, dist) and np.array_equal(D.prev, prev) and D.stats["sweeps"] == st["sweeps"]
+    degs = np.concatenate([np.arange(10, 151, 10), 360 - np.arange(150, 9, -10)]).astype(np.float32)
+    recv = rt.closest_point(gr, np.deg2rad(degs).astype(np.float64), np.full(len(degs), R), system="polar")
+    paths = rt.recontruct_path(D.prev, source, recv)
+    assert len(paths) == 30
+    for rc, p in zip(recv, paths):
+        assert np.array_equal(p, O.reconstruct_path(prev, source, int(rc)))
+    for deg, t in ((30, 376.49), (90, 785.97), (180, 1189.47)):  # SURVEY 8c-4 sanity values
+        rc = rt.closest_point(gr, float(np.deg2rad(np.float32(deg))), R, system="polar")
+        assert abs(D.dist[rc - 1] - t) < 0.006
+
+
+def test_init_annulus_rejects_bad_arguments(rt):
+    for args in ((4, 10, 20.0), (36, 1, 20.0), (36, 10, 0.0)):
+        with pytest.raises(rt.RtError):
+            rt.init_annulus(args[0], args[1], spacing=args[2])
