@@ -1,0 +1,177 @@
+# RayTracerB200.jl -- thin `ccall` front of librt_sssp.so that re-creates the exported interface of
+# RayTracer.jl (src/RayTracer.jl:24-34) for the shortest-path-method hot path.  No CUDA.jl, no kernels in
+# Julia: every call lands in the C ABI declared in include/rt_sssp.h.
+#
+#     include("julia/RayTracerB200.jl"); using .RayTracerB200
+#     gr, G, halo = init_annulus(180, 50; spacing = 1)
+#     source      = closest_point(gr, 0.0, R; system = :polar)
+#     Vp          = interpolate_velocity(gr.r, LinearInterpolation(profile.r, profile.Vp))
+#     D           = bfm(G, halo, source, gr, Vp)          # D.dist :: Vector{Float64}, D.prev :: Vector{Int64}
+#     path        = recontruct_path(D.prev, source, receiver)
+#
+# NOTE: Julia is not installed in the build image, so this file is the binding a maintainer would add; the
+# same entry points are exercised by the Python ctypes front (raytracer.jl_b200/api.py) in tests/ and bench.py.
+module RayTracerB200
+
+using SparseArrays
+
+export Grid2D, BellmanFordMoore, R, init_annulus, closest_point, interpolate_velocity, bfm, recontruct_path,
+       LinearInterpolation, bfm_batch
+
+const R = 6371.0                                   # src/utils.jl:2
+const LIB = get(ENV, "RT_SSSP_LIB", joinpath(@__DIR__, "..", "raytracer.jl_b200", "librt_sssp.so"))
+
+struct RtStats                                     # mirrors rt_stats (include/rt_sssp.h)
+    sweeps::Int64
+    relaxed_edges::Int64
+    vertex_updates::Int64
+    graph_edges::Int64
+    kernel_ms::Float64
+    relax_ms::Float64
+    relax_launches::Int64
+    total_launches::Int64
+end
+
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:rt_last_error, LIB), Cstring, ()))
+    rc == 3 && throw(BoundsError())                # interpolation outside the knots, as Interpolations.jl throws
+    error("rt_sssp error $rc: $msg")
+end
+
+mutable struct MeshHandle
+    ptr::Ptr{Cvoid}
+    function MeshHandle(p::Ptr{Cvoid})
+        h = new(p)
+        finalizer(x -> (x.ptr != C_NULL && ccall((:rt_mesh_free, LIB), Cint, (Ptr{Cvoid},), x.ptr); x.ptr = C_NULL), h)
+        return h
+    end
+end
+
+# Grid2D of src/GridAnnulus.jl:9-21 plus the native handle
+mutable struct Grid2D
+    x::Vector{Float64}
+    z::Vector{Float64}
+    θ::Vector{Float64}
+    r::Vector{Float64}
+    e2n::Dict{Int,Vector{Int64}}
+    nθ::Int64
+    nr::Int64
+    nel::Int64
+    nnods::Int64
+    neighbours::Vector{Vector{Int64}}
+    element_type::Dict{Int,Symbol}
+    handle::Union{Nothing,MeshHandle}
+end
+Base.length(gr::Grid2D) = gr.nnods
+
+struct BellmanFordMoore{T,M}                       # src/SSSP/ssspm.jl:3-10
+    prev::T
+    dist::M
+end
+
+struct LinearInterpolation                         # stand-in for Interpolations.LinearInterpolation (README.md:32)
+    knots::Vector{Float64}
+    values::Vector{Float64}
+end
+
+# init_annulus(nθ, nr; spacing) -- src/GridAnnulus.jl:57-70, built by CUDA kernels
+function init_annulus(nθ::Int64, nr::Int64; spacing = 20)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rt_annulus_build, LIB), Cint, (Int64, Int64, Cdouble, Ref{Ptr{Cvoid}}), nθ, nr, Float64(spacing), out))
+    h = MeshHandle(out[])
+    sz = zeros(Int64, 8)
+    check(ccall((:rt_mesh_sizes, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), h.ptr, sz))
+    n, nel, se, nnz, hr, sn = sz[1], sz[2], sz[3], sz[4], sz[5], sz[6]
+    x, z, θ, r = zeros(n), zeros(n), zeros(n), zeros(n)
+    e2n_off, e2n_idx = zeros(Int64, nel + 1), zeros(Int64, se)
+    colptr, rowval = zeros(Int64, n + 1), zeros(Int64, nnz)
+    halo = zeros(Int64, hr, 2)                     # column-major (2H x 2) exactly as the ABI writes it
+    nbr_off, nbr_idx, el_type = zeros(Int64, nel + 1), zeros(Int64, sn), zeros(Int8, nel)
+    check(ccall((:rt_mesh_export, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64},
+                 Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int8}),
+                h.ptr, x, z, θ, r, e2n_off, e2n_idx, colptr, rowval, halo, nbr_off, nbr_idx, el_type))
+    e2n = Dict{Int,Vector{Int64}}(i => e2n_idx[(e2n_off[i] + 1):e2n_off[i + 1]] for i in 1:nel)
+    neighbours = [nbr_idx[(nbr_off[i] + 1):nbr_off[i + 1]] for i in 1:nel]
+    etype = Dict{Int,Symbol}(i => (el_type[i] == 0 ? :Quad : :Tri) for i in 1:nel)
+    gr = Grid2D(x, z, θ, r, e2n, sz[7], sz[8], nel, n, neighbours, etype, h)
+    G = SparseMatrixCSC{Bool,Int64}(nel, n, colptr, rowval, fill(true, nnz))
+    return gr, G, halo
+end
+
+# adopt a graph built by the reference itself (gr without a native handle)
+function mesh_handle(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, gr)
+    hasproperty(gr, :handle) && gr.handle !== nothing && return gr.handle
+    nel = gr.nel
+    e2n_off = zeros(Int64, nel + 1)
+    for i in 1:nel
+        e2n_off[i + 1] = e2n_off[i] + length(gr.e2n[i])
+    end
+    e2n_idx = reduce(vcat, (gr.e2n[i] for i in 1:nel))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    halo64 = Matrix{Int64}(halo)
+    check(ccall((:rt_mesh_from_arrays, LIB), Cint,
+                (Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                G.n, nel, e2n_off, e2n_idx, G.colptr, G.rowval, halo64, size(halo64, 1), gr.x, gr.z, gr.θ, gr.r, out))
+    h = MeshHandle(out[])
+    hasproperty(gr, :handle) && (gr.handle = h)
+    return h
+end
+
+# interpolate_velocity(r, interpolant) -- src/utils.jl:38-44 (buffer kw: src/ShortestPath.jl:74-90)
+function interpolate_velocity(r::AbstractArray, itp::LinearInterpolation; buffer = nothing)
+    V = similar(r, Float64)
+    rr = Vector{Float64}(vec(r))
+    check(ccall((:rt_interp_velocity, LIB), Cint,
+                (Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Cdouble, Ptr{Float64}),
+                itp.knots, itp.values, length(itp.knots), rr, length(rr), buffer === nothing ? -1.0 : Float64(buffer), V))
+    return V
+end
+
+# closest_point(gr, px, pz; system) -- src/GridAnnulus.jl:823-840
+function closest_point(gr::Grid2D, px, pz; system = :cartesian)
+    out = zeros(Int64, 1)
+    check(ccall((:rt_closest_point, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Cint, Ptr{Int64}),
+                gr.handle.ptr, [Float64(px)], [Float64(pz)], 1, system == :cartesian ? 0 : 1, out))
+    return out[1]
+end
+
+# bfm(G, halo, source, gr, U) -- src/SSSP/bfm.jl:1-52
+function bfm(G::SparseMatrixCSC{Bool,M}, halo::Matrix, source::Integer, gr, U::AbstractArray{T}) where {M,T}
+    D, st = bfm_batch(G, halo, Int64[source], gr, U)
+    println("Converged in $(st.sweeps + 1) iterations")          # bfm.jl:49 (it starts at 1)
+    return BellmanFordMoore(D.prev[:, 1], D.dist[:, 1])
+end
+
+# batch API: many earthquakes on one mesh; tables are n x nsrc (column per source)
+function bfm_batch(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector{Int64}, gr, U::AbstractArray)
+    h = mesh_handle(G, halo, gr)
+    n, ns = G.n, length(sources)
+    dist = Matrix{Float64}(undef, n, ns)
+    prev = Matrix{Int64}(undef, n, ns)
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0))
+    check(ccall((:rt_bfm_solve, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
+                h.ptr, Vector{Float64}(U), sources, ns, 64, dist, prev, st))
+    return BellmanFordMoore(prev, dist), st[]
+end
+
+# recontruct_path(prev, source, receiver) -- src/SSSP/ssspm.jl:30-40 (the misspelling is the reference's API)
+function recontruct_path(prev::Vector, source, receiver)
+    p64 = Vector{Int64}(prev)
+    off = zeros(Int64, 2)
+    rc = Int64[receiver]
+    check(ccall((:rt_reconstruct_paths, LIB), Cint,
+                (Ptr{Int64}, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Int64),
+                p64, length(p64), source, rc, 1, off, C_NULL, 0))
+    path = zeros(Int64, off[2])
+    check(ccall((:rt_reconstruct_paths, LIB), Cint,
+                (Ptr{Int64}, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Int64),
+                p64, length(p64), source, rc, 1, off, path, length(path)))
+    return Vector{Int}(path)
+end
+recontruct_path(D::BellmanFordMoore, source, receiver) = recontruct_path(D.prev, source, receiver)
+
+end # module

@@ -248,19 +248,33 @@ def _solve(handle, n, U, sources, want_prev=True):
     return dist, prev, st.as_dict()
 
 
-def bfm(G, halo, source, gr, U):
+SCHEDULES = {"jacobi": 0, "near-far": 1}
+
+
+def bfm(G, halo, source, gr, U, schedule=None, delta=None):
     """D = bfm(G, halo, source, gr, U) -- src/SSSP/bfm.jl:1-52.  `source` may be an array of sources, in which
-    case D.dist / D.prev are [nsrc x n] tables (the batch API); a scalar gives vectors as in the reference."""
+    case D.dist / D.prev are [nsrc x n] tables (the batch API); a scalar gives vectors as in the reference.
+
+    schedule (extension): "jacobi" = the reference's sweeps (dist and prev bit-identical, ties included);
+    "near-far" = work-efficient push schedule (dist bit-identical, prev identical except on exact ties)."""
     handle = mesh_from_arrays(gr, G, halo)
+    if schedule is not None:
+        handle.set_option("schedule", SCHEDULES[schedule])
+    if delta is not None:
+        handle.set_option("delta", delta)
     dist, prev, st = _solve(handle, int(G.n), U, source)
     if np.ndim(source) == 0:
         return BellmanFordMoore(prev[0], dist[0], st)
     return BellmanFordMoore(prev, dist, st)
 
 
-def bfm3d(gr3, source, U):
+def bfm3d(gr3, source, U, schedule=None, delta=None):
     """BFM(G, source, gr, U, fw) of src/Dijsktra.jl:294-343 on the implicit star-L graph of a Grid3D with the
     edge weight of src/SSSP/weights.jl:20."""
+    if schedule is not None:
+        gr3._handle.set_option("schedule", SCHEDULES[schedule])
+    if delta is not None:
+        gr3._handle.set_option("delta", delta)
     dist, prev, st = _solve(gr3._handle, gr3.n, U, source)
     if np.ndim(source) == 0:
         return BellmanFordMoore(prev[0], dist[0], st)

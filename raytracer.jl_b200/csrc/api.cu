@@ -221,6 +221,9 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
   } else if (!std::strcmp(key, "delta")) {
     RT_ARG(value >= 0.0, "delta must be >= 0");
     m->opts.delta = value;
+  } else if (!std::strcmp(key, "delta_factor")) {
+    RT_ARG(value >= 0.0, "delta_factor must be >= 0");
+    m->opts.delta_factor = value;
   } else {
     rt_set_error("unknown option '%s'", key);
     return RT_ERR_ARG;

@@ -259,8 +259,11 @@ int ensure_workspace(rt_mesh* h) {
 
 }  // namespace
 
+int bfm2d_ensure_workspace(rt_mesh* h) { return ensure_workspace(h); }
+
 int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                 rt_stats* stats) {
+  if (h->opts.schedule == 1) return bfm2d_solve_push(h, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
   Mesh2D& m = *h->m2;
   cudaStream_t s = h->stream;
   RT_TRY(ensure_workspace(h));

@@ -1,0 +1,568 @@
+// bfm2d_push.cu -- work-efficient schedule for bfm on the two-level annulus graph (schedule = 1, "near-far").
+//
+// The reference's Jacobi sweeps (src/SSSP/bfm.jl:29-47) re-relax every vertex 40-70 times on these meshes
+// (measured: E_relaxed / E_graph = 39.6 ... 67).  Because fp `+` is monotone and weights are >= 0 the converged
+// travel times are the least fixed point and do not depend on the relaxation order, so this file
+// uses a label-correcting PUSH schedule ordered by travel time instead:
+//   * dist is updated with a 64-bit atomicMin on the bit pattern of the (non-negative) double;
+//   * a node whose value improved carries a flag; it is released (pushes dist + w to its whole star patch) only
+//     once its value is below the moving threshold tau ("near"); improvements above tau wait in a far list;
+//     when no near work is left tau moves to (smallest waiting value + delta);
+//   * a released work item (<= 32 nodes sharing one G column) is expanded by one CTA: its column's elements are
+//     spread over the warps, lanes hold TARGET nodes (coalesced id loads, gathers of x, z, U), the released
+//     sources are broadcast from shared memory, and the edge weight 2*len/(U_i+U_j) is computed in registers
+//     with the reference's operation order (it is bitwise symmetric in i and j);
+//   * the halo rule (update_halo!, bfm.jl:54-62) is a zero-weight coupling between twins and is pushed too.
+// Travel times are therefore bit-identical to the Jacobi schedule / the reference.  Predecessors are assigned
+// afterwards by a deterministic pass: prev[i] = first candidate in the reference's scan order that is
+// bit-exactly tight (dist[j] + w == dist[i]) with dist[j] < dist[i]; nodes that owe their value to a
+// zero-weight coupling (twins, coincident duplicates) inherit along that coupling.  This equals the
+// reference's prev except on exact ties (which are systematic on these meshes: every radial edge exists twice).
+#include "mesh2d.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int PUSH_BLOCK = 128;
+
+struct PP {
+  const double* __restrict__ x;
+  const double* __restrict__ z;
+  const double* __restrict__ U;
+  const i32* __restrict__ e2n_off;
+  const i32* __restrict__ e2n_idx;
+  const i64* __restrict__ g_off;
+  const i32* __restrict__ g_idx;
+  const i32* __restrict__ item_first;
+  const i32* __restrict__ node_item;
+  const i32* __restrict__ hn_node;
+  const i32* __restrict__ hn_off;
+  const i32* __restrict__ hn_part;
+  int n_hn;
+  double* dist;
+  i32* prev;
+  unsigned* pend_mask;
+  unsigned* far_mask;
+  unsigned* infar;
+  unsigned* cur_mask;
+  u64* counters;  // [0],[1] near counts (ping-pong) [2] evals [3] releases [4],[5] far counts (ping-pong)
+                  // [6] unresolved count [7] scratch
+  double* tau;    // [0] tau [1] delta [2] min far (bits)
+};
+
+__device__ __forceinline__ double edge_delta(double di, double xi, double zi, double Ui, double xj, double zj,
+                                             double Uj) {
+  const double dx = __dsub_rn(xi, xj);
+  const double dz = __dsub_rn(zi, zj);
+  const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+  const double len2 = __dmul_rn(2.0, __dsqrt_rn(d2));
+  return __dadd_rn(di, __ddiv_rn(len2, __dadd_rn(Ui, Uj)));
+}
+
+__global__ void node_item_kernel(const i32* __restrict__ item_first, i64 n_items, i32* __restrict__ node_item) {
+  const i64 it = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (it >= n_items) return;
+  const int v0 = item_first[it], t = item_first[it + 1] - v0;
+  if (lane < t) node_item[v0 + lane] = (i32)it;
+}
+
+// smallest positive weight between consecutive entries of the element lists: proxy for the lightest edge
+__global__ void wmin_kernel(PP p, i64 nel, u64* __restrict__ out) {
+  const i64 w = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  u64 best = ~0ull;
+  if (w < nel) {
+    for (i32 q = p.e2n_off[w] + lane; q + 1 < p.e2n_off[w + 1]; q += 32) {
+      const int a = p.e2n_idx[q], b = p.e2n_idx[q + 1];
+      const double wt = edge_delta(0.0, p.x[a], p.z[a], p.U[a], p.x[b], p.z[b], p.U[b]);
+      if (wt > 0.0 && wt == wt) {
+        const u64 bits = (u64)__double_as_longlong(wt);
+        best = bits < best ? bits : best;
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 other = __shfl_xor_sync(FULL, best, o);
+    best = other < best ? other : best;
+  }
+  if (lane == 0 && best != ~0ull) atomicMin(out, best);
+}
+
+// flag node j (whose value just improved to d) for propagation: near list if d < tau, else far list
+__device__ __forceinline__ void enqueue(const PP& p, int j, double d, double tau, i32* __restrict__ near_next,
+                                        int nxt, i32* __restrict__ far_list, int fcur) {
+  const int it = p.node_item[j];
+  const unsigned bit = 1u << (j - p.item_first[it]);
+  if (d < tau) {
+    const unsigned old = atomicOr(&p.pend_mask[it], bit);
+    if (old == 0u) near_next[atomicAdd(&p.counters[nxt], 1ull)] = it;
+    if (p.far_mask[it] & bit) atomicAnd(&p.far_mask[it], ~bit);
+  } else {
+    atomicOr(&p.far_mask[it], bit);
+    if (atomicExch(&p.infar[it], 1u) == 0u) far_list[atomicAdd(&p.counters[4 + fcur], 1ull)] = it;
+  }
+}
+
+// try dist[j] = min(dist[j], d); returns true if it improved
+__device__ __forceinline__ bool relax_to(const PP& p, int j, double d) {
+  const u64 bits = (u64)__double_as_longlong(d);
+  const u64 old = atomicMin((u64*)&p.dist[j], bits);
+  return bits < old;
+}
+
+// round step 1: take the released bits of every item of the near list
+__global__ void prep_kernel(PP p, const i32* __restrict__ near_cur, int cur) {
+  const i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= (i64)p.counters[cur]) return;
+  const int it = near_cur[slot];
+  p.cur_mask[slot] = atomicExch(&p.pend_mask[it], 0u);
+}
+
+// round step 2: one CTA per released item; warps split the elements of its G column; lanes = targets.
+__global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
+                                                           i32* __restrict__ near_next, i32* __restrict__ far_list,
+                                                           int fcur) {
+  __shared__ double sx[32], sz[32], sU[32], sd[32];
+  __shared__ int s_id[32];
+  __shared__ int s_ns;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const i64 n_near = (i64)p.counters[cur];
+  const double tau = p.tau[0];
+  u64 evals = 0;
+  for (i64 slot = blockIdx.x; slot < n_near; slot += gridDim.x) {
+    const int it = near_cur[slot];
+    const unsigned mask = p.cur_mask[slot];
+    const int v0 = p.item_first[it];
+    __syncthreads();  // smem reuse across slots
+    if (warp == 0) {
+      // compact the released sources into shared memory
+      const bool on = (mask >> lane) & 1u;
+      const int pos = __popc(mask & ((1u << lane) - 1u));
+      if (on) {
+        const int i = v0 + lane;
+        sx[pos] = p.x[i];
+        sz[pos] = p.z[i];
+        sU[pos] = p.U[i];
+        sd[pos] = p.dist[i];
+        s_id[pos] = i;
+      }
+      if (lane == 0) s_ns = __popc(mask);
+    }
+    __syncthreads();
+    const int ns = s_ns;
+    if (ns == 0) continue;
+    // zero-weight halo coupling (update_halo!): lane s of warp 0 serves source s
+    if (warp == 0 && p.n_hn > 0 && lane < ns) {
+      const int i = s_id[lane];
+      int lo = 0, hi = p.n_hn;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (p.hn_node[mid] < i)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      if (lo < p.n_hn && p.hn_node[lo] == i) {
+        const double d = sd[lane];
+        for (int q = p.hn_off[lo]; q < p.hn_off[lo + 1]; ++q) {
+          const int b = p.hn_part[q];
+          if (d < p.dist[b] && relax_to(p, b, d)) enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+        }
+      }
+    }
+    const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
+    for (i64 c = c0 + warp; c < c1; c += nwarp) {
+      const int el = p.g_idx[c];
+      const int s = p.e2n_off[el];
+      const int m = p.e2n_off[el + 1] - s;
+      for (int k = lane; k < m; k += 32) {
+        const int j = p.e2n_idx[s + k];
+        const double dj = p.dist[j];
+        const double xj = p.x[j], zj = p.z[j], Uj = p.U[j];
+        double best = dj;
+        for (int q = 0; q < ns; ++q) {
+          const double di = sd[q];
+          if (di >= dj) continue;  // di + w >= di >= dj: cannot improve
+          const double delta = edge_delta(di, sx[q], sz[q], sU[q], xj, zj, Uj);
+          best = delta < best ? delta : best;
+        }
+        if (best < dj && relax_to(p, j, best)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+      }
+      if (lane == 0) evals += (u64)m * (u64)ns;
+    }
+    if (threadIdx.x == 0) atomicAdd(&p.counters[3], (u64)ns);
+  }
+  if (lane == 0 && evals) atomicAdd(&p.counters[2], evals);
+}
+
+// threshold advance, step 1: smallest waiting value
+__global__ void far_min_kernel(PP p, const i32* __restrict__ far_cur, int fcur) {
+  const i64 slot = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  u64 best = ~0ull;
+  if (slot < (i64)p.counters[4 + fcur]) {
+    const int it = far_cur[slot];
+    const unsigned m = p.far_mask[it];
+    if ((m >> lane) & 1u) best = (u64)__double_as_longlong(p.dist[p.item_first[it] + lane]);
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 other = __shfl_xor_sync(FULL, best, o);
+    best = other < best ? other : best;
+  }
+  if (lane == 0 && best != ~0ull) atomicMin((u64*)&p.tau[2], best);
+}
+// step 2: tau = min + delta; release the waiting nodes below it, keep the others in the new far list
+__global__ void far_release_kernel(PP p, const i32* __restrict__ far_cur, int fcur, i32* __restrict__ far_next,
+                                   i32* __restrict__ near_next, int nxt) {
+  const i64 slot = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slot >= (i64)p.counters[4 + fcur]) return;
+  const double tau = __dadd_rn(p.tau[2], p.tau[1]);
+  const int it = far_cur[slot];
+  const unsigned m = p.far_mask[it];
+  const bool mine = (m >> lane) & 1u;
+  const bool rel = mine && p.dist[p.item_first[it] + lane] < tau;
+  const unsigned relm = __ballot_sync(FULL, rel);
+  if (lane == 0) {
+    const unsigned keep = m & ~relm;
+    p.far_mask[it] = keep;
+    if (keep)
+      far_next[atomicAdd(&p.counters[4 + (fcur ^ 1)], 1ull)] = it;
+    else
+      p.infar[it] = 0u;
+    if (relm) {
+      const unsigned old = atomicOr(&p.pend_mask[it], relm);
+      if (old == 0u) near_next[atomicAdd(&p.counters[nxt], 1ull)] = it;
+    }
+    if (slot == 0) p.tau[0] = tau;
+  }
+}
+
+__global__ void push_init_kernel(PP p, i64 n, int source, double delta, i32* __restrict__ near0) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    p.dist[i] = (i == source) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+    p.prev[i] = -1;
+  }
+  if (i == 0) {
+    const int it = p.node_item[source];
+    p.pend_mask[it] = 1u << (source - p.item_first[it]);
+    near0[0] = it;
+    p.counters[0] = 1ull;
+    p.tau[0] = delta;
+    p.tau[1] = delta;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- predecessors
+// pass 1: prev[i] = first candidate in scan order with dist[j] < dist[i] and dist[j] + w == dist[i] (bitwise).
+// Same (target, part) lane layout as the Jacobi relax kernel; parts are merged on the scan position.
+__global__ void __launch_bounds__(256) prev_tight_kernel(PP p, i64 n_items, int source, i32* __restrict__ unres) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  for (i64 it = (i64)blockIdx.x * wpb + (threadIdx.x >> 5); it < n_items; it += (i64)gridDim.x * wpb) {
+    const int v0 = p.item_first[it];
+    const int t = p.item_first[it + 1] - v0;
+    int lg = 0;
+    while ((1 << lg) < t) ++lg;
+    const int tl = 1 << lg, parts = 32 >> lg;
+    const int ti = lane & (tl - 1), part = lane >> lg;
+    const int i = v0 + min(ti, t - 1);
+    const double xi = p.x[i], zi = p.z[i], Ui = p.U[i], di = p.dist[i];
+    const bool want = di < INF && i != source;
+    int bpos = 0x7fffffff, bid = -1;
+    if (__any_sync(FULL, want)) {
+      int pos_base = 0;
+      const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
+      for (i64 c = c0; c < c1; ++c) {
+        const int el = p.g_idx[c];
+        const int s = p.e2n_off[el];
+        const int m = p.e2n_off[el + 1] - s;
+        for (int k = part; k < m; k += parts) {
+          const int j = p.e2n_idx[s + k];
+          const double dj = p.dist[j];
+          if (want && bid < 0 && dj < di) {
+            const double delta = edge_delta(dj, xi, zi, Ui, p.x[j], p.z[j], p.U[j]);
+            if (delta == di) {
+              bpos = pos_base + k;
+              bid = j;
+            }
+          }
+        }
+        pos_base += m;
+      }
+    }
+    for (int off = 16; off >= tl; off >>= 1) {
+      const int op = __shfl_xor_sync(FULL, bpos, off);
+      const int oi = __shfl_xor_sync(FULL, bid, off);
+      if (op < bpos) {
+        bpos = op;
+        bid = oi;
+      }
+    }
+    if (part == 0 && ti < t && want) {
+      if (bid >= 0)
+        p.prev[i] = bid;
+      else
+        unres[atomicAdd(&p.counters[6], 1ull)] = i;
+    }
+  }
+}
+
+// pass 2 (iterated): nodes without a strictly-earlier tight predecessor owe their value to a zero-weight
+// coupling: a halo twin (inherit ITS predecessor, as update_halo! does) or a coincident duplicate at equal
+// travel time (first one in scan order that is already resolved).
+__global__ void prev_resolve_kernel(PP p, const i32* __restrict__ unres, i64 n_unres, int source,
+                                    i32* __restrict__ unres_next, int* __restrict__ pending_prev) {
+  const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_unres) return;
+  const int i = unres[q];
+  const double di = p.dist[i];
+  int found = -1;
+  // (a) halo partners
+  if (p.n_hn > 0) {
+    int lo = 0, hi = p.n_hn;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (p.hn_node[mid] < i)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    if (lo < p.n_hn && p.hn_node[lo] == i)
+      for (int r = p.hn_off[lo]; r < p.hn_off[lo + 1] && found < 0; ++r) {
+        const int b = p.hn_part[r];
+        if (p.dist[b] == di) {
+          if (b == source)
+            found = source;
+          else if (p.prev[b] >= 0)
+            found = p.prev[b];
+        }
+      }
+  }
+  // (b) equal-time tight candidates (zero-weight edges between coincident nodes), scan order
+  if (found < 0) {
+    const double xi = p.x[i], zi = p.z[i], Ui = p.U[i];
+    for (i64 c = p.g_off[i]; c < p.g_off[i + 1] && found < 0; ++c) {
+      const int el = p.g_idx[c];
+      for (int k = p.e2n_off[el]; k < p.e2n_off[el + 1]; ++k) {
+        const int j = p.e2n_idx[k];
+        if (j == i || p.dist[j] != di) continue;
+        if (j != source && p.prev[j] < 0) continue;
+        if (edge_delta(di, xi, zi, Ui, p.x[j], p.z[j], p.U[j]) == di) {
+          found = j;
+          break;
+        }
+      }
+    }
+  }
+  if (found >= 0)
+    pending_prev[q] = found;  // applied after the kernel: all decisions of one iteration see the same state
+  else
+    pending_prev[q] = -1;
+  (void)unres_next;
+}
+__global__ void prev_apply_kernel(PP p, const i32* __restrict__ unres, i64 n_unres,
+                                  const int* __restrict__ pending_prev, i32* __restrict__ unres_next) {
+  const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_unres) return;
+  const int i = unres[q];
+  if (pending_prev[q] >= 0)
+    p.prev[i] = pending_prev[q];
+  else
+    unres_next[atomicAdd(&p.counters[7], 1ull)] = i;
+}
+__global__ void prev_halo_init_kernel(PP p, const i32* __restrict__ hnode, const i32* __restrict__ hval, i64 nh) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nh) p.prev[hnode[k]] = hval[k];
+}
+
+int ensure_push_workspace(rt_mesh* h) {
+  Mesh2D& m = *h->m2;
+  if (m.push_ready) return RT_OK;
+  cudaStream_t s = h->stream;
+  RT_TRY(m.node_item.alloc(m.n));
+  node_item_kernel<<<grid_for(m.n_items * 32, 256), 256, 0, s>>>(m.item_first.p, m.n_items, m.node_item.p);
+  RT_TRY(m.pend_mask.alloc(m.n_items));
+  RT_TRY(m.far_mask.alloc(m.n_items));
+  RT_TRY(m.infar_u.alloc(m.n_items));
+  RT_TRY(m.cur_mask.alloc(m.n_items));
+  for (int k = 0; k < 2; ++k) {
+    RT_TRY(m.nearq[k].alloc(m.n_items));
+    RT_TRY(m.farq[k].alloc(m.n_items));
+    RT_TRY(m.unresolved[k].alloc(m.n));
+  }
+  RT_TRY(m.pending_prev.alloc(m.n));
+  RT_TRY(m.tau.alloc(4));
+  RT_CUDA(cudaStreamSynchronize(s));
+  m.push_ready = true;
+  return RT_OK;
+}
+
+}  // namespace
+
+int bfm2d_ensure_workspace(rt_mesh* h);
+
+int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                     rt_stats* stats) {
+  Mesh2D& m = *h->m2;
+  cudaStream_t s = h->stream;
+  RT_TRY(bfm2d_ensure_workspace(h));
+  RT_TRY(ensure_push_workspace(h));
+  const i64 n = m.n;
+  PP p;
+  p.x = m.x.p;
+  p.z = m.z.p;
+  p.U = U_dev;
+  p.e2n_off = m.e2n_off.p;
+  p.e2n_idx = m.e2n_idx.p;
+  p.g_off = m.g_off.p;
+  p.g_idx = m.g_idx.p;
+  p.item_first = m.item_first.p;
+  p.node_item = m.node_item.p;
+  p.hn_node = m.hn_node.p;
+  p.hn_off = m.hn_off.p;
+  p.hn_part = m.hn_part.p;
+  p.n_hn = (int)m.n_hn;
+  p.dist = m.dist.p;
+  p.prev = m.prev.p;
+  p.pend_mask = m.pend_mask.p;
+  p.far_mask = m.far_mask.p;
+  p.infar = m.infar_u.p;
+  p.cur_mask = m.cur_mask.p;
+  p.counters = m.counters.p;
+  p.tau = m.tau.p;
+  u64* ch = m.counters_host;
+
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+  const i64 max_blocks = (i64)sm_count * 16;
+
+  cudaEvent_t ev0, ev1;
+  RT_CUDA(cudaEventCreate(&ev0));
+  RT_CUDA(cudaEventCreate(&ev1));
+  rt_stats st = {};
+  st.graph_edges = m.graph_edges;
+  int rc = RT_OK;
+
+  // bucket width: option "delta" [s], or delta_factor x (lightest consecutive-node edge)
+  double delta = h->opts.delta;
+  if (!(delta > 0.0)) {
+    RT_CUDA(cudaMemsetAsync(m.counters.p + 7, 0xff, sizeof(u64), s));
+    wmin_kernel<<<grid_for(m.nel * 32, 256), 256, 0, s>>>(p, m.nel, m.counters.p + 7);
+    u64 bits = 0;
+    RT_CUDA(cudaMemcpyAsync(&bits, m.counters.p + 7, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    RT_CUDA(cudaStreamSynchronize(s));
+    double wmin = 1.0;
+    if (bits != ~0ull) memcpy(&wmin, &bits, sizeof(double));
+    delta = wmin * (h->opts.delta_factor > 0.0 ? h->opts.delta_factor : 8.0);
+  }
+
+  for (i64 si = 0; si < nsrc && rc == RT_OK; ++si) {
+    const i64 src1 = sources[si];
+    if (src1 < 1 || src1 > n) {
+      rt_set_error("source %lld out of range 1..%lld", (long long)src1, (long long)n);
+      rc = RT_ERR_ARG;
+      break;
+    }
+    const int src = (int)(src1 - 1);
+    cudaEventRecord(ev0, s);
+    cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u64), s);
+    cudaMemsetAsync(m.pend_mask.p, 0, m.n_items * sizeof(unsigned), s);
+    cudaMemsetAsync(m.far_mask.p, 0, m.n_items * sizeof(unsigned), s);
+    cudaMemsetAsync(m.infar_u.p, 0, m.n_items * sizeof(unsigned), s);
+    push_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, src, delta, m.nearq[0].p);
+    st.total_launches += 1;
+    int cur = 0, fcur = 0;
+    i64 n_near = 1, n_far = 0;
+    i64 rounds = 0;
+    while (n_near > 0 || n_far > 0) {
+      const int nxt = cur ^ 1;
+      if (n_near > 0) {
+        cudaMemsetAsync(m.counters.p + nxt, 0, sizeof(u64), s);
+        prep_kernel<<<grid_for(n_near, 256), 256, 0, s>>>(p, m.nearq[cur].p, cur);
+        push2d_kernel<<<(unsigned)std::min<i64>(n_near, max_blocks), PUSH_BLOCK, 0, s>>>(
+            p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
+        st.total_launches += 2;
+        st.relax_launches += 1;
+        cur = nxt;
+      } else {
+        // advance the threshold: near list slot `cur` is empty and stays the target of the releases
+        cudaMemsetAsync(m.tau.p + 2, 0xff, sizeof(double), s);
+        cudaMemsetAsync(m.counters.p + 4 + (fcur ^ 1), 0, sizeof(u64), s);
+        cudaMemsetAsync(m.counters.p + cur, 0, sizeof(u64), s);
+        far_min_kernel<<<grid_for(n_far * 32, 256), 256, 0, s>>>(p, m.farq[fcur].p, fcur);
+        far_release_kernel<<<grid_for(n_far * 32, 256), 256, 0, s>>>(p, m.farq[fcur].p, fcur, m.farq[fcur ^ 1].p,
+                                                                     m.nearq[cur].p, cur);
+        st.total_launches += 2;
+        fcur ^= 1;
+      }
+      cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        rc = RT_ERR_CUDA;
+        break;
+      }
+      n_near = (i64)ch[cur];
+      n_far = (i64)ch[4 + fcur];
+      ++rounds;
+    }
+    if (rc != RT_OK) break;
+    st.sweeps += rounds;
+    st.relaxed_edges += (i64)ch[2];
+    st.vertex_updates += (i64)ch[3];
+    // ---- predecessors
+    if (m.n_hinit)
+      prev_halo_init_kernel<<<grid_for(m.n_hinit, 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p, m.n_hinit);
+    cudaMemsetAsync(m.counters.p + 6, 0, sizeof(u64), s);
+    prev_tight_kernel<<<(unsigned)std::min<i64>((m.n_items + 7) / 8, (i64)sm_count * 8), 256, 0, s>>>(
+        p, m.n_items, src, m.unresolved[0].p);
+    st.total_launches += 2;
+    st.relaxed_edges += m.graph_edges;  // the tightness pass walks every scan list once
+    cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      rc = RT_ERR_CUDA;
+      break;
+    }
+    i64 n_un = (i64)ch[6];
+    int ucur = 0;
+    for (int iter = 0; iter < 64 && n_un > 0; ++iter) {
+      cudaMemsetAsync(m.counters.p + 7, 0, sizeof(u64), s);
+      prev_resolve_kernel<<<grid_for(n_un, 128), 128, 0, s>>>(p, m.unresolved[ucur].p, n_un, src,
+                                                             m.unresolved[ucur ^ 1].p, m.pending_prev.p);
+      prev_apply_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un, m.pending_prev.p,
+                                                            m.unresolved[ucur ^ 1].p);
+      st.total_launches += 2;
+      cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        rc = RT_ERR_CUDA;
+        break;
+      }
+      const i64 left = (i64)ch[7];
+      ucur ^= 1;
+      if (left == n_un) break;  // no progress: the rest keeps its halo-init / unset predecessor
+      n_un = left;
+    }
+    if (rc != RT_OK) break;
+    cudaEventRecord(ev1, s);
+    if (dist_dev) cudaMemcpyAsync(dist_dev + si * n, m.dist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (prev_dev) cudaMemcpyAsync(prev_dev + si * n, m.prev.p, n * sizeof(i32), cudaMemcpyDeviceToDevice, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      rc = RT_ERR_CUDA;
+      break;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    st.kernel_ms += ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (rc == RT_ERR_CUDA || e != cudaSuccess) {
+    rt_set_error("CUDA failure in bfm2d_solve_push: %s", cudaGetErrorString(e));
+    rc = RT_ERR_CUDA;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (stats) *stats = st;
+  return rc;
+}

@@ -86,6 +86,7 @@ struct SolverOpts {
   int profile_timers = 0;  // 1: time the relax kernel with its own events (adds syncs)
   int check_every = 1;     // sweeps between host convergence checks
   double delta = 0.0;      // near-far bucket width [s]; 0 = automatic
+  double delta_factor = 0.0;  // automatic width = delta_factor x lightest edge (0 = default)
 };
 
 struct Mesh2D;

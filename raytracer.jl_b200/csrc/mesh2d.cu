@@ -233,6 +233,28 @@ int mesh2d_finalize(rt_mesh* h, const i64* halo_host) {
     RT_TRY(m.h2_twin.upload(tw.data(), tw.size(), s));
   }
   {
+    // zero-weight coupling partners of every halo node (row (a, b) lets a improve b), sorted by node, for the
+    // near-far schedule
+    std::vector<std::pair<i32, i32>> pr;
+    pr.reserve(R2);
+    for (i64 k = 0; k < R2; ++k) pr.push_back({h1[k], h2[k]});
+    std::sort(pr.begin(), pr.end());
+    pr.erase(std::unique(pr.begin(), pr.end()), pr.end());
+    std::vector<i32> nd, off, part;
+    for (size_t q = 0; q < pr.size(); ++q) {
+      if (nd.empty() || nd.back() != pr[q].first) {
+        nd.push_back(pr[q].first);
+        off.push_back((i32)q);
+      }
+      part.push_back(pr[q].second);
+    }
+    off.push_back((i32)pr.size());
+    m.n_hn = (i64)nd.size();
+    RT_TRY(m.hn_node.upload(nd.data(), nd.size(), s));
+    RT_TRY(m.hn_off.upload(off.data(), off.size(), s));
+    RT_TRY(m.hn_part.upload(part.data(), part.size(), s));
+  }
+  {
     // init_halo_path! (src/SSSP/bfm.jl:64-70) in serial row order; last writer wins
     std::map<i32, i32> init;
     for (i64 k = 0; k < R2; ++k) {

@@ -41,8 +41,22 @@ struct Mesh2D {
   DevBuf<u64> counters;  // [0],[1]: active counts (ping-pong); [2]: evals; [3]: vertex updates; [4]: improved flag
   u64* counters_host = nullptr;  // pinned
   bool ws_ready = false;
+  // ---- near-far (push) schedule
+  DevBuf<i32> node_item;               // node -> work item
+  DevBuf<unsigned> pend_mask, far_mask;  // per item: nodes with an unpropagated improvement (near / far)
+  DevBuf<unsigned> infar_u;            // per item: already in the far list
+  DevBuf<unsigned> cur_mask;           // per near-list slot: the nodes released this round
+  DevBuf<i32> nearq[2], farq[2];
+  DevBuf<i32> hn_node, hn_off, hn_part;  // halo partners: sorted unique nodes -> CSR of partner nodes
+  i64 n_hn = 0;
+  DevBuf<double> tau;                  // [0] current threshold, [1] delta, [2] min far dist (as u64 bits)
+  DevBuf<i32> unresolved[2];
+  DevBuf<int> pending_prev;
+  bool push_ready = false;
 };
 
 // Finishes a Mesh2D whose primary arrays (x,z,e2n_*,g_*) are already on the device: builds n2e, work items,
 // halo tables, E_graph.  halo_host: (2H x 2) column-major 1-based (may be null if halo_rows == 0).
 int mesh2d_finalize(rt_mesh* h, const i64* halo_host);
+int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                     rt_stats* stats);

@@ -260,3 +260,69 @@ def test_init_annulus_rejects_bad_arguments(rt):
     for args in ((4, 10, 20.0), (36, 1, 20.0), (36, 10, 0.0)):
         with pytest.raises(rt.RtError):
             rt.init_annulus(args[0], args[1], spacing=args[2])
+
+
+# ------------------------------------------------------------------------- near-far (work-efficient) schedule
+def check_prev_tie_aware(m, U, src, dist, prev_new, prev_ref):
+    """dist must be bit-identical; where prev differs from the reference it must still be a
+    bit-exactly tight predecessor (an exact tie), or a zero-weight coupling (halo twin / coincident node)."""
+    n = m.n
+    idx = np.arange(n)
+    p = prev_new - 1
+    reached = np.isfinite(dist) & (idx != src - 1)
+    assert np.all(p[reached] >= 0), "reached node without predecessor"
+    i = idx[reached]
+    j = p[reached]
+    w = weight2d(m.x, m.z, U, i, j)
+    tight = dist[j] + w == dist[i]
+    hm = m.halo_matrix() - 1 if m.halo_rows else np.zeros((0, 2), np.int64)
+    partner_of = {}
+    for a, b in hm:
+        partner_of.setdefault(int(b), []).append(int(a))
+    bad = []
+    for q in np.nonzero(~tight)[0]:
+        node = int(i[q])
+        # halo copy: inherits the predecessor of an equal-time twin (update_halo!)
+        ok = any(dist[t] == dist[node] and (prev_new[t] == prev_new[node] or t == src - 1 and prev_new[node] == src)
+                 for t in partner_of.get(node, []))
+        if not ok:
+            bad.append(node)
+    assert not bad, "non-tight predecessors at nodes %s" % bad[:10]
+    assert np.all(dist[j] <= dist[i])
+    same = int((prev_new == prev_ref).sum())
+    return same / n
+
+
+@pytest.mark.parametrize("nt,nr,sp", [(24, 6, 300.0), (36, 10, 100.0), (180, 50, 50.0)])
+def test_bfm2d_near_far_schedule(rt, O, annulus, ak135, nt, nr, sp):
+    m = annulus(nt, nr, sp)
+    gr, G, halo = adopt(rt, m)
+    Vp = O.interp_velocity(ak135[0], ak135[1], m.r)
+    src = O.closest_point(m.theta, m.r, 0.0, R)
+    dist, prev, st = O.bfm(m, Vp, src)
+    for delta in (None, 0.5, 50.0):
+        D = rt.bfm(G, halo, src, gr, Vp, schedule="near-far", delta=delta if delta else 0.0)
+        assert np.array_equal(D.dist, dist), "travel times must be bit-identical in any schedule"
+        frac = check_prev_tie_aware(m, Vp, src, dist, D.prev, prev)
+        assert frac > 0.3
+        # every reconstructed path reaches the source with non-increasing travel time
+        degs = np.arange(10, 351, 20).astype(np.float32)
+        for deg in degs:
+            rc = O.closest_point(m.theta, m.r, float(np.deg2rad(deg)), R)
+            path = rt.recontruct_path(D.prev, src, rc)
+            assert path[-1] == src and np.all(np.diff(dist[path - 1]) <= 0)
+        assert D.stats["relaxed_edges"] < st["relaxed_edges"]  # work-efficient
+    rt.bfm(G, halo, src, gr, Vp, schedule="jacobi")  # leave the cached handle in the default schedule
+
+
+def test_bfm2d_near_far_random_velocity_sources(rt, O, annulus):
+    m = annulus(36, 10, 100.0)
+    gr, G, halo = adopt(rt, m)
+    U = 4.0 + 6.0 * splitmix64(99, m.n)
+    srcs = np.array([1, m.n, m.n // 2, int(m.halo_matrix()[0, 0]), m.nr * m.ntheta + 1], np.int64)
+    D = rt.bfm(G, halo, srcs, gr, U, schedule="near-far")
+    for k, s in enumerate(srcs):
+        dist, prev, st = O.bfm(m, U, int(s))
+        assert np.array_equal(D.dist[k], dist), "source %d" % s
+        check_prev_tie_aware(m, U, int(s), dist, D.prev[k], prev)
+    rt.bfm(G, halo, 1, gr, U, schedule="jacobi")
