@@ -39,6 +39,7 @@ struct PP {
   const i32* __restrict__ hn_off;
   const i32* __restrict__ hn_part;
   int n_hn;
+  int source;  // the source never 'improves', so update_halo! never fires from it (bfm.jl:56)
   double* dist;
   i32* prev;
   unsigned* pend_mask;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __r
     const int ns = s_ns;
     if (ns == 0) continue;
     // zero-weight halo coupling (update_halo!): lane s of warp 0 serves source s
-    if (warp == 0 && p.n_hn > 0 && lane < ns) {
+    if (warp == 0 && p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {
       const int i = s_id[lane];
       int lo = 0, hi = p.n_hn;
       while (lo < hi) {
@@ -303,10 +304,12 @@ __global__ void __launch_bounds__(256) prev_tight_kernel(PP p, i64 n_items, int 
       }
     }
     if (part == 0 && ti < t && want) {
-      if (bid >= 0)
+      if (bid >= 0) {
         p.prev[i] = bid;
-      else
+      } else {
+        p.prev[i] = -2;  // reached but unresolved (overrides the halo-init value until pass 2 settles it)
         unres[atomicAdd(&p.counters[6], 1ull)] = i;
+      }
     }
   }
 }
@@ -374,6 +377,10 @@ __global__ void prev_apply_kernel(PP p, const i32* __restrict__ unres, i64 n_unr
   else
     unres_next[atomicAdd(&p.counters[7], 1ull)] = i;
 }
+__global__ void prev_giveup_kernel(PP p, const i32* __restrict__ unres, i64 n_unres) {
+  const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n_unres) p.prev[unres[q]] = -1;
+}
 __global__ void prev_halo_init_kernel(PP p, const i32* __restrict__ hnode, const i32* __restrict__ hval, i64 nh) {
   const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nh) p.prev[hnode[k]] = hval[k];
@@ -426,6 +433,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.hn_off = m.hn_off.p;
   p.hn_part = m.hn_part.p;
   p.n_hn = (int)m.n_hn;
+  p.source = -1;
   p.dist = m.dist.p;
   p.prev = m.prev.p;
   p.pend_mask = m.pend_mask.p;
@@ -468,6 +476,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       break;
     }
     const int src = (int)(src1 - 1);
+    p.source = src;
     cudaEventRecord(ev0, s);
     cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u64), s);
     cudaMemsetAsync(m.pend_mask.p, 0, m.n_items * sizeof(unsigned), s);
@@ -545,6 +554,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       n_un = left;
     }
     if (rc != RT_OK) break;
+    if (n_un > 0) prev_giveup_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un);
     cudaEventRecord(ev1, s);
     if (dist_dev) cudaMemcpyAsync(dist_dev + si * n, m.dist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
     if (prev_dev) cudaMemcpyAsync(prev_dev + si * n, m.prev.p, n * sizeof(i32), cudaMemcpyDeviceToDevice, s);
