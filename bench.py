@@ -43,7 +43,7 @@ WORKLOADS = {
     # BASELINE.json configs[2] mesh: annulus 720x200 default spacing
     "annulus_720_200_20km": dict(kind="2d", ntheta=720, nr=200, spacing=20.0, cpu=(720, 200, 20.0), dim=2),
 }
-DEFAULT_WORKLOAD = os.environ.get("RT_BENCH_WORKLOAD", "grid3d_216")
+DEFAULT_WORKLOAD = os.environ.get("RT_BENCH_WORKLOAD", "annulus_1440_400_0.25km")
 SHELL_C0 = (np.deg2rad(70.0), np.deg2rad(70.0), R - 2000.0)  # benchmarks/cpu.jl:9-13 rescaled to km
 SHELL_C1 = (np.deg2rad(110.0), np.deg2rad(110.0), R)
 
@@ -100,7 +100,7 @@ def ak135():
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 class GpuWorkload:
-    def __init__(self, name, rt, torch):
+    def __init__(self, name, rt, torch, schedule="near-far"):
         self.name, self.rt, self.torch = name, rt, torch
         self.w = WORKLOADS[name]
         prof = rt.velocity_profile()
@@ -134,6 +134,10 @@ class GpuWorkload:
         self.dist_dev = torch.empty(self.n, dtype=torch.float64, device="cuda")
         self.prev_dev = torch.empty(self.n, dtype=torch.int32, device="cuda")
         self.handle.set_option("profile_timers", 1)
+        self.schedule = schedule
+        self.handle.set_option("schedule", {"jacobi": 0, "near-far": 1}[schedule] if self.w["kind"] == "2d" else 0)
+        if self.w["kind"] == "3d":
+            self.schedule = "jacobi"
         # pinned host buffers of the end-to-end arm
         self.U_pin = torch.from_numpy(self.U_host).pin_memory()
         self.dist_pin = torch.empty(self.n, dtype=torch.float64).pin_memory()
@@ -172,7 +176,7 @@ def run_gpu(args):
     rt_loader.load_build().build()
     rt = rt_loader.load()
     rt.api.check(rt.lib().rt_set_device(local))
-    wl = GpuWorkload(args.workload, rt, torch)
+    wl = GpuWorkload(args.workload, rt, torch, args.schedule)
     n = wl.n
     gather_d = gather_p = None
     if dist_on:
@@ -244,7 +248,9 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "nodes": n, "graph_edges_per_source": e_graph,
-                       "sources_per_step_per_gpu": 1, "velocity": "AK135 Vp", "schedule": "jacobi (reference)",
+                       "sources_per_step_per_gpu": 1, "velocity": "AK135 Vp",
+                       "schedule": "jacobi (reference sweeps)" if wl.schedule == "jacobi" else
+                       "near-far push (dist bit-identical, prev exact except ties)",
                        "l2": "inputs larger than L2 (%.0f MB of node state per sweep set)" % (n * 48 / 1e6),
                        "parallelism": "source-sharded x%d, NCCL all_gather of tables" % world},
             "ms_per_source": wall_ms / args.steps,
@@ -261,7 +267,8 @@ def run_gpu(args):
                     "d2h_bytes_per_step": n * 16},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "relax3d_kernel" if wl.w["kind"] == "3d" else "relax2d_kernel",
+                         "kernel": "relax3d_kernel" if wl.w["kind"] == "3d" else
+                         ("relax2d_kernel" if wl.schedule == "jacobi" else "push2d_kernel"),
                          "bytes_model": "12 B per relaxed candidate + %d B per active-vertex update" % wl.bv,
                          "avg_launch_ms": relax_ms / max(acc["relax_launches"], 1)},
         }
@@ -343,6 +350,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--schedule", default="near-far", choices=["jacobi", "near-far"])
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

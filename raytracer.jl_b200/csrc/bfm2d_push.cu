@@ -68,26 +68,18 @@ __global__ void node_item_kernel(const i32* __restrict__ item_first, i64 n_items
   if (lane < t) node_item[v0 + lane] = (i32)it;
 }
 
-// smallest positive weight between consecutive entries of the element lists: proxy for the lightest edge
-__global__ void wmin_kernel(PP p, i64 nel, u64* __restrict__ out) {
-  const i64 w = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  u64 best = ~0ull;
-  if (w < nel) {
-    for (i32 q = p.e2n_off[w] + lane; q + 1 < p.e2n_off[w + 1]; q += 32) {
-      const int a = p.e2n_idx[q], b = p.e2n_idx[q + 1];
-      const double wt = edge_delta(0.0, p.x[a], p.z[a], p.U[a], p.x[b], p.z[b], p.U[b]);
-      if (wt > 0.0 && wt == wt) {
-        const u64 bits = (u64)__double_as_longlong(wt);
-        best = bits < best ? bits : best;
-      }
-    }
+// mean travel time across a cell (first to third node of every element = the diagonal of a quad): the scale
+// of the long edges of a star patch, used to size the near-far bucket automatically
+__global__ void wdiag_kernel(PP p, i64 nel, double* __restrict__ sum) {
+  const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  double wt = 0.0;
+  if (e < nel && p.e2n_off[e + 1] - p.e2n_off[e] >= 3) {
+    const int a = p.e2n_idx[p.e2n_off[e]], b = p.e2n_idx[p.e2n_off[e] + 2];
+    wt = edge_delta(0.0, p.x[a], p.z[a], p.U[a], p.x[b], p.z[b], p.U[b]);
+    if (!(wt == wt) || wt > 1e300) wt = 0.0;
   }
-  for (int o = 16; o; o >>= 1) {
-    const u64 other = __shfl_xor_sync(FULL, best, o);
-    best = other < best ? other : best;
-  }
-  if (lane == 0 && best != ~0ull) atomicMin(out, best);
+  for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(FULL, wt, o);
+  if ((threadIdx.x & 31) == 0 && wt > 0.0) atomicAdd(sum, wt);
 }
 
 // flag node j (whose value just improved to d) for propagation: near list if d < tau, else far list
@@ -448,24 +440,26 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
   const i64 max_blocks = (i64)sm_count * 16;
 
-  cudaEvent_t ev0, ev1;
+  cudaEvent_t ev0, ev1, evr0, evr1;
   RT_CUDA(cudaEventCreate(&ev0));
   RT_CUDA(cudaEventCreate(&ev1));
+  RT_CUDA(cudaEventCreate(&evr0));
+  RT_CUDA(cudaEventCreate(&evr1));
   rt_stats st = {};
   st.graph_edges = m.graph_edges;
   int rc = RT_OK;
+  const bool timers = h->opts.profile_timers != 0;
 
   // bucket width: option "delta" [s], or delta_factor x (lightest consecutive-node edge)
   double delta = h->opts.delta;
   if (!(delta > 0.0)) {
-    RT_CUDA(cudaMemsetAsync(m.counters.p + 7, 0xff, sizeof(u64), s));
-    wmin_kernel<<<grid_for(m.nel * 32, 256), 256, 0, s>>>(p, m.nel, m.counters.p + 7);
-    u64 bits = 0;
-    RT_CUDA(cudaMemcpyAsync(&bits, m.counters.p + 7, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    RT_CUDA(cudaMemsetAsync(m.tau.p + 3, 0, sizeof(double), s));
+    wdiag_kernel<<<grid_for(m.nel, 256), 256, 0, s>>>(p, m.nel, m.tau.p + 3);
+    double wsum = 0.0;
+    RT_CUDA(cudaMemcpyAsync(&wsum, m.tau.p + 3, sizeof(double), cudaMemcpyDeviceToHost, s));
     RT_CUDA(cudaStreamSynchronize(s));
-    double wmin = 1.0;
-    if (bits != ~0ull) memcpy(&wmin, &bits, sizeof(double));
-    delta = wmin * (h->opts.delta_factor > 0.0 ? h->opts.delta_factor : 8.0);
+    const double wmean = wsum > 0.0 ? wsum / (double)m.nel : 1.0;
+    delta = wmean * (h->opts.delta_factor > 0.0 ? h->opts.delta_factor : 1.0);
   }
 
   for (i64 si = 0; si < nsrc && rc == RT_OK; ++si) {
@@ -489,11 +483,15 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     i64 rounds = 0;
     while (n_near > 0 || n_far > 0) {
       const int nxt = cur ^ 1;
+      bool pushed = false;
       if (n_near > 0) {
         cudaMemsetAsync(m.counters.p + nxt, 0, sizeof(u64), s);
         prep_kernel<<<grid_for(n_near, 256), 256, 0, s>>>(p, m.nearq[cur].p, cur);
+        if (timers) cudaEventRecord(evr0, s);
         push2d_kernel<<<(unsigned)std::min<i64>(n_near, max_blocks), PUSH_BLOCK, 0, s>>>(
             p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
+        if (timers) cudaEventRecord(evr1, s);
+        pushed = true;
         st.total_launches += 2;
         st.relax_launches += 1;
         cur = nxt;
@@ -512,6 +510,11 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       if (cudaStreamSynchronize(s) != cudaSuccess) {
         rc = RT_ERR_CUDA;
         break;
+      }
+      if (timers && pushed) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evr0, evr1);
+        st.relax_ms += ms;
       }
       n_near = (i64)ch[cur];
       n_far = (i64)ch[4 + fcur];
@@ -573,6 +576,8 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   }
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
+  cudaEventDestroy(evr0);
+  cudaEventDestroy(evr1);
   if (stats) *stats = st;
   return rc;
 }
