@@ -55,7 +55,6 @@ __global__ void __launch_bounds__(RELAX_BLOCK) relax2d_kernel(P2 p, const i32* _
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const i64 n_active = (i64)p.counters[cur];
-  const double INF = __longlong_as_double(0x7ff0000000000000LL);
   u64 evals = 0, updates = 0;
   for (i64 w = (i64)blockIdx.x * wpb + (threadIdx.x >> 5); w < n_active; w += (i64)gridDim.x * wpb) {
     const int item = active[w];
@@ -81,8 +80,14 @@ __global__ void __launch_bounds__(RELAX_BLOCK) relax2d_kernel(P2 p, const i32* _
       for (int k = part; k < m; k += parts) {
         const int j = p.e2n_idx[s + k];
         const double dj = p.dist0[j];
+        if (!(dj < best)) continue;  // dj + w >= dj >= best (also dj == Inf)
         const double xj = p.x[j], zj = p.z[j], Uj = p.U[j];
-        const double delta = (dj == INF) ? INF : cand_delta(dj, xi, zi, Ui, xj, zj, Uj);
+        {
+          const double dx = __dsub_rn(xi, xj), dz = __dsub_rn(zi, zj);
+          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+          if (screen_cannot_improve(best, dj, d2, __dadd_rn(Ui, Uj))) continue;
+        }
+        const double delta = cand_delta(dj, xi, zi, Ui, xj, zj, Uj);
         if (delta < best) {
           best = delta;
           bpos = pos_base + k;

@@ -176,8 +176,14 @@ __global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __r
         double best = dj;
         for (int q = 0; q < ns; ++q) {
           const double di = sd[q];
-          if (di >= dj) continue;  // di + w >= di >= dj: cannot improve
-          const double delta = edge_delta(di, sx[q], sz[q], sU[q], xj, zj, Uj);
+          if (!(di < best)) continue;  // di + w >= di >= best: cannot improve
+          const double sxq = sx[q], szq = sz[q], sUq = sU[q];
+          {
+            const double dx = __dsub_rn(sxq, xj), dz = __dsub_rn(szq, zj);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+            if (screen_cannot_improve(best, di, d2, __dadd_rn(sUq, Uj))) continue;
+          }
+          const double delta = edge_delta(di, sxq, szq, sUq, xj, zj, Uj);
           best = delta < best ? delta : best;
         }
         if (best < dj && relax_to(p, j, best)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
@@ -277,7 +283,11 @@ __global__ void __launch_bounds__(256) prev_tight_kernel(PP p, i64 n_items, int 
           const int j = p.e2n_idx[s + k];
           const double dj = p.dist[j];
           if (want && bid < 0 && dj < di) {
-            const double delta = edge_delta(dj, xi, zi, Ui, p.x[j], p.z[j], p.U[j]);
+            const double xj = p.x[j], zj = p.z[j], Uj = p.U[j];
+            const double dx = __dsub_rn(xi, xj), dz = __dsub_rn(zi, zj);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+            if (!screen_maybe_tight(di, dj, d2, __dadd_rn(Ui, Uj))) continue;
+            const double delta = edge_delta(dj, xi, zi, Ui, xj, zj, Uj);
             if (delta == di) {
               bpos = pos_base + k;
               bid = j;

@@ -77,6 +77,37 @@ struct DevBuf {
   }
 };
 
+#if defined(__CUDACC__)
+// Algebraic screen (no sqrt, no division): is  d_from + w  >= bound  guaranteed, where the edge weight is
+// w = 2*sqrt(d2)/ssum (2-D: (2.0*len)/(Ui+Uj); 3-D: len*(1/|Ui+Uj|)*2, both within 3 roundings of the real value)?
+//   w >= t  <=>  d2 >= (t*ssum/2)^2   with t = bound - d_from.
+// Slack: 4e-15*bound absorbs the rounding of (bound - d_from) and of the final fl(d_from + w); the factor
+// (1 + 1e-9) absorbs the roundings of the products and of w itself.  A `true` answer is exact-safe: the
+// candidate can be skipped without changing any result; `false` means "evaluate exactly".
+__device__ __forceinline__ bool screen_cannot_improve(double bound, double d_from, double d2, double ssum) {
+  const double t = bound - d_from;
+  if (!(t > 0.0)) return true;  // d_from >= bound (w >= 0), or Inf - Inf
+  if (!(ssum > 0.0)) return false;
+  const double ts = (t + bound * 4e-15) * ssum * 0.5;
+  return d2 > ts * ts * (1.0 + 1e-9);
+}
+// Can fl(d_from + w) == target hold?  false => certainly not tight.
+__device__ __forceinline__ bool screen_maybe_tight(double target, double d_from, double d2, double ssum) {
+  const double t = target - d_from;
+  if (!(t >= 0.0)) return false;
+  if (!(ssum > 0.0)) return true;
+  const double slack = target * 4e-15;
+  const double hi = (t + slack) * ssum * 0.5;
+  if (d2 > hi * hi * (1.0 + 1e-9)) return false;
+  const double tl = t - slack;
+  if (tl > 0.0) {
+    const double lo = tl * ssum * 0.5;
+    if (d2 < lo * lo * (1.0 - 1e-9)) return false;
+  }
+  return true;
+}
+#endif
+
 inline unsigned grid_for(i64 work, int block) { return (unsigned)((work + block - 1) / block); }
 
 // ---------------------------------------------------------------------------------------------------------

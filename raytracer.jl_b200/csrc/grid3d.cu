@@ -112,7 +112,6 @@ __global__ void __launch_bounds__(TILE_THREADS) relax3d_kernel(P3 p, const i32* 
   double* sU = sZ + SN;
   double* sD = sU + SN;
   const i64 n_active = (i64)p.counters[cur];
-  const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const int tid = threadIdx.x;
   const int lx = tid % TX, ly = (tid / TX) % TY, lz = tid / (TX * TY);
   u64 evals = 0, updates = 0;
@@ -151,7 +150,14 @@ __global__ void __launch_bounds__(TILE_THREADS) relax3d_kernel(P3 p, const i32* 
             const int c = rowc + xx;
             if (!p.self && c == ci) continue;
             const double dj = sD[c];
-            const double delta = (dj == INF) ? INF : cand3(dj, xi, yi, zi, ui, sX[c], sY[c], sZ[c], sU[c]);
+            if (!(dj < best)) continue;  // dj + w >= dj >= best (also dj == Inf)
+            const double xj = sX[c], yj = sY[c], zj = sZ[c], uj = sU[c];
+            {
+              const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
+              const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+              if (screen_cannot_improve(best, dj, d2, fabs(__dadd_rn(ui, uj)))) continue;
+            }
+            const double delta = cand3(dj, xi, yi, zi, ui, xj, yj, zj, uj);
             if (delta < best) {
               best = delta;
               bid = (i64)xx + (i64)p.nx * ((i64)yy + (i64)p.ny * zz);
