@@ -133,7 +133,7 @@ class GpuWorkload:
         self.U_dev = torch.from_numpy(self.U_host).cuda()
         self.dist_dev = torch.empty(self.n, dtype=torch.float64, device="cuda")
         self.prev_dev = torch.empty(self.n, dtype=torch.int32, device="cuda")
-        self.handle.set_option("profile_timers", 1)
+        self.handle.set_option("profile_timers", 0)
         self.schedule = schedule
         self.handle.set_option("schedule", {"jacobi": 0, "near-far": 1}[schedule] if self.w["kind"] == "2d" else 0)
         if self.w["kind"] == "3d":
@@ -221,6 +221,17 @@ def run_gpu(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     wall_ms, dev_ms = float(times[0]), float(times[1])
 
+    # roofline pass: same step with per-launch CUDA-event timers around the relaxation kernel (the timers force a
+    # host sync per round, so they stay out of the timed region above)
+    wl.handle.set_option("profile_timers", 1)
+    prof = dict(relaxed_edges=0, vertex_updates=0, relax_ms=0.0, relax_launches=0, kernel_ms=0.0)
+    prof_steps = max(1, min(args.steps, 2))
+    for k in range(prof_steps):
+        st = wl.solve_dev(wl.sources[0])
+        for key in prof:
+            prof[key] += st[key]
+    wl.handle.set_option("profile_timers", 0)
+
     # end-to-end arm: same step through the host-buffer ABI call (H2D + D2H inside the timed region)
     e2e_steps = max(1, min(args.steps, 3))
     wl.solve_e2e(wl.sources[0])
@@ -239,8 +250,10 @@ def run_gpu(args):
         peak, peak_src = peaks()
         nsolved = args.steps * world
         value = e_graph * nsolved / (wall_ms * 1e-3) / 1e9
-        bytes_alg = acc["relaxed_edges"] * 12 + acc["vertex_updates"] * wl.bv
-        relax_ms = max(acc["relax_ms"], 1e-9)
+        bytes_alg = prof["relaxed_edges"] * 12 + prof["vertex_updates"] * wl.bv
+        if wl.schedule != "jacobi":  # the tightness (prev) pass is counted in relaxed_edges but not in relax_ms
+            bytes_alg -= e_graph * prof_steps * 12
+        relax_ms = max(prof["relax_ms"], 1e-9)
         achieved = bytes_alg / (relax_ms * 1e-3) / 1e9
         out = {
             "metric": "sssp_relaxed_edges_per_s", "value": value, "unit": "GTEPS", "n_gpus": world,
@@ -256,10 +269,10 @@ def run_gpu(args):
             "ms_per_source": wall_ms / args.steps,
             "device_ms_per_step": dev_ms / args.steps,
             "teps_graph_gteps": value,
-            "relax_rate_gteps": acc["relaxed_edges"] / (relax_ms * 1e-3) / 1e9,
+            "relax_rate_gteps": (bytes_alg / 12.0) / (relax_ms * 1e-3) / 1e9,
             "relaxed_edges_per_source": acc["relaxed_edges"] / args.steps,
             "sweeps_per_source": acc["sweeps"] / args.steps,
-            "relax_kernel_share_of_step": relax_ms / max(dev_ms, 1e-9),
+            "relax_kernel_share_of_step": relax_ms / max(prof["kernel_ms"], 1e-9),
             "gpu_launches": acc["total_launches"],
             "clocks": clocks,
             "e2e": {"value": e_graph * e2e_steps * world / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS",
@@ -270,7 +283,7 @@ def run_gpu(args):
                          "kernel": "relax3d_kernel" if wl.w["kind"] == "3d" else
                          ("relax2d_kernel" if wl.schedule == "jacobi" else "push2d_kernel"),
                          "bytes_model": "12 B per relaxed candidate + %d B per active-vertex update" % wl.bv,
-                         "avg_launch_ms": relax_ms / max(acc["relax_launches"], 1)},
+                         "avg_launch_ms": relax_ms / max(prof["relax_launches"], 1)},
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.workload, steps=1)

@@ -216,7 +216,7 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
   } else if (!std::strcmp(key, "profile_timers")) {
     m->opts.profile_timers = value != 0.0;
   } else if (!std::strcmp(key, "check_every")) {
-    RT_ARG(value >= 1.0 && value <= 1024.0, "check_every must be in 1..1024");
+    RT_ARG(value >= 0.0 && value <= 1024.0, "check_every must be in 0..1024");
     m->opts.check_every = (int)value;
   } else if (!std::strcmp(key, "delta")) {
     RT_ARG(value >= 0.0, "delta must be >= 0");

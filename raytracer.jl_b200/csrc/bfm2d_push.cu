@@ -49,6 +49,10 @@ struct PP {
   u64* counters;  // [0],[1] near counts (ping-pong) [2] evals [3] releases [4],[5] far counts (ping-pong)
                   // [6] unresolved count [7] scratch
   double* tau;    // [0] tau [1] delta [2] min far (bits)
+  i32* nearq[2];
+  i32* farq[2];
+  int* ctl;       // device-side round control: [0] cur [1] fcur [2] mode (1 push, 2 advance) [3] done [4] rounds
+                  // [5] push rounds
 };
 
 __device__ __forceinline__ double edge_delta(double di, double xi, double zi, double Ui, double xj, double zj,
@@ -113,9 +117,8 @@ __global__ void prep_kernel(PP p, const i32* __restrict__ near_cur, int cur) {
 }
 
 // round step 2: one CTA per released item; warps split the elements of its G column; lanes = targets.
-__global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
-                                                           i32* __restrict__ near_next, i32* __restrict__ far_list,
-                                                           int fcur) {
+__device__ __forceinline__ void push2d_body(const PP& p, const i32* __restrict__ near_cur, int cur,
+                                            i32* __restrict__ near_next, i32* __restrict__ far_list, int fcur) {
   __shared__ double sx[32], sz[32], sU[32], sd[32];
   __shared__ int s_id[32];
   __shared__ int s_ns;
@@ -193,6 +196,11 @@ __global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __r
     if (threadIdx.x == 0) atomicAdd(&p.counters[3], (u64)ns);
   }
   if (lane == 0 && evals) atomicAdd(&p.counters[2], evals);
+}
+__global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
+                                                           i32* __restrict__ near_next, i32* __restrict__ far_list,
+                                                           int fcur) {
+  push2d_body(p, near_cur, cur, near_next, far_list, fcur);
 }
 
 // threshold advance, step 1: smallest waiting value
@@ -388,6 +396,101 @@ __global__ void prev_halo_init_kernel(PP p, const i32* __restrict__ hnode, const
   if (k < nh) p.prev[hnode[k]] = hval[k];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Device-controlled rounds: the host enqueues a fixed sequence of launches per round and only synchronises every
+// `check_every` rounds; which phase runs (push / threshold advance / nothing) is decided on the device.
+__global__ void round_begin_kernel(PP p) {
+  int* c = p.ctl;
+  if (c[3]) return;
+  if (c[2] == 1)
+    c[0] ^= 1;
+  else if (c[2] == 2)
+    c[1] ^= 1;
+  const int cur = c[0], fcur = c[1];
+  const u64 n_near = p.counters[cur], n_far = p.counters[4 + fcur];
+  if (n_near == 0 && n_far == 0) {
+    c[2] = 0;
+    c[3] = 1;
+    return;
+  }
+  c[4] += 1;
+  if (n_near > 0) {
+    c[2] = 1;
+    c[5] += 1;
+    p.counters[cur ^ 1] = 0;
+  } else {
+    c[2] = 2;
+    p.tau[2] = __longlong_as_double(-1LL);
+    p.counters[4 + (fcur ^ 1)] = 0;
+  }
+}
+__global__ void prep_dc_kernel(PP p) {
+  if (p.ctl[2] != 1) return;
+  const int cur = p.ctl[0];
+  const i32* near_cur = p.nearq[cur];
+  const i64 n = (i64)p.counters[cur];
+  for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (i64)gridDim.x * blockDim.x)
+    p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
+}
+__global__ void __launch_bounds__(PUSH_BLOCK) push2d_dc_kernel(PP p) {
+  if (p.ctl[2] != 1) return;
+  const int cur = p.ctl[0], fcur = p.ctl[1];
+  push2d_body(p, p.nearq[cur], cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
+}
+__global__ void far_min_dc_kernel(PP p) {
+  if (p.ctl[2] != 2) return;
+  const int fcur = p.ctl[1];
+  const i32* far_cur = p.farq[fcur];
+  const i64 nslots = (i64)p.counters[4 + fcur];
+  const int lane = threadIdx.x & 31;
+  u64 best = ~0ull;
+  for (i64 slot = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < nslots;
+       slot += ((i64)gridDim.x * blockDim.x) >> 5) {
+    const int it = far_cur[slot];
+    const unsigned m = p.far_mask[it];
+    if ((m >> lane) & 1u) {
+      const u64 b = (u64)__double_as_longlong(p.dist[p.item_first[it] + lane]);
+      best = b < best ? b : best;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 other = __shfl_xor_sync(FULL, best, o);
+    best = other < best ? other : best;
+  }
+  if (lane == 0 && best != ~0ull) atomicMin((u64*)&p.tau[2], best);
+}
+__global__ void far_release_dc_kernel(PP p) {
+  if (p.ctl[2] != 2) return;
+  const int cur = p.ctl[0], fcur = p.ctl[1];
+  const i32* far_cur = p.farq[fcur];
+  i32* far_next = p.farq[fcur ^ 1];
+  i32* near_next = p.nearq[cur];
+  const i64 nslots = (i64)p.counters[4 + fcur];
+  const int lane = threadIdx.x & 31;
+  const double tau = __dadd_rn(p.tau[2], p.tau[1]);
+  for (i64 slot = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < nslots;
+       slot += ((i64)gridDim.x * blockDim.x) >> 5) {
+    const int it = far_cur[slot];
+    const unsigned m = p.far_mask[it];
+    const bool mine = (m >> lane) & 1u;
+    const bool rel = mine && p.dist[p.item_first[it] + lane] < tau;
+    const unsigned relm = __ballot_sync(FULL, rel);
+    if (lane == 0) {
+      const unsigned keep = m & ~relm;
+      p.far_mask[it] = keep;
+      if (keep)
+        far_next[atomicAdd(&p.counters[4 + (fcur ^ 1)], 1ull)] = it;
+      else
+        p.infar[it] = 0u;
+      if (relm) {
+        const unsigned old = atomicOr(&p.pend_mask[it], relm);
+        if (old == 0u) near_next[atomicAdd(&p.counters[cur], 1ull)] = it;
+      }
+      if (slot == 0) p.tau[0] = tau;
+    }
+  }
+}
+
 int ensure_push_workspace(rt_mesh* h) {
   Mesh2D& m = *h->m2;
   if (m.push_ready) return RT_OK;
@@ -405,6 +508,7 @@ int ensure_push_workspace(rt_mesh* h) {
   }
   RT_TRY(m.pending_prev.alloc(m.n));
   RT_TRY(m.tau.alloc(4));
+  RT_TRY(m.ctl.alloc(8));
   RT_CUDA(cudaStreamSynchronize(s));
   m.push_ready = true;
   return RT_OK;
@@ -444,6 +548,11 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.cur_mask = m.cur_mask.p;
   p.counters = m.counters.p;
   p.tau = m.tau.p;
+  p.nearq[0] = m.nearq[0].p;
+  p.nearq[1] = m.nearq[1].p;
+  p.farq[0] = m.farq[0].p;
+  p.farq[1] = m.farq[1].p;
+  p.ctl = m.ctl.p;
   u64* ch = m.counters_host;
 
   int sm_count = 148;
@@ -488,47 +597,74 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     cudaMemsetAsync(m.infar_u.p, 0, m.n_items * sizeof(unsigned), s);
     push_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, src, delta, m.nearq[0].p);
     st.total_launches += 1;
-    int cur = 0, fcur = 0;
-    i64 n_near = 1, n_far = 0;
     i64 rounds = 0;
-    while (n_near > 0 || n_far > 0) {
-      const int nxt = cur ^ 1;
-      bool pushed = false;
-      if (n_near > 0) {
-        cudaMemsetAsync(m.counters.p + nxt, 0, sizeof(u64), s);
-        prep_kernel<<<grid_for(n_near, 256), 256, 0, s>>>(p, m.nearq[cur].p, cur);
-        if (timers) cudaEventRecord(evr0, s);
-        push2d_kernel<<<(unsigned)std::min<i64>(n_near, max_blocks), PUSH_BLOCK, 0, s>>>(
-            p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
-        if (timers) cudaEventRecord(evr1, s);
-        pushed = true;
-        st.total_launches += 2;
-        st.relax_launches += 1;
-        cur = nxt;
-      } else {
-        // advance the threshold: near list slot `cur` is empty and stays the target of the releases
-        cudaMemsetAsync(m.tau.p + 2, 0xff, sizeof(double), s);
-        cudaMemsetAsync(m.counters.p + 4 + (fcur ^ 1), 0, sizeof(u64), s);
-        cudaMemsetAsync(m.counters.p + cur, 0, sizeof(u64), s);
-        far_min_kernel<<<grid_for(n_far * 32, 256), 256, 0, s>>>(p, m.farq[fcur].p, fcur);
-        far_release_kernel<<<grid_for(n_far * 32, 256), 256, 0, s>>>(p, m.farq[fcur].p, fcur, m.farq[fcur ^ 1].p,
-                                                                     m.nearq[cur].p, cur);
-        st.total_launches += 2;
-        fcur ^= 1;
+    if (!timers) {
+      // device-controlled rounds, host sync every `check_every` rounds
+      const int R = h->opts.check_every > 1 ? h->opts.check_every : 32;
+      const unsigned gsmall = (unsigned)(sm_count * 2);
+      cudaMemsetAsync(m.ctl.p, 0, 8 * sizeof(int), s);
+      int hctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      while (!hctl[3]) {
+        for (int r = 0; r < R; ++r) {
+          round_begin_kernel<<<1, 1, 0, s>>>(p);
+          prep_dc_kernel<<<gsmall, 256, 0, s>>>(p);
+          push2d_dc_kernel<<<(unsigned)max_blocks, PUSH_BLOCK, 0, s>>>(p);
+          far_min_dc_kernel<<<gsmall, 256, 0, s>>>(p);
+          far_release_dc_kernel<<<gsmall, 256, 0, s>>>(p);
+        }
+        cudaMemcpyAsync(hctl, m.ctl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) {
+          rc = RT_ERR_CUDA;
+          break;
+        }
       }
+      rounds = hctl[4];
+      st.total_launches += 2 * (i64)hctl[4];  // launches that did work: (prep, push) or (min, release)
+      st.relax_launches += hctl[5];
       cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
-      if (cudaStreamSynchronize(s) != cudaSuccess) {
-        rc = RT_ERR_CUDA;
-        break;
+      if (rc == RT_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = RT_ERR_CUDA;
+    } else {
+      int cur = 0, fcur = 0;
+      i64 n_near = 1, n_far = 0;
+      while (n_near > 0 || n_far > 0) {
+        const int nxt = cur ^ 1;
+        bool pushed = false;
+        if (n_near > 0) {
+          cudaMemsetAsync(m.counters.p + nxt, 0, sizeof(u64), s);
+          prep_kernel<<<grid_for(n_near, 256), 256, 0, s>>>(p, m.nearq[cur].p, cur);
+          if (timers) cudaEventRecord(evr0, s);
+          push2d_kernel<<<(unsigned)std::min<i64>(n_near, max_blocks), PUSH_BLOCK, 0, s>>>(
+              p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
+          if (timers) cudaEventRecord(evr1, s);
+          pushed = true;
+          st.total_launches += 2;
+          st.relax_launches += 1;
+          cur = nxt;
+        } else {
+          // advance the threshold: near list slot `cur` is empty and stays the target of the releases
+          cudaMemsetAsync(m.tau.p + 2, 0xff, sizeof(double), s);
+          cudaMemsetAsync(m.counters.p + 4 + (fcur ^ 1), 0, sizeof(u64), s);
+          cudaMemsetAsync(m.counters.p + cur, 0, sizeof(u64), s);
+          far_min_kernel<<<grid_for(n_far * 32, 256), 256, 0, s>>>(p, m.farq[fcur].p, fcur);
+          far_release_kernel<<<grid_for(n_far * 32, 256), 256, 0, s>>>(p, m.farq[fcur].p, fcur, m.farq[fcur ^ 1].p,
+                                                                       m.nearq[cur].p, cur);
+          st.total_launches += 2;
+          fcur ^= 1;
+        }
+        cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) {
+          rc = RT_ERR_CUDA;
+          break;
+        }
+        if (timers && pushed) {
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, evr0, evr1);
+          st.relax_ms += ms;
+        }
+        n_near = (i64)ch[cur];
+        n_far = (i64)ch[4 + fcur];
+        ++rounds;
       }
-      if (timers && pushed) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, evr0, evr1);
-        st.relax_ms += ms;
-      }
-      n_near = (i64)ch[cur];
-      n_far = (i64)ch[4 + fcur];
-      ++rounds;
     }
     if (rc != RT_OK) break;
     st.sweeps += rounds;

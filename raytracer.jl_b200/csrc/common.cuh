@@ -115,7 +115,7 @@ inline unsigned grid_for(i64 work, int block) { return (unsigned)((work + block 
 struct SolverOpts {
   int schedule = 0;        // 0 = Jacobi sweeps (reference schedule), 1 = near-far work-efficient
   int profile_timers = 0;  // 1: time the relax kernel with its own events (adds syncs)
-  int check_every = 1;     // sweeps between host convergence checks
+  int check_every = 0;     // rounds between host convergence checks (0 = default)
   double delta = 0.0;      // near-far bucket width [s]; 0 = automatic
   double delta_factor = 0.0;  // automatic width = delta_factor x lightest edge (0 = default)
 };

@@ -52,6 +52,7 @@ struct Mesh2D {
   DevBuf<double> tau;                  // [0] current threshold, [1] delta, [2] min far dist (as u64 bits)
   DevBuf<i32> unresolved[2];
   DevBuf<int> pending_prev;
+  DevBuf<int> ctl;
   bool push_ready = false;
 };
 
