@@ -221,6 +221,8 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
   } else if (!std::strcmp(key, "delta")) {
     RT_ARG(value >= 0.0, "delta must be >= 0");
     m->opts.delta = value;
+  } else if (!std::strcmp(key, "persistent")) {
+    m->opts.persistent = value != 0.0;
   } else if (!std::strcmp(key, "delta_factor")) {
     RT_ARG(value >= 0.0, "delta_factor must be >= 0");
     m->opts.delta_factor = value;

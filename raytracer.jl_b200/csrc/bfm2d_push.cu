@@ -18,7 +18,11 @@
 // bit-exactly tight (dist[j] + w == dist[i]) with dist[j] < dist[i]; nodes that owe their value to a
 // zero-weight coupling (twins, coincident duplicates) inherit along that coupling.  This equals the
 // reference's prev except on exact ties (which are systematic on these meshes: every radial edge exists twice).
+#include <cooperative_groups.h>
+
 #include "mesh2d.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -94,7 +98,7 @@ __device__ __forceinline__ void enqueue(const PP& p, int j, double d, double tau
   if (d < tau) {
     const unsigned old = atomicOr(&p.pend_mask[it], bit);
     if (old == 0u) near_next[atomicAdd(&p.counters[nxt], 1ull)] = it;
-    if (p.far_mask[it] & bit) atomicAnd(&p.far_mask[it], ~bit);
+    if (__ldcg(&p.far_mask[it]) & bit) atomicAnd(&p.far_mask[it], ~bit);
   } else {
     atomicOr(&p.far_mask[it], bit);
     if (atomicExch(&p.infar[it], 1u) == 0u) far_list[atomicAdd(&p.counters[4 + fcur], 1ull)] = it;
@@ -117,18 +121,20 @@ __global__ void prep_kernel(PP p, const i32* __restrict__ near_cur, int cur) {
 }
 
 // round step 2: one CTA per released item; warps split the elements of its G column; lanes = targets.
-__device__ __forceinline__ void push2d_body(const PP& p, const i32* __restrict__ near_cur, int cur,
-                                            i32* __restrict__ near_next, i32* __restrict__ far_list, int fcur) {
+// All state that another SM may have written in an earlier phase of the SAME launch (persistent kernel) is read
+// with ld.global.cg (L2) so that a stale L1 line can never hide an update; mesh arrays are read-only.
+__device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
+                                            i32* far_list, int fcur) {
   __shared__ double sx[32], sz[32], sU[32], sd[32];
   __shared__ int s_id[32];
   __shared__ int s_ns;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const i64 n_near = (i64)p.counters[cur];
-  const double tau = p.tau[0];
+  const i64 n_near = (i64)__ldcg(&p.counters[cur]);
+  const double tau = __ldcg(&p.tau[0]);
   u64 evals = 0;
   for (i64 slot = blockIdx.x; slot < n_near; slot += gridDim.x) {
-    const int it = near_cur[slot];
-    const unsigned mask = p.cur_mask[slot];
+    const int it = __ldcg(&near_cur[slot]);
+    const unsigned mask = __ldcg(&p.cur_mask[slot]);
     const int v0 = p.item_first[it];
     __syncthreads();  // smem reuse across slots
     if (warp == 0) {
@@ -140,7 +146,7 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* __restrict__
         sx[pos] = p.x[i];
         sz[pos] = p.z[i];
         sU[pos] = p.U[i];
-        sd[pos] = p.dist[i];
+        sd[pos] = __ldcg(&p.dist[i]);
         s_id[pos] = i;
       }
       if (lane == 0) s_ns = __popc(mask);
@@ -163,7 +169,7 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* __restrict__
         const double d = sd[lane];
         for (int q = p.hn_off[lo]; q < p.hn_off[lo + 1]; ++q) {
           const int b = p.hn_part[q];
-          if (d < p.dist[b] && relax_to(p, b, d)) enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+          if (d < __ldcg(&p.dist[b]) && relax_to(p, b, d)) enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
         }
       }
     }
@@ -174,7 +180,7 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* __restrict__
       const int m = p.e2n_off[el + 1] - s;
       for (int k = lane; k < m; k += 32) {
         const int j = p.e2n_idx[s + k];
-        const double dj = p.dist[j];
+        const double dj = __ldcg(&p.dist[j]);
         const double xj = p.x[j], zj = p.z[j], Uj = p.U[j];
         double best = dj;
         for (int q = 0; q < ns; ++q) {
@@ -491,6 +497,97 @@ __global__ void far_release_dc_kernel(PP p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant: ONE cooperative launch runs up to `max_rounds` rounds; phases are separated by grid-wide
+// barriers instead of kernel boundaries (a round costs two or three grid.sync() instead of ~5 launches).
+__global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP p, int max_rounds) {
+  cg::grid_group grid = cg::this_grid();
+  const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+  const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 gsize = (i64)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  int cur = p.ctl[0], fcur = p.ctl[1];
+  int rounds = 0, pushes = 0, done = 0;
+  for (int r = 0; r < max_rounds; ++r) {
+    const i64 n_near = (i64)__ldcg(&p.counters[cur]);
+    const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
+    if (n_near == 0 && n_far == 0) {
+      done = 1;
+      break;
+    }
+    ++rounds;
+    if (n_near > 0) {
+      if (first) p.counters[cur ^ 1] = 0;
+      const i32* near_cur = p.nearq[cur];
+      for (i64 slot = gtid; slot < n_near; slot += gsize)
+        p.cur_mask[slot] = atomicExch(&p.pend_mask[__ldcg(&near_cur[slot])], 0u);
+      grid.sync();
+      push2d_body(p, near_cur, cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
+      grid.sync();
+      cur ^= 1;
+      ++pushes;
+    } else {
+      if (first) {
+        p.tau[2] = __longlong_as_double(-1LL);
+        p.counters[4 + (fcur ^ 1)] = 0;
+      }
+      grid.sync();
+      const i32* far_cur = p.farq[fcur];
+      {
+        u64 best = ~0ull;
+        for (i64 slot = gtid >> 5; slot < n_far; slot += gsize >> 5) {
+          const int it = __ldcg(&far_cur[slot]);
+          const unsigned m = __ldcg(&p.far_mask[it]);
+          if ((m >> lane) & 1u) {
+            const u64 b = (u64)__double_as_longlong(__ldcg(&p.dist[p.item_first[it] + lane]));
+            best = b < best ? b : best;
+          }
+        }
+        for (int o = 16; o; o >>= 1) {
+          const u64 other = __shfl_xor_sync(FULL, best, o);
+          best = other < best ? other : best;
+        }
+        if (lane == 0 && best != ~0ull) atomicMin((u64*)&p.tau[2], best);
+      }
+      grid.sync();
+      {
+        const double tau = __dadd_rn(__ldcg(&p.tau[2]), __ldcg(&p.tau[1]));
+        i32* far_next = p.farq[fcur ^ 1];
+        i32* near_next = p.nearq[cur];
+        for (i64 slot = gtid >> 5; slot < n_far; slot += gsize >> 5) {
+          const int it = __ldcg(&far_cur[slot]);
+          const unsigned m = __ldcg(&p.far_mask[it]);
+          const bool mine = (m >> lane) & 1u;
+          const bool rel = mine && __ldcg(&p.dist[p.item_first[it] + lane]) < tau;
+          const unsigned relm = __ballot_sync(FULL, rel);
+          if (lane == 0) {
+            const unsigned keep = m & ~relm;
+            p.far_mask[it] = keep;
+            if (keep)
+              far_next[atomicAdd(&p.counters[4 + (fcur ^ 1)], 1ull)] = it;
+            else
+              p.infar[it] = 0u;
+            if (relm) {
+              const unsigned old = atomicOr(&p.pend_mask[it], relm);
+              if (old == 0u) near_next[atomicAdd(&p.counters[cur], 1ull)] = it;
+            }
+          }
+        }
+        if (first) p.tau[0] = tau;
+      }
+      grid.sync();
+      fcur ^= 1;
+    }
+  }
+  if (first) {
+    p.ctl[0] = cur;
+    p.ctl[1] = fcur;
+    p.ctl[3] = done;
+    p.ctl[4] += rounds;
+    p.ctl[5] += pushes;
+  }
+}
+
 int ensure_push_workspace(rt_mesh* h) {
   Mesh2D& m = *h->m2;
   if (m.push_ready) return RT_OK;
@@ -558,6 +655,14 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
   const i64 max_blocks = (i64)sm_count * 16;
+  i64 coop_blocks = 0;
+  {
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nearfar_persistent_kernel, PUSH_BLOCK, 0) ==
+                    cudaSuccess)
+      coop_blocks = (i64)per_sm * sm_count;
+  }
 
   cudaEvent_t ev0, ev1, evr0, evr1;
   RT_CUDA(cudaEventCreate(&ev0));
@@ -598,7 +703,31 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     push_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, src, delta, m.nearq[0].p);
     st.total_launches += 1;
     i64 rounds = 0;
-    if (!timers) {
+    if (!timers && coop_blocks > 0 && h->opts.persistent != 0) {
+      // persistent cooperative kernel: all rounds on the device, host only re-launches every `max_rounds`
+      cudaMemsetAsync(m.ctl.p, 0, 8 * sizeof(int), s);
+      int hctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int max_rounds = 8192;
+      while (!hctl[3]) {
+        void* args[] = {(void*)&p, (void*)&max_rounds};
+        cudaError_t le = cudaLaunchCooperativeKernel((const void*)nearfar_persistent_kernel, dim3((unsigned)coop_blocks),
+                                                     dim3(PUSH_BLOCK), args, 0, s);
+        if (le != cudaSuccess) {
+          rc = RT_ERR_CUDA;
+          break;
+        }
+        st.total_launches += 1;
+        cudaMemcpyAsync(hctl, m.ctl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) {
+          rc = RT_ERR_CUDA;
+          break;
+        }
+      }
+      rounds = hctl[4];
+      st.relax_launches += hctl[5];
+      cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+      if (rc == RT_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = RT_ERR_CUDA;
+    } else if (!timers) {
       // device-controlled rounds, host sync every `check_every` rounds
       const int R = h->opts.check_every > 1 ? h->opts.check_every : 32;
       const unsigned gsmall = (unsigned)(sm_count * 2);
