@@ -44,6 +44,7 @@ typedef struct rt_stats {
   double relax_ms;         /* device time of the relax kernel alone (0 unless profiling timers are enabled)  */
   int64_t relax_launches;  /* launches of the relax kernel                                                  */
   int64_t total_launches;  /* all kernel launches issued by the solve(s)                                    */
+  double prev_ms;          /* device time of the predecessor (tightness) pass of the near-far schedule      */
 } rt_stats;
 
 /* ---- library ------------------------------------------------------------------------------------------ */

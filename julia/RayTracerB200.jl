@@ -30,6 +30,7 @@ struct RtStats                                     # mirrors rt_stats (include/r
     relax_ms::Float64
     relax_launches::Int64
     total_launches::Int64
+    prev_ms::Float64
 end
 
 function check(rc::Cint)
@@ -151,7 +152,7 @@ function bfm_batch(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector
     n, ns = G.n, length(sources)
     dist = Matrix{Float64}(undef, n, ns)
     prev = Matrix{Int64}(undef, n, ns)
-    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0))
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0))
     check(ccall((:rt_bfm_solve, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
                 h.ptr, Vector{Float64}(U), sources, ns, 64, dist, prev, st))

@@ -203,6 +203,7 @@ int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t ns
     total.relax_ms += st.relax_ms;
     total.relax_launches += st.relax_launches;
     total.total_launches += st.total_launches;
+    total.prev_ms += st.prev_ms;
   }
   if (stats) *stats = total;
   return RT_OK;

@@ -28,6 +28,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int PUSH_BLOCK = 128;
+constexpr int PUSH_GY = 8;  // element groups per released item (x 4 warps = 32 elements per pass)
 
 struct PP {
   const double* __restrict__ x;
@@ -42,6 +43,7 @@ struct PP {
   const i32* __restrict__ hn_node;
   const i32* __restrict__ hn_off;
   const i32* __restrict__ hn_part;
+  const i32* __restrict__ hn_index;  // node -> row of hn_off (or -1)
   int n_hn;
   int source;  // the source never 'improves', so update_halo! never fires from it (bfm.jl:56)
   double* dist;
@@ -68,6 +70,10 @@ __device__ __forceinline__ double edge_delta(double di, double xi, double zi, do
   return __dadd_rn(di, __ddiv_rn(len2, __dadd_rn(Ui, Uj)));
 }
 
+__global__ void hn_index_kernel(const i32* __restrict__ hn_node, i64 n_hn, i32* __restrict__ hn_index) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_hn) hn_index[hn_node[k]] = (i32)k;
+}
 __global__ void node_item_kernel(const i32* __restrict__ item_first, i64 n_items, i32* __restrict__ node_item) {
   const i64 it = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,11 +138,17 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
   const i64 n_near = (i64)__ldcg(&p.counters[cur]);
   const double tau = __ldcg(&p.tau[0]);
   u64 evals = 0;
-  for (i64 slot = blockIdx.x; slot < n_near; slot += gridDim.x) {
+  // work unit = (near-list slot, element group gy): the column of one released item is spread over PUSH_GY
+  // CTAs x 4 warps (warp per element), so a round with few released items still fills the machine
+  for (i64 unit = blockIdx.x; unit < n_near * PUSH_GY; unit += gridDim.x) {
+    const i64 slot = unit / PUSH_GY;
+    const int gy = (int)(unit - slot * PUSH_GY);
     const int it = __ldcg(&near_cur[slot]);
-    const unsigned mask = __ldcg(&p.cur_mask[slot]);
     const int v0 = p.item_first[it];
-    __syncthreads();  // smem reuse across slots
+    const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
+    if (c0 + (i64)gy * nwarp >= c1 && gy != 0) continue;  // block-uniform: this group has no element
+    const unsigned mask = __ldcg(&p.cur_mask[slot]);
+    __syncthreads();  // smem reuse across units
     if (warp == 0) {
       // compact the released sources into shared memory
       const bool on = (mask >> lane) & 1u;
@@ -154,18 +166,10 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
     __syncthreads();
     const int ns = s_ns;
     if (ns == 0) continue;
-    // zero-weight halo coupling (update_halo!): lane s of warp 0 serves source s
-    if (warp == 0 && p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {
-      const int i = s_id[lane];
-      int lo = 0, hi = p.n_hn;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (p.hn_node[mid] < i)
-          lo = mid + 1;
-        else
-          hi = mid;
-      }
-      if (lo < p.n_hn && p.hn_node[lo] == i) {
+    // zero-weight halo coupling (update_halo!): lane s of the last warp of group 0 serves source s
+    if (gy == 0 && warp == nwarp - 1 && p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {
+      const int lo = p.hn_index[s_id[lane]];
+      if (lo >= 0) {
         const double d = sd[lane];
         for (int q = p.hn_off[lo]; q < p.hn_off[lo + 1]; ++q) {
           const int b = p.hn_part[q];
@@ -173,8 +177,7 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
         }
       }
     }
-    const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
-    for (i64 c = c0 + warp; c < c1; c += nwarp) {
+    for (i64 c = c0 + (i64)gy * nwarp + warp; c < c1; c += (i64)PUSH_GY * nwarp) {
       const int el = p.g_idx[c];
       const int s = p.e2n_off[el];
       const int m = p.e2n_off[el + 1] - s;
@@ -199,7 +202,7 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
       }
       if (lane == 0) evals += (u64)m * (u64)ns;
     }
-    if (threadIdx.x == 0) atomicAdd(&p.counters[3], (u64)ns);
+    if (gy == 0 && threadIdx.x == 0) atomicAdd(&p.counters[3], (u64)ns);
   }
   if (lane == 0 && evals) atomicAdd(&p.counters[2], evals);
 }
@@ -594,6 +597,9 @@ int ensure_push_workspace(rt_mesh* h) {
   cudaStream_t s = h->stream;
   RT_TRY(m.node_item.alloc(m.n));
   node_item_kernel<<<grid_for(m.n_items * 32, 256), 256, 0, s>>>(m.item_first.p, m.n_items, m.node_item.p);
+  RT_TRY(m.hn_index.alloc(m.n));
+  RT_CUDA(cudaMemsetAsync(m.hn_index.p, 0xff, m.n * sizeof(i32), s));
+  if (m.n_hn) hn_index_kernel<<<grid_for(m.n_hn, 256), 256, 0, s>>>(m.hn_node.p, m.n_hn, m.hn_index.p);
   RT_TRY(m.pend_mask.alloc(m.n_items));
   RT_TRY(m.far_mask.alloc(m.n_items));
   RT_TRY(m.infar_u.alloc(m.n_items));
@@ -635,6 +641,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.hn_node = m.hn_node.p;
   p.hn_off = m.hn_off.p;
   p.hn_part = m.hn_part.p;
+  p.hn_index = m.hn_index.p;
   p.n_hn = (int)m.n_hn;
   p.source = -1;
   p.dist = m.dist.p;
@@ -762,7 +769,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
           cudaMemsetAsync(m.counters.p + nxt, 0, sizeof(u64), s);
           prep_kernel<<<grid_for(n_near, 256), 256, 0, s>>>(p, m.nearq[cur].p, cur);
           if (timers) cudaEventRecord(evr0, s);
-          push2d_kernel<<<(unsigned)std::min<i64>(n_near, max_blocks), PUSH_BLOCK, 0, s>>>(
+          push2d_kernel<<<(unsigned)std::min<i64>(n_near * PUSH_GY, max_blocks), PUSH_BLOCK, 0, s>>>(
               p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           if (timers) cudaEventRecord(evr1, s);
           pushed = true;
@@ -800,6 +807,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     st.relaxed_edges += (i64)ch[2];
     st.vertex_updates += (i64)ch[3];
     // ---- predecessors
+    cudaEventRecord(evr0, s);
     if (m.n_hinit)
       prev_halo_init_kernel<<<grid_for(m.n_hinit, 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p, m.n_hinit);
     cudaMemsetAsync(m.counters.p + 6, 0, sizeof(u64), s);
@@ -833,6 +841,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     }
     if (rc != RT_OK) break;
     if (n_un > 0) prev_giveup_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un);
+    cudaEventRecord(evr1, s);
     cudaEventRecord(ev1, s);
     if (dist_dev) cudaMemcpyAsync(dist_dev + si * n, m.dist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
     if (prev_dev) cudaMemcpyAsync(prev_dev + si * n, m.prev.p, n * sizeof(i32), cudaMemcpyDeviceToDevice, s);
@@ -843,6 +852,8 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     st.kernel_ms += ms;
+    cudaEventElapsedTime(&ms, evr0, evr1);
+    st.prev_ms += ms;
   }
   cudaError_t e = cudaGetLastError();
   if (rc == RT_ERR_CUDA || e != cudaSuccess) {

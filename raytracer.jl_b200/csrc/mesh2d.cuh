@@ -47,6 +47,7 @@ struct Mesh2D {
   DevBuf<unsigned> infar_u;            // per item: already in the far list
   DevBuf<unsigned> cur_mask;           // per near-list slot: the nodes released this round
   DevBuf<i32> nearq[2], farq[2];
+  DevBuf<i32> hn_index;                // node -> row in hn_off, -1 if the node has no halo partner
   DevBuf<i32> hn_node, hn_off, hn_part;  // halo partners: sorted unique nodes -> CSR of partner nodes
   i64 n_hn = 0;
   DevBuf<double> tau;                  // [0] current threshold, [1] delta, [2] min far dist (as u64 bits)
