@@ -224,7 +224,7 @@ def run_gpu(args):
     # roofline pass: same step with per-launch CUDA-event timers around the relaxation kernel (the timers force a
     # host sync per round, so they stay out of the timed region above)
     wl.handle.set_option("profile_timers", 1)
-    prof = dict(relaxed_edges=0, vertex_updates=0, relax_ms=0.0, relax_launches=0, kernel_ms=0.0)
+    prof = dict(relaxed_edges=0, vertex_updates=0, relax_ms=0.0, relax_launches=0, kernel_ms=0.0, prev_ms=0.0)
     prof_steps = max(1, min(args.steps, 2))
     for k in range(prof_steps):
         st = wl.solve_dev(wl.sources[0])
@@ -273,6 +273,7 @@ def run_gpu(args):
             "relaxed_edges_per_source": acc["relaxed_edges"] / args.steps,
             "sweeps_per_source": acc["sweeps"] / args.steps,
             "relax_kernel_share_of_step": relax_ms / max(prof["kernel_ms"], 1e-9),
+            "prev_pass_share_of_step": prof["prev_ms"] / max(prof["kernel_ms"], 1e-9),
             "gpu_launches": acc["total_launches"],
             "clocks": clocks,
             "e2e": {"value": e_graph * e2e_steps * world / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS",

@@ -134,6 +134,7 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
   __shared__ double sx[32], sz[32], sU[32], sd[32];
   __shared__ int s_id[32];
   __shared__ int s_ns;
+  __shared__ double s_dmin;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const i64 n_near = (i64)__ldcg(&p.counters[cur]);
   const double tau = __ldcg(&p.tau[0]);
@@ -161,11 +162,17 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
         sd[pos] = __ldcg(&p.dist[i]);
         s_id[pos] = i;
       }
-      if (lane == 0) s_ns = __popc(mask);
+      double dm = on ? __ldcg(&p.dist[v0 + lane]) : __longlong_as_double(0x7ff0000000000000LL);
+      for (int o = 16; o; o >>= 1) dm = fmin(dm, __shfl_xor_sync(FULL, dm, o));
+      if (lane == 0) {
+        s_ns = __popc(mask);
+        s_dmin = dm;
+      }
     }
     __syncthreads();
     const int ns = s_ns;
     if (ns == 0) continue;
+    const double dmin = s_dmin;
     // zero-weight halo coupling (update_halo!): lane s of the last warp of group 0 serves source s
     if (gy == 0 && warp == nwarp - 1 && p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {
       const int lo = p.hn_index[s_id[lane]];
@@ -184,6 +191,7 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
       for (int k = lane; k < m; k += 32) {
         const int j = p.e2n_idx[s + k];
         const double dj = __ldcg(&p.dist[j]);
+        if (!(dmin < dj)) continue;  // every released source is at or behind this target: nothing can improve
         const double xj = p.x[j], zj = p.z[j], Uj = p.U[j];
         double best = dj;
         for (int q = 0; q < ns; ++q) {
@@ -312,6 +320,7 @@ __global__ void __launch_bounds__(256) prev_tight_kernel(PP p, i64 n_items, int 
           }
         }
         pos_base += m;
+        if (__all_sync(FULL, !want || bid >= 0)) break;  // every lane has its first tight candidate
       }
     }
     for (int off = 16; off >= tl; off >>= 1) {
