@@ -223,7 +223,7 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
     RT_ARG(value >= 0.0, "delta must be >= 0");
     m->opts.delta = value;
   } else if (!std::strcmp(key, "persistent")) {
-    m->opts.persistent = value != 0.0;
+    m->opts.persistent = value < 0.0 ? -1 : (value != 0.0);
   } else if (!std::strcmp(key, "delta_factor")) {
     RT_ARG(value >= 0.0, "delta_factor must be >= 0");
     m->opts.delta_factor = value;

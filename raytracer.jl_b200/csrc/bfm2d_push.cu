@@ -719,7 +719,10 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     push_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, src, delta, m.nearq[0].p);
     st.total_launches += 1;
     i64 rounds = 0;
-    if (!timers && coop_blocks > 0 && h->opts.persistent != 0) {
+    // persistent kernel wins while the frontier is small (few grid-wide barriers beat 5 launches per round);
+    // large meshes are better served by hardware block scheduling of the batched launches
+    const bool small_mesh = m.n_items <= 65536;
+    if (!timers && coop_blocks > 0 && (h->opts.persistent == 1 || (h->opts.persistent < 0 && small_mesh))) {
       // persistent cooperative kernel: all rounds on the device, host only re-launches every `max_rounds`
       cudaMemsetAsync(m.ctl.p, 0, 8 * sizeof(int), s);
       int hctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -117,7 +117,7 @@ struct SolverOpts {
   int profile_timers = 0;  // 1: time the relax kernel with its own events (adds syncs)
   int check_every = 0;     // rounds between host convergence checks (0 = default)
   double delta = 0.0;      // near-far bucket width [s]; 0 = automatic
-  int persistent = 1;      // near-far: 1 = persistent cooperative kernel, 0 = one launch sequence per round
+  int persistent = -1;     // near-far: 1 = persistent cooperative kernel, 0 = launch sequence per round, -1 = auto
   double delta_factor = 0.0;  // automatic width = delta_factor x lightest edge (0 = default)
 };
 
