@@ -131,7 +131,7 @@ __global__ void prep_kernel(PP p, const i32* __restrict__ near_cur, int cur) {
 // with ld.global.cg (L2) so that a stale L1 line can never hide an update; mesh arrays are read-only.
 __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
-  __shared__ double sx[32], sz[32], sU[32], sd[32];
+  __shared__ double2 sxz[32], sUd[32];  // (x, z) and (U, dist) of the released sources: one LDS.128 each
   __shared__ int s_id[32];
   __shared__ int s_ns;
   __shared__ double s_dmin;
@@ -156,10 +156,8 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
       const int pos = __popc(mask & ((1u << lane) - 1u));
       if (on) {
         const int i = v0 + lane;
-        sx[pos] = p.x[i];
-        sz[pos] = p.z[i];
-        sU[pos] = p.U[i];
-        sd[pos] = __ldcg(&p.dist[i]);
+        sxz[pos] = make_double2(p.x[i], p.z[i]);
+        sUd[pos] = make_double2(p.U[i], __ldcg(&p.dist[i]));
         s_id[pos] = i;
       }
       double dm = on ? __ldcg(&p.dist[v0 + lane]) : __longlong_as_double(0x7ff0000000000000LL);
@@ -177,7 +175,7 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
     if (gy == 0 && warp == nwarp - 1 && p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {
       const int lo = p.hn_index[s_id[lane]];
       if (lo >= 0) {
-        const double d = sd[lane];
+        const double d = sUd[lane].y;
         for (int q = p.hn_off[lo]; q < p.hn_off[lo + 1]; ++q) {
           const int b = p.hn_part[q];
           if (d < __ldcg(&p.dist[b]) && relax_to(p, b, d)) enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
@@ -188,25 +186,49 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
       const int el = p.g_idx[c];
       const int s = p.e2n_off[el];
       const int m = p.e2n_off[el + 1] - s;
-      for (int k = lane; k < m; k += 32) {
-        const int j = p.e2n_idx[s + k];
-        const double dj = __ldcg(&p.dist[j]);
-        if (!(dmin < dj)) continue;  // every released source is at or behind this target: nothing can improve
-        const double xj = p.x[j], zj = p.z[j], Uj = p.U[j];
-        double best = dj;
-        for (int q = 0; q < ns; ++q) {
-          const double di = sd[q];
-          if (!(di < best)) continue;  // di + w >= di >= best: cannot improve
-          const double sxq = sx[q], szq = sz[q], sUq = sU[q];
-          {
-            const double dx = __dsub_rn(sxq, xj), dz = __dsub_rn(szq, zj);
-            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
-            if (screen_cannot_improve(best, di, d2, __dadd_rn(sUq, Uj))) continue;
-          }
-          const double delta = edge_delta(di, sxq, szq, sUq, xj, zj, Uj);
-          best = delta < best ? delta : best;
+      // software-pipelined target loop: the gathers of the next target are in flight while this one is evaluated
+      int k = lane;
+      int j = k < m ? p.e2n_idx[s + k] : -1;
+      double dj = 0.0, xj = 0.0, zj = 0.0, Uj = 0.0;
+      if (j >= 0) {
+        dj = __ldcg(&p.dist[j]);
+        xj = p.x[j];
+        zj = p.z[j];
+        Uj = p.U[j];
+      }
+      while (k < m) {
+        const int kn = k + 32;
+        const int jn = kn < m ? p.e2n_idx[s + kn] : -1;
+        double djn = 0.0, xjn = 0.0, zjn = 0.0, Ujn = 0.0;
+        if (jn >= 0) {
+          djn = __ldcg(&p.dist[jn]);
+          xjn = p.x[jn];
+          zjn = p.z[jn];
+          Ujn = p.U[jn];
         }
-        if (best < dj && relax_to(p, j, best)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+        if (dmin < dj) {  // else every released source is at or behind this target: nothing can improve
+          double best = dj;
+          for (int q = 0; q < ns; ++q) {
+            const double2 ud = sUd[q];  // (U, dist) of source q
+            const double di = ud.y;
+            if (!(di < best)) continue;  // di + w >= di >= best: cannot improve
+            const double2 xz = sxz[q];
+            {
+              const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
+              const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+              if (screen_cannot_improve(best, di, d2, __dadd_rn(ud.x, Uj))) continue;
+            }
+            const double delta = edge_delta(di, xz.x, xz.y, ud.x, xj, zj, Uj);
+            best = delta < best ? delta : best;
+          }
+          if (best < dj && relax_to(p, j, best)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+        }
+        k = kn;
+        j = jn;
+        dj = djn;
+        xj = xjn;
+        zj = zjn;
+        Uj = Ujn;
       }
       if (lane == 0) evals += (u64)m * (u64)ns;
     }
