@@ -743,7 +743,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     i64 rounds = 0;
     // persistent kernel wins while the frontier is small (few grid-wide barriers beat 5 launches per round);
     // large meshes are better served by hardware block scheduling of the batched launches
-    const bool small_mesh = m.n_items <= 65536;
+    const bool small_mesh = m.n <= 1500000;
     if (!timers && coop_blocks > 0 && (h->opts.persistent == 1 || (h->opts.persistent < 0 && small_mesh))) {
       // persistent cooperative kernel: all rounds on the device, host only re-launches every `max_rounds`
       cudaMemsetAsync(m.ctl.p, 0, 8 * sizeof(int), s);
