@@ -92,6 +92,13 @@ int rt_mesh_free(rt_mesh* m);
 int rt_interp_velocity(const double* knots_r, const double* knots_v, int64_t nk, const double* r, int64_t n,
                        double buffer, double* out);
 
+/* interpolate!(V, gr) src/Interpolations/interpolation.jl:5-18: re-interpolate the velocity of every secondary
+ * node from the corner values of its cell (bilinear.jl:1-17 for quads in (theta, r) space, barycentric.jl:1-15 for
+ * the centre triangles); a node shared by two cells keeps the value of the cell with the larger id, as the
+ * reference's sequential loop does.  V is a host array [n], updated in place.  el_type[nel] (0 = :Quad,
+ * 1 = :Tri) may be NULL for a mesh built by rt_annulus_build. */
+int rt_interpolate_cells(rt_mesh* m, const int8_t* el_type, double* V);
+
 /* Same, r_dev / out_dev are DEVICE pointers (knots stay on the host: they are 6372 entries). */
 int rt_interp_velocity_dev(const double* knots_r, const double* knots_v, int64_t nk, const double* r_dev,
                            int64_t n, double buffer, double* out_dev);

@@ -50,6 +50,7 @@ def lib():
         L.ora_grid3d_coords.argtypes = [F64P, F64P, I64P, C.c_int, F64P, F64P, F64P]
         L.ora_bfm3d.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, C.c_int, I64, F64P, I64P, I64P]
         L.ora_dijkstra3d.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, F64P]
+        L.ora_interpolate_cells.argtypes = [I64, I64P, I64P, I8P, F64P, F64P, F64P]
         L.ora_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -168,6 +169,13 @@ def dijkstra3d(nn, star_levels, X, Y, Z, U, source):
     dist = np.zeros(int(np.prod(nn)))
     lib().ora_dijkstra3d(nn, int(star_levels), X, Y, Z, np.ascontiguousarray(U, np.float64), int(source), dist)
     return dist
+
+
+def interpolate_cells(mesh, V):
+    """interpolate!(V, gr) src/Interpolations/interpolation.jl:5-18 (in place on a copy)."""
+    V = np.array(V, np.float64)
+    lib().ora_interpolate_cells(mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.el_type, mesh.theta, mesh.r, V)
+    return V
 
 
 def num_threads():

@@ -759,6 +759,44 @@ int ora_dijkstra3d(const i64* nn, int star_levels, const double* X, const double
   return 0;
 }
 
+// src/Interpolations/interpolation.jl:5-18 interpolate!(V, gr); bilinear.jl:1-30; barycentric.jl:1-32.
+// Points are Point2D{Polar}(theta, r) (GridAnnulus.jl:25): .x = theta, .z = r.  The reference wraps the sums in
+// @muladd (fusing is up to LLVM -> unpinned at the ulp level); here: plain left-to-right arithmetic.
+void ora_interpolate_cells(i64 nel, const i64* e2n_off, const i64* e2n_idx, const int8_t* el_type,
+                           const double* theta, const double* r, double* V) {
+  for (i64 e = 0; e < nel; ++e) {
+    const i64* el = e2n_idx + e2n_off[e];
+    const i64 len = e2n_off[e + 1] - e2n_off[e];
+    if (el_type[e] == 0) {
+      if (len < 4) continue;
+      double z1 = r[el[0] - 1], z2 = r[el[3] - 1];
+      double x1 = theta[el[0] - 1], x2 = theta[el[1] - 1];
+      if (x2 - x1 > PI) x1 += 2 * PI;
+      const double vu1 = V[el[0] - 1], vu2 = V[el[1] - 1], vu3 = V[el[2] - 1], vu4 = V[el[3] - 1];
+      const double dx21 = x2 - x1, dz21 = z2 - z1;
+      for (i64 q = 4; q < len; ++q) {
+        const i64 nd = el[q] - 1;
+        const double dx2 = x2 - theta[nd], dx1 = theta[nd] - x1, dz2 = z2 - r[nd], dz1 = r[nd] - z1;
+        V[nd] = 1 / (dx21 * dz21) * (vu1 * dx2 * dz2 + vu2 * dx1 * dz2 + vu4 * dx2 * dz1 + vu3 * dx1 * dz1);
+      }
+    } else {
+      if (len < 3) continue;
+      const double x1 = theta[el[0] - 1], x2 = theta[el[1] - 1], x3 = theta[el[2] - 1];
+      const double z1 = r[el[0] - 1], z2 = r[el[1] - 1], z3 = r[el[2] - 1];
+      const double vu1 = V[el[0] - 1], vu2 = V[el[1] - 1], vu3 = V[el[2] - 1];
+      for (i64 q = 3; q < len; ++q) {
+        const i64 nd = el[q] - 1;
+        const double x = theta[nd], z = r[nd];
+        const double den = (z2 - z3) * (x1 - x3) + (x3 - x2) * (z1 - z3);
+        const double N1 = ((z2 - z3) * (x - x3) + (x3 - x2) * (z - z3)) / den;
+        const double N2 = ((z3 - z1) * (x - x3) + (x1 - x3) * (z - z3)) / den;
+        const double N3 = 1 - N1 - N2;
+        V[nd] = N1 * vu1 + N2 * vu2 + N3 * vu3;
+      }
+    }
+  }
+}
+
 int ora_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -219,6 +219,17 @@ def interpolate_velocity(r, interpolant, buffer=None):
     return out
 
 
+def interpolate_inplace(V, gr, G=None, halo=None):
+    """interpolate!(V, gr) of src/Interpolations/interpolation.jl:5-18 (Python cannot spell the `!`): cell-wise
+    bilinear / barycentric re-interpolation of the secondary-node velocities, in place.  Returns V."""
+    handle = gr._handle if gr._handle is not None else mesh_from_arrays(gr, G, halo)
+    if not (isinstance(V, np.ndarray) and V.dtype == np.float64 and V.flags.c_contiguous):
+        raise ValueError("V must be a contiguous float64 array (it is updated in place)")
+    et = None if gr.element_type is None else np.ascontiguousarray(gr.element_type, np.int8)
+    check(lib().rt_interpolate_cells(handle.h, ptr(et), V))
+    return V
+
+
 # ------------------------------------------------------------------------------------------ closest_point
 def closest_point(gr, px, pz, system="cartesian"):
     """closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 -> 1-based node id (scalar or array)."""

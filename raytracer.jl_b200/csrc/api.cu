@@ -154,6 +154,19 @@ int rt_mesh_coords_dev(const rt_mesh* m, const double** a, const double** b, con
   return RT_ERR_ARG;
 }
 
+int rt_interpolate_cells(rt_mesh* m, const int8_t* el_type, double* V) {
+  RT_ARG(m && m->kind == 2 && V, "rt_interpolate_cells needs a 2-D mesh and a velocity array");
+  RT_CUDA(cudaSetDevice(m->device));
+  i64 sz[8];
+  mesh2d_sizes(m, sz);
+  DevBuf<double> dV;
+  RT_TRY(dV.upload(V, sz[0]));
+  RT_CUDA(cudaDeviceSynchronize());
+  RT_TRY(mesh2d_interpolate_cells(m, el_type, dV.p));
+  RT_CUDA(cudaMemcpy(V, dV.p, sz[0] * sizeof(double), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
 int rt_closest_point(const rt_mesh* m, const double* pa, const double* pb, int64_t npts, int system,
                      int64_t* index_out) {
   RT_ARG(m && m->kind == 2, "rt_closest_point needs a 2-D mesh");

@@ -103,6 +103,60 @@ __global__ void graph_edges_kernel(const i64* __restrict__ g_off, const i32* __r
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
+// ---- interpolate!(V, gr) (src/Interpolations/interpolation.jl:5-18): the reference loops over the elements in
+// order and overwrites the secondary nodes of each, so a node shared by two cells keeps the value computed in the
+// cell with the LARGER id.  Pass 1 finds that owner per node, pass 2 evaluates bilinear (bilinear.jl:1-17, in
+// (theta, r) space, including the wrap-column quirk) / barycentric (barycentric.jl:1-15) weights there.
+__global__ void interp_owner_kernel(const i32* __restrict__ e2n_off, const i32* __restrict__ e2n_idx, i64 nel,
+                                    const int8_t* __restrict__ el_type, i32* __restrict__ owner) {
+  const i64 e = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= nel) return;
+  const int nc = el_type[e] == 0 ? 4 : 3;
+  for (i32 q = e2n_off[e] + nc + lane; q < e2n_off[e + 1]; q += 32) atomicMax(&owner[e2n_idx[q]], (i32)e);
+}
+__global__ void interp_cells_kernel(const i32* __restrict__ e2n_off, const i32* __restrict__ e2n_idx, i64 nel,
+                                    const int8_t* __restrict__ el_type, const i32* __restrict__ owner,
+                                    const double* __restrict__ theta, const double* __restrict__ r,
+                                    const double* __restrict__ V0, double* __restrict__ V) {
+  const i64 e = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= nel) return;
+  const i32* el = e2n_idx + e2n_off[e];
+  const int len = e2n_off[e + 1] - e2n_off[e];
+  const double PI = 3.141592653589793;
+  if (el_type[e] == 0) {
+    if (len < 4) return;
+    const double z1 = r[el[0]], z2 = r[el[3]];
+    double x1 = theta[el[0]];
+    const double x2 = theta[el[1]];
+    if (x2 - x1 > PI) x1 += 2 * PI;
+    const double vu1 = V0[el[0]], vu2 = V0[el[1]], vu3 = V0[el[2]], vu4 = V0[el[3]];
+    const double dx21 = x2 - x1, dz21 = z2 - z1;
+    for (int q = 4 + lane; q < len; q += 32) {
+      const int nd = el[q];
+      if (owner[nd] != (i32)e) continue;
+      const double dx2 = x2 - theta[nd], dx1 = theta[nd] - x1, dz2 = z2 - r[nd], dz1 = r[nd] - z1;
+      V[nd] = 1 / (dx21 * dz21) * (vu1 * dx2 * dz2 + vu2 * dx1 * dz2 + vu4 * dx2 * dz1 + vu3 * dx1 * dz1);
+    }
+  } else {
+    if (len < 3) return;
+    const double x1 = theta[el[0]], x2 = theta[el[1]], x3 = theta[el[2]];
+    const double z1 = r[el[0]], z2 = r[el[1]], z3 = r[el[2]];
+    const double vu1 = V0[el[0]], vu2 = V0[el[1]], vu3 = V0[el[2]];
+    const double den = (z2 - z3) * (x1 - x3) + (x3 - x2) * (z1 - z3);
+    for (int q = 3 + lane; q < len; q += 32) {
+      const int nd = el[q];
+      if (owner[nd] != (i32)e) continue;
+      const double x = theta[nd], z = r[nd];
+      const double N1 = ((z2 - z3) * (x - x3) + (x3 - x2) * (z - z3)) / den;
+      const double N2 = ((z3 - z1) * (x - x3) + (x1 - x3) * (z - z3)) / den;
+      const double N3 = 1 - N1 - N2;
+      V[nd] = N1 * vu1 + N2 * vu2 + N3 * vu3;
+    }
+  }
+}
+
 template <typename T>
 int scan_exclusive(const T* in, T* out, i64 count, cudaStream_t s) {
   size_t bytes = 0;
@@ -402,5 +456,32 @@ int mesh2d_coords(const rt_mesh* h, const double** x, const double** z, const do
   *z = m.z.p;
   *theta = m.has_polar ? m.theta.p : nullptr;
   *r = m.has_polar ? m.r.p : nullptr;
+  return RT_OK;
+}
+
+// interpolate!(V, gr): V_dev in/out (device, n doubles).  el_type: host array (0 = :Quad, 1 = :Tri) or null for a
+// mesh built by rt_annulus_build.
+int mesh2d_interpolate_cells(rt_mesh* h, const int8_t* el_type_host, double* V_dev) {
+  Mesh2D& m = *h->m2;
+  cudaStream_t s = h->stream;
+  RT_ARG(m.has_polar, "mesh has no (theta, r) arrays");
+  const int8_t* et = el_type_host;
+  if (!et) {
+    RT_ARG((i64)m.el_type_h.size() == m.nel, "element types are needed for a mesh adopted from arrays");
+    et = m.el_type_h.data();
+  }
+  DevBuf<int8_t> d_et;
+  DevBuf<i32> owner;
+  DevBuf<double> V0;
+  RT_TRY(d_et.upload(et, m.nel, s));
+  RT_TRY(owner.alloc(m.n));
+  RT_CUDA(cudaMemsetAsync(owner.p, 0xff, m.n * sizeof(i32), s));
+  RT_TRY(V0.alloc(m.n));
+  RT_CUDA(cudaMemcpyAsync(V0.p, V_dev, m.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  interp_owner_kernel<<<grid_for(m.nel * 32, 256), 256, 0, s>>>(m.e2n_off.p, m.e2n_idx.p, m.nel, d_et.p, owner.p);
+  interp_cells_kernel<<<grid_for(m.nel * 32, 256), 256, 0, s>>>(m.e2n_off.p, m.e2n_idx.p, m.nel, d_et.p, owner.p,
+                                                               m.theta.p, m.r.p, V0.p, V_dev);
+  RT_CUDA(cudaGetLastError());
+  RT_CUDA(cudaStreamSynchronize(s));
   return RT_OK;
 }

@@ -326,3 +326,24 @@ def test_bfm2d_near_far_random_velocity_sources(rt, O, annulus):
         assert np.array_equal(D.dist[k], dist), "source %d" % s
         check_prev_tie_aware(m, U, int(s), dist, D.prev[k], prev)
     rt.bfm(G, halo, 1, gr, U, schedule="jacobi")
+
+
+def test_interpolate_cells_matches_oracle(rt, O, annulus, ak135):
+    """interpolate!(V, gr) (src/Interpolations/*.jl) through the ABI, on adopted and on device-built meshes."""
+    m = annulus(36, 10, 100.0)
+    U = O.interp_velocity(ak135[0], ak135[1], m.r)
+    want = O.interpolate_cells(m, U)
+    gr, G, halo = adopt(rt, m)
+    gr.element_type = m.el_type
+    got = rt.interpolate_inplace(U.copy(), gr, G, halo)
+    assert np.array_equal(got, want)
+    gr2, G2, halo2 = rt.init_annulus(36, 10, spacing=100.0)
+    V = rt.interpolate_velocity(gr2.r, rt.LinearInterpolation(*ak135))
+    assert np.array_equal(rt.interpolate_inplace(V, gr2), want)
+    # benchmarks/gpu.jl:54-58 flow: interpolant -> interpolate! -> bfm still solves and matches the oracle
+    src = rt.closest_point(gr2, 0.0, R, system="polar")
+    D = rt.bfm(G2, halo2, src, gr2, V)
+    mm = O.Annulus(36, 10, 100.0)
+    mm.x, mm.z = gr2.x, gr2.z
+    dist, prev, st = O.bfm(mm, V, src)
+    assert np.array_equal(D.dist, dist) and np.array_equal(D.prev, prev)
