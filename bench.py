@@ -135,9 +135,7 @@ class GpuWorkload:
         self.prev_dev = torch.empty(self.n, dtype=torch.int32, device="cuda")
         self.handle.set_option("profile_timers", 0)
         self.schedule = schedule
-        self.handle.set_option("schedule", {"jacobi": 0, "near-far": 1}[schedule] if self.w["kind"] == "2d" else 0)
-        if self.w["kind"] == "3d":
-            self.schedule = "jacobi"
+        self.handle.set_option("schedule", {"jacobi": 0, "near-far": 1}[schedule])
         # pinned host buffers of the end-to-end arm
         self.U_pin = torch.from_numpy(self.U_host).pin_memory()
         self.dist_pin = torch.empty(self.n, dtype=torch.float64).pin_memory()
@@ -281,8 +279,8 @@ def run_gpu(args):
                     "d2h_bytes_per_step": n * 16},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "relax3d_kernel" if wl.w["kind"] == "3d" else
-                         ("relax2d_kernel" if wl.schedule == "jacobi" else "push2d_kernel"),
+                         "kernel": ("relax%s_kernel" if wl.schedule == "jacobi" else "push%s_kernel") %
+                         ("3d" if wl.w["kind"] == "3d" else "2d"),
                          "bytes_model": "12 B per relaxed candidate + %d B per active-vertex update" % wl.bv,
                          "avg_launch_ms": relax_ms / max(prof["relax_launches"], 1)},
         }

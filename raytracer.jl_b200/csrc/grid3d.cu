@@ -41,6 +41,14 @@ struct Grid3D {
   DevBuf<u64> counters;
   u64* counters_host = nullptr;
   bool ws_ready = false;
+  // ---- near-far (push) schedule: items = runs of 32 consecutive x-nodes of one (y, z) grid line
+  i64 nbx = 0, n_items = 0;
+  DevBuf<unsigned> pend_mask, far_mask, infar, cur_mask;
+  DevBuf<i32> nearq[2], farq[2];
+  DevBuf<double> tau;
+  DevBuf<int> ctl;
+  DevBuf<i32> unresolved;
+  bool push_ready = false;
 };
 
 namespace {
@@ -329,8 +337,451 @@ int grid3d_n(const rt_mesh* h, i64* n) {
   return RT_OK;
 }
 
+
+// =========================================================================================================
+// Near-far push schedule on the implicit star-L graph (see bfm2d_push.cu for the scheme).  Work item = 32
+// consecutive x-nodes of one (y, z) grid line; a released item pushes into the (32 + 2w) x (2w+1)^2 block around
+// it: lanes walk the target x positions (coalesced loads of X, Y, Z, U, dist), each target is reached by the <= 2w+1
+// released sources within +-w in x, broadcast from shared memory.
+namespace {
+
+struct Q3 {
+  const double* __restrict__ X;
+  const double* __restrict__ Y;
+  const double* __restrict__ Z;
+  const double* __restrict__ U;
+  double* dist;
+  i32* prev;
+  unsigned* pend_mask;
+  unsigned* far_mask;
+  unsigned* infar;
+  unsigned* cur_mask;
+  u64* counters;  // [0],[1] near counts [2] evals [3] releases [4],[5] far counts [6] unresolved
+  double* tau;    // [0] tau [1] delta [2] min far bits [3] scratch
+  i32* nearq[2];
+  i32* farq[2];
+  int* ctl;       // [0] cur [1] fcur [2] mode [3] done [4] rounds [5] push rounds
+  int nx, ny, nz, nbx;
+  int w, self;
+};
+
+__device__ __forceinline__ void enqueue3(const Q3& p, i64 J, double d, double tau, i32* near_next, int nxt,
+                                         i32* far_list, int fcur) {
+  const int ix = (int)(J % p.nx);
+  const i64 line = J / p.nx;
+  const int it = (int)((ix >> 5) + (i64)p.nbx * line);
+  const unsigned bit = 1u << (ix & 31);
+  if (d < tau) {
+    const unsigned old = atomicOr(&p.pend_mask[it], bit);
+    if (old == 0u) near_next[atomicAdd(&p.counters[nxt], 1ull)] = it;
+    if (__ldcg(&p.far_mask[it]) & bit) atomicAnd(&p.far_mask[it], ~bit);
+  } else {
+    atomicOr(&p.far_mask[it], bit);
+    if (atomicExch(&p.infar[it], 1u) == 0u) far_list[atomicAdd(&p.counters[4 + fcur], 1ull)] = it;
+  }
+}
+
+constexpr int P3_BLOCK = 128;
+
+__device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, int cur, i32* near_next,
+                                            i32* far_list, int fcur) {
+  __shared__ double sX[32], sY[32], sZ[32], sU[32], sD[32];
+  __shared__ unsigned s_mask;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int w = p.w, W = 2 * w + 1;
+  const i64 n_near = (i64)__ldcg(&p.counters[cur]);
+  const double tau = __ldcg(&p.tau[0]);
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  u64 evals = 0;
+  // unit = (slot, dz): one CTA per z-plane of the target block, warps over its y rows
+  for (i64 unit = blockIdx.x; unit < n_near * W; unit += gridDim.x) {
+    const i64 slot = unit / W;
+    const int dzi = (int)(unit - slot * W) - w;
+    const int it = __ldcg(&near_cur[slot]);
+    const int bx = it % p.nbx;
+    const i64 line = it / p.nbx;
+    const int sy = (int)(line % p.ny), sz = (int)(line / p.ny);
+    const int tz = sz + dzi;
+    if (tz < 0 || tz >= p.nz) continue;  // block-uniform
+    const unsigned mask = __ldcg(&p.cur_mask[slot]);
+    __syncthreads();
+    if (warp == 0) {
+      const int gx = bx * 32 + lane;
+      if (((mask >> lane) & 1u) && gx < p.nx) {
+        const i64 I = (i64)gx + (i64)p.nx * ((i64)sy + (i64)p.ny * sz);
+        sX[lane] = p.X[I];
+        sY[lane] = p.Y[I];
+        sZ[lane] = p.Z[I];
+        sU[lane] = p.U[I];
+        sD[lane] = __ldcg(&p.dist[I]);
+      } else {
+        sD[lane] = INF;
+      }
+      if (lane == 0) s_mask = mask;
+    }
+    __syncthreads();
+    const unsigned m = s_mask;
+    if (m == 0u) continue;
+    const int x_lo = max(0, bx * 32 - w), x_hi = min(p.nx - 1, bx * 32 + 31 + w);
+    for (int dyi = warp; dyi < W; dyi += nwarp) {
+      const int ty = sy + dyi - w;
+      if (ty < 0 || ty >= p.ny) continue;
+      for (int tx = x_lo + lane; tx <= x_hi; tx += 32) {
+        const i64 J = (i64)tx + (i64)p.nx * ((i64)ty + (i64)p.ny * tz);
+        const double dj = __ldcg(&p.dist[J]);
+        const double xj = p.X[J], yj = p.Y[J], zj = p.Z[J], uj = p.U[J];
+        double best = dj;
+        const int q0 = max(tx - w, bx * 32) - bx * 32, q1 = min(tx + w, bx * 32 + 31) - bx * 32;
+        for (int q = q0; q <= q1; ++q) {
+          const double di = sD[q];  // INF if not released
+          if (!(di < best)) continue;
+          if (!p.self && dyi == w && dzi == 0 && bx * 32 + q == tx) continue;
+          const double dx = __dsub_rn(sX[q], xj), dy = __dsub_rn(sY[q], yj), dz = __dsub_rn(sZ[q], zj);
+          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          const double ss = fabs(__dadd_rn(sU[q], uj));
+          if (screen_cannot_improve(best, di, d2, ss)) continue;
+          const double delta = cand3(di, sX[q], sY[q], sZ[q], sU[q], xj, yj, zj, uj);
+          best = delta < best ? delta : best;
+        }
+        if (best < dj) {
+          const u64 bits = (u64)__double_as_longlong(best);
+          const u64 old = atomicMin((u64*)&p.dist[J], bits);
+          if (bits < old) enqueue3(p, J, best, tau, near_next, cur ^ 1, far_list, fcur);
+        }
+      }
+    }
+    if (threadIdx.x == 0) {
+      // evaluations of this z-plane: per released source, clipped x-extent times clipped y-extent
+      u64 e = 0;
+      const int ycnt = min(p.ny - 1, sy + w) - max(0, sy - w) + 1;
+      for (int q = 0; q < 32; ++q)
+        if ((m >> q) & 1u) {
+          const int gx = bx * 32 + q;
+          e += (u64)(min(p.nx - 1, gx + w) - max(0, gx - w) + 1) * (u64)ycnt;
+        }
+      evals += e;
+      if (dzi == 0) atomicAdd(&p.counters[3], (u64)__popc(m));
+    }
+  }
+  if (threadIdx.x == 0 && evals) atomicAdd(&p.counters[2], evals);
+}
+
+__global__ void round_begin3_kernel(Q3 p) {
+  int* c = p.ctl;
+  if (c[3]) return;
+  if (c[2] == 1)
+    c[0] ^= 1;
+  else if (c[2] == 2)
+    c[1] ^= 1;
+  const int cur = c[0], fcur = c[1];
+  const u64 n_near = p.counters[cur], n_far = p.counters[4 + fcur];
+  if (n_near == 0 && n_far == 0) {
+    c[2] = 0;
+    c[3] = 1;
+    return;
+  }
+  c[4] += 1;
+  if (n_near > 0) {
+    c[2] = 1;
+    c[5] += 1;
+    p.counters[cur ^ 1] = 0;
+  } else {
+    c[2] = 2;
+    p.tau[2] = __longlong_as_double(-1LL);
+    p.counters[4 + (fcur ^ 1)] = 0;
+  }
+}
+__global__ void prep3_kernel(Q3 p) {
+  if (p.ctl[2] != 1) return;
+  const int cur = p.ctl[0];
+  const i32* near_cur = p.nearq[cur];
+  const i64 n = (i64)p.counters[cur];
+  for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (i64)gridDim.x * blockDim.x)
+    p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
+}
+__global__ void __launch_bounds__(P3_BLOCK) push3d_kernel(Q3 p) {
+  if (p.ctl[2] != 1) return;
+  const int cur = p.ctl[0], fcur = p.ctl[1];
+  push3d_body(p, p.nearq[cur], cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
+}
+__device__ __forceinline__ i64 item_node0(const Q3& p, int it) {
+  const int bx = it % p.nbx;
+  const i64 line = it / p.nbx;
+  return (i64)bx * 32 + (i64)p.nx * line;
+}
+__global__ void far_min3_kernel(Q3 p) {
+  if (p.ctl[2] != 2) return;
+  const int fcur = p.ctl[1];
+  const i32* far_cur = p.farq[fcur];
+  const i64 nslots = (i64)p.counters[4 + fcur];
+  const int lane = threadIdx.x & 31;
+  u64 best = ~0ull;
+  for (i64 slot = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < nslots;
+       slot += ((i64)gridDim.x * blockDim.x) >> 5) {
+    const int it = far_cur[slot];
+    const unsigned m = p.far_mask[it];
+    if ((m >> lane) & 1u) {
+      const u64 b = (u64)__double_as_longlong(p.dist[item_node0(p, it) + lane]);
+      best = b < best ? b : best;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 other = __shfl_xor_sync(FULL, best, o);
+    best = other < best ? other : best;
+  }
+  if (lane == 0 && best != ~0ull) atomicMin((u64*)&p.tau[2], best);
+}
+__global__ void far_release3_kernel(Q3 p) {
+  if (p.ctl[2] != 2) return;
+  const int cur = p.ctl[0], fcur = p.ctl[1];
+  const i32* far_cur = p.farq[fcur];
+  i32* far_next = p.farq[fcur ^ 1];
+  i32* near_next = p.nearq[cur];
+  const i64 nslots = (i64)p.counters[4 + fcur];
+  const int lane = threadIdx.x & 31;
+  const double tau = __dadd_rn(p.tau[2], p.tau[1]);
+  for (i64 slot = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < nslots;
+       slot += ((i64)gridDim.x * blockDim.x) >> 5) {
+    const int it = far_cur[slot];
+    const unsigned m = p.far_mask[it];
+    const bool mine = (m >> lane) & 1u;
+    const bool rel = mine && p.dist[item_node0(p, it) + lane] < tau;
+    const unsigned relm = __ballot_sync(FULL, rel);
+    if (lane == 0) {
+      const unsigned keep = m & ~relm;
+      p.far_mask[it] = keep;
+      if (keep)
+        far_next[atomicAdd(&p.counters[4 + (fcur ^ 1)], 1ull)] = it;
+      else
+        p.infar[it] = 0u;
+      if (relm) {
+        const unsigned old = atomicOr(&p.pend_mask[it], relm);
+        if (old == 0u) near_next[atomicAdd(&p.counters[cur], 1ull)] = it;
+      }
+      if (slot == 0) p.tau[0] = tau;
+    }
+  }
+}
+__global__ void push3_init_kernel(Q3 p, i64 n, i64 source, double delta) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    p.dist[i] = (i == source) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+    p.prev[i] = -1;
+  }
+  if (i == 0) {
+    const int ix = (int)(source % p.nx);
+    const i64 line = source / p.nx;
+    const int it = (int)((ix >> 5) + (i64)p.nbx * line);
+    p.pend_mask[it] = 1u << (ix & 31);
+    p.nearq[0][0] = it;
+    p.counters[0] = 1ull;
+    p.tau[0] = delta;
+    p.tau[1] = delta;
+  }
+}
+// mean travel time along the cell diagonal (node -> node + (1,1,1)): sizes the bucket
+__global__ void wdiag3_kernel(Q3 p, double* __restrict__ sum, u64* __restrict__ cnt) {
+  const i64 I = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 7;  // sample every 7th node
+  double wt = 0.0;
+  const i64 n = (i64)p.nx * p.ny * p.nz;
+  if (I < n) {
+    const int i = (int)(I % p.nx), j = (int)((I / p.nx) % p.ny), k = (int)(I / ((i64)p.nx * p.ny));
+    const int i2 = min(i + 1, p.nx - 1), j2 = min(j + 1, p.ny - 1), k2 = min(k + 1, p.nz - 1);
+    const i64 J = (i64)i2 + (i64)p.nx * ((i64)j2 + (i64)p.ny * k2);
+    if (J != I) wt = cand3(0.0, p.X[I], p.Y[I], p.Z[I], p.U[I], p.X[J], p.Y[J], p.Z[J], p.U[J]);
+    if (!(wt == wt) || wt > 1e300) wt = 0.0;
+  }
+  const unsigned has = __ballot_sync(FULL, wt > 0.0);
+  for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(FULL, wt, o);
+  if ((threadIdx.x & 31) == 0 && has) {
+    atomicAdd(sum, wt);
+    atomicAdd(cnt, (u64)__popc(has));
+  }
+}
+// predecessors: first candidate in ascending linear id (the canonical scan order) with dist[J] < dist[I] that is
+// bit-exactly tight.  Thread per node, window read straight from global memory (L2-resident neighbourhood).
+__global__ void prev_tight3_kernel(Q3 p, i64 n, i64 source) {
+  const i64 I = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= n) return;
+  const double di = p.dist[I];
+  if (!(di < __longlong_as_double(0x7ff0000000000000LL)) || I == source) return;
+  const int i = (int)(I % p.nx), j = (int)((I / p.nx) % p.ny), k = (int)(I / ((i64)p.nx * p.ny));
+  const int w = p.w;
+  const double xi = p.X[I], yi = p.Y[I], zi = p.Z[I], ui = p.U[I];
+  for (int zz = max(0, k - w); zz <= min(p.nz - 1, k + w); ++zz)
+    for (int yy = max(0, j - w); yy <= min(p.ny - 1, j + w); ++yy)
+      for (int xx = max(0, i - w); xx <= min(p.nx - 1, i + w); ++xx) {
+        const i64 J = (i64)xx + (i64)p.nx * ((i64)yy + (i64)p.ny * zz);
+        const double dj = p.dist[J];
+        if (!(dj < di)) continue;
+        const double xj = p.X[J], yj = p.Y[J], zj = p.Z[J], uj = p.U[J];
+        const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (!screen_maybe_tight(di, dj, d2, fabs(__dadd_rn(ui, uj)))) continue;
+        if (cand3(dj, xi, yi, zi, ui, xj, yj, zj, uj) == di) {
+          p.prev[I] = (i32)J;
+          return;
+        }
+      }
+}
+
+int ensure_push3(rt_mesh* h) {
+  Grid3D& g = *h->g3;
+  if (g.push_ready) return RT_OK;
+  g.nbx = (g.nn[0] + 31) / 32;
+  g.n_items = g.nbx * g.nn[1] * g.nn[2];
+  RT_TRY(g.pend_mask.alloc(g.n_items));
+  RT_TRY(g.far_mask.alloc(g.n_items));
+  RT_TRY(g.infar.alloc(g.n_items));
+  RT_TRY(g.cur_mask.alloc(g.n_items));
+  for (int k = 0; k < 2; ++k) {
+    RT_TRY(g.nearq[k].alloc(g.n_items));
+    RT_TRY(g.farq[k].alloc(g.n_items));
+  }
+  RT_TRY(g.tau.alloc(4));
+  RT_TRY(g.ctl.alloc(8));
+  g.push_ready = true;
+  return RT_OK;
+}
+
+}  // namespace
+
+int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                     rt_stats* stats) {
+  Grid3D& g = *h->g3;
+  cudaStream_t s = h->stream;
+  RT_TRY(ensure_ws3(h));
+  RT_TRY(ensure_push3(h));
+  const i64 n = g.n;
+  Q3 p;
+  p.X = g.X.p;
+  p.Y = g.Y.p;
+  p.Z = g.Z.p;
+  p.U = U_dev;
+  p.dist = g.dist.p;
+  p.prev = g.prev.p;
+  p.pend_mask = g.pend_mask.p;
+  p.far_mask = g.far_mask.p;
+  p.infar = g.infar.p;
+  p.cur_mask = g.cur_mask.p;
+  p.counters = g.counters.p;
+  p.tau = g.tau.p;
+  p.nearq[0] = g.nearq[0].p;
+  p.nearq[1] = g.nearq[1].p;
+  p.farq[0] = g.farq[0].p;
+  p.farq[1] = g.farq[1].p;
+  p.ctl = g.ctl.p;
+  p.nx = (int)g.nn[0];
+  p.ny = (int)g.nn[1];
+  p.nz = (int)g.nn[2];
+  p.nbx = (int)g.nbx;
+  p.w = g.w;
+  p.self = g.self;
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+  const unsigned gbig = (unsigned)(sm_count * 16), gsmall = (unsigned)(sm_count * 2);
+  u64* ch = g.counters_host;
+  cudaEvent_t ev0, ev1, evr0, evr1;
+  RT_CUDA(cudaEventCreate(&ev0));
+  RT_CUDA(cudaEventCreate(&ev1));
+  RT_CUDA(cudaEventCreate(&evr0));
+  RT_CUDA(cudaEventCreate(&evr1));
+  rt_stats st = {};
+  st.graph_edges = g.graph_edges;
+  int rc = RT_OK;
+  const bool timers = h->opts.profile_timers != 0;
+  double delta = h->opts.delta;
+  if (!(delta > 0.0)) {
+    RT_CUDA(cudaMemsetAsync(g.tau.p + 3, 0, sizeof(double), s));
+    RT_CUDA(cudaMemsetAsync(g.counters.p + 7, 0, sizeof(u64), s));
+    wdiag3_kernel<<<grid_for((n + 6) / 7, 256), 256, 0, s>>>(p, g.tau.p + 3, g.counters.p + 7);
+    double wsum = 0.0;
+    u64 wc = 0;
+    RT_CUDA(cudaMemcpyAsync(&wsum, g.tau.p + 3, sizeof(double), cudaMemcpyDeviceToHost, s));
+    RT_CUDA(cudaMemcpyAsync(&wc, g.counters.p + 7, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    RT_CUDA(cudaStreamSynchronize(s));
+    const double wmean = wc ? wsum / (double)wc : 1.0;
+    delta = wmean * (h->opts.delta_factor > 0.0 ? h->opts.delta_factor : 1.0);
+  }
+  for (i64 si = 0; si < nsrc && rc == RT_OK; ++si) {
+    const i64 src1 = sources[si];
+    if (src1 < 1 || src1 > n) {
+      rt_set_error("source %lld out of range 1..%lld", (long long)src1, (long long)n);
+      rc = RT_ERR_ARG;
+      break;
+    }
+    const i64 src = src1 - 1;
+    cudaEventRecord(ev0, s);
+    cudaMemsetAsync(g.counters.p, 0, 8 * sizeof(u64), s);
+    cudaMemsetAsync(g.pend_mask.p, 0, g.n_items * sizeof(unsigned), s);
+    cudaMemsetAsync(g.far_mask.p, 0, g.n_items * sizeof(unsigned), s);
+    cudaMemsetAsync(g.infar.p, 0, g.n_items * sizeof(unsigned), s);
+    cudaMemsetAsync(g.ctl.p, 0, 8 * sizeof(int), s);
+    push3_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, src, delta);
+    st.total_launches += 1;
+    int hctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int R = timers ? 1 : (h->opts.check_every > 1 ? h->opts.check_every : 32);
+    while (!hctl[3]) {
+      for (int r = 0; r < R; ++r) {
+        round_begin3_kernel<<<1, 1, 0, s>>>(p);
+        prep3_kernel<<<gsmall, 256, 0, s>>>(p);
+        if (timers) cudaEventRecord(evr0, s);
+        push3d_kernel<<<gbig, P3_BLOCK, 0, s>>>(p);
+        if (timers) cudaEventRecord(evr1, s);
+        far_min3_kernel<<<gsmall, 256, 0, s>>>(p);
+        far_release3_kernel<<<gsmall, 256, 0, s>>>(p);
+      }
+      cudaMemcpyAsync(hctl, g.ctl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        rc = RT_ERR_CUDA;
+        break;
+      }
+      if (timers && hctl[2] == 1) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evr0, evr1);
+        st.relax_ms += ms;
+      }
+    }
+    if (rc != RT_OK) break;
+    st.sweeps += hctl[4];
+    st.relax_launches += hctl[5];
+    st.total_launches += 2 * (i64)hctl[4];
+    cudaEventRecord(evr0, s);
+    prev_tight3_kernel<<<grid_for(n, 128), 128, 0, s>>>(p, n, src);
+    cudaEventRecord(evr1, s);
+    st.total_launches += 1;
+    cudaMemcpyAsync(ch, g.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+    cudaEventRecord(ev1, s);
+    if (dist_dev) cudaMemcpyAsync(dist_dev + si * n, g.dist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (prev_dev) cudaMemcpyAsync(prev_dev + si * n, g.prev.p, n * sizeof(i32), cudaMemcpyDeviceToDevice, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      rc = RT_ERR_CUDA;
+      break;
+    }
+    st.relaxed_edges += (i64)ch[2] + g.graph_edges;  // pushes + the tightness pass over every window
+    st.vertex_updates += (i64)ch[3];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    st.kernel_ms += ms;
+    cudaEventElapsedTime(&ms, evr0, evr1);
+    st.prev_ms += ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (rc == RT_ERR_CUDA || e != cudaSuccess) {
+    rt_set_error("CUDA failure in bfm3d_solve_push: %s", cudaGetErrorString(e));
+    rc = RT_ERR_CUDA;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  cudaEventDestroy(evr0);
+  cudaEventDestroy(evr1);
+  if (stats) *stats = st;
+  return rc;
+}
+
 int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                 rt_stats* stats) {
+  if (h->opts.schedule == 1) return bfm3d_solve_push(h, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
   Grid3D& g = *h->g3;
   cudaStream_t s = h->stream;
   RT_TRY(ensure_ws3(h));

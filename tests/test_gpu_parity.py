@@ -347,3 +347,32 @@ def test_interpolate_cells_matches_oracle(rt, O, annulus, ak135):
     mm.x, mm.z = gr2.x, gr2.z
     dist, prev, st = O.bfm(mm, V, src)
     assert np.array_equal(D.dist, dist) and np.array_equal(D.prev, prev)
+
+
+@pytest.mark.parametrize("nn,lv,cs", [((7, 6, 5), 1, "spherical"), ((40, 40, 24), 1, "spherical"),
+                                      ((33, 18, 10), 2, "cartesian"), ((70, 9, 13), 0, "spherical")])
+def test_bfm3d_near_far_schedule(rt, O, nn, lv, cs):
+    if cs == "spherical":
+        c0 = (np.deg2rad(70.0), np.deg2rad(70.0), R - 2000.0)
+        c1 = (np.deg2rad(110.0), np.deg2rad(110.0), R)
+    else:
+        c0, c1 = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)
+    g = rt.grid(c0, c1, nn, neighbour_levels=lv, coord_system=cs)
+    X, Y, Z = g.coordinates()
+    n = int(np.prod(nn))
+    U = 4.0 + 6.0 * splitmix64(11 + n, n)
+    srcs = np.array([1, n, n // 2 + 3], np.int64)
+    for delta in (0.0, 1e-3, 1e9):
+        D = rt.bfm3d(g, srcs, U, schedule="near-far", delta=delta)
+        for k, s in enumerate(srcs):
+            dist, prev, st = O.bfm3d(nn, lv, X, Y, Z, U, int(s))
+            assert np.array_equal(D.dist[k], dist), "travel times must be bit-identical in any schedule"
+            p = D.prev[k]
+            i = np.nonzero(p > 0)[0]
+            assert len(i) == n - 1 and p[s - 1] == 0
+            assert np.array_equal(dist[p[i] - 1] + weight3d(X, Y, Z, U, i, p[i] - 1), dist[i])  # tight
+            assert np.all(dist[p[i] - 1] < dist[i])
+            path = rt.recontruct_path(p, int(s), 1 if s != 1 else n)
+            assert path[-1] == s and np.all(np.diff(dist[path - 1]) <= 0)
+    assert D.stats["relaxed_edges"] > 0
+    rt.bfm3d(g, 1, U, schedule="jacobi")
