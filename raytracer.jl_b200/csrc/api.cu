@@ -235,6 +235,8 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
   } else if (!std::strcmp(key, "delta")) {
     RT_ARG(value >= 0.0, "delta must be >= 0");
     m->opts.delta = value;
+  } else if (!std::strcmp(key, "packed_prev")) {
+    m->opts.packed_prev = value != 0.0;
   } else if (!std::strcmp(key, "persistent")) {
     m->opts.persistent = value < 0.0 ? -1 : (value != 0.0);
   } else if (!std::strcmp(key, "delta_factor")) {

@@ -46,7 +46,9 @@ struct PP {
   const i32* __restrict__ hn_index;  // node -> row of hn_off (or -1)
   int n_hn;
   int source;  // the source never 'improves', so update_halo! never fires from it (bfm.jl:56)
-  double* dist;
+  double* dist;   // travel times; element stride ds (1 = plain array, 2 = first word of the packed (dist, key) pairs)
+  int ds;
+  u64* keys;      // packed mode: keys[2*j + 1] = predecessor key of node j (same allocation as dist)
   i32* prev;
   unsigned* pend_mask;
   unsigned* far_mask;
@@ -114,8 +116,62 @@ __device__ __forceinline__ void enqueue(const PP& p, int j, double d, double tau
 // try dist[j] = min(dist[j], d); returns true if it improved
 __device__ __forceinline__ bool relax_to(const PP& p, int j, double d) {
   const u64 bits = (u64)__double_as_longlong(d);
-  const u64 old = atomicMin((u64*)&p.dist[j], bits);
+  const u64 old = atomicMin((u64*)&p.dist[(i64)j * p.ds], bits);
   return bits < old;
+}
+
+
+// ---- packed (travel time, predecessor key) pairs: one 128-bit atomic compare-and-swap keeps them consistent, so
+// no separate predecessor pass is needed.  Order: smaller time wins; on an exact tie a REGULAR predecessor
+// (positive-weight edge) with a smaller node id wins; zero-weight couplings (coincident nodes, halo twins) only
+// win by strict improvement (no cycles among equal-time nodes).  The result is schedule independent: every tight
+// predecessor eventually pushes its final value, so the key ends as the smallest id among them.
+constexpr u64 KEY_NONE = ~0ull;
+constexpr u64 KEY_ZW = 1ull << 40;    // zero-weight edge between coincident nodes
+constexpr u64 KEY_HALO = 1ull << 41;  // zero-weight halo coupling (resolved to the twin's predecessor afterwards)
+constexpr u64 KEY_ZMASK = KEY_ZW | KEY_HALO;
+
+struct alignas(16) DP {
+  u64 d;  // bit pattern of the (non-negative) travel time
+  u64 k;
+};
+__device__ __forceinline__ DP dp_cas(DP* addr, DP expected, DP desired) {
+  DP old;
+  asm volatile(
+      "{\n"
+      ".reg .b128 e, d, o;\n"
+      "mov.b128 e, {%2, %3};\n"
+      "mov.b128 d, {%4, %5};\n"
+      "atom.global.relaxed.gpu.cas.b128 o, [%6], e, d;\n"
+      "mov.b128 {%0, %1}, o;\n"
+      "}\n"
+      : "=l"(old.d), "=l"(old.k)
+      : "l"(expected.d), "l"(expected.k), "l"(desired.d), "l"(desired.k), "l"(addr)
+      : "memory");
+  return old;
+}
+__device__ __forceinline__ DP dp_load(const PP& p, int j) {
+  DP v;
+  const u64* a = (const u64*)p.dist + 2 * (i64)j;
+  v.d = __ldcg(a);
+  v.k = __ldcg(a + 1);
+  return v;  // a torn read only costs one failed CAS
+}
+// returns true iff the travel time strictly improved
+__device__ __forceinline__ bool dp_update(const PP& p, int j, DP cur, double delta, u64 key) {
+  const u64 db = (u64)__double_as_longlong(delta);
+  DP* addr = (DP*)p.dist + j;
+  while (true) {
+    const bool strictly = db < cur.d;
+    const bool tie = db == cur.d && !(key & KEY_ZMASK) && key < cur.k;
+    if (!strictly && !tie) return false;
+    DP des;
+    des.d = db;
+    des.k = key;
+    const DP old = dp_cas(addr, cur, des);
+    if (old.d == cur.d && old.k == cur.k) return strictly;
+    cur = old;
+  }
 }
 
 // round step 1: take the released bits of every item of the near list
@@ -129,8 +185,9 @@ __global__ void prep_kernel(PP p, const i32* __restrict__ near_cur, int cur) {
 // round step 2: one CTA per released item; warps split the elements of its G column; lanes = targets.
 // All state that another SM may have written in an earlier phase of the SAME launch (persistent kernel) is read
 // with ld.global.cg (L2) so that a stale L1 line can never hide an update; mesh arrays are read-only.
-__device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
-                                            i32* far_list, int fcur) {
+template <bool PACKED>
+__device__ __forceinline__ void push2d_body_t(const PP& p, const i32* near_cur, int cur, i32* near_next,
+                                              i32* far_list, int fcur) {
   __shared__ double2 sxz[32], sUd[32];  // (x, z) and (U, dist) of the released sources: one LDS.128 each
   __shared__ int s_id[32];
   __shared__ int s_ns;
@@ -157,10 +214,10 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
       if (on) {
         const int i = v0 + lane;
         sxz[pos] = make_double2(p.x[i], p.z[i]);
-        sUd[pos] = make_double2(p.U[i], __ldcg(&p.dist[i]));
+        sUd[pos] = make_double2(p.U[i], __ldcg(&p.dist[(i64)i * p.ds]));
         s_id[pos] = i;
       }
-      double dm = on ? __ldcg(&p.dist[v0 + lane]) : __longlong_as_double(0x7ff0000000000000LL);
+      double dm = on ? __ldcg(&p.dist[(i64)(v0 + lane) * p.ds]) : __longlong_as_double(0x7ff0000000000000LL);
       for (int o = 16; o; o >>= 1) dm = fmin(dm, __shfl_xor_sync(FULL, dm, o));
       if (lane == 0) {
         s_ns = __popc(mask);
@@ -178,7 +235,13 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
         const double d = sUd[lane].y;
         for (int q = p.hn_off[lo]; q < p.hn_off[lo + 1]; ++q) {
           const int b = p.hn_part[q];
-          if (d < __ldcg(&p.dist[b]) && relax_to(p, b, d)) enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+          if (PACKED) {
+            const DP cb = dp_load(p, b);
+            if ((u64)__double_as_longlong(d) < cb.d && dp_update(p, b, cb, d, KEY_HALO | (u64)s_id[lane]))
+              enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+          } else if (d < __ldcg(&p.dist[(i64)b * p.ds]) && relax_to(p, b, d)) {
+            enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+          }
         }
       }
     }
@@ -190,8 +253,10 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
       int k = lane;
       int j = k < m ? p.e2n_idx[s + k] : -1;
       double dj = 0.0, xj = 0.0, zj = 0.0, Uj = 0.0;
+      u64 kj = KEY_NONE, kjn = KEY_NONE;
       if (j >= 0) {
-        dj = __ldcg(&p.dist[j]);
+        if (PACKED) kj = __ldcg(p.keys + 2 * (i64)j + 1);
+        dj = __ldcg(&p.dist[(i64)j * p.ds]);
         xj = p.x[j];
         zj = p.z[j];
         Uj = p.U[j];
@@ -201,13 +266,16 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
         const int jn = kn < m ? p.e2n_idx[s + kn] : -1;
         double djn = 0.0, xjn = 0.0, zjn = 0.0, Ujn = 0.0;
         if (jn >= 0) {
-          djn = __ldcg(&p.dist[jn]);
+          if (PACKED) kjn = __ldcg(p.keys + 2 * (i64)jn + 1);
+          djn = __ldcg(&p.dist[(i64)jn * p.ds]);
           xjn = p.x[jn];
           zjn = p.z[jn];
           Ujn = p.U[jn];
         }
         if (dmin < dj) {  // else every released source is at or behind this target: nothing can improve
           double best = dj;
+          u64 bkey = kj;
+          bool changed = false;
           for (int q = 0; q < ns; ++q) {
             const double2 ud = sUd[q];  // (U, dist) of source q
             const double di = ud.y;
@@ -219,12 +287,35 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
               if (screen_cannot_improve(best, di, d2, __dadd_rn(ud.x, Uj))) continue;
             }
             const double delta = edge_delta(di, xz.x, xz.y, ud.x, xj, zj, Uj);
-            best = delta < best ? delta : best;
+            if (PACKED) {
+              // delta == di means the weight was absorbed (coincident nodes): a zero-weight coupling
+              const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
+              if (delta < best) {
+                best = delta;
+                bkey = key;
+                changed = true;
+              } else if (delta == best && !(key & KEY_ZMASK) && key < bkey) {
+                bkey = key;
+                changed = true;
+              }
+            } else {
+              best = delta < best ? delta : best;
+            }
           }
-          if (best < dj && relax_to(p, j, best)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+          if (PACKED) {
+            if (changed) {
+              DP cur_dp;
+              cur_dp.d = (u64)__double_as_longlong(dj);
+              cur_dp.k = kj;
+              if (dp_update(p, j, cur_dp, best, bkey)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+            }
+          } else if (best < dj && relax_to(p, j, best)) {
+            enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+          }
         }
         k = kn;
         j = jn;
+        kj = kjn;
         dj = djn;
         xj = xjn;
         zj = zjn;
@@ -235,6 +326,13 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
     if (gy == 0 && threadIdx.x == 0) atomicAdd(&p.counters[3], (u64)ns);
   }
   if (lane == 0 && evals) atomicAdd(&p.counters[2], evals);
+}
+__device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
+                                            i32* far_list, int fcur) {
+  if (p.ds == 2)
+    push2d_body_t<true>(p, near_cur, cur, near_next, far_list, fcur);
+  else
+    push2d_body_t<false>(p, near_cur, cur, near_next, far_list, fcur);
 }
 __global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
                                                            i32* __restrict__ near_next, i32* __restrict__ far_list,
@@ -250,7 +348,7 @@ __global__ void far_min_kernel(PP p, const i32* __restrict__ far_cur, int fcur) 
   if (slot < (i64)p.counters[4 + fcur]) {
     const int it = far_cur[slot];
     const unsigned m = p.far_mask[it];
-    if ((m >> lane) & 1u) best = (u64)__double_as_longlong(p.dist[p.item_first[it] + lane]);
+    if ((m >> lane) & 1u) best = (u64)__double_as_longlong(p.dist[(i64)(p.item_first[it] + lane) * p.ds]);
   }
   for (int o = 16; o; o >>= 1) {
     const u64 other = __shfl_xor_sync(FULL, best, o);
@@ -268,7 +366,7 @@ __global__ void far_release_kernel(PP p, const i32* __restrict__ far_cur, int fc
   const int it = far_cur[slot];
   const unsigned m = p.far_mask[it];
   const bool mine = (m >> lane) & 1u;
-  const bool rel = mine && p.dist[p.item_first[it] + lane] < tau;
+  const bool rel = mine && p.dist[(i64)(p.item_first[it] + lane) * p.ds] < tau;
   const unsigned relm = __ballot_sync(FULL, rel);
   if (lane == 0) {
     const unsigned keep = m & ~relm;
@@ -288,7 +386,8 @@ __global__ void far_release_kernel(PP p, const i32* __restrict__ far_cur, int fc
 __global__ void push_init_kernel(PP p, i64 n, int source, double delta, i32* __restrict__ near0) {
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    p.dist[i] = (i == source) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+    p.dist[i * p.ds] = (i == source) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+    if (p.ds == 2) p.keys[2 * i + 1] = KEY_NONE;
     p.prev[i] = -1;
   }
   if (i == 0) {
@@ -489,7 +588,7 @@ __global__ void far_min_dc_kernel(PP p) {
     const int it = far_cur[slot];
     const unsigned m = p.far_mask[it];
     if ((m >> lane) & 1u) {
-      const u64 b = (u64)__double_as_longlong(p.dist[p.item_first[it] + lane]);
+      const u64 b = (u64)__double_as_longlong(p.dist[(i64)(p.item_first[it] + lane) * p.ds]);
       best = b < best ? b : best;
     }
   }
@@ -513,7 +612,7 @@ __global__ void far_release_dc_kernel(PP p) {
     const int it = far_cur[slot];
     const unsigned m = p.far_mask[it];
     const bool mine = (m >> lane) & 1u;
-    const bool rel = mine && p.dist[p.item_first[it] + lane] < tau;
+    const bool rel = mine && p.dist[(i64)(p.item_first[it] + lane) * p.ds] < tau;
     const unsigned relm = __ballot_sync(FULL, rel);
     if (lane == 0) {
       const unsigned keep = m & ~relm;
@@ -573,7 +672,7 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP p, in
           const int it = __ldcg(&far_cur[slot]);
           const unsigned m = __ldcg(&p.far_mask[it]);
           if ((m >> lane) & 1u) {
-            const u64 b = (u64)__double_as_longlong(__ldcg(&p.dist[p.item_first[it] + lane]));
+            const u64 b = (u64)__double_as_longlong(__ldcg(&p.dist[(i64)(p.item_first[it] + lane) * p.ds]));
             best = b < best ? b : best;
           }
         }
@@ -592,7 +691,7 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP p, in
           const int it = __ldcg(&far_cur[slot]);
           const unsigned m = __ldcg(&p.far_mask[it]);
           const bool mine = (m >> lane) & 1u;
-          const bool rel = mine && __ldcg(&p.dist[p.item_first[it] + lane]) < tau;
+          const bool rel = mine && __ldcg(&p.dist[(i64)(p.item_first[it] + lane) * p.ds]) < tau;
           const unsigned relm = __ballot_sync(FULL, rel);
           if (lane == 0) {
             const unsigned keep = m & ~relm;
@@ -620,6 +719,36 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP p, in
     p.ctl[4] += rounds;
     p.ctl[5] += pushes;
   }
+}
+
+// ---- packed mode epilogue: split the pairs into dist / prev; halo-coupled nodes take the predecessor of their
+// twin (update_halo!: p[h2] = p[h1], bfm.jl:59), resolved in a few passes for twin chains.
+__global__ void unpack_kernel(PP p, i64 n, int source, double* __restrict__ dist_out) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = p.dist[2 * i];
+  dist_out[i] = d;
+  const u64 k = p.keys[2 * i + 1];
+  if (i == source || k == KEY_NONE) return;  // keeps the halo-init / unset value like the reference
+  if (k & KEY_HALO)
+    p.prev[i] = -3 - (i32)(k & 0xffffffffull);
+  else
+    p.prev[i] = (i32)(k & 0xffffffffull);
+}
+__global__ void halo_prev_fix_kernel(PP p, const i32* __restrict__ h2, i64 rows, int source, int last) {
+  const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int b = h2[r];
+  const i32 pv = p.prev[b];
+  if (pv > -3) return;
+  const int t = -3 - pv;
+  const i32 pt = p.prev[t];
+  if (t == source)
+    p.prev[b] = source;
+  else if (pt > -3 && pt >= 0)
+    p.prev[b] = pt;
+  else if (last)
+    p.prev[b] = t;  // unresolved chain: the twin itself is a valid zero-weight predecessor
 }
 
 int ensure_push_workspace(rt_mesh* h) {
@@ -675,7 +804,11 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.hn_index = m.hn_index.p;
   p.n_hn = (int)m.n_hn;
   p.source = -1;
-  p.dist = m.dist.p;
+  const bool packed = h->opts.packed_prev != 0;
+  if (packed && !m.dp.p) RT_TRY(m.dp.alloc(2 * (size_t)m.n));
+  p.dist = packed ? m.dp.p : m.dist.p;
+  p.ds = packed ? 2 : 1;
+  p.keys = packed ? (u64*)m.dp.p : nullptr;
   p.prev = m.prev.p;
   p.pend_mask = m.pend_mask.p;
   p.far_mask = m.far_mask.p;
@@ -842,38 +975,52 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     st.vertex_updates += (i64)ch[3];
     // ---- predecessors
     cudaEventRecord(evr0, s);
-    if (m.n_hinit)
-      prev_halo_init_kernel<<<grid_for(m.n_hinit, 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p, m.n_hinit);
-    cudaMemsetAsync(m.counters.p + 6, 0, sizeof(u64), s);
-    prev_tight_kernel<<<(unsigned)std::min<i64>((m.n_items + 7) / 8, (i64)sm_count * 8), 256, 0, s>>>(
-        p, m.n_items, src, m.unresolved[0].p);
-    st.total_launches += 2;
-    st.relaxed_edges += m.graph_edges;  // the tightness pass walks every scan list once
-    cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
-    if (cudaStreamSynchronize(s) != cudaSuccess) {
-      rc = RT_ERR_CUDA;
-      break;
-    }
-    i64 n_un = (i64)ch[6];
+    i64 n_un = 0;
     int ucur = 0;
-    for (int iter = 0; iter < 64 && n_un > 0; ++iter) {
-      cudaMemsetAsync(m.counters.p + 7, 0, sizeof(u64), s);
-      prev_resolve_kernel<<<grid_for(n_un, 128), 128, 0, s>>>(p, m.unresolved[ucur].p, n_un, src,
-                                                             m.unresolved[ucur ^ 1].p, m.pending_prev.p);
-      prev_apply_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un, m.pending_prev.p,
-                                                            m.unresolved[ucur ^ 1].p);
+    if (packed) {
+      // the keys already hold a consistent predecessor per node: split the pairs, resolve the halo couplings
+      if (m.n_hinit)
+        prev_halo_init_kernel<<<grid_for(m.n_hinit, 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p, m.n_hinit);
+      unpack_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, src, m.dist.p);
       st.total_launches += 2;
+      if (m.halo_rows > 0)
+        for (int pass = 0; pass < 4; ++pass) {
+          halo_prev_fix_kernel<<<grid_for(m.halo_rows, 256), 256, 0, s>>>(p, m.halo_h2.p, m.halo_rows, src, pass == 3);
+          st.total_launches += 1;
+        }
+    } else {
+      if (m.n_hinit)
+        prev_halo_init_kernel<<<grid_for(m.n_hinit, 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p, m.n_hinit);
+      cudaMemsetAsync(m.counters.p + 6, 0, sizeof(u64), s);
+      prev_tight_kernel<<<(unsigned)std::min<i64>((m.n_items + 7) / 8, (i64)sm_count * 8), 256, 0, s>>>(
+          p, m.n_items, src, m.unresolved[0].p);
+      st.total_launches += 2;
+      st.relaxed_edges += m.graph_edges;  // the tightness pass walks every scan list once
       cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
       if (cudaStreamSynchronize(s) != cudaSuccess) {
         rc = RT_ERR_CUDA;
         break;
       }
-      const i64 left = (i64)ch[7];
-      ucur ^= 1;
-      if (left == n_un) break;  // no progress: the rest keeps its halo-init / unset predecessor
-      n_un = left;
+      n_un = (i64)ch[6];
+      for (int iter = 0; iter < 64 && n_un > 0; ++iter) {
+        cudaMemsetAsync(m.counters.p + 7, 0, sizeof(u64), s);
+        prev_resolve_kernel<<<grid_for(n_un, 128), 128, 0, s>>>(p, m.unresolved[ucur].p, n_un, src,
+                                                               m.unresolved[ucur ^ 1].p, m.pending_prev.p);
+        prev_apply_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un, m.pending_prev.p,
+                                                              m.unresolved[ucur ^ 1].p);
+        st.total_launches += 2;
+        cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) {
+          rc = RT_ERR_CUDA;
+          break;
+        }
+        const i64 left = (i64)ch[7];
+        ucur ^= 1;
+        if (left == n_un) break;  // no progress: the rest keeps its halo-init / unset predecessor
+        n_un = left;
+      }
+      if (rc != RT_OK) break;
     }
-    if (rc != RT_OK) break;
     if (n_un > 0) prev_giveup_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un);
     cudaEventRecord(evr1, s);
     cudaEventRecord(ev1, s);

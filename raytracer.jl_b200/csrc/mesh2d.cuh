@@ -54,6 +54,7 @@ struct Mesh2D {
   DevBuf<i32> unresolved[2];
   DevBuf<int> pending_prev;
   DevBuf<int> ctl;
+  DevBuf<double> dp;                   // packed (travel time bits, predecessor key) pairs, 16 B per node
   bool push_ready = false;
 };
 

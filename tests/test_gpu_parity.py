@@ -376,3 +376,67 @@ def test_bfm3d_near_far_schedule(rt, O, nn, lv, cs):
             assert path[-1] == s and np.all(np.diff(dist[path - 1]) <= 0)
     assert D.stats["relaxed_edges"] > 0
     rt.bfm3d(g, 1, U, schedule="jacobi")
+
+
+def test_annulus_schedules_agree_at_scale(rt):
+    """Size-independent properties on a mesh the oracle is too slow for (180x50 @5 km, 0.76 M nodes, E_graph
+    1.2e9): both schedules give bit-identical travel times; near-far predecessors are bit-exactly tight."""
+    gr, G, halo = rt.init_annulus(180, 50, spacing=5.0)
+    prof = rt.velocity_profile()
+    Vp = rt.interpolate_velocity(gr.r, rt.LinearInterpolation(prof.r, prof.Vp))
+    src = rt.closest_point(gr, 0.0, R, system="polar")
+    Dj = rt.bfm(G, halo, src, gr, Vp, schedule="jacobi")
+    Dn = rt.bfm(G, halo, src, gr, Vp, schedule="near-far")
+    assert np.array_equal(Dj.dist, Dn.dist)
+    assert Dn.stats["relaxed_edges"] * 5 < Dj.stats["relaxed_edges"]
+    d, p = Dn.dist, Dn.prev
+    assert d[src - 1] == 0.0 and np.isfinite(d).all()
+    assert np.array_equal(d[halo[:, 0] - 1], d[halo[:, 1] - 1])  # twins
+    i = np.nonzero((p > 0))[0]
+    tight = d[p[i] - 1] + weight2d(gr.x, gr.z, Vp, i, p[i] - 1) == d[i]
+    halo_nodes = np.zeros(len(d), bool)
+    halo_nodes[halo.ravel() - 1] = True
+    assert np.all(tight | halo_nodes[i])  # non-tight only where the value came through a zero-weight twin coupling
+    assert tight.mean() > 0.95
+    recv = rt.closest_point(gr, np.deg2rad(np.arange(10.0, 351.0, 10.0)), np.full(35, R), system="polar")
+    for path_j, path_n in zip(rt.recontruct_path(Dj.prev, src, recv), rt.recontruct_path(Dn.prev, src, recv)):
+        assert path_j[-1] == src and path_n[-1] == src
+        assert np.all(np.diff(d[path_n - 1]) <= 0)
+        # the two paths may differ in node ids on exact ties, never in travel time along them
+        assert d[path_j[0] - 1] == d[path_n[0] - 1]
+
+
+def test_config2_full_size_properties(rt):
+    """BASELINE config[1] at full size (annulus 1440x400 @0.25 km, 106.6 M nodes; the reference cannot build it):
+    properties that need no oracle."""
+    import ctypes as C
+    import torch
+    gr, G, halo = rt.init_annulus(1440, 400, spacing=0.25, export=False)
+    n = gr.nnods
+    assert n == 106619041  # SURVEY 8: ~106.6 M
+    h = gr._handle
+    prof = rt.velocity_profile()
+    itp = rt.LinearInterpolation(prof.r, prof.Vp)
+    x_d, z_d, th_d, r_d = h.coords_dev()
+    U = torch.empty(n, dtype=torch.float64, device="cuda")
+    rt.api.check(rt.lib().rt_interp_velocity_dev(itp.knots, itp.values, len(itp.knots), r_d, n, -1.0, U.data_ptr()))
+    src = rt.closest_point(gr, 0.0, R, system="polar")
+    h.set_option("schedule", 1)
+    d = torch.empty(n, dtype=torch.float64, device="cuda")
+    p = torch.empty(n, dtype=torch.int32, device="cuda")
+    st = rt.RtStats()
+    rt.api.check(rt.lib().rt_bfm_solve_dev(h.h, U.data_ptr(), np.array([src], np.int64), 1, 64, d.data_ptr(),
+                                           p.data_ptr(), C.byref(st)))
+    assert float(d[src - 1]) == 0.0 and bool(torch.isfinite(d).all())
+    assert int((p < 0).sum()) == 1  # only the source has no predecessor
+    nrp, nt = gr.nr, gr.ntheta
+    ring = d[:nrp * nt].reshape(nt, nrp)
+    mirror = torch.flip(ring[1:], dims=[0])
+    assert float(((ring[1:] - mirror).abs() / ring[1:].clamp_min(1e-9)).max()) < 1e-9  # theta <-> 2 pi - theta
+    t180 = float(ring[nt // 2, nrp - 1])
+    assert 1150.0 < t180 < 1212.08  # CMB-diffracted first arrival, below the straight-through bound
+    assert st.relaxed_edges < 3 * st.graph_edges
+    rec = rt.closest_point(gr, np.deg2rad(np.array([30.0, 90.0, 180.0])), np.full(3, R), system="polar")
+    off = np.zeros(4, np.int64)
+    rt.api.check(rt.lib().rt_reconstruct_paths_dev(p.data_ptr(), n, src, rec, 3, off, None, 0))
+    assert np.all(np.diff(off) > 10)
