@@ -397,7 +397,7 @@ def test_annulus_schedules_agree_at_scale(rt):
     halo_nodes = np.zeros(len(d), bool)
     halo_nodes[halo.ravel() - 1] = True
     assert np.all(tight | halo_nodes[i])  # non-tight only where the value came through a zero-weight twin coupling
-    assert tight.mean() > 0.95
+    assert tight.mean() > 0.85  # ~13 % of the nodes of this mesh are halo twins
     recv = rt.closest_point(gr, np.deg2rad(np.arange(10.0, 351.0, 10.0)), np.full(35, R), system="polar")
     for path_j, path_n in zip(rt.recontruct_path(Dj.prev, src, recv), rt.recontruct_path(Dn.prev, src, recv)):
         assert path_j[-1] == src and path_n[-1] == src
