@@ -383,18 +383,23 @@ __device__ __forceinline__ void enqueue3(const Q3& p, i64 J, double d, double ta
 
 constexpr int P3_BLOCK = 128;
 
+// Warp-level work unit = (near-list slot, dz): the warp keeps the 32 sources of its item in a private shared-memory
+// slab (no block barrier), then walks the (32 + 2w) target columns of that z-plane; for each lane the loads of all
+// 2w+1 target rows are issued back to back (memory-level parallelism) before any of them is evaluated.
+constexpr int P3_MAXW = 7;  // 2w+1 for star_levels <= 2 (w <= 3)
 __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
-  __shared__ double sX[32], sY[32], sZ[32], sU[32], sD[32];
-  __shared__ unsigned s_mask;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  __shared__ double sm_src[P3_BLOCK / 32][5][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double(*S)[32] = sm_src[warp];
   const int w = p.w, W = 2 * w + 1;
   const i64 n_near = (i64)__ldcg(&p.counters[cur]);
   const double tau = __ldcg(&p.tau[0]);
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
   u64 evals = 0;
-  // unit = (slot, dz): one CTA per z-plane of the target block, warps over its y rows
-  for (i64 unit = blockIdx.x; unit < n_near * W; unit += gridDim.x) {
+  for (i64 unit = gw; unit < n_near * W; unit += nw) {
     const i64 slot = unit / W;
     const int dzi = (int)(unit - slot * W) - w;
     const int it = __ldcg(&near_cur[slot]);
@@ -402,68 +407,79 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
     const i64 line = it / p.nbx;
     const int sy = (int)(line % p.ny), sz = (int)(line / p.ny);
     const int tz = sz + dzi;
-    if (tz < 0 || tz >= p.nz) continue;  // block-uniform
+    if (tz < 0 || tz >= p.nz) continue;  // warp-uniform
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
-    __syncthreads();
-    if (warp == 0) {
+    if (mask == 0u) continue;
+    __syncwarp();
+    {
       const int gx = bx * 32 + lane;
       if (((mask >> lane) & 1u) && gx < p.nx) {
         const i64 I = (i64)gx + (i64)p.nx * ((i64)sy + (i64)p.ny * sz);
-        sX[lane] = p.X[I];
-        sY[lane] = p.Y[I];
-        sZ[lane] = p.Z[I];
-        sU[lane] = p.U[I];
-        sD[lane] = __ldcg(&p.dist[I]);
+        S[0][lane] = p.X[I];
+        S[1][lane] = p.Y[I];
+        S[2][lane] = p.Z[I];
+        S[3][lane] = p.U[I];
+        S[4][lane] = __ldcg(&p.dist[I]);
       } else {
-        sD[lane] = INF;
+        S[4][lane] = INF;
       }
-      if (lane == 0) s_mask = mask;
     }
-    __syncthreads();
-    const unsigned m = s_mask;
-    if (m == 0u) continue;
+    __syncwarp();
     const int x_lo = max(0, bx * 32 - w), x_hi = min(p.nx - 1, bx * 32 + 31 + w);
-    for (int dyi = warp; dyi < W; dyi += nwarp) {
-      const int ty = sy + dyi - w;
-      if (ty < 0 || ty >= p.ny) continue;
-      for (int tx = x_lo + lane; tx <= x_hi; tx += 32) {
-        const i64 J = (i64)tx + (i64)p.nx * ((i64)ty + (i64)p.ny * tz);
-        const double dj = __ldcg(&p.dist[J]);
-        const double xj = p.X[J], yj = p.Y[J], zj = p.Z[J], uj = p.U[J];
+    const int y0 = max(0, sy - w), y1 = min(p.ny - 1, sy + w);
+    for (int tx = x_lo + lane; tx <= x_hi; tx += 32) {
+      double tj[P3_MAXW], txv[P3_MAXW], tyv[P3_MAXW], tzv[P3_MAXW], tu[P3_MAXW];
+#pragma unroll
+      for (int r = 0; r < P3_MAXW; ++r) {
+        const int ty = y0 + r;
+        if (ty <= y1) {
+          const i64 J = (i64)tx + (i64)p.nx * ((i64)ty + (i64)p.ny * tz);
+          tj[r] = __ldcg(&p.dist[J]);
+          txv[r] = p.X[J];
+          tyv[r] = p.Y[J];
+          tzv[r] = p.Z[J];
+          tu[r] = p.U[J];
+        }
+      }
+      const int q0 = max(tx - w, bx * 32) - bx * 32, q1 = min(tx + w, bx * 32 + 31) - bx * 32;
+#pragma unroll
+      for (int r = 0; r < P3_MAXW; ++r) {
+        const int ty = y0 + r;
+        if (ty > y1) continue;
+        const double dj = tj[r];
         double best = dj;
-        const int q0 = max(tx - w, bx * 32) - bx * 32, q1 = min(tx + w, bx * 32 + 31) - bx * 32;
         for (int q = q0; q <= q1; ++q) {
-          const double di = sD[q];  // INF if not released
+          const double di = S[4][q];  // INF if not released
           if (!(di < best)) continue;
-          if (!p.self && dyi == w && dzi == 0 && bx * 32 + q == tx) continue;
-          const double dx = __dsub_rn(sX[q], xj), dy = __dsub_rn(sY[q], yj), dz = __dsub_rn(sZ[q], zj);
+          if (!p.self && ty == sy && dzi == 0 && bx * 32 + q == tx) continue;
+          const double dx = __dsub_rn(S[0][q], txv[r]), dy = __dsub_rn(S[1][q], tyv[r]), dz = __dsub_rn(S[2][q], tzv[r]);
           const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-          const double ss = fabs(__dadd_rn(sU[q], uj));
-          if (screen_cannot_improve(best, di, d2, ss)) continue;
-          const double delta = cand3(di, sX[q], sY[q], sZ[q], sU[q], xj, yj, zj, uj);
+          if (screen_cannot_improve(best, di, d2, fabs(__dadd_rn(S[3][q], tu[r])))) continue;
+          const double delta = cand3(di, S[0][q], S[1][q], S[2][q], S[3][q], txv[r], tyv[r], tzv[r], tu[r]);
           best = delta < best ? delta : best;
         }
         if (best < dj) {
+          const i64 J = (i64)tx + (i64)p.nx * ((i64)ty + (i64)p.ny * tz);
           const u64 bits = (u64)__double_as_longlong(best);
           const u64 old = atomicMin((u64*)&p.dist[J], bits);
           if (bits < old) enqueue3(p, J, best, tau, near_next, cur ^ 1, far_list, fcur);
         }
       }
     }
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
       // evaluations of this z-plane: per released source, clipped x-extent times clipped y-extent
       u64 e = 0;
-      const int ycnt = min(p.ny - 1, sy + w) - max(0, sy - w) + 1;
+      const int ycnt = y1 - y0 + 1;
       for (int q = 0; q < 32; ++q)
-        if ((m >> q) & 1u) {
+        if ((mask >> q) & 1u) {
           const int gx = bx * 32 + q;
           e += (u64)(min(p.nx - 1, gx + w) - max(0, gx - w) + 1) * (u64)ycnt;
         }
       evals += e;
-      if (dzi == 0) atomicAdd(&p.counters[3], (u64)__popc(m));
+      if (dzi == 0) atomicAdd(&p.counters[3], (u64)__popc(mask));
     }
   }
-  if (threadIdx.x == 0 && evals) atomicAdd(&p.counters[2], evals);
+  if (lane == 0 && evals) atomicAdd(&p.counters[2], evals);
 }
 
 __global__ void round_begin3_kernel(Q3 p) {
