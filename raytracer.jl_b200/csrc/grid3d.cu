@@ -386,7 +386,6 @@ constexpr int P3_BLOCK = 128;
 // Warp-level work unit = (near-list slot, dz): the warp keeps the 32 sources of its item in a private shared-memory
 // slab (no block barrier), then walks the (32 + 2w) target columns of that z-plane; for each lane the loads of all
 // 2w+1 target rows are issued back to back (memory-level parallelism) before any of them is evaluated.
-constexpr int P3_MAXW = 7;  // 2w+1 for star_levels <= 2 (w <= 3)
 __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
   __shared__ double sm_src[P3_BLOCK / 32][5][32];
@@ -425,52 +424,41 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
       }
     }
     __syncwarp();
-    const int x_lo = max(0, bx * 32 - w), x_hi = min(p.nx - 1, bx * 32 + 31 + w);
+    // targets of this unit: rows y0..y1 times the columns within +-w of the released span (a thin wavefront
+    // releases only one or two nodes of an x-line per round, so the block is usually ~5 x 5, not 36 x 5)
+    const int first = __ffs(mask) - 1, last = 31 - __clz(mask);
+    const int xa = max(0, bx * 32 + first - w), xb = min(p.nx - 1, bx * 32 + last + w);
     const int y0 = max(0, sy - w), y1 = min(p.ny - 1, sy + w);
-    for (int tx = x_lo + lane; tx <= x_hi; tx += 32) {
-      double tj[P3_MAXW], txv[P3_MAXW], tyv[P3_MAXW], tzv[P3_MAXW], tu[P3_MAXW];
-#pragma unroll
-      for (int r = 0; r < P3_MAXW; ++r) {
-        const int ty = y0 + r;
-        if (ty <= y1) {
-          const i64 J = (i64)tx + (i64)p.nx * ((i64)ty + (i64)p.ny * tz);
-          tj[r] = __ldcg(&p.dist[J]);
-          txv[r] = p.X[J];
-          tyv[r] = p.Y[J];
-          tzv[r] = p.Z[J];
-          tu[r] = p.U[J];
-        }
-      }
+    const int ncol = xb - xa + 1, nt = ncol * (y1 - y0 + 1);
+    for (int t = lane; t < nt; t += 32) {
+      const int r = t / ncol;
+      const int tx = xa + (t - r * ncol), ty = y0 + r;
+      const i64 J = (i64)tx + (i64)p.nx * ((i64)ty + (i64)p.ny * tz);
+      const double dj = __ldcg(&p.dist[J]);
+      const double xj = p.X[J], yj = p.Y[J], zj = p.Z[J], uj = p.U[J];
+      double best = dj;
       const int q0 = max(tx - w, bx * 32) - bx * 32, q1 = min(tx + w, bx * 32 + 31) - bx * 32;
-#pragma unroll
-      for (int r = 0; r < P3_MAXW; ++r) {
-        const int ty = y0 + r;
-        if (ty > y1) continue;
-        const double dj = tj[r];
-        double best = dj;
-        for (int q = q0; q <= q1; ++q) {
-          const double di = S[4][q];  // INF if not released
-          if (!(di < best)) continue;
-          if (!p.self && ty == sy && dzi == 0 && bx * 32 + q == tx) continue;
-          const double dx = __dsub_rn(S[0][q], txv[r]), dy = __dsub_rn(S[1][q], tyv[r]), dz = __dsub_rn(S[2][q], tzv[r]);
-          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-          if (screen_cannot_improve(best, di, d2, fabs(__dadd_rn(S[3][q], tu[r])))) continue;
-          const double delta = cand3(di, S[0][q], S[1][q], S[2][q], S[3][q], txv[r], tyv[r], tzv[r], tu[r]);
-          best = delta < best ? delta : best;
-        }
-        if (best < dj) {
-          const i64 J = (i64)tx + (i64)p.nx * ((i64)ty + (i64)p.ny * tz);
-          const u64 bits = (u64)__double_as_longlong(best);
-          const u64 old = atomicMin((u64*)&p.dist[J], bits);
-          if (bits < old) enqueue3(p, J, best, tau, near_next, cur ^ 1, far_list, fcur);
-        }
+      for (int q = q0; q <= q1; ++q) {
+        const double di = S[4][q];  // INF if not released
+        if (!(di < best)) continue;
+        if (!p.self && ty == sy && dzi == 0 && bx * 32 + q == tx) continue;
+        const double dx = __dsub_rn(S[0][q], xj), dy = __dsub_rn(S[1][q], yj), dz = __dsub_rn(S[2][q], zj);
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (screen_cannot_improve(best, di, d2, fabs(__dadd_rn(S[3][q], uj)))) continue;
+        const double delta = cand3(di, S[0][q], S[1][q], S[2][q], S[3][q], xj, yj, zj, uj);
+        best = delta < best ? delta : best;
+      }
+      if (best < dj) {
+        const u64 bits = (u64)__double_as_longlong(best);
+        const u64 old = atomicMin((u64*)&p.dist[J], bits);
+        if (bits < old) enqueue3(p, J, best, tau, near_next, cur ^ 1, far_list, fcur);
       }
     }
     if (lane == 0) {
       // evaluations of this z-plane: per released source, clipped x-extent times clipped y-extent
       u64 e = 0;
       const int ycnt = y1 - y0 + 1;
-      for (int q = 0; q < 32; ++q)
+      for (int q = first; q <= last; ++q)
         if ((mask >> q) & 1u) {
           const int gx = bx * 32 + q;
           e += (u64)(min(p.nx - 1, gx + w) - max(0, gx - w) + 1) * (u64)ycnt;
