@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 
+int prev_to_host_i64_staged(const i32* prev_dev, i64 count, i64* out, i64* stage64, cudaStream_t s);
 int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* receivers, i64 nrec, i64* path_off,
                              i64* path_idx, i64 cap);
 int prev_host_to_device_i32(const i64* prev, i64 n, DevBuf<i32>& out);
@@ -194,20 +195,24 @@ int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t ns
   RT_ARG(m && U && sources && nsrc >= 0, "null argument");
   RT_CUDA(cudaSetDevice(m->device));
   const i64 n = mesh_n(m);
-  DevBuf<double> dU, dd;
-  DevBuf<i32> dp;
-  RT_TRY(dU.upload(U, n));
-  RT_CUDA(cudaDeviceSynchronize());
+  cudaStream_t cs = m->stream;
+  if (m->stage_U.n != (size_t)n) RT_TRY(m->stage_U.alloc(n));
+  if (dist_out && m->stage_dist.n != (size_t)n) RT_TRY(m->stage_dist.alloc(n));
+  if (prev_out && m->stage_prev.n != (size_t)n) {
+    RT_TRY(m->stage_prev.alloc(n));
+    RT_TRY(m->stage_prev64.alloc(n));
+  }
+  RT_CUDA(cudaMemcpyAsync(m->stage_U.p, U, n * sizeof(double), cudaMemcpyHostToDevice, cs));
   rt_stats total = {};
   // one source at a time keeps the staging buffers at n entries regardless of the batch size
-  if (dist_out) RT_TRY(dd.alloc(n));
-  if (prev_out) RT_TRY(dp.alloc(n));
   for (i64 s = 0; s < nsrc; ++s) {
     rt_stats st = {};
-    RT_TRY(rt_bfm_solve_dev(m, dU.p, sources + s, 1, precision, dist_out ? dd.p : nullptr,
-                            prev_out ? dp.p : nullptr, &st));
-    if (dist_out) RT_CUDA(cudaMemcpy(dist_out + s * n, dd.p, n * sizeof(double), cudaMemcpyDeviceToHost));
-    if (prev_out) RT_TRY(prev_to_host_i64(dp.p, n, prev_out + s * n, m->stream));
+    RT_TRY(rt_bfm_solve_dev(m, m->stage_U.p, sources + s, 1, precision, dist_out ? m->stage_dist.p : nullptr,
+                            prev_out ? m->stage_prev.p : nullptr, &st));
+    if (dist_out)
+      RT_CUDA(cudaMemcpyAsync(dist_out + s * n, m->stage_dist.p, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (prev_out) RT_TRY(prev_to_host_i64_staged(m->stage_prev.p, n, prev_out + s * n, m->stage_prev64.p, cs));
+    RT_CUDA(cudaStreamSynchronize(cs));
     total.sweeps += st.sweeps;
     total.relaxed_edges += st.relaxed_edges;
     total.vertex_updates += st.vertex_updates;

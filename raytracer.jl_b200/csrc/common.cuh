@@ -132,6 +132,10 @@ struct rt_mesh {
   SolverOpts opts;
   Mesh2D* m2 = nullptr;
   Grid3D* g3 = nullptr;
+  // staging buffers of the host-buffer entry point rt_bfm_solve (kept across calls)
+  DevBuf<double> stage_U, stage_dist;
+  DevBuf<i32> stage_prev;
+  DevBuf<i64> stage_prev64;
 };
 
 // 2-D (mesh2d.cu / bfm2d.cu)

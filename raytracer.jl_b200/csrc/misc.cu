@@ -203,6 +203,12 @@ int prev_to_host_i64(const i32* prev_dev, i64 count, i64* out, cudaStream_t s) {
   return RT_OK;
 }
 
+int prev_to_host_i64_staged(const i32* prev_dev, i64 count, i64* out, i64* stage64, cudaStream_t s) {
+  prev_i32_to_i64_kernel<<<grid_for(count, 256), 256, 0, s>>>(prev_dev, stage64, count);
+  RT_CUDA(cudaMemcpyAsync(out, stage64, count * sizeof(i64), cudaMemcpyDeviceToHost, s));
+  return RT_OK;
+}
+
 // prev_dev: 0-based int32 table on the device.  receivers: host, 1-based.
 int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* receivers, i64 nrec,
                              i64* path_off, i64* path_idx, i64 cap) {
