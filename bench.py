@@ -249,8 +249,6 @@ def run_gpu(args):
         nsolved = args.steps * world
         value = e_graph * nsolved / (wall_ms * 1e-3) / 1e9
         bytes_alg = prof["relaxed_edges"] * 12 + prof["vertex_updates"] * wl.bv
-        if wl.schedule != "jacobi":  # the tightness (prev) pass is counted in relaxed_edges but not in relax_ms
-            bytes_alg -= e_graph * prof_steps * 12
         relax_ms = max(prof["relax_ms"], 1e-9)
         achieved = bytes_alg / (relax_ms * 1e-3) / 1e9
         out = {

@@ -37,7 +37,7 @@ typedef struct rt_mesh rt_mesh; /* opaque: a graph resident in HBM (2-D annulus 
  * println("Converged in $it iterations") src/SSSP/bfm.jl:49 (it == sweeps + 1 there). */
 typedef struct rt_stats {
   int64_t sweeps;          /* relaxation sweeps executed                                                    */
-  int64_t relaxed_edges;   /* E_relaxed: candidate (edge) evaluations executed by the relax kernels         */
+  int64_t relaxed_edges;   /* E_relaxed: candidate (edge) evaluations of the relax / push kernels           */
   int64_t vertex_updates;  /* active-vertex updates (vertices relaxed, summed over sweeps)                   */
   int64_t graph_edges;     /* E_graph: sum over vertices of |scan list| (reference multiplicities, per source)*/
   double kernel_ms;        /* device time of the solve loop(s), CUDA events on the solver stream            */

@@ -995,7 +995,6 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       prev_tight_kernel<<<(unsigned)std::min<i64>((m.n_items + 7) / 8, (i64)sm_count * 8), 256, 0, s>>>(
           p, m.n_items, src, m.unresolved[0].p);
       st.total_launches += 2;
-      st.relaxed_edges += m.graph_edges;  // the tightness pass walks every scan list once
       cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
       if (cudaStreamSynchronize(s) != cudaSuccess) {
         rc = RT_ERR_CUDA;
