@@ -196,22 +196,25 @@ int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t ns
   RT_CUDA(cudaSetDevice(m->device));
   const i64 n = mesh_n(m);
   cudaStream_t cs = m->stream;
+  // sources go through in chunks so that small meshes can advance several sources in lock step while the
+  // staging buffers stay bounded (<= 32 tables, <= ~2 GB)
+  i64 chunk = std::max<i64>(1, std::min<i64>(std::min<i64>(nsrc, 32), ((i64)1 << 28) / std::max<i64>(n, 1)));
   if (m->stage_U.n != (size_t)n) RT_TRY(m->stage_U.alloc(n));
-  if (dist_out && m->stage_dist.n != (size_t)n) RT_TRY(m->stage_dist.alloc(n));
-  if (prev_out && m->stage_prev.n != (size_t)n) {
-    RT_TRY(m->stage_prev.alloc(n));
-    RT_TRY(m->stage_prev64.alloc(n));
+  if (dist_out && m->stage_dist.n < (size_t)(chunk * n)) RT_TRY(m->stage_dist.alloc(chunk * n));
+  if (prev_out && m->stage_prev.n < (size_t)(chunk * n)) {
+    RT_TRY(m->stage_prev.alloc(chunk * n));
+    RT_TRY(m->stage_prev64.alloc(chunk * n));
   }
   RT_CUDA(cudaMemcpyAsync(m->stage_U.p, U, n * sizeof(double), cudaMemcpyHostToDevice, cs));
   rt_stats total = {};
-  // one source at a time keeps the staging buffers at n entries regardless of the batch size
-  for (i64 s = 0; s < nsrc; ++s) {
+  for (i64 s = 0; s < nsrc; s += chunk) {
+    const i64 c = std::min(chunk, nsrc - s);
     rt_stats st = {};
-    RT_TRY(rt_bfm_solve_dev(m, m->stage_U.p, sources + s, 1, precision, dist_out ? m->stage_dist.p : nullptr,
+    RT_TRY(rt_bfm_solve_dev(m, m->stage_U.p, sources + s, c, precision, dist_out ? m->stage_dist.p : nullptr,
                             prev_out ? m->stage_prev.p : nullptr, &st));
     if (dist_out)
-      RT_CUDA(cudaMemcpyAsync(dist_out + s * n, m->stage_dist.p, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
-    if (prev_out) RT_TRY(prev_to_host_i64_staged(m->stage_prev.p, n, prev_out + s * n, m->stage_prev64.p, cs));
+      RT_CUDA(cudaMemcpyAsync(dist_out + s * n, m->stage_dist.p, c * n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (prev_out) RT_TRY(prev_to_host_i64_staged(m->stage_prev.p, c * n, prev_out + s * n, m->stage_prev64.p, cs));
     RT_CUDA(cudaStreamSynchronize(cs));
     total.sweeps += st.sweeps;
     total.relaxed_edges += st.relaxed_edges;
@@ -240,6 +243,9 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
   } else if (!std::strcmp(key, "delta")) {
     RT_ARG(value >= 0.0, "delta must be >= 0");
     m->opts.delta = value;
+  } else if (!std::strcmp(key, "batch")) {
+    RT_ARG(value >= 0.0 && value <= 32.0, "batch must be in 0..32");
+    m->opts.batch = (int)value;
   } else if (!std::strcmp(key, "packed_prev")) {
     m->opts.packed_prev = value != 0.0;
   } else if (!std::strcmp(key, "persistent")) {

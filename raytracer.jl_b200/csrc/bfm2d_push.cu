@@ -61,7 +61,33 @@ struct PP {
   i32* farq[2];
   int* ctl;       // device-side round control: [0] cur [1] fcur [2] mode (1 push, 2 advance) [3] done [4] rounds
                   // [5] push rounds
+  // batch of sources solved in lock step (state arrays hold nb slices; pp_view() selects one)
+  int nb;
+  i64 n, n_items;
+  const int* sources;  // [nb] 0-based
 };
+
+// slice b of the per-source state (mesh arrays are shared)
+__device__ __forceinline__ PP pp_view(const PP& p, int b) {
+  PP v = p;
+  v.dist = p.dist + (i64)b * p.n * p.ds;
+  v.keys = p.keys ? p.keys + (i64)b * p.n * 2 : nullptr;
+  v.prev = p.prev + (i64)b * p.n;
+  v.pend_mask = p.pend_mask + (i64)b * p.n_items;
+  v.far_mask = p.far_mask + (i64)b * p.n_items;
+  v.infar = p.infar + (i64)b * p.n_items;
+  v.cur_mask = p.cur_mask + (i64)b * p.n_items;
+  v.counters = p.counters + (i64)b * 8;
+  v.tau = p.tau + (i64)b * 4;
+  v.nearq[0] = p.nearq[0] + (i64)b * p.n_items;
+  v.nearq[1] = p.nearq[1] + (i64)b * p.n_items;
+  v.farq[0] = p.farq[0] + (i64)b * p.n_items;
+  v.farq[1] = p.farq[1] + (i64)b * p.n_items;
+  v.ctl = p.ctl + (i64)b * 8;
+  v.source = p.sources ? p.sources[b] : p.source;
+  v.nb = 1;
+  return v;
+}
 
 __device__ __forceinline__ double edge_delta(double di, double xi, double zi, double Ui, double xj, double zj,
                                              double Uj) {
@@ -383,7 +409,10 @@ __global__ void far_release_kernel(PP p, const i32* __restrict__ far_cur, int fc
   }
 }
 
-__global__ void push_init_kernel(PP p, i64 n, int source, double delta, i32* __restrict__ near0) {
+__global__ void push_init_kernel(PP pb, i64 n, double delta) {
+  const PP p = pp_view(pb, blockIdx.y);
+  const int source = p.source;
+  i32* near0 = p.nearq[0];
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     p.dist[i * p.ds] = (i == source) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
@@ -394,7 +423,10 @@ __global__ void push_init_kernel(PP p, i64 n, int source, double delta, i32* __r
     const int it = p.node_item[source];
     p.pend_mask[it] = 1u << (source - p.item_first[it]);
     near0[0] = it;
-    p.counters[0] = 1ull;
+    for (int k = 0; k < 8; ++k) {
+      p.counters[k] = k == 0 ? 1ull : 0ull;
+      p.ctl[k] = 0;
+    }
     p.tau[0] = delta;
     p.tau[1] = delta;
   }
@@ -530,7 +562,8 @@ __global__ void prev_giveup_kernel(PP p, const i32* __restrict__ unres, i64 n_un
   const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n_unres) p.prev[unres[q]] = -1;
 }
-__global__ void prev_halo_init_kernel(PP p, const i32* __restrict__ hnode, const i32* __restrict__ hval, i64 nh) {
+__global__ void prev_halo_init_kernel(PP pb, const i32* __restrict__ hnode, const i32* __restrict__ hval, i64 nh) {
+  const PP p = pp_view(pb, blockIdx.y);
   const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nh) p.prev[hnode[k]] = hval[k];
 }
@@ -538,7 +571,9 @@ __global__ void prev_halo_init_kernel(PP p, const i32* __restrict__ hnode, const
 // ---------------------------------------------------------------------------------------------------------
 // Device-controlled rounds: the host enqueues a fixed sequence of launches per round and only synchronises every
 // `check_every` rounds; which phase runs (push / threshold advance / nothing) is decided on the device.
-__global__ void round_begin_kernel(PP p) {
+__global__ void round_begin_kernel(PP pb) {
+  if ((int)threadIdx.x >= pb.nb) return;
+  const PP p = pp_view(pb, threadIdx.x);
   int* c = p.ctl;
   if (c[3]) return;
   if (c[2] == 1)
@@ -563,7 +598,8 @@ __global__ void round_begin_kernel(PP p) {
     p.counters[4 + (fcur ^ 1)] = 0;
   }
 }
-__global__ void prep_dc_kernel(PP p) {
+__global__ void prep_dc_kernel(PP pb) {
+  const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0];
   const i32* near_cur = p.nearq[cur];
@@ -571,12 +607,14 @@ __global__ void prep_dc_kernel(PP p) {
   for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (i64)gridDim.x * blockDim.x)
     p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
 }
-__global__ void __launch_bounds__(PUSH_BLOCK) push2d_dc_kernel(PP p) {
+__global__ void __launch_bounds__(PUSH_BLOCK) push2d_dc_kernel(PP pb) {
+  const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];
   push2d_body(p, p.nearq[cur], cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
 }
-__global__ void far_min_dc_kernel(PP p) {
+__global__ void far_min_dc_kernel(PP pb) {
+  const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 2) return;
   const int fcur = p.ctl[1];
   const i32* far_cur = p.farq[fcur];
@@ -598,7 +636,8 @@ __global__ void far_min_dc_kernel(PP p) {
   }
   if (lane == 0 && best != ~0ull) atomicMin((u64*)&p.tau[2], best);
 }
-__global__ void far_release_dc_kernel(PP p) {
+__global__ void far_release_dc_kernel(PP pb) {
+  const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 2) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];
   const i32* far_cur = p.farq[fcur];
@@ -633,47 +672,69 @@ __global__ void far_release_dc_kernel(PP p) {
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant: ONE cooperative launch runs up to `max_rounds` rounds; phases are separated by grid-wide
 // barriers instead of kernel boundaries (a round costs two or three grid.sync() instead of ~5 launches).
-__global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP p, int max_rounds) {
+__global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, int max_rounds) {
   cg::grid_group grid = cg::this_grid();
   const bool first = blockIdx.x == 0 && threadIdx.x == 0;
   const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const i64 gsize = (i64)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  int cur = p.ctl[0], fcur = p.ctl[1];
-  int rounds = 0, pushes = 0, done = 0;
+  const int nb = pb.nb;  // <= 32 sources in lock step
+  unsigned curb = 0, fcurb = 0;  // bit b = ping-pong index of source b
+  for (int b = 0; b < nb; ++b) {
+    curb |= (unsigned)(pb.ctl[b * 8 + 0] & 1) << b;
+    fcurb |= (unsigned)(pb.ctl[b * 8 + 1] & 1) << b;
+  }
+  int rounds = 0;
+  unsigned pushes = 0, advances = 0;  // per-source activity of the LAST round (for the counters below)
+  int done = 0;
   for (int r = 0; r < max_rounds; ++r) {
-    const i64 n_near = (i64)__ldcg(&p.counters[cur]);
-    const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
-    if (n_near == 0 && n_far == 0) {
+    // ---- phase A: decide each source's mode from its (stable) counters; prepare
+    unsigned mode1 = 0, mode2 = 0;
+    for (int b = 0; b < nb; ++b) {
+      const PP p = pp_view(pb, b);
+      const int cur = (curb >> b) & 1, fcur = (fcurb >> b) & 1;
+      const i64 n_near = (i64)__ldcg(&p.counters[cur]);
+      const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
+      if (n_near > 0) {
+        mode1 |= 1u << b;
+        if (first) {
+          p.counters[cur ^ 1] = 0;
+          p.ctl[5] += 1;
+        }
+        const i32* near_cur = p.nearq[cur];
+        for (i64 slot = gtid; slot < n_near; slot += gsize)
+          p.cur_mask[slot] = atomicExch(&p.pend_mask[__ldcg(&near_cur[slot])], 0u);
+      } else if (n_far > 0) {
+        mode2 |= 1u << b;
+        if (first) {
+          p.tau[2] = __longlong_as_double(-1LL);
+          p.counters[4 + (fcur ^ 1)] = 0;
+        }
+      }
+      if (first && (n_near > 0 || n_far > 0)) p.ctl[4] += 1;
+    }
+    if ((mode1 | mode2) == 0u) {
       done = 1;
       break;
     }
     ++rounds;
-    if (n_near > 0) {
-      if (first) p.counters[cur ^ 1] = 0;
-      const i32* near_cur = p.nearq[cur];
-      for (i64 slot = gtid; slot < n_near; slot += gsize)
-        p.cur_mask[slot] = atomicExch(&p.pend_mask[__ldcg(&near_cur[slot])], 0u);
-      grid.sync();
-      push2d_body(p, near_cur, cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
-      grid.sync();
-      cur ^= 1;
-      ++pushes;
-    } else {
-      if (first) {
-        p.tau[2] = __longlong_as_double(-1LL);
-        p.counters[4 + (fcur ^ 1)] = 0;
-      }
-      grid.sync();
-      const i32* far_cur = p.farq[fcur];
-      {
+    grid.sync();
+    // ---- phase B: push (mode 1) / smallest waiting value (mode 2)
+    for (int b = 0; b < nb; ++b) {
+      const PP p = pp_view(pb, b);
+      const int cur = (curb >> b) & 1, fcur = (fcurb >> b) & 1;
+      if ((mode1 >> b) & 1u) {
+        push2d_body(p, p.nearq[cur], cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
+      } else if ((mode2 >> b) & 1u) {
+        const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
+        const i32* far_cur = p.farq[fcur];
         u64 best = ~0ull;
         for (i64 slot = gtid >> 5; slot < n_far; slot += gsize >> 5) {
           const int it = __ldcg(&far_cur[slot]);
           const unsigned m = __ldcg(&p.far_mask[it]);
           if ((m >> lane) & 1u) {
-            const u64 b = (u64)__double_as_longlong(__ldcg(&p.dist[(i64)(p.item_first[it] + lane) * p.ds]));
-            best = b < best ? b : best;
+            const u64 bb = (u64)__double_as_longlong(__ldcg(&p.dist[(i64)(p.item_first[it] + lane) * p.ds]));
+            best = bb < best ? bb : best;
           }
         }
         for (int o = 16; o; o >>= 1) {
@@ -682,8 +743,16 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP p, in
         }
         if (lane == 0 && best != ~0ull) atomicMin((u64*)&p.tau[2], best);
       }
-      grid.sync();
-      {
+    }
+    grid.sync();
+    // ---- phase C: release below the new threshold (mode 2)
+    if (mode2) {
+      for (int b = 0; b < nb; ++b) {
+        if (!((mode2 >> b) & 1u)) continue;
+        const PP p = pp_view(pb, b);
+        const int cur = (curb >> b) & 1, fcur = (fcurb >> b) & 1;
+        const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
+        const i32* far_cur = p.farq[fcur];
         const double tau = __dadd_rn(__ldcg(&p.tau[2]), __ldcg(&p.tau[1]));
         i32* far_next = p.farq[fcur ^ 1];
         i32* near_next = p.nearq[cur];
@@ -709,21 +778,30 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP p, in
         if (first) p.tau[0] = tau;
       }
       grid.sync();
-      fcur ^= 1;
     }
+    curb ^= mode1;
+    fcurb ^= mode2;
+    pushes = mode1;
+    advances = mode2;
   }
+  (void)pushes;
+  (void)advances;
+  (void)rounds;
   if (first) {
-    p.ctl[0] = cur;
-    p.ctl[1] = fcur;
-    p.ctl[3] = done;
-    p.ctl[4] += rounds;
-    p.ctl[5] += pushes;
+    for (int b = 0; b < nb; ++b) {
+      pb.ctl[b * 8 + 0] = (curb >> b) & 1;
+      pb.ctl[b * 8 + 1] = (fcurb >> b) & 1;
+      pb.ctl[b * 8 + 3] = done;
+    }
   }
 }
 
 // ---- packed mode epilogue: split the pairs into dist / prev; halo-coupled nodes take the predecessor of their
 // twin (update_halo!: p[h2] = p[h1], bfm.jl:59), resolved in a few passes for twin chains.
-__global__ void unpack_kernel(PP p, i64 n, int source, double* __restrict__ dist_out) {
+__global__ void unpack_kernel(PP pb, i64 n, double* __restrict__ dist_out_base) {
+  const PP p = pp_view(pb, blockIdx.y);
+  const int source = p.source;
+  double* dist_out = dist_out_base + (i64)blockIdx.y * n;
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double d = p.dist[2 * i];
@@ -735,7 +813,9 @@ __global__ void unpack_kernel(PP p, i64 n, int source, double* __restrict__ dist
   else
     p.prev[i] = (i32)(k & 0xffffffffull);
 }
-__global__ void halo_prev_fix_kernel(PP p, const i32* __restrict__ h2, i64 rows, int source, int last) {
+__global__ void halo_prev_fix_kernel(PP pb, const i32* __restrict__ h2, i64 rows, int last) {
+  const PP p = pp_view(pb, blockIdx.y);
+  const int source = p.source;
   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const int b = h2[r];
@@ -751,29 +831,40 @@ __global__ void halo_prev_fix_kernel(PP p, const i32* __restrict__ h2, i64 rows,
     p.prev[b] = t;  // unresolved chain: the twin itself is a valid zero-weight predecessor
 }
 
-int ensure_push_workspace(rt_mesh* h) {
+int ensure_push_workspace(rt_mesh* h, int nb, bool packed) {
   Mesh2D& m = *h->m2;
-  if (m.push_ready) return RT_OK;
   cudaStream_t s = h->stream;
-  RT_TRY(m.node_item.alloc(m.n));
-  node_item_kernel<<<grid_for(m.n_items * 32, 256), 256, 0, s>>>(m.item_first.p, m.n_items, m.node_item.p);
-  RT_TRY(m.hn_index.alloc(m.n));
-  RT_CUDA(cudaMemsetAsync(m.hn_index.p, 0xff, m.n * sizeof(i32), s));
-  if (m.n_hn) hn_index_kernel<<<grid_for(m.n_hn, 256), 256, 0, s>>>(m.hn_node.p, m.n_hn, m.hn_index.p);
-  RT_TRY(m.pend_mask.alloc(m.n_items));
-  RT_TRY(m.far_mask.alloc(m.n_items));
-  RT_TRY(m.infar_u.alloc(m.n_items));
-  RT_TRY(m.cur_mask.alloc(m.n_items));
-  for (int k = 0; k < 2; ++k) {
-    RT_TRY(m.nearq[k].alloc(m.n_items));
-    RT_TRY(m.farq[k].alloc(m.n_items));
-    RT_TRY(m.unresolved[k].alloc(m.n));
+  if (!m.push_ready) {
+    RT_TRY(m.node_item.alloc(m.n));
+    node_item_kernel<<<grid_for(m.n_items * 32, 256), 256, 0, s>>>(m.item_first.p, m.n_items, m.node_item.p);
+    RT_TRY(m.hn_index.alloc(m.n));
+    RT_CUDA(cudaMemsetAsync(m.hn_index.p, 0xff, m.n * sizeof(i32), s));
+    if (m.n_hn) hn_index_kernel<<<grid_for(m.n_hn, 256), 256, 0, s>>>(m.hn_node.p, m.n_hn, m.hn_index.p);
+    for (int k = 0; k < 2; ++k) RT_TRY(m.unresolved[k].alloc(m.n));
+    RT_TRY(m.pending_prev.alloc(m.n));
+    RT_CUDA(cudaStreamSynchronize(s));
+    m.push_ready = true;
   }
-  RT_TRY(m.pending_prev.alloc(m.n));
-  RT_TRY(m.tau.alloc(4));
-  RT_TRY(m.ctl.alloc(8));
-  RT_CUDA(cudaStreamSynchronize(s));
-  m.push_ready = true;
+  if (m.push_nb < nb) {  // per-source state for a batch of nb sources solved in lock step
+    const size_t B = (size_t)nb;
+    RT_TRY(m.pend_mask.alloc(B * m.n_items));
+    RT_TRY(m.far_mask.alloc(B * m.n_items));
+    RT_TRY(m.infar_u.alloc(B * m.n_items));
+    RT_TRY(m.cur_mask.alloc(B * m.n_items));
+    for (int k = 0; k < 2; ++k) {
+      RT_TRY(m.nearq[k].alloc(B * m.n_items));
+      RT_TRY(m.farq[k].alloc(B * m.n_items));
+    }
+    RT_TRY(m.tau.alloc(B * 4));
+    RT_TRY(m.ctl.alloc(B * 8));
+    RT_TRY(m.bcounters.alloc(B * 8));
+    RT_TRY(m.bsources.alloc(B));
+    RT_TRY(m.bprev.alloc(B * m.n));
+    RT_TRY(m.bdist.alloc(B * m.n));
+    m.dp.release();
+    m.push_nb = nb;
+  }
+  if (packed && !m.dp.p) RT_TRY(m.dp.alloc(2 * (size_t)m.n * (size_t)m.push_nb));
   return RT_OK;
 }
 
@@ -785,9 +876,20 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
                      rt_stats* stats) {
   Mesh2D& m = *h->m2;
   cudaStream_t s = h->stream;
-  RT_TRY(bfm2d_ensure_workspace(h));
-  RT_TRY(ensure_push_workspace(h));
   const i64 n = m.n;
+  const bool timers = h->opts.profile_timers != 0;
+  const bool packed = h->opts.packed_prev != 0;
+  // batch width: small meshes leave the GPU idle per round, so several sources advance in lock step
+  int nb = 1;
+  if (!timers && packed && nsrc > 1 && n <= 4000000) {
+    const i64 per_src = n * 32 + m.n_items * 40;
+    nb = (int)std::min<i64>(std::min<i64>(nsrc, h->opts.batch > 0 ? h->opts.batch : 32),
+                            std::max<i64>(1, ((i64)6 << 30) / per_src));
+    nb = std::max(1, std::min(nb, 32));
+  }
+  if (timers || !packed) RT_TRY(bfm2d_ensure_workspace(h));  // pinned counter mirror of the host-driven paths
+  RT_TRY(ensure_push_workspace(h, nb, packed));
+  nb = std::min(nb, m.push_nb);
   PP p;
   p.x = m.x.p;
   p.z = m.z.p;
@@ -804,24 +906,25 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.hn_index = m.hn_index.p;
   p.n_hn = (int)m.n_hn;
   p.source = -1;
-  const bool packed = h->opts.packed_prev != 0;
-  if (packed && !m.dp.p) RT_TRY(m.dp.alloc(2 * (size_t)m.n));
-  p.dist = packed ? m.dp.p : m.dist.p;
+  p.dist = packed ? m.dp.p : m.bdist.p;
   p.ds = packed ? 2 : 1;
   p.keys = packed ? (u64*)m.dp.p : nullptr;
-  p.prev = m.prev.p;
+  p.prev = m.bprev.p;
   p.pend_mask = m.pend_mask.p;
   p.far_mask = m.far_mask.p;
   p.infar = m.infar_u.p;
   p.cur_mask = m.cur_mask.p;
-  p.counters = m.counters.p;
+  p.counters = m.bcounters.p;
   p.tau = m.tau.p;
   p.nearq[0] = m.nearq[0].p;
   p.nearq[1] = m.nearq[1].p;
   p.farq[0] = m.farq[0].p;
   p.farq[1] = m.farq[1].p;
   p.ctl = m.ctl.p;
-  u64* ch = m.counters_host;
+  p.nb = 1;
+  p.n = n;
+  p.n_items = m.n_items;
+  p.sources = m.bsources.p;
 
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
@@ -834,7 +937,6 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
                     cudaSuccess)
       coop_blocks = (i64)per_sm * sm_count;
   }
-
   cudaEvent_t ev0, ev1, evr0, evr1;
   RT_CUDA(cudaEventCreate(&ev0));
   RT_CUDA(cudaEventCreate(&ev1));
@@ -843,9 +945,8 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   rt_stats st = {};
   st.graph_edges = m.graph_edges;
   int rc = RT_OK;
-  const bool timers = h->opts.profile_timers != 0;
 
-  // bucket width: option "delta" [s], or delta_factor x (lightest consecutive-node edge)
+  // bucket width: option "delta" [s], or delta_factor x (mean travel time across a cell)
   double delta = h->opts.delta;
   if (!(delta > 0.0)) {
     RT_CUDA(cudaMemsetAsync(m.tau.p + 3, 0, sizeof(double), s));
@@ -856,33 +957,41 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     const double wmean = wsum > 0.0 ? wsum / (double)m.nel : 1.0;
     delta = wmean * (h->opts.delta_factor > 0.0 ? h->opts.delta_factor : 1.0);
   }
+  // persistent kernel wins while the frontier is small (few grid-wide barriers beat 5 launches per round); large
+  // meshes are better served by hardware block scheduling of the batched launches
+  const bool small_mesh = (i64)n * nb <= 1500000 || (nb > 1 && n <= 1500000);
+  const bool use_persistent =
+      !timers && coop_blocks > 0 && (h->opts.persistent == 1 || (h->opts.persistent < 0 && small_mesh));
+  std::vector<int> hsrc(nb);
+  std::vector<int> hctl((size_t)nb * 8);
+  std::vector<u64> hcnt((size_t)nb * 8);
 
-  for (i64 si = 0; si < nsrc && rc == RT_OK; ++si) {
-    const i64 src1 = sources[si];
-    if (src1 < 1 || src1 > n) {
-      rt_set_error("source %lld out of range 1..%lld", (long long)src1, (long long)n);
-      rc = RT_ERR_ARG;
-      break;
+  for (i64 s0 = 0; s0 < nsrc && rc == RT_OK; s0 += nb) {
+    const int B = (int)std::min<i64>(nb, nsrc - s0);
+    for (int b = 0; b < B; ++b) {
+      const i64 src1 = sources[s0 + b];
+      if (src1 < 1 || src1 > n) {
+        rt_set_error("source %lld out of range 1..%lld", (long long)src1, (long long)n);
+        rc = RT_ERR_ARG;
+        break;
+      }
+      hsrc[b] = (int)(src1 - 1);
     }
-    const int src = (int)(src1 - 1);
-    p.source = src;
+    if (rc != RT_OK) break;
+    p.nb = B;
+    p.source = hsrc[0];
     cudaEventRecord(ev0, s);
-    cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u64), s);
-    cudaMemsetAsync(m.pend_mask.p, 0, m.n_items * sizeof(unsigned), s);
-    cudaMemsetAsync(m.far_mask.p, 0, m.n_items * sizeof(unsigned), s);
-    cudaMemsetAsync(m.infar_u.p, 0, m.n_items * sizeof(unsigned), s);
-    push_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, src, delta, m.nearq[0].p);
+    cudaMemcpyAsync(m.bsources.p, hsrc.data(), B * sizeof(int), cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(m.pend_mask.p, 0, (size_t)B * m.n_items * sizeof(unsigned), s);
+    cudaMemsetAsync(m.far_mask.p, 0, (size_t)B * m.n_items * sizeof(unsigned), s);
+    cudaMemsetAsync(m.infar_u.p, 0, (size_t)B * m.n_items * sizeof(unsigned), s);
+    push_init_kernel<<<dim3(grid_for(n, 256), B), 256, 0, s>>>(p, n, delta);
     st.total_launches += 1;
     i64 rounds = 0;
-    // persistent kernel wins while the frontier is small (few grid-wide barriers beat 5 launches per round);
-    // large meshes are better served by hardware block scheduling of the batched launches
-    const bool small_mesh = m.n <= 1500000;
-    if (!timers && coop_blocks > 0 && (h->opts.persistent == 1 || (h->opts.persistent < 0 && small_mesh))) {
-      // persistent cooperative kernel: all rounds on the device, host only re-launches every `max_rounds`
-      cudaMemsetAsync(m.ctl.p, 0, 8 * sizeof(int), s);
-      int hctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (use_persistent) {
+      bool all_done = false;
       int max_rounds = 8192;
-      while (!hctl[3]) {
+      while (!all_done) {
         void* args[] = {(void*)&p, (void*)&max_rounds};
         cudaError_t le = cudaLaunchCooperativeKernel((const void*)nearfar_persistent_kernel, dim3((unsigned)coop_blocks),
                                                      dim3(PUSH_BLOCK), args, 0, s);
@@ -891,75 +1000,71 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
           break;
         }
         st.total_launches += 1;
-        cudaMemcpyAsync(hctl, m.ctl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(hctl.data(), m.ctl.p, (size_t)B * 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
         if (cudaStreamSynchronize(s) != cudaSuccess) {
           rc = RT_ERR_CUDA;
           break;
         }
+        all_done = true;
+        for (int b = 0; b < B; ++b) all_done = all_done && hctl[b * 8 + 3];
       }
-      rounds = hctl[4];
-      st.relax_launches += hctl[5];
-      cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
-      if (rc == RT_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = RT_ERR_CUDA;
     } else if (!timers) {
       // device-controlled rounds, host sync every `check_every` rounds
       const int R = h->opts.check_every > 1 ? h->opts.check_every : 32;
       const unsigned gsmall = (unsigned)(sm_count * 2);
-      cudaMemsetAsync(m.ctl.p, 0, 8 * sizeof(int), s);
-      int hctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      while (!hctl[3]) {
+      const unsigned gpush = (unsigned)std::max<i64>(sm_count, max_blocks / B);
+      bool all_done = false;
+      while (!all_done) {
         for (int r = 0; r < R; ++r) {
-          round_begin_kernel<<<1, 1, 0, s>>>(p);
-          prep_dc_kernel<<<gsmall, 256, 0, s>>>(p);
-          push2d_dc_kernel<<<(unsigned)max_blocks, PUSH_BLOCK, 0, s>>>(p);
-          far_min_dc_kernel<<<gsmall, 256, 0, s>>>(p);
-          far_release_dc_kernel<<<gsmall, 256, 0, s>>>(p);
+          round_begin_kernel<<<1, 32, 0, s>>>(p);
+          prep_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
+          push2d_dc_kernel<<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
+          far_min_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
+          far_release_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
         }
-        cudaMemcpyAsync(hctl, m.ctl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(hctl.data(), m.ctl.p, (size_t)B * 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
         if (cudaStreamSynchronize(s) != cudaSuccess) {
           rc = RT_ERR_CUDA;
           break;
         }
+        all_done = true;
+        for (int b = 0; b < B; ++b) all_done = all_done && hctl[b * 8 + 3];
       }
-      rounds = hctl[4];
-      st.total_launches += 2 * (i64)hctl[4];  // launches that did work: (prep, push) or (min, release)
-      st.relax_launches += hctl[5];
-      cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
-      if (rc == RT_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = RT_ERR_CUDA;
     } else {
+      // host-driven rounds with CUDA-event timers around every push launch (single source)
       int cur = 0, fcur = 0;
       i64 n_near = 1, n_far = 0;
+      u64* ch = m.counters_host;
       while (n_near > 0 || n_far > 0) {
         const int nxt = cur ^ 1;
         bool pushed = false;
         if (n_near > 0) {
-          cudaMemsetAsync(m.counters.p + nxt, 0, sizeof(u64), s);
+          cudaMemsetAsync(p.counters + nxt, 0, sizeof(u64), s);
           prep_kernel<<<grid_for(n_near, 256), 256, 0, s>>>(p, m.nearq[cur].p, cur);
-          if (timers) cudaEventRecord(evr0, s);
+          cudaEventRecord(evr0, s);
           push2d_kernel<<<(unsigned)std::min<i64>(n_near * PUSH_GY, max_blocks), PUSH_BLOCK, 0, s>>>(
               p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
-          if (timers) cudaEventRecord(evr1, s);
+          cudaEventRecord(evr1, s);
           pushed = true;
           st.total_launches += 2;
           st.relax_launches += 1;
           cur = nxt;
         } else {
-          // advance the threshold: near list slot `cur` is empty and stays the target of the releases
           cudaMemsetAsync(m.tau.p + 2, 0xff, sizeof(double), s);
-          cudaMemsetAsync(m.counters.p + 4 + (fcur ^ 1), 0, sizeof(u64), s);
-          cudaMemsetAsync(m.counters.p + cur, 0, sizeof(u64), s);
+          cudaMemsetAsync(p.counters + 4 + (fcur ^ 1), 0, sizeof(u64), s);
+          cudaMemsetAsync(p.counters + cur, 0, sizeof(u64), s);
           far_min_kernel<<<grid_for(n_far * 32, 256), 256, 0, s>>>(p, m.farq[fcur].p, fcur);
           far_release_kernel<<<grid_for(n_far * 32, 256), 256, 0, s>>>(p, m.farq[fcur].p, fcur, m.farq[fcur ^ 1].p,
                                                                        m.nearq[cur].p, cur);
           st.total_launches += 2;
           fcur ^= 1;
         }
-        cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(ch, p.counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
         if (cudaStreamSynchronize(s) != cudaSuccess) {
           rc = RT_ERR_CUDA;
           break;
         }
-        if (timers && pushed) {
+        if (pushed) {
           float ms = 0.f;
           cudaEventElapsedTime(&ms, evr0, evr1);
           st.relax_ms += ms;
@@ -970,45 +1075,64 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       }
     }
     if (rc != RT_OK) break;
+    cudaMemcpyAsync(hcnt.data(), p.counters, (size_t)B * 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      rc = RT_ERR_CUDA;
+      break;
+    }
+    if (!timers)
+      for (int b = 0; b < B; ++b) {
+        rounds = std::max<i64>(rounds, hctl[b * 8 + 4]);
+        st.relax_launches += hctl[b * 8 + 5];
+        st.total_launches += 2 * (i64)hctl[b * 8 + 4];
+      }
     st.sweeps += rounds;
-    st.relaxed_edges += (i64)ch[2];
-    st.vertex_updates += (i64)ch[3];
+    for (int b = 0; b < B; ++b) {
+      st.relaxed_edges += (i64)hcnt[b * 8 + 2];
+      st.vertex_updates += (i64)hcnt[b * 8 + 3];
+    }
     // ---- predecessors
     cudaEventRecord(evr0, s);
+    double* dist_out = dist_dev ? dist_dev + s0 * n : m.bdist.p;
     i64 n_un = 0;
     int ucur = 0;
     if (packed) {
       // the keys already hold a consistent predecessor per node: split the pairs, resolve the halo couplings
       if (m.n_hinit)
-        prev_halo_init_kernel<<<grid_for(m.n_hinit, 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p, m.n_hinit);
-      unpack_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, n, src, m.dist.p);
+        prev_halo_init_kernel<<<dim3(grid_for(m.n_hinit, 256), B), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p,
+                                                                                m.n_hinit);
+      unpack_kernel<<<dim3(grid_for(n, 256), B), 256, 0, s>>>(p, n, dist_out);
       st.total_launches += 2;
       if (m.halo_rows > 0)
         for (int pass = 0; pass < 4; ++pass) {
-          halo_prev_fix_kernel<<<grid_for(m.halo_rows, 256), 256, 0, s>>>(p, m.halo_h2.p, m.halo_rows, src, pass == 3);
+          halo_prev_fix_kernel<<<dim3(grid_for(m.halo_rows, 256), B), 256, 0, s>>>(p, m.halo_h2.p, m.halo_rows,
+                                                                                   pass == 3);
           st.total_launches += 1;
         }
     } else {
+      // separate tightness pass (single source): dist lives in bdist, prev in bprev
+      u64* ch = m.counters_host;
       if (m.n_hinit)
-        prev_halo_init_kernel<<<grid_for(m.n_hinit, 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p, m.n_hinit);
-      cudaMemsetAsync(m.counters.p + 6, 0, sizeof(u64), s);
+        prev_halo_init_kernel<<<dim3(grid_for(m.n_hinit, 256), 1), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p,
+                                                                                m.n_hinit);
+      cudaMemsetAsync(p.counters + 6, 0, sizeof(u64), s);
       prev_tight_kernel<<<(unsigned)std::min<i64>((m.n_items + 7) / 8, (i64)sm_count * 8), 256, 0, s>>>(
-          p, m.n_items, src, m.unresolved[0].p);
+          p, m.n_items, hsrc[0], m.unresolved[0].p);
       st.total_launches += 2;
-      cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+      cudaMemcpyAsync(ch, p.counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
       if (cudaStreamSynchronize(s) != cudaSuccess) {
         rc = RT_ERR_CUDA;
         break;
       }
       n_un = (i64)ch[6];
       for (int iter = 0; iter < 64 && n_un > 0; ++iter) {
-        cudaMemsetAsync(m.counters.p + 7, 0, sizeof(u64), s);
-        prev_resolve_kernel<<<grid_for(n_un, 128), 128, 0, s>>>(p, m.unresolved[ucur].p, n_un, src,
+        cudaMemsetAsync(p.counters + 7, 0, sizeof(u64), s);
+        prev_resolve_kernel<<<grid_for(n_un, 128), 128, 0, s>>>(p, m.unresolved[ucur].p, n_un, hsrc[0],
                                                                m.unresolved[ucur ^ 1].p, m.pending_prev.p);
         prev_apply_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un, m.pending_prev.p,
                                                               m.unresolved[ucur ^ 1].p);
         st.total_launches += 2;
-        cudaMemcpyAsync(ch, m.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(ch, p.counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
         if (cudaStreamSynchronize(s) != cudaSuccess) {
           rc = RT_ERR_CUDA;
           break;
@@ -1019,12 +1143,13 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
         n_un = left;
       }
       if (rc != RT_OK) break;
+      if (n_un > 0) prev_giveup_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un);
+      if (dist_dev) cudaMemcpyAsync(dist_out, m.bdist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
     }
-    if (n_un > 0) prev_giveup_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un);
     cudaEventRecord(evr1, s);
     cudaEventRecord(ev1, s);
-    if (dist_dev) cudaMemcpyAsync(dist_dev + si * n, m.dist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
-    if (prev_dev) cudaMemcpyAsync(prev_dev + si * n, m.prev.p, n * sizeof(i32), cudaMemcpyDeviceToDevice, s);
+    if (prev_dev)
+      cudaMemcpyAsync(prev_dev + s0 * n, m.bprev.p, (size_t)B * n * sizeof(i32), cudaMemcpyDeviceToDevice, s);
     if (cudaStreamSynchronize(s) != cudaSuccess) {
       rc = RT_ERR_CUDA;
       break;

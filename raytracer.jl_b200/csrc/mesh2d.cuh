@@ -56,6 +56,11 @@ struct Mesh2D {
   DevBuf<int> ctl;
   DevBuf<double> dp;                   // packed (travel time bits, predecessor key) pairs, 16 B per node
   bool push_ready = false;
+  int push_nb = 0;                     // batch width the per-source state is allocated for
+  DevBuf<u64> bcounters;               // [nb x 8]
+  DevBuf<int> bsources;
+  DevBuf<i32> bprev;                   // [nb x n]
+  DevBuf<double> bdist;                // [nb x n]
 };
 
 // Finishes a Mesh2D whose primary arrays (x,z,e2n_*,g_*) are already on the device: builds n2e, work items,

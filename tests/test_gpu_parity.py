@@ -440,3 +440,22 @@ def test_config2_full_size_properties(rt):
     off = np.zeros(4, np.int64)
     rt.api.check(rt.lib().rt_reconstruct_paths_dev(p.data_ptr(), n, src, rec, 3, off, None, 0))
     assert np.all(np.diff(off) > 10)
+
+
+def test_bfm2d_near_far_batched_sources(rt, O, annulus, ak135):
+    """Many earthquakes on one mesh: sources advance in lock step inside the kernels (batch API); every table must
+    equal the single-source solve bit for bit."""
+    m = annulus(90, 20, 20.0)
+    gr, G, halo = adopt(rt, m)
+    Vp = O.interp_velocity(ak135[0], ak135[1], m.r)
+    k = np.arange(37)
+    srcs = np.array([O.closest_point(m.theta, m.r, 2 * np.pi * kk / 37.0, R) for kk in k] + [1, m.n, 5], np.int64)
+    D = rt.bfm(G, halo, srcs, gr, Vp, schedule="near-far")
+    assert D.dist.shape == (40, m.n)
+    for idx in (0, 1, 17, 31, 32, 36, 37, 38, 39):  # both chunks (32 + 8), first/last entries
+        d1, p1, _ = O.bfm(m, Vp, int(srcs[idx]))
+        assert np.array_equal(D.dist[idx], d1), "source #%d" % idx
+        check_prev_tie_aware(m, Vp, int(srcs[idx]), d1, D.prev[idx], p1)
+    single = rt.bfm(G, halo, int(srcs[17]), gr, Vp, schedule="near-far")
+    assert np.array_equal(single.dist, D.dist[17]) and np.array_equal(single.prev, D.prev[17])  # deterministic prev
+    rt.bfm(G, halo, 1, gr, Vp, schedule="jacobi")
