@@ -57,15 +57,19 @@ struct PP {
   u64* counters;  // [0],[1] near counts (ping-pong) [2] evals [3] releases [4],[5] far counts (ping-pong)
                   // [6] unresolved count [7] scratch
   double* tau;    // [0] tau [1] delta [2] min far (bits)
-  i32* nearq[2];
-  i32* farq[2];
+  i32 *nearq0, *nearq1;  // selected with nq() / fq(): no dynamic indexing, so the struct stays out of local memory
+  i32 *farq0, *farq1;
   int* ctl;       // device-side round control: [0] cur [1] fcur [2] mode (1 push, 2 advance) [3] done [4] rounds
                   // [5] push rounds
   // batch of sources solved in lock step (state arrays hold nb slices; pp_view() selects one)
   int nb;
+  int warp_units;  // 1: short columns -> warp-per-item push (push2d_warp_body), 0: CTA per (item, element group)
   i64 n, n_items;
   const int* sources;  // [nb] 0-based
 };
+
+__device__ __forceinline__ i32* nq(const PP& p, int k) { return k ? p.nearq1 : p.nearq0; }
+__device__ __forceinline__ i32* fq(const PP& p, int k) { return k ? p.farq1 : p.farq0; }
 
 // slice b of the per-source state (mesh arrays are shared)
 __device__ __forceinline__ PP pp_view(const PP& p, int b) {
@@ -79,10 +83,10 @@ __device__ __forceinline__ PP pp_view(const PP& p, int b) {
   v.cur_mask = p.cur_mask + (i64)b * p.n_items;
   v.counters = p.counters + (i64)b * 8;
   v.tau = p.tau + (i64)b * 4;
-  v.nearq[0] = p.nearq[0] + (i64)b * p.n_items;
-  v.nearq[1] = p.nearq[1] + (i64)b * p.n_items;
-  v.farq[0] = p.farq[0] + (i64)b * p.n_items;
-  v.farq[1] = p.farq[1] + (i64)b * p.n_items;
+  v.nearq0 = p.nearq0 + (i64)b * p.n_items;
+  v.nearq1 = p.nearq1 + (i64)b * p.n_items;
+  v.farq0 = p.farq0 + (i64)b * p.n_items;
+  v.farq1 = p.farq1 + (i64)b * p.n_items;
   v.ctl = p.ctl + (i64)b * 8;
   v.source = p.sources ? p.sources[b] : p.source;
   v.nb = 1;
@@ -353,14 +357,169 @@ __device__ __forceinline__ void push2d_body_t(const PP& p, const i32* near_cur, 
   }
   if (lane == 0 && evals) atomicAdd(&p.counters[2], evals);
 }
+// ---------------------------------------------------------------------------------------------------------
+// Warp-level push for meshes whose G columns are short (coarse spacing: a column holds a few hundred candidates):
+// one warp owns one released item, no block barrier.  The element offsets of the column are fetched by the lanes
+// in parallel and prefix-summed, so the targets of ALL its elements form one flat index space that the lanes walk
+// with full utilisation (an element holds ~10 nodes there); sources sit in a warp-private shared-memory slab.
+template <bool PACKED>
+__device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned mask, int cur, i32* near_next,
+                                                 i32* far_list, int fcur, double tau, double2* sxz, double2* sUd,
+                                                 int* s_id, int* s_pre, int* s_start) {
+  const int lane = threadIdx.x & 31;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const int v0 = p.item_first[it];
+  __syncwarp();
+  const bool on = (mask >> lane) & 1u;
+  const int pos = __popc(mask & ((1u << lane) - 1u));
+  double dmy = INF;
+  if (on) {
+    const int i = v0 + lane;
+    dmy = __ldcg(&p.dist[(i64)i * p.ds]);
+    sxz[pos] = make_double2(p.x[i], p.z[i]);
+    sUd[pos] = make_double2(p.U[i], dmy);
+    s_id[pos] = i;
+  }
+  double dmin = dmy;
+  for (int o = 16; o; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
+  const int ns = __popc(mask);
+  __syncwarp();
+  // zero-weight halo coupling
+  if (p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {
+    const int lo = p.hn_index[s_id[lane]];
+    if (lo >= 0) {
+      const double d = sUd[lane].y;
+      for (int q = p.hn_off[lo]; q < p.hn_off[lo + 1]; ++q) {
+        const int b = p.hn_part[q];
+        if (PACKED) {
+          const DP cb = dp_load(p, b);
+          if ((u64)__double_as_longlong(d) < cb.d && dp_update(p, b, cb, d, KEY_HALO | (u64)s_id[lane]))
+            enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+        } else if (d < __ldcg(&p.dist[(i64)b * p.ds]) && relax_to(p, b, d)) {
+          enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+        }
+      }
+    }
+  }
+  const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
+  u64 evals = 0;
+  for (i64 cb0 = c0; cb0 < c1; cb0 += 32) {  // element batches of 32 (a column has <= 16 elements, the centre 2T)
+    const int ne = (int)min((i64)32, c1 - cb0);
+    int s_l = 0, m_l = 0;
+    if (lane < ne) {
+      const int el = p.g_idx[cb0 + lane];
+      s_l = p.e2n_off[el];
+      m_l = p.e2n_off[el + 1] - s_l;
+    }
+    int incl = m_l;  // inclusive prefix sum of the element lengths
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    __syncwarp();
+    s_pre[lane] = incl;
+    s_start[lane] = s_l;
+    __syncwarp();
+    evals += (u64)total * (u64)ns;
+    for (int t = lane; t < total; t += 32) {
+      // element e with pre[e-1] <= t < pre[e]
+      int lo = 0, hi = ne - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_pre[mid] <= t)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      const int k = t - (lo ? s_pre[lo - 1] : 0);
+      const int j = p.e2n_idx[s_start[lo] + k];
+      const double dj = __ldcg(&p.dist[(i64)j * p.ds]);
+      if (!(dmin < dj)) continue;
+      u64 kj = KEY_NONE;
+      if (PACKED) kj = __ldcg(p.keys + 2 * (i64)j + 1);
+      const double xj = p.x[j], zj = p.z[j], Uj = p.U[j];
+      double best = dj;
+      u64 bkey = kj;
+      bool changed = false;
+      for (int q = 0; q < ns; ++q) {
+        const double2 ud = sUd[q];
+        const double di = ud.y;
+        if (!(di < best)) continue;
+        const double2 xz = sxz[q];
+        {
+          const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
+          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+          if (screen_cannot_improve(best, di, d2, __dadd_rn(ud.x, Uj))) continue;
+        }
+        const double delta = edge_delta(di, xz.x, xz.y, ud.x, xj, zj, Uj);
+        if (PACKED) {
+          const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
+          if (delta < best) {
+            best = delta;
+            bkey = key;
+            changed = true;
+          } else if (delta == best && !(key & KEY_ZMASK) && key < bkey) {
+            bkey = key;
+            changed = true;
+          }
+        } else {
+          best = delta < best ? delta : best;
+        }
+      }
+      if (PACKED) {
+        if (changed) {
+          DP cur_dp;
+          cur_dp.d = (u64)__double_as_longlong(dj);
+          cur_dp.k = kj;
+          if (dp_update(p, j, cur_dp, best, bkey)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+        }
+      } else if (best < dj && relax_to(p, j, best)) {
+        enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    atomicAdd(&p.counters[2], evals);
+    atomicAdd(&p.counters[3], (u64)ns);
+  }
+}
+
+// warp-level units of ONE source: slots of its near list
+__device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
+                                                 i32* far_list, int fcur, i64 first_warp, i64 n_warps) {
+  __shared__ double2 w_sxz[PUSH_BLOCK / 32][32], w_sUd[PUSH_BLOCK / 32][32];
+  __shared__ int w_id[PUSH_BLOCK / 32][32], w_pre[PUSH_BLOCK / 32][32], w_start[PUSH_BLOCK / 32][32];
+  const int warp = threadIdx.x >> 5;
+  const i64 n_near = (i64)__ldcg(&p.counters[cur]);
+  const double tau = __ldcg(&p.tau[0]);
+  for (i64 slot = first_warp; slot < n_near; slot += n_warps) {
+    const int it = __ldcg(&near_cur[slot]);
+    const unsigned mask = __ldcg(&p.cur_mask[slot]);
+    if (mask == 0u) continue;
+    if (p.ds == 2)
+      push2d_warp_unit<true>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp], w_id[warp],
+                             w_pre[warp], w_start[warp]);
+    else
+      push2d_warp_unit<false>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp], w_id[warp],
+                              w_pre[warp], w_start[warp]);
+  }
+}
+
 __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
-  if (p.ds == 2)
+  if (p.warp_units) {
+    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+    push2d_warp_body(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
+  } else if (p.ds == 2) {
     push2d_body_t<true>(p, near_cur, cur, near_next, far_list, fcur);
-  else
+  } else {
     push2d_body_t<false>(p, near_cur, cur, near_next, far_list, fcur);
+  }
 }
-__global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
+__global__ void __launch_bounds__(PUSH_BLOCK, 8) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
                                                            i32* __restrict__ near_next, i32* __restrict__ far_list,
                                                            int fcur) {
   push2d_body(p, near_cur, cur, near_next, far_list, fcur);
@@ -412,7 +571,7 @@ __global__ void far_release_kernel(PP p, const i32* __restrict__ far_cur, int fc
 __global__ void push_init_kernel(PP pb, i64 n, double delta) {
   const PP p = pp_view(pb, blockIdx.y);
   const int source = p.source;
-  i32* near0 = p.nearq[0];
+  i32* near0 = nq(p, 0);
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     p.dist[i * p.ds] = (i == source) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
@@ -602,22 +761,22 @@ __global__ void prep_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0];
-  const i32* near_cur = p.nearq[cur];
+  const i32* near_cur = nq(p, cur);
   const i64 n = (i64)p.counters[cur];
   for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (i64)gridDim.x * blockDim.x)
     p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
 }
-__global__ void __launch_bounds__(PUSH_BLOCK) push2d_dc_kernel(PP pb) {
+__global__ void __launch_bounds__(PUSH_BLOCK, 8) push2d_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];
-  push2d_body(p, p.nearq[cur], cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
+  push2d_body(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
 }
 __global__ void far_min_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 2) return;
   const int fcur = p.ctl[1];
-  const i32* far_cur = p.farq[fcur];
+  const i32* far_cur = fq(p, fcur);
   const i64 nslots = (i64)p.counters[4 + fcur];
   const int lane = threadIdx.x & 31;
   u64 best = ~0ull;
@@ -640,9 +799,9 @@ __global__ void far_release_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 2) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];
-  const i32* far_cur = p.farq[fcur];
-  i32* far_next = p.farq[fcur ^ 1];
-  i32* near_next = p.nearq[cur];
+  const i32* far_cur = fq(p, fcur);
+  i32* far_next = fq(p, fcur ^ 1);
+  i32* near_next = nq(p, cur);
   const i64 nslots = (i64)p.counters[4 + fcur];
   const int lane = threadIdx.x & 31;
   const double tau = __dadd_rn(p.tau[2], p.tau[1]);
@@ -672,7 +831,7 @@ __global__ void far_release_dc_kernel(PP pb) {
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant: ONE cooperative launch runs up to `max_rounds` rounds; phases are separated by grid-wide
 // barriers instead of kernel boundaries (a round costs two or three grid.sync() instead of ~5 launches).
-__global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, int max_rounds) {
+__global__ void __launch_bounds__(PUSH_BLOCK, 6) nearfar_persistent_kernel(PP pb, int max_rounds) {
   cg::grid_group grid = cg::this_grid();
   const bool first = blockIdx.x == 0 && threadIdx.x == 0;
   const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -701,7 +860,7 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, i
           p.counters[cur ^ 1] = 0;
           p.ctl[5] += 1;
         }
-        const i32* near_cur = p.nearq[cur];
+        const i32* near_cur = nq(p, cur);
         for (i64 slot = gtid; slot < n_near; slot += gsize)
           p.cur_mask[slot] = atomicExch(&p.pend_mask[__ldcg(&near_cur[slot])], 0u);
       } else if (n_far > 0) {
@@ -724,10 +883,18 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, i
       const PP p = pp_view(pb, b);
       const int cur = (curb >> b) & 1, fcur = (fcurb >> b) & 1;
       if ((mode1 >> b) & 1u) {
-        push2d_body(p, p.nearq[cur], cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
+        if (p.warp_units && nb > 1) {
+          // every source gets its own team of warps (warp w serves source w % nb) so that the sources advance
+          // concurrently instead of one after the other
+          const i64 gw = gtid >> 5, nw = gsize >> 5;
+          if ((int)(gw % nb) == b) push2d_warp_body(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, gw / nb,
+                                                    (nw - b + nb - 1) / nb);
+        } else {
+          push2d_body(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
+        }
       } else if ((mode2 >> b) & 1u) {
         const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
-        const i32* far_cur = p.farq[fcur];
+        const i32* far_cur = fq(p, fcur);
         u64 best = ~0ull;
         for (i64 slot = gtid >> 5; slot < n_far; slot += gsize >> 5) {
           const int it = __ldcg(&far_cur[slot]);
@@ -752,10 +919,10 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, i
         const PP p = pp_view(pb, b);
         const int cur = (curb >> b) & 1, fcur = (fcurb >> b) & 1;
         const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
-        const i32* far_cur = p.farq[fcur];
+        const i32* far_cur = fq(p, fcur);
         const double tau = __dadd_rn(__ldcg(&p.tau[2]), __ldcg(&p.tau[1]));
-        i32* far_next = p.farq[fcur ^ 1];
-        i32* near_next = p.nearq[cur];
+        i32* far_next = fq(p, fcur ^ 1);
+        i32* near_next = nq(p, cur);
         for (i64 slot = gtid >> 5; slot < n_far; slot += gsize >> 5) {
           const int it = __ldcg(&far_cur[slot]);
           const unsigned m = __ldcg(&p.far_mask[it]);
@@ -916,12 +1083,13 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.cur_mask = m.cur_mask.p;
   p.counters = m.bcounters.p;
   p.tau = m.tau.p;
-  p.nearq[0] = m.nearq[0].p;
-  p.nearq[1] = m.nearq[1].p;
-  p.farq[0] = m.farq[0].p;
-  p.farq[1] = m.farq[1].p;
+  p.nearq0 = m.nearq[0].p;
+  p.nearq1 = m.nearq[1].p;
+  p.farq0 = m.farq[0].p;
+  p.farq1 = m.farq[1].p;
   p.ctl = m.ctl.p;
   p.nb = 1;
+  p.warp_units = (h->opts.warp_units == 1 || (h->opts.warp_units < 0 && m.graph_edges / std::max<i64>(n, 1) < 1500)) ? 1 : 0;
   p.n = n;
   p.n_items = m.n_items;
   p.sources = m.bsources.p;
