@@ -507,9 +507,10 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
   }
 }
 
+template <bool WARP>
 __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
-  if (p.warp_units) {
+  if (WARP) {
     const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
     push2d_warp_body(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
@@ -519,10 +520,11 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
     push2d_body_t<false>(p, near_cur, cur, near_next, far_list, fcur);
   }
 }
-__global__ void __launch_bounds__(PUSH_BLOCK, 8) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
+template <bool WARP>
+__global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
                                                            i32* __restrict__ near_next, i32* __restrict__ far_list,
                                                            int fcur) {
-  push2d_body(p, near_cur, cur, near_next, far_list, fcur);
+  push2d_body<WARP>(p, near_cur, cur, near_next, far_list, fcur);
 }
 
 // threshold advance, step 1: smallest waiting value
@@ -766,11 +768,12 @@ __global__ void prep_dc_kernel(PP pb) {
   for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (i64)gridDim.x * blockDim.x)
     p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
 }
-__global__ void __launch_bounds__(PUSH_BLOCK, 8) push2d_dc_kernel(PP pb) {
+template <bool WARP>
+__global__ void __launch_bounds__(PUSH_BLOCK) push2d_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];
-  push2d_body(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
+  push2d_body<WARP>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
 }
 __global__ void far_min_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
@@ -831,7 +834,8 @@ __global__ void far_release_dc_kernel(PP pb) {
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant: ONE cooperative launch runs up to `max_rounds` rounds; phases are separated by grid-wide
 // barriers instead of kernel boundaries (a round costs two or three grid.sync() instead of ~5 launches).
-__global__ void __launch_bounds__(PUSH_BLOCK, 6) nearfar_persistent_kernel(PP pb, int max_rounds) {
+template <bool WARP>
+__global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, int max_rounds) {
   cg::grid_group grid = cg::this_grid();
   const bool first = blockIdx.x == 0 && threadIdx.x == 0;
   const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -883,14 +887,14 @@ __global__ void __launch_bounds__(PUSH_BLOCK, 6) nearfar_persistent_kernel(PP pb
       const PP p = pp_view(pb, b);
       const int cur = (curb >> b) & 1, fcur = (fcurb >> b) & 1;
       if ((mode1 >> b) & 1u) {
-        if (p.warp_units && nb > 1) {
+        if (WARP && nb > 1) {
           // every source gets its own team of warps (warp w serves source w % nb) so that the sources advance
           // concurrently instead of one after the other
           const i64 gw = gtid >> 5, nw = gsize >> 5;
           if ((int)(gw % nb) == b) push2d_warp_body(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, gw / nb,
                                                     (nw - b + nb - 1) / nb);
         } else {
-          push2d_body(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
+          push2d_body<WARP>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
         }
       } else if ((mode2 >> b) & 1u) {
         const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
@@ -1101,9 +1105,10 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   {
     int coop = 0, per_sm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
-    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nearfar_persistent_kernel, PUSH_BLOCK, 0) ==
-                    cudaSuccess)
-      coop_blocks = (i64)per_sm * sm_count;
+    const cudaError_t oe =
+        p.warp_units ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nearfar_persistent_kernel<true>, PUSH_BLOCK, 0)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nearfar_persistent_kernel<false>, PUSH_BLOCK, 0);
+    if (coop && oe == cudaSuccess) coop_blocks = (i64)per_sm * sm_count;
   }
   cudaEvent_t ev0, ev1, evr0, evr1;
   RT_CUDA(cudaEventCreate(&ev0));
@@ -1161,8 +1166,9 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       int max_rounds = 8192;
       while (!all_done) {
         void* args[] = {(void*)&p, (void*)&max_rounds};
-        cudaError_t le = cudaLaunchCooperativeKernel((const void*)nearfar_persistent_kernel, dim3((unsigned)coop_blocks),
-                                                     dim3(PUSH_BLOCK), args, 0, s);
+        const void* kfn = p.warp_units ? (const void*)nearfar_persistent_kernel<true>
+                                       : (const void*)nearfar_persistent_kernel<false>;
+        cudaError_t le = cudaLaunchCooperativeKernel(kfn, dim3((unsigned)coop_blocks), dim3(PUSH_BLOCK), args, 0, s);
         if (le != cudaSuccess) {
           rc = RT_ERR_CUDA;
           break;
@@ -1186,7 +1192,10 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
         for (int r = 0; r < R; ++r) {
           round_begin_kernel<<<1, 32, 0, s>>>(p);
           prep_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
-          push2d_dc_kernel<<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
+          if (p.warp_units)
+            push2d_dc_kernel<true><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
+          else
+            push2d_dc_kernel<false><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
           far_min_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
           far_release_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
         }
@@ -1210,8 +1219,12 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
           cudaMemsetAsync(p.counters + nxt, 0, sizeof(u64), s);
           prep_kernel<<<grid_for(n_near, 256), 256, 0, s>>>(p, m.nearq[cur].p, cur);
           cudaEventRecord(evr0, s);
-          push2d_kernel<<<(unsigned)std::min<i64>(n_near * PUSH_GY, max_blocks), PUSH_BLOCK, 0, s>>>(
-              p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
+          if (p.warp_units)
+            push2d_kernel<true><<<(unsigned)std::min<i64>((n_near + 3) / 4, max_blocks), PUSH_BLOCK, 0, s>>>(
+                p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
+          else
+            push2d_kernel<false><<<(unsigned)std::min<i64>(n_near * PUSH_GY, max_blocks), PUSH_BLOCK, 0, s>>>(
+                p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           cudaEventRecord(evr1, s);
           pushed = true;
           st.total_launches += 2;
