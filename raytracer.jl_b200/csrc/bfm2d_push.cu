@@ -217,7 +217,7 @@ __global__ void prep_kernel(PP p, const i32* __restrict__ near_cur, int cur) {
 // with ld.global.cg (L2) so that a stale L1 line can never hide an update; mesh arrays are read-only.
 template <bool PACKED>
 __device__ __forceinline__ void push2d_body_t(const PP& p, const i32* near_cur, int cur, i32* near_next,
-                                              i32* far_list, int fcur, i64 bid, i64 nblk) {
+                                              i32* far_list, int fcur) {
   __shared__ double2 sxz[32], sUd[32];  // (x, z) and (U, dist) of the released sources: one LDS.128 each
   __shared__ int s_id[32];
   __shared__ int s_ns;
@@ -228,7 +228,7 @@ __device__ __forceinline__ void push2d_body_t(const PP& p, const i32* near_cur, 
   u64 evals = 0;
   // work unit = (near-list slot, element group gy): the column of one released item is spread over PUSH_GY
   // CTAs x 4 warps (warp per element), so a round with few released items still fills the machine
-  for (i64 unit = bid; unit < n_near * PUSH_GY; unit += nblk) {
+  for (i64 unit = blockIdx.x; unit < n_near * PUSH_GY; unit += gridDim.x) {
     const i64 slot = unit / PUSH_GY;
     const int gy = (int)(unit - slot * PUSH_GY);
     const int it = __ldcg(&near_cur[slot]);
@@ -507,24 +507,24 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
   }
 }
 
-// bid / nblk: rank and number of the CTAs that serve this source (the whole grid unless sources share a launch)
 template <bool WARP>
 __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
-                                            i32* far_list, int fcur, i64 bid, i64 nblk) {
+                                            i32* far_list, int fcur) {
   if (WARP) {
-    const i64 wpb = blockDim.x >> 5;
-    push2d_warp_body(p, near_cur, cur, near_next, far_list, fcur, bid * wpb + (threadIdx.x >> 5), nblk * wpb);
+    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+    push2d_warp_body(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
   } else if (p.ds == 2) {
-    push2d_body_t<true>(p, near_cur, cur, near_next, far_list, fcur, bid, nblk);
+    push2d_body_t<true>(p, near_cur, cur, near_next, far_list, fcur);
   } else {
-    push2d_body_t<false>(p, near_cur, cur, near_next, far_list, fcur, bid, nblk);
+    push2d_body_t<false>(p, near_cur, cur, near_next, far_list, fcur);
   }
 }
 template <bool WARP>
 __global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
                                                            i32* __restrict__ near_next, i32* __restrict__ far_list,
                                                            int fcur) {
-  push2d_body<WARP>(p, near_cur, cur, near_next, far_list, fcur, blockIdx.x, gridDim.x);
+  push2d_body<WARP>(p, near_cur, cur, near_next, far_list, fcur);
 }
 
 // threshold advance, step 1: smallest waiting value
@@ -773,7 +773,7 @@ __global__ void __launch_bounds__(PUSH_BLOCK) push2d_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];
-  push2d_body<WARP>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, blockIdx.x, gridDim.x);
+  push2d_body<WARP>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
 }
 __global__ void far_min_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
@@ -837,96 +837,97 @@ __global__ void far_release_dc_kernel(PP pb) {
 template <bool WARP>
 __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, int max_rounds) {
   cg::grid_group grid = cg::this_grid();
+  const bool first = blockIdx.x == 0 && threadIdx.x == 0;
   const i64 gtid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   const i64 gsize = (i64)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int nb = pb.nb;  // <= 32 sources in lock step
-  // Every source is served by its own TEAM of warps (warp w -> source w % nb) in every phase, so the dependent
-  // load chains of the sources overlap instead of adding up.  With WARP == false and nb == 1 the team is the grid.
-  // Teams are made of warps when the push works per warp, of whole CTAs otherwise (its CTA-level barriers).
-  const i64 wpb = blockDim.x >> 5;
-  const i64 gw = gtid >> 5, nw = gsize >> 5;
-  const int my_b = WARP ? (int)(gw % nb) : (int)(blockIdx.x % nb);
-  const i64 tblk = blockIdx.x / nb;                                    // CTA rank inside the team (CTA teams)
-  const i64 tnblk = ((i64)gridDim.x - my_b + nb - 1) / nb;             // CTAs in the team
-  const i64 trank = WARP ? gw / nb : tblk * wpb + (threadIdx.x >> 5);  // warp rank inside the team
-  const i64 tsize = WARP ? (nw - my_b + nb - 1) / nb : tnblk * wpb;    // warps in the team
-  const bool leader = trank == 0 && lane == 0;
   unsigned curb = 0, fcurb = 0;  // bit b = ping-pong index of source b
   for (int b = 0; b < nb; ++b) {
     curb |= (unsigned)(pb.ctl[b * 8 + 0] & 1) << b;
     fcurb |= (unsigned)(pb.ctl[b * 8 + 1] & 1) << b;
   }
+  int rounds = 0;
+  unsigned pushes = 0, advances = 0;  // per-source activity of the LAST round (for the counters below)
   int done = 0;
-  const PP p = pp_view(pb, my_b);
   for (int r = 0; r < max_rounds; ++r) {
-    // ---- phase A: every thread derives the mode of every source from its (stable) counters (uniform control
-    // flow for the grid barriers); the team prepares its own source
+    // ---- phase A: decide each source's mode from its (stable) counters; prepare
     unsigned mode1 = 0, mode2 = 0;
     for (int b = 0; b < nb; ++b) {
-      const u64* cb = pb.counters + (i64)b * 8;
-      const i64 nn = (i64)__ldcg(&cb[(curb >> b) & 1]);
-      const i64 nf = (i64)__ldcg(&cb[4 + ((fcurb >> b) & 1)]);
-      if (nn > 0)
+      const PP p = pp_view(pb, b);
+      const int cur = (curb >> b) & 1, fcur = (fcurb >> b) & 1;
+      const i64 n_near = (i64)__ldcg(&p.counters[cur]);
+      const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
+      if (n_near > 0) {
         mode1 |= 1u << b;
-      else if (nf > 0)
+        if (first) {
+          p.counters[cur ^ 1] = 0;
+          p.ctl[5] += 1;
+        }
+        const i32* near_cur = nq(p, cur);
+        for (i64 slot = gtid; slot < n_near; slot += gsize)
+          p.cur_mask[slot] = atomicExch(&p.pend_mask[__ldcg(&near_cur[slot])], 0u);
+      } else if (n_far > 0) {
         mode2 |= 1u << b;
+        if (first) {
+          p.tau[2] = __longlong_as_double(-1LL);
+          p.counters[4 + (fcur ^ 1)] = 0;
+        }
+      }
+      if (first && (n_near > 0 || n_far > 0)) p.ctl[4] += 1;
     }
     if ((mode1 | mode2) == 0u) {
       done = 1;
       break;
     }
-    const int cur = (curb >> my_b) & 1, fcur = (fcurb >> my_b) & 1;
-    const bool m1 = (mode1 >> my_b) & 1u, m2 = (mode2 >> my_b) & 1u;
-    const i64 n_near = m1 ? (i64)__ldcg(&p.counters[cur]) : 0;
-    const i64 n_far = m2 ? (i64)__ldcg(&p.counters[4 + fcur]) : 0;
-    if (m1) {
-      if (leader) {
-        p.counters[cur ^ 1] = 0;
-        p.ctl[4] += 1;
-        p.ctl[5] += 1;
-      }
-      const i32* near_cur = nq(p, cur);
-      for (i64 slot = trank * 32 + lane; slot < n_near; slot += tsize * 32)
-        p.cur_mask[slot] = atomicExch(&p.pend_mask[__ldcg(&near_cur[slot])], 0u);
-    } else if (m2 && leader) {
-      p.tau[2] = __longlong_as_double(-1LL);
-      p.counters[4 + (fcur ^ 1)] = 0;
-      p.ctl[4] += 1;
-    }
+    ++rounds;
     grid.sync();
     // ---- phase B: push (mode 1) / smallest waiting value (mode 2)
-    if (m1) {
-      if (WARP)
-        push2d_warp_body(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, trank, tsize);
-      else
-        push2d_body<false>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tblk, tnblk);
-    } else if (m2) {
-      const i32* far_cur = fq(p, fcur);
-      u64 best = ~0ull;
-      for (i64 slot = trank; slot < n_far; slot += tsize) {
-        const int it = __ldcg(&far_cur[slot]);
-        const unsigned m = __ldcg(&p.far_mask[it]);
-        if ((m >> lane) & 1u) {
-          const u64 bb = (u64)__double_as_longlong(__ldcg(&p.dist[(i64)(p.item_first[it] + lane) * p.ds]));
-          best = bb < best ? bb : best;
+    for (int b = 0; b < nb; ++b) {
+      const PP p = pp_view(pb, b);
+      const int cur = (curb >> b) & 1, fcur = (fcurb >> b) & 1;
+      if ((mode1 >> b) & 1u) {
+        if (WARP && nb > 1) {
+          // every source gets its own team of warps (warp w serves source w % nb) so that the sources advance
+          // concurrently instead of one after the other
+          const i64 gw = gtid >> 5, nw = gsize >> 5;
+          if ((int)(gw % nb) == b) push2d_warp_body(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, gw / nb,
+                                                    (nw - b + nb - 1) / nb);
+        } else {
+          push2d_body<WARP>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
         }
+      } else if ((mode2 >> b) & 1u) {
+        const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
+        const i32* far_cur = fq(p, fcur);
+        u64 best = ~0ull;
+        for (i64 slot = gtid >> 5; slot < n_far; slot += gsize >> 5) {
+          const int it = __ldcg(&far_cur[slot]);
+          const unsigned m = __ldcg(&p.far_mask[it]);
+          if ((m >> lane) & 1u) {
+            const u64 bb = (u64)__double_as_longlong(__ldcg(&p.dist[(i64)(p.item_first[it] + lane) * p.ds]));
+            best = bb < best ? bb : best;
+          }
+        }
+        for (int o = 16; o; o >>= 1) {
+          const u64 other = __shfl_xor_sync(FULL, best, o);
+          best = other < best ? other : best;
+        }
+        if (lane == 0 && best != ~0ull) atomicMin((u64*)&p.tau[2], best);
       }
-      for (int o = 16; o; o >>= 1) {
-        const u64 other = __shfl_xor_sync(FULL, best, o);
-        best = other < best ? other : best;
-      }
-      if (lane == 0 && best != ~0ull) atomicMin((u64*)&p.tau[2], best);
     }
     grid.sync();
     // ---- phase C: release below the new threshold (mode 2)
     if (mode2) {
-      if (m2) {
+      for (int b = 0; b < nb; ++b) {
+        if (!((mode2 >> b) & 1u)) continue;
+        const PP p = pp_view(pb, b);
+        const int cur = (curb >> b) & 1, fcur = (fcurb >> b) & 1;
+        const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
         const i32* far_cur = fq(p, fcur);
         const double tau = __dadd_rn(__ldcg(&p.tau[2]), __ldcg(&p.tau[1]));
         i32* far_next = fq(p, fcur ^ 1);
         i32* near_next = nq(p, cur);
-        for (i64 slot = trank; slot < n_far; slot += tsize) {
+        for (i64 slot = gtid >> 5; slot < n_far; slot += gsize >> 5) {
           const int it = __ldcg(&far_cur[slot]);
           const unsigned m = __ldcg(&p.far_mask[it]);
           const bool mine = (m >> lane) & 1u;
@@ -945,17 +946,24 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, i
             }
           }
         }
-        if (leader) p.tau[0] = tau;
+        if (first) p.tau[0] = tau;
       }
       grid.sync();
     }
     curb ^= mode1;
     fcurb ^= mode2;
+    pushes = mode1;
+    advances = mode2;
   }
-  if (leader) {
-    p.ctl[0] = (curb >> my_b) & 1;
-    p.ctl[1] = (fcurb >> my_b) & 1;
-    p.ctl[3] = done;
+  (void)pushes;
+  (void)advances;
+  (void)rounds;
+  if (first) {
+    for (int b = 0; b < nb; ++b) {
+      pb.ctl[b * 8 + 0] = (curb >> b) & 1;
+      pb.ctl[b * 8 + 1] = (fcurb >> b) & 1;
+      pb.ctl[b * 8 + 3] = done;
+    }
   }
 }
 
