@@ -93,6 +93,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def ncu_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` captures (profiles/traffic.json); None if that kernel / workload was not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    return t.get("%s@%s" % (kernel, workload))
+
+
 def ak135():
     d = np.load(os.path.join(ROOT, "raytracer.jl_b200", "data", "ak135_profile.npz"))
     return (d["depth_km"].max() - d["depth_km"])[::-1].copy(), d["vp"][::-1].copy()
@@ -100,7 +110,7 @@ def ak135():
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 class GpuWorkload:
-    def __init__(self, name, rt, torch, schedule="near-far"):
+    def __init__(self, name, rt, torch, schedule="near-far", sps=1):
         self.name, self.rt, self.torch = name, rt, torch
         self.w = WORKLOADS[name]
         prof = rt.velocity_profile()
@@ -130,22 +140,23 @@ class GpuWorkload:
             k = np.arange(65)
             self.sources = [int(s) for s in rt.closest_point(gr, 2 * np.pi * k / 65.0, np.full(65, R), "polar")]
             self.bv = 52
+        self.sps = sps
         self.U_dev = torch.from_numpy(self.U_host).cuda()
-        self.dist_dev = torch.empty(self.n, dtype=torch.float64, device="cuda")
-        self.prev_dev = torch.empty(self.n, dtype=torch.int32, device="cuda")
+        self.dist_dev = torch.empty(self.n * sps, dtype=torch.float64, device="cuda")
+        self.prev_dev = torch.empty(self.n * sps, dtype=torch.int32, device="cuda")
         self.handle.set_option("profile_timers", 0)
         self.schedule = schedule
         self.handle.set_option("schedule", {"jacobi": 0, "near-far": 1}[schedule])
         # pinned host buffers of the end-to-end arm
         self.U_pin = torch.from_numpy(self.U_host).pin_memory()
-        self.dist_pin = torch.empty(self.n, dtype=torch.float64).pin_memory()
-        self.prev_pin = torch.empty(self.n, dtype=torch.int64).pin_memory()
+        self.dist_pin = torch.empty(self.n * sps, dtype=torch.float64).pin_memory()
+        self.prev_pin = torch.empty(self.n * sps, dtype=torch.int64).pin_memory()
 
     def solve_dev(self, source):
         import ctypes as C
         st = self.rt.RtStats()
-        src = np.array([source], np.int64)
-        self.rt.api.check(self.rt.lib().rt_bfm_solve_dev(self.handle.h, self.U_dev.data_ptr(), src, 1, 64,
+        src = np.ascontiguousarray(np.atleast_1d(np.asarray(source, np.int64)))
+        self.rt.api.check(self.rt.lib().rt_bfm_solve_dev(self.handle.h, self.U_dev.data_ptr(), src, len(src), 64,
                                                          self.dist_dev.data_ptr(), self.prev_dev.data_ptr(),
                                                          C.byref(st)))
         return st.as_dict()
@@ -154,8 +165,8 @@ class GpuWorkload:
         """The reference-facing call: host buffers in, host tables out (H2D of U, D2H of dist and prev inside)."""
         import ctypes as C
         st = self.rt.RtStats()
-        src = np.array([source], np.int64)
-        self.rt.api.check(self.rt.lib().rt_bfm_solve(self.handle.h, self.U_pin.numpy(), src, 1, 64,
+        src = np.ascontiguousarray(np.atleast_1d(np.asarray(source, np.int64)))
+        self.rt.api.check(self.rt.lib().rt_bfm_solve(self.handle.h, self.U_pin.numpy(), src, len(src), 64,
                                                      self.dist_pin.data_ptr(), self.prev_pin.data_ptr(), C.byref(st)))
         return st.as_dict()
 
@@ -174,12 +185,13 @@ def run_gpu(args):
     rt_loader.load_build().build()
     rt = rt_loader.load()
     rt.api.check(rt.lib().rt_set_device(local))
-    wl = GpuWorkload(args.workload, rt, torch, args.schedule)
+    wl = GpuWorkload(args.workload, rt, torch, args.schedule, args.sources_per_step)
+    sps = args.sources_per_step
     n = wl.n
     gather_d = gather_p = None
     if dist_on:
-        gather_d = torch.empty(world * n, dtype=torch.float64, device="cuda")
-        gather_p = torch.empty(world * n, dtype=torch.int32, device="cuda")
+        gather_d = torch.empty(world * n * sps, dtype=torch.float64, device="cuda")
+        gather_p = torch.empty(world * n * sps, dtype=torch.int32, device="cuda")
 
     def barrier():
         torch.cuda.synchronize()
@@ -187,9 +199,13 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def pick(k):
+        if sps == 1:
+            return wl.sources[(rank + k * world) % len(wl.sources)] if dist_on else wl.sources[0]
+        return [wl.sources[(rank + (k * sps + q) * world) % len(wl.sources)] for q in range(sps)]
+
     def step(k):
-        src = wl.sources[(rank + k * world) % len(wl.sources)] if dist_on else wl.sources[0]
-        st = wl.solve_dev(src)
+        st = wl.solve_dev(pick(k))
         if dist_on:  # gather the travel-time tables of this step on every rank
             dist.all_gather_into_tensor(gather_d, wl.dist_dev)
             dist.all_gather_into_tensor(gather_p, wl.prev_dev)
@@ -225,19 +241,18 @@ def run_gpu(args):
     prof = dict(relaxed_edges=0, vertex_updates=0, relax_ms=0.0, relax_launches=0, kernel_ms=0.0, prev_ms=0.0)
     prof_steps = max(1, min(args.steps, 2))
     for k in range(prof_steps):
-        st = wl.solve_dev(wl.sources[0])
+        st = wl.solve_dev(pick(0) if sps == 1 else wl.sources[0])
         for key in prof:
             prof[key] += st[key]
     wl.handle.set_option("profile_timers", 0)
 
     # end-to-end arm: same step through the host-buffer ABI call (H2D + D2H inside the timed region)
     e2e_steps = max(1, min(args.steps, 3))
-    wl.solve_e2e(wl.sources[0])
+    wl.solve_e2e(pick(0))
     barrier()
     t2 = time.perf_counter()
     for k in range(e2e_steps):
-        src = wl.sources[(rank + k * world) % len(wl.sources)] if dist_on else wl.sources[0]
-        wl.solve_e2e(src)
+        wl.solve_e2e(pick(k))
     barrier()
     e2e_ms = torch.tensor([(time.perf_counter() - t2) * 1e3], dtype=torch.float64, device="cuda")
     if dist_on:
@@ -246,8 +261,9 @@ def run_gpu(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        nsolved = args.steps * world
+        nsolved = args.steps * world * sps
         value = e_graph * nsolved / (wall_ms * 1e-3) / 1e9
+        kname = ("relax%s_kernel" if wl.schedule == "jacobi" else "push%s_kernel") % ("3d" if wl.w["kind"] == "3d" else "2d")
         bytes_alg = prof["relaxed_edges"] * 12 + prof["vertex_updates"] * wl.bv
         relax_ms = max(prof["relax_ms"], 1e-9)
         achieved = bytes_alg / (relax_ms * 1e-3) / 1e9
@@ -257,12 +273,12 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "nodes": n, "graph_edges_per_source": e_graph,
-                       "sources_per_step_per_gpu": 1, "velocity": "AK135 Vp",
+                       "sources_per_step_per_gpu": sps, "velocity": "AK135 Vp",
                        "schedule": "jacobi (reference sweeps)" if wl.schedule == "jacobi" else
                        "near-far push (dist bit-identical, prev exact except ties)",
                        "l2": "inputs larger than L2 (%.0f MB of node state per sweep set)" % (n * 48 / 1e6),
                        "parallelism": "source-sharded x%d, NCCL all_gather of tables" % world},
-            "ms_per_source": wall_ms / args.steps,
+            "ms_per_source": wall_ms / args.steps / sps,
             "device_ms_per_step": dev_ms / args.steps,
             "teps_graph_gteps": value,
             "relax_rate_gteps": (bytes_alg / 12.0) / (relax_ms * 1e-3) / 1e9,
@@ -272,13 +288,12 @@ def run_gpu(args):
             "prev_pass_share_of_step": prof["prev_ms"] / max(prof["kernel_ms"], 1e-9),
             "gpu_launches": acc["total_launches"],
             "clocks": clocks,
-            "e2e": {"value": e_graph * e2e_steps * world / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS",
-                    "ms_per_source": e2e_ms / e2e_steps, "h2d_bytes_per_step": n * 8 + 8,
-                    "d2h_bytes_per_step": n * 16},
+            "e2e": {"value": e_graph * e2e_steps * world * sps / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS",
+                    "ms_per_source": e2e_ms / e2e_steps / sps, "h2d_bytes_per_step": n * 8 + 8 * sps,
+                    "d2h_bytes_per_step": n * 16 * sps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": ("relax%s_kernel" if wl.schedule == "jacobi" else "push%s_kernel") %
-                         ("3d" if wl.w["kind"] == "3d" else "2d"),
+                         "frac": achieved / peak, "traffic": ncu_traffic(kname, args.workload),
+                         "peak_source": peak_src, "kernel": kname,
                          "bytes_model": "12 B per relaxed candidate + %d B per active-vertex update" % wl.bv,
                          "avg_launch_ms": relax_ms / max(prof["relax_launches"], 1)},
         }
@@ -361,6 +376,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--schedule", default="near-far", choices=["jacobi", "near-far"])
+    ap.add_argument("--sources-per-step", type=int, default=1,
+                    help="sources solved per step and GPU (BASELINE config[2]: batches of earthquakes on one mesh)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
