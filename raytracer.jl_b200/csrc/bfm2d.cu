@@ -10,8 +10,9 @@
 //     (column -> elements -> e2n lists) is read once per warp with coalesced id loads; lanes are laid out as
 //     (target, part) so that small items still fill 32 lanes, and parts are merged with a lexicographic
 //     (delta, scan position) shuffle reduction that reproduces the serial tie rule;
-//   * the frontier is kept per element ("dirty" = contains an improved node) and per item (active = some element
-//     of its column is dirty), which is the same vertex set as update_Q! by symmetry of the star patches;
+//   * the frontier follows update_Q! literally but at element granularity: an improved node touches every
+//     element of its G column (push side), a node is active iff an element that contains it was touched (pull
+//     side), an item is relaxed iff one of its nodes is active (a superset relaxes nothing new: bit-identical);
 //   * edge weights 2*len/(U_i+U_j) are computed in registers with round-to-nearest intrinsics (no FMA).
 // All arithmetic on the value path is IEEE fp64 with the reference's operation order.
 #include "mesh2d.cuh"

@@ -468,3 +468,25 @@ def test_bfm2d_near_far_batched_sources(rt, O, annulus, ak135):
         assert int(i) in halo_nodes or d[a] == d[i] or d[b] == d[i], "regular predecessor differs at node %d" % (i + 1)
     assert len(diff) < 0.1 * m.n
     rt.bfm(G, halo, 1, gr, Vp, schedule="jacobi")
+
+
+def test_edge_cases_empty_and_tiny(rt, O, annulus):
+    """Empty source batch, a single-node-per-axis 3-D grid, many receivers at once."""
+    import ctypes as C
+    m = annulus(24, 6, 300.0)
+    gr, G, halo = adopt(rt, m)
+    U = np.full(m.n, 5.0)
+    h = rt.mesh_from_arrays(gr, G, halo)
+    st = rt.RtStats()
+    rt.api.check(rt.lib().rt_bfm_solve(h.h, U, np.zeros(1, np.int64), 0, 64, None, None, C.byref(st)))  # nsrc = 0
+    assert st.sweeps == 0
+    D = rt.bfm(G, halo, 1, gr, U)
+    recv = np.arange(2, 400, dtype=np.int64)
+    paths = rt.recontruct_path(D.prev, 1, recv)
+    assert len(paths) == len(recv) and all(p[0] == r and p[-1] == 1 for p, r in zip(paths, recv))
+    g = rt.grid((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), (5, 1, 1), neighbour_levels=1)  # degenerate axes
+    X, Y, Z = g.coordinates()
+    D3 = rt.bfm3d(g, 1, np.ones(5))
+    d3, p3, _ = O.bfm3d((5, 1, 1), 1, X, Y, Z, np.ones(5), 1)
+    assert np.array_equal(D3.dist, d3) and np.array_equal(D3.prev, p3)
+    assert np.array_equal(rt.bfm3d(g, 1, np.ones(5), schedule="near-far").dist, d3)
