@@ -243,6 +243,8 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
   } else if (!std::strcmp(key, "delta")) {
     RT_ARG(value >= 0.0, "delta must be >= 0");
     m->opts.delta = value;
+  } else if (!std::strcmp(key, "cta_units")) {
+    m->opts.cta_units = value != 0.0;
   } else if (!std::strcmp(key, "warp_units")) {
     m->opts.warp_units = value < 0.0 ? -1 : (value != 0.0);
   } else if (!std::strcmp(key, "batch")) {

@@ -63,6 +63,7 @@ struct PP {
                   // [5] push rounds
   // batch of sources solved in lock step (state arrays hold nb slices; pp_view() selects one)
   int nb;
+  int cta_units;   // long columns: 1 = CTA per (item, element group) with block barriers, 0 = warp per (item, element)
   int warp_units;  // 1: short columns -> warp-per-item push (push2d_warp_body), 0: CTA per (item, element group)
   i64 n, n_items;
   const int* sources;  // [nb] 0-based
@@ -507,6 +508,153 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Barrier-free push for long columns: warp-level unit = (released item, element lane e): the warp keeps its own copy
+// of the released sources (warp-private smem slab) and walks the elements e, e + PUSH_GE, ... of the column with the
+// software-pipelined target loop.  (The CTA-level variant above spends a third of its stall time in __syncthreads.)
+constexpr int PUSH_GE = 16;
+template <bool PACKED>
+__device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned mask, int e0, int cur, i32* near_next,
+                                                 i32* far_list, int fcur, double tau, double2* sxz, double2* sUd,
+                                                 int* s_id) {
+  const int lane = threadIdx.x & 31;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const int v0 = p.item_first[it];
+  const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
+  if (c0 + e0 >= c1 && e0 != 0) return;  // warp-uniform: no element for this lane of the column
+  __syncwarp();
+  const bool on = (mask >> lane) & 1u;
+  const int pos = __popc(mask & ((1u << lane) - 1u));
+  double dmy = INF;
+  if (on) {
+    const int i = v0 + lane;
+    dmy = __ldcg(&p.dist[(i64)i * p.ds]);
+    sxz[pos] = make_double2(p.x[i], p.z[i]);
+    sUd[pos] = make_double2(p.U[i], dmy);
+    s_id[pos] = i;
+  }
+  double dmin = dmy;
+  for (int o = 16; o; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
+  const int ns = __popc(mask);
+  __syncwarp();
+  if (e0 == 0 && p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {  // zero-weight halo coupling
+    const int lo = p.hn_index[s_id[lane]];
+    if (lo >= 0) {
+      const double d = sUd[lane].y;
+      for (int q = p.hn_off[lo]; q < p.hn_off[lo + 1]; ++q) {
+        const int b = p.hn_part[q];
+        if (PACKED) {
+          const DP cb = dp_load(p, b);
+          if ((u64)__double_as_longlong(d) < cb.d && dp_update(p, b, cb, d, KEY_HALO | (u64)s_id[lane]))
+            enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+        } else if (d < __ldcg(&p.dist[(i64)b * p.ds]) && relax_to(p, b, d)) {
+          enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+        }
+      }
+    }
+  }
+  u64 evals = 0;
+  for (i64 c = c0 + e0; c < c1; c += PUSH_GE) {
+    const int el = p.g_idx[c];
+    const int s = p.e2n_off[el];
+    const int m = p.e2n_off[el + 1] - s;
+    int k = lane;
+    int j = k < m ? p.e2n_idx[s + k] : -1;
+    double dj = 0.0, xj = 0.0, zj = 0.0, Uj = 0.0;
+    u64 kj = KEY_NONE, kjn = KEY_NONE;
+    if (j >= 0) {
+      if (PACKED) kj = __ldcg(p.keys + 2 * (i64)j + 1);
+      dj = __ldcg(&p.dist[(i64)j * p.ds]);
+      xj = p.x[j];
+      zj = p.z[j];
+      Uj = p.U[j];
+    }
+    while (k < m) {
+      const int kn = k + 32;
+      const int jn = kn < m ? p.e2n_idx[s + kn] : -1;
+      double djn = 0.0, xjn = 0.0, zjn = 0.0, Ujn = 0.0;
+      if (jn >= 0) {
+        if (PACKED) kjn = __ldcg(p.keys + 2 * (i64)jn + 1);
+        djn = __ldcg(&p.dist[(i64)jn * p.ds]);
+        xjn = p.x[jn];
+        zjn = p.z[jn];
+        Ujn = p.U[jn];
+      }
+      if (dmin < dj) {
+        double best = dj;
+        u64 bkey = kj;
+        bool changed = false;
+        for (int q = 0; q < ns; ++q) {
+          const double2 ud = sUd[q];
+          const double di = ud.y;
+          if (!(di < best)) continue;
+          const double2 xz = sxz[q];
+          {
+            const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+            if (screen_cannot_improve(best, di, d2, __dadd_rn(ud.x, Uj))) continue;
+          }
+          const double delta = edge_delta(di, xz.x, xz.y, ud.x, xj, zj, Uj);
+          if (PACKED) {
+            const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
+            if (delta < best) {
+              best = delta;
+              bkey = key;
+              changed = true;
+            } else if (delta == best && !(key & KEY_ZMASK) && key < bkey) {
+              bkey = key;
+              changed = true;
+            }
+          } else {
+            best = delta < best ? delta : best;
+          }
+        }
+        if (PACKED) {
+          if (changed) {
+            DP cur_dp;
+            cur_dp.d = (u64)__double_as_longlong(dj);
+            cur_dp.k = kj;
+            if (dp_update(p, j, cur_dp, best, bkey)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+          }
+        } else if (best < dj && relax_to(p, j, best)) {
+          enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+        }
+      }
+      k = kn;
+      j = jn;
+      kj = kjn;
+      dj = djn;
+      xj = xjn;
+      zj = zjn;
+      Uj = Ujn;
+    }
+    evals += (u64)m * (u64)ns;
+  }
+  if (lane == 0) {
+    if (evals) atomicAdd(&p.counters[2], evals);
+    if (e0 == 0) atomicAdd(&p.counters[3], (u64)ns);
+  }
+}
+__device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
+                                                 i32* far_list, int fcur, i64 first_warp, i64 n_warps) {
+  __shared__ double2 e_sxz[PUSH_BLOCK / 32][32], e_sUd[PUSH_BLOCK / 32][32];
+  __shared__ int e_id[PUSH_BLOCK / 32][32];
+  const int warp = threadIdx.x >> 5;
+  const i64 n_near = (i64)__ldcg(&p.counters[cur]);
+  const double tau = __ldcg(&p.tau[0]);
+  for (i64 unit = first_warp; unit < n_near * PUSH_GE; unit += n_warps) {
+    const i64 slot = unit / PUSH_GE;
+    const int e0 = (int)(unit - slot * PUSH_GE);
+    const int it = __ldcg(&near_cur[slot]);
+    const unsigned mask = __ldcg(&p.cur_mask[slot]);
+    if (mask == 0u) continue;
+    if (p.ds == 2)
+      push2d_elem_unit<true>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp], e_id[warp]);
+    else
+      push2d_elem_unit<false>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp], e_id[warp]);
+  }
+}
+
 template <bool WARP>
 __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
@@ -514,10 +662,15 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
     const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
     push2d_warp_body(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
-  } else if (p.ds == 2) {
-    push2d_body_t<true>(p, near_cur, cur, near_next, far_list, fcur);
+  } else if (p.cta_units) {
+    if (p.ds == 2)
+      push2d_body_t<true>(p, near_cur, cur, near_next, far_list, fcur);
+    else
+      push2d_body_t<false>(p, near_cur, cur, near_next, far_list, fcur);
   } else {
-    push2d_body_t<false>(p, near_cur, cur, near_next, far_list, fcur);
+    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+    push2d_elem_body(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
   }
 }
 template <bool WARP>
@@ -1094,6 +1247,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.ctl = m.ctl.p;
   p.nb = 1;
   p.warp_units = (h->opts.warp_units == 1 || (h->opts.warp_units < 0 && m.graph_edges / std::max<i64>(n, 1) < 1500)) ? 1 : 0;
+  p.cta_units = h->opts.cta_units;
   p.n = n;
   p.n_items = m.n_items;
   p.sources = m.bsources.p;
@@ -1223,7 +1377,7 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
             push2d_kernel<true><<<(unsigned)std::min<i64>((n_near + 3) / 4, max_blocks), PUSH_BLOCK, 0, s>>>(
                 p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           else
-            push2d_kernel<false><<<(unsigned)std::min<i64>(n_near * PUSH_GY, max_blocks), PUSH_BLOCK, 0, s>>>(
+            push2d_kernel<false><<<(unsigned)std::min<i64>(n_near * (p.cta_units ? PUSH_GY : PUSH_GE / 4), max_blocks), PUSH_BLOCK, 0, s>>>(
                 p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           cudaEventRecord(evr1, s);
           pushed = true;

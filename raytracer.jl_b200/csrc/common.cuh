@@ -118,6 +118,7 @@ struct SolverOpts {
   int check_every = 0;     // rounds between host convergence checks (0 = default)
   double delta = 0.0;      // near-far bucket width [s]; 0 = automatic
   int persistent = -1;     // near-far: 1 = persistent cooperative kernel, 0 = launch sequence per round, -1 = auto
+  int cta_units = 0;       // near-far 2-D, long columns: 1 = CTA-level units with block barriers (older variant)
   int warp_units = -1;     // near-far 2-D push mapping: 1 warp per item, 0 CTA per (item, element group), -1 auto
   int batch = 0;           // near-far: sources solved in lock step on small meshes (0 = automatic, <= 32)
   int packed_prev = 1;     // near-far 2-D: 1 = 128-bit (time, predecessor) CAS, 0 = separate tightness pass

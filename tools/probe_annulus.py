@@ -29,6 +29,7 @@ for (nt, nr, sp) in meshes:
     import os
     h.set_option("profile_timers", int(os.environ.get("RT_TIMERS", "1")))
     h.set_option("persistent", int(os.environ.get("RT_PERSISTENT", "-1")))
+    h.set_option("cta_units", int(os.environ.get("RT_CTA_UNITS", "0")))
     h.set_option("check_every", int(os.environ.get("RT_CHECK_EVERY", "0")))
     d = torch.empty(n, dtype=torch.float64, device="cuda")
     p = torch.empty(n, dtype=torch.int32, device="cuda")
