@@ -327,10 +327,19 @@ def cpu_instance(workload):
     return run, desc
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it, the CPU arm is
+    meant to use the whole box)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(workload, steps=1):
     from oracle import oracle as O
     run, desc = cpu_instance(workload)
-    cores = O.num_threads()
+    cores = host_threads()
     t0 = time.perf_counter()
     for _ in range(steps):
         d, p, st = run(cores)
@@ -347,9 +356,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
     run, desc = cpu_instance(args.workload)
-    cores = O.num_threads()
+    cores = host_threads()
     for _ in range(min(args.warmup, 1)):
         run(cores)
     t0 = time.perf_counter()

@@ -36,7 +36,7 @@ struct Grid3D {
   // workspace
   DevBuf<double> dist, dist0;
   DevBuf<i32> prev;
-  DevBuf<uint8_t> improved;  // per tile
+  DevBuf<unsigned> improved;  // per tile: 0 = nothing improved, else bit 31 | bounding box of the improved nodes
   DevBuf<i32> act[2];
   DevBuf<u64> counters;
   u64* counters_host = nullptr;
@@ -61,7 +61,7 @@ struct P3 {
   double* dist;
   double* dist0;
   i32* prev;
-  uint8_t* improved;
+  unsigned* improved;
   u64* counters;
   int nx, ny, nz;
   int tnx, tny, tnz;
@@ -207,7 +207,24 @@ __global__ void __launch_bounds__(TILE_THREADS) commit3d_kernel(P3 p, const i32*
         imp = true;
       }
     }
-    if (__syncthreads_or(imp) && tid == 0) p.improved[tile] = 1;
+    // bounding box (tile-local coordinates) of the improved nodes: lets activate3d skip neighbours that the
+    // +-w window of those nodes cannot reach
+    __shared__ int s_box[6];
+    if (tid < 6) s_box[tid] = (tid & 1) ? -1 : 99;  // [minx, maxx, miny, maxy, minz, maxz]
+    __syncthreads();
+    if (imp) {
+      atomicMin(&s_box[0], lx);
+      atomicMax(&s_box[1], lx);
+      atomicMin(&s_box[2], ly);
+      atomicMax(&s_box[3], ly);
+      atomicMin(&s_box[4], lz);
+      atomicMax(&s_box[5], lz);
+    }
+    __syncthreads();
+    if (tid == 0 && s_box[1] >= 0)
+      p.improved[tile] = 0x80000000u | (unsigned)s_box[0] | ((unsigned)s_box[1] << 3) | ((unsigned)s_box[2] << 6) |
+                         ((unsigned)s_box[3] << 8) | ((unsigned)s_box[4] << 10) | ((unsigned)s_box[5] << 12);
+    __syncthreads();
   }
 }
 
@@ -220,11 +237,19 @@ __global__ void activate3d_kernel(P3 p, i64 n_tiles, i32* __restrict__ next_acti
     const int rx = (p.w + TX - 1) / TX, ry = (p.w + TY - 1) / TY, rz = (p.w + TZ - 1) / TZ;
     for (int zz = max(0, tz - rz); zz <= min(p.tnz - 1, tz + rz) && !act; ++zz)
       for (int yy = max(0, ty - ry); yy <= min(p.tny - 1, ty + ry) && !act; ++yy)
-        for (int xx = max(0, tx - rx); xx <= min(p.tnx - 1, tx + rx); ++xx)
-          if (p.improved[(i64)xx + (i64)p.tnx * ((i64)yy + (i64)p.tny * zz)]) {
+        for (int xx = max(0, tx - rx); xx <= min(p.tnx - 1, tx + rx); ++xx) {
+          const unsigned b = p.improved[(i64)xx + (i64)p.tnx * ((i64)yy + (i64)p.tny * zz)];
+          if (!b) continue;
+          // improved box of that tile, grown by the window half width, against this tile's node range
+          const int x0 = xx * TX + (int)(b & 7u) - p.w, x1 = xx * TX + (int)((b >> 3) & 7u) + p.w;
+          const int y0 = yy * TY + (int)((b >> 6) & 3u) - p.w, y1 = yy * TY + (int)((b >> 8) & 3u) + p.w;
+          const int z0 = zz * TZ + (int)((b >> 10) & 3u) - p.w, z1 = zz * TZ + (int)((b >> 12) & 3u) + p.w;
+          if (x0 <= tx * TX + TX - 1 && x1 >= tx * TX && y0 <= ty * TY + TY - 1 && y1 >= ty * TY &&
+              z0 <= tz * TZ + TZ - 1 && z1 >= tz * TZ) {
             act = true;
             break;
           }
+        }
   }
   const unsigned ball = __ballot_sync(FULL, act);
   if (ball) {
@@ -834,18 +859,19 @@ int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
     const i64 src = src1 - 1;
     cudaEventRecord(ev0, s);
     init3d_kernel<<<grid_for(n, 256), 256, 0, s>>>(p.dist, p.dist0, p.prev, n, src);
-    cudaMemsetAsync(g.improved.p, 0, g.n_tiles, s);
+    cudaMemsetAsync(g.improved.p, 0, g.n_tiles * sizeof(unsigned), s);
     cudaMemsetAsync(g.counters.p, 0, 8 * sizeof(u64), s);
     // initial active set = window of the source (BFM: union!(active, G[source])) -> tiles around its tile
     {
       const i64 sx = src % g.nn[0], sy = (src / g.nn[0]) % g.nn[1], sz = src / (g.nn[0] * g.nn[1]);
       const i64 st_tile = (sx / TX) + g.tn[0] * ((sy / TY) + g.tn[1] * (sz / TZ));
-      const uint8_t one = 1;
-      cudaMemcpyAsync(g.improved.p + st_tile, &one, 1, cudaMemcpyHostToDevice, s);
+      const unsigned lx = (unsigned)(sx % TX), ly = (unsigned)(sy % TY), lz = (unsigned)(sz % TZ);
+      const unsigned one = 0x80000000u | lx | (lx << 3) | (ly << 6) | (ly << 8) | (lz << 10) | (lz << 12);
+      cudaMemcpyAsync(g.improved.p + st_tile, &one, sizeof(unsigned), cudaMemcpyHostToDevice, s);
     }
     int cur = 0;
     activate3d_kernel<<<grid_for(g.n_tiles, 256), 256, 0, s>>>(p, g.n_tiles, g.act[cur].p, cur);
-    cudaMemsetAsync(g.improved.p, 0, g.n_tiles, s);
+    cudaMemsetAsync(g.improved.p, 0, g.n_tiles * sizeof(unsigned), s);
     cudaMemcpyAsync(g.counters_host, g.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
     st.total_launches += 2;
     if (cudaStreamSynchronize(s) != cudaSuccess) {
@@ -862,7 +888,7 @@ int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
       commit3d_kernel<<<nb, TILE_THREADS, 0, s>>>(p, g.act[cur].p, cur);
       cudaMemsetAsync(g.counters.p + nxt, 0, sizeof(u64), s);
       activate3d_kernel<<<grid_for(g.n_tiles, 256), 256, 0, s>>>(p, g.n_tiles, g.act[nxt].p, nxt);
-      cudaMemsetAsync(g.improved.p, 0, g.n_tiles, s);
+      cudaMemsetAsync(g.improved.p, 0, g.n_tiles * sizeof(unsigned), s);
       cudaMemcpyAsync(g.counters_host, g.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
       st.total_launches += 3;
       st.relax_launches += 1;
