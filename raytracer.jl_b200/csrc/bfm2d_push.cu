@@ -54,9 +54,6 @@ struct PP {
   unsigned* far_mask;
   unsigned* infar;
   unsigned* cur_mask;
-  double* emax;   // per element: an upper bound of max(dist) over its nodes (travel times only decrease, so a value that
-                  // was the maximum at some moment stays a valid bound); lets a push skip elements that lie behind it
-  i64 nel;
   u64* counters;  // [0],[1] near counts (ping-pong) [2] evals [3] releases [4],[5] far counts (ping-pong)
                   // [6] unresolved count [7] scratch
   double* tau;    // [0] tau [1] delta [2] min far (bits)
@@ -85,7 +82,6 @@ __device__ __forceinline__ PP pp_view(const PP& p, int b) {
   v.far_mask = p.far_mask + (i64)b * p.n_items;
   v.infar = p.infar + (i64)b * p.n_items;
   v.cur_mask = p.cur_mask + (i64)b * p.n_items;
-  v.emax = p.emax + (i64)b * p.nel;
   v.counters = p.counters + (i64)b * 8;
   v.tau = p.tau + (i64)b * 4;
   v.nearq0 = p.nearq0 + (i64)b * p.n_items;
@@ -560,11 +556,8 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
   u64 evals = 0;
   for (i64 c = c0 + e0; c < c1; c += PUSH_GE) {
     const int el = p.g_idx[c];
-    // every node of this element is already at or below the earliest released source: nothing to do
-    if (!(dmin < __ldcg(&p.emax[el]))) continue;
     const int s = p.e2n_off[el];
     const int m = p.e2n_off[el + 1] - s;
-    double lmax = 0.0;  // running max of the node values seen (after this unit's own updates)
     int k = lane;
     int j = k < m ? p.e2n_idx[s + k] : -1;
     double dj = 0.0, xj = 0.0, zj = 0.0, Uj = 0.0;
@@ -587,7 +580,6 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
         zjn = p.z[jn];
         Ujn = p.U[jn];
       }
-      double vj = dj;  // value of this node after the unit (for the element bound)
       if (dmin < dj) {
         double best = dj;
         u64 bkey = kj;
@@ -627,9 +619,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
         } else if (best < dj && relax_to(p, j, best)) {
           enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
         }
-        vj = best;
       }
-      lmax = fmax(lmax, vj);
       k = kn;
       j = jn;
       kj = kjn;
@@ -639,8 +629,6 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
       Uj = Ujn;
     }
     evals += (u64)m * (u64)ns;
-    for (int o = 16; o; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(FULL, lmax, o));
-    if (lane == 0) p.emax[el] = lmax;  // the whole element was scanned by this warp
   }
   if (lane == 0) {
     if (evals) atomicAdd(&p.counters[2], evals);
@@ -740,7 +728,6 @@ __global__ void push_init_kernel(PP pb, i64 n, double delta) {
   const int source = p.source;
   i32* near0 = nq(p, 0);
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < p.nel) p.emax[i] = __longlong_as_double(0x7ff0000000000000LL);
   if (i < n) {
     p.dist[i * p.ds] = (i == source) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
     if (p.ds == 2) p.keys[2 * i + 1] = KEY_NONE;
@@ -1188,7 +1175,6 @@ int ensure_push_workspace(rt_mesh* h, int nb, bool packed) {
     RT_TRY(m.far_mask.alloc(B * m.n_items));
     RT_TRY(m.infar_u.alloc(B * m.n_items));
     RT_TRY(m.cur_mask.alloc(B * m.n_items));
-    RT_TRY(m.emax.alloc(B * m.nel));
     for (int k = 0; k < 2; ++k) {
       RT_TRY(m.nearq[k].alloc(B * m.n_items));
       RT_TRY(m.farq[k].alloc(B * m.n_items));
@@ -1252,8 +1238,6 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.far_mask = m.far_mask.p;
   p.infar = m.infar_u.p;
   p.cur_mask = m.cur_mask.p;
-  p.emax = m.emax.p;
-  p.nel = m.nel;
   p.counters = m.bcounters.p;
   p.tau = m.tau.p;
   p.nearq0 = m.nearq[0].p;

@@ -45,7 +45,6 @@ struct Mesh2D {
   DevBuf<i32> node_item;               // node -> work item
   DevBuf<unsigned> pend_mask, far_mask;  // per item: nodes with an unpropagated improvement (near / far)
   DevBuf<unsigned> infar_u;            // per item: already in the far list
-  DevBuf<double> emax;                 // per element upper bound of its nodes' travel times (push pruning)
   DevBuf<unsigned> cur_mask;           // per near-list slot: the nodes released this round
   DevBuf<i32> nearq[2], farq[2];
   DevBuf<i32> hn_index;                // node -> row in hn_off, -1 if the node has no halo partner
