@@ -107,6 +107,20 @@ int rt_interp_velocity_dev(const double* knots_r, const double* knots_v, int64_t
  * gr.r (theta / r NULL if the mesh was adopted without them); 3-D -> (X, Y, Z, NULL). */
 int rt_mesh_coords_dev(const rt_mesh* m, const double** a, const double** b, const double** c, const double** d);
 
+/* ---- node-to-node topology (src/topology/topology.jl, src/SSSP/rcm.jl) ------------------------------------- */
+/* nodal_incidence(gr::Grid2D) src/GridAnnulus.jl:763-804 as the CSR container SparseAdjencyList{list,deg,idx} of
+ * sparse_adjacency_list (topology.jl:94-111): star-0 neighbours (nodes sharing a cell, self excluded, each once).
+ * deg[n] = nodal_degree (topology.jl:70-77); list_off[n+1] 0-based offsets (the reference's idx = list_off + 1);
+ * list_idx 1-based ids in (ascending cell, list order) -- the reference iterates a Julia Set, whose order is not
+ * reproducible.  Two-call pattern: list_idx == NULL writes only deg / list_off.  Any pointer may be NULL. */
+int rt_nodal_adjacency(rt_mesh* m, int64_t* deg, int64_t* list_off, int64_t* list_idx, int64_t cap);
+
+/* symrcm(adjgr, degrees) src/SSSP/rcm.jl:2-46 on that adjacency: BFS from the minimum-degree node (next component:
+ * next minimum-degree unplaced node), children ordered by (position of their earliest parent, node id) where the
+ * reference uses Set iteration order, result reversed.  perm_out[n] 1-based: position k of the reordered mesh holds
+ * old node perm_out[k], i.e. `gr.x .= gr.x[prm]` of reorder! (rcm.jl:62-85). */
+int rt_rcm(rt_mesh* m, int64_t* perm_out);
+
 /* ---- closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 ---------------------------------------- */
 /* system 0 = :cartesian (x,z), 1 = :polar ((theta, r) treated as Cartesian).  First index of the minimum. */
 int rt_closest_point(const rt_mesh* m, const double* pa, const double* pb, int64_t npts, int system,

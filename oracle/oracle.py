@@ -51,6 +51,7 @@ def lib():
         L.ora_bfm3d.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, C.c_int, I64, F64P, I64P, I64P]
         L.ora_dijkstra3d.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, F64P]
         L.ora_interpolate_cells.argtypes = [I64, I64P, I64P, I8P, F64P, F64P, F64P]
+        L.ora_nodal_adjacency.argtypes = [I64, I64, I64P, I64P, I64P, I64P, C.c_void_p]
         L.ora_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -176,6 +177,16 @@ def interpolate_cells(mesh, V):
     V = np.array(V, np.float64)
     lib().ora_interpolate_cells(mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.el_type, mesh.theta, mesh.r, V)
     return V
+
+
+def nodal_adjacency(mesh):
+    """nodal_incidence(gr::Grid2D) src/GridAnnulus.jl:763-804 -> (deg, off, list ascending per node, 1-based)."""
+    deg = np.zeros(mesh.n, np.int64)
+    off = np.zeros(mesh.n + 1, np.int64)
+    lib().ora_nodal_adjacency(mesh.n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, deg, off, None)
+    lst = np.zeros(int(off[-1]), np.int64)
+    lib().ora_nodal_adjacency(mesh.n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, deg, off, lst.ctypes.data_as(C.c_void_p))
+    return deg, off, lst
 
 
 def num_threads():

@@ -797,6 +797,26 @@ void ora_interpolate_cells(i64 nel, const i64* e2n_off, const i64* e2n_idx, cons
   }
 }
 
+// src/GridAnnulus.jl:763-804 nodal_incidence(gr::Grid2D): Q[nJ] = nodes of every cell containing nJ, self excluded,
+// each once.  Output: deg[n] and (if list != null) the neighbours ASCENDING per node (set semantics).
+void ora_nodal_adjacency(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, i64* deg, i64* off, i64* list) {
+  std::vector<std::vector<i64>> Q(n);
+  for (i64 e = 0; e < nel; ++e)
+    for (i64 a = e2n_off[e]; a < e2n_off[e + 1]; ++a)
+      for (i64 b = e2n_off[e]; b < e2n_off[e + 1]; ++b)
+        if (e2n_idx[a] != e2n_idx[b]) Q[e2n_idx[a] - 1].push_back(e2n_idx[b]);
+  i64 o = 0;
+  for (i64 v = 0; v < n; ++v) {
+    std::sort(Q[v].begin(), Q[v].end());
+    Q[v].erase(std::unique(Q[v].begin(), Q[v].end()), Q[v].end());
+    deg[v] = (i64)Q[v].size();
+    off[v] = o;
+    if (list) std::copy(Q[v].begin(), Q[v].end(), list + o);
+    o += deg[v];
+  }
+  off[n] = o;
+}
+
 int ora_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -17,7 +17,7 @@ I64P = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 SYMBOLS = [
     "rt_last_error", "rt_version", "rt_device_count", "rt_set_device", "rt_annulus_build", "rt_mesh_sizes",
     "rt_mesh_export", "rt_mesh_from_arrays", "rt_grid3d_build", "rt_grid3d_export", "rt_mesh_free",
-    "rt_interp_velocity", "rt_interp_velocity_dev", "rt_interpolate_cells", "rt_mesh_coords_dev", "rt_closest_point", "rt_bfm_solve",
+    "rt_interp_velocity", "rt_interp_velocity_dev", "rt_interpolate_cells", "rt_nodal_adjacency", "rt_rcm", "rt_mesh_coords_dev", "rt_closest_point", "rt_bfm_solve",
     "rt_bfm_solve_dev", "rt_set_option", "rt_reconstruct_paths", "rt_reconstruct_paths_dev",
 ]
 
@@ -62,6 +62,8 @@ def lib():
     L.rt_mesh_free.argtypes = [VP]
     L.rt_interp_velocity.argtypes = [F64P, F64P, I64, F64P, I64, C.c_double, F64P]
     L.rt_interpolate_cells.argtypes = [VP, VP, F64P]
+    L.rt_nodal_adjacency.argtypes = [VP, VP, VP, VP, I64]
+    L.rt_rcm.argtypes = [VP, I64P]
     L.rt_interp_velocity_dev.argtypes = [F64P, F64P, I64, VP, I64, C.c_double, VP]
     L.rt_mesh_coords_dev.argtypes = [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), C.POINTER(VP)]
     L.rt_closest_point.argtypes = [VP, F64P, F64P, I64, C.c_int, I64P]

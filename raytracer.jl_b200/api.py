@@ -230,6 +230,68 @@ def interpolate_inplace(V, gr, G=None, halo=None):
     return V
 
 
+# ----------------------------------------------------------------------------------------------- topology
+class SparseAdjencyList:
+    """SparseAdjencyList{list, deg, idx} of src/topology/topology.jl:88-92 (sic): CSR of the star-0 node adjacency;
+    idx is 1-based like the reference (idx = 1 + cumsum(deg))."""
+
+    def __init__(self, lst, deg, idx):
+        self.list, self.deg, self.idx = lst, deg, idx
+
+    def neighbours(self, node):
+        return self.list[self.idx[node - 1] - 1:self.idx[node - 1] - 1 + self.deg[node - 1]]
+
+
+def _handle_of(gr, G=None, halo=None):
+    return gr._handle if gr._handle is not None else mesh_from_arrays(gr, G, halo)
+
+
+def nodal_degree(gr, G=None, halo=None):
+    """nodal_degree(nodal_incidence(gr)) -- src/topology/topology.jl:70-77 on src/GridAnnulus.jl:763-804."""
+    deg = np.zeros(gr.nnods, np.int64)
+    check(lib().rt_nodal_adjacency(_handle_of(gr, G, halo).h, ptr(deg), None, None, 0))
+    return deg
+
+
+def sparse_adjacency_list(gr, G=None, halo=None):
+    """sparse_adjacency_list(nodal_incidence(gr)) -- src/topology/topology.jl:94-111."""
+    h = _handle_of(gr, G, halo)
+    n = gr.nnods
+    deg = np.zeros(n, np.int64)
+    off = np.zeros(n + 1, np.int64)
+    check(lib().rt_nodal_adjacency(h.h, ptr(deg), ptr(off), None, 0))
+    lst = np.zeros(int(off[-1]), np.int64)
+    check(lib().rt_nodal_adjacency(h.h, None, None, ptr(lst), len(lst)))
+    return SparseAdjencyList(lst, deg, off[:-1] + 1)
+
+
+def symrcm(gr, G=None, halo=None):
+    """symrcm(nodal_incidence(gr), degrees) -- src/SSSP/rcm.jl:2-46.  Returns prm (1-based int64)."""
+    prm = np.zeros(gr.nnods, np.int64)
+    check(lib().rt_rcm(_handle_of(gr, G, halo).h, prm))
+    return prm
+
+
+def reorder(gr, G, halo, prm):
+    """reorder!(gr, prm) of src/SSSP/rcm.jl:62-85 as a pure function: coordinates permuted (x .= x[prm]), e2n
+    relabelled with the inverse map (rordering_map :87-94).  Unlike the reference (which forgets `halo` and leaves
+    G stale) the halo matrix and the columns of G are relabelled too, so the result can be passed to bfm."""
+    prm = np.asarray(prm, np.int64)
+    n = gr.nnods
+    inv = np.zeros(n + 1, np.int64)
+    inv[prm] = np.arange(1, n + 1)
+    sel = prm - 1
+    col_len = np.diff(G.colptr)[sel]
+    colptr = np.concatenate([[1], 1 + np.cumsum(col_len)]).astype(np.int64)
+    starts = G.colptr[:-1][sel] - 1
+    take = np.repeat(starts - (colptr[:-1] - 1), col_len) + np.arange(int(col_len.sum()))
+    gr2 = Grid2D(gr.x[sel].copy(), gr.z[sel].copy(), gr.theta[sel].copy(), gr.r[sel].copy(), gr.e2n_off.copy(),
+                 inv[gr.e2n_idx], gr.ntheta, gr.nr, gr.nel, n, gr.nbr_off, gr.nbr_idx, gr.element_type)
+    G2 = SparseMatrixCSC(G.m, n, colptr, G.rowval[take].copy())
+    halo2 = None if halo is None else inv[np.asarray(halo, np.int64)]
+    return gr2, G2, halo2
+
+
 # ------------------------------------------------------------------------------------------ closest_point
 def closest_point(gr, px, pz, system="cartesian"):
     """closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 -> 1-based node id (scalar or array)."""

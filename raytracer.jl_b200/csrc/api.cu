@@ -168,6 +168,18 @@ int rt_interpolate_cells(rt_mesh* m, const int8_t* el_type, double* V) {
   return RT_OK;
 }
 
+int rt_nodal_adjacency(rt_mesh* m, int64_t* deg, int64_t* list_off, int64_t* list_idx, int64_t cap) {
+  RT_ARG(m && m->kind == 2, "rt_nodal_adjacency needs a 2-D mesh");
+  RT_CUDA(cudaSetDevice(m->device));
+  return mesh2d_nodal_adjacency(m, deg, list_off, list_idx, cap);
+}
+
+int rt_rcm(rt_mesh* m, int64_t* perm_out) {
+  RT_ARG(m && m->kind == 2 && perm_out, "rt_rcm needs a 2-D mesh and an output array");
+  RT_CUDA(cudaSetDevice(m->device));
+  return mesh2d_rcm(m, perm_out);
+}
+
 int rt_closest_point(const rt_mesh* m, const double* pa, const double* pb, int64_t npts, int system,
                      int64_t* index_out) {
   RT_ARG(m && m->kind == 2, "rt_closest_point needs a 2-D mesh");

@@ -154,6 +154,8 @@ int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
 int mesh2d_closest(const rt_mesh* h, const double* pa, const double* pb, i64 npts, int system, i64* out);
 int annulus_build_device(rt_mesh* h, i64 ntheta, i64 nr, double spacing);
 int mesh2d_interpolate_cells(rt_mesh* h, const int8_t* el_type_host, double* V_dev);
+int mesh2d_nodal_adjacency(rt_mesh* h, i64* deg_out, i64* list_off, i64* list_idx, i64 cap);
+int mesh2d_rcm(rt_mesh* h, i64* perm_out);
 int mesh2d_coords(const rt_mesh* h, const double** x, const double** z, const double** theta, const double** r);
 int grid3d_coords(const rt_mesh* h, const double** X, const double** Y, const double** Z, const double** none);
 

@@ -490,3 +490,43 @@ def test_edge_cases_empty_and_tiny(rt, O, annulus):
     d3, p3, _ = O.bfm3d((5, 1, 1), 1, X, Y, Z, np.ones(5), 1)
     assert np.array_equal(D3.dist, d3) and np.array_equal(D3.prev, p3)
     assert np.array_equal(rt.bfm3d(g, 1, np.ones(5), schedule="near-far").dist, d3)
+
+
+def test_topology_containers_and_rcm(rt, O, annulus, ak135):
+    """nodal_incidence / nodal_degree / sparse_adjacency_list (src/topology/topology.jl) and symrcm + reorder!
+    (src/SSSP/rcm.jl) on the device."""
+    m = annulus(36, 10, 100.0)
+    gr, G, halo = adopt(rt, m)
+    rt.mesh_from_arrays(gr, G, halo)
+    deg_o, off_o, lst_o = O.nodal_adjacency(m)
+    assert np.array_equal(rt.nodal_degree(gr), deg_o)
+    A = rt.sparse_adjacency_list(gr)
+    assert np.array_equal(A.deg, deg_o) and np.array_equal(A.idx, off_o[:-1] + 1)
+    for v in (1, 7, m.nr * m.ntheta + 1, m.n // 2, m.n):  # same neighbour SETS (the reference's order is a Set's)
+        assert sorted(A.neighbours(v)) == list(lst_o[off_o[v - 1]:off_o[v]])
+    assert np.array_equal(np.sort(A.list[:off_o[50]].reshape(-1)), np.sort(lst_o[:off_o[50]]))
+    # symrcm: a permutation; every node but the component seeds has a neighbour placed before it in BFS order
+    prm = rt.symrcm(gr)
+    assert sorted(prm) == list(range(1, m.n + 1))
+    F = prm[::-1]  # Cuthill-McKee order before the reversal
+    posF = np.zeros(m.n + 1, np.int64)
+    posF[F] = np.arange(m.n)
+    seeds = 0
+    for v in F:
+        nb = lst_o[off_o[v - 1]:off_o[v]]
+        if len(nb) == 0 or posF[nb].min() > posF[v]:
+            seeds += 1
+    assert 1 <= seeds <= 16  # one seed per connected component (8 velocity layers, twins are separate nodes)
+    assert deg_o[F[0] - 1] == deg_o.min()  # starts from a minimum-degree node (rcm.jl:4,13-22)
+    # reorder! + solve: travel times are the same function of the (relabelled) nodes
+    Vp = O.interp_velocity(ak135[0], ak135[1], m.r)
+    src = O.closest_point(m.theta, m.r, 0.0, R)
+    D = rt.bfm(G, halo, src, gr, Vp)
+    gr2, G2, halo2 = rt.reorder(gr, G, halo, prm)
+    inv = np.zeros(m.n + 1, np.int64)
+    inv[prm] = np.arange(1, m.n + 1)
+    D2 = rt.bfm(G2, halo2, int(inv[src]), gr2, Vp[prm - 1])
+    assert np.array_equal(D2.dist, D.dist[prm - 1])
+    # bandwidth of the element lists (max id spread inside a cell) does not explode under RCM
+    spread = lambda g: max(int(g.e2n[e].max() - g.e2n[e].min()) for e in range(1, m.nel + 1, 7))
+    assert spread(gr2) <= 2 * spread(gr)
