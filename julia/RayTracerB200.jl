@@ -16,7 +16,7 @@ module RayTracerB200
 using SparseArrays
 
 export Grid2D, BellmanFordMoore, R, init_annulus, closest_point, interpolate_velocity, bfm, recontruct_path,
-       LinearInterpolation, bfm_batch
+       LinearInterpolation, bfm_batch, interpolate!, symrcm, nodal_degree
 
 const R = 6371.0                                   # src/utils.jl:2
 const LIB = get(ENV, "RT_SSSP_LIB", joinpath(@__DIR__, "..", "raytracer.jl_b200", "librt_sssp.so"))
@@ -157,6 +157,28 @@ function bfm_batch(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
                 h.ptr, Vector{Float64}(U), sources, ns, 64, dist, prev, st))
     return BellmanFordMoore(prev, dist), st[]
+end
+
+# interpolate!(V, gr) -- src/Interpolations/interpolation.jl:5-18 (cell-wise bilinear / barycentric), in place
+function interpolate!(V::Vector{Float64}, gr::Grid2D)
+    et = Int8[gr.element_type[i] == :Quad ? 0 : 1 for i in 1:gr.nel]
+    check(ccall((:rt_interpolate_cells, LIB), Cint, (Ptr{Cvoid}, Ptr{Int8}, Ptr{Float64}), gr.handle.ptr, et, V))
+    return V
+end
+
+# symrcm(nodal_incidence(gr), degrees) -- src/SSSP/rcm.jl:2-46
+function symrcm(gr::Grid2D)
+    prm = zeros(Int64, gr.nnods)
+    check(ccall((:rt_rcm, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), gr.handle.ptr, prm))
+    return prm
+end
+
+# nodal_degree(nodal_incidence(gr)) -- src/topology/topology.jl:70-77
+function nodal_degree(gr::Grid2D)
+    deg = zeros(Int64, gr.nnods)
+    check(ccall((:rt_nodal_adjacency, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64),
+                gr.handle.ptr, deg, C_NULL, C_NULL, 0))
+    return deg
 end
 
 # recontruct_path(prev, source, receiver) -- src/SSSP/ssspm.jl:30-40 (the misspelling is the reference's API)
