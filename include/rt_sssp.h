@@ -140,6 +140,17 @@ int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t ns
 int rt_bfm_solve_dev(rt_mesh* m, const double* U_dev, const int64_t* sources, int64_t nsrc, int precision,
                      double* dist_dev, int32_t* prev_dev, rt_stats* stats);
 
+/* Dual-velocity variant: bfm with U::Matrix -> _relax!(..., U::Matrix) src/SSSP/bfm.jl:113-159.  U2 is the
+ * [n x 2] matrix of dual_velocity (column-major: U[:,1] "below" values, then U[:,2] "above" values); for an edge
+ * between node i and candidate j the pair is U[i, tail] + U[j, head] with head = (r_i > r_j) + 1, tail = 3 - head.
+ * Reference (Jacobi) schedule; outputs as rt_bfm_solve.  Needs a mesh that carries gr.r. */
+int rt_bfm_solve_dual(rt_mesh* m, const double* U2, const int64_t* sources, int64_t nsrc, double* dist_out,
+                      int64_t* prev_out, rt_stats* stats);
+
+/* dual_velocity(r, interpolant; buffer) src/utils.jl:51-66 -> out[n x 2] column-major. */
+int rt_dual_velocity(const double* knots_r, const double* knots_v, int64_t nk, const double* r, int64_t n,
+                     double buffer, double* out);
+
 /* Solver options: key/value, e.g. ("schedule", 0 = Jacobi sweeps exactly as the reference (default),
  * 1 = work-efficient near-far ordering; dist identical, prev may differ on exact ties),
  * ("profile_timers", 1) to fill rt_stats.relax_ms. */

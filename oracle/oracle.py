@@ -52,6 +52,9 @@ def lib():
         L.ora_dijkstra3d.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, F64P]
         L.ora_interpolate_cells.argtypes = [I64, I64P, I64P, I8P, F64P, F64P, F64P]
         L.ora_nodal_adjacency.argtypes = [I64, I64, I64P, I64P, I64P, I64P, C.c_void_p]
+        L.ora_bfm_dual.argtypes = [I64, I64, I64P, I64P, I64P, I64P, I64P, I64, F64P, F64P, F64P, F64P, F64P, I64, C.c_int,
+                                   F64P, I64P, I64P]
+        L.ora_dual_velocity.argtypes = [F64P, F64P, I64, F64P, I64, C.c_double, F64P]
         L.ora_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -187,6 +190,33 @@ def nodal_adjacency(mesh):
     lst = np.zeros(int(off[-1]), np.int64)
     lib().ora_nodal_adjacency(mesh.n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, deg, off, lst.ctypes.data_as(C.c_void_p))
     return deg, off, lst
+
+
+def dual_velocity(knots_r, knots_v, r, buffer=1.0):
+    """dual_velocity(r, interpolant; buffer) src/utils.jl:51-66 -> (n, 2) array like the Julia Matrix."""
+    r = np.ascontiguousarray(r, np.float64)
+    out = np.zeros(2 * len(r))
+    if lib().ora_dual_velocity(np.ascontiguousarray(knots_r, np.float64), np.ascontiguousarray(knots_v, np.float64),
+                               len(knots_r), r, len(r), float(buffer), out):
+        raise ValueError("interpolation point outside the knots")
+    return out.reshape(2, len(r)).T.copy()
+
+
+def bfm_dual(mesh, U2, source, nthreads=1):
+    """bfm(G, halo, source, gr, U::Matrix) -> _relax!(..., U::Matrix) src/SSSP/bfm.jl:113-159."""
+    n = mesh.n
+    U2 = np.asarray(U2, np.float64)
+    u1, u2 = np.ascontiguousarray(U2[:, 0]), np.ascontiguousarray(U2[:, 1])
+    dist = np.zeros(n)
+    prev = np.zeros(n, np.int64)
+    stats = np.zeros(4, np.int64)
+    halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
+    rc = lib().ora_bfm_dual(n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.G_colptr, mesh.G_rowval, halo,
+                            mesh.halo_rows, mesh.x, mesh.z, mesh.r, u1, u2, int(source), int(nthreads), dist, prev, stats)
+    if rc:
+        raise ValueError("bad source")
+    return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
+                            graph_edges=int(stats[3]))
 
 
 def num_threads():

@@ -442,9 +442,10 @@ i64 ora_closest_point(const double* a, const double* b, i64 n, double pa, double
 // ------------------------------------------------------------------------------------ bfm (src/SSSP/bfm.jl)
 // stats[0] = sweeps, stats[1] = candidate evaluations (E_relaxed), stats[2] = active-vertex updates,
 // stats[3] = E_graph (sum over vertices of |scan list|)
-int ora_bfm(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
-            const i64* halo, i64 halo_rows, const double* x, const double* z, const double* U, i64 source,
-            int nthreads, i64 max_sweeps, double* dist, i64* prev, i64* stats) {
+static int bfm_impl(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
+                    const i64* halo, i64 halo_rows, const double* x, const double* z, const double* U, const double* U2,
+                    const double* r, i64 source, int nthreads, i64 max_sweeps, double* dist, i64* prev, i64* stats) {
+  // U2 != null: dual-velocity relax, _relax!(..., U::Matrix) bfm.jl:113-159 (U = U[:,1], U2 = U[:,2])
   Graph2D g{n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U};
   if (source < 1 || source > n) return 1;
 #ifdef _OPENMP
@@ -488,7 +489,20 @@ int ora_bfm(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* c
         for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q) {
           i64 j0 = e2n_idx[q] - 1;
           double dj = dist0[j0];
-          double delta = (dj == INF) ? INF : cand2d(g, dj, i0, j0);
+          double delta;
+          if (dj == INF) {
+            delta = INF;
+          } else if (!U2) {
+            delta = cand2d(g, dj, i0, j0);
+          } else {
+            // head_idx = (ri > r[Gi]) + 1; tail_idx = (head_idx == 1) + 1; muladd(2, len / (Ui[tail] + U[Gi, head]), dGi)
+            const bool down = r[i0] > r[j0];
+            const double ut = down ? U[i0] : U2[i0];
+            const double uh = down ? U2[j0] : U[j0];
+            const double dx = x[i0] - x[j0], dz = z[i0] - z[j0];
+            const double q = std::sqrt(dx * dx + dz * dz) / (ut + uh);
+            delta = 2 * q + dj;  // muladd: the product by 2 is exact, fused or not
+          }
           if (di > delta) {
             di = delta;
             prev[i0] = j0 + 1;
@@ -536,6 +550,45 @@ int ora_bfm(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* c
     stats[1] = evals;
     stats[2] = updates;
     stats[3] = eg;
+  }
+  return 0;
+}
+
+int ora_bfm(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
+            const i64* halo, i64 halo_rows, const double* x, const double* z, const double* U, i64 source,
+            int nthreads, i64 max_sweeps, double* dist, i64* prev, i64* stats) {
+  return bfm_impl(n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U, nullptr, nullptr, source,
+                  nthreads, max_sweeps, dist, prev, stats);
+}
+
+// bfm with U::Matrix (dual velocity): U1 = U[:,1], U2 = U[:,2], r = gr.r
+int ora_bfm_dual(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
+                 const i64* halo, i64 halo_rows, const double* x, const double* z, const double* r, const double* U1,
+                 const double* U2, i64 source, int nthreads, double* dist, i64* prev, i64* stats) {
+  return bfm_impl(n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U1, U2, r, source, nthreads, 0, dist,
+                  prev, stats);
+}
+
+// dual_velocity(r, interpolant; buffer) src/utils.jl:51-66 -> V[n x 2] column-major
+int ora_dual_velocity(const double* kr, const double* kv, i64 nk, const double* r, i64 n, double buffer, double* out) {
+  auto itp = [&](double xq, double& v) {
+    if (!(xq >= kr[0] && xq <= kr[nk - 1])) return 1;
+    i64 idx = (i64)(std::upper_bound(kr, kr + nk, xq) - kr);
+    if (idx < 1) idx = 1;
+    if (idx > nk - 1) idx = nk - 1;
+    double f = (xq - kr[idx - 1]) / (kr[idx] - kr[idx - 1]);
+    v = (1.0 - f) * kv[idx - 1] + f * kv[idx];
+    return 0;
+  };
+  for (i64 i = 0; i < n; ++i) {
+    bool on = false;
+    for (int k = 0; k < 7; ++k) on = on || r[i] == RL[k];
+    if (on) {
+      if (itp(r[i] - buffer, out[i]) || itp(r[i] + buffer, out[n + i])) return 1;
+    } else {
+      if (itp(r[i], out[i])) return 1;
+      out[n + i] = out[i];
+    }
   }
   return 0;
 }

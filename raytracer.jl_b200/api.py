@@ -292,6 +292,16 @@ def reorder(gr, G, halo, prm):
     return gr2, G2, halo2
 
 
+def dual_velocity(r, interpolant, buffer=1):
+    """dual_velocity(r, interpolant; buffer) src/utils.jl:51-66 -> (n, 2) array: column 0 = U[:,1] (value just
+    below a discontinuity), column 1 = U[:,2] (just above); both equal away from the discontinuities."""
+    r = np.ascontiguousarray(r, np.float64)
+    out = np.empty(2 * r.size, np.float64)
+    check(lib().rt_dual_velocity(interpolant.knots, interpolant.values, len(interpolant.knots), r.reshape(-1), r.size,
+                                 float(buffer), out))
+    return out.reshape(2, r.size).T.copy()
+
+
 # ------------------------------------------------------------------------------------------ closest_point
 def closest_point(gr, px, pz, system="cartesian"):
     """closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 -> 1-based node id (scalar or array)."""
@@ -321,6 +331,21 @@ def _solve(handle, n, U, sources, want_prev=True):
     return dist, prev, st.as_dict()
 
 
+def _solve_dual(handle, n, U2, source):
+    U2 = np.asarray(U2, np.float64)
+    if U2.shape != (n, 2):
+        raise ValueError("dual velocity must have shape (%d, 2), got %s" % (n, U2.shape))
+    ucm = np.ascontiguousarray(U2.T).reshape(-1)  # column-major like the Julia Matrix
+    src = np.atleast_1d(np.asarray(source, np.int64)).copy()
+    dist = np.empty((len(src), n), np.float64)
+    prev = np.empty((len(src), n), np.int64)
+    st = RtStats()
+    check(lib().rt_bfm_solve_dual(handle.h, ucm, src, len(src), ptr(dist), ptr(prev), C.byref(st)))
+    if np.ndim(source) == 0:
+        return BellmanFordMoore(prev[0], dist[0], st.as_dict())
+    return BellmanFordMoore(prev, dist, st.as_dict())
+
+
 SCHEDULES = {"jacobi": 0, "near-far": 1}
 
 
@@ -331,6 +356,8 @@ def bfm(G, halo, source, gr, U, schedule=None, delta=None):
     schedule (extension): "jacobi" = the reference's sweeps (dist and prev bit-identical, ties included);
     "near-far" = work-efficient push schedule (dist bit-identical, prev identical except on exact ties)."""
     handle = mesh_from_arrays(gr, G, halo)
+    if np.ndim(U) == 2:  # U::Matrix -> dual-velocity relax (bfm.jl:113-159), reference schedule
+        return _solve_dual(handle, int(G.n), U, source)
     if schedule is not None:
         handle.set_option("schedule", SCHEDULES[schedule])
     if delta is not None:

@@ -5,6 +5,8 @@
 
 #include "common.cuh"
 
+int dual_velocity_device(const double* kr, const double* kv, i64 nk, const double* r_dev, i64 n, double buffer,
+                         double* out_dev);
 int prev_to_host_i64_staged(const i32* prev_dev, i64 count, i64* out, i64* stage64, cudaStream_t s);
 int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* receivers, i64 nrec, i64* path_off,
                              i64* path_idx, i64 cap);
@@ -239,6 +241,52 @@ int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t ns
     total.prev_ms += st.prev_ms;
   }
   if (stats) *stats = total;
+  return RT_OK;
+}
+
+int rt_bfm_solve_dual(rt_mesh* m, const double* U2, const int64_t* sources, int64_t nsrc, double* dist_out,
+                      int64_t* prev_out, rt_stats* stats) {
+  RT_ARG(m && m->kind == 2 && U2 && sources && nsrc >= 0, "rt_bfm_solve_dual needs a 2-D mesh, U[n x 2] and sources");
+  RT_CUDA(cudaSetDevice(m->device));
+  const i64 n = mesh_n(m);
+  cudaStream_t cs = m->stream;
+  DevBuf<double> dU;
+  RT_TRY(dU.upload(U2, 2 * n, cs));
+  if (dist_out && m->stage_dist.n < (size_t)n) RT_TRY(m->stage_dist.alloc(n));
+  if (prev_out && m->stage_prev.n < (size_t)n) {
+    RT_TRY(m->stage_prev.alloc(n));
+    RT_TRY(m->stage_prev64.alloc(n));
+  }
+  rt_stats total = {};
+  for (i64 s = 0; s < nsrc; ++s) {
+    rt_stats st = {};
+    RT_TRY(bfm2d_solve_dual(m, dU.p, sources + s, 1, dist_out ? m->stage_dist.p : nullptr,
+                            prev_out ? m->stage_prev.p : nullptr, &st));
+    if (dist_out)
+      RT_CUDA(cudaMemcpyAsync(dist_out + s * n, m->stage_dist.p, n * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (prev_out) RT_TRY(prev_to_host_i64_staged(m->stage_prev.p, n, prev_out + s * n, m->stage_prev64.p, cs));
+    RT_CUDA(cudaStreamSynchronize(cs));
+    total.sweeps += st.sweeps;
+    total.relaxed_edges += st.relaxed_edges;
+    total.vertex_updates += st.vertex_updates;
+    total.graph_edges = st.graph_edges;
+    total.kernel_ms += st.kernel_ms;
+    total.relax_ms += st.relax_ms;
+    total.relax_launches += st.relax_launches;
+    total.total_launches += st.total_launches;
+  }
+  if (stats) *stats = total;
+  return RT_OK;
+}
+
+int rt_dual_velocity(const double* knots_r, const double* knots_v, int64_t nk, const double* r, int64_t n,
+                     double buffer, double* out) {
+  RT_ARG(knots_r && knots_v && r && out && n >= 0 && nk >= 2 && buffer >= 0.0, "bad dual_velocity arguments");
+  DevBuf<double> dr, dout;
+  RT_TRY(dr.upload(r, n));
+  RT_TRY(dout.alloc(2 * n));
+  RT_TRY(dual_velocity_device(knots_r, knots_v, nk, dr.p, n, buffer, dout.p));
+  if (n) RT_CUDA(cudaMemcpy(out, dout.p, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
   return RT_OK;
 }
 

@@ -26,6 +26,10 @@ struct P2 {
   const double* __restrict__ x;
   const double* __restrict__ z;
   const double* __restrict__ U;
+  // dual-velocity relax (_relax!(..., U::Matrix), bfm.jl:113-159): U1 = U[:,1] (below), U2 = U[:,2] (above), r = gr.r
+  const double* __restrict__ U1;
+  const double* __restrict__ U2;
+  const double* __restrict__ r;
   const i32* __restrict__ e2n_off;
   const i32* __restrict__ e2n_idx;
   const i64* __restrict__ g_off;
@@ -51,7 +55,10 @@ __device__ __forceinline__ double cand_delta(double dj, double xi, double zi, do
   return __dadd_rn(dj, w);
 }
 
-// One warp per active work item.
+// One warp per active work item.  DUAL: the velocity pair of an edge is chosen by the radial order of its ends
+// (head_idx = (r_i > r_j) + 1, tail_idx = (head_idx == 1) + 1, bfm.jl:137-138); muladd(2, len/(Ut+Uh), d) there
+// equals d + (2 len)/(Ut+Uh) bit for bit because the factor 2 is exact with or without FMA.
+template <bool DUAL>
 __global__ void __launch_bounds__(RELAX_BLOCK) relax2d_kernel(P2 p, const i32* __restrict__ active, int cur) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -68,7 +75,9 @@ __global__ void __launch_bounds__(RELAX_BLOCK) relax2d_kernel(P2 p, const i32* _
     const int ti = lane & (tl - 1);
     const int part = lane >> lg;
     const int i = v0 + min(ti, t - 1);
-    const double xi = p.x[i], zi = p.z[i], Ui = p.U[i];
+    const double xi = p.x[i], zi = p.z[i];
+    const double Ui = DUAL ? 0.0 : p.U[i];
+    const double Ui1 = DUAL ? p.U1[i] : 0.0, Ui2 = DUAL ? p.U2[i] : 0.0, ri = DUAL ? p.r[i] : 0.0;
     double best = p.dist0[i];
     int bpos = -1, bid = -1;  // -1 = incumbent dist0[i]; wins every tie (strict `di > delta`)
     int pos_base = 0;
@@ -82,13 +91,21 @@ __global__ void __launch_bounds__(RELAX_BLOCK) relax2d_kernel(P2 p, const i32* _
         const int j = p.e2n_idx[s + k];
         const double dj = p.dist0[j];
         if (!(dj < best)) continue;  // dj + w >= dj >= best (also dj == Inf)
-        const double xj = p.x[j], zj = p.z[j], Uj = p.U[j];
+        const double xj = p.x[j], zj = p.z[j];
+        double Ut = Ui, Uj;  // tail (this node) and head (candidate) velocities
+        if (DUAL) {
+          const bool down = ri > p.r[j];  // head_idx = 2 (above value of the candidate), tail_idx = 1
+          Ut = down ? Ui1 : Ui2;
+          Uj = down ? p.U2[j] : p.U1[j];
+        } else {
+          Uj = p.U[j];
+        }
         {
           const double dx = __dsub_rn(xi, xj), dz = __dsub_rn(zi, zj);
           const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
-          if (screen_cannot_improve(best, dj, d2, __dadd_rn(Ui, Uj))) continue;
+          if (screen_cannot_improve(best, dj, d2, __dadd_rn(Ut, Uj))) continue;
         }
-        const double delta = cand_delta(dj, xi, zi, Ui, xj, zj, Uj);
+        const double delta = cand_delta(dj, xi, zi, Ut, xj, zj, Uj);
         if (delta < best) {
           best = delta;
           bpos = pos_base + k;
@@ -267,9 +284,24 @@ int ensure_workspace(rt_mesh* h) {
 
 int bfm2d_ensure_workspace(rt_mesh* h) { return ensure_workspace(h); }
 
+int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sources, i64 nsrc, double* dist_dev,
+                     i32* prev_dev, rt_stats* stats);
+
 int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                 rt_stats* stats) {
   if (h->opts.schedule == 1) return bfm2d_solve_push(h, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
+  return bfm2d_solve_impl(h, U_dev, false, sources, nsrc, dist_dev, prev_dev, stats);
+}
+
+// U2_dev: [n x 2] column-major (Julia Matrix): U[:,1] then U[:,2].  Reference (Jacobi) schedule only.
+int bfm2d_solve_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                     rt_stats* stats) {
+  RT_ARG(h->m2->has_polar, "the dual-velocity relax needs gr.r (mesh adopted without theta / r)");
+  return bfm2d_solve_impl(h, U2_dev, true, sources, nsrc, dist_dev, prev_dev, stats);
+}
+
+int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sources, i64 nsrc, double* dist_dev,
+                     i32* prev_dev, rt_stats* stats) {
   Mesh2D& m = *h->m2;
   cudaStream_t s = h->stream;
   RT_TRY(ensure_workspace(h));
@@ -278,6 +310,9 @@ int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
   p.x = m.x.p;
   p.z = m.z.p;
   p.U = U_dev;
+  p.U1 = U_dev;
+  p.U2 = dual ? U_dev + m.n : U_dev;
+  p.r = m.r.p;
   p.e2n_off = m.e2n_off.p;
   p.e2n_idx = m.e2n_idx.p;
   p.g_off = m.g_off.p;
@@ -332,7 +367,10 @@ int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
       const int nxt = cur ^ 1;
       const i64 rb = std::min<i64>((n_active + wpb - 1) / wpb, max_relax_blocks);
       if (h->opts.profile_timers) cudaEventRecord(evr0, s);
-      relax2d_kernel<<<(unsigned)rb, RELAX_BLOCK, 0, s>>>(p, m.act[cur].p, cur);
+      if (dual)
+        relax2d_kernel<true><<<(unsigned)rb, RELAX_BLOCK, 0, s>>>(p, m.act[cur].p, cur);
+      else
+        relax2d_kernel<false><<<(unsigned)rb, RELAX_BLOCK, 0, s>>>(p, m.act[cur].p, cur);
       if (h->opts.profile_timers) cudaEventRecord(evr1, s);
       if (m.halo_rows > 0) {
         if (m.halo_structured) {

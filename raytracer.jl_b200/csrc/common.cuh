@@ -151,6 +151,8 @@ int mesh2d_export(const rt_mesh* h, double* x, double* z, double* theta, double*
 void mesh2d_free(rt_mesh* h);
 int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                 rt_stats* stats);
+int bfm2d_solve_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                     rt_stats* stats);
 int mesh2d_closest(const rt_mesh* h, const double* pa, const double* pb, i64 npts, int system, i64* out);
 int annulus_build_device(rt_mesh* h, i64 ntheta, i64 nr, double spacing);
 int mesh2d_interpolate_cells(rt_mesh* h, const int8_t* el_type_host, double* V_dev);

@@ -49,6 +49,48 @@ __global__ void interp_kernel(const double* __restrict__ kr, const double* __res
   out[i] = __dadd_rn(__dmul_rn(__dsub_rn(1.0, f), kv[idx - 1]), __dmul_rn(f, kv[idx]));
 }
 
+// dual_velocity(r, interpolant; buffer) src/utils.jl:51-66: on a discontinuity radius V[i,1] = itp(r - buffer),
+// V[i,2] = itp(r + buffer), elsewhere both = itp(r).  out: [n x 2] column-major.
+__device__ __forceinline__ double lerp_knots(const double* __restrict__ kr, const double* __restrict__ kv, i64 nk,
+                                             double xq, int* bad) {
+  if (!(xq >= kr[0] && xq <= kr[nk - 1])) {
+    *bad = 1;
+    return __longlong_as_double(0x7ff8000000000000LL);
+  }
+  i64 lo = 0, hi = nk;
+  while (lo < hi) {
+    const i64 mid = (lo + hi) >> 1;
+    if (kr[mid] <= xq)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  i64 idx = lo;
+  if (idx < 1) idx = 1;
+  if (idx > nk - 1) idx = nk - 1;
+  const double k0 = kr[idx - 1], k1 = kr[idx];
+  const double f = __ddiv_rn(__dsub_rn(xq, k0), __dsub_rn(k1, k0));
+  return __dadd_rn(__dmul_rn(__dsub_rn(1.0, f), kv[idx - 1]), __dmul_rn(f, kv[idx]));
+}
+__global__ void dual_velocity_kernel(const double* __restrict__ kr, const double* __restrict__ kv, i64 nk,
+                                     const double* __restrict__ r, i64 n, double buffer, double* __restrict__ out,
+                                     int* __restrict__ bad) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ri = r[i];
+  bool on_layer = false;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) on_layer = on_layer || (ri == RL_DEV[k]);
+  if (on_layer) {
+    out[i] = lerp_knots(kr, kv, nk, __dsub_rn(ri, buffer), bad);
+    out[n + i] = lerp_knots(kr, kv, nk, __dadd_rn(ri, buffer), bad);
+  } else {
+    const double v = lerp_knots(kr, kv, nk, ri, bad);
+    out[i] = v;
+    out[n + i] = v;
+  }
+}
+
 // closest_point (src/GridAnnulus.jl:823-840): argmin_i sqrt((a_i-pa)^2 + (b_i-pb)^2), FIRST index on ties.
 // Pass 1: 64-bit atomicMin on the bit pattern of the (non-negative) distance; pass 2: atomicMin on the index
 // among the nodes that attain it.  One grid row (blockIdx.y) per query point.
@@ -155,6 +197,26 @@ int interp_velocity_device(const double* kr_h, const double* kv_h, i64 nk, const
   RT_TRY(bad.alloc(1));
   RT_TRY(bad.zero());
   if (n) interp_kernel<<<grid_for(n, 256), 256>>>(kr.p, kv.p, nk, r_dev, n, buffer, out_dev, bad.p);
+  RT_CUDA(cudaGetLastError());
+  int hb = 0;
+  RT_CUDA(cudaMemcpy(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (hb) {
+    rt_set_error("interpolation point outside the knots (BoundsError in the reference)");
+    return RT_ERR_RANGE;
+  }
+  return RT_OK;
+}
+
+int dual_velocity_device(const double* kr_h, const double* kv_h, i64 nk, const double* r_dev, i64 n, double buffer,
+                         double* out_dev) {
+  for (i64 k = 0; k + 1 < nk; ++k) RT_ARG(kr_h[k] < kr_h[k + 1], "knots must be strictly ascending");
+  DevBuf<double> kr, kv;
+  DevBuf<int> bad;
+  RT_TRY(kr.upload(kr_h, nk));
+  RT_TRY(kv.upload(kv_h, nk));
+  RT_TRY(bad.alloc(1));
+  RT_TRY(bad.zero());
+  if (n) dual_velocity_kernel<<<grid_for(n, 256), 256>>>(kr.p, kv.p, nk, r_dev, n, buffer, out_dev, bad.p);
   RT_CUDA(cudaGetLastError());
   int hb = 0;
   RT_CUDA(cudaMemcpy(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost));

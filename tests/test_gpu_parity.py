@@ -530,3 +530,24 @@ def test_topology_containers_and_rcm(rt, O, annulus, ak135):
     # bandwidth of the element lists (max id spread inside a cell) does not explode under RCM
     spread = lambda g: max(int(g.e2n[e].max() - g.e2n[e].min()) for e in range(1, m.nel + 1, 7))
     assert spread(gr2) <= 2 * spread(gr)
+
+
+def test_dual_velocity_relax_bit_exact(rt, O, annulus, ak135):
+    """SURVEY 8(f)-1: bfm with U::Matrix (dual_velocity, discontinuity-aware relax) in the reference schedule."""
+    for nt, nr, sp in ((24, 6, 300.0), (36, 10, 100.0), (90, 20, 20.0)):
+        m = annulus(nt, nr, sp)
+        gr, G, halo = adopt(rt, m)
+        itp = rt.LinearInterpolation(*ak135)
+        V2 = rt.dual_velocity(gr.r, itp, buffer=1)
+        assert np.array_equal(V2, O.dual_velocity(ak135[0], ak135[1], m.r, 1.0))
+        src = O.closest_point(m.theta, m.r, 0.0, R)
+        D = rt.bfm(G, halo, src, gr, V2)
+        dist, prev, st = O.bfm_dual(m, V2, src)
+        assert np.array_equal(D.dist, dist) and np.array_equal(D.prev, prev) and D.stats["sweeps"] == st["sweeps"]
+    V2r = np.stack([4.0 + 6.0 * splitmix64(5, m.n), 4.0 + 6.0 * splitmix64(6, m.n)], 1)  # arbitrary pairs
+    D = rt.bfm(G, halo, [1, m.n // 3], gr, V2r)
+    for k, s in enumerate((1, m.n // 3)):
+        dist, prev, st = O.bfm_dual(m, V2r, s)
+        assert np.array_equal(D.dist[k], dist) and np.array_equal(D.prev[k], prev)
+    with pytest.raises(ValueError):
+        rt.bfm(G, halo, 1, gr, V2r[:-1])
