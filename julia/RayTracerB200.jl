@@ -16,7 +16,7 @@ module RayTracerB200
 using SparseArrays
 
 export Grid2D, BellmanFordMoore, R, init_annulus, closest_point, interpolate_velocity, bfm, recontruct_path,
-       LinearInterpolation, bfm_batch, interpolate!, symrcm, nodal_degree
+       LinearInterpolation, bfm_batch, interpolate!, symrcm, nodal_degree, dual_velocity
 
 const R = 6371.0                                   # src/utils.jl:2
 const LIB = get(ENV, "RT_SSSP_LIB", joinpath(@__DIR__, "..", "raytracer.jl_b200", "librt_sssp.so"))
@@ -157,6 +157,29 @@ function bfm_batch(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
                 h.ptr, Vector{Float64}(U), sources, ns, 64, dist, prev, st))
     return BellmanFordMoore(prev, dist), st[]
+end
+
+# dual_velocity(r, interpolant; buffer) -- src/utils.jl:51-66
+function dual_velocity(r::AbstractArray, itp::LinearInterpolation; buffer = 1)
+    V = Matrix{Float64}(undef, length(r), 2)
+    check(ccall((:rt_dual_velocity, LIB), Cint,
+                (Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Cdouble, Ptr{Float64}),
+                itp.knots, itp.values, length(itp.knots), Vector{Float64}(vec(r)), length(r), Float64(buffer), V))
+    return V
+end
+
+# bfm with U::Matrix -- the dual-velocity relax _relax!(..., U::Matrix) src/SSSP/bfm.jl:113-159
+function bfm(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, source::Integer, gr, U::Matrix{Float64})
+    h = mesh_handle(G, halo, gr)
+    n = G.n
+    dist = Vector{Float64}(undef, n)
+    prev = Vector{Int64}(undef, n)
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0))
+    check(ccall((:rt_bfm_solve_dual, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
+                h.ptr, U, Int64[source], 1, dist, prev, st))
+    println("Converged in $(st[].sweeps + 1) iterations")
+    return BellmanFordMoore(prev, dist)
 end
 
 # interpolate!(V, gr) -- src/Interpolations/interpolation.jl:5-18 (cell-wise bilinear / barycentric), in place
