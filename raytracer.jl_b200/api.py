@@ -397,6 +397,20 @@ def recontruct_path(prev, source, receiver):
     return paths[0] if np.ndim(receiver) == 0 else paths
 
 
+def travel_times(D, gr, receivers, isave=False, flname=""):
+    """travel_times(D, gr, receivers; isave, flname) src/utils.jl:4-15: D.dist at the receiver nodes; with isave the
+    (degree, travel_time) table is written as CSV like the reference's DataFrame (degree = rad2deg(gr.theta))."""
+    rec = np.atleast_1d(np.asarray(receivers, np.int64))
+    tt = np.asarray(D.dist, np.float64)[rec - 1].copy()
+    if isave:
+        deg = np.rad2deg(np.asarray(gr.theta, np.float64)[rec - 1])
+        with open(os.path.join(os.getcwd(), flname), "w") as f:
+            f.write("degree,travel_time\n")
+            for a, b in zip(deg, tt):
+                f.write("%r,%r\n" % (float(a), float(b)))
+    return tt
+
+
 def device_count():
     c = C.c_int(0)
     check(lib().rt_device_count(C.byref(c)))
