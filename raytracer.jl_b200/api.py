@@ -356,12 +356,12 @@ def bfm(G, halo, source, gr, U, schedule=None, delta=None):
     schedule (extension): "jacobi" = the reference's sweeps (dist and prev bit-identical, ties included);
     "near-far" = work-efficient push schedule (dist bit-identical, prev identical except on exact ties)."""
     handle = mesh_from_arrays(gr, G, halo)
-    if np.ndim(U) == 2:  # U::Matrix -> dual-velocity relax (bfm.jl:113-159), reference schedule
-        return _solve_dual(handle, int(G.n), U, source)
     if schedule is not None:
         handle.set_option("schedule", SCHEDULES[schedule])
     if delta is not None:
         handle.set_option("delta", delta)
+    if np.ndim(U) == 2:  # U::Matrix -> dual-velocity relax (bfm.jl:113-159)
+        return _solve_dual(handle, int(G.n), U, source)
     dist, prev, st = _solve(handle, int(G.n), U, source)
     if np.ndim(source) == 0:
         return BellmanFordMoore(prev[0], dist[0], st)

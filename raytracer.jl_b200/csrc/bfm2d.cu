@@ -293,10 +293,11 @@ int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
   return bfm2d_solve_impl(h, U_dev, false, sources, nsrc, dist_dev, prev_dev, stats);
 }
 
-// U2_dev: [n x 2] column-major (Julia Matrix): U[:,1] then U[:,2].  Reference (Jacobi) schedule only.
+// U2_dev: [n x 2] column-major (Julia Matrix): U[:,1] then U[:,2].
 int bfm2d_solve_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                      rt_stats* stats) {
   RT_ARG(h->m2->has_polar, "the dual-velocity relax needs gr.r (mesh adopted without theta / r)");
+  if (h->opts.schedule == 1) return bfm2d_solve_push_dual(h, U2_dev, sources, nsrc, dist_dev, prev_dev, stats);
   return bfm2d_solve_impl(h, U2_dev, true, sources, nsrc, dist_dev, prev_dev, stats);
 }
 

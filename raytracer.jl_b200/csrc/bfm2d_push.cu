@@ -34,6 +34,9 @@ struct PP {
   const double* __restrict__ x;
   const double* __restrict__ z;
   const double* __restrict__ U;
+  const double* __restrict__ U1;  // dual-velocity relax (bfm.jl:113-159): U[:,1] / U[:,2] and gr.r
+  const double* __restrict__ U2;
+  const double* __restrict__ r;
   const i32* __restrict__ e2n_off;
   const i32* __restrict__ e2n_idx;
   const i64* __restrict__ g_off;
@@ -363,9 +366,9 @@ __device__ __forceinline__ void push2d_body_t(const PP& p, const i32* near_cur, 
 // one warp owns one released item, no block barrier.  The element offsets of the column are fetched by the lanes
 // in parallel and prefix-summed, so the targets of ALL its elements form one flat index space that the lanes walk
 // with full utilisation (an element holds ~10 nodes there); sources sit in a warp-private shared-memory slab.
-template <bool PACKED>
+template <bool PACKED, bool DUAL>
 __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned mask, int cur, i32* near_next,
-                                                 i32* far_list, int fcur, double tau, double2* sxz, double2* sUd,
+                                                 i32* far_list, int fcur, double tau, double2* sxz, double2* sUd, double2* sU2r,
                                                  int* s_id, int* s_pre, int* s_start) {
   const int lane = threadIdx.x & 31;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -378,7 +381,8 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
     const int i = v0 + lane;
     dmy = __ldcg(&p.dist[(i64)i * p.ds]);
     sxz[pos] = make_double2(p.x[i], p.z[i]);
-    sUd[pos] = make_double2(p.U[i], dmy);
+    sUd[pos] = make_double2(DUAL ? p.U1[i] : p.U[i], dmy);
+    if (DUAL) sU2r[pos] = make_double2(p.U2[i], p.r[i]);
     s_id[pos] = i;
   }
   double dmin = dmy;
@@ -439,7 +443,9 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
       if (!(dmin < dj)) continue;
       u64 kj = KEY_NONE;
       if (PACKED) kj = __ldcg(p.keys + 2 * (i64)j + 1);
-      const double xj = p.x[j], zj = p.z[j], Uj = p.U[j];
+      const double xj = p.x[j], zj = p.z[j];
+      const double Uj = DUAL ? p.U1[j] : p.U[j];
+      const double U2j = DUAL ? p.U2[j] : 0.0, rj = DUAL ? p.r[j] : 0.0;
       double best = dj;
       u64 bkey = kj;
       bool changed = false;
@@ -448,12 +454,19 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
         const double di = ud.y;
         if (!(di < best)) continue;
         const double2 xz = sxz[q];
+        double us = ud.x, ut = Uj;  // velocities of the source (head) and of the target (tail)
+        if (DUAL) {
+          const double2 u2r = sU2r[q];
+          const bool down = rj > u2r.y;  // head_idx = (r_i > r_Gi) + 1 with i = target, Gi = source
+          ut = down ? Uj : U2j;
+          us = down ? u2r.x : ud.x;
+        }
         {
           const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
           const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
-          if (screen_cannot_improve(best, di, d2, __dadd_rn(ud.x, Uj))) continue;
+          if (screen_cannot_improve(best, di, d2, __dadd_rn(ut, us))) continue;
         }
-        const double delta = edge_delta(di, xz.x, xz.y, ud.x, xj, zj, Uj);
+        const double delta = edge_delta(di, xz.x, xz.y, us, xj, zj, ut);
         if (PACKED) {
           const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
           if (delta < best) {
@@ -488,9 +501,10 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
 }
 
 // warp-level units of ONE source: slots of its near list
+template <bool DUAL>
 __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                                  i32* far_list, int fcur, i64 first_warp, i64 n_warps) {
-  __shared__ double2 w_sxz[PUSH_BLOCK / 32][32], w_sUd[PUSH_BLOCK / 32][32];
+  __shared__ double2 w_sxz[PUSH_BLOCK / 32][32], w_sUd[PUSH_BLOCK / 32][32], w_sU2r[DUAL ? PUSH_BLOCK / 32 : 1][32];
   __shared__ int w_id[PUSH_BLOCK / 32][32], w_pre[PUSH_BLOCK / 32][32], w_start[PUSH_BLOCK / 32][32];
   const int warp = threadIdx.x >> 5;
   const i64 n_near = (i64)__ldcg(&p.counters[cur]);
@@ -500,11 +514,11 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
     if (mask == 0u) continue;
     if (p.ds == 2)
-      push2d_warp_unit<true>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp], w_id[warp],
-                             w_pre[warp], w_start[warp]);
+      push2d_warp_unit<true, DUAL>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
+                                   w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
     else
-      push2d_warp_unit<false>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp], w_id[warp],
-                              w_pre[warp], w_start[warp]);
+      push2d_warp_unit<false, DUAL>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
+                                    w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
   }
 }
 
@@ -513,9 +527,9 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
 // of the released sources (warp-private smem slab) and walks the elements e, e + PUSH_GE, ... of the column with the
 // software-pipelined target loop.  (The CTA-level variant above spends a third of its stall time in __syncthreads.)
 constexpr int PUSH_GE = 16;
-template <bool PACKED>
+template <bool PACKED, bool DUAL>
 __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned mask, int e0, int cur, i32* near_next,
-                                                 i32* far_list, int fcur, double tau, double2* sxz, double2* sUd,
+                                                 i32* far_list, int fcur, double tau, double2* sxz, double2* sUd, double2* sU2r,
                                                  int* s_id) {
   const int lane = threadIdx.x & 31;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -530,7 +544,8 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     const int i = v0 + lane;
     dmy = __ldcg(&p.dist[(i64)i * p.ds]);
     sxz[pos] = make_double2(p.x[i], p.z[i]);
-    sUd[pos] = make_double2(p.U[i], dmy);
+    sUd[pos] = make_double2(DUAL ? p.U1[i] : p.U[i], dmy);
+    if (DUAL) sU2r[pos] = make_double2(p.U2[i], p.r[i]);
     s_id[pos] = i;
   }
   double dmin = dmy;
@@ -560,25 +575,33 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     const int m = p.e2n_off[el + 1] - s;
     int k = lane;
     int j = k < m ? p.e2n_idx[s + k] : -1;
-    double dj = 0.0, xj = 0.0, zj = 0.0, Uj = 0.0;
+    double dj = 0.0, xj = 0.0, zj = 0.0, Uj = 0.0, U2j = 0.0, rj = 0.0;
     u64 kj = KEY_NONE, kjn = KEY_NONE;
     if (j >= 0) {
       if (PACKED) kj = __ldcg(p.keys + 2 * (i64)j + 1);
       dj = __ldcg(&p.dist[(i64)j * p.ds]);
       xj = p.x[j];
       zj = p.z[j];
-      Uj = p.U[j];
+      Uj = DUAL ? p.U1[j] : p.U[j];
+      if (DUAL) {
+        U2j = p.U2[j];
+        rj = p.r[j];
+      }
     }
     while (k < m) {
       const int kn = k + 32;
       const int jn = kn < m ? p.e2n_idx[s + kn] : -1;
-      double djn = 0.0, xjn = 0.0, zjn = 0.0, Ujn = 0.0;
+      double djn = 0.0, xjn = 0.0, zjn = 0.0, Ujn = 0.0, U2jn = 0.0, rjn = 0.0;
       if (jn >= 0) {
         if (PACKED) kjn = __ldcg(p.keys + 2 * (i64)jn + 1);
         djn = __ldcg(&p.dist[(i64)jn * p.ds]);
         xjn = p.x[jn];
         zjn = p.z[jn];
-        Ujn = p.U[jn];
+        Ujn = DUAL ? p.U1[jn] : p.U[jn];
+        if (DUAL) {
+          U2jn = p.U2[jn];
+          rjn = p.r[jn];
+        }
       }
       if (dmin < dj) {
         double best = dj;
@@ -589,12 +612,19 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
           const double di = ud.y;
           if (!(di < best)) continue;
           const double2 xz = sxz[q];
+          double us = ud.x, ut = Uj;  // velocities of the source (head) and of the target (tail)
+          if (DUAL) {
+            const double2 u2r = sU2r[q];
+            const bool down = rj > u2r.y;  // head_idx = (r_i > r_Gi) + 1 with i = target, Gi = source
+            ut = down ? Uj : U2j;
+            us = down ? u2r.x : ud.x;
+          }
           {
             const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
             const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
-            if (screen_cannot_improve(best, di, d2, __dadd_rn(ud.x, Uj))) continue;
+            if (screen_cannot_improve(best, di, d2, __dadd_rn(ut, us))) continue;
           }
-          const double delta = edge_delta(di, xz.x, xz.y, ud.x, xj, zj, Uj);
+          const double delta = edge_delta(di, xz.x, xz.y, us, xj, zj, ut);
           if (PACKED) {
             const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
             if (delta < best) {
@@ -627,6 +657,8 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
       xj = xjn;
       zj = zjn;
       Uj = Ujn;
+      U2j = U2jn;
+      rj = rjn;
     }
     evals += (u64)m * (u64)ns;
   }
@@ -635,9 +667,10 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     if (e0 == 0) atomicAdd(&p.counters[3], (u64)ns);
   }
 }
+template <bool DUAL>
 __device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                                  i32* far_list, int fcur, i64 first_warp, i64 n_warps) {
-  __shared__ double2 e_sxz[PUSH_BLOCK / 32][32], e_sUd[PUSH_BLOCK / 32][32];
+  __shared__ double2 e_sxz[PUSH_BLOCK / 32][32], e_sUd[PUSH_BLOCK / 32][32], e_sU2r[DUAL ? PUSH_BLOCK / 32 : 1][32];
   __shared__ int e_id[PUSH_BLOCK / 32][32];
   const int warp = threadIdx.x >> 5;
   const i64 n_near = (i64)__ldcg(&p.counters[cur]);
@@ -649,19 +682,21 @@ __device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cu
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
     if (mask == 0u) continue;
     if (p.ds == 2)
-      push2d_elem_unit<true>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp], e_id[warp]);
+      push2d_elem_unit<true, DUAL>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
+                                   e_sU2r[DUAL ? warp : 0], e_id[warp]);
     else
-      push2d_elem_unit<false>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp], e_id[warp]);
+      push2d_elem_unit<false, DUAL>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
+                                    e_sU2r[DUAL ? warp : 0], e_id[warp]);
   }
 }
 
-template <bool WARP>
+template <bool WARP, bool DUAL>
 __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
   if (WARP) {
     const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
-    push2d_warp_body(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
+    push2d_warp_body<DUAL>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
   } else if (p.cta_units) {
     if (p.ds == 2)
       push2d_body_t<true>(p, near_cur, cur, near_next, far_list, fcur);
@@ -670,14 +705,14 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
   } else {
     const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
-    push2d_elem_body(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
+    push2d_elem_body<DUAL>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
   }
 }
-template <bool WARP>
+template <bool WARP, bool DUAL>
 __global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
                                                            i32* __restrict__ near_next, i32* __restrict__ far_list,
                                                            int fcur) {
-  push2d_body<WARP>(p, near_cur, cur, near_next, far_list, fcur);
+  push2d_body<WARP, DUAL>(p, near_cur, cur, near_next, far_list, fcur);
 }
 
 // threshold advance, step 1: smallest waiting value
@@ -921,12 +956,12 @@ __global__ void prep_dc_kernel(PP pb) {
   for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (i64)gridDim.x * blockDim.x)
     p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
 }
-template <bool WARP>
+template <bool WARP, bool DUAL>
 __global__ void __launch_bounds__(PUSH_BLOCK) push2d_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];
-  push2d_body<WARP>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
+  push2d_body<WARP, DUAL>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
 }
 __global__ void far_min_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
@@ -987,7 +1022,7 @@ __global__ void far_release_dc_kernel(PP pb) {
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant: ONE cooperative launch runs up to `max_rounds` rounds; phases are separated by grid-wide
 // barriers instead of kernel boundaries (a round costs two or three grid.sync() instead of ~5 launches).
-template <bool WARP>
+template <bool WARP, bool DUAL>
 __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, int max_rounds) {
   cg::grid_group grid = cg::this_grid();
   const bool first = blockIdx.x == 0 && threadIdx.x == 0;
@@ -1044,10 +1079,10 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, i
           // every source gets its own team of warps (warp w serves source w % nb) so that the sources advance
           // concurrently instead of one after the other
           const i64 gw = gtid >> 5, nw = gsize >> 5;
-          if ((int)(gw % nb) == b) push2d_warp_body(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, gw / nb,
+          if ((int)(gw % nb) == b) push2d_warp_body<DUAL>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, gw / nb,
                                                     (nw - b + nb - 1) / nb);
         } else {
-          push2d_body<WARP>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
+          push2d_body<WARP, DUAL>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
         }
       } else if ((mode2 >> b) & 1u) {
         const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
@@ -1196,9 +1231,27 @@ int ensure_push_workspace(rt_mesh* h, int nb, bool packed) {
 
 int bfm2d_ensure_workspace(rt_mesh* h);
 
+int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sources, i64 nsrc, double* dist_dev,
+                          i32* prev_dev, rt_stats* stats);
+
 int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                      rt_stats* stats) {
+  return bfm2d_solve_push_impl(h, U_dev, false, sources, nsrc, dist_dev, prev_dev, stats);
+}
+// U2_dev: [n x 2] column-major (dual_velocity)
+int bfm2d_solve_push_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 nsrc, double* dist_dev,
+                          i32* prev_dev, rt_stats* stats) {
+  return bfm2d_solve_push_impl(h, U2_dev, true, sources, nsrc, dist_dev, prev_dev, stats);
+}
+
+int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sources, i64 nsrc, double* dist_dev,
+                          i32* prev_dev, rt_stats* stats) {
   Mesh2D& m = *h->m2;
+  if (dual) {
+    RT_ARG(m.has_polar, "the dual-velocity relax needs gr.r (mesh adopted without theta / r)");
+    RT_ARG(h->opts.packed_prev != 0 && h->opts.cta_units == 0 && h->opts.profile_timers == 0,
+           "dual velocity in the near-far schedule needs packed_prev=1, cta_units=0, profile_timers=0");
+  }
   cudaStream_t s = h->stream;
   const i64 n = m.n;
   const bool timers = h->opts.profile_timers != 0;
@@ -1218,6 +1271,9 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.x = m.x.p;
   p.z = m.z.p;
   p.U = U_dev;
+  p.U1 = U_dev;
+  p.U2 = dual ? U_dev + m.n : U_dev;
+  p.r = m.r.p;
   p.e2n_off = m.e2n_off.p;
   p.e2n_idx = m.e2n_idx.p;
   p.g_off = m.g_off.p;
@@ -1259,9 +1315,11 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   {
     int coop = 0, per_sm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
-    const cudaError_t oe =
-        p.warp_units ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nearfar_persistent_kernel<true>, PUSH_BLOCK, 0)
-                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nearfar_persistent_kernel<false>, PUSH_BLOCK, 0);
+    const void* pk = p.warp_units ? (dual ? (const void*)nearfar_persistent_kernel<true, true>
+                                          : (const void*)nearfar_persistent_kernel<true, false>)
+                                  : (dual ? (const void*)nearfar_persistent_kernel<false, true>
+                                          : (const void*)nearfar_persistent_kernel<false, false>);
+    const cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, PUSH_BLOCK, 0);
     if (coop && oe == cudaSuccess) coop_blocks = (i64)per_sm * sm_count;
   }
   cudaEvent_t ev0, ev1, evr0, evr1;
@@ -1320,8 +1378,10 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       int max_rounds = 8192;
       while (!all_done) {
         void* args[] = {(void*)&p, (void*)&max_rounds};
-        const void* kfn = p.warp_units ? (const void*)nearfar_persistent_kernel<true>
-                                       : (const void*)nearfar_persistent_kernel<false>;
+        const void* kfn = p.warp_units ? (dual ? (const void*)nearfar_persistent_kernel<true, true>
+                                               : (const void*)nearfar_persistent_kernel<true, false>)
+                                       : (dual ? (const void*)nearfar_persistent_kernel<false, true>
+                                               : (const void*)nearfar_persistent_kernel<false, false>);
         cudaError_t le = cudaLaunchCooperativeKernel(kfn, dim3((unsigned)coop_blocks), dim3(PUSH_BLOCK), args, 0, s);
         if (le != cudaSuccess) {
           rc = RT_ERR_CUDA;
@@ -1346,10 +1406,14 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
         for (int r = 0; r < R; ++r) {
           round_begin_kernel<<<1, 32, 0, s>>>(p);
           prep_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
-          if (p.warp_units)
-            push2d_dc_kernel<true><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
+          if (p.warp_units && dual)
+            push2d_dc_kernel<true, true><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
+          else if (p.warp_units)
+            push2d_dc_kernel<true, false><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
+          else if (dual)
+            push2d_dc_kernel<false, true><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
           else
-            push2d_dc_kernel<false><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
+            push2d_dc_kernel<false, false><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
           far_min_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
           far_release_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
         }
@@ -1374,10 +1438,10 @@ int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
           prep_kernel<<<grid_for(n_near, 256), 256, 0, s>>>(p, m.nearq[cur].p, cur);
           cudaEventRecord(evr0, s);
           if (p.warp_units)
-            push2d_kernel<true><<<(unsigned)std::min<i64>((n_near + 3) / 4, max_blocks), PUSH_BLOCK, 0, s>>>(
+            push2d_kernel<true, false><<<(unsigned)std::min<i64>((n_near + 3) / 4, max_blocks), PUSH_BLOCK, 0, s>>>(
                 p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           else
-            push2d_kernel<false><<<(unsigned)std::min<i64>(n_near * (p.cta_units ? PUSH_GY : PUSH_GE / 4), max_blocks), PUSH_BLOCK, 0, s>>>(
+            push2d_kernel<false, false><<<(unsigned)std::min<i64>(n_near * (p.cta_units ? PUSH_GY : PUSH_GE / 4), max_blocks), PUSH_BLOCK, 0, s>>>(
                 p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           cudaEventRecord(evr1, s);
           pushed = true;

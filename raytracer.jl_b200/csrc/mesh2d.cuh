@@ -66,5 +66,7 @@ struct Mesh2D {
 // Finishes a Mesh2D whose primary arrays (x,z,e2n_*,g_*) are already on the device: builds n2e, work items,
 // halo tables, E_graph.  halo_host: (2H x 2) column-major 1-based (may be null if halo_rows == 0).
 int mesh2d_finalize(rt_mesh* h, const i64* halo_host);
+int bfm2d_solve_push_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 nsrc, double* dist_dev,
+                          i32* prev_dev, rt_stats* stats);
 int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                      rt_stats* stats);

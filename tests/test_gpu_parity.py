@@ -551,3 +551,20 @@ def test_dual_velocity_relax_bit_exact(rt, O, annulus, ak135):
         assert np.array_equal(D.dist[k], dist) and np.array_equal(D.prev[k], prev)
     with pytest.raises(ValueError):
         rt.bfm(G, halo, 1, gr, V2r[:-1])
+    # near-far schedule with the dual relax: same travel times bit for bit, tight predecessors
+    def wdual(i, j):  # weight seen by target i pulling from j (bfm.jl:137-145)
+        down = m.r[i] > m.r[j]
+        us = np.where(down, V2r[i, 0], V2r[i, 1]) + np.where(down, V2r[j, 1], V2r[j, 0])
+        dx, dz = m.x[i] - m.x[j], m.z[i] - m.z[j]
+        return 2.0 * np.sqrt(dx * dx + dz * dz) / us
+    for s in (1, m.n // 3):
+        dist, prev, st = O.bfm_dual(m, V2r, s)
+        Dn = rt.bfm(G, halo, s, gr, V2r, schedule="near-far")
+        assert np.array_equal(Dn.dist, dist)
+        p = Dn.prev
+        i = np.nonzero((p > 0) & np.isfinite(dist))[0]
+        tight = dist[p[i] - 1] + wdual(i, p[i] - 1) == dist[i]
+        halo_nodes = np.zeros(m.n, bool)
+        halo_nodes[halo.ravel() - 1] = True
+        assert np.all(tight | halo_nodes[i]) and len(i) == np.isfinite(dist).sum() - 1
+    rt.bfm(G, halo, 1, gr, V2r, schedule="jacobi")
