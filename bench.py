@@ -32,6 +32,8 @@ R = 6371.0
 WORKLOADS = {
     # BASELINE.json configs[3]: 3-D spherical-shell grid ~10M nodes, star1, single source, AK135
     "grid3d_216": dict(kind="3d", nn=(216, 216, 216), cpu_nn=(128, 128, 128), dim=3),
+    # BASELINE.json configs[4]: 3-D grid ~50M nodes (368^3), multi-source batch
+    "grid3d_368": dict(kind="3d", nn=(368, 368, 368), cpu_nn=(128, 128, 128), dim=3),
     "grid3d_128": dict(kind="3d", nn=(128, 128, 128), cpu_nn=(96, 96, 96), dim=3),
     "grid3d_64": dict(kind="3d", nn=(64, 64, 64), cpu_nn=(64, 64, 64), dim=3),
     # BASELINE.json configs[0]: README example, annulus 180x50, spacing 1 km

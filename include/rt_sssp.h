@@ -143,7 +143,8 @@ int rt_bfm_solve_dev(rt_mesh* m, const double* U_dev, const int64_t* sources, in
 /* Dual-velocity variant: bfm with U::Matrix -> _relax!(..., U::Matrix) src/SSSP/bfm.jl:113-159.  U2 is the
  * [n x 2] matrix of dual_velocity (column-major: U[:,1] "below" values, then U[:,2] "above" values); for an edge
  * between node i and candidate j the pair is U[i, tail] + U[j, head] with head = (r_i > r_j) + 1, tail = 3 - head.
- * Reference (Jacobi) schedule; outputs as rt_bfm_solve.  Needs a mesh that carries gr.r. */
+ * Runs in the schedule selected by rt_set_option("schedule") like rt_bfm_solve (travel times bit-identical in
+ * both; near-far needs packed_prev = 1, the default); outputs as rt_bfm_solve.  Needs a mesh that carries gr.r. */
 int rt_bfm_solve_dual(rt_mesh* m, const double* U2, const int64_t* sources, int64_t nsrc, double* dist_out,
                       int64_t* prev_out, rt_stats* stats);
 

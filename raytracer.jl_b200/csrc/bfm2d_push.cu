@@ -709,7 +709,7 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
   }
 }
 template <bool WARP, bool DUAL>
-__global__ void __launch_bounds__(PUSH_BLOCK) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
+__global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
                                                            i32* __restrict__ near_next, i32* __restrict__ far_list,
                                                            int fcur) {
   push2d_body<WARP, DUAL>(p, near_cur, cur, near_next, far_list, fcur);
@@ -957,7 +957,7 @@ __global__ void prep_dc_kernel(PP pb) {
     p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
 }
 template <bool WARP, bool DUAL>
-__global__ void __launch_bounds__(PUSH_BLOCK) push2d_dc_kernel(PP pb) {
+__global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];

@@ -263,7 +263,7 @@ def test_init_annulus_rejects_bad_arguments(rt):
 
 
 # ------------------------------------------------------------------------- near-far (work-efficient) schedule
-def check_prev_tie_aware(m, U, src, dist, prev_new, prev_ref):
+def check_prev_tie_aware(m, U, src, dist, prev_new, prev_ref, weight=None):
     """dist must be bit-identical; where prev differs from the reference it must still be a
     bit-exactly tight predecessor (an exact tie), or a zero-weight coupling (halo twin / coincident node)."""
     n = m.n
@@ -273,7 +273,7 @@ def check_prev_tie_aware(m, U, src, dist, prev_new, prev_ref):
     assert np.all(p[reached] >= 0), "reached node without predecessor"
     i = idx[reached]
     j = p[reached]
-    w = weight2d(m.x, m.z, U, i, j)
+    w = weight(i, j) if weight else weight2d(m.x, m.z, U, i, j)
     tight = dist[j] + w == dist[i]
     hm = m.halo_matrix() - 1 if m.halo_rows else np.zeros((0, 2), np.int64)
     partner_of = {}
@@ -561,10 +561,149 @@ def test_dual_velocity_relax_bit_exact(rt, O, annulus, ak135):
         dist, prev, st = O.bfm_dual(m, V2r, s)
         Dn = rt.bfm(G, halo, s, gr, V2r, schedule="near-far")
         assert np.array_equal(Dn.dist, dist)
-        p = Dn.prev
-        i = np.nonzero((p > 0) & np.isfinite(dist))[0]
-        tight = dist[p[i] - 1] + wdual(i, p[i] - 1) == dist[i]
-        halo_nodes = np.zeros(m.n, bool)
-        halo_nodes[halo.ravel() - 1] = True
-        assert np.all(tight | halo_nodes[i]) and len(i) == np.isfinite(dist).sum() - 1
+        check_prev_tie_aware(m, None, s, dist, Dn.prev, prev, weight=wdual)
     rt.bfm(G, halo, 1, gr, V2r, schedule="jacobi")
+
+
+# ------------------------------------------------- BASELINE configs[2], [3], [4] at full size (device-side checks)
+def _solve_dev(rt, h, n, U_dev, srcs):
+    import ctypes as C
+    import torch
+    srcs = np.ascontiguousarray(srcs, np.int64)
+    d = torch.empty(len(srcs) * n, dtype=torch.float64, device="cuda")
+    p = torch.empty(len(srcs) * n, dtype=torch.int32, device="cuda")
+    st = rt.RtStats()
+    rt.api.check(rt.lib().rt_bfm_solve_dev(h.h, U_dev.data_ptr(), srcs, len(srcs), 64, d.data_ptr(), p.data_ptr(),
+                                           C.byref(st)))
+    return d.view(len(srcs), n), p.view(len(srcs), n), st
+
+
+def test_config3_batch_512_sources_properties(rt):
+    """BASELINE config[2]: annulus 720x200 (591 121 nodes), 512 earthquakes, full travel-time tables resident on
+    the device.  Checked with torch fp64 elementwise ops (no contraction, IEEE sqrt/div): source rows, twin
+    equality, bit-exact tightness of every regular predecessor, reciprocity T_a(b) ~ T_b(a), and one table against
+    the reference schedule."""
+    import torch
+    gr, G, halo = rt.init_annulus(720, 200)
+    n = gr.nnods
+    assert n == 591121  # SURVEY 8 table
+    h = gr._handle
+    prof = rt.velocity_profile()
+    Vp = rt.interpolate_velocity(gr.r, rt.LinearInterpolation(prof.r, prof.Vp))
+    U = torch.from_numpy(Vp).cuda()
+    k = np.arange(512)
+    srcs = rt.closest_point(gr, 2 * np.pi * k / 512.0, np.full(512, R), "polar")
+    h.set_option("schedule", 1)
+    d, p, st = _solve_dev(rt, h, n, U, srcs)
+    torch.cuda.synchronize()
+    s_t = torch.from_numpy(srcs - 1).cuda()
+    rows = torch.arange(512, device="cuda")
+    assert bool((d[rows, s_t] == 0).all()) and bool(torch.isfinite(d).all())
+    assert int((p < 0).sum()) == 512  # only the sources have no predecessor
+    hl = torch.from_numpy(halo - 1).cuda()
+    assert bool((d[:, hl[:, 0]] == d[:, hl[:, 1]]).all())
+    # reciprocity: the graph is undirected, so T_a(b) and T_b(a) are the same path summed in opposite order
+    T = d[:, s_t]
+    assert float(((T - T.T).abs() / T.clamp_min(1.0)).max()) < 1e-12
+    x, z = torch.from_numpy(gr.x).cuda(), torch.from_numpy(gr.z).cuda()
+    is_halo = torch.zeros(n, dtype=torch.bool, device="cuda")
+    is_halo[hl.reshape(-1)] = True
+    idx = torch.arange(n, device="cuda")
+    for row in (0, 129, 511):
+        pr = p[row].long()
+        ok = pr >= 0
+        i, j = idx[ok], pr[ok]
+        dx, dz = x[i] - x[j], z[i] - z[j]
+        w = 2.0 * torch.sqrt(dx * dx + dz * dz) / (U[i] + U[j])
+        tight = d[row, j] + w == d[row, i]
+        assert bool((tight | is_halo[i]).all()) and float(tight.double().mean()) > 0.9
+    h.set_option("schedule", 0)
+    dj, pj, stj = _solve_dev(rt, h, n, U, srcs[129:130])
+    assert bool((dj[0] == d[129]).all())
+    assert st.relaxed_edges < 4 * 512 * st.graph_edges  # graph_edges is per source
+
+
+def _shell(rt, nn):
+    import torch
+    c0 = (np.deg2rad(70.0), np.deg2rad(70.0), R - 2000.0)
+    c1 = (np.deg2rad(110.0), np.deg2rad(110.0), R)
+    g = rt.grid(c0, c1, nn, neighbour_levels=1, coord_system="spherical")
+    X, Y, Z = g.coordinates()
+    rr = np.minimum(np.sqrt(X * X + Y * Y + Z * Z), R)
+    prof = rt.velocity_profile()
+    U = rt.interpolate_velocity(rr, rt.LinearInterpolation(prof.r, prof.Vp))
+    return g, [torch.from_numpy(a).cuda() for a in (X, Y, Z, U)]
+
+
+def _check_tight3d(d, p, X, Y, Z, U, chunk=1 << 24):
+    import torch
+    n = d.numel()
+    for a in range(0, n, chunk):
+        i = torch.arange(a, min(n, a + chunk), device="cuda")
+        j = p[i].long()
+        ok = j >= 0
+        i, j = i[ok], j[ok]
+        dx, dy, dz = X[i] - X[j], Y[i] - Y[j], Z[i] - Z[j]
+        w = torch.sqrt(dx * dx + dy * dy + dz * dz) * (1.0 / (U[i] + U[j]).abs()) * 2.0
+        assert bool((d[j] + w == d[i]).all())
+
+
+def test_config4_grid3d_216_properties(rt):
+    """BASELINE config[3]: 3-D spherical shell 216^3 (10 077 696 nodes), star-1, single source.  Both schedules
+    give the same table bit for bit; every predecessor is bit-exactly tight (weights.jl:20 operation order)."""
+    g, (X, Y, Z, U) = _shell(rt, (216, 216, 216))
+    n = g.n
+    assert n == 10077696
+    src = 1 + 108 + 216 * (108 + 216 * 215)
+    h = g._handle
+    h.set_option("schedule", 0)
+    dj, pj, stj = _solve_dev(rt, h, n, U, [src])
+    h.set_option("schedule", 1)
+    dn, pn, stn = _solve_dev(rt, h, n, U, [src])
+    h.set_option("schedule", 0)
+    assert bool((dj == dn).all()) and float(dj[0, src - 1]) == 0.0 and bool(torch_isfinite_all(dj))
+    for d, p in ((dj, pj), (dn, pn)):
+        assert int((p < 0).sum()) == 1
+        _check_tight3d(d[0], p[0], X, Y, Z, U)
+    assert stn.relaxed_edges < stj.relaxed_edges
+
+
+def torch_isfinite_all(t):
+    import torch
+    return torch.isfinite(t).all()
+
+
+def test_config5_grid3d_368_batch_and_receiver_sweep(rt):
+    """BASELINE config[4]: 3-D shell 368^3 (49 836 032 nodes), a batch of surface sources (8 of the 64: the
+    per-source work is identical) and a 1000-receiver recontruct_path sweep on device-resident predecessors."""
+    import torch
+    nx = 368
+    g, (X, Y, Z, U) = _shell(rt, (nx, nx, nx))
+    n = g.n
+    assert n == 49836032
+    srcs = np.array([1 + (nx * (2 * a + 1)) // 8 + nx * ((nx * (2 * b + 1)) // 4 + nx * (nx - 1))
+                     for a in range(4) for b in range(2)], np.int64)
+    h = g._handle
+    h.set_option("schedule", 1)
+    d, p, st = _solve_dev(rt, h, n, U, srcs)
+    h.set_option("schedule", 0)
+    rows = torch.arange(len(srcs), device="cuda")
+    assert bool((d[rows, torch.from_numpy(srcs - 1).cuda()] == 0).all()) and bool(torch.isfinite(d).all())
+    assert int((p < 0).sum()) == len(srcs)
+    _check_tight3d(d[0], p[0], X, Y, Z, U)
+    _check_tight3d(d[7], p[7], X, Y, Z, U)
+    # 1000 receivers on the bottom and top faces
+    rng = np.random.default_rng(7)
+    rec = np.concatenate([1 + rng.integers(0, nx * nx, 500), 1 + n - nx * nx + rng.integers(0, nx * nx, 500)])
+    rec = rec[rec != srcs[3]].astype(np.int64)
+    off = np.zeros(len(rec) + 1, np.int64)
+    lib = rt.lib()
+    rt.api.check(lib.rt_reconstruct_paths_dev(p[3].data_ptr(), n, int(srcs[3]), rec, len(rec), off, None, 0))
+    idx = np.zeros(int(off[-1]), np.int64)
+    rt.api.check(lib.rt_reconstruct_paths_dev(p[3].data_ptr(), n, int(srcs[3]), rec, len(rec), off,
+                                              rt.api.ptr(idx), len(idx)))
+    d3 = d[3].cpu().numpy()
+    for kk in range(0, len(rec), 37):
+        path = idx[off[kk]:off[kk + 1]]
+        assert path[0] == rec[kk] and path[-1] == srcs[3] and np.all(np.diff(d3[path - 1]) < 0)
+    assert np.all(idx[off[1:] - 1] == srcs[3]) and np.all(idx[off[:-1]] == rec)
