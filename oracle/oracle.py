@@ -49,6 +49,9 @@ def lib():
         L.ora_reconstruct_path.argtypes = [I64P, I64, I64, I64, I64P, I64]
         L.ora_grid3d_coords.argtypes = [F64P, F64P, I64P, C.c_int, F64P, F64P, F64P]
         L.ora_bfm3d.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, C.c_int, I64, F64P, I64P, I64P]
+        L.ora_bfm_f32.argtypes = [I64, I64, I64P, I64P, I64P, I64P, I64P, I64, F64P, F64P, F64P, I64, C.c_int, F64P,
+                                  I64P, I64P]
+        L.ora_bfm3d_f32.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, C.c_int, F64P, I64P, I64P]
         L.ora_dijkstra3d.argtypes = [I64P, C.c_int, F64P, F64P, F64P, F64P, I64, F64P]
         L.ora_interpolate_cells.argtypes = [I64, I64P, I64P, I8P, F64P, F64P, F64P]
         L.ora_nodal_adjacency.argtypes = [I64, I64, I64P, I64P, I64P, I64P, C.c_void_p]
@@ -123,6 +126,23 @@ def bfm(mesh, U, source, nthreads=1, max_sweeps=0):
                             graph_edges=int(stats[3]))
 
 
+def bfm_f32(mesh, U, source, nthreads=1):
+    """Float32 comparison path (src/SSSP/bfm_gpu.jl:170-205, 487-526): x, z, U cast to Float32, travel times relaxed
+    in Float32.  Returns the Float32 travel times widened to float64, prev, stats."""
+    n = mesh.n
+    dist = np.zeros(n)
+    prev = np.zeros(n, np.int64)
+    stats = np.zeros(4, np.int64)
+    halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
+    rc = lib().ora_bfm_f32(n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.G_colptr, mesh.G_rowval, halo,
+                           mesh.halo_rows, mesh.x, mesh.z, np.ascontiguousarray(U, np.float64), int(source),
+                           int(nthreads), dist, prev, stats)
+    if rc:
+        raise ValueError("bad source")
+    return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
+                            graph_edges=int(stats[3]))
+
+
 def dijkstra(mesh, U, source):
     dist = np.zeros(mesh.n)
     halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
@@ -162,6 +182,21 @@ def bfm3d(nn, star_levels, X, Y, Z, U, source, nthreads=1, max_sweeps=0):
     stats = np.zeros(4, np.int64)
     rc = lib().ora_bfm3d(nn, int(star_levels), X, Y, Z, np.ascontiguousarray(U, np.float64), int(source),
                          int(nthreads), int(max_sweeps), dist, prev, stats)
+    if rc:
+        raise ValueError("bad source")
+    return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
+                            graph_edges=int(stats[3]))
+
+
+def bfm3d_f32(nn, star_levels, X, Y, Z, U, source, nthreads=1):
+    """3-D solve with coordinates, U and travel times in Float32 (benchmarks/cpu.jl:9-13 runs the grid in Float32)."""
+    nn = np.asarray(nn, np.int64)
+    n = int(np.prod(nn))
+    dist = np.zeros(n)
+    prev = np.zeros(n, np.int64)
+    stats = np.zeros(4, np.int64)
+    rc = lib().ora_bfm3d_f32(nn, int(star_levels), X, Y, Z, np.ascontiguousarray(U, np.float64), int(source),
+                             int(nthreads), dist, prev, stats)
     if rc:
         raise ValueError("bad source")
     return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),

@@ -325,22 +325,29 @@ void element_incidence(Mesh& m) {
 }
 
 // flat views used by the solvers -------------------------------------------------------------------------
-struct Graph2D {
+template <typename T>
+struct Graph2DT {
   i64 n, nel;
   const i64 *e2n_off, *e2n_idx;  // e2n_off[nel+1] 0-based offsets; e2n_idx 1-based node ids
   const i64 *colptr, *rowval;    // Julia CSC, 1-based
   const i64* halo;
   i64 halo_rows;
-  const double *x, *z, *U;
+  const T *x, *z, *U;
 };
+using Graph2D = Graph2DT<double>;
 
 // src/SSSP/bfm.jl:186 + src/GridAnnulus.jl:808-815: dGi + 2.0 * sqrt(0 + dx^2 + dz^2) / (Ui + Uj)
-inline double cand2d(const Graph2D& g, double dj, i64 i0, i64 j0) {
-  double dx = g.x[i0] - g.x[j0], dz = g.z[i0] - g.z[j0];
-  double d = 0.0;
+// T = float restates the Float32 path of src/SSSP/bfm_gpu.jl:487-526 (every array cast to Float32 :170-205):
+// dist0[Gi] + 2 * distance(xi, zi, x[Gi], z[Gi]) / (Ui + U[Gi]) with every operation rounded to Float32.
+template <typename T>
+inline T cand2d(const Graph2DT<T>& g, T dj, i64 i0, i64 j0) {
+  T dx = g.x[i0] - g.x[j0], dz = g.z[i0] - g.z[j0];
+  T d = T(0);
   d += dx * dx;
   d += dz * dz;
-  return dj + 2.0 * std::sqrt(d) / (g.U[i0] + g.U[j0]);
+  T len2 = T(2) * std::sqrt(d);
+  T w = len2 / (g.U[i0] + g.U[j0]);
+  return dj + w;
 }
 
 const double INF = std::numeric_limits<double>::infinity();
@@ -442,16 +449,19 @@ i64 ora_closest_point(const double* a, const double* b, i64 n, double pa, double
 // ------------------------------------------------------------------------------------ bfm (src/SSSP/bfm.jl)
 // stats[0] = sweeps, stats[1] = candidate evaluations (E_relaxed), stats[2] = active-vertex updates,
 // stats[3] = E_graph (sum over vertices of |scan list|)
+extern "C++" {
+template <typename T>
 static int bfm_impl(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
-                    const i64* halo, i64 halo_rows, const double* x, const double* z, const double* U, const double* U2,
-                    const double* r, i64 source, int nthreads, i64 max_sweeps, double* dist, i64* prev, i64* stats) {
+                    const i64* halo, i64 halo_rows, const T* x, const T* z, const T* U, const T* U2,
+                    const T* r, i64 source, int nthreads, i64 max_sweeps, T* dist, i64* prev, i64* stats) {
+  const T INF = std::numeric_limits<T>::infinity();
   // U2 != null: dual-velocity relax, _relax!(..., U::Matrix) bfm.jl:113-159 (U = U[:,1], U2 = U[:,2])
-  Graph2D g{n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U};
+  Graph2DT<T> g{n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U};
   if (source < 1 || source > n) return 1;
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-  std::vector<double> dist0(n);
+  std::vector<T> dist0(n);
   std::vector<uint8_t> Q(n, 0);
   for (i64 i = 0; i < n; ++i) prev[i] = 0;  // reference leaves p undefined (bfm.jl:12)
   // init_halo_path! :64-70 (n = length(halo) / 2 == all 2H rows)
@@ -466,7 +476,7 @@ static int bfm_impl(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, cons
     for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q) Q[e2n_idx[q] - 1] = 1;
   }
   for (i64 i = 0; i < n; ++i) dist[i] = INF;
-  dist[source - 1] = 0.0;
+  dist[source - 1] = T(0);
   for (i64 i = 0; i < n; ++i) dist0[i] = dist[i];
   i64 sweeps = 0, evals = 0, updates = 0;
   std::vector<i64> active;
@@ -483,13 +493,13 @@ static int bfm_impl(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, cons
 #pragma omp parallel for schedule(static) reduction(+ : ev)
     for (i64 a = 0; a < na; ++a) {
       i64 i0 = active[a];
-      double di = dist0[i0];
+      T di = dist0[i0];
       for (i64 p = colptr[i0]; p < colptr[i0 + 1]; ++p) {
         i64 el = rowval[p - 1];
         for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q) {
           i64 j0 = e2n_idx[q] - 1;
-          double dj = dist0[j0];
-          double delta;
+          T dj = dist0[j0];
+          T delta;
           if (dj == INF) {
             delta = INF;
           } else if (!U2) {
@@ -497,10 +507,10 @@ static int bfm_impl(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, cons
           } else {
             // head_idx = (ri > r[Gi]) + 1; tail_idx = (head_idx == 1) + 1; muladd(2, len / (Ui[tail] + U[Gi, head]), dGi)
             const bool down = r[i0] > r[j0];
-            const double ut = down ? U[i0] : U2[i0];
-            const double uh = down ? U2[j0] : U[j0];
-            const double dx = x[i0] - x[j0], dz = z[i0] - z[j0];
-            const double q = std::sqrt(dx * dx + dz * dz) / (ut + uh);
+            const T ut = down ? U[i0] : U2[i0];
+            const T uh = down ? U2[j0] : U[j0];
+            const T dx = x[i0] - x[j0], dz = z[i0] - z[j0];
+            const T q = std::sqrt(dx * dx + dz * dz) / (ut + uh);
             delta = 2 * q + dj;  // muladd: the product by 2 is exact, fused or not
           }
           if (di > delta) {
@@ -536,7 +546,7 @@ static int bfm_impl(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, cons
         }
       }
     }
-    std::memcpy(dist0.data(), dist, sizeof(double) * n);  // :43
+    std::memcpy(dist0.data(), dist, sizeof(T) * n);  // :43
     ++sweeps;
   }
   if (stats) {
@@ -553,20 +563,39 @@ static int bfm_impl(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, cons
   }
   return 0;
 }
+}  // extern "C++"
 
 int ora_bfm(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
             const i64* halo, i64 halo_rows, const double* x, const double* z, const double* U, i64 source,
             int nthreads, i64 max_sweeps, double* dist, i64* prev, i64* stats) {
-  return bfm_impl(n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U, nullptr, nullptr, source,
-                  nthreads, max_sweeps, dist, prev, stats);
+  return bfm_impl<double>(n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U, nullptr, nullptr, source,
+                          nthreads, max_sweeps, dist, prev, stats);
+}
+
+// Float32 comparison path (src/SSSP/bfm_gpu.jl:170-205): x, z, U cast to Float32 (round to nearest), travel times
+// kept and relaxed in Float32 (:487-526); halo rows applied in serial order like the CPU path.  dist_out holds the
+// Float32 values widened to double.
+int ora_bfm_f32(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
+                const i64* halo, i64 halo_rows, const double* x, const double* z, const double* U, i64 source,
+                int nthreads, double* dist_out, i64* prev, i64* stats) {
+  std::vector<float> xf(n), zf(n), Uf(n), df(n);
+  for (i64 i = 0; i < n; ++i) {
+    xf[i] = (float)x[i];
+    zf[i] = (float)z[i];
+    Uf[i] = (float)U[i];
+  }
+  int rc = bfm_impl<float>(n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, xf.data(), zf.data(), Uf.data(),
+                           nullptr, nullptr, source, nthreads, 0, df.data(), prev, stats);
+  for (i64 i = 0; i < n; ++i) dist_out[i] = (double)df[i];
+  return rc;
 }
 
 // bfm with U::Matrix (dual velocity): U1 = U[:,1], U2 = U[:,2], r = gr.r
 int ora_bfm_dual(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
                  const i64* halo, i64 halo_rows, const double* x, const double* z, const double* r, const double* U1,
                  const double* U2, i64 source, int nthreads, double* dist, i64* prev, i64* stats) {
-  return bfm_impl(n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U1, U2, r, source, nthreads, 0, dist,
-                  prev, stats);
+  return bfm_impl<double>(n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U1, U2, r, source, nthreads,
+                          0, dist, prev, stats);
 }
 
 // dual_velocity(r, interpolant; buffer) src/utils.jl:51-66 -> V[n x 2] column-major
@@ -684,20 +713,25 @@ void ora_grid3d_coords(const double* c0, const double* c1, const i64* nn, int co
 }
 
 // src/SSSP/weights.jl:20  edge_weight = distance3D(p1,p2) * (1/abs(U1+U2)) * 2 ; distance3D StructuredGrid.jl:239
-static inline double cand3d(const double* X, const double* Y, const double* Z, const double* U, double dj,
-                            i64 i, i64 j) {
-  double dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
-  double d = std::sqrt(dx * dx + dy * dy + dz * dz);
-  double w = d * (1.0 / std::fabs(U[i] + U[j])) * 2.0;
+extern "C++" {
+template <typename T>
+static inline T cand3d(const T* X, const T* Y, const T* Z, const T* U, T dj, i64 i, i64 j) {
+  T dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
+  T d = std::sqrt(dx * dx + dy * dy + dz * dz);
+  T w = d * (T(1) / std::fabs(U[i] + U[j])) * T(2);
   return dj + w;
 }
+}  // extern "C++"
 
 // star-L adjacency of nodal_incidence (StructuredGrid.jl:177-223): L = 0 -> 26-neighbourhood without self;
 // L >= 1 -> clipped (2L+3)^3 window INCLUDING self.  Canonical scan order = ascending linear id (the
 // reference iterates a Julia Set, whose order is not reproducible).  Control flow = BFM/foo!/goo!
 // (src/Dijsktra.jl:294-343, 376-403).
-int ora_bfm3d(const i64* nn, int star_levels, const double* X, const double* Y, const double* Z,
-              const double* U, i64 source, int nthreads, i64 max_sweeps, double* dist, i64* prev, i64* stats) {
+extern "C++" {
+template <typename T>
+static int bfm3d_impl(const i64* nn, int star_levels, const T* X, const T* Y, const T* Z, const T* U, i64 source,
+                      int nthreads, i64 max_sweeps, T* dist, i64* prev, i64* stats) {
+  const T INF = std::numeric_limits<T>::infinity();
   const i64 nx = nn[0], ny = nn[1], nz = nn[2], n = nx * ny * nz;
   const i64 w = star_levels + 1;
   const bool self = star_levels >= 1;
@@ -705,13 +739,13 @@ int ora_bfm3d(const i64* nn, int star_levels, const double* X, const double* Y, 
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
-  std::vector<double> dist0(n);
+  std::vector<T> dist0(n);
   std::vector<uint8_t> act(n, 0), imp(n, 0);
   for (i64 i = 0; i < n; ++i) {
     dist[i] = INF;
     prev[i] = 0;
   }
-  dist[source - 1] = 0.0;
+  dist[source - 1] = T(0);
   dist0.assign(dist, dist + n);
   auto mark_window = [&](i64 I, std::vector<uint8_t>& flags) {
     i64 i = I % nx, j = (I / nx) % ny, k = I / (nx * ny);
@@ -738,14 +772,14 @@ int ora_bfm3d(const i64* nn, int star_levels, const double* X, const double* Y, 
     for (i64 a = 0; a < na; ++a) {
       i64 I = active[a];
       i64 i = I % nx, j = (I / nx) % ny, k = I / (nx * ny);
-      double di = dist0[I];
+      T di = dist0[I];
       for (i64 kk = std::max<i64>(0, k - w); kk <= std::min(nz - 1, k + w); ++kk)
         for (i64 jj = std::max<i64>(0, j - w); jj <= std::min(ny - 1, j + w); ++jj)
           for (i64 ii = std::max<i64>(0, i - w); ii <= std::min(nx - 1, i + w); ++ii) {
             i64 J = ii + nx * (jj + ny * kk);
             if (J == I && !self) continue;
-            double dj = dist0[J];
-            double t = (dj == INF) ? INF : cand3d(X, Y, Z, U, dj, I, J);
+            T dj = dist0[J];
+            T t = (dj == INF) ? INF : cand3d<T>(X, Y, Z, U, dj, I, J);
             if (di > t) {
               di = t;
               prev[I] = J + 1;
@@ -759,7 +793,7 @@ int ora_bfm3d(const i64* nn, int star_levels, const double* X, const double* Y, 
     std::fill(act.begin(), act.end(), 0);
     for (i64 I = 0; I < n; ++I)
       if (dist[I] < dist0[I]) mark_window(I, act);  // goo!
-    std::memcpy(dist0.data(), dist, sizeof(double) * n);
+    std::memcpy(dist0.data(), dist, sizeof(T) * n);
     ++sweeps;
   }
   if (stats) {
@@ -778,6 +812,30 @@ int ora_bfm3d(const i64* nn, int star_levels, const double* X, const double* Y, 
     stats[3] = eg;
   }
   return 0;
+}
+}  // extern "C++"
+
+int ora_bfm3d(const i64* nn, int star_levels, const double* X, const double* Y, const double* Z,
+              const double* U, i64 source, int nthreads, i64 max_sweeps, double* dist, i64* prev, i64* stats) {
+  return bfm3d_impl<double>(nn, star_levels, X, Y, Z, U, source, nthreads, max_sweeps, dist, prev, stats);
+}
+
+// Float32 variant (the 3-D benchmarks of the reference run the grid in Float32, benchmarks/cpu.jl:9-13): coordinates
+// and U cast to Float32, weights.jl:20 evaluated in Float32; dist_out = the Float32 values widened to double.
+int ora_bfm3d_f32(const i64* nn, int star_levels, const double* X, const double* Y, const double* Z,
+                  const double* U, i64 source, int nthreads, double* dist_out, i64* prev, i64* stats) {
+  const i64 n = nn[0] * nn[1] * nn[2];
+  std::vector<float> Xf(n), Yf(n), Zf(n), Uf(n), df(n);
+  for (i64 i = 0; i < n; ++i) {
+    Xf[i] = (float)X[i];
+    Yf[i] = (float)Y[i];
+    Zf[i] = (float)Z[i];
+    Uf[i] = (float)U[i];
+  }
+  int rc = bfm3d_impl<float>(nn, star_levels, Xf.data(), Yf.data(), Zf.data(), Uf.data(), source, nthreads, 0,
+                             df.data(), prev, stats);
+  for (i64 i = 0; i < n; ++i) dist_out[i] = (double)df[i];
+  return rc;
 }
 
 int ora_dijkstra3d(const i64* nn, int star_levels, const double* X, const double* Y, const double* Z,

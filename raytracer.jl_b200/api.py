@@ -319,7 +319,7 @@ def closest_point(gr, px, pz, system="cartesian"):
 
 
 # ------------------------------------------------------------------------------------------------- solver
-def _solve(handle, n, U, sources, want_prev=True):
+def _solve(handle, n, U, sources, want_prev=True, precision=64):
     U = np.ascontiguousarray(U, np.float64)
     if U.shape != (n,):
         raise ValueError("U must have one entry per node (%d), got %s" % (n, U.shape))
@@ -327,7 +327,11 @@ def _solve(handle, n, U, sources, want_prev=True):
     dist = np.empty((len(src), n), np.float64)
     prev = np.empty((len(src), n), np.int64) if want_prev else None
     st = RtStats()
-    check(lib().rt_bfm_solve(handle.h, U, src, len(src), 64, ptr(dist), ptr(prev), C.byref(st)))
+    if precision not in (64, 32):
+        raise ValueError("precision must be 64 or 32")
+    check(lib().rt_bfm_solve(handle.h, U, src, len(src), int(precision), ptr(dist), ptr(prev), C.byref(st)))
+    if precision == 32:  # the values are Float32 numbers held in float64 storage: the narrowing is exact
+        dist = dist.astype(np.float32)
     return dist, prev, st.as_dict()
 
 
@@ -349,33 +353,42 @@ def _solve_dual(handle, n, U2, source):
 SCHEDULES = {"jacobi": 0, "near-far": 1}
 
 
-def bfm(G, halo, source, gr, U, schedule=None, delta=None):
+def bfm(G, halo, source, gr, U, schedule=None, delta=None, precision=64):
     """D = bfm(G, halo, source, gr, U) -- src/SSSP/bfm.jl:1-52.  `source` may be an array of sources, in which
     case D.dist / D.prev are [nsrc x n] tables (the batch API); a scalar gives vectors as in the reference.
 
     schedule (extension): "jacobi" = the reference's sweeps (dist and prev bit-identical, ties included);
-    "near-far" = work-efficient push schedule (dist bit-identical, prev identical except on exact ties)."""
+    "near-far" = work-efficient push schedule (dist bit-identical, prev identical except on exact ties).
+    precision=32: the Float32 arithmetic of bfm_gpu (src/SSSP/bfm_gpu.jl:170-205): x, z, U cast to Float32, travel
+    times relaxed in Float32; D.dist is a float32 array."""
     handle = mesh_from_arrays(gr, G, halo)
     if schedule is not None:
         handle.set_option("schedule", SCHEDULES[schedule])
     if delta is not None:
         handle.set_option("delta", delta)
     if np.ndim(U) == 2:  # U::Matrix -> dual-velocity relax (bfm.jl:113-159)
+        if precision != 64:
+            raise ValueError("the dual-velocity relax is Float64 only")
         return _solve_dual(handle, int(G.n), U, source)
-    dist, prev, st = _solve(handle, int(G.n), U, source)
+    dist, prev, st = _solve(handle, int(G.n), U, source, precision=precision)
     if np.ndim(source) == 0:
         return BellmanFordMoore(prev[0], dist[0], st)
     return BellmanFordMoore(prev, dist, st)
 
 
-def bfm3d(gr3, source, U, schedule=None, delta=None):
+def bfm_gpu(G, halo, source, gr, U, schedule=None):
+    """bfm_gpu(G, halo, source, gr, U) src/SSSP/bfm_gpu.jl:212-250: the reference's Float32 device path."""
+    return bfm(G, halo, source, gr, U, schedule=schedule, precision=32)
+
+
+def bfm3d(gr3, source, U, schedule=None, delta=None, precision=64):
     """BFM(G, source, gr, U, fw) of src/Dijsktra.jl:294-343 on the implicit star-L graph of a Grid3D with the
     edge weight of src/SSSP/weights.jl:20."""
     if schedule is not None:
         gr3._handle.set_option("schedule", SCHEDULES[schedule])
     if delta is not None:
         gr3._handle.set_option("delta", delta)
-    dist, prev, st = _solve(gr3._handle, gr3.n, U, source)
+    dist, prev, st = _solve(gr3._handle, gr3.n, U, source, precision=precision)
     if np.ndim(source) == 0:
         return BellmanFordMoore(prev[0], dist[0], st)
     return BellmanFordMoore(prev, dist, st)

@@ -193,15 +193,21 @@ int rt_closest_point(const rt_mesh* m, const double* pa, const double* pb, int64
 int rt_bfm_solve_dev(rt_mesh* m, const double* U_dev, const int64_t* sources, int64_t nsrc, int precision,
                      double* dist_dev, int32_t* prev_dev, rt_stats* stats) {
   RT_ARG(m && U_dev && sources && nsrc >= 0, "null argument");
-  if (precision != 64) {
-    rt_set_error("precision %d not implemented (only 64 = reference semantics)", precision);
-    return RT_ERR_UNSUPPORTED;
-  }
+  RT_ARG(precision == 64 || precision == 32, "precision must be 64 (bfm) or 32 (the Float32 path of bfm_gpu)");
+  RT_ARG(m->kind == 2 || m->kind == 3, "mesh handle is empty");
   RT_CUDA(cudaSetDevice(m->device));
-  if (m->kind == 2) return bfm2d_solve(m, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
-  if (m->kind == 3) return bfm3d_solve(m, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
-  rt_set_error("mesh handle is empty");
-  return RT_ERR_ARG;
+  m->f32 = precision == 32;
+  if (m->f32) {
+    // Float32.(U) (bfm_gpu.jl:173); the coordinates are rounded once per mesh inside the solvers
+    const i64 n = mesh_n(m);
+    if (m->Uf.n != (size_t)n) RT_TRY(m->Uf.alloc(n));
+    RT_TRY(round_to_f32_device(U_dev, m->Uf.p, n, m->stream));
+    U_dev = m->Uf.p;
+  }
+  const int rc = m->kind == 2 ? bfm2d_solve(m, U_dev, sources, nsrc, dist_dev, prev_dev, stats)
+                              : bfm3d_solve(m, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
+  m->f32 = false;
+  return rc;
 }
 
 int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t nsrc, int precision,

@@ -45,20 +45,22 @@ struct P2 {
 };
 
 // dGi + 2.0 * sqrt(0 + dx*dx + dz*dz) / (Ui + Uj)   (bfm.jl:186, GridAnnulus.jl:808-815), no contraction
+// F32: the Float32 relax of src/SSSP/bfm_gpu.jl:487-526 (every operation rounded to Float32, see rnd<> in common.cuh)
+template <bool F32>
 __device__ __forceinline__ double cand_delta(double dj, double xi, double zi, double Ui, double xj, double zj,
                                              double Uj) {
-  const double dx = __dsub_rn(xi, xj);
-  const double dz = __dsub_rn(zi, zj);
-  const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
-  const double len2 = __dmul_rn(2.0, __dsqrt_rn(d2));
-  const double w = __ddiv_rn(len2, __dadd_rn(Ui, Uj));
-  return __dadd_rn(dj, w);
+  const double dx = rnd<F32>(__dsub_rn(xi, xj));
+  const double dz = rnd<F32>(__dsub_rn(zi, zj));
+  const double d2 = rnd<F32>(__dadd_rn(rnd<F32>(__dmul_rn(dx, dx)), rnd<F32>(__dmul_rn(dz, dz))));
+  const double len2 = __dmul_rn(2.0, rnd<F32>(__dsqrt_rn(d2)));
+  const double w = rnd<F32>(__ddiv_rn(len2, rnd<F32>(__dadd_rn(Ui, Uj))));
+  return rnd<F32>(__dadd_rn(dj, w));
 }
 
 // One warp per active work item.  DUAL: the velocity pair of an edge is chosen by the radial order of its ends
 // (head_idx = (r_i > r_j) + 1, tail_idx = (head_idx == 1) + 1, bfm.jl:137-138); muladd(2, len/(Ut+Uh), d) there
 // equals d + (2 len)/(Ut+Uh) bit for bit because the factor 2 is exact with or without FMA.
-template <bool DUAL>
+template <bool DUAL, bool F32>
 __global__ void __launch_bounds__(RELAX_BLOCK) relax2d_kernel(P2 p, const i32* __restrict__ active, int cur) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -103,9 +105,9 @@ __global__ void __launch_bounds__(RELAX_BLOCK) relax2d_kernel(P2 p, const i32* _
         {
           const double dx = __dsub_rn(xi, xj), dz = __dsub_rn(zi, zj);
           const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
-          if (screen_cannot_improve(best, dj, d2, __dadd_rn(Ut, Uj))) continue;
+          if (screen_cannot_improve_t<F32>(best, dj, d2, __dadd_rn(Ut, Uj))) continue;
         }
-        const double delta = cand_delta(dj, xi, zi, Ut, xj, zj, Uj);
+        const double delta = cand_delta<F32>(dj, xi, zi, Ut, xj, zj, Uj);
         if (delta < best) {
           best = delta;
           bpos = pos_base + k;
@@ -287,6 +289,17 @@ int bfm2d_ensure_workspace(rt_mesh* h) { return ensure_workspace(h); }
 int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sources, i64 nsrc, double* dist_dev,
                      i32* prev_dev, rt_stats* stats);
 
+// precision = 32: Float32-rounded copies of the coordinates (Float32.(gr.x), bfm_gpu.jl:176-177), built once
+int mesh2d_prepare_f32(rt_mesh* h) {
+  Mesh2D& m = *h->m2;
+  if (m.xf.n == (size_t)m.n) return RT_OK;
+  RT_TRY(m.xf.alloc(m.n));
+  RT_TRY(m.zf.alloc(m.n));
+  RT_TRY(round_to_f32_device(m.x.p, m.xf.p, m.n, h->stream));
+  RT_TRY(round_to_f32_device(m.z.p, m.zf.p, m.n, h->stream));
+  return RT_OK;
+}
+
 int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                 rt_stats* stats) {
   if (h->opts.schedule == 1) return bfm2d_solve_push(h, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
@@ -297,6 +310,10 @@ int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
 int bfm2d_solve_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                      rt_stats* stats) {
   RT_ARG(h->m2->has_polar, "the dual-velocity relax needs gr.r (mesh adopted without theta / r)");
+  if (h->f32) {
+    rt_set_error("precision = 32 is not available for the dual-velocity relax");
+    return RT_ERR_UNSUPPORTED;
+  }
   if (h->opts.schedule == 1) return bfm2d_solve_push_dual(h, U2_dev, sources, nsrc, dist_dev, prev_dev, stats);
   return bfm2d_solve_impl(h, U2_dev, true, sources, nsrc, dist_dev, prev_dev, stats);
 }
@@ -307,9 +324,11 @@ int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sour
   cudaStream_t s = h->stream;
   RT_TRY(ensure_workspace(h));
   const i64 n = m.n;
+  const bool f32 = h->f32;
+  if (f32) RT_TRY(mesh2d_prepare_f32(h));
   P2 p;
-  p.x = m.x.p;
-  p.z = m.z.p;
+  p.x = f32 ? m.xf.p : m.x.p;
+  p.z = f32 ? m.zf.p : m.z.p;
   p.U = U_dev;
   p.U1 = U_dev;
   p.U2 = dual ? U_dev + m.n : U_dev;
@@ -369,9 +388,11 @@ int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sour
       const i64 rb = std::min<i64>((n_active + wpb - 1) / wpb, max_relax_blocks);
       if (h->opts.profile_timers) cudaEventRecord(evr0, s);
       if (dual)
-        relax2d_kernel<true><<<(unsigned)rb, RELAX_BLOCK, 0, s>>>(p, m.act[cur].p, cur);
+        relax2d_kernel<true, false><<<(unsigned)rb, RELAX_BLOCK, 0, s>>>(p, m.act[cur].p, cur);
+      else if (f32)
+        relax2d_kernel<false, true><<<(unsigned)rb, RELAX_BLOCK, 0, s>>>(p, m.act[cur].p, cur);
       else
-        relax2d_kernel<false><<<(unsigned)rb, RELAX_BLOCK, 0, s>>>(p, m.act[cur].p, cur);
+        relax2d_kernel<false, false><<<(unsigned)rb, RELAX_BLOCK, 0, s>>>(p, m.act[cur].p, cur);
       if (h->opts.profile_timers) cudaEventRecord(evr1, s);
       if (m.halo_rows > 0) {
         if (m.halo_structured) {

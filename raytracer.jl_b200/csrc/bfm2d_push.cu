@@ -97,14 +97,18 @@ __device__ __forceinline__ PP pp_view(const PP& p, int b) {
   return v;
 }
 
+// F32: every operation rounded to Float32 (bfm_gpu.jl:487-526; rnd<> in common.cuh)
+template <bool F32 = false>
 __device__ __forceinline__ double edge_delta(double di, double xi, double zi, double Ui, double xj, double zj,
                                              double Uj) {
-  const double dx = __dsub_rn(xi, xj);
-  const double dz = __dsub_rn(zi, zj);
-  const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
-  const double len2 = __dmul_rn(2.0, __dsqrt_rn(d2));
-  return __dadd_rn(di, __ddiv_rn(len2, __dadd_rn(Ui, Uj)));
+  const double dx = rnd<F32>(__dsub_rn(xi, xj));
+  const double dz = rnd<F32>(__dsub_rn(zi, zj));
+  const double d2 = rnd<F32>(__dadd_rn(rnd<F32>(__dmul_rn(dx, dx)), rnd<F32>(__dmul_rn(dz, dz))));
+  const double len2 = __dmul_rn(2.0, rnd<F32>(__dsqrt_rn(d2)));
+  return rnd<F32>(__dadd_rn(di, rnd<F32>(__ddiv_rn(len2, rnd<F32>(__dadd_rn(Ui, Uj))))));
 }
+// relax modes of the push kernels: plain fp64, dual velocity (bfm.jl:113-159), Float32 arithmetic
+constexpr int MODE_F64 = 0, MODE_DUAL = 1, MODE_F32 = 2;
 
 __global__ void hn_index_kernel(const i32* __restrict__ hn_node, i64 n_hn, i32* __restrict__ hn_index) {
   const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -366,10 +370,11 @@ __device__ __forceinline__ void push2d_body_t(const PP& p, const i32* near_cur, 
 // one warp owns one released item, no block barrier.  The element offsets of the column are fetched by the lanes
 // in parallel and prefix-summed, so the targets of ALL its elements form one flat index space that the lanes walk
 // with full utilisation (an element holds ~10 nodes there); sources sit in a warp-private shared-memory slab.
-template <bool PACKED, bool DUAL>
+template <bool PACKED, int MODE>
 __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned mask, int cur, i32* near_next,
                                                  i32* far_list, int fcur, double tau, double2* sxz, double2* sUd, double2* sU2r,
                                                  int* s_id, int* s_pre, int* s_start) {
+  constexpr bool DUAL = MODE == MODE_DUAL, F32 = MODE == MODE_F32;
   const int lane = threadIdx.x & 31;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const int v0 = p.item_first[it];
@@ -464,9 +469,9 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
         {
           const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
           const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
-          if (screen_cannot_improve(best, di, d2, __dadd_rn(ut, us))) continue;
+          if (screen_cannot_improve_t<F32>(best, di, d2, __dadd_rn(ut, us))) continue;
         }
-        const double delta = edge_delta(di, xz.x, xz.y, us, xj, zj, ut);
+        const double delta = edge_delta<F32>(di, xz.x, xz.y, us, xj, zj, ut);
         if (PACKED) {
           const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
           if (delta < best) {
@@ -501,9 +506,10 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
 }
 
 // warp-level units of ONE source: slots of its near list
-template <bool DUAL>
+template <int MODE>
 __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                                  i32* far_list, int fcur, i64 first_warp, i64 n_warps) {
+  constexpr bool DUAL = MODE == MODE_DUAL;
   __shared__ double2 w_sxz[PUSH_BLOCK / 32][32], w_sUd[PUSH_BLOCK / 32][32], w_sU2r[DUAL ? PUSH_BLOCK / 32 : 1][32];
   __shared__ int w_id[PUSH_BLOCK / 32][32], w_pre[PUSH_BLOCK / 32][32], w_start[PUSH_BLOCK / 32][32];
   const int warp = threadIdx.x >> 5;
@@ -514,10 +520,10 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
     if (mask == 0u) continue;
     if (p.ds == 2)
-      push2d_warp_unit<true, DUAL>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
+      push2d_warp_unit<true, MODE>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
                                    w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
     else
-      push2d_warp_unit<false, DUAL>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
+      push2d_warp_unit<false, MODE>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
                                     w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
   }
 }
@@ -527,10 +533,11 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
 // of the released sources (warp-private smem slab) and walks the elements e, e + PUSH_GE, ... of the column with the
 // software-pipelined target loop.  (The CTA-level variant above spends a third of its stall time in __syncthreads.)
 constexpr int PUSH_GE = 16;
-template <bool PACKED, bool DUAL>
+template <bool PACKED, int MODE>
 __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned mask, int e0, int cur, i32* near_next,
                                                  i32* far_list, int fcur, double tau, double2* sxz, double2* sUd, double2* sU2r,
                                                  int* s_id) {
+  constexpr bool DUAL = MODE == MODE_DUAL, F32 = MODE == MODE_F32;
   const int lane = threadIdx.x & 31;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const int v0 = p.item_first[it];
@@ -622,9 +629,9 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
           {
             const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
             const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
-            if (screen_cannot_improve(best, di, d2, __dadd_rn(ut, us))) continue;
+            if (screen_cannot_improve_t<F32>(best, di, d2, __dadd_rn(ut, us))) continue;
           }
-          const double delta = edge_delta(di, xz.x, xz.y, us, xj, zj, ut);
+          const double delta = edge_delta<F32>(di, xz.x, xz.y, us, xj, zj, ut);
           if (PACKED) {
             const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
             if (delta < best) {
@@ -667,9 +674,10 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     if (e0 == 0) atomicAdd(&p.counters[3], (u64)ns);
   }
 }
-template <bool DUAL>
+template <int MODE>
 __device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                                  i32* far_list, int fcur, i64 first_warp, i64 n_warps) {
+  constexpr bool DUAL = MODE == MODE_DUAL;
   __shared__ double2 e_sxz[PUSH_BLOCK / 32][32], e_sUd[PUSH_BLOCK / 32][32], e_sU2r[DUAL ? PUSH_BLOCK / 32 : 1][32];
   __shared__ int e_id[PUSH_BLOCK / 32][32];
   const int warp = threadIdx.x >> 5;
@@ -682,21 +690,21 @@ __device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cu
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
     if (mask == 0u) continue;
     if (p.ds == 2)
-      push2d_elem_unit<true, DUAL>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
+      push2d_elem_unit<true, MODE>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
                                    e_sU2r[DUAL ? warp : 0], e_id[warp]);
     else
-      push2d_elem_unit<false, DUAL>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
+      push2d_elem_unit<false, MODE>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
                                     e_sU2r[DUAL ? warp : 0], e_id[warp]);
   }
 }
 
-template <bool WARP, bool DUAL>
+template <bool WARP, int MODE>
 __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
   if (WARP) {
     const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
-    push2d_warp_body<DUAL>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
+    push2d_warp_body<MODE>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
   } else if (p.cta_units) {
     if (p.ds == 2)
       push2d_body_t<true>(p, near_cur, cur, near_next, far_list, fcur);
@@ -705,14 +713,14 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
   } else {
     const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
-    push2d_elem_body<DUAL>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
+    push2d_elem_body<MODE>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
   }
 }
-template <bool WARP, bool DUAL>
+template <bool WARP, int MODE>
 __global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
                                                            i32* __restrict__ near_next, i32* __restrict__ far_list,
                                                            int fcur) {
-  push2d_body<WARP, DUAL>(p, near_cur, cur, near_next, far_list, fcur);
+  push2d_body<WARP, MODE>(p, near_cur, cur, near_next, far_list, fcur);
 }
 
 // threshold advance, step 1: smallest waiting value
@@ -956,12 +964,12 @@ __global__ void prep_dc_kernel(PP pb) {
   for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (i64)gridDim.x * blockDim.x)
     p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
 }
-template <bool WARP, bool DUAL>
+template <bool WARP, int MODE>
 __global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];
-  push2d_body<WARP, DUAL>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
+  push2d_body<WARP, MODE>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
 }
 __global__ void far_min_dc_kernel(PP pb) {
   const PP p = pp_view(pb, blockIdx.y);
@@ -1022,7 +1030,7 @@ __global__ void far_release_dc_kernel(PP pb) {
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant: ONE cooperative launch runs up to `max_rounds` rounds; phases are separated by grid-wide
 // barriers instead of kernel boundaries (a round costs two or three grid.sync() instead of ~5 launches).
-template <bool WARP, bool DUAL>
+template <bool WARP, int MODE>
 __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, int max_rounds) {
   cg::grid_group grid = cg::this_grid();
   const bool first = blockIdx.x == 0 && threadIdx.x == 0;
@@ -1079,10 +1087,10 @@ __global__ void __launch_bounds__(PUSH_BLOCK) nearfar_persistent_kernel(PP pb, i
           // every source gets its own team of warps (warp w serves source w % nb) so that the sources advance
           // concurrently instead of one after the other
           const i64 gw = gtid >> 5, nw = gsize >> 5;
-          if ((int)(gw % nb) == b) push2d_warp_body<DUAL>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, gw / nb,
+          if ((int)(gw % nb) == b) push2d_warp_body<MODE>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur, gw / nb,
                                                     (nw - b + nb - 1) / nb);
         } else {
-          push2d_body<WARP, DUAL>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
+          push2d_body<WARP, MODE>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
         }
       } else if ((mode2 >> b) & 1u) {
         const i64 n_far = (i64)__ldcg(&p.counters[4 + fcur]);
@@ -1227,11 +1235,40 @@ int ensure_push_workspace(rt_mesh* h, int nb, bool packed) {
   return RT_OK;
 }
 
+
+const void* persistent_kernel_for(bool warp, int mode) {
+  if (warp) {
+    if (mode == MODE_DUAL) return (const void*)nearfar_persistent_kernel<true, MODE_DUAL>;
+    if (mode == MODE_F32) return (const void*)nearfar_persistent_kernel<true, MODE_F32>;
+    return (const void*)nearfar_persistent_kernel<true, MODE_F64>;
+  }
+  if (mode == MODE_DUAL) return (const void*)nearfar_persistent_kernel<false, MODE_DUAL>;
+  if (mode == MODE_F32) return (const void*)nearfar_persistent_kernel<false, MODE_F32>;
+  return (const void*)nearfar_persistent_kernel<false, MODE_F64>;
+}
+void launch_push_dc(bool warp, int mode, dim3 grid, cudaStream_t s, const PP& p) {
+  if (warp) {
+    if (mode == MODE_DUAL)
+      push2d_dc_kernel<true, MODE_DUAL><<<grid, PUSH_BLOCK, 0, s>>>(p);
+    else if (mode == MODE_F32)
+      push2d_dc_kernel<true, MODE_F32><<<grid, PUSH_BLOCK, 0, s>>>(p);
+    else
+      push2d_dc_kernel<true, MODE_F64><<<grid, PUSH_BLOCK, 0, s>>>(p);
+  } else {
+    if (mode == MODE_DUAL)
+      push2d_dc_kernel<false, MODE_DUAL><<<grid, PUSH_BLOCK, 0, s>>>(p);
+    else if (mode == MODE_F32)
+      push2d_dc_kernel<false, MODE_F32><<<grid, PUSH_BLOCK, 0, s>>>(p);
+    else
+      push2d_dc_kernel<false, MODE_F64><<<grid, PUSH_BLOCK, 0, s>>>(p);
+  }
+}
+
 }  // namespace
 
 int bfm2d_ensure_workspace(rt_mesh* h);
 
-int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sources, i64 nsrc, double* dist_dev,
+int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const i64* sources, i64 nsrc, double* dist_dev,
                           i32* prev_dev, rt_stats* stats);
 
 int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
@@ -1244,14 +1281,16 @@ int bfm2d_solve_push_dual(rt_mesh* h, const double* U2_dev, const i64* sources, 
   return bfm2d_solve_push_impl(h, U2_dev, true, sources, nsrc, dist_dev, prev_dev, stats);
 }
 
-int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sources, i64 nsrc, double* dist_dev,
+int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const i64* sources, i64 nsrc, double* dist_dev,
                           i32* prev_dev, rt_stats* stats) {
   Mesh2D& m = *h->m2;
-  if (dual) {
-    RT_ARG(m.has_polar, "the dual-velocity relax needs gr.r (mesh adopted without theta / r)");
+  const bool dual = dual_arg, f32 = h->f32;
+  const int mode = dual ? MODE_DUAL : (f32 ? MODE_F32 : MODE_F64);
+  if (dual) RT_ARG(m.has_polar, "the dual-velocity relax needs gr.r (mesh adopted without theta / r)");
+  if (mode != MODE_F64)
     RT_ARG(h->opts.packed_prev != 0 && h->opts.cta_units == 0 && h->opts.profile_timers == 0,
-           "dual velocity in the near-far schedule needs packed_prev=1, cta_units=0, profile_timers=0");
-  }
+           "dual velocity / precision 32 in the near-far schedule need packed_prev=1, cta_units=0, profile_timers=0");
+  if (f32) RT_TRY(mesh2d_prepare_f32(h));
   cudaStream_t s = h->stream;
   const i64 n = m.n;
   const bool timers = h->opts.profile_timers != 0;
@@ -1268,8 +1307,8 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual, const i64*
   RT_TRY(ensure_push_workspace(h, nb, packed));
   nb = std::min(nb, m.push_nb);
   PP p;
-  p.x = m.x.p;
-  p.z = m.z.p;
+  p.x = f32 ? m.xf.p : m.x.p;
+  p.z = f32 ? m.zf.p : m.z.p;
   p.U = U_dev;
   p.U1 = U_dev;
   p.U2 = dual ? U_dev + m.n : U_dev;
@@ -1315,10 +1354,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual, const i64*
   {
     int coop = 0, per_sm = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
-    const void* pk = p.warp_units ? (dual ? (const void*)nearfar_persistent_kernel<true, true>
-                                          : (const void*)nearfar_persistent_kernel<true, false>)
-                                  : (dual ? (const void*)nearfar_persistent_kernel<false, true>
-                                          : (const void*)nearfar_persistent_kernel<false, false>);
+    const void* pk = persistent_kernel_for(p.warp_units != 0, mode);
     const cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, PUSH_BLOCK, 0);
     if (coop && oe == cudaSuccess) coop_blocks = (i64)per_sm * sm_count;
   }
@@ -1378,10 +1414,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual, const i64*
       int max_rounds = 8192;
       while (!all_done) {
         void* args[] = {(void*)&p, (void*)&max_rounds};
-        const void* kfn = p.warp_units ? (dual ? (const void*)nearfar_persistent_kernel<true, true>
-                                               : (const void*)nearfar_persistent_kernel<true, false>)
-                                       : (dual ? (const void*)nearfar_persistent_kernel<false, true>
-                                               : (const void*)nearfar_persistent_kernel<false, false>);
+        const void* kfn = persistent_kernel_for(p.warp_units != 0, mode);
         cudaError_t le = cudaLaunchCooperativeKernel(kfn, dim3((unsigned)coop_blocks), dim3(PUSH_BLOCK), args, 0, s);
         if (le != cudaSuccess) {
           rc = RT_ERR_CUDA;
@@ -1406,14 +1439,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual, const i64*
         for (int r = 0; r < R; ++r) {
           round_begin_kernel<<<1, 32, 0, s>>>(p);
           prep_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
-          if (p.warp_units && dual)
-            push2d_dc_kernel<true, true><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
-          else if (p.warp_units)
-            push2d_dc_kernel<true, false><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
-          else if (dual)
-            push2d_dc_kernel<false, true><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
-          else
-            push2d_dc_kernel<false, false><<<dim3(gpush, B), PUSH_BLOCK, 0, s>>>(p);
+          launch_push_dc(p.warp_units != 0, mode, dim3(gpush, B), s, p);
           far_min_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
           far_release_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
         }
@@ -1438,10 +1464,10 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual, const i64*
           prep_kernel<<<grid_for(n_near, 256), 256, 0, s>>>(p, m.nearq[cur].p, cur);
           cudaEventRecord(evr0, s);
           if (p.warp_units)
-            push2d_kernel<true, false><<<(unsigned)std::min<i64>((n_near + 3) / 4, max_blocks), PUSH_BLOCK, 0, s>>>(
+            push2d_kernel<true, MODE_F64><<<(unsigned)std::min<i64>((n_near + 3) / 4, max_blocks), PUSH_BLOCK, 0, s>>>(
                 p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           else
-            push2d_kernel<false, false><<<(unsigned)std::min<i64>(n_near * (p.cta_units ? PUSH_GY : PUSH_GE / 4), max_blocks), PUSH_BLOCK, 0, s>>>(
+            push2d_kernel<false, MODE_F64><<<(unsigned)std::min<i64>(n_near * (p.cta_units ? PUSH_GY : PUSH_GE / 4), max_blocks), PUSH_BLOCK, 0, s>>>(
                 p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           cudaEventRecord(evr1, s);
           pushed = true;

@@ -84,27 +84,46 @@ struct DevBuf {
 // Slack: 4e-15*bound absorbs the rounding of (bound - d_from) and of the final fl(d_from + w); the factor
 // (1 + 1e-9) absorbs the roundings of the products and of w itself.  A `true` answer is exact-safe: the
 // candidate can be skipped without changing any result; `false` means "evaluate exactly".
-__device__ __forceinline__ bool screen_cannot_improve(double bound, double d_from, double d2, double ssum) {
+// ---- Float32 mode (precision = 32; the reference's Float32 path src/SSSP/bfm_gpu.jl:170-205, 487-526).  Values stay
+// in fp64 storage but every arithmetic result is rounded to Float32: for +, -, *, / and sqrt of Float32 operands,
+// rounding the correctly rounded fp64 result to Float32 equals the correctly rounded Float32 result (53 >= 2*24 + 2,
+// double rounding is innocuous), so the travel times are bit-identical to genuine Float32 arithmetic.
+template <bool F32>
+__device__ __forceinline__ double rnd(double v) {
+  if constexpr (F32) return (double)__double2float_rn(v);
+  return v;
+}
+// F32 slacks: (bound - d_from) is exact up to fp64 rounding, the final fl32(d_from + w) moves by <= 6e-8 relative, and
+// the Float32 weight differs from the real one by < 4 roundings of 6e-8 (d2 and ssum below are the fp64 values).
+template <bool F32>
+__device__ __forceinline__ bool screen_cannot_improve_t(double bound, double d_from, double d2, double ssum) {
   const double t = bound - d_from;
   if (!(t > 0.0)) return true;  // d_from >= bound (w >= 0), or Inf - Inf
   if (!(ssum > 0.0)) return false;
-  const double ts = (t + bound * 4e-15) * ssum * 0.5;
-  return d2 > ts * ts * (1.0 + 1e-9);
+  const double ts = (t + bound * (F32 ? 1.3e-7 : 4e-15)) * ssum * 0.5;
+  return d2 > ts * ts * (F32 ? 1.0 + 2e-6 : 1.0 + 1e-9);
+}
+__device__ __forceinline__ bool screen_cannot_improve(double bound, double d_from, double d2, double ssum) {
+  return screen_cannot_improve_t<false>(bound, d_from, d2, ssum);
 }
 // Can fl(d_from + w) == target hold?  false => certainly not tight.
-__device__ __forceinline__ bool screen_maybe_tight(double target, double d_from, double d2, double ssum) {
+template <bool F32>
+__device__ __forceinline__ bool screen_maybe_tight_t(double target, double d_from, double d2, double ssum) {
   const double t = target - d_from;
   if (!(t >= 0.0)) return false;
   if (!(ssum > 0.0)) return true;
-  const double slack = target * 4e-15;
+  const double slack = target * (F32 ? 1.3e-7 : 4e-15);
   const double hi = (t + slack) * ssum * 0.5;
-  if (d2 > hi * hi * (1.0 + 1e-9)) return false;
+  if (d2 > hi * hi * (F32 ? 1.0 + 2e-6 : 1.0 + 1e-9)) return false;
   const double tl = t - slack;
   if (tl > 0.0) {
     const double lo = tl * ssum * 0.5;
-    if (d2 < lo * lo * (1.0 - 1e-9)) return false;
+    if (d2 < lo * lo * (F32 ? 1.0 - 2e-6 : 1.0 - 1e-9)) return false;
   }
   return true;
+}
+__device__ __forceinline__ bool screen_maybe_tight(double target, double d_from, double d2, double ssum) {
+  return screen_maybe_tight_t<false>(target, d_from, d2, ssum);
 }
 #endif
 
@@ -133,6 +152,8 @@ struct rt_mesh {
   int device = 0;
   cudaStream_t stream = nullptr;
   SolverOpts opts;
+  bool f32 = false;  // set by the ABI entry for the duration of one solve: precision = 32
+  DevBuf<double> Uf;  // U rounded to Float32 (precision = 32)
   Mesh2D* m2 = nullptr;
   Grid3D* g3 = nullptr;
   // staging buffers of the host-buffer entry point rt_bfm_solve (kept across calls)
@@ -171,6 +192,7 @@ int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
                 rt_stats* stats);
 
 // misc.cu
+int round_to_f32_device(const double* in, double* out, i64 n, cudaStream_t s);  // out[i] = (double)(float)in[i]
 int interp_velocity_device(const double* kr, const double* kv, i64 nk, const double* r, i64 n, double buffer,
                            double* out);
 int closest_point_device(const double* a_dev, const double* b_dev, i64 n, const double* pa, const double* pb,

@@ -30,6 +30,7 @@ struct Grid3D {
   int coord_system = 0;
   double c0[3], c1[3];
   DevBuf<double> X, Y, Z;
+  DevBuf<double> Xf, Yf, Zf;  // Float32-rounded coordinates (precision = 32), built on first use
   i64 tn[3] = {0, 0, 0};
   i64 n_tiles = 0;
   i64 graph_edges = 0;
@@ -99,16 +100,21 @@ __global__ void coords3d_kernel(double c0x, double c0y, double c0z, double c1x, 
 }
 
 // dist0[J] + distance3D(pI,pJ) * (1/abs(UI+UJ)) * 2   (weights.jl:20, StructuredGrid.jl:239-241)
+// F32: the same expression with every operation rounded to Float32 (precision = 32; rnd<> in common.cuh)
+template <bool F32 = false>
 __device__ __forceinline__ double cand3(double dj, double xi, double yi, double zi, double ui, double xj,
                                         double yj, double zj, double uj) {
-  const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
-  const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-  const double d = __dsqrt_rn(s);
-  const double wgt = __dmul_rn(__dmul_rn(d, __drcp_rn(fabs(__dadd_rn(ui, uj)))), 2.0);
-  return __dadd_rn(dj, wgt);
+  const double dx = rnd<F32>(__dsub_rn(xi, xj)), dy = rnd<F32>(__dsub_rn(yi, yj)), dz = rnd<F32>(__dsub_rn(zi, zj));
+  const double s = rnd<F32>(__dadd_rn(rnd<F32>(__dadd_rn(rnd<F32>(__dmul_rn(dx, dx)), rnd<F32>(__dmul_rn(dy, dy)))),
+                                      rnd<F32>(__dmul_rn(dz, dz))));
+  const double d = rnd<F32>(__dsqrt_rn(s));
+  const double rcp = rnd<F32>(__drcp_rn(fabs(rnd<F32>(__dadd_rn(ui, uj)))));
+  const double wgt = __dmul_rn(rnd<F32>(__dmul_rn(d, rcp)), 2.0);
+  return rnd<F32>(__dadd_rn(dj, wgt));
 }
 
 // One CTA per active tile; dynamic smem = 5 * SX*SY*SZ doubles.
+template <bool F32>
 __global__ void __launch_bounds__(TILE_THREADS) relax3d_kernel(P3 p, const i32* __restrict__ active, int cur) {
   extern __shared__ double sm[];
   const int w = p.w;
@@ -163,9 +169,9 @@ __global__ void __launch_bounds__(TILE_THREADS) relax3d_kernel(P3 p, const i32* 
             {
               const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
               const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-              if (screen_cannot_improve(best, dj, d2, fabs(__dadd_rn(ui, uj)))) continue;
+              if (screen_cannot_improve_t<F32>(best, dj, d2, fabs(__dadd_rn(ui, uj)))) continue;
             }
-            const double delta = cand3(dj, xi, yi, zi, ui, xj, yj, zj, uj);
+            const double delta = cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj);
             if (delta < best) {
               best = delta;
               bid = (i64)xx + (i64)p.nx * ((i64)yy + (i64)p.ny * zz);
@@ -411,6 +417,7 @@ constexpr int P3_BLOCK = 128;
 // Warp-level work unit = (near-list slot, dz): the warp keeps the 32 sources of its item in a private shared-memory
 // slab (no block barrier), then walks the (32 + 2w) target columns of that z-plane; for each lane the loads of all
 // 2w+1 target rows are issued back to back (memory-level parallelism) before any of them is evaluated.
+template <bool F32>
 __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
   __shared__ double sm_src[P3_BLOCK / 32][5][32];
@@ -469,8 +476,8 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
         if (!p.self && ty == sy && dzi == 0 && bx * 32 + q == tx) continue;
         const double dx = __dsub_rn(S[0][q], xj), dy = __dsub_rn(S[1][q], yj), dz = __dsub_rn(S[2][q], zj);
         const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        if (screen_cannot_improve(best, di, d2, fabs(__dadd_rn(S[3][q], uj)))) continue;
-        const double delta = cand3(di, S[0][q], S[1][q], S[2][q], S[3][q], xj, yj, zj, uj);
+        if (screen_cannot_improve_t<F32>(best, di, d2, fabs(__dadd_rn(S[3][q], uj)))) continue;
+        const double delta = cand3<F32>(di, S[0][q], S[1][q], S[2][q], S[3][q], xj, yj, zj, uj);
         best = delta < best ? delta : best;
       }
       if (best < dj) {
@@ -528,10 +535,11 @@ __global__ void prep3_kernel(Q3 p) {
   for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (i64)gridDim.x * blockDim.x)
     p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
 }
+template <bool F32>
 __global__ void __launch_bounds__(P3_BLOCK) push3d_kernel(Q3 p) {
   if (p.ctl[2] != 1) return;
   const int cur = p.ctl[0], fcur = p.ctl[1];
-  push3d_body(p, p.nearq[cur], cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
+  push3d_body<F32>(p, p.nearq[cur], cur, p.nearq[cur ^ 1], p.farq[fcur], fcur);
 }
 __device__ __forceinline__ i64 item_node0(const Q3& p, int it) {
   const int bx = it % p.nbx;
@@ -629,6 +637,7 @@ __global__ void wdiag3_kernel(Q3 p, double* __restrict__ sum, u64* __restrict__ 
 }
 // predecessors: first candidate in ascending linear id (the canonical scan order) with dist[J] < dist[I] that is
 // bit-exactly tight.  Thread per node, window read straight from global memory (L2-resident neighbourhood).
+template <bool F32>
 __global__ void prev_tight3_kernel(Q3 p, i64 n, i64 source) {
   const i64 I = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (I >= n) return;
@@ -646,12 +655,24 @@ __global__ void prev_tight3_kernel(Q3 p, i64 n, i64 source) {
         const double xj = p.X[J], yj = p.Y[J], zj = p.Z[J], uj = p.U[J];
         const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
         const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        if (!screen_maybe_tight(di, dj, d2, fabs(__dadd_rn(ui, uj)))) continue;
-        if (cand3(dj, xi, yi, zi, ui, xj, yj, zj, uj) == di) {
+        if (!screen_maybe_tight_t<F32>(di, dj, d2, fabs(__dadd_rn(ui, uj)))) continue;
+        if (cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj) == di) {
           p.prev[I] = (i32)J;
           return;
         }
       }
+}
+
+int grid3d_prepare_f32(rt_mesh* h) {
+  Grid3D& g = *h->g3;
+  if (g.Xf.n == (size_t)g.n) return RT_OK;
+  RT_TRY(g.Xf.alloc(g.n));
+  RT_TRY(g.Yf.alloc(g.n));
+  RT_TRY(g.Zf.alloc(g.n));
+  RT_TRY(round_to_f32_device(g.X.p, g.Xf.p, g.n, h->stream));
+  RT_TRY(round_to_f32_device(g.Y.p, g.Yf.p, g.n, h->stream));
+  RT_TRY(round_to_f32_device(g.Z.p, g.Zf.p, g.n, h->stream));
+  return RT_OK;
 }
 
 int ensure_push3(rt_mesh* h) {
@@ -682,10 +703,12 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   RT_TRY(ensure_ws3(h));
   RT_TRY(ensure_push3(h));
   const i64 n = g.n;
+  const bool f32 = h->f32;
+  if (f32) RT_TRY(grid3d_prepare_f32(h));
   Q3 p;
-  p.X = g.X.p;
-  p.Y = g.Y.p;
-  p.Z = g.Z.p;
+  p.X = f32 ? g.Xf.p : g.X.p;
+  p.Y = f32 ? g.Yf.p : g.Y.p;
+  p.Z = f32 ? g.Zf.p : g.Z.p;
   p.U = U_dev;
   p.dist = g.dist.p;
   p.prev = g.prev.p;
@@ -756,7 +779,10 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
         round_begin3_kernel<<<1, 1, 0, s>>>(p);
         prep3_kernel<<<gsmall, 256, 0, s>>>(p);
         if (timers) cudaEventRecord(evr0, s);
-        push3d_kernel<<<gbig, P3_BLOCK, 0, s>>>(p);
+        if (f32)
+          push3d_kernel<true><<<gbig, P3_BLOCK, 0, s>>>(p);
+        else
+          push3d_kernel<false><<<gbig, P3_BLOCK, 0, s>>>(p);
         if (timers) cudaEventRecord(evr1, s);
         far_min3_kernel<<<gsmall, 256, 0, s>>>(p);
         far_release3_kernel<<<gsmall, 256, 0, s>>>(p);
@@ -777,7 +803,10 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     st.relax_launches += hctl[5];
     st.total_launches += 2 * (i64)hctl[4];
     cudaEventRecord(evr0, s);
-    prev_tight3_kernel<<<grid_for(n, 128), 128, 0, s>>>(p, n, src);
+    if (f32)
+      prev_tight3_kernel<true><<<grid_for(n, 128), 128, 0, s>>>(p, n, src);
+    else
+      prev_tight3_kernel<false><<<grid_for(n, 128), 128, 0, s>>>(p, n, src);
     cudaEventRecord(evr1, s);
     st.total_launches += 1;
     cudaMemcpyAsync(ch, g.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
@@ -816,10 +845,12 @@ int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
   cudaStream_t s = h->stream;
   RT_TRY(ensure_ws3(h));
   const i64 n = g.n;
+  const bool f32 = h->f32;
+  if (f32) RT_TRY(grid3d_prepare_f32(h));
   P3 p;
-  p.X = g.X.p;
-  p.Y = g.Y.p;
-  p.Z = g.Z.p;
+  p.X = f32 ? g.Xf.p : g.X.p;
+  p.Y = f32 ? g.Yf.p : g.Y.p;
+  p.Z = f32 ? g.Zf.p : g.Z.p;
   p.U = U_dev;
   p.dist = g.dist.p;
   p.dist0 = g.dist0.p;
@@ -836,7 +867,8 @@ int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
   p.self = g.self;
   const int w = g.w;
   const size_t smem = (size_t)5 * (TX + 2 * w) * (TY + 2 * w) * (TZ + 2 * w) * sizeof(double);
-  RT_CUDA(cudaFuncSetAttribute(relax3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RT_CUDA(cudaFuncSetAttribute(relax3d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RT_CUDA(cudaFuncSetAttribute(relax3d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
   const i64 max_blocks = (i64)sm_count * 16;
@@ -883,7 +915,10 @@ int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
       const int nxt = cur ^ 1;
       const unsigned nb = (unsigned)std::min<i64>(n_active, max_blocks);
       if (h->opts.profile_timers) cudaEventRecord(evr0, s);
-      relax3d_kernel<<<nb, TILE_THREADS, smem, s>>>(p, g.act[cur].p, cur);
+      if (f32)
+        relax3d_kernel<true><<<nb, TILE_THREADS, smem, s>>>(p, g.act[cur].p, cur);
+      else
+        relax3d_kernel<false><<<nb, TILE_THREADS, smem, s>>>(p, g.act[cur].p, cur);
       if (h->opts.profile_timers) cudaEventRecord(evr1, s);
       commit3d_kernel<<<nb, TILE_THREADS, 0, s>>>(p, g.act[cur].p, cur);
       cudaMemsetAsync(g.counters.p + nxt, 0, sizeof(u64), s);

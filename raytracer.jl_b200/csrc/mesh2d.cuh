@@ -14,6 +14,7 @@
 struct Mesh2D {
   i64 n = 0, nel = 0, sum_e2n = 0, nnzG = 0, halo_rows = 0, sum_nbr = 0, ntheta = 0, nr = 0;
   DevBuf<double> x, z, theta, r;
+  DevBuf<double> xf, zf;  // Float32-rounded coordinates (precision = 32), built on first use
   bool has_polar = false;
   DevBuf<i32> e2n_off, e2n_idx;
   DevBuf<i64> g_off;
@@ -66,6 +67,7 @@ struct Mesh2D {
 // Finishes a Mesh2D whose primary arrays (x,z,e2n_*,g_*) are already on the device: builds n2e, work items,
 // halo tables, E_graph.  halo_host: (2H x 2) column-major 1-based (may be null if halo_rows == 0).
 int mesh2d_finalize(rt_mesh* h, const i64* halo_host);
+int mesh2d_prepare_f32(rt_mesh* h);
 int bfm2d_solve_push_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 nsrc, double* dist_dev,
                           i32* prev_dev, rt_stats* stats);
 int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,

@@ -10,6 +10,12 @@ namespace {
 __constant__ double RL_DEV[7] = {6371.0 - 20.0,  6371.0 - 35.0,   6371.0 - 210.0, 6371.0 - 410.0,
                                  6371.0 - 660.0, 6371.0 - 2740.0, 6371.0 - 2891.5};
 
+// Float32.(v) of src/SSSP/bfm_gpu.jl:173-177, kept in fp64 storage
+__global__ void round_f32_kernel(const double* __restrict__ in, double* __restrict__ out, i64 n) {
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+    out[i] = (double)__double2float_rn(in[i]);
+}
+
 // interpolate_velocity: src/utils.jl:38-44 (buffer < 0) / src/ShortestPath.jl:74-90 (buffer >= 0).
 // Interpolations.jl gridded linear: i = clamp(searchsortedlast(knots, x), 1, nk-1);
 // f = (x - k[i]) / (k[i+1] - k[i]);  v = (1 - f) * y[i] + f * y[i+1]   (no FMA)
@@ -317,5 +323,12 @@ int prev_host_to_device_i32(const i64* prev, i64 n, DevBuf<i32>& out) {
   prev_i64_to_i32_kernel<<<grid_for(n, 256), 256>>>(tmp.p, out.p, n);
   RT_CUDA(cudaGetLastError());
   RT_CUDA(cudaDeviceSynchronize());
+  return RT_OK;
+}
+
+int round_to_f32_device(const double* in, double* out, i64 n, cudaStream_t s) {
+  if (n <= 0) return RT_OK;
+  round_f32_kernel<<<(unsigned)std::min<i64>((n + 255) / 256, 148 * 16), 256, 0, s>>>(in, out, n);
+  RT_CUDA(cudaGetLastError());
   return RT_OK;
 }

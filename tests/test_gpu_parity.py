@@ -707,3 +707,78 @@ def test_config5_grid3d_368_batch_and_receiver_sweep(rt):
         path = idx[off[kk]:off[kk + 1]]
         assert path[0] == rec[kk] and path[-1] == srcs[3] and np.all(np.diff(d3[path - 1]) < 0)
     assert np.all(idx[off[1:] - 1] == srcs[3]) and np.all(idx[off[:-1]] == rec)
+
+
+# ------------------------------------------------------------------ precision = 32 (Float32 path of bfm_gpu.jl)
+@pytest.mark.parametrize("nt,nr,sp", [(24, 6, 300.0), (36, 10, 100.0), (90, 20, 20.0)])
+def test_bfm2d_float32_mode(rt, O, annulus, ak135, nt, nr, sp):
+    """Float32 comparison path (src/SSSP/bfm_gpu.jl:170-205, 487-526).  x, z, U are cast to Float32 and
+    every operation is rounded to Float32; the result must equal genuine Float32 arithmetic (the oracle computes
+    in `float`) bit for bit in both schedules, predecessors included in the reference schedule, and stay within
+    the Float32 accuracy of the Float64 tables."""
+    m = annulus(nt, nr, sp)
+    gr, G, halo = adopt(rt, m)
+    Vp = O.interp_velocity(ak135[0], ak135[1], m.r)
+    srcs = [O.closest_point(m.theta, m.r, 0.0, R), m.n // 2]
+    for src in srcs:
+        d32, p32, st32 = O.bfm_f32(m, Vp, src)
+        D = rt.bfm(G, halo, src, gr, Vp, schedule="jacobi", precision=32)
+        assert D.dist.dtype == np.float32
+        assert np.array_equal(D.dist.astype(np.float64), d32)
+        assert np.array_equal(D.prev, p32) and D.stats["sweeps"] == st32["sweeps"]
+        Dn = rt.bfm_gpu(G, halo, src, gr, Vp, schedule="near-far")
+        assert np.array_equal(Dn.dist.astype(np.float64), d32)
+        f32 = lambda a: a.astype(np.float32)
+
+        def w32(i, j):  # Float32 weight, numpy float32 ops round after every operation
+            dx, dz = f32(m.x)[i] - f32(m.x)[j], f32(m.z)[i] - f32(m.z)[j]
+            return (np.float32(2) * np.sqrt(dx * dx + dz * dz) / (f32(Vp)[i] + f32(Vp)[j])).astype(np.float64)
+
+        def wsum(i, j):  # tightness in Float32: fl32(d[j] + w)
+            return w32(i, j)
+        dref = d32.astype(np.float32)
+        p = Dn.prev - 1
+        idx = np.arange(m.n)
+        ok = np.isfinite(d32) & (idx != src - 1)
+        i, j = idx[ok], p[ok]
+        tight = (dref[j] + w32(i, j).astype(np.float32)) == dref[i]
+        halo_nodes = np.zeros(m.n, bool)
+        halo_nodes[halo.ravel() - 1] = True
+        assert np.all(tight | halo_nodes[i])
+        d64, _, _ = O.bfm(m, Vp, src)
+        assert np.max(np.abs(d32 - d64) / np.maximum(d64, 1e-9)) < 5e-5  # Float32 accumulates ~1e-5 on these meshes
+    # batch of sources in lock step + back to Float64 on the same handle (the rounded copies must not leak)
+    D = rt.bfm(G, halo, srcs, gr, Vp, schedule="near-far", precision=32)
+    for k, src in enumerate(srcs):
+        assert np.array_equal(D.dist[k].astype(np.float64), O.bfm_f32(m, Vp, src)[0])
+    D64 = rt.bfm(G, halo, srcs[0], gr, Vp, schedule="jacobi")
+    assert np.array_equal(D64.dist, O.bfm(m, Vp, srcs[0])[0])
+    with pytest.raises(ValueError):
+        rt.bfm(G, halo, 1, gr, Vp, precision=16)
+
+
+@pytest.mark.parametrize("nn,cs", [((9, 8, 7), "cartesian"), ((24, 20, 16), "spherical")])
+def test_bfm3d_float32_mode(rt, O, nn, cs):
+    if cs == "spherical":
+        c0 = (np.deg2rad(70.0), np.deg2rad(70.0), R - 2000.0)
+        c1 = (np.deg2rad(110.0), np.deg2rad(110.0), R)
+    else:
+        c0, c1 = (0.0, 0.0, 0.0), (90.0, 70.0, 60.0)
+    g = rt.grid(c0, c1, nn, neighbour_levels=1, coord_system=cs)
+    X, Y, Z = g.coordinates()
+    U = 4.0 + 6.0 * splitmix64(11, g.n)
+    for src in (1, g.n // 2):
+        d32, p32, st = O.bfm3d_f32(nn, 1, X, Y, Z, U, src)
+        D = rt.bfm3d(g, src, U, schedule="jacobi", precision=32)
+        assert np.array_equal(D.dist.astype(np.float64), d32) and np.array_equal(D.prev, p32)
+        Dn = rt.bfm3d(g, src, U, schedule="near-far", precision=32)
+        assert np.array_equal(Dn.dist.astype(np.float64), d32)
+        # near-far predecessors: bit-exactly tight in Float32
+        f = lambda a: a.astype(np.float32)
+        i = np.nonzero(Dn.prev > 0)[0]
+        j = Dn.prev[i] - 1
+        assert len(i) == g.n - 1
+        dx, dy, dz = f(X)[i] - f(X)[j], f(Y)[i] - f(Y)[j], f(Z)[i] - f(Z)[j]
+        w = np.sqrt(dx * dx + dy * dy + dz * dz) * (np.float32(1) / np.abs(f(U)[i] + f(U)[j])) * np.float32(2)
+        assert w.dtype == np.float32 and np.array_equal(f(d32)[j] + w, f(d32)[i])
+    rt.bfm3d(g, 1, U, schedule="jacobi")
