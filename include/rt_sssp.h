@@ -129,8 +129,11 @@ int rt_closest_point(const rt_mesh* m, const double* pa, const double* pb, int64
 /* ---- solver: bfm(G, halo, source, gr, U) src/SSSP/bfm.jl:1-52 -------------------------------------------- */
 /* Solves nsrc independent single-source problems on the same mesh and velocity.  dist_out / prev_out are
  * [nsrc x n] row-major (source-major) host buffers == BellmanFordMoore(prev, dist) per source
- * (src/SSSP/ssspm.jl:3-10).  Either output may be NULL.  precision: 64 (reference semantics; only this is
- * implemented).  stats may be NULL. */
+ * (src/SSSP/ssspm.jl:3-10).  Either output may be NULL.  stats may be NULL.
+ * precision: 64 = the Float64 arithmetic of bfm (src/SSSP/bfm.jl); 32 = the Float32 arithmetic of bfm_gpu
+ * (src/SSSP/bfm_gpu.jl:170-205, 487-526): x, z (X, Y, Z) and U are rounded to Float32 and every operation of the
+ * relax is rounded to Float32; dist_out then holds Float32 values widened to double (narrowing them is exact).
+ * Both precisions run in both schedules and give results bit-identical to the respective arithmetic. */
 int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t nsrc, int precision,
                  double* dist_out, int64_t* prev_out, rt_stats* stats);
 

@@ -16,7 +16,7 @@ module RayTracerB200
 using SparseArrays
 
 export Grid2D, BellmanFordMoore, R, init_annulus, closest_point, interpolate_velocity, bfm, recontruct_path,
-       LinearInterpolation, bfm_batch, interpolate!, symrcm, nodal_degree, dual_velocity
+       LinearInterpolation, bfm_batch, bfm_gpu, interpolate!, symrcm, nodal_degree, dual_velocity
 
 const R = 6371.0                                   # src/utils.jl:2
 const LIB = get(ENV, "RT_SSSP_LIB", joinpath(@__DIR__, "..", "raytracer.jl_b200", "librt_sssp.so"))
@@ -146,8 +146,17 @@ function bfm(G::SparseMatrixCSC{Bool,M}, halo::Matrix, source::Integer, gr, U::A
     return BellmanFordMoore(D.prev[:, 1], D.dist[:, 1])
 end
 
+# bfm_gpu(G, halo, source, gr, U) -- src/SSSP/bfm_gpu.jl:212-250: same call, Float32 arithmetic (precision = 32);
+# D.dist::Vector{Float32}, D.prev::Vector{Int32} as in the reference's device path
+function bfm_gpu(G::SparseMatrixCSC{Bool,M}, halo::Matrix, source::Int, gr, U::AbstractArray{T}) where {M,T}
+    D, st = bfm_batch(G, halo, Int64[source], gr, U; precision = 32)
+    println("Converged in $(st.sweeps + 1) iterations")
+    return BellmanFordMoore(Int32.(D.prev[:, 1]), Float32.(D.dist[:, 1]))   # exact: the values are Float32 numbers
+end
+
 # batch API: many earthquakes on one mesh; tables are n x nsrc (column per source)
-function bfm_batch(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector{Int64}, gr, U::AbstractArray)
+function bfm_batch(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector{Int64}, gr, U::AbstractArray;
+                   precision::Integer = 64)
     h = mesh_handle(G, halo, gr)
     n, ns = G.n, length(sources)
     dist = Matrix{Float64}(undef, n, ns)
@@ -155,7 +164,7 @@ function bfm_batch(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector
     st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0))
     check(ccall((:rt_bfm_solve, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
-                h.ptr, Vector{Float64}(U), sources, ns, 64, dist, prev, st))
+                h.ptr, Vector{Float64}(U), sources, ns, precision, dist, prev, st))
     return BellmanFordMoore(prev, dist), st[]
 end
 
