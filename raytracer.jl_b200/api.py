@@ -265,6 +265,34 @@ def sparse_adjacency_list(gr, G=None, halo=None):
     return SparseAdjencyList(lst, deg, off[:-1] + 1)
 
 
+class AdjencyList:
+    """AdjencyList{G, N} of src/topology/topology.jl:1-4 (sic): G is the zero-padded [maxdeg x nnods] neighbour matrix
+    (column j = neighbours of node j, 1-based, 0 = padding; Julia column-major == this array's Fortran order), N the
+    nodal degrees."""
+
+    def __init__(self, G, N):
+        self.G, self.N = G, N
+
+
+def adjacency_list(gr, G=None, halo=None):
+    """adjacency_list(nodal_incidence(gr)) -- src/topology/topology.jl:52-68: the dense padded form of the same
+    star-0 adjacency (neighbours in ascending id; the reference's order is the iteration order of a Julia Set).
+    Only sensible on coarse meshes: the matrix has maxdeg x nnods Int32 entries."""
+    sp = sparse_adjacency_list(gr, G, halo)
+    n = gr.nnods
+    maxdeg = int(sp.deg.max()) if n else 0
+    out = np.zeros((maxdeg, n), np.int32, order="F")
+    col = np.repeat(np.arange(n), sp.deg)
+    row = np.arange(len(sp.list)) - np.repeat(sp.idx - 1, sp.deg)
+    out[row, col] = sp.list
+    return AdjencyList(out, sp.deg.astype(np.int32))
+
+
+def element_degree(G):
+    """element_degree(IM) -- src/topology/topology.jl:79-86: number of elements in each column of G."""
+    return np.diff(G.colptr).astype(np.int64)
+
+
 def symrcm(gr, G=None, halo=None):
     """symrcm(nodal_incidence(gr), degrees) -- src/SSSP/rcm.jl:2-46.  Returns prm (1-based int64)."""
     prm = np.zeros(gr.nnods, np.int64)

@@ -518,6 +518,14 @@ def test_topology_containers_and_rcm(rt, O, annulus, ak135):
             seeds += 1
     assert 1 <= seeds <= 16  # one seed per connected component (8 velocity layers, twins are separate nodes)
     assert deg_o[F[0] - 1] == deg_o.min()  # starts from a minimum-degree node (rcm.jl:4,13-22)
+    # dense padded container (topology.jl:1-4, 52-68) and element_degree (:79-86)
+    sp = rt.sparse_adjacency_list(gr)
+    A = rt.adjacency_list(gr, G, halo)
+    assert A.G.shape == (int(deg_o.max()), m.n) and np.array_equal(A.N, deg_o)
+    for node in (1, 7, m.n // 2, m.n):
+        col = A.G[:, node - 1]
+        assert np.array_equal(col[:deg_o[node - 1]], sp.neighbours(node)) and not col[deg_o[node - 1]:].any()
+    assert np.array_equal(rt.element_degree(G), np.diff(m.G_colptr))
     # reorder! + solve: travel times are the same function of the (relabelled) nodes
     Vp = O.interp_velocity(ak135[0], ak135[1], m.r)
     src = O.closest_point(m.theta, m.r, 0.0, R)
