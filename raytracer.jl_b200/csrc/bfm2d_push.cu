@@ -580,8 +580,11 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     const int el = p.g_idx[c];
     const int s = p.e2n_off[el];
     const int m = p.e2n_off[el + 1] - s;
+    // the target ids run two iterations ahead of the evaluation and the gathers one iteration ahead, so neither the
+    // id load nor the gathers that depend on it are waited for in the iteration that issues them
     int k = lane;
     int j = k < m ? p.e2n_idx[s + k] : -1;
+    int jn = k + 32 < m ? p.e2n_idx[s + k + 32] : -1;
     double dj = 0.0, xj = 0.0, zj = 0.0, Uj = 0.0, U2j = 0.0, rj = 0.0;
     u64 kj = KEY_NONE, kjn = KEY_NONE;
     if (j >= 0) {
@@ -597,7 +600,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     }
     while (k < m) {
       const int kn = k + 32;
-      const int jn = kn < m ? p.e2n_idx[s + kn] : -1;
+      const int jnn = kn + 32 < m ? p.e2n_idx[s + kn + 32] : -1;
       double djn = 0.0, xjn = 0.0, zjn = 0.0, Ujn = 0.0, U2jn = 0.0, rjn = 0.0;
       if (jn >= 0) {
         if (PACKED) kjn = __ldcg(p.keys + 2 * (i64)jn + 1);
@@ -659,6 +662,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
       }
       k = kn;
       j = jn;
+      jn = jnn;
       kj = kjn;
       dj = djn;
       xj = xjn;
