@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "librt_sssp.so")
+SO_PATH = os.environ.get("RT_SSSP_LIB") or os.path.join(HERE, "librt_sssp.so")  # RT_SSSP_LIB: kernel-variant A/B runs
 
 I64 = C.c_int64
 VP = C.c_void_p

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(RELAX_BLOCK) relax2d_kernel(P2 p, const i32* _
         }
         {
           const double dx = __dsub_rn(xi, xj), dz = __dsub_rn(zi, zj);
-          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+          const double d2 = __fma_rn(dx, dx, dz * dz);
           if (screen_cannot_improve_t<F32>(best, dj, d2, __dadd_rn(Ut, Uj))) continue;
         }
         const double delta = cand_delta<F32>(dj, xi, zi, Ut, xj, zj, Uj);

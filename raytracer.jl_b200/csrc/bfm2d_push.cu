@@ -321,7 +321,7 @@ __device__ __forceinline__ void push2d_body_t(const PP& p, const i32* near_cur, 
             const double2 xz = sxz[q];
             {
               const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
-              const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+              const double d2 = __fma_rn(dx, dx, dz * dz);
               if (screen_cannot_improve(best, di, d2, __dadd_rn(ud.x, Uj))) continue;
             }
             const double delta = edge_delta(di, xz.x, xz.y, ud.x, xj, zj, Uj);
@@ -468,7 +468,7 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
         }
         {
           const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
-          const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+          const double d2 = __fma_rn(dx, dx, dz * dz);
           if (screen_cannot_improve_t<F32>(best, di, d2, __dadd_rn(ut, us))) continue;
         }
         const double delta = edge_delta<F32>(di, xz.x, xz.y, us, xj, zj, ut);
@@ -631,7 +631,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
           }
           {
             const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
-            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz));
+            const double d2 = __fma_rn(dx, dx, dz * dz);
             if (screen_cannot_improve_t<F32>(best, di, d2, __dadd_rn(ut, us))) continue;
           }
           const double delta = edge_delta<F32>(di, xz.x, xz.y, us, xj, zj, ut);

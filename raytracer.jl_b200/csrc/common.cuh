@@ -95,13 +95,13 @@ __device__ __forceinline__ double rnd(double v) {
 }
 // F32 slacks: (bound - d_from) is exact up to fp64 rounding, the final fl32(d_from + w) moves by <= 6e-8 relative, and
 // the Float32 weight differs from the real one by < 4 roundings of 6e-8 (d2 and ssum below are the fp64 values).
+// Callers guarantee d_from < bound (so t > 0; bound = Inf gives ts = Inf and never skips).  The screen itself is free
+// to contract (explicit FMAs): it only has to be conservative, not bit-reproducible.
 template <bool F32>
 __device__ __forceinline__ bool screen_cannot_improve_t(double bound, double d_from, double d2, double ssum) {
-  const double t = bound - d_from;
-  if (!(t > 0.0)) return true;  // d_from >= bound (w >= 0), or Inf - Inf
-  if (!(ssum > 0.0)) return false;
-  const double ts = (t + bound * (F32 ? 1.3e-7 : 4e-15)) * ssum * 0.5;
-  return d2 > ts * ts * (F32 ? 1.0 + 2e-6 : 1.0 + 1e-9);
+  const double tt = __fma_rn(bound, F32 ? 1.3e-7 : 4e-15, bound - d_from);
+  const double ts = tt * ssum;
+  return (d2 > ts * ts * (F32 ? 0.25 * (1.0 + 2e-6) : 0.25 * (1.0 + 1e-9))) && (ssum > 0.0);
 }
 __device__ __forceinline__ bool screen_cannot_improve(double bound, double d_from, double d2, double ssum) {
   return screen_cannot_improve_t<false>(bound, d_from, d2, ssum);

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(TILE_THREADS) relax3d_kernel(P3 p, const i32* 
             const double xj = sX[c], yj = sY[c], zj = sZ[c], uj = sU[c];
             {
               const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
-              const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+              const double d2 = __fma_rn(dx, dx, __fma_rn(dy, dy, dz * dz));
               if (screen_cannot_improve_t<F32>(best, dj, d2, fabs(__dadd_rn(ui, uj)))) continue;
             }
             const double delta = cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj);
@@ -475,7 +475,7 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
         if (!(di < best)) continue;
         if (!p.self && ty == sy && dzi == 0 && bx * 32 + q == tx) continue;
         const double dx = __dsub_rn(S[0][q], xj), dy = __dsub_rn(S[1][q], yj), dz = __dsub_rn(S[2][q], zj);
-        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        const double d2 = __fma_rn(dx, dx, __fma_rn(dy, dy, dz * dz));
         if (screen_cannot_improve_t<F32>(best, di, d2, fabs(__dadd_rn(S[3][q], uj)))) continue;
         const double delta = cand3<F32>(di, S[0][q], S[1][q], S[2][q], S[3][q], xj, yj, zj, uj);
         best = delta < best ? delta : best;
