@@ -533,8 +533,11 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
 // of the released sources (warp-private smem slab) and walks the elements e, e + PUSH_GE, ... of the column with the
 // software-pipelined target loop.  (The CTA-level variant above spends a third of its stall time in __syncthreads.)
 constexpr int PUSH_GE = 16;
+constexpr int PUSH_SPLIT = 8;     // max warps per (item, element) in sparse rounds
+constexpr int PUSH_FILL = 148 * 24;  // resident warps the split aims to occupy
 template <bool PACKED, int MODE>
-__device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned mask, int e0, int cur, i32* near_next,
+__device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned mask, int e0, int sub, int kst, int cur,
+                                                 i32* near_next,
                                                  i32* far_list, int fcur, double tau, double2* sxz, double2* sUd, double2* sU2r,
                                                  int* s_id) {
   constexpr bool DUAL = MODE == MODE_DUAL, F32 = MODE == MODE_F32;
@@ -559,7 +562,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
   for (int o = 16; o; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
   const int ns = __popc(mask);
   __syncwarp();
-  if (e0 == 0 && p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {  // zero-weight halo coupling
+  if (e0 == 0 && sub == 0 && p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {  // zero-weight halo coupling
     const int lo = p.hn_index[s_id[lane]];
     if (lo >= 0) {
       const double d = sUd[lane].y;
@@ -582,9 +585,10 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     const int m = p.e2n_off[el + 1] - s;
     // the target ids run two iterations ahead of the evaluation and the gathers one iteration ahead, so neither the
     // id load nor the gathers that depend on it are waited for in the iteration that issues them
-    int k = lane;
+    // (sub, kst): when a round releases few items the targets of an element are split over kst/32 warps
+    int k = lane + 32 * sub;
     int j = k < m ? p.e2n_idx[s + k] : -1;
-    int jn = k + 32 < m ? p.e2n_idx[s + k + 32] : -1;
+    int jn = k + kst < m ? p.e2n_idx[s + k + kst] : -1;
     double dj = 0.0, xj = 0.0, zj = 0.0, Uj = 0.0, U2j = 0.0, rj = 0.0;
     u64 kj = KEY_NONE, kjn = KEY_NONE;
     if (j >= 0) {
@@ -599,8 +603,8 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
       }
     }
     while (k < m) {
-      const int kn = k + 32;
-      const int jnn = kn + 32 < m ? p.e2n_idx[s + kn + 32] : -1;
+      const int kn = k + kst;
+      const int jnn = kn + kst < m ? p.e2n_idx[s + kn + kst] : -1;
       double djn = 0.0, xjn = 0.0, zjn = 0.0, Ujn = 0.0, U2jn = 0.0, rjn = 0.0;
       if (jn >= 0) {
         if (PACKED) kjn = __ldcg(p.keys + 2 * (i64)jn + 1);
@@ -671,11 +675,11 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
       U2j = U2jn;
       rj = rjn;
     }
-    evals += (u64)m * (u64)ns;
+    if (sub == 0) evals += (u64)m * (u64)ns;
   }
   if (lane == 0) {
     if (evals) atomicAdd(&p.counters[2], evals);
-    if (e0 == 0) atomicAdd(&p.counters[3], (u64)ns);
+    if (e0 == 0 && sub == 0) atomicAdd(&p.counters[3], (u64)ns);
   }
 }
 template <int MODE>
@@ -687,17 +691,24 @@ __device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cu
   const int warp = threadIdx.x >> 5;
   const i64 n_near = (i64)__ldcg(&p.counters[cur]);
   const double tau = __ldcg(&p.tau[0]);
-  for (i64 unit = first_warp; unit < n_near * PUSH_GE; unit += n_warps) {
-    const i64 slot = unit / PUSH_GE;
-    const int e0 = (int)(unit - slot * PUSH_GE);
+  // a round that releases few items would leave most of the machine idle while single warps walk whole elements
+  // (tens of dependent gather rounds each): split every element over up to PUSH_SPLIT warps then
+  const i64 base = n_near * PUSH_GE;
+  const int split = (int)max((i64)1, min((i64)PUSH_SPLIT, (i64)PUSH_FILL / max(base, (i64)1)));
+  const int kst = 32 * split;
+  for (i64 unit = first_warp; unit < base * split; unit += n_warps) {
+    const i64 eu = unit / split;
+    const int sub = (int)(unit - eu * split);
+    const i64 slot = eu / PUSH_GE;
+    const int e0 = (int)(eu - slot * PUSH_GE);
     const int it = __ldcg(&near_cur[slot]);
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
     if (mask == 0u) continue;
     if (p.ds == 2)
-      push2d_elem_unit<true, MODE>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
+      push2d_elem_unit<true, MODE>(p, it, mask, e0, sub, kst, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
                                    e_sU2r[DUAL ? warp : 0], e_id[warp]);
     else
-      push2d_elem_unit<false, MODE>(p, it, mask, e0, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
+      push2d_elem_unit<false, MODE>(p, it, mask, e0, sub, kst, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
                                     e_sU2r[DUAL ? warp : 0], e_id[warp]);
   }
 }
@@ -1471,7 +1482,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
             push2d_kernel<true, MODE_F64><<<(unsigned)std::min<i64>((n_near + 3) / 4, max_blocks), PUSH_BLOCK, 0, s>>>(
                 p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           else
-            push2d_kernel<false, MODE_F64><<<(unsigned)std::min<i64>(n_near * (p.cta_units ? PUSH_GY : PUSH_GE / 4), max_blocks), PUSH_BLOCK, 0, s>>>(
+            push2d_kernel<false, MODE_F64><<<(unsigned)std::min<i64>(p.cta_units ? n_near * PUSH_GY : std::max<i64>(n_near * (PUSH_GE / 4), std::min<i64>(n_near * (PUSH_GE / 4) * PUSH_SPLIT, PUSH_FILL / 4)), max_blocks), PUSH_BLOCK, 0, s>>>(
                 p, m.nearq[cur].p, cur, m.nearq[nxt].p, m.farq[fcur].p, fcur);
           cudaEventRecord(evr1, s);
           pushed = true;
