@@ -533,8 +533,14 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
 // of the released sources (warp-private smem slab) and walks the elements e, e + PUSH_GE, ... of the column with the
 // software-pipelined target loop.  (The CTA-level variant above spends a third of its stall time in __syncthreads.)
 constexpr int PUSH_GE = 16;
-constexpr int PUSH_SPLIT = 8;     // max warps per (item, element) in sparse rounds
-constexpr int PUSH_FILL = 148 * 24;  // resident warps the split aims to occupy
+#ifndef RT_PUSH_SPLIT
+#define RT_PUSH_SPLIT 32
+#endif
+#ifndef RT_PUSH_FILL
+#define RT_PUSH_FILL (148 * 96)
+#endif
+constexpr int PUSH_SPLIT = RT_PUSH_SPLIT;     // max warps per (item, element) in sparse rounds
+constexpr int PUSH_FILL = RT_PUSH_FILL;  // warps the split aims to create (4 waves of resident warps; measured optimum is flat)
 template <bool PACKED, int MODE>
 __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned mask, int e0, int sub, int kst, int cur,
                                                  i32* near_next,
