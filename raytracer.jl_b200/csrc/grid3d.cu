@@ -394,21 +394,33 @@ struct Q3 {
   int* ctl;       // [0] cur [1] fcur [2] mode [3] done [4] rounds [5] push rounds
   int nx, ny, nz, nbx;
   int w, self;
+  FastDiv fd_nx, fd_ny, fd_nbx, fd_W;  // node id -> (x, line), line -> (y, z), item -> (bx, line), unit -> (slot, dz)
 };
+
+// append to a list through its (hot) counter: one atomic per group of converged lanes instead of one per lane
+__device__ __forceinline__ void list_append(i32* __restrict__ list, u64* counter, i32 v) {
+  const unsigned act = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(act) - 1;
+  u64 base = 0;
+  if (lane == leader) base = atomicAdd(counter, (u64)__popc(act));
+  base = __shfl_sync(act, base, leader);
+  list[base + __popc(act & ((1u << lane) - 1u))] = v;
+}
 
 __device__ __forceinline__ void enqueue3(const Q3& p, i64 J, double d, double tau, i32* near_next, int nxt,
                                          i32* far_list, int fcur) {
-  const int ix = (int)(J % p.nx);
-  const i64 line = J / p.nx;
-  const int it = (int)((ix >> 5) + (i64)p.nbx * line);
+  unsigned line, ix;
+  p.fd_nx.divmod((unsigned)J, line, ix);
+  const int it = (int)((ix >> 5) + (unsigned)p.nbx * line);
   const unsigned bit = 1u << (ix & 31);
   if (d < tau) {
     const unsigned old = atomicOr(&p.pend_mask[it], bit);
-    if (old == 0u) near_next[atomicAdd(&p.counters[nxt], 1ull)] = it;
+    if (old == 0u) list_append(near_next, &p.counters[nxt], it);
     if (__ldcg(&p.far_mask[it]) & bit) atomicAnd(&p.far_mask[it], ~bit);
   } else {
     atomicOr(&p.far_mask[it], bit);
-    if (atomicExch(&p.infar[it], 1u) == 0u) far_list[atomicAdd(&p.counters[4 + fcur], 1ull)] = it;
+    if (atomicExch(&p.infar[it], 1u) == 0u) list_append(far_list, &p.counters[4 + fcur], it);
   }
 }
 
@@ -431,12 +443,14 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
   const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
   u64 evals = 0;
   for (i64 unit = gw; unit < n_near * W; unit += nw) {
-    const i64 slot = unit / W;
-    const int dzi = (int)(unit - slot * W) - w;
+    unsigned slot_u, dz_u, line_u, bx_u, sy_u, sz_u;
+    p.fd_W.divmod((unsigned)unit, slot_u, dz_u);  // n_near * W < 2^32 (n_items * 7 at the largest accepted grid)
+    const i64 slot = slot_u;
+    const int dzi = (int)dz_u - w;
     const int it = __ldcg(&near_cur[slot]);
-    const int bx = it % p.nbx;
-    const i64 line = it / p.nbx;
-    const int sy = (int)(line % p.ny), sz = (int)(line / p.ny);
+    p.fd_nbx.divmod((unsigned)it, line_u, bx_u);
+    p.fd_ny.divmod(line_u, sz_u, sy_u);
+    const int bx = (int)bx_u, sy = (int)sy_u, sz = (int)sz_u;
     const int tz = sz + dzi;
     if (tz < 0 || tz >= p.nz) continue;  // warp-uniform
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
@@ -462,16 +476,21 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
     const int xa = max(0, bx * 32 + first - w), xb = min(p.nx - 1, bx * 32 + last + w);
     const int y0 = max(0, sy - w), y1 = min(p.ny - 1, sy + w);
     const int ncol = xb - xa + 1, nt = ncol * (y1 - y0 + 1);
+    const float rcol = 1.0f / (float)ncol;
     for (int t = lane; t < nt; t += 32) {
-      const int r = t / ncol;
+      const int r = __float2int_rz(((float)t + 0.5f) * rcol);  // exact: t < 36 * 7, ncol <= 46
       const int tx = xa + (t - r * ncol), ty = y0 + r;
       const i64 J = (i64)tx + (i64)p.nx * ((i64)ty + (i64)p.ny * tz);
       const double dj = __ldcg(&p.dist[J]);
       const double xj = p.X[J], yj = p.Y[J], zj = p.Z[J], uj = p.U[J];
       double best = dj;
       const int q0 = max(tx - w, bx * 32) - bx * 32, q1 = min(tx + w, bx * 32 + 31) - bx * 32;
-      for (int q = q0; q <= q1; ++q) {
-        const double di = S[4][q];  // INF if not released
+      // released sources inside the window of this target
+      unsigned wm = (mask >> q0) & (0xffffffffu >> (31 - (q1 - q0)));
+      while (wm) {
+        const int q = q0 + __ffs(wm) - 1;
+        wm &= wm - 1u;
+        const double di = S[4][q];
         if (!(di < best)) continue;
         if (!p.self && ty == sy && dzi == 0 && bx * 32 + q == tx) continue;
         const double dx = __dsub_rn(S[0][q], xj), dy = __dsub_rn(S[1][q], yj), dz = __dsub_rn(S[2][q], zj);
@@ -490,11 +509,15 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
       // evaluations of this z-plane: per released source, clipped x-extent times clipped y-extent
       u64 e = 0;
       const int ycnt = y1 - y0 + 1;
-      for (int q = first; q <= last; ++q)
-        if ((mask >> q) & 1u) {
-          const int gx = bx * 32 + q;
-          e += (u64)(min(p.nx - 1, gx + w) - max(0, gx - w) + 1) * (u64)ycnt;
-        }
+      if (bx * 32 + first - w >= 0 && bx * 32 + last + w <= p.nx - 1) {
+        e = (u64)__popc(mask) * (u64)(2 * w + 1) * (u64)ycnt;  // interior item: full x-extent for every source
+      } else {
+        for (int q = first; q <= last; ++q)
+          if ((mask >> q) & 1u) {
+            const int gx = bx * 32 + q;
+            e += (u64)(min(p.nx - 1, gx + w) - max(0, gx - w) + 1) * (u64)ycnt;
+          }
+      }
       evals += e;
       if (dzi == 0) atomicAdd(&p.counters[3], (u64)__popc(mask));
     }
@@ -729,6 +752,11 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.nbx = (int)g.nbx;
   p.w = g.w;
   p.self = g.self;
+  p.fd_nx = FastDiv((unsigned)g.nn[0]);
+  p.fd_ny = FastDiv((unsigned)g.nn[1]);
+  p.fd_nbx = FastDiv((unsigned)g.nbx);
+  p.fd_W = FastDiv((unsigned)(2 * g.w + 1));
+  RT_ARG(g.n_items * (2 * g.w + 1) < ((i64)1 << 32), "grid too large for the near-far schedule");
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
   const unsigned gbig = (unsigned)(sm_count * 16), gsmall = (unsigned)(sm_count * 2);
