@@ -26,7 +26,8 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = sources() + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + [os.path.join(ROOT, "include", "rt_sssp.h")]
+    deps = (sources() + glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "csrc", "*.h"))
+            + [os.path.join(ROOT, "include", "rt_sssp.h")])
     return any(os.path.getmtime(d) > t for d in deps)
 
 
