@@ -60,6 +60,13 @@ def test_bfm2d_golden_vectors(rt):
     D = rt.bfm(G, halo, int(g["source"]), gr, g["U"])
     assert np.array_equal(D.dist, g["dist"]) and np.array_equal(D.prev, g["prev"])
     assert D.stats["sweeps"] == int(g["sweeps"])
+    gm = np.load(os.path.join(GOLD, "annulus_24_6_300_modes.npz"))  # Float32 and dual-velocity modes
+    D32 = rt.bfm(G, halo, int(g["source"]), gr, g["U"], precision=32)
+    assert np.array_equal(D32.dist, gm["dist_f32"]) and np.array_equal(D32.prev, gm["prev_f32"])
+    assert np.array_equal(rt.bfm_gpu(G, halo, int(g["source"]), gr, g["U"], schedule="near-far").dist, gm["dist_f32"])
+    rt.bfm(G, halo, 1, gr, g["U"], schedule="jacobi")
+    Dd = rt.bfm(G, halo, int(g["source"]), gr, gm["V2"])
+    assert np.array_equal(Dd.dist, gm["dist_dual"]) and np.array_equal(Dd.prev, gm["prev_dual"])
 
 
 def test_bfm2d_random_velocity_and_interior_sources(rt, O, annulus):
@@ -183,6 +190,13 @@ def test_bfm3d_golden(rt):
         assert np.array_equal(D.dist, g3["dist"]) and np.array_equal(D.prev, g3["prev"])
     else:  # coordinates differ in the last ulp (device vs glibc sin/cos): travel times agree to ~1e-15
         assert np.allclose(D.dist, g3["dist"], rtol=1e-13, atol=0)
+    g3f = np.load(os.path.join(GOLD, "grid3d_7_6_5_f32.npz"))
+    D32 = rt.bfm3d(g, int(g3["source"]), g3["U"], precision=32)
+    f = lambda a: a.astype(np.float32)
+    if all(np.array_equal(f(a), f(b)) for a, b in ((X, g3["X"]), (Y, g3["Y"]), (Z, g3["Z"]))):
+        assert np.array_equal(D32.dist, g3f["dist_f32"]) and np.array_equal(D32.prev, g3f["prev_f32"])
+    else:
+        assert np.allclose(D32.dist, g3f["dist_f32"], rtol=1e-6, atol=0)
 
 
 def test_bfm3d_full_size_properties(rt):
