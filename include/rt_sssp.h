@@ -143,6 +143,15 @@ int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t ns
 int rt_bfm_solve_dev(rt_mesh* m, const double* U_dev, const int64_t* sources, int64_t nsrc, int precision,
                      double* dist_dev, int32_t* prev_dev, rt_stats* stats);
 
+/* Single-process multi-GPU batch (many earthquakes shard by source; no exchange inside the relaxation).
+ * meshes[0..ndev) are replicas of the SAME mesh, one per device (built by the caller after rt_set_device(d) with
+ * rt_annulus_build / rt_mesh_from_arrays / rt_grid3d_build); replica d solves the contiguous block
+ * sources[d*k .. (d+1)*k), k = ceil(nsrc / ndev), on its own host thread and stream and writes its rows of the
+ * [nsrc x n] host tables directly -- the "gather" is the host buffer the caller (Julia) owns.  stats: sums over the
+ * replicas, kernel_ms = max over replicas.  Options (schedule ...) are taken from each replica's own handle. */
+int rt_bfm_solve_multi(rt_mesh* const* meshes, int ndev, const double* U, const int64_t* sources, int64_t nsrc,
+                       int precision, double* dist_out, int64_t* prev_out, rt_stats* stats);
+
 /* Dual-velocity variant: bfm with U::Matrix -> _relax!(..., U::Matrix) src/SSSP/bfm.jl:113-159.  U2 is the
  * [n x 2] matrix of dual_velocity (column-major: U[:,1] "below" values, then U[:,2] "above" values); for an edge
  * between node i and candidate j the pair is U[i, tail] + U[j, head] with head = (r_i > r_j) + 1, tail = 3 - head.

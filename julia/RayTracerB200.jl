@@ -16,7 +16,7 @@ module RayTracerB200
 using SparseArrays
 
 export Grid2D, BellmanFordMoore, R, init_annulus, closest_point, interpolate_velocity, bfm, recontruct_path,
-       LinearInterpolation, bfm_batch, bfm_gpu, interpolate!, symrcm, nodal_degree, dual_velocity
+       LinearInterpolation, bfm_batch, bfm_batch_multi, set_device, bfm_gpu, interpolate!, symrcm, nodal_degree, dual_velocity
 
 const R = 6371.0                                   # src/utils.jl:2
 const LIB = get(ENV, "RT_SSSP_LIB", joinpath(@__DIR__, "..", "raytracer.jl_b200", "librt_sssp.so"))
@@ -165,6 +165,21 @@ function bfm_batch(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector
     check(ccall((:rt_bfm_solve, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
                 h.ptr, Vector{Float64}(U), sources, ns, precision, dist, prev, st))
+    return BellmanFordMoore(prev, dist), st[]
+end
+
+# many earthquakes over several GPUs from one Julia process: `grids` are replicas of the same mesh, one per device
+# (build each after `set_device(d)`); replica d solves a contiguous block of `sources` on its own host thread
+set_device(d::Integer) = check(ccall((:rt_set_device, LIB), Cint, (Cint,), d))
+function bfm_batch_multi(grids::Vector, sources::Vector{Int64}, U::AbstractArray; precision::Integer = 64)
+    hs = Ptr{Cvoid}[g.handle.ptr for g in grids]
+    n, ns = length(U), length(sources)
+    dist = Matrix{Float64}(undef, n, ns)
+    prev = Matrix{Int64}(undef, n, ns)
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0))
+    check(ccall((:rt_bfm_solve_multi, LIB), Cint,
+                (Ptr{Ptr{Cvoid}}, Cint, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
+                hs, length(hs), Vector{Float64}(U), sources, ns, precision, dist, prev, st))
     return BellmanFordMoore(prev, dist), st[]
 end
 

@@ -18,7 +18,7 @@ SYMBOLS = [
     "rt_last_error", "rt_version", "rt_device_count", "rt_set_device", "rt_annulus_build", "rt_mesh_sizes",
     "rt_mesh_export", "rt_mesh_from_arrays", "rt_grid3d_build", "rt_grid3d_export", "rt_mesh_free",
     "rt_interp_velocity", "rt_interp_velocity_dev", "rt_interpolate_cells", "rt_nodal_adjacency", "rt_rcm", "rt_mesh_coords_dev", "rt_closest_point", "rt_bfm_solve",
-    "rt_bfm_solve_dev", "rt_bfm_solve_dual", "rt_dual_velocity", "rt_set_option", "rt_reconstruct_paths", "rt_reconstruct_paths_dev",
+    "rt_bfm_solve_dev", "rt_bfm_solve_multi", "rt_bfm_solve_dual", "rt_dual_velocity", "rt_set_option", "rt_reconstruct_paths", "rt_reconstruct_paths_dev",
 ]
 
 
@@ -69,6 +69,7 @@ def lib():
     L.rt_closest_point.argtypes = [VP, F64P, F64P, I64, C.c_int, I64P]
     L.rt_bfm_solve.argtypes = [VP, F64P, I64P, I64, C.c_int, VP, VP, C.POINTER(RtStats)]
     L.rt_bfm_solve_dev.argtypes = [VP, VP, I64P, I64, C.c_int, VP, VP, C.POINTER(RtStats)]
+    L.rt_bfm_solve_multi.argtypes = [C.POINTER(VP), C.c_int, F64P, I64P, I64, C.c_int, VP, VP, C.POINTER(RtStats)]
     L.rt_bfm_solve_dual.argtypes = [VP, F64P, I64P, I64, VP, VP, C.POINTER(RtStats)]
     L.rt_dual_velocity.argtypes = [F64P, F64P, I64, F64P, I64, C.c_double, F64P]
     L.rt_set_option.argtypes = [VP, C.c_char_p, C.c_double]

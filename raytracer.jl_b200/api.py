@@ -452,6 +452,38 @@ def travel_times(D, gr, receivers, isave=False, flname=""):
     return tt
 
 
+def set_device(device):
+    """Selects the CUDA device for the meshes built next (rt_set_device)."""
+    check(lib().rt_set_device(int(device)))
+
+
+def bfm_multi(grids, sources, U, schedule=None, precision=64):
+    """Batch of earthquakes over several GPUs from ONE process (rt_bfm_solve_multi): `grids` are replicas of the same
+    mesh, one per device (build each after set_device(d): Grid2D objects from init_annulus / mesh_from_arrays, or
+    Grid3D objects); replica d solves a contiguous block of `sources` on its own host thread.  Returns
+    BellmanFordMoore with [nsrc x n] tables in the order of `sources`."""
+    handles = [g._handle for g in grids]
+    if any(h is None for h in handles):
+        raise ValueError("every replica needs a device handle (init_annulus / mesh_from_arrays / grid)")
+    n = grids[0].n if isinstance(grids[0], Grid3D) else int(grids[0].nnods)
+    U = np.ascontiguousarray(U, np.float64)
+    if U.shape != (n,):
+        raise ValueError("U must have one entry per node (%d), got %s" % (n, U.shape))
+    if schedule is not None:
+        for h in handles:
+            h.set_option("schedule", SCHEDULES[schedule])
+    src = np.atleast_1d(np.asarray(sources, np.int64)).copy()
+    dist = np.empty((len(src), n), np.float64)
+    prev = np.empty((len(src), n), np.int64)
+    st = RtStats()
+    arr = (C.c_void_p * len(handles))(*[h.h for h in handles])
+    check(lib().rt_bfm_solve_multi(arr, len(handles), U, src, len(src), int(precision), ptr(dist), ptr(prev),
+                                   C.byref(st)))
+    if precision == 32:
+        dist = dist.astype(np.float32)
+    return BellmanFordMoore(prev, dist, st.as_dict())
+
+
 def device_count():
     c = C.c_int(0)
     check(lib().rt_device_count(C.byref(c)))

@@ -2,6 +2,9 @@
 // host <-> device staging around the kernels.  No compute happens on the host.
 #include <algorithm>
 #include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -280,6 +283,51 @@ int rt_bfm_solve_dual(rt_mesh* m, const double* U2, const int64_t* sources, int6
     total.relax_ms += st.relax_ms;
     total.relax_launches += st.relax_launches;
     total.total_launches += st.total_launches;
+  }
+  if (stats) *stats = total;
+  return RT_OK;
+}
+
+int rt_bfm_solve_multi(rt_mesh* const* meshes, int ndev, const double* U, const int64_t* sources, int64_t nsrc,
+                       int precision, double* dist_out, int64_t* prev_out, rt_stats* stats) {
+  RT_ARG(meshes && ndev >= 1 && U && sources && nsrc >= 0, "null argument");
+  for (int d = 0; d < ndev; ++d) RT_ARG(meshes[d] && meshes[d]->kind == meshes[0]->kind, "replicas must be meshes of one kind");
+  const i64 n = mesh_n(meshes[0]);
+  for (int d = 1; d < ndev; ++d) {
+    RT_ARG(mesh_n(meshes[d]) == n, "replicas must have the same number of nodes");
+    for (int e = 0; e < d; ++e) RT_ARG(meshes[e] != meshes[d], "every replica needs its own handle");
+  }
+  const i64 k = (nsrc + ndev - 1) / ndev;
+  std::vector<int> rc(ndev, RT_OK);
+  std::vector<std::string> err(ndev);
+  std::vector<rt_stats> st(ndev);
+  std::vector<std::thread> workers;
+  for (int d = 0; d < ndev; ++d) {
+    workers.emplace_back([&, d]() {
+      const i64 lo = std::min<i64>(nsrc, d * k), hi = std::min<i64>(nsrc, (d + 1) * k);
+      st[d] = rt_stats{};
+      if (hi <= lo) return;
+      rc[d] = rt_bfm_solve(meshes[d], U, sources + lo, hi - lo, precision, dist_out ? dist_out + lo * n : nullptr,
+                           prev_out ? prev_out + lo * n : nullptr, &st[d]);
+      if (rc[d] != RT_OK) err[d] = rt_last_error();  // the message lives in the worker's thread-local buffer
+    });
+  }
+  for (auto& w : workers) w.join();
+  rt_stats total = {};
+  for (int d = 0; d < ndev; ++d) {
+    if (rc[d] != RT_OK) {
+      rt_set_error("replica %d (device %d): %s", d, meshes[d]->device, err[d].c_str());
+      return rc[d];
+    }
+    total.sweeps += st[d].sweeps;
+    total.relaxed_edges += st[d].relaxed_edges;
+    total.vertex_updates += st[d].vertex_updates;
+    total.graph_edges = std::max(total.graph_edges, st[d].graph_edges);
+    total.kernel_ms = std::max(total.kernel_ms, st[d].kernel_ms);
+    total.relax_ms = std::max(total.relax_ms, st[d].relax_ms);
+    total.relax_launches += st[d].relax_launches;
+    total.total_launches += st[d].total_launches;
+    total.prev_ms = std::max(total.prev_ms, st[d].prev_ms);
   }
   if (stats) *stats = total;
   return RT_OK;

@@ -804,3 +804,49 @@ def test_bfm3d_float32_mode(rt, O, nn, cs):
         w = np.sqrt(dx * dx + dy * dy + dz * dz) * (np.float32(1) / np.abs(f(U)[i] + f(U)[j])) * np.float32(2)
         assert w.dtype == np.float32 and np.array_equal(f(d32)[j] + w, f(d32)[i])
     rt.bfm3d(g, 1, U, schedule="jacobi")
+
+
+# ----------------------------------------------------------- single-process multi-GPU batch (rt_bfm_solve_multi)
+def test_bfm_multi_replicas(rt, O, annulus, ak135):
+    """sources shard over replicas of the mesh, one host thread per replica, tables land in the caller's
+    host buffers in source order.  Replicas go to distinct devices when the box has several, otherwise two replicas
+    share device 0 (same code path: separate handles, streams and host threads)."""
+    m = annulus(36, 10, 100.0)
+    Vp = O.interp_velocity(ak135[0], ak135[1], m.r)
+    ndev = max(2, min(rt.device_count(), 4))
+    reps = []
+    for d in range(ndev):
+        rt.set_device(d % rt.device_count())
+        gr, G, halo = adopt(rt, m)
+        rt.mesh_from_arrays(gr, G, halo)
+        reps.append(gr)
+    rt.set_device(0)
+    srcs = np.array([1, m.n, m.n // 2, 7, 1234, m.n // 3, 99], np.int64)  # 7 sources: ragged shards
+    for sched in ("jacobi", "near-far"):
+        D = rt.bfm_multi(reps, srcs, Vp, schedule=sched)
+        assert D.dist.shape == (len(srcs), m.n)
+        for k, s in enumerate(srcs):
+            d1, p1, _ = O.bfm(m, Vp, int(s))
+            assert np.array_equal(D.dist[k], d1), "source #%d (%s)" % (k, sched)
+            if sched == "jacobi":
+                assert np.array_equal(D.prev[k], p1)
+    D32 = rt.bfm_multi(reps, srcs[:3], Vp, schedule="jacobi", precision=32)
+    assert np.array_equal(D32.dist[2].astype(np.float64), O.bfm_f32(m, Vp, int(srcs[2]))[0])
+    one = rt.bfm_multi(reps, srcs[:1], Vp)  # fewer sources than replicas
+    assert np.array_equal(one.dist[0], O.bfm(m, Vp, 1)[0])
+    with pytest.raises(rt.RtError):
+        rt.bfm_multi(reps, [0], Vp)  # bad source id reported from the worker thread
+    with pytest.raises(rt.RtError):
+        rt.bfm_multi([reps[0], reps[0]], srcs, Vp)  # the same handle twice
+    # 3-D replicas
+    nn = (12, 10, 8)
+    gs = []
+    for d in range(2):
+        rt.set_device(d % rt.device_count())
+        gs.append(rt.grid((0.0, 0.0, 0.0), (90.0, 70.0, 60.0), nn, neighbour_levels=1, coord_system="cartesian"))
+    rt.set_device(0)
+    X, Y, Z = gs[0].coordinates()
+    U3 = 4.0 + 6.0 * splitmix64(5, gs[0].n)
+    D3 = rt.bfm_multi(gs, [1, gs[0].n, 17], U3, schedule="near-far")
+    for k, s in enumerate((1, gs[0].n, 17)):
+        assert np.array_equal(D3.dist[k], O.bfm3d(nn, 1, X, Y, Z, U3, s)[0])
