@@ -16,7 +16,8 @@ module RayTracerB200
 using SparseArrays
 
 export Grid2D, BellmanFordMoore, R, init_annulus, closest_point, interpolate_velocity, bfm, recontruct_path,
-       LinearInterpolation, bfm_batch, bfm_batch_multi, set_device, bfm_gpu, interpolate!, symrcm, nodal_degree, dual_velocity
+       LinearInterpolation, bfm_batch, bfm_batch_multi, set_device, bfm_gpu, interpolate!, symrcm, nodal_degree,
+       dual_velocity, SparseAdjencyList, sparse_adjacency_list, travel_times, set_schedule!, Grid3D, grid, coordinates, BFM
 
 const R = 6371.0                                   # src/utils.jl:2
 const LIB = get(ENV, "RT_SSSP_LIB", joinpath(@__DIR__, "..", "raytracer.jl_b200", "librt_sssp.so"))
@@ -226,6 +227,84 @@ function nodal_degree(gr::Grid2D)
     check(ccall((:rt_nodal_adjacency, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64),
                 gr.handle.ptr, deg, C_NULL, C_NULL, 0))
     return deg
+end
+
+# sparse_adjacency_list(nodal_incidence(gr)) -- src/topology/topology.jl:88-111 (Int32 CSR: list, deg, idx = 1 + cumsum)
+struct SparseAdjencyList{T}
+    list::Vector{T}
+    deg::Vector{T}
+    idx::Vector{T}
+end
+function sparse_adjacency_list(gr::Grid2D)
+    n = gr.nnods
+    deg, off = zeros(Int64, n), zeros(Int64, n + 1)
+    check(ccall((:rt_nodal_adjacency, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64),
+                gr.handle.ptr, deg, off, C_NULL, 0))
+    list = zeros(Int64, off[end])
+    check(ccall((:rt_nodal_adjacency, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64),
+                gr.handle.ptr, C_NULL, C_NULL, list, length(list)))
+    return SparseAdjencyList(Int32.(list), Int32.(deg), Int32.(off[1:n] .+ 1))
+end
+
+# travel_times(D, gr, receivers; isave, flname) -- src/utils.jl:4-15 (the CSV is written without DataFrames/CSV.jl)
+function travel_times(D, gr, receivers; isave = false, flname = "")
+    travel_time = [D.dist[receiver] for receiver in receivers]
+    if isave
+        θ = rad2deg.(gr.θ[receivers])
+        open(joinpath(pwd(), flname), "w") do io
+            println(io, "degree,travel_time")
+            for (a, b) in zip(θ, travel_time)
+                println(io, a, ",", b)
+            end
+        end
+    end
+    return travel_time
+end
+
+# solver schedule of a mesh: :jacobi = the reference's sweeps (default), Symbol("near-far") = work-efficient ordering
+function set_schedule!(gr, schedule::Symbol)
+    check(ccall((:rt_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Cdouble), gr.handle.ptr, "schedule",
+                schedule == :jacobi ? 0.0 : 1.0))
+    return gr
+end
+
+# ---- 3-D structured grid: grid(c0, c1, nnods) src/StructuredGrid.jl:35-45, nodal_incidence :177-223 (implicit here),
+# BFM(G, source, gr, U, fw) src/Dijsktra.jl:294-343 with the weight of src/SSSP/weights.jl:20
+mutable struct Grid3D
+    c0::NTuple{3,Float64}
+    c1::NTuple{3,Float64}
+    nnods::NTuple{3,Int64}
+    neighbour_levels::Int
+    handle::MeshHandle
+end
+Base.length(gr::Grid3D) = prod(gr.nnods)
+
+function grid(c0, c1, nnods; neighbour_levels = 1, coord_system = :cartesian)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    a, b, nn = Float64[c0...], Float64[c1...], Int64[nnods...]
+    check(ccall((:rt_grid3d_build, LIB), Cint, (Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Cint, Cint, Ref{Ptr{Cvoid}}),
+                a, b, nn, neighbour_levels, coord_system == :cartesian ? 0 : 1, out))
+    return Grid3D((a...,), (b...,), (nn...,), neighbour_levels, MeshHandle(out[]))
+end
+
+# Cartesian node coordinates (x fastest), what gr[I] of the reference evaluates lazily
+function coordinates(gr::Grid3D)
+    n = length(gr)
+    X, Y, Z = zeros(n), zeros(n), zeros(n)
+    check(ccall((:rt_grid3d_export, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                gr.handle.ptr, X, Y, Z))
+    return X, Y, Z
+end
+
+function BFM(gr::Grid3D, source::Integer, U::AbstractVector; precision::Integer = 64)
+    n = length(gr)
+    dist = Vector{Float64}(undef, n)
+    prev = Vector{Int64}(undef, n)
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0))
+    check(ccall((:rt_bfm_solve, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
+                gr.handle.ptr, Vector{Float64}(U), Int64[source], 1, precision, dist, prev, st))
+    return BellmanFordMoore(prev, dist)
 end
 
 # recontruct_path(prev, source, receiver) -- src/SSSP/ssspm.jl:30-40 (the misspelling is the reference's API)
