@@ -533,6 +533,7 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
 // of the released sources (warp-private smem slab) and walks the elements e, e + PUSH_GE, ... of the column with the
 // software-pipelined target loop.  (The CTA-level variant above spends a third of its stall time in __syncthreads.)
 constexpr int PUSH_GE = 16;
+constexpr int FAR_EVERY = 3;  // the threshold-advance kernels are enqueued every FAR_EVERY-th round
 #ifndef RT_PUSH_SPLIT
 #define RT_PUSH_SPLIT 32
 #endif
@@ -949,11 +950,15 @@ __global__ void prev_halo_init_kernel(PP pb, const i32* __restrict__ hnode, cons
 // ---------------------------------------------------------------------------------------------------------
 // Device-controlled rounds: the host enqueues a fixed sequence of launches per round and only synchronises every
 // `check_every` rounds; which phase runs (push / threshold advance / nothing) is decided on the device.
-__global__ void round_begin_kernel(PP pb) {
+// after_far: the far kernels were enqueued between the previous round_begin and this one.  They are only enqueued
+// every FAR_EVERY-th round (in most rounds they have nothing to do), so a source whose threshold advance has been
+// requested (mode 2) stays put -- prep / push return at once -- until a round_begin that follows them.
+__global__ void round_begin_kernel(PP pb, int after_far) {
   if ((int)threadIdx.x >= pb.nb) return;
   const PP p = pp_view(pb, threadIdx.x);
   int* c = p.ctl;
   if (c[3]) return;
+  if (c[2] == 2 && !after_far) return;
   if (c[2] == 1)
     c[0] ^= 1;
   else if (c[2] == 2)
@@ -1456,13 +1461,25 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
       const unsigned gsmall = (unsigned)(sm_count * 2);
       const unsigned gpush = (unsigned)std::max<i64>(sm_count, max_blocks / B);
       bool all_done = false;
+      int after_far = 1;  // nothing is pending before the first round
+      i64 enq_rounds = 0;
       while (!all_done) {
         for (int r = 0; r < R; ++r) {
-          round_begin_kernel<<<1, 32, 0, s>>>(p);
+          round_begin_kernel<<<1, 32, 0, s>>>(p, after_far);
           prep_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
           launch_push_dc(p.warp_units != 0, mode, dim3(gpush, B), s, p);
-          far_min_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
-          far_release_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
+          after_far = 0;
+          if (r % FAR_EVERY == FAR_EVERY - 1 || r == R - 1) {
+            far_min_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
+            far_release_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
+            after_far = 1;
+          }
+        }
+        enq_rounds += R;
+        if (enq_rounds > ((i64)1 << 26)) {  // a solve needs ~1e4 rounds: never spin forever on a logic error
+          rt_set_error("near-far schedule did not converge within %lld rounds", (long long)enq_rounds);
+          rc = RT_ERR_CUDA;
+          break;
         }
         cudaMemcpyAsync(hctl.data(), m.ctl.p, (size_t)B * 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
         if (cudaStreamSynchronize(s) != cudaSuccess) {

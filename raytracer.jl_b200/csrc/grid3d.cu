@@ -525,9 +525,13 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
   if (lane == 0 && evals) atomicAdd(&p.counters[2], evals);
 }
 
-__global__ void round_begin3_kernel(Q3 p) {
+// after_far: the far kernels were enqueued since the previous round_begin (they only are every FAR3_EVERY-th
+// round); a requested threshold advance (mode 2) waits for them, prep / push return at once meanwhile
+constexpr int FAR3_EVERY = 3;
+__global__ void round_begin3_kernel(Q3 p, int after_far) {
   int* c = p.ctl;
   if (c[3]) return;
+  if (c[2] == 2 && !after_far) return;
   if (c[2] == 1)
     c[0] ^= 1;
   else if (c[2] == 2)
@@ -802,9 +806,11 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     st.total_launches += 1;
     int hctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int R = timers ? 1 : (h->opts.check_every > 1 ? h->opts.check_every : 32);
+    int after_far = 1;
+    i64 enq_rounds = 0;
     while (!hctl[3]) {
       for (int r = 0; r < R; ++r) {
-        round_begin3_kernel<<<1, 1, 0, s>>>(p);
+        round_begin3_kernel<<<1, 1, 0, s>>>(p, after_far);
         prep3_kernel<<<gsmall, 256, 0, s>>>(p);
         if (timers) cudaEventRecord(evr0, s);
         if (f32)
@@ -812,8 +818,17 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
         else
           push3d_kernel<false><<<gbig, P3_BLOCK, 0, s>>>(p);
         if (timers) cudaEventRecord(evr1, s);
-        far_min3_kernel<<<gsmall, 256, 0, s>>>(p);
-        far_release3_kernel<<<gsmall, 256, 0, s>>>(p);
+        after_far = 0;
+        if (r % FAR3_EVERY == FAR3_EVERY - 1 || r == R - 1) {
+          far_min3_kernel<<<gsmall, 256, 0, s>>>(p);
+          far_release3_kernel<<<gsmall, 256, 0, s>>>(p);
+          after_far = 1;
+        }
+      }
+      enq_rounds += R;
+      if (enq_rounds > ((i64)1 << 26)) {  // never spin forever on a logic error
+        rc = RT_ERR_CUDA;
+        break;
       }
       cudaMemcpyAsync(hctl, g.ctl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
       if (cudaStreamSynchronize(s) != cudaSuccess) {
