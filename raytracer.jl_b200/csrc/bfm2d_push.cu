@@ -1476,7 +1476,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
           }
         }
         enq_rounds += R;
-        if (enq_rounds > ((i64)1 << 26)) {  // a solve needs ~1e4 rounds: never spin forever on a logic error
+        if (enq_rounds > ((i64)1 << 22)) {  // a solve needs 1e3 - 1e5 rounds: never spin forever on a logic error
           rt_set_error("near-far schedule did not converge within %lld rounds", (long long)enq_rounds);
           rc = RT_ERR_CUDA;
           break;

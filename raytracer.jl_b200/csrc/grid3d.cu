@@ -826,7 +826,7 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
         }
       }
       enq_rounds += R;
-      if (enq_rounds > ((i64)1 << 26)) {  // never spin forever on a logic error
+      if (enq_rounds > ((i64)1 << 22)) {  // a solve needs 1e2 - 1e4 rounds: never spin forever on a logic error
         rc = RT_ERR_CUDA;
         break;
       }
