@@ -1468,10 +1468,12 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
           round_begin_kernel<<<1, 32, 0, s>>>(p, after_far);
           prep_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
           launch_push_dc(p.warp_units != 0, mode, dim3(gpush, B), s, p);
+          st.total_launches += 3;
           after_far = 0;
           if (r % FAR_EVERY == FAR_EVERY - 1 || r == R - 1) {
             far_min_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
             far_release_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
+            st.total_launches += 2;
             after_far = 1;
           }
         }
@@ -1546,8 +1548,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
     if (!timers)
       for (int b = 0; b < B; ++b) {
         rounds = std::max<i64>(rounds, hctl[b * 8 + 4]);
-        st.relax_launches += hctl[b * 8 + 5];
-        st.total_launches += 2 * (i64)hctl[b * 8 + 4];
+        st.relax_launches += hctl[b * 8 + 5];  // push rounds that had work (total_launches counts what was enqueued)
       }
     st.sweeps += rounds;
     for (int b = 0; b < B; ++b) {

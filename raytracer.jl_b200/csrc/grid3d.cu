@@ -818,10 +818,12 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
         else
           push3d_kernel<false><<<gbig, P3_BLOCK, 0, s>>>(p);
         if (timers) cudaEventRecord(evr1, s);
+        st.total_launches += 3;
         after_far = 0;
         if (r % FAR3_EVERY == FAR3_EVERY - 1 || r == R - 1) {
           far_min3_kernel<<<gsmall, 256, 0, s>>>(p);
           far_release3_kernel<<<gsmall, 256, 0, s>>>(p);
+          st.total_launches += 2;
           after_far = 1;
         }
       }
@@ -844,7 +846,7 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
     if (rc != RT_OK) break;
     st.sweeps += hctl[4];
     st.relax_launches += hctl[5];
-    st.total_launches += 2 * (i64)hctl[4];
+
     cudaEventRecord(evr0, s);
     if (f32)
       prev_tight3_kernel<true><<<grid_for(n, 128), 128, 0, s>>>(p, n, src);
