@@ -54,3 +54,24 @@ def test_velocity_profile_table(rt):
     assert len(p.r) == 6372 and p.r[0] == 0.0 and p.r[-1] == 6371.0
     assert p.Vp[-1] == 5.8 and p.Vp[0] == 11.2409  # surface / centre of AK135
     assert np.all(np.diff(p.r) == 1.0)
+
+
+def test_binary_is_sm100a_and_carries_the_expected_instructions(rt):
+    """The shipped library holds sm_100a machine code only, the packed (time, predecessor) update is the 128-bit
+    compare-and-swap the design relies on, the value path is plain fp64 (no tensor-core instructions: min-plus with
+    sqrt/div has no MMA form), and the exact path is not contracted (FMAs come from the conservative screen only)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elfs = subprocess.run([cuobjdump, "-lelf", rt.SO_PATH], capture_output=True, text=True).stdout
+    names = re.findall(r"ELF file\s+\d+:\s+(\S+)", elfs)
+    assert names and all(".sm_100a." in nme for nme in names), names
+    sass = subprocess.run([cuobjdump, "-sass", rt.SO_PATH], capture_output=True, text=True).stdout
+    assert "ATOMG.E.CAS.128" in sass          # dp_cas in bfm2d_push.cu
+    assert "DSETP" in sass and "DADD" in sass and "MUFU.RSQ64H" in sass  # fp64 compare / add / sqrt seed
+    assert not re.search(r"\b(HMMA|IMMA|DMMA|UTCHMMA|UTCIMMA|QMMA)\b", sass)
+    for kernel in ("relax2d_kernel", "push2d_dc_kernel", "nearfar_persistent_kernel", "relax3d_kernel",
+                   "push3d_kernel", "closest_pass1_kernel", "interp_kernel", "path_fill_kernel"):
+        assert kernel in sass, kernel
