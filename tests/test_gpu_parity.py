@@ -850,3 +850,36 @@ def test_bfm_multi_replicas(rt, O, annulus, ak135):
     D3 = rt.bfm_multi(gs, [1, gs[0].n, 17], U3, schedule="near-far")
     for k, s in enumerate((1, gs[0].n, 17)):
         assert np.array_equal(D3.dist[k], O.bfm3d(nn, 1, X, Y, Z, U3, s)[0])
+
+
+# ------------------------------------------------------------------ every solver option of the near-far schedule
+def test_near_far_option_matrix(rt, O, annulus, ak135):
+    """rt_set_option switches between equivalent execution strategies of the near-far schedule (persistent kernel /
+    launch sequence / host-driven rounds with timers, warp-per-item / warp-per-(item, element) / CTA units, packed
+    128-bit pairs / separate tightness pass, batch width, bucket width).  Travel times must be bit-identical to the
+    oracle under every combination, predecessors tie-aware tight."""
+    m = annulus(36, 10, 100.0)
+    gr, G, halo = adopt(rt, m)
+    h = rt.mesh_from_arrays(gr, G, halo)
+    Vp = O.interp_velocity(ak135[0], ak135[1], m.r)
+    srcs = [O.closest_point(m.theta, m.r, 0.0, R), m.n // 2, 5]
+    want = [O.bfm(m, Vp, s) for s in srcs]
+    defaults = dict(profile_timers=0, check_every=0, cta_units=0, warp_units=-1, batch=0, packed_prev=1, persistent=-1,
+                    delta_factor=0.0)
+    combos = [dict(persistent=1, warp_units=1), dict(persistent=1, warp_units=0), dict(persistent=0, warp_units=1),
+              dict(persistent=0, warp_units=0), dict(persistent=0, warp_units=0, check_every=4),
+              dict(persistent=0, warp_units=0, cta_units=1), dict(profile_timers=1, warp_units=0),
+              dict(profile_timers=1, warp_units=1), dict(packed_prev=0), dict(packed_prev=0, persistent=0),
+              dict(batch=2), dict(batch=1), dict(delta_factor=0.25), dict(delta_factor=16.0)]
+    try:
+        for combo in combos:
+            for k, v in {**defaults, **combo}.items():
+                h.set_option(k, v)
+            D = rt.bfm(G, halo, srcs, gr, Vp, schedule="near-far")
+            for k, s in enumerate(srcs):
+                assert np.array_equal(D.dist[k], want[k][0]), "options %s, source %d" % (combo, s)
+                check_prev_tie_aware(m, Vp, int(s), want[k][0], D.prev[k], want[k][1])
+    finally:
+        for k, v in defaults.items():
+            h.set_option(k, v)
+        h.set_option("schedule", 0)
