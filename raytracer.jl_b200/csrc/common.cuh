@@ -77,13 +77,9 @@ struct DevBuf {
   }
 };
 
+#include "screen.h"
+
 #if defined(__CUDACC__)
-// Algebraic screen (no sqrt, no division): is  d_from + w  >= bound  guaranteed, where the edge weight is
-// w = 2*sqrt(d2)/ssum (2-D: (2.0*len)/(Ui+Uj); 3-D: len*(1/|Ui+Uj|)*2, both within 3 roundings of the real value)?
-//   w >= t  <=>  d2 >= (t*ssum/2)^2   with t = bound - d_from.
-// Slack: 4e-15*bound absorbs the rounding of (bound - d_from) and of the final fl(d_from + w); the factor
-// (1 + 1e-9) absorbs the roundings of the products and of w itself.  A `true` answer is exact-safe: the
-// candidate can be skipped without changing any result; `false` means "evaluate exactly".
 // ---- Float32 mode (precision = 32; the reference's Float32 path src/SSSP/bfm_gpu.jl:170-205, 487-526).  Values stay
 // in fp64 storage but every arithmetic result is rounded to Float32: for +, -, *, / and sqrt of Float32 operands,
 // rounding the correctly rounded fp64 result to Float32 equals the correctly rounded Float32 result (53 >= 2*24 + 2,
@@ -92,38 +88,6 @@ template <bool F32>
 __device__ __forceinline__ double rnd(double v) {
   if constexpr (F32) return (double)__double2float_rn(v);
   return v;
-}
-// F32 slacks: (bound - d_from) is exact up to fp64 rounding, the final fl32(d_from + w) moves by <= 6e-8 relative, and
-// the Float32 weight differs from the real one by < 4 roundings of 6e-8 (d2 and ssum below are the fp64 values).
-// Callers guarantee d_from < bound (so t > 0; bound = Inf gives ts = Inf and never skips).  The screen itself is free
-// to contract (explicit FMAs): it only has to be conservative, not bit-reproducible.
-template <bool F32>
-__device__ __forceinline__ bool screen_cannot_improve_t(double bound, double d_from, double d2, double ssum) {
-  const double tt = __fma_rn(bound, F32 ? 1.3e-7 : 4e-15, bound - d_from);
-  const double ts = tt * ssum;
-  return (d2 > ts * ts * (F32 ? 0.25 * (1.0 + 2e-6) : 0.25 * (1.0 + 1e-9))) && (ssum > 0.0);
-}
-__device__ __forceinline__ bool screen_cannot_improve(double bound, double d_from, double d2, double ssum) {
-  return screen_cannot_improve_t<false>(bound, d_from, d2, ssum);
-}
-// Can fl(d_from + w) == target hold?  false => certainly not tight.
-template <bool F32>
-__device__ __forceinline__ bool screen_maybe_tight_t(double target, double d_from, double d2, double ssum) {
-  const double t = target - d_from;
-  if (!(t >= 0.0)) return false;
-  if (!(ssum > 0.0)) return true;
-  const double slack = target * (F32 ? 1.3e-7 : 4e-15);
-  const double hi = (t + slack) * ssum * 0.5;
-  if (d2 > hi * hi * (F32 ? 1.0 + 2e-6 : 1.0 + 1e-9)) return false;
-  const double tl = t - slack;
-  if (tl > 0.0) {
-    const double lo = tl * ssum * 0.5;
-    if (d2 < lo * lo * (F32 ? 1.0 - 2e-6 : 1.0 - 1e-9)) return false;
-  }
-  return true;
-}
-__device__ __forceinline__ bool screen_maybe_tight(double target, double d_from, double d2, double ssum) {
-  return screen_maybe_tight_t<false>(target, d_from, d2, ssum);
 }
 #endif
 

@@ -1,0 +1,73 @@
+// screen_driver.cpp -- TEST INFRASTRUCTURE: evaluates the algebraic screen of raytracer.jl_b200/csrc/screen.h (the very
+// functions the kernels inline) next to the exact candidate value in the reference's operation order, so that
+// tests/test_screen.py can check on the CPU that a "skip" can never change a result.  Build with -ffp-contract=off.
+#include <cmath>
+
+#include "../raytracer.jl_b200/csrc/screen.h"
+
+namespace {
+// exact candidate, 2-D: dj + (2*sqrt(dx^2 + dz^2)) / (Ui + Uj)   (bfm.jl:186); T = float is genuine Float32 arithmetic
+template <typename T>
+T cand2(T dj, T xi, T zi, T Ui, T xj, T zj, T Uj) {
+  T dx = xi - xj, dz = zi - zj;
+  T d2 = dx * dx + dz * dz;
+  T len2 = T(2) * std::sqrt(d2);
+  T w = len2 / (Ui + Uj);
+  return dj + w;
+}
+// exact candidate, 3-D: dj + sqrt(dx^2 + dy^2 + dz^2) * (1 / |Ui + Uj|) * 2   (weights.jl:20)
+template <typename T>
+T cand3(T dj, T xi, T yi, T zi, T Ui, T xj, T yj, T zj, T Uj) {
+  T dx = xi - xj, dy = yi - yj, dz = zi - zj;
+  T d = std::sqrt(dx * dx + dy * dy + dz * dz);
+  T w = d * (T(1) / std::fabs(Ui + Uj)) * T(2);
+  return dj + w;
+}
+}  // namespace
+
+extern "C" {
+
+// in: 9 arrays of n doubles (Float32 mode: values must be Float32 numbers); out: skip flags, tight flags (for
+// target[i]), exact candidate values
+void screen2d_batch(long n, int f32, const double* bound, const double* dj, const double* xi, const double* zi,
+                    const double* Ui, const double* xj, const double* zj, const double* Uj, const double* target,
+                    unsigned char* skip, unsigned char* maybe_tight, double* delta) {
+  for (long i = 0; i < n; ++i) {
+    // what the kernels pass: fp64 differences of the (possibly Float32-valued) inputs, FMA'd square sum
+    const double dx = xi[i] - xj[i], dz = zi[i] - zj[i];
+    const double d2 = rt_fma(dx, dx, dz * dz);
+    const double ssum = Ui[i] + Uj[i];
+    if (f32) {
+      skip[i] = screen_cannot_improve_t<true>(bound[i], dj[i], d2, ssum);
+      maybe_tight[i] = screen_maybe_tight_t<true>(target[i], dj[i], d2, ssum);
+      delta[i] = (double)cand2<float>((float)dj[i], (float)xi[i], (float)zi[i], (float)Ui[i], (float)xj[i],
+                                      (float)zj[i], (float)Uj[i]);
+    } else {
+      skip[i] = screen_cannot_improve_t<false>(bound[i], dj[i], d2, ssum);
+      maybe_tight[i] = screen_maybe_tight_t<false>(target[i], dj[i], d2, ssum);
+      delta[i] = cand2<double>(dj[i], xi[i], zi[i], Ui[i], xj[i], zj[i], Uj[i]);
+    }
+  }
+}
+
+void screen3d_batch(long n, int f32, const double* bound, const double* dj, const double* xi, const double* yi,
+                    const double* zi, const double* Ui, const double* xj, const double* yj, const double* zj,
+                    const double* Uj, const double* target, unsigned char* skip, unsigned char* maybe_tight,
+                    double* delta) {
+  for (long i = 0; i < n; ++i) {
+    const double dx = xi[i] - xj[i], dy = yi[i] - yj[i], dz = zi[i] - zj[i];
+    const double d2 = rt_fma(dx, dx, rt_fma(dy, dy, dz * dz));
+    const double ssum = std::fabs(Ui[i] + Uj[i]);
+    if (f32) {
+      skip[i] = screen_cannot_improve_t<true>(bound[i], dj[i], d2, ssum);
+      maybe_tight[i] = screen_maybe_tight_t<true>(target[i], dj[i], d2, ssum);
+      delta[i] = (double)cand3<float>((float)dj[i], (float)xi[i], (float)yi[i], (float)zi[i], (float)Ui[i],
+                                      (float)xj[i], (float)yj[i], (float)zj[i], (float)Uj[i]);
+    } else {
+      skip[i] = screen_cannot_improve_t<false>(bound[i], dj[i], d2, ssum);
+      maybe_tight[i] = screen_maybe_tight_t<false>(target[i], dj[i], d2, ssum);
+      delta[i] = cand3<double>(dj[i], xi[i], yi[i], zi[i], Ui[i], xj[i], yj[i], zj[i], Uj[i]);
+    }
+  }
+}
+}

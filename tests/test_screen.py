@@ -1,0 +1,103 @@
+"""Safety of the algebraic screen (raytracer.jl_b200/csrc/screen.h, inlined by every relax / push / tightness kernel):
+whenever it answers "skip", the exact candidate -- evaluated in the reference's operation order, in Float64 or in
+genuine Float32 arithmetic -- is >= the incumbent, i.e. skipping cannot change a result; whenever a candidate is
+bit-exactly tight, `maybe_tight` is true.  Inputs are adversarial: incumbents within a few ulp of the candidate."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+F64P = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+U8P = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def drv():
+    so = os.path.join(HERE, "libscreen_test.so")
+    src = os.path.join(HERE, "screen_driver.cpp")
+    hdr = os.path.join(HERE, "..", "raytracer.jl_b200", "csrc", "screen.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so,
+                               src])
+    L = C.CDLL(so)
+    L.screen2d_batch.argtypes = [C.c_long, C.c_int] + [F64P] * 9 + [U8P, U8P, F64P]
+    L.screen3d_batch.argtypes = [C.c_long, C.c_int] + [F64P] * 11 + [U8P, U8P, F64P]
+    return L
+
+
+def nextafter_k(a, k, dtype):
+    """a moved by k units in the last place of `dtype` (k may be negative)."""
+    b = a.astype(dtype)
+    step = np.where(k > 0, np.inf, -np.inf).astype(dtype)
+    for _ in range(int(np.max(np.abs(k)))):
+        mv = np.abs(k) > 0
+        b = np.where(mv, np.nextafter(b, step), b)
+        k = k - np.sign(k) * mv
+    return b.astype(np.float64)
+
+
+def cases(rng, n, dim, f32):
+    r = lambda a: a.astype(np.float32).astype(np.float64) if f32 else a
+    base = rng.uniform(-6371.0, 6371.0, (dim, n))
+    # neighbour offsets from 1e-3 km (secondary nodes at fine spacing) to 300 km, plus exact coincidences
+    scale = 10.0 ** rng.uniform(-3.0, 2.5, n)
+    off = rng.normal(size=(dim, n)) * scale
+    off[:, rng.random(n) < 0.02] = 0.0
+    pi = [r(base[k]) for k in range(dim)]
+    pj = [r(base[k] + off[k]) for k in range(dim)]
+    Ui, Uj = r(rng.uniform(1.0, 14.0, n)), r(rng.uniform(1.0, 14.0, n))
+    dj = r(np.where(rng.random(n) < 0.05, 0.0, rng.uniform(0.0, 2500.0, n)))
+    return pi, pj, Ui, Uj, dj
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("f32", [0, 1])
+def test_screen_is_exact_safe(drv, dim, f32):
+    rng = np.random.default_rng(20261018 + 10 * dim + f32)
+    n = 400000
+    pi, pj, Ui, Uj, dj = cases(rng, n, dim, bool(f32))
+    dtype = np.float32 if f32 else np.float64
+    skip, tight, delta = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n)
+
+    def run(bound, target):
+        args = [np.ascontiguousarray(bound), dj] + pi + [Ui] + pj + [Uj, np.ascontiguousarray(target)]
+        (drv.screen2d_batch if dim == 2 else drv.screen3d_batch)(n, f32, *args, skip, tight, delta)
+
+    run(np.full(n, np.inf), np.zeros(n))  # first pass: the exact candidate values
+    d0 = delta.copy()
+    assert not skip.any()  # an unreached target (incumbent Inf) is never skipped
+    # independent numpy evaluation of the exact candidate (same operation order, numpy never contracts)
+    P, Q = [a.astype(dtype) for a in pi], [a.astype(dtype) for a in pj]
+    s = sum((a - b) * (a - b) for a, b in zip(P, Q)) if dim == 3 else (P[0] - Q[0]) * (P[0] - Q[0]) + (P[1] - Q[1]) * (P[1] - Q[1])
+    if dim == 2:
+        want = dj.astype(dtype) + dtype(2) * np.sqrt(s) / (Ui.astype(dtype) + Uj.astype(dtype))
+    else:
+        want = dj.astype(dtype) + np.sqrt(s) * (dtype(1) / np.abs(Ui.astype(dtype) + Uj.astype(dtype))) * dtype(2)
+    assert np.array_equal(want.astype(np.float64), d0)
+    checked = skipped = 0
+    for trial in range(6):
+        if trial < 4:   # incumbents within +-40 ulp of the candidate: the adversarial band
+            k = rng.integers(-40, 41, n)
+            bound = nextafter_k(d0, k, dtype)
+        elif trial == 4:  # incumbents a little further away
+            bound = (d0 * (1.0 + rng.normal(size=n) * (3e-6 if f32 else 3e-9))).astype(dtype).astype(np.float64)
+        else:  # anything
+            bound = (dj + (d0 - dj) * rng.uniform(0.0, 3.0, n)).astype(dtype).astype(np.float64)
+        ok = dj < bound  # the callers' precondition
+        run(bound, d0)
+        bad = ok & (skip != 0) & ~(d0 >= bound)
+        assert not bad.any(), "unsafe skip at %s" % np.nonzero(bad)[0][:5]
+        assert np.all(tight[np.isfinite(d0)] != 0)  # target == candidate: must never be ruled out
+        checked += int(ok.sum())
+        skipped += int((ok & (skip != 0)).sum())
+        if trial == 5:  # sharpness: clearly losing candidates are skipped, clearly non-tight ones ruled out
+            margin = 1e-4 if f32 else 1e-7
+            lose = ok & (d0 > bound * (1.0 + margin)) & (d0 - dj > 1e-9)
+            assert (skip[lose] != 0).mean() > 0.999
+            run(bound, np.where(d0 > dj, dj + (d0 - dj) * 0.5, d0))  # a target half a weight below the candidate
+            far = ok & (d0 - dj > (1e-3 if f32 else 1e-6) * np.maximum(d0, 1.0))
+            assert (tight[far] == 0).mean() > 0.999
+    assert checked > n and skipped > 0
