@@ -45,16 +45,11 @@ struct P2 {
 };
 
 // dGi + 2.0 * sqrt(0 + dx*dx + dz*dz) / (Ui + Uj)   (bfm.jl:186, GridAnnulus.jl:808-815), no contraction
-// F32: the Float32 relax of src/SSSP/bfm_gpu.jl:487-526 (every operation rounded to Float32, see rnd<> in common.cuh)
+// exact_cand2<F32> (exact.h); F32 = the Float32 relax of src/SSSP/bfm_gpu.jl:487-526
 template <bool F32>
 __device__ __forceinline__ double cand_delta(double dj, double xi, double zi, double Ui, double xj, double zj,
                                              double Uj) {
-  const double dx = rnd<F32>(__dsub_rn(xi, xj));
-  const double dz = rnd<F32>(__dsub_rn(zi, zj));
-  const double d2 = rnd<F32>(__dadd_rn(rnd<F32>(__dmul_rn(dx, dx)), rnd<F32>(__dmul_rn(dz, dz))));
-  const double len2 = __dmul_rn(2.0, rnd<F32>(__dsqrt_rn(d2)));
-  const double w = rnd<F32>(__ddiv_rn(len2, rnd<F32>(__dadd_rn(Ui, Uj))));
-  return rnd<F32>(__dadd_rn(dj, w));
+  return exact_cand2<F32>(dj, xi, zi, Ui, xj, zj, Uj);
 }
 
 // One warp per active work item.  DUAL: the velocity pair of an edge is chosen by the radial order of its ends

@@ -97,15 +97,11 @@ __device__ __forceinline__ PP pp_view(const PP& p, int b) {
   return v;
 }
 
-// F32: every operation rounded to Float32 (bfm_gpu.jl:487-526; rnd<> in common.cuh)
+// exact_cand2<F32> (exact.h); F32: every operation rounded to Float32 (bfm_gpu.jl:487-526)
 template <bool F32 = false>
 __device__ __forceinline__ double edge_delta(double di, double xi, double zi, double Ui, double xj, double zj,
                                              double Uj) {
-  const double dx = rnd<F32>(__dsub_rn(xi, xj));
-  const double dz = rnd<F32>(__dsub_rn(zi, zj));
-  const double d2 = rnd<F32>(__dadd_rn(rnd<F32>(__dmul_rn(dx, dx)), rnd<F32>(__dmul_rn(dz, dz))));
-  const double len2 = __dmul_rn(2.0, rnd<F32>(__dsqrt_rn(d2)));
-  return rnd<F32>(__dadd_rn(di, rnd<F32>(__ddiv_rn(len2, rnd<F32>(__dadd_rn(Ui, Uj))))));
+  return exact_cand2<F32>(di, xi, zi, Ui, xj, zj, Uj);
 }
 // relax modes of the push kernels: plain fp64, dual velocity (bfm.jl:113-159), Float32 arithmetic
 constexpr int MODE_F64 = 0, MODE_DUAL = 1, MODE_F32 = 2;

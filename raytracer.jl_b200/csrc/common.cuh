@@ -77,19 +77,7 @@ struct DevBuf {
   }
 };
 
-#include "screen.h"
-
-#if defined(__CUDACC__)
-// ---- Float32 mode (precision = 32; the reference's Float32 path src/SSSP/bfm_gpu.jl:170-205, 487-526).  Values stay
-// in fp64 storage but every arithmetic result is rounded to Float32: for +, -, *, / and sqrt of Float32 operands,
-// rounding the correctly rounded fp64 result to Float32 equals the correctly rounded Float32 result (53 >= 2*24 + 2,
-// double rounding is innocuous), so the travel times are bit-identical to genuine Float32 arithmetic.
-template <bool F32>
-__device__ __forceinline__ double rnd(double v) {
-  if constexpr (F32) return (double)__double2float_rn(v);
-  return v;
-}
-#endif
+#include "exact.h"  // exact candidate values + the Float32 rounding helper; pulls in screen.h
 
 #include "fastdiv.h"
 

@@ -100,17 +100,11 @@ __global__ void coords3d_kernel(double c0x, double c0y, double c0z, double c1x, 
 }
 
 // dist0[J] + distance3D(pI,pJ) * (1/abs(UI+UJ)) * 2   (weights.jl:20, StructuredGrid.jl:239-241)
-// F32: the same expression with every operation rounded to Float32 (precision = 32; rnd<> in common.cuh)
+// exact_cand3<F32> (exact.h); F32: every operation rounded to Float32 (precision = 32)
 template <bool F32 = false>
 __device__ __forceinline__ double cand3(double dj, double xi, double yi, double zi, double ui, double xj,
                                         double yj, double zj, double uj) {
-  const double dx = rnd<F32>(__dsub_rn(xi, xj)), dy = rnd<F32>(__dsub_rn(yi, yj)), dz = rnd<F32>(__dsub_rn(zi, zj));
-  const double s = rnd<F32>(__dadd_rn(rnd<F32>(__dadd_rn(rnd<F32>(__dmul_rn(dx, dx)), rnd<F32>(__dmul_rn(dy, dy)))),
-                                      rnd<F32>(__dmul_rn(dz, dz))));
-  const double d = rnd<F32>(__dsqrt_rn(s));
-  const double rcp = rnd<F32>(__drcp_rn(fabs(rnd<F32>(__dadd_rn(ui, uj)))));
-  const double wgt = __dmul_rn(rnd<F32>(__dmul_rn(d, rcp)), 2.0);
-  return rnd<F32>(__dadd_rn(dj, wgt));
+  return exact_cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj);
 }
 
 // One CTA per active tile; dynamic smem = 5 * SX*SY*SZ doubles.

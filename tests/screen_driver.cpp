@@ -1,9 +1,11 @@
-// screen_driver.cpp -- TEST INFRASTRUCTURE: evaluates the algebraic screen of raytracer.jl_b200/csrc/screen.h (the very
-// functions the kernels inline) next to the exact candidate value in the reference's operation order, so that
-// tests/test_screen.py can check on the CPU that a "skip" can never change a result.  Build with -ffp-contract=off.
+// screen_driver.cpp -- TEST INFRASTRUCTURE: evaluates the algebraic screen (raytracer.jl_b200/csrc/screen.h) and the exact
+// candidate expression (exact.h) -- the very functions the kernels inline -- next to the candidate value in the
+// reference's operation order computed in plain `double` / genuine `float` arithmetic, so that tests/test_screen.py can
+// check on the CPU that a "skip" can never change a result and that the fp64-with-rounding emulation of Float32 is
+// exact.  Build with -ffp-contract=off.
 #include <cmath>
 
-#include "../raytracer.jl_b200/csrc/screen.h"
+#include "../raytracer.jl_b200/csrc/exact.h"  // pulls in screen.h
 
 namespace {
 // exact candidate, 2-D: dj + (2*sqrt(dx^2 + dz^2)) / (Ui + Uj)   (bfm.jl:186); T = float is genuine Float32 arithmetic
@@ -31,8 +33,10 @@ extern "C" {
 // target[i]), exact candidate values
 void screen2d_batch(long n, int f32, const double* bound, const double* dj, const double* xi, const double* zi,
                     const double* Ui, const double* xj, const double* zj, const double* Uj, const double* target,
-                    unsigned char* skip, unsigned char* maybe_tight, double* delta) {
+                    unsigned char* skip, unsigned char* maybe_tight, double* delta, double* delta_kernel) {
   for (long i = 0; i < n; ++i) {
+    delta_kernel[i] = f32 ? exact_cand2<true>(dj[i], xi[i], zi[i], Ui[i], xj[i], zj[i], Uj[i])
+                          : exact_cand2<false>(dj[i], xi[i], zi[i], Ui[i], xj[i], zj[i], Uj[i]);
     // what the kernels pass: fp64 differences of the (possibly Float32-valued) inputs, FMA'd square sum
     const double dx = xi[i] - xj[i], dz = zi[i] - zj[i];
     const double d2 = rt_fma(dx, dx, dz * dz);
@@ -53,8 +57,10 @@ void screen2d_batch(long n, int f32, const double* bound, const double* dj, cons
 void screen3d_batch(long n, int f32, const double* bound, const double* dj, const double* xi, const double* yi,
                     const double* zi, const double* Ui, const double* xj, const double* yj, const double* zj,
                     const double* Uj, const double* target, unsigned char* skip, unsigned char* maybe_tight,
-                    double* delta) {
+                    double* delta, double* delta_kernel) {
   for (long i = 0; i < n; ++i) {
+    delta_kernel[i] = f32 ? exact_cand3<true>(dj[i], xi[i], yi[i], zi[i], Ui[i], xj[i], yj[i], zj[i], Uj[i])
+                          : exact_cand3<false>(dj[i], xi[i], yi[i], zi[i], Ui[i], xj[i], yj[i], zj[i], Uj[i]);
     const double dx = xi[i] - xj[i], dy = yi[i] - yj[i], dz = zi[i] - zj[i];
     const double d2 = rt_fma(dx, dx, rt_fma(dy, dy, dz * dz));
     const double ssum = std::fabs(Ui[i] + Uj[i]);

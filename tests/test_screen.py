@@ -1,7 +1,9 @@
-"""Safety of the algebraic screen (raytracer.jl_b200/csrc/screen.h, inlined by every relax / push / tightness kernel):
-whenever it answers "skip", the exact candidate -- evaluated in the reference's operation order, in Float64 or in
-genuine Float32 arithmetic -- is >= the incumbent, i.e. skipping cannot change a result; whenever a candidate is
-bit-exactly tight, `maybe_tight` is true.  Inputs are adversarial: incumbents within a few ulp of the candidate."""
+"""The two header-only pieces every relax / push / tightness kernel inlines, run on the CPU:
+* exact.h -- the exact candidate expression: equals numpy Float64 arithmetic in the reference's operation order, and in
+  Float32 mode (fp64 operations each rounded to Float32) equals genuine `float` arithmetic bit for bit;
+* screen.h -- the algebraic screen: whenever it answers "skip", the exact candidate is >= the incumbent, i.e. skipping
+  cannot change a result; whenever a candidate is bit-exactly tight, `maybe_tight` is true.  Inputs are adversarial:
+  incumbents within a few ulp of the candidate."""
 import ctypes as C
 import os
 import subprocess
@@ -18,13 +20,13 @@ U8P = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 def drv():
     so = os.path.join(HERE, "libscreen_test.so")
     src = os.path.join(HERE, "screen_driver.cpp")
-    hdr = os.path.join(HERE, "..", "raytracer.jl_b200", "csrc", "screen.h")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "raytracer.jl_b200", "csrc", h) for h in ("screen.h", "exact.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so,
                                src])
     L = C.CDLL(so)
-    L.screen2d_batch.argtypes = [C.c_long, C.c_int] + [F64P] * 9 + [U8P, U8P, F64P]
-    L.screen3d_batch.argtypes = [C.c_long, C.c_int] + [F64P] * 11 + [U8P, U8P, F64P]
+    L.screen2d_batch.argtypes = [C.c_long, C.c_int] + [F64P] * 9 + [U8P, U8P, F64P, F64P]
+    L.screen3d_batch.argtypes = [C.c_long, C.c_int] + [F64P] * 11 + [U8P, U8P, F64P, F64P]
     return L
 
 
@@ -60,11 +62,11 @@ def test_screen_is_exact_safe(drv, dim, f32):
     n = 400000
     pi, pj, Ui, Uj, dj = cases(rng, n, dim, bool(f32))
     dtype = np.float32 if f32 else np.float64
-    skip, tight, delta = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n)
+    skip, tight, delta, dker = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n), np.zeros(n)
 
     def run(bound, target):
         args = [np.ascontiguousarray(bound), dj] + pi + [Ui] + pj + [Uj, np.ascontiguousarray(target)]
-        (drv.screen2d_batch if dim == 2 else drv.screen3d_batch)(n, f32, *args, skip, tight, delta)
+        (drv.screen2d_batch if dim == 2 else drv.screen3d_batch)(n, f32, *args, skip, tight, delta, dker)
 
     run(np.full(n, np.inf), np.zeros(n))  # first pass: the exact candidate values
     d0 = delta.copy()
@@ -77,6 +79,9 @@ def test_screen_is_exact_safe(drv, dim, f32):
     else:
         want = dj.astype(dtype) + np.sqrt(s) * (dtype(1) / np.abs(Ui.astype(dtype) + Uj.astype(dtype))) * dtype(2)
     assert np.array_equal(want.astype(np.float64), d0)
+    # the expression the kernels inline (exact.h): Float64 = the reference order; Float32 = exact emulation
+    assert np.array_equal(dker, d0)
+    assert (d0 == dj).sum() > 1000 and np.isfinite(d0).all()  # coincident nodes (zero weight) are in the sample
     checked = skipped = 0
     for trial in range(6):
         if trial < 4:   # incumbents within +-40 ulp of the candidate: the adversarial band
