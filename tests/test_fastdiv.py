@@ -25,3 +25,15 @@ def test_fastdiv_exact():
         for k in (1, 2, 1000, 2 ** 32 // d):                         # around multiples of d
             lo = max(0, k * d - 3)
             assert L.fastdiv_mismatches(d, lo, min(2 ** 32 - 1, k * d + 3), 1) == 0
+
+
+def test_float_row_index_is_exact():
+    """push3d_body (grid3d.cu) splits the flat target index t of a z-plane into (row, column) with
+    r = __float2int_rz((float(t) + 0.5f) * (1.0f / float(ncol))): exact for every size a unit can have
+    (ncol <= 32 + 2w columns, <= 2w + 1 rows, w <= 7)."""
+    import numpy as np
+    for ncol in range(1, 47):
+        rcol = np.float32(1.0) / np.float32(ncol)
+        t = np.arange(0, ncol * 15, dtype=np.int64)
+        r = np.trunc((t.astype(np.float32) + np.float32(0.5)) * rcol).astype(np.int64)
+        assert np.array_equal(r, t // ncol), ncol
