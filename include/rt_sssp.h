@@ -78,11 +78,30 @@ int rt_mesh_from_arrays(int64_t n, int64_t nel, const int64_t* e2n_off, const in
 
 /* ---- 3-D structured grid: grid(c0,c1,nnods) src/StructuredGrid.jl:35-45 + nodal_incidence :177-223 ------- */
 /* coord_system 0: Cartesian axes; 1: axes are (theta, phi, r) mapped through spherical2cart :225-235.
- * star_levels = neighbour_levels (0: 26-neighbourhood; L>=1: clipped (2L+3)^3 window incl. self).
- * Edge weight = distance3D(p1,p2) * (1/abs(U1+U2)) * 2  (src/SSSP/weights.jl:20). */
+ * star_levels = neighbour_levels: 0 = 26-neighbourhood; L >= 1 = the clipped (2*2^L + 1)^3 window incl. self -- every
+ * expansion round of nodal_incidence (:204-212) unions the neighbours' current sets, so the radius doubles per level
+ * (5^3 at L = 1, 9^3 at L = 2).  L = 3 (17^3) returns RT_ERR_UNSUPPORTED.
+ * Edge weight: rt_set_option("weight3d", 0) (default) = distance3D(p1,p2) * (1/abs(U1+U2)) * 2 (src/SSSP/weights.jl:20);
+ * ("weight3d", 1) = fw(a,b) / abs(U[a]+U[b]) * 0.5, the expression inside BFM/foo! (src/Dijsktra.jl:388) and dijsktra
+ * (:44).  The solver's control flow is BFM/foo!/goo! (src/Dijsktra.jl:294-343, 376-403) in both modes. */
 int rt_grid3d_build(const double c0[3], const double c1[3], const int64_t nn[3], int star_levels,
                     int coord_system, rt_mesh** out);
 int rt_grid3d_export(const rt_mesh* m, double* X, double* Y, double* Z); /* Cartesian node coordinates */
+
+/* gr.x, gr.y, gr.z: the nodal ranges collect(LinRange(c0[d], c1[d], nnods[d])) (:38-40); any pointer may be NULL. */
+int rt_grid3d_axes(const rt_mesh* m, double* x, double* y, double* z);
+/* getindex(gr, I) (:77-81) for `count` linear indices (1-based): xyz[count x 3] = Point(gr.x[i], gr.y[j], gr.z[k]),
+ * ijk[count x 3] = CartesianIndex(gr, I) (:90-96).  Either output may be NULL.  (gr[i, j, k] is axes[i], [j], [k].) */
+int rt_grid3d_points(const rt_mesh* m, const int64_t* I, int64_t count, double* xyz, int64_t* ijk);
+/* connectivity(gr) / connectivity(gr, iel) (:121-168): the 8 corner ids of the hexes first_el .. first_el+count-1
+ * (1-based), e2n[count x 8] row-major in the reference's corner order. */
+int rt_grid3d_connectivity(const rt_mesh* m, int64_t first_el, int64_t count, int64_t* e2n);
+/* closest_point(gr, x, y, z) (:257-270) for a batch of query points: first index of the minimum of
+ * distance3D(gr[i], p) on the RAW axis coordinates (the reference does not apply spherical2cart here). */
+int rt_closest_point3d(const rt_mesh* m, const double* px, const double* py, const double* pz, int64_t npts,
+                       int64_t* index_out);
+/* polardistance3D(a, b) (:245-255) for `count` pairs of (theta, phi, r) triples: a, b [count x 3] row-major. */
+int rt_polardistance3d(const double* a, const double* b, int64_t count, double* out);
 
 int rt_mesh_free(rt_mesh* m);
 
@@ -174,6 +193,18 @@ int rt_set_option(rt_mesh* m, const char* key, double value);
  * [receiver, ..., source].  Returns RT_ERR_NOPATH if a chase does not reach `source` within n steps. */
 int rt_reconstruct_paths(const int64_t* prev, int64_t n, int64_t source, const int64_t* receivers, int64_t nrec,
                          int64_t* path_off, int64_t* path_idx, int64_t cap);
+
+/* recontruct_path(D, source, receiver) src/SSSP/ssspm.jl:14-28, the method on the result structs: the chase runs until
+ * a node repeats (`while ipath ∉ path`), then `source` is appended; reading an unset predecessor (the reference:
+ * BoundsError) returns RT_ERR_NOPATH.  Same two-call pattern. */
+int rt_reconstruct_paths_guarded(const int64_t* prev, int64_t n, int64_t source, const int64_t* receivers,
+                                 int64_t nrec, int64_t* path_off, int64_t* path_idx, int64_t cap);
+
+/* travel_times(D, gr, receivers) src/utils.jl:4-8 for a batch of sources: out[nsrc x nrec] = dist[s, receivers[k]]
+ * gathered on the device from [nsrc x n] tables (host table / table resident on the device). */
+int rt_travel_times(const double* dist, int64_t n, int64_t nsrc, const int64_t* receivers, int64_t nrec, double* out);
+int rt_travel_times_dev(const double* dist_dev, int64_t n, int64_t nsrc, const int64_t* receivers, int64_t nrec,
+                        double* out);
 
 /* Same with the predecessor table resident on the device (int32, 0-based, -1 = never set) as written by
  * rt_bfm_solve_dev; receivers / outputs are host arrays with 1-based ids. */

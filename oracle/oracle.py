@@ -58,6 +58,9 @@ def lib():
         L.ora_bfm_dual.argtypes = [I64, I64, I64P, I64P, I64P, I64P, I64P, I64, F64P, F64P, F64P, F64P, F64P, I64, C.c_int,
                                    F64P, I64P, I64P]
         L.ora_dual_velocity.argtypes = [F64P, F64P, I64, F64P, I64, C.c_double, F64P]
+        L.ora_set_weight3d.argtypes = [C.c_int]
+        L.ora_window3d.argtypes = [C.c_int]
+        L.ora_nodal_incidence3d.argtypes = [I64P, C.c_int, I64P, C.c_void_p]
         L.ora_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -208,6 +211,89 @@ def dijkstra3d(nn, star_levels, X, Y, Z, U, source):
     dist = np.zeros(int(np.prod(nn)))
     lib().ora_dijkstra3d(nn, int(star_levels), X, Y, Z, np.ascontiguousarray(U, np.float64), int(source), dist)
     return dist
+
+
+def set_weight3d(mode):
+    """0: src/SSSP/weights.jl:20 (default); 1: the expression inside BFM/foo! src/Dijsktra.jl:388."""
+    lib().ora_set_weight3d(int(mode))
+
+
+def window3d(star_levels):
+    """Half width of the implicit window equivalent to nodal_incidence(gr; neighbour_levels) (2^L)."""
+    return int(lib().ora_window3d(int(star_levels)))
+
+
+def nodal_incidence3d(nn, star_levels):
+    """nodal_incidence(gr; neighbour_levels) src/StructuredGrid.jl:177-223 built literally (hexes -> Dict of Sets ->
+    expansion rounds).  Returns (off[n+1], list ascending per node, 1-based).  Small grids only."""
+    nn = np.asarray(nn, np.int64)
+    n = int(np.prod(nn))
+    off = np.zeros(n + 1, np.int64)
+    lib().ora_nodal_incidence3d(nn, int(star_levels), off, None)
+    lst = np.zeros(int(off[-1]), np.int64)
+    lib().ora_nodal_incidence3d(nn, int(star_levels), off, lst.ctypes.data_as(C.c_void_p))
+    return off, lst
+
+
+def grid3d_axes(c0, c1, nn):
+    """collect(LinRange(c0[d], c1[d], nn[d])) src/StructuredGrid.jl:38-40 (Julia's lerpi: t = j/d; (1-t)*a + t*b)."""
+    out = []
+    for d in range(3):
+        m = int(nn[d])
+        if m == 1:
+            out.append(np.array([float(c0[d])]))
+            continue
+        t = np.arange(m, dtype=np.float64) / float(m - 1)
+        out.append((1.0 - t) * float(c0[d]) + t * float(c1[d]))
+    return out
+
+
+def cartesian_index3d(nn, I):
+    """CartesianIndex(gr, I) src/StructuredGrid.jl:90-96 (1-based)."""
+    nx, nxny = int(nn[0]), int(nn[0]) * int(nn[1])
+    i = (I - 1) % nx + 1
+    k = -(-I // nxny)
+    j = -(-(I - nxny * (k - 1)) // nx)
+    return i, j, k
+
+
+def connectivity3d(nn):
+    """connectivity(gr) src/StructuredGrid.jl:121-168 with cornerindex_ijk :106-112 -> (nel, 8) 1-based."""
+    nx, ny, nz = (int(v) for v in nn)
+    ex, ey, ez = nx - 1, ny - 1, nz - 1
+    iel = np.arange(1, ex * ey * ez + 1, dtype=np.int64)
+    i = (iel - 1) % ex + 1
+    j = (-(-iel // ex) - 1) % ey + 1
+    k = -(-iel // (ex * ey))
+    idx = i + (j - 1) * nx + (k - 1) * nx * ny
+    nxny = nx * ny
+    return np.stack([idx, idx + 1, idx + 1 + nx, idx + nx, idx + nxny, idx + nxny + 1, idx + nxny + 1 + nx,
+                     idx + nxny + nx], axis=1)
+
+
+def closest_point3d(axes, p):
+    """closest_point(gr, x, y, z) src/StructuredGrid.jl:257-270: first linear index (x fastest) of the strict minimum
+    of distance3D(gr[i], p) on the raw axis coordinates; -1 if no distance is < Inf."""
+    ax, ay, az = axes
+    d = np.sqrt((((ax - p[0]) ** 2)[None, None, :] + ((ay - p[1]) ** 2)[None, :, None]) + ((az - p[2]) ** 2)[:, None, None])
+    d = d.reshape(-1)
+    ok = ~np.isnan(d) & (d < np.inf)
+    if not ok.any():
+        return -1
+    return int(np.flatnonzero(ok & (d == d[ok].min()))[0]) + 1
+
+
+def reconstruct_path_struct(prev, source, receiver):
+    """recontruct_path(D, source, receiver) src/SSSP/ssspm.jl:14-28 (the struct method), literally."""
+    path = [int(receiver)]
+    ip = int(prev[receiver - 1])
+    while ip not in path:
+        if ip < 1:
+            raise IndexError("BoundsError: prev[%d]" % ip)
+        path.append(ip)
+        ip = int(prev[ip - 1])
+    path.append(int(source))
+    return np.asarray(path, np.int64)
 
 
 def interpolate_cells(mesh, V):

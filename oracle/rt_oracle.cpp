@@ -22,6 +22,7 @@
 #include <cstring>
 #include <limits>
 #include <queue>
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -712,19 +713,63 @@ void ora_grid3d_coords(const double* c0, const double* c1, const i64* nn, int co
       }
 }
 
-// src/SSSP/weights.jl:20  edge_weight = distance3D(p1,p2) * (1/abs(U1+U2)) * 2 ; distance3D StructuredGrid.jl:239
+// 3-D edge weight, two reference definitions (selected with ora_set_weight3d):
+//   mode 0 (default)  src/SSSP/weights.jl:20   edge_weight = distance3D(p1,p2) * (1/abs(U1+U2)) * 2
+//   mode 1            src/Dijsktra.jl:388 (BFM/foo!) and :44 (dijsktra)   fw(a,b) / abs(U[a] + U[b]) * 0.5, fw = distance3D
+// distance3D: StructuredGrid.jl:239-241.
+static int g_weight3d = 0;
+void ora_set_weight3d(int mode) { g_weight3d = mode ? 1 : 0; }
+// window half width of nodal_incidence(gr; neighbour_levels = L) (StructuredGrid.jl:177-212): level 0 is the
+// 26-neighbourhood (radius 1); every expansion round deep-copies Q and unions Q0[n] for n in Q0[i], so the radius
+// DOUBLES per round: 2^L (5^3 window at L = 1, 9^3 at L = 2, 17^3 at L = 3), self included once L >= 1.
+int ora_window3d(int star_levels) { return 1 << star_levels; }
 extern "C++" {
 template <typename T>
 static inline T cand3d(const T* X, const T* Y, const T* Z, const T* U, T dj, i64 i, i64 j) {
   T dx = X[i] - X[j], dy = Y[i] - Y[j], dz = Z[i] - Z[j];
   T d = std::sqrt(dx * dx + dy * dy + dz * dz);
-  T w = d * (T(1) / std::fabs(U[i] + U[j])) * T(2);
+  T w = g_weight3d ? d / std::fabs(U[i] + U[j]) * T(0.5) : d * (T(1) / std::fabs(U[i] + U[j])) * T(2);
   return dj + w;
 }
 }  // extern "C++"
 
+// nodal_incidence(gr; neighbour_levels) transliterated with the reference's container semantics (Dict of Sets built
+// from the 8-node hexes of connectivity(gr), StructuredGrid.jl:121-168, then `neighbour_levels` rounds of
+// Q0 = deepcopy(Q); union!(Q[i], Q0[n]) for n in Q0[i]).  Only for small grids: pins the implicit window used by the
+// solvers.  Output CSR: off[n+1], list ascending per node (1-based); with list == null only off is written.
+void ora_nodal_incidence3d(const i64* nn, int star_levels, i64* off, i64* list) {
+  const i64 nx = nn[0], ny = nn[1], nz = nn[2], n = nx * ny * nz;
+  std::vector<std::set<i64>> Q(n);
+  for (i64 k = 0; k + 1 < nz; ++k)
+    for (i64 j = 0; j + 1 < ny; ++j)
+      for (i64 i = 0; i + 1 < nx; ++i) {
+        i64 el[8];
+        int c = 0;
+        for (i64 dk = 0; dk < 2; ++dk)
+          for (i64 dj = 0; dj < 2; ++dj)
+            for (i64 di = 0; di < 2; ++di) el[c++] = (i + di) + nx * ((j + dj) + ny * (k + dk));
+        for (int a = 0; a < 8; ++a)
+          for (int b = 0; b < 8; ++b)
+            if (a != b) Q[el[a]].insert(el[b]);
+      }
+  for (int lev = 0; lev < star_levels; ++lev) {
+    const std::vector<std::set<i64>> Q0 = Q;
+    for (i64 i = 0; i < n; ++i)
+      for (i64 m : Q0[i]) Q[i].insert(Q0[m].begin(), Q0[m].end());
+  }
+  i64 o = 0;
+  for (i64 i = 0; i < n; ++i) {
+    off[i] = o;
+    if (list)
+      for (i64 m : Q[i]) list[o++] = m + 1;
+    else
+      o += (i64)Q[i].size();
+  }
+  off[n] = o;
+}
+
 // star-L adjacency of nodal_incidence (StructuredGrid.jl:177-223): L = 0 -> 26-neighbourhood without self;
-// L >= 1 -> clipped (2L+3)^3 window INCLUDING self.  Canonical scan order = ascending linear id (the
+// L >= 1 -> clipped (2*2^L+1)^3 window INCLUDING self (checked against ora_nodal_incidence3d, the literal Dict/Set build).  Canonical scan order = ascending linear id (the
 // reference iterates a Julia Set, whose order is not reproducible).  Control flow = BFM/foo!/goo!
 // (src/Dijsktra.jl:294-343, 376-403).
 extern "C++" {
@@ -733,7 +778,7 @@ static int bfm3d_impl(const i64* nn, int star_levels, const T* X, const T* Y, co
                       int nthreads, i64 max_sweeps, T* dist, i64* prev, i64* stats) {
   const T INF = std::numeric_limits<T>::infinity();
   const i64 nx = nn[0], ny = nn[1], nz = nn[2], n = nx * ny * nz;
-  const i64 w = star_levels + 1;
+  const i64 w = (i64)1 << star_levels;
   const bool self = star_levels >= 1;
   if (source < 1 || source > n) return 1;
 #ifdef _OPENMP
@@ -841,7 +886,7 @@ int ora_bfm3d_f32(const i64* nn, int star_levels, const double* X, const double*
 int ora_dijkstra3d(const i64* nn, int star_levels, const double* X, const double* Y, const double* Z,
                    const double* U, i64 source, double* dist) {
   const i64 nx = nn[0], ny = nn[1], nz = nn[2], n = nx * ny * nz;
-  const i64 w = star_levels + 1;
+  const i64 w = (i64)1 << star_levels;
   for (i64 i = 0; i < n; ++i) dist[i] = INF;
   dist[source - 1] = 0.0;
   typedef std::pair<double, i64> PQE;

@@ -19,6 +19,8 @@ SYMBOLS = [
     "rt_mesh_export", "rt_mesh_from_arrays", "rt_grid3d_build", "rt_grid3d_export", "rt_mesh_free",
     "rt_interp_velocity", "rt_interp_velocity_dev", "rt_interpolate_cells", "rt_nodal_adjacency", "rt_rcm", "rt_mesh_coords_dev", "rt_closest_point", "rt_bfm_solve",
     "rt_bfm_solve_dev", "rt_bfm_solve_multi", "rt_bfm_solve_dual", "rt_dual_velocity", "rt_set_option", "rt_reconstruct_paths", "rt_reconstruct_paths_dev",
+    "rt_grid3d_axes", "rt_grid3d_points", "rt_grid3d_connectivity", "rt_closest_point3d", "rt_polardistance3d",
+    "rt_reconstruct_paths_guarded", "rt_travel_times", "rt_travel_times_dev",
 ]
 
 
@@ -75,6 +77,14 @@ def lib():
     L.rt_set_option.argtypes = [VP, C.c_char_p, C.c_double]
     L.rt_reconstruct_paths.argtypes = [I64P, I64, I64, I64P, I64, I64P, VP, I64]
     L.rt_reconstruct_paths_dev.argtypes = [VP, I64, I64, I64P, I64, I64P, VP, I64]
+    L.rt_grid3d_axes.argtypes = [VP, VP, VP, VP]
+    L.rt_grid3d_points.argtypes = [VP, I64P, I64, VP, VP]
+    L.rt_grid3d_connectivity.argtypes = [VP, I64, I64, I64P]
+    L.rt_closest_point3d.argtypes = [VP, F64P, F64P, F64P, I64, I64P]
+    L.rt_polardistance3d.argtypes = [F64P, F64P, I64, F64P]
+    L.rt_reconstruct_paths_guarded.argtypes = [I64P, I64, I64, I64P, I64, I64P, VP, I64]
+    L.rt_travel_times.argtypes = [F64P, I64, I64, I64P, I64, F64P]
+    L.rt_travel_times_dev.argtypes = [VP, I64, I64, I64P, I64, F64P]
     _lib = L
     return L
 

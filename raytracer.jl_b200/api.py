@@ -97,11 +97,29 @@ class Grid2D:
         return self.nbr_idx[self.nbr_off[el - 1]:self.nbr_off[el]]
 
 
-class BellmanFordMoore:
-    """BellmanFordMoore(prev, dist) of src/SSSP/ssspm.jl:3-10.  prev: int64 1-based (0 = never set)."""
+class AbstractSPM:
+    """abstract type AbstractSPM (src/SSSP/ssspm.jl:1): result structs hold (prev, dist); prev is int64 1-based
+    (0 = never set).  Base.getindex(spm) = spm.prev (:12) is spelled spm[()]."""
 
     def __init__(self, prev, dist, stats=None):
         self.prev, self.dist, self.stats = prev, dist, stats
+
+    def __getitem__(self, key):
+        if key != ():
+            raise IndexError("only spm[()] (Base.getindex(spm::AbstractSPM) = spm.prev) is defined")
+        return self.prev
+
+
+class BellmanFordMoore(AbstractSPM):
+    """BellmanFordMoore(prev, dist) of src/SSSP/ssspm.jl:3-10."""
+
+
+class Dijkstra(AbstractSPM):
+    """Dijkstra(prev, dist) of src/SSSP/ssspm.jl:3-10 (result of `dijkstra`)."""
+
+
+class RadiusStepping(AbstractSPM):
+    """RadiusStepping(prev, dist) of src/SSSP/ssspm.jl:3-10 (result of `radius_stepping`)."""
 
 
 class VelProfile:
@@ -193,6 +211,94 @@ class Grid3D:
         X, Y, Z = np.zeros(self.n), np.zeros(self.n), np.zeros(self.n)
         check(lib().rt_grid3d_export(self._handle.h, X, Y, Z))
         return X, Y, Z
+
+    # ---- the fields / indexing of the reference's Grid (src/StructuredGrid.jl:7-16, 57-104)
+    @property
+    def nels(self):
+        return tuple(v - 1 for v in self.nnods)
+
+    @property
+    def nxny(self):
+        return self.nnods[0] * self.nnods[1]
+
+    def _axes(self):
+        if getattr(self, "_ax", None) is None:
+            ax = [np.zeros(v) for v in self.nnods]
+            check(lib().rt_grid3d_axes(self._handle.h, ptr(ax[0]), ptr(ax[1]), ptr(ax[2])))
+            self._ax = ax
+        return self._ax
+
+    x = property(lambda self: self._axes()[0])
+    y = property(lambda self: self._axes()[1])
+    z = property(lambda self: self._axes()[2])
+
+    def __getitem__(self, key):
+        """gr[I] (linear, 1-based, x fastest; :77-81) and gr[I, J, K] (:57-62) -> Point(x, y, z) of the RAW axes.
+        An array of linear indices gives an (m, 3) array."""
+        if isinstance(key, tuple):
+            if len(key) != 3:
+                raise IndexError("gr[I] or gr[I, J, K]")
+            I, J, K = (int(v) for v in key)
+            for v, nmax in zip((I, J, K), self.nnods):
+                if not 1 <= v <= nmax:  # the reference @asserts only the upper bound; Julia then throws BoundsError
+                    raise IndexError("index out of range")
+            ax = self._axes()
+            return Point(ax[0][I - 1], ax[1][J - 1], ax[2][K - 1])
+        ids = np.atleast_1d(np.asarray(key, np.int64)).copy()
+        xyz = np.zeros((len(ids), 3))
+        check(lib().rt_grid3d_points(self._handle.h, ids, len(ids), ptr(xyz), None))
+        return Point(*xyz[0]) if np.ndim(key) == 0 else xyz
+
+    def CartesianIndex(self, I):
+        """CartesianIndex(gr, I) (:90-96) -> (i, j, k), 1-based; arrays give an (m, 3) array."""
+        ids = np.atleast_1d(np.asarray(I, np.int64)).copy()
+        ijk = np.zeros((len(ids), 3), np.int64)
+        check(lib().rt_grid3d_points(self._handle.h, ids, len(ids), None, ptr(ijk)))
+        return tuple(int(v) for v in ijk[0]) if np.ndim(I) == 0 else ijk
+
+
+class Point:
+    """Point{T}(x, y, z) of src/StructuredGrid.jl:27-31."""
+
+    __slots__ = ("x", "y", "z")
+
+    def __init__(self, x, y, z):
+        self.x, self.y, self.z = float(x), float(y), float(z)
+
+    def __iter__(self):
+        return iter((self.x, self.y, self.z))
+
+    def __eq__(self, o):
+        return tuple(self) == tuple(o)
+
+    def __repr__(self):
+        return "Point(%r, %r, %r)" % (self.x, self.y, self.z)
+
+
+def connectivity(gr3, iel=None):
+    """connectivity(gr) -> (nel, 8) int64 array of 1-based corner ids; connectivity(gr, iel) -> the 8-tuple of one
+    element (src/StructuredGrid.jl:121-168)."""
+    nel = int(np.prod([max(v, 0) for v in gr3.nels]))
+    if iel is None:
+        out = np.zeros((nel, 8), np.int64)
+        if nel:
+            check(lib().rt_grid3d_connectivity(gr3._handle.h, 1, nel, out.reshape(-1)))
+        return out
+    out = np.zeros(8, np.int64)
+    check(lib().rt_grid3d_connectivity(gr3._handle.h, int(iel), 1, out))
+    return tuple(int(v) for v in out)
+
+
+def polardistance3D(p1, p2):
+    """polardistance3D(p1, p2) src/StructuredGrid.jl:245-255: p = (theta, phi, r) -> Euclidean distance of the
+    spherical2cart images.  Accepts Points / triples, or (m, 3) arrays for a batch."""
+    a = np.ascontiguousarray(np.atleast_2d(np.asarray([tuple(p1)] if isinstance(p1, Point) else p1, np.float64)))
+    b = np.ascontiguousarray(np.atleast_2d(np.asarray([tuple(p2)] if isinstance(p2, Point) else p2, np.float64)))
+    if a.shape != b.shape or a.shape[1] != 3:
+        raise ValueError("points must be (theta, phi, r) triples")
+    out = np.zeros(len(a))
+    check(lib().rt_polardistance3d(a.reshape(-1), b.reshape(-1), len(a), out))
+    return float(out[0]) if (isinstance(p1, Point) or np.ndim(p1) == 1) else out
 
 
 def grid(c0, c1, nnods, neighbour_levels=1, coord_system="cartesian"):
@@ -331,8 +437,17 @@ def dual_velocity(r, interpolant, buffer=1):
 
 
 # ------------------------------------------------------------------------------------------ closest_point
-def closest_point(gr, px, pz, system="cartesian"):
-    """closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 -> 1-based node id (scalar or array)."""
+def closest_point(gr, px, pz, pw=None, system="cartesian"):
+    """closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 -> 1-based node id (scalar or array).
+    With a Grid3D: closest_point(gr, x, y, z) of src/StructuredGrid.jl:257-270 (raw axis coordinates)."""
+    if isinstance(gr, Grid3D):
+        if pw is None:
+            raise TypeError("closest_point(gr::Grid, x, y, z) needs three coordinates")
+        a, b, c = np.broadcast_arrays(*(np.atleast_1d(np.asarray(v, np.float64)) for v in (px, pz, pw)))
+        a, b, c = (np.ascontiguousarray(v) for v in (a, b, c))
+        out = np.zeros(len(a), np.int64)
+        check(lib().rt_closest_point3d(gr._handle.h, a, b, c, len(a), out))
+        return int(out[0]) if all(np.ndim(v) == 0 for v in (px, pz, pw)) else out
     handle = gr._handle
     if handle is None:
         raise ValueError("grid has no device handle; call mesh_from_arrays(gr, G, halo) or bfm(...) first")
@@ -425,15 +540,20 @@ def bfm3d(gr3, source, U, schedule=None, delta=None, precision=64):
 # -------------------------------------------------------------------------------------------------- paths
 def recontruct_path(prev, source, receiver):
     """recontruct_path(prev::Vector, source, receiver) src/SSSP/ssspm.jl:30-40 -> [receiver, ..., source].
-    (The misspelling is the reference's API.)  `receiver` may be an array -> list of paths."""
-    if isinstance(prev, BellmanFordMoore):
+    (The misspelling is the reference's API.)  `receiver` may be an array -> list of paths.
+    Passing a result struct (BellmanFordMoore / Dijkstra / RadiusStepping) dispatches, as in Julia, to the struct
+    method recontruct_path(D, source, receiver) :14-28: the chase runs until a node repeats, then `source` is
+    appended; it raises RtError (the reference: BoundsError) when it reads an unset predecessor."""
+    fn = lib().rt_reconstruct_paths
+    if isinstance(prev, AbstractSPM):
         prev = prev.prev
+        fn = lib().rt_reconstruct_paths_guarded
     prev = np.ascontiguousarray(prev, np.int64)
     rec = np.atleast_1d(np.asarray(receiver, np.int64)).copy()
     off = np.zeros(len(rec) + 1, np.int64)
-    check(lib().rt_reconstruct_paths(prev, len(prev), int(source), rec, len(rec), off, None, 0))
+    check(fn(prev, len(prev), int(source), rec, len(rec), off, None, 0))
     idx = np.zeros(int(off[-1]), np.int64)
-    check(lib().rt_reconstruct_paths(prev, len(prev), int(source), rec, len(rec), off, ptr(idx), len(idx)))
+    check(fn(prev, len(prev), int(source), rec, len(rec), off, ptr(idx), len(idx)))
     paths = [idx[off[k]:off[k + 1]].copy() for k in range(len(rec))]
     return paths[0] if np.ndim(receiver) == 0 else paths
 
@@ -441,9 +561,15 @@ def recontruct_path(prev, source, receiver):
 def travel_times(D, gr, receivers, isave=False, flname=""):
     """travel_times(D, gr, receivers; isave, flname) src/utils.jl:4-15: D.dist at the receiver nodes; with isave the
     (degree, travel_time) table is written as CSV like the reference's DataFrame (degree = rad2deg(gr.theta))."""
-    rec = np.atleast_1d(np.asarray(receivers, np.int64))
-    tt = np.asarray(D.dist, np.float64)[rec - 1].copy()
+    rec = np.ascontiguousarray(np.atleast_1d(np.asarray(receivers, np.int64)))
+    d = np.ascontiguousarray(D.dist, np.float64)
+    nsrc = 1 if d.ndim == 1 else d.shape[0]
+    tt = np.zeros(nsrc * len(rec))
+    check(lib().rt_travel_times(d.reshape(-1), d.shape[-1], nsrc, rec, len(rec), tt))  # device gather
+    tt = tt if d.ndim == 1 else tt.reshape(nsrc, len(rec))
     if isave:
+        if d.ndim != 1:
+            raise ValueError("isave writes the (degree, travel_time) table of ONE source")
         deg = np.rad2deg(np.asarray(gr.theta, np.float64)[rec - 1])
         with open(os.path.join(os.getcwd(), flname), "w") as f:
             f.write("degree,travel_time\n")

@@ -12,7 +12,7 @@ int dual_velocity_device(const double* kr, const double* kv, i64 nk, const doubl
                          double* out_dev);
 int prev_to_host_i64_staged(const i32* prev_dev, i64 count, i64* out, i64* stage64, cudaStream_t s);
 int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* receivers, i64 nrec, i64* path_off,
-                             i64* path_idx, i64 cap);
+                             i64* path_idx, i64 cap, int guarded);
 int prev_host_to_device_i32(const i64* prev, i64 n, DevBuf<i32>& out);
 
 static thread_local char g_err[512] = "";
@@ -185,9 +185,50 @@ int rt_rcm(rt_mesh* m, int64_t* perm_out) {
   return mesh2d_rcm(m, perm_out);
 }
 
+int rt_closest_point3d(const rt_mesh* m, const double* px, const double* py, const double* pz, int64_t npts,
+                       int64_t* index_out) {
+  RT_ARG(m && m->kind == 3, "rt_closest_point3d needs a 3-D grid");
+  RT_CUDA(cudaSetDevice(m->device));
+  return grid3d_closest(m, px, py, pz, npts, index_out);
+}
+
+int rt_grid3d_axes(const rt_mesh* m, double* x, double* y, double* z) {
+  RT_ARG(m && m->kind == 3, "rt_grid3d_axes needs a 3-D grid");
+  RT_CUDA(cudaSetDevice(m->device));
+  return grid3d_axes(m, x, y, z);
+}
+
+int rt_grid3d_points(const rt_mesh* m, const int64_t* I, int64_t count, double* xyz, int64_t* ijk) {
+  RT_ARG(m && m->kind == 3, "rt_grid3d_points needs a 3-D grid");
+  RT_CUDA(cudaSetDevice(m->device));
+  return grid3d_points(m, I, count, xyz, ijk);
+}
+
+int rt_grid3d_connectivity(const rt_mesh* m, int64_t first_el, int64_t count, int64_t* e2n) {
+  RT_ARG(m && m->kind == 3, "rt_grid3d_connectivity needs a 3-D grid");
+  RT_CUDA(cudaSetDevice(m->device));
+  return grid3d_connectivity(m, first_el, count, e2n);
+}
+
+int rt_polardistance3d(const double* a, const double* b, int64_t count, double* out) {
+  return polardistance3d_device(a, b, count, out);
+}
+
+int rt_travel_times_dev(const double* dist_dev, int64_t n, int64_t nsrc, const int64_t* receivers, int64_t nrec,
+                        double* out) {
+  return travel_times_device(dist_dev, n, nsrc, receivers, nrec, out);
+}
+
+int rt_travel_times(const double* dist, int64_t n, int64_t nsrc, const int64_t* receivers, int64_t nrec, double* out) {
+  RT_ARG(dist && n > 0 && nsrc >= 0, "bad travel_times arguments");
+  DevBuf<double> d;
+  RT_TRY(d.upload(dist, (size_t)n * (size_t)nsrc));
+  return travel_times_device(d.p, n, nsrc, receivers, nrec, out);
+}
+
 int rt_closest_point(const rt_mesh* m, const double* pa, const double* pb, int64_t npts, int system,
                      int64_t* index_out) {
-  RT_ARG(m && m->kind == 2, "rt_closest_point needs a 2-D mesh");
+  RT_ARG(m && m->kind == 2, "rt_closest_point needs a 2-D mesh (3-D grids: rt_closest_point3d)");
   RT_ARG(system == 0 || system == 1, "system must be 0 (:cartesian) or 1 (:polar)");
   RT_CUDA(cudaSetDevice(m->device));
   return mesh2d_closest(m, pa, pb, npts, system, index_out);
@@ -257,6 +298,7 @@ int rt_bfm_solve_dual(rt_mesh* m, const double* U2, const int64_t* sources, int6
                       int64_t* prev_out, rt_stats* stats) {
   RT_ARG(m && m->kind == 2 && U2 && sources && nsrc >= 0, "rt_bfm_solve_dual needs a 2-D mesh, U[n x 2] and sources");
   RT_CUDA(cudaSetDevice(m->device));
+  m->f32 = false;  // an earlier precision = 32 call that failed half way must not leak into this Float64 solve
   const i64 n = mesh_n(m);
   cudaStream_t cs = m->stream;
   DevBuf<double> dU;
@@ -283,6 +325,7 @@ int rt_bfm_solve_dual(rt_mesh* m, const double* U2, const int64_t* sources, int6
     total.relax_ms += st.relax_ms;
     total.relax_launches += st.relax_launches;
     total.total_launches += st.total_launches;
+    total.prev_ms += st.prev_ms;
   }
   if (stats) *stats = total;
   return RT_OK;
@@ -368,6 +411,11 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
     m->opts.packed_prev = value != 0.0;
   } else if (!std::strcmp(key, "persistent")) {
     m->opts.persistent = value < 0.0 ? -1 : (value != 0.0);
+  } else if (!std::strcmp(key, "weight3d")) {
+    RT_ARG(value == 0.0 || value == 1.0, "weight3d must be 0 (weights.jl:20) or 1 (Dijsktra.jl:388)");
+    m->opts.weight3d = (int)value;
+  } else if (!std::strcmp(key, "canonical_prev")) {
+    m->opts.canonical_prev = value != 0.0;
   } else if (!std::strcmp(key, "delta_factor")) {
     RT_ARG(value >= 0.0, "delta_factor must be >= 0");
     m->opts.delta_factor = value;
@@ -383,12 +431,20 @@ int rt_reconstruct_paths(const int64_t* prev, int64_t n, int64_t source, const i
   RT_ARG(prev && n > 0, "null prev table");
   DevBuf<i32> dprev;
   RT_TRY(prev_host_to_device_i32(prev, n, dprev));
-  return reconstruct_paths_device(dprev.p, n, source, receivers, nrec, path_off, path_idx, cap);
+  return reconstruct_paths_device(dprev.p, n, source, receivers, nrec, path_off, path_idx, cap, 0);
+}
+
+int rt_reconstruct_paths_guarded(const int64_t* prev, int64_t n, int64_t source, const int64_t* receivers,
+                                 int64_t nrec, int64_t* path_off, int64_t* path_idx, int64_t cap) {
+  RT_ARG(prev && n > 0, "null prev table");
+  DevBuf<i32> dprev;
+  RT_TRY(prev_host_to_device_i32(prev, n, dprev));
+  return reconstruct_paths_device(dprev.p, n, source, receivers, nrec, path_off, path_idx, cap, 1);
 }
 
 int rt_reconstruct_paths_dev(const int32_t* prev_dev, int64_t n, int64_t source, const int64_t* receivers,
                              int64_t nrec, int64_t* path_off, int64_t* path_idx, int64_t cap) {
-  return reconstruct_paths_device(prev_dev, n, source, receivers, nrec, path_off, path_idx, cap);
+  return reconstruct_paths_device(prev_dev, n, source, receivers, nrec, path_off, path_idx, cap, 0);
 }
 
 }  // extern "C"

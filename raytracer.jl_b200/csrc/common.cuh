@@ -96,6 +96,8 @@ struct SolverOpts {
   int batch = 0;           // near-far: sources solved in lock step on small meshes (0 = automatic, <= 32)
   int packed_prev = 1;     // near-far 2-D: 1 = 128-bit (time, predecessor) CAS, 0 = separate tightness pass
   double delta_factor = 0.0;  // automatic width = delta_factor x lightest edge (0 = default)
+  int weight3d = 0;        // 3-D edge weight: 0 = weights.jl:20 (d * (1/|Ui+Uj|) * 2), 1 = Dijsktra.jl:388 (d / |Ui+Uj| * 0.5)
+  int canonical_prev = 0;  // near-far: 1 = reproduce the reference's predecessors exactly, ties included
 };
 
 struct Mesh2D;
@@ -142,6 +144,10 @@ int grid3d_build(rt_mesh* h, const double c0[3], const double c1[3], const i64 n
 int grid3d_export(const rt_mesh* h, double* X, double* Y, double* Z);
 void grid3d_free(rt_mesh* h);
 int grid3d_n(const rt_mesh* h, i64* n);
+int grid3d_axes(const rt_mesh* h, double* x, double* y, double* z);
+int grid3d_points(const rt_mesh* h, const i64* ids, i64 count, double* xyz, i64* ijk);
+int grid3d_connectivity(const rt_mesh* h, i64 first_el, i64 count, i64* e2n);
+int grid3d_closest(const rt_mesh* h, const double* px, const double* py, const double* pz, i64 npts, i64* out);
 int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                 rt_stats* stats);
 
@@ -152,3 +158,5 @@ int interp_velocity_device(const double* kr, const double* kv, i64 nk, const dou
 int closest_point_device(const double* a_dev, const double* b_dev, i64 n, const double* pa, const double* pb,
                          i64 npts, i64* out, cudaStream_t s);
 int prev_to_host_i64(const i32* prev_dev, i64 count, i64* out, cudaStream_t s);
+int travel_times_device(const double* dist_dev, i64 n, i64 nsrc, const i64* receivers, i64 nrec, double* out);
+int polardistance3d_device(const double* a, const double* b, i64 count, double* out);

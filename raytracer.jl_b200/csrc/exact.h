@@ -52,15 +52,26 @@ RT_HD double exact_cand2(double d_from, double xi, double zi, double Ui, double 
   return rnd<F32>(RT_DADD(d_from, w));
 }
 
-// 3-D: d_from + distance3D(pI, pJ) * (1 / abs(UI + UJ)) * 2   (src/SSSP/weights.jl:20, src/StructuredGrid.jl:239-241)
+// 3-D, weight mode 0 (default): d_from + distance3D(pI, pJ) * (1 / abs(UI + UJ)) * 2   (src/SSSP/weights.jl:20,
+// src/StructuredGrid.jl:239-241); weight mode 1: d_from + distance3D(pJ, pI) / abs(UJ + UI) * 0.5, the expression of
+// the legacy 3-D solvers BFM/foo! (src/Dijsktra.jl:388) and dijsktra (:44).  The two differ in rounding (reciprocal
+// then multiply against a division) and by a factor 4.  `wmode` is uniform per launch.
 template <bool F32>
 RT_HD double exact_cand3(double d_from, double xi, double yi, double zi, double ui, double xj, double yj, double zj,
-                         double uj) {
+                         double uj, int wmode = 0) {
   const double dx = rnd<F32>(RT_DSUB(xi, xj)), dy = rnd<F32>(RT_DSUB(yi, yj)), dz = rnd<F32>(RT_DSUB(zi, zj));
   const double s = rnd<F32>(RT_DADD(rnd<F32>(RT_DADD(rnd<F32>(RT_DMUL(dx, dx)), rnd<F32>(RT_DMUL(dy, dy)))),
                                     rnd<F32>(RT_DMUL(dz, dz))));
   const double d = rnd<F32>(RT_DSQRT(s));
-  const double rcp = rnd<F32>(RT_DRCP(fabs(rnd<F32>(RT_DADD(ui, uj)))));
-  const double wgt = RT_DMUL(rnd<F32>(RT_DMUL(d, rcp)), 2.0);
+  const double us = fabs(rnd<F32>(RT_DADD(ui, uj)));
+  double wgt;
+  if (wmode) {
+    wgt = rnd<F32>(RT_DMUL(rnd<F32>(RT_DDIV(d, us)), 0.5));
+  } else {
+    const double rcp = rnd<F32>(RT_DRCP(us));
+    wgt = rnd<F32>(RT_DMUL(rnd<F32>(RT_DMUL(d, rcp)), 2.0));
+  }
   return rnd<F32>(RT_DADD(d_from, wgt));
 }
+// the screens are written for w = 2*sqrt(d2)/ssum; mode 1 is 0.5*sqrt(d2)/ssum = 2*sqrt(d2)/(4*ssum): scale ssum (exact)
+RT_HD double screen_ssum3(double us_abs, int wmode) { return wmode ? 4.0 * us_abs : us_abs; }

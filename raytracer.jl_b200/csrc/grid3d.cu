@@ -5,7 +5,8 @@
 // edge_weight src/SSSP/weights.jl:20 and the control flow of BFM / foo! / goo! src/Dijsktra.jl:294-343,376-403.
 //
 // The reference materialises Dict{Int,Set{Int}} with ~125 entries per node; here the adjacency is implicit:
-// star-L of a box grid is the clipped (2L+3)^3 window (self included once L >= 1), so no adjacency arrays
+// star-L of a box grid is the clipped (2*2^L+1)^3 window (every expansion round of nodal_incidence unions the
+// neighbours' CURRENT sets, so the radius doubles per level; self included once L >= 1), so no adjacency arrays
 // exist at all.  A CTA owns one 8x4x4 tile of nodes, stages the tile plus its halo of (X,Y,Z,U,dist0) in
 // shared memory once, and every thread scans its window in ascending linear id (the canonical scan order:
 // the reference iterates a Julia Set whose order is not reproducible).  Frontier = active tile list.
@@ -25,12 +26,13 @@ struct Grid3D {
   i64 nn[3] = {0, 0, 0};
   i64 n = 0;
   int star_levels = 1;
-  int w = 2;  // window half width = star_levels + 1
+  int w = 2;  // window half width = 2^star_levels (StructuredGrid.jl:204-212)
   int self = 1;
   int coord_system = 0;
   double c0[3], c1[3];
   DevBuf<double> X, Y, Z;
   DevBuf<double> Xf, Yf, Zf;  // Float32-rounded coordinates (precision = 32), built on first use
+  DevBuf<double> ax, ay, az;  // raw axis coordinates gr.x, gr.y, gr.z (getindex / closest_point), built on first use
   i64 tn[3] = {0, 0, 0};
   i64 n_tiles = 0;
   i64 graph_edges = 0;
@@ -67,6 +69,7 @@ struct P3 {
   int nx, ny, nz;
   int tnx, tny, tnz;
   int w, self;
+  int wmode;  // 0: weights.jl:20, 1: Dijsktra.jl:388 (exact.h)
 };
 
 // Julia Base lerpi (LinRange element): t = j/d; (1-t)*a + t*b
@@ -103,8 +106,8 @@ __global__ void coords3d_kernel(double c0x, double c0y, double c0z, double c1x, 
 // exact_cand3<F32> (exact.h); F32: every operation rounded to Float32 (precision = 32)
 template <bool F32 = false>
 __device__ __forceinline__ double cand3(double dj, double xi, double yi, double zi, double ui, double xj,
-                                        double yj, double zj, double uj) {
-  return exact_cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj);
+                                        double yj, double zj, double uj, int wmode) {
+  return exact_cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj, wmode);
 }
 
 // One CTA per active tile; dynamic smem = 5 * SX*SY*SZ doubles.
@@ -163,9 +166,9 @@ __global__ void __launch_bounds__(TILE_THREADS) relax3d_kernel(P3 p, const i32* 
             {
               const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
               const double d2 = __fma_rn(dx, dx, __fma_rn(dy, dy, dz * dz));
-              if (screen_cannot_improve_t<F32>(best, dj, d2, fabs(__dadd_rn(ui, uj)))) continue;
+              if (screen_cannot_improve_t<F32>(best, dj, d2, screen_ssum3(fabs(__dadd_rn(ui, uj)), p.wmode))) continue;
             }
-            const double delta = cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj);
+            const double delta = cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj, p.wmode);
             if (delta < best) {
               best = delta;
               bid = (i64)xx + (i64)p.nx * ((i64)yy + (i64)p.ny * zz);
@@ -294,6 +297,12 @@ int grid3d_build(rt_mesh* h, const double c0[3], const double c1[3], const i64 n
   RT_ARG(c0 && c1 && nn, "null argument");
   RT_ARG(nn[0] >= 1 && nn[1] >= 1 && nn[2] >= 1, "grid needs at least one node per axis");
   RT_ARG(star_levels >= 0 && star_levels <= 3, "star_levels must be in 0..3");
+  if (star_levels == 3) {
+    // radius 2^3 = 8: a 17^3 window (4913 candidates per node); the tile + halo of the relax kernel would need
+    // 384 KB of shared memory.  Not built: the reference itself cannot hold that Dict beyond toy grids.
+    rt_set_error("neighbour_levels = 3 (17^3 window) is not supported; use 0, 1 or 2");
+    return RT_ERR_UNSUPPORTED;
+  }
   RT_ARG(coord_system == 0 || coord_system == 1, "coord_system must be 0 or 1");
   const i64 n = nn[0] * nn[1] * nn[2];
   RT_ARG(n < (i64)2000000000 && nn[0] < 65536 * 16 && nn[1] < 65536 * 16 && nn[2] < 65536 * 16, "grid too large");
@@ -308,7 +317,7 @@ int grid3d_build(rt_mesh* h, const double c0[3], const double c1[3], const i64 n
   }
   g.n = n;
   g.star_levels = star_levels;
-  g.w = star_levels + 1;
+  g.w = 1 << star_levels;
   g.self = star_levels >= 1 ? 1 : 0;
   g.coord_system = coord_system;
   g.tn[0] = (nn[0] + TX - 1) / TX;
@@ -388,6 +397,7 @@ struct Q3 {
   int* ctl;       // [0] cur [1] fcur [2] mode [3] done [4] rounds [5] push rounds
   int nx, ny, nz, nbx;
   int w, self;
+  int wmode;  // 0: weights.jl:20, 1: Dijsktra.jl:388 (exact.h)
   FastDiv fd_nx, fd_ny, fd_nbx, fd_W;  // node id -> (x, line), line -> (y, z), item -> (bx, line), unit -> (slot, dz)
 };
 
@@ -489,8 +499,8 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
         if (!p.self && ty == sy && dzi == 0 && bx * 32 + q == tx) continue;
         const double dx = __dsub_rn(S[0][q], xj), dy = __dsub_rn(S[1][q], yj), dz = __dsub_rn(S[2][q], zj);
         const double d2 = __fma_rn(dx, dx, __fma_rn(dy, dy, dz * dz));
-        if (screen_cannot_improve_t<F32>(best, di, d2, fabs(__dadd_rn(S[3][q], uj)))) continue;
-        const double delta = cand3<F32>(di, S[0][q], S[1][q], S[2][q], S[3][q], xj, yj, zj, uj);
+        if (screen_cannot_improve_t<F32>(best, di, d2, screen_ssum3(fabs(__dadd_rn(S[3][q], uj)), p.wmode))) continue;
+        const double delta = cand3<F32>(di, S[0][q], S[1][q], S[2][q], S[3][q], xj, yj, zj, uj, p.wmode);
         best = delta < best ? delta : best;
       }
       if (best < dj) {
@@ -646,7 +656,7 @@ __global__ void wdiag3_kernel(Q3 p, double* __restrict__ sum, u64* __restrict__ 
     const int i = (int)(I % p.nx), j = (int)((I / p.nx) % p.ny), k = (int)(I / ((i64)p.nx * p.ny));
     const int i2 = min(i + 1, p.nx - 1), j2 = min(j + 1, p.ny - 1), k2 = min(k + 1, p.nz - 1);
     const i64 J = (i64)i2 + (i64)p.nx * ((i64)j2 + (i64)p.ny * k2);
-    if (J != I) wt = cand3(0.0, p.X[I], p.Y[I], p.Z[I], p.U[I], p.X[J], p.Y[J], p.Z[J], p.U[J]);
+    if (J != I) wt = cand3(0.0, p.X[I], p.Y[I], p.Z[I], p.U[I], p.X[J], p.Y[J], p.Z[J], p.U[J], p.wmode);
     if (!(wt == wt) || wt > 1e300) wt = 0.0;
   }
   const unsigned has = __ballot_sync(FULL, wt > 0.0);
@@ -676,8 +686,8 @@ __global__ void prev_tight3_kernel(Q3 p, i64 n, i64 source) {
         const double xj = p.X[J], yj = p.Y[J], zj = p.Z[J], uj = p.U[J];
         const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
         const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        if (!screen_maybe_tight_t<F32>(di, dj, d2, fabs(__dadd_rn(ui, uj)))) continue;
-        if (cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj) == di) {
+        if (!screen_maybe_tight_t<F32>(di, dj, d2, screen_ssum3(fabs(__dadd_rn(ui, uj)), p.wmode))) continue;
+        if (cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj, p.wmode) == di) {
           p.prev[I] = (i32)J;
           return;
         }
@@ -750,6 +760,7 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.nbx = (int)g.nbx;
   p.w = g.w;
   p.self = g.self;
+  p.wmode = h->opts.weight3d;
   p.fd_nx = FastDiv((unsigned)g.nn[0]);
   p.fd_ny = FastDiv((unsigned)g.nn[1]);
   p.fd_nbx = FastDiv((unsigned)g.nbx);
@@ -904,6 +915,7 @@ int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
   p.tnz = (int)g.tn[2];
   p.w = g.w;
   p.self = g.self;
+  p.wmode = h->opts.weight3d;
   const int w = g.w;
   const size_t smem = (size_t)5 * (TX + 2 * w) * (TY + 2 * w) * (TZ + 2 * w) * sizeof(double);
   RT_CUDA(cudaFuncSetAttribute(relax3d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1004,4 +1016,222 @@ int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
   cudaEventDestroy(evr1);
   if (stats) *stats = st;
   return rc;
+}
+
+// =========================================================================================================
+// The rest of the 3-D grid surface of src/StructuredGrid.jl: axes, getindex (linear and Cartesian), connectivity,
+// closest_point.  All of it works on the RAW axis coordinates (gr.x, gr.y, gr.z) exactly like the reference:
+// gr[I] = Point(gr.x[i], gr.y[j], gr.z[k]) (:77-81) is NOT mapped through spherical2cart.
+namespace {
+
+__global__ void axes3d_kernel(double c0x, double c0y, double c0z, double c1x, double c1y, double c1z, int nx, int ny,
+                              int nz, double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nx) ax[t] = lerpi_dev(t, nx - 1, c0x, c1x);
+  if (t < ny) ay[t] = lerpi_dev(t, ny - 1, c0y, c1y);
+  if (t < nz) az[t] = lerpi_dev(t, nz - 1, c0z, c1z);
+}
+
+// gr[I] (:77-81) with CartesianIndex(gr, I) (:90-96): i = mod(I-1, nx)+1; k = cld(I, nx*ny); j = cld(I - nx*ny*(k-1), nx)
+__global__ void points3d_kernel(const double* __restrict__ ax, const double* __restrict__ ay,
+                                const double* __restrict__ az, i64 nx, i64 ny, const i64* __restrict__ ids, i64 count,
+                                double* __restrict__ xyz, i64* __restrict__ ijk) {
+  const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  const i64 I = ids[q];
+  const i64 i = (I - 1) % nx + 1;
+  const i64 k = (I + nx * ny - 1) / (nx * ny);
+  const i64 r = I - nx * ny * (k - 1);
+  const i64 j = (r + nx - 1) / nx;
+  if (xyz) {
+    xyz[3 * q + 0] = ax[i - 1];
+    xyz[3 * q + 1] = ay[j - 1];
+    xyz[3 * q + 2] = az[k - 1];
+  }
+  if (ijk) {
+    ijk[3 * q + 0] = i;
+    ijk[3 * q + 1] = j;
+    ijk[3 * q + 2] = k;
+  }
+}
+
+// connectivity(gr, iel) (:146-168) with cornerindex_ijk (:106-112): 8 corner ids of hex `iel` (1-based), ordered
+// (idx, idx+1, idx+1+nx, idx+nx, idx+nxny, idx+nxny+1, idx+nxny+1+nx, idx+nxny+nx)
+__global__ void connectivity3d_kernel(i64 nx, i64 ny, i64 ex, i64 ey, i64 first, i64 count, i64* __restrict__ out) {
+  const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  const i64 iel = first + q;
+  const i64 i = (iel - 1) % ex + 1;
+  const i64 j = ((iel + ex - 1) / ex - 1) % ey + 1;
+  const i64 k = (iel + ex * ey - 1) / (ex * ey);
+  const i64 idx = i + (j - 1) * nx + (k - 1) * nx * ny;
+  const i64 nxny = nx * ny;
+  i64* o = out + 8 * q;
+  o[0] = idx;
+  o[1] = idx + 1;
+  o[2] = idx + 1 + nx;
+  o[3] = idx + nx;
+  o[4] = idx + nxny;
+  o[5] = idx + nxny + 1;
+  o[6] = idx + nxny + 1 + nx;
+  o[7] = idx + nxny + nx;
+}
+
+// closest_point(gr, x, y, z) (:257-270): argmin over the linear index of distance3D(gr[i], p) with strict `<`
+// (first index wins).  Pass 1: the minimum of the ROUNDED distances (the square root is only taken when the squared
+// distance undercuts the thread's best: sqrt is monotone, so a candidate with d2 >= best d2 can never be strictly
+// closer); pass 2: the first index attaining it (sqrt only for d2 within rounding reach of the target).
+__device__ __forceinline__ double d2_3(double a, double b, double c, double pa, double pb, double pc) {
+  const double da = __dsub_rn(a, pa), db = __dsub_rn(b, pb), dc = __dsub_rn(c, pc);
+  return __dadd_rn(__dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db)), __dmul_rn(dc, dc));
+}
+__global__ void closest3d_pass1_kernel(const double* __restrict__ ax, const double* __restrict__ ay,
+                                       const double* __restrict__ az, int nx, int ny, int nz, FastDiv fnx, FastDiv fny,
+                                       const double* __restrict__ pq, u64* __restrict__ best) {
+  const int q = blockIdx.y;
+  const double qa = pq[3 * q], qb = pq[3 * q + 1], qc = pq[3 * q + 2];
+  const i64 n = (i64)nx * ny * nz;
+  double bd2 = __longlong_as_double(0x7ff0000000000000LL);
+  u64 m = ~0ull;
+  for (i64 I = (i64)blockIdx.x * blockDim.x + threadIdx.x; I < n; I += (i64)gridDim.x * blockDim.x) {
+    unsigned line, i, k, j;
+    fnx.divmod((unsigned)I, line, i);
+    fny.divmod(line, k, j);
+    const double d2 = d2_3(ax[i], ay[j], az[k], qa, qb, qc);
+    if (d2 < bd2) {
+      bd2 = d2;
+      const u64 bits = (u64)__double_as_longlong(__dsqrt_rn(d2));
+      m = bits < m ? bits : m;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 other = __shfl_xor_sync(0xffffffffu, m, o);
+    m = other < m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&best[q], m);
+}
+__global__ void closest3d_pass2_kernel(const double* __restrict__ ax, const double* __restrict__ ay,
+                                       const double* __restrict__ az, int nx, int ny, int nz, FastDiv fnx, FastDiv fny,
+                                       const double* __restrict__ pq, const u64* __restrict__ best,
+                                       u64* __restrict__ index) {
+  const int q = blockIdx.y;
+  const double qa = pq[3 * q], qb = pq[3 * q + 1], qc = pq[3 * q + 2];
+  const i64 n = (i64)nx * ny * nz;
+  const u64 target = best[q];
+  const double tv = __longlong_as_double((long long)target);
+  const double reach = tv * tv * (1.0 + 1e-15) + 1e-300;  // d2 above this cannot round to the target
+  u64 m = ~0ull;
+  for (i64 I = (i64)blockIdx.x * blockDim.x + threadIdx.x; I < n; I += (i64)gridDim.x * blockDim.x) {
+    unsigned line, i, k, j;
+    fnx.divmod((unsigned)I, line, i);
+    fny.divmod(line, k, j);
+    const double d2 = d2_3(ax[i], ay[j], az[k], qa, qb, qc);
+    if (d2 <= reach && (u64)__double_as_longlong(__dsqrt_rn(d2)) == target) {
+      m = (u64)I;
+      break;  // ascending per thread: the first hit is this thread's smallest
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 other = __shfl_xor_sync(0xffffffffu, m, o);
+    m = other < m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&index[q], m);
+}
+
+int ensure_axes3(const rt_mesh* h) {
+  Grid3D& g = *h->g3;
+  if (g.ax.n == (size_t)g.nn[0] && g.ay.n == (size_t)g.nn[1] && g.az.n == (size_t)g.nn[2]) return RT_OK;
+  RT_TRY(g.ax.alloc(g.nn[0]));
+  RT_TRY(g.ay.alloc(g.nn[1]));
+  RT_TRY(g.az.alloc(g.nn[2]));
+  const i64 m = std::max(g.nn[0], std::max(g.nn[1], g.nn[2]));
+  axes3d_kernel<<<grid_for(m, 256), 256, 0, h->stream>>>(g.c0[0], g.c0[1], g.c0[2], g.c1[0], g.c1[1], g.c1[2],
+                                                        (int)g.nn[0], (int)g.nn[1], (int)g.nn[2], g.ax.p, g.ay.p, g.az.p);
+  RT_CUDA(cudaGetLastError());
+  RT_CUDA(cudaStreamSynchronize(h->stream));
+  return RT_OK;
+}
+
+}  // namespace
+
+int grid3d_axes(const rt_mesh* h, double* x, double* y, double* z) {
+  RT_TRY(ensure_axes3(h));
+  const Grid3D& g = *h->g3;
+  if (x) RT_CUDA(cudaMemcpy(x, g.ax.p, g.nn[0] * sizeof(double), cudaMemcpyDeviceToHost));
+  if (y) RT_CUDA(cudaMemcpy(y, g.ay.p, g.nn[1] * sizeof(double), cudaMemcpyDeviceToHost));
+  if (z) RT_CUDA(cudaMemcpy(z, g.az.p, g.nn[2] * sizeof(double), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+int grid3d_points(const rt_mesh* h, const i64* ids, i64 count, double* xyz, i64* ijk) {
+  RT_ARG(ids && count >= 0, "bad getindex arguments");
+  const Grid3D& g = *h->g3;
+  for (i64 q = 0; q < count; ++q) RT_ARG(ids[q] >= 1 && ids[q] <= g.n, "linear index out of range (BoundsError)");
+  if (count == 0) return RT_OK;
+  RT_TRY(ensure_axes3(h));
+  DevBuf<i64> dids, dijk;
+  DevBuf<double> dxyz;
+  RT_TRY(dids.upload(ids, count));
+  if (xyz) RT_TRY(dxyz.alloc(3 * count));
+  if (ijk) RT_TRY(dijk.alloc(3 * count));
+  points3d_kernel<<<grid_for(count, 256), 256>>>(g.ax.p, g.ay.p, g.az.p, g.nn[0], g.nn[1], dids.p, count,
+                                                 xyz ? dxyz.p : nullptr, ijk ? dijk.p : nullptr);
+  RT_CUDA(cudaGetLastError());
+  if (xyz) RT_CUDA(cudaMemcpy(xyz, dxyz.p, 3 * count * sizeof(double), cudaMemcpyDeviceToHost));
+  if (ijk) RT_CUDA(cudaMemcpy(ijk, dijk.p, 3 * count * sizeof(i64), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+int grid3d_connectivity(const rt_mesh* h, i64 first_el, i64 count, i64* e2n) {
+  const Grid3D& g = *h->g3;
+  const i64 ex = g.nn[0] - 1, ey = g.nn[1] - 1, ez = g.nn[2] - 1;
+  const i64 nel = (ex > 0 && ey > 0 && ez > 0) ? ex * ey * ez : 0;
+  RT_ARG(e2n && count >= 0 && first_el >= 1 && first_el + count - 1 <= nel, "element range outside 1..prod(nels)");
+  const i64 slab = (i64)1 << 24;
+  DevBuf<i64> out;
+  RT_TRY(out.alloc(8 * std::min(count, slab)));
+  for (i64 o = 0; o < count; o += slab) {
+    const i64 c = std::min(slab, count - o);
+    connectivity3d_kernel<<<grid_for(c, 256), 256>>>(g.nn[0], g.nn[1], ex, ey, first_el + o, c, out.p);
+    RT_CUDA(cudaGetLastError());
+    RT_CUDA(cudaMemcpy(e2n + 8 * o, out.p, 8 * c * sizeof(i64), cudaMemcpyDeviceToHost));
+  }
+  return RT_OK;
+}
+
+int grid3d_closest(const rt_mesh* h, const double* px, const double* py, const double* pz, i64 npts, i64* out) {
+  RT_ARG(px && py && pz && out && npts >= 0, "bad closest_point arguments");
+  if (npts == 0) return RT_OK;
+  RT_TRY(ensure_axes3(h));
+  const Grid3D& g = *h->g3;
+  cudaStream_t s = h->stream;
+  std::vector<double> pq(3 * npts);
+  for (i64 q = 0; q < npts; ++q) {
+    pq[3 * q] = px[q];
+    pq[3 * q + 1] = py[q];
+    pq[3 * q + 2] = pz[q];
+  }
+  DevBuf<double> dpq;
+  DevBuf<u64> best, index;
+  RT_TRY(dpq.upload(pq.data(), 3 * npts, s));
+  RT_TRY(best.alloc(npts));
+  RT_TRY(index.alloc(npts));
+  RT_CUDA(cudaMemsetAsync(best.p, 0xff, npts * sizeof(u64), s));
+  RT_CUDA(cudaMemsetAsync(index.p, 0xff, npts * sizeof(u64), s));
+  const FastDiv fnx((unsigned)g.nn[0]), fny((unsigned)g.nn[1]);
+  const unsigned bx = (unsigned)std::min<i64>(grid_for(g.n, 256), 592);
+  for (i64 q0 = 0; q0 < npts; q0 += 32768) {
+    const i64 nq = std::min<i64>(32768, npts - q0);
+    dim3 grid(bx, (unsigned)nq);
+    closest3d_pass1_kernel<<<grid, 256, 0, s>>>(g.ax.p, g.ay.p, g.az.p, (int)g.nn[0], (int)g.nn[1], (int)g.nn[2], fnx,
+                                                fny, dpq.p + 3 * q0, best.p + q0);
+    closest3d_pass2_kernel<<<grid, 256, 0, s>>>(g.ax.p, g.ay.p, g.az.p, (int)g.nn[0], (int)g.nn[1], (int)g.nn[2], fnx,
+                                                fny, dpq.p + 3 * q0, best.p + q0, index.p + q0);
+  }
+  RT_CUDA(cudaGetLastError());
+  std::vector<u64> hi(npts);
+  RT_CUDA(cudaMemcpyAsync(hi.data(), index.p, npts * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  RT_CUDA(cudaStreamSynchronize(s));
+  for (i64 q = 0; q < npts; ++q) out[q] = hi[q] == ~0ull ? -1 : (i64)hi[q] + 1;  // -1 as in the reference (NaN query)
+  return RT_OK;
 }

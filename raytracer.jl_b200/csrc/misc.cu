@@ -190,6 +190,84 @@ __global__ void path_fill_kernel(const i32* __restrict__ prev, i32 source, const
   out[o] = (i64)source + 1;
 }
 
+
+// recontruct_path(D, source, receiver) src/SSSP/ssspm.jl:14-28 (the struct method): the chase runs `while ipath ∉ path`
+// -- until a node repeats -- and `source` is appended afterwards, whether or not the chase passed through it.  The
+// number of distinct nodes of the sequence x0 = receiver, x(k+1) = prev[x(k)] is mu + lambda (tail + cycle), found
+// with Brent's cycle detection; an unset entry (the reference: BoundsError / UndefRefError) gives len = -1.
+__device__ __forceinline__ i32 chase(const i32* __restrict__ prev, i64 n, i32 v) {
+  return (v < 0 || v >= n) ? -1 : prev[v];
+}
+__global__ void path_len_guarded_kernel(const i32* __restrict__ prev, i64 n, const i32* __restrict__ recv, i64 nrec,
+                                        i64* __restrict__ len) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nrec) return;
+  const i32 x0 = recv[k];
+  len[k] = -1;
+  if (x0 < 0 || x0 >= n) return;
+  i64 power = 1, lam = 1;
+  i32 tortoise = x0, hare = chase(prev, n, x0);
+  while (tortoise != hare) {
+    if (hare < 0) return;
+    if (power == lam) {
+      tortoise = hare;
+      power *= 2;
+      lam = 0;
+    }
+    hare = chase(prev, n, hare);
+    ++lam;
+  }
+  tortoise = hare = x0;
+  for (i64 q = 0; q < lam; ++q) hare = chase(prev, n, hare);
+  i64 mu = 0;
+  while (tortoise != hare) {
+    tortoise = chase(prev, n, tortoise);
+    hare = chase(prev, n, hare);
+    ++mu;
+  }
+  len[k] = mu + lam + 1;
+}
+__global__ void path_fill_guarded_kernel(const i32* __restrict__ prev, i32 source, const i32* __restrict__ recv,
+                                         i64 nrec, const i64* __restrict__ off, i64* __restrict__ out) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nrec) return;
+  i64 o = off[k];
+  const i64 end = off[k + 1];
+  i32 ip = recv[k];
+  while (o < end - 1) {
+    out[o++] = (i64)ip + 1;
+    ip = prev[ip];
+  }
+  out[o] = (i64)source + 1;
+}
+
+// travel_times(D, gr, receivers) src/utils.jl:4-8 for a batch: out[s, k] = dist[s, receivers[k]]
+__global__ void travel_times_kernel(const double* __restrict__ dist, i64 n, i64 nsrc, const i64* __restrict__ recv,
+                                    i64 nrec, double* __restrict__ out) {
+  const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsrc * nrec) return;
+  const i64 s = t / nrec, k = t - s * nrec;
+  out[t] = dist[s * n + (recv[k] - 1)];
+}
+
+// polardistance3D(a, b) src/StructuredGrid.jl:245-255: spherical2cart (:225-230) of both (theta, phi, r) triples,
+// then distance3D (:239-241)
+__global__ void polardistance3d_kernel(const double* __restrict__ a, const double* __restrict__ b, i64 count,
+                                       double* __restrict__ out) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  double c[2][3];
+  const double* pts[2] = {a + 3 * k, b + 3 * k};
+  for (int q = 0; q < 2; ++q) {
+    const double th = pts[q][0], ph = pts[q][1], r = pts[q][2];
+    c[q][0] = __dmul_rn(__dmul_rn(r, cos(ph)), sin(th));
+    c[q][1] = __dmul_rn(__dmul_rn(r, sin(ph)), sin(th));
+    c[q][2] = __dmul_rn(r, cos(th));
+  }
+  const double dx = __dsub_rn(c[0][0], c[1][0]), dy = __dsub_rn(c[0][1], c[1][1]), dz = __dsub_rn(c[0][2], c[1][2]);
+  out[k] = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+}
+
 }  // namespace
 
 int interp_velocity_device(const double* kr_h, const double* kv_h, i64 nk, const double* r_dev, i64 n,
@@ -235,7 +313,7 @@ int dual_velocity_device(const double* kr_h, const double* kv_h, i64 nk, const d
 
 int closest_point_device(const double* a_dev, const double* b_dev, i64 n, const double* pa, const double* pb,
                          i64 npts, i64* out, cudaStream_t s) {
-  RT_ARG(pa && pb && out && npts >= 0 && npts < 65536, "bad closest_point arguments (npts < 65536)");
+  RT_ARG(pa && pb && out && npts >= 0, "bad closest_point arguments");
   if (npts == 0) return RT_OK;
   DevBuf<double> dpa, dpb;
   DevBuf<u64> best, index;
@@ -246,9 +324,12 @@ int closest_point_device(const double* a_dev, const double* b_dev, i64 n, const 
   RT_CUDA(cudaMemsetAsync(best.p, 0xff, npts * sizeof(u64), s));
   RT_CUDA(cudaMemsetAsync(index.p, 0xff, npts * sizeof(u64), s));
   const unsigned bx = (unsigned)std::min<i64>(grid_for(n, 256), 1184);
-  dim3 grid(bx, (unsigned)npts);
-  closest_pass1_kernel<<<grid, 256, 0, s>>>(a_dev, b_dev, n, dpa.p, dpb.p, best.p);
-  closest_pass2_kernel<<<grid, 256, 0, s>>>(a_dev, b_dev, n, dpa.p, dpb.p, best.p, index.p);
+  for (i64 q0 = 0; q0 < npts; q0 += 32768) {  // one grid row per query: gridDim.y <= 65535
+    const i64 nq = std::min<i64>(32768, npts - q0);
+    dim3 grid(bx, (unsigned)nq);
+    closest_pass1_kernel<<<grid, 256, 0, s>>>(a_dev, b_dev, n, dpa.p + q0, dpb.p + q0, best.p + q0);
+    closest_pass2_kernel<<<grid, 256, 0, s>>>(a_dev, b_dev, n, dpa.p + q0, dpb.p + q0, best.p + q0, index.p + q0);
+  }
   RT_CUDA(cudaGetLastError());
   std::vector<u64> hi(npts);
   RT_CUDA(cudaMemcpyAsync(hi.data(), index.p, npts * sizeof(u64), cudaMemcpyDeviceToHost, s));
@@ -277,9 +358,10 @@ int prev_to_host_i64_staged(const i32* prev_dev, i64 count, i64* out, i64* stage
   return RT_OK;
 }
 
-// prev_dev: 0-based int32 table on the device.  receivers: host, 1-based.
+// prev_dev: 0-based int32 table on the device.  receivers: host, 1-based.  guarded = 1: the struct method
+// recontruct_path(D, source, receiver) (ssspm.jl:14-28) instead of the vector method (:30-40).
 int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* receivers, i64 nrec,
-                             i64* path_off, i64* path_idx, i64 cap) {
+                             i64* path_off, i64* path_idx, i64 cap, int guarded) {
   RT_ARG(prev_dev && receivers && path_off && nrec >= 0, "bad path arguments");
   RT_ARG(source >= 1 && source <= n, "source out of range");
   std::vector<i32> r32(nrec);
@@ -291,15 +373,21 @@ int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* 
   DevBuf<i64> len;
   RT_TRY(recv.upload(r32.data(), nrec));
   RT_TRY(len.alloc(nrec));
-  if (nrec) path_len_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, n, (i32)(source - 1), recv.p, nrec, len.p);
+  if (nrec) {
+    if (guarded)
+      path_len_guarded_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, n, recv.p, nrec, len.p);
+    else
+      path_len_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, n, (i32)(source - 1), recv.p, nrec, len.p);
+  }
   RT_CUDA(cudaGetLastError());
   std::vector<i64> hl(nrec);
   RT_CUDA(cudaMemcpy(hl.data(), len.p, nrec * sizeof(i64), cudaMemcpyDeviceToHost));
   path_off[0] = 0;
   for (i64 k = 0; k < nrec; ++k) {
     if (hl[k] < 0) {
-      rt_set_error("recontruct_path: receiver %lld does not reach source %lld", (long long)receivers[k],
-                   (long long)source);
+      rt_set_error(guarded ? "recontruct_path: the chase from receiver %lld (source %lld) reads an unset predecessor"
+                           : "recontruct_path: receiver %lld does not reach source %lld",
+                   (long long)receivers[k], (long long)source);
       return RT_ERR_NOPATH;
     }
     path_off[k + 1] = path_off[k] + hl[k];
@@ -310,9 +398,39 @@ int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* 
   DevBuf<i64> off, out;
   RT_TRY(off.upload(path_off, nrec + 1));
   RT_TRY(out.alloc(path_off[nrec]));
-  path_fill_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, (i32)(source - 1), recv.p, nrec, off.p, out.p);
+  if (guarded)
+    path_fill_guarded_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, (i32)(source - 1), recv.p, nrec, off.p, out.p);
+  else
+    path_fill_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, (i32)(source - 1), recv.p, nrec, off.p, out.p);
   RT_CUDA(cudaGetLastError());
   RT_CUDA(cudaMemcpy(path_idx, out.p, path_off[nrec] * sizeof(i64), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+int travel_times_device(const double* dist_dev, i64 n, i64 nsrc, const i64* receivers, i64 nrec, double* out) {
+  RT_ARG(dist_dev && receivers && out && n > 0 && nsrc >= 0 && nrec >= 0, "bad travel_times arguments");
+  for (i64 k = 0; k < nrec; ++k) RT_ARG(receivers[k] >= 1 && receivers[k] <= n, "receiver out of range");
+  if (nsrc * nrec == 0) return RT_OK;
+  DevBuf<i64> recv;
+  DevBuf<double> dout;
+  RT_TRY(recv.upload(receivers, nrec));
+  RT_TRY(dout.alloc(nsrc * nrec));
+  travel_times_kernel<<<grid_for(nsrc * nrec, 256), 256>>>(dist_dev, n, nsrc, recv.p, nrec, dout.p);
+  RT_CUDA(cudaGetLastError());
+  RT_CUDA(cudaMemcpy(out, dout.p, nsrc * nrec * sizeof(double), cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+int polardistance3d_device(const double* a, const double* b, i64 count, double* out) {
+  RT_ARG(a && b && out && count >= 0, "bad polardistance3D arguments");
+  if (count == 0) return RT_OK;
+  DevBuf<double> da, db, dout;
+  RT_TRY(da.upload(a, 3 * count));
+  RT_TRY(db.upload(b, 3 * count));
+  RT_TRY(dout.alloc(count));
+  polardistance3d_kernel<<<grid_for(count, 256), 256>>>(da.p, db.p, count, dout.p);
+  RT_CUDA(cudaGetLastError());
+  RT_CUDA(cudaMemcpy(out, dout.p, count * sizeof(double), cudaMemcpyDeviceToHost));
   return RT_OK;
 }
 
