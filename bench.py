@@ -10,10 +10,20 @@ and solves its own shard of the source batch (weak scaling, no collective inside
 travel-time / predecessor tables of a step are then all-gathered over NCCL inside the timed region.
 
 value   = TEPS_graph = E_graph * sources_solved / time   (Graph500-style: E_graph = sum of the reference's scan
-          list lengths, schedule independent, so the ratio against the CPU arm is a pure time ratio)
-roofline= HBM roofline of the relaxation kernel with the algorithmic bytes of SURVEY.md 8(d):
-          12 B per relaxed candidate + B_v per active-vertex update (52 B 2-D / 60 B 3-D), over the relax
-          kernel's own CUDA-event time on its launching stream.
+          list lengths, schedule independent)
+roofline= HBM roofline of the relaxation kernel with the algorithmic bytes of SURVEY.md 8(d): 12 B per relaxed
+          candidate + B_v per active-vertex update (52 B 2-D / 60 B 3-D) over the relax kernel's own CUDA-event time.
+          This is a THROUGHPUT figure in byte units of a flat-CSR model, not measured DRAM traffic (`traffic` is the
+          ncu figure); `roofline_fp64` next to it is the compute roofline that actually binds these kernels.
+
+Blocks added to the same JSON line (all measured in this run, after the timed region of the main metric):
+  same_config_check  GPU and CPU arm on the SAME meshes (annulus 180x50 @20 km and @5 km, arrays built once and handed to
+                     both), travel times compared bit for bit: the only GPU/CPU ratio that compares one problem.
+  batch_cfg3         BASELINE configs[2]: 512 sources on annulus 720x200, sharded over the N ranks, NCCL gather of the
+                     [512 x n] tables, gathered rows of foreign sources verified against fresh single solves on rank 0.
+  batch_cfg5         BASELINE configs[4] reduced to 8 sources per rank: 3-D 368^3, 1000-receiver recontruct_path sweep.
+  other_workloads    (N = 1) driver-run numbers for the other BASELINE shapes: 3-D 216^3 in both schedules, annulus
+                     180x50 @1 km.
 """
 import argparse
 import json
@@ -38,7 +48,7 @@ WORKLOADS = {
     "grid3d_64": dict(kind="3d", nn=(64, 64, 64), cpu_nn=(64, 64, 64), dim=3),
     # BASELINE.json configs[0]: README example, annulus 180x50, spacing 1 km
     "annulus_180_50_1km": dict(kind="2d", ntheta=180, nr=50, spacing=1.0, cpu=(180, 50, 20.0), dim=2),
-    "annulus_180_50_5km": dict(kind="2d", ntheta=180, nr=50, spacing=5.0, cpu=(180, 50, 20.0), dim=2),
+    "annulus_180_50_5km": dict(kind="2d", ntheta=180, nr=50, spacing=5.0, cpu=(180, 50, 5.0), dim=2),
     "annulus_180_50_20km": dict(kind="2d", ntheta=180, nr=50, spacing=20.0, cpu=(180, 50, 20.0), dim=2),
     # BASELINE.json configs[1]: annulus 1440x400, spacing 0.25 km (~107M nodes)
     "annulus_1440_400_0.25km": dict(kind="2d", ntheta=1440, nr=400, spacing=0.25, cpu=(180, 50, 20.0), dim=2),
@@ -48,6 +58,16 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = os.environ.get("RT_BENCH_WORKLOAD", "annulus_1440_400_0.25km")
 SHELL_C0 = (np.deg2rad(70.0), np.deg2rad(70.0), R - 2000.0)  # benchmarks/cpu.jl:9-13 rescaled to km
 SHELL_C1 = (np.deg2rad(110.0), np.deg2rad(110.0), R)
+# fp64 instructions per candidate of the push / relax kernels (SASS count of screen.h / exact.h, FMA = 1):
+DP_SCREEN, DP_EXACT = 12, 40
+
+
+def cpu_name(w):
+    """Name of the workload the CPU arm actually solves for GPU workload `w` (the reduced instance)."""
+    if w["kind"] == "3d":
+        return "grid3d_%d" % w["cpu_nn"][0]
+    nt, nr, sp = w["cpu"]
+    return "annulus_%d_%d_%gkm" % (nt, nr, sp)
 
 
 def peaks():
@@ -95,14 +115,17 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def ncu_traffic(kernel, workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` captures (profiles/traffic.json); None if that kernel / workload was not captured."""
+def ncu_record(kernel, workload):
+    """Per-launch figures of the dominant kernel read from the committed `ncu --set full` captures
+    (profiles/traffic.json): {"traffic": dram bytes read + written per launch, "fp64_pipe_pct": ...} or {}."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
-        return None
+        return {}
     t = json.load(open(p))
-    return t.get("%s@%s" % (kernel, workload))
+    v = t.get("%s@%s" % (kernel, workload))
+    if v is None:
+        return {}
+    return v if isinstance(v, dict) else {"traffic": v}
 
 
 def ak135():
@@ -112,7 +135,7 @@ def ak135():
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 class GpuWorkload:
-    def __init__(self, name, rt, torch, schedule="near-far", sps=1):
+    def __init__(self, name, rt, torch, schedule="near-far", sps=1, pinned=True):
         self.name, self.rt, self.torch = name, rt, torch
         self.w = WORKLOADS[name]
         prof = rt.velocity_profile()
@@ -144,22 +167,23 @@ class GpuWorkload:
             self.bv = 52
         self.sps = sps
         self.U_dev = torch.from_numpy(self.U_host).cuda()
-        self.dist_dev = torch.empty(self.n * sps, dtype=torch.float64, device="cuda")
-        self.prev_dev = torch.empty(self.n * sps, dtype=torch.int32, device="cuda")
+        # two sets of result tables: a step's NCCL gather may still read one while the next step writes the other
+        self.dist_dev = [torch.empty(self.n * sps, dtype=torch.float64, device="cuda") for _ in range(2)]
+        self.prev_dev = [torch.empty(self.n * sps, dtype=torch.int32, device="cuda") for _ in range(2)]
         self.handle.set_option("profile_timers", 0)
         self.schedule = schedule
         self.handle.set_option("schedule", {"jacobi": 0, "near-far": 1}[schedule])
-        # pinned host buffers of the end-to-end arm
-        self.U_pin = torch.from_numpy(self.U_host).pin_memory()
-        self.dist_pin = torch.empty(self.n * sps, dtype=torch.float64).pin_memory()
-        self.prev_pin = torch.empty(self.n * sps, dtype=torch.int64).pin_memory()
+        if pinned:  # pinned host buffers of the end-to-end arm
+            self.U_pin = torch.from_numpy(self.U_host).pin_memory()
+            self.dist_pin = torch.empty(self.n * sps, dtype=torch.float64).pin_memory()
+            self.prev_pin = torch.empty(self.n * sps, dtype=torch.int64).pin_memory()
 
-    def solve_dev(self, source):
+    def solve_dev(self, source, buf=0):
         import ctypes as C
         st = self.rt.RtStats()
         src = np.ascontiguousarray(np.atleast_1d(np.asarray(source, np.int64)))
         self.rt.api.check(self.rt.lib().rt_bfm_solve_dev(self.handle.h, self.U_dev.data_ptr(), src, len(src), 64,
-                                                         self.dist_dev.data_ptr(), self.prev_dev.data_ptr(),
+                                                         self.dist_dev[buf].data_ptr(), self.prev_dev[buf].data_ptr(),
                                                          C.byref(st)))
         return st.as_dict()
 
@@ -173,6 +197,300 @@ class GpuWorkload:
         return st.as_dict()
 
 
+def timed_solves(wl, sources, reps):
+    """Device-resident solves of `sources` (one per call), wall time per solve [ms] (median of reps) + last stats."""
+    ts = []
+    st = None
+    for k in range(reps):
+        t0 = time.perf_counter()
+        st = wl.solve_dev(sources[k % len(sources)])
+        ts.append((time.perf_counter() - t0) * 1e3)
+    return float(np.median(ts)), st
+
+
+def roofline_pass(wl, source, steps, peak, peak_src, workload, sm_mhz):
+    """Same solve with per-launch CUDA-event timers around the relaxation kernel (the timers force a host sync per
+    round, so this stays out of the timed region).  Returns (roofline, roofline_fp64, extras)."""
+    wl.handle.set_option("profile_timers", 1)
+    prof = dict(relaxed_edges=0, vertex_updates=0, relax_ms=0.0, relax_launches=0, kernel_ms=0.0, prev_ms=0.0,
+                screened_edges=0, exact_edges=0)
+    for k in range(steps):
+        st = wl.solve_dev(source)
+        for key in prof:
+            prof[key] += st[key]
+    wl.handle.set_option("profile_timers", 0)
+    kname = ("relax%s_kernel" if wl.schedule == "jacobi" else "push%s_kernel") % ("3d" if wl.w["kind"] == "3d" else "2d")
+    bytes_alg = prof["relaxed_edges"] * 12 + prof["vertex_updates"] * wl.bv
+    relax_s = max(prof["relax_ms"], 1e-9) * 1e-3
+    achieved = bytes_alg / relax_s / 1e9
+    rec = ncu_record(kname, workload)
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": rec.get("traffic"), "peak_source": peak_src, "kernel": kname,
+            "bytes_model": "12 B per relaxed candidate (nominal count: every (released source, target) pair of a "
+                           "released item) + %d B per active-vertex update; a flat-CSR throughput model, the measured "
+                           "DRAM traffic per launch is `traffic`" % wl.bv,
+            "avg_launch_ms": prof["relax_ms"] / max(prof["relax_launches"], 1)}
+    # compute roofline: fp64 instructions issued per second against the SM's fp64 issue rate (64 lanes / clk / SM)
+    clock = (sm_mhz or 1965.0) * 1e6
+    dp_peak = 148 * 64 * clock
+    if prof["screened_edges"] > 0:
+        dp_ops = prof["screened_edges"] * DP_SCREEN + prof["exact_edges"] * DP_EXACT
+        cand, note = prof["screened_edges"], "counted on the device: candidates that reached the screen x %d + exact evaluations x %d" % (DP_SCREEN, DP_EXACT)
+    else:  # kernels without the counters (3-D, Jacobi): every nominal candidate is assumed to reach the screen
+        dp_ops = prof["relaxed_edges"] * DP_SCREEN
+        cand, note = prof["relaxed_edges"], "upper bound: every nominal candidate x %d (no device counter for this kernel)" % DP_SCREEN
+    roof64 = {"bound": "fp64 issue", "dp_ops_per_cand": dp_ops / max(cand, 1), "achieved_dp_per_s": dp_ops / relax_s,
+              "peak": dp_peak, "peak_source": "148 SM x 64 fp64 lanes x %.0f MHz" % (clock / 1e6),
+              "frac": dp_ops / relax_s / dp_peak, "pipe_pct_ncu": rec.get("fp64_pipe_pct"), "how": note}
+    extras = {"relax_rate_gteps": prof["relaxed_edges"] / relax_s / 1e9,
+              "E_relaxed_nominal_per_source": prof["relaxed_edges"] / steps,
+              "E_evaluated_per_source": (prof["screened_edges"] / steps) if prof["screened_edges"] else None,
+              "E_exact_per_source": (prof["exact_edges"] / steps) if prof["screened_edges"] else None,
+              "relax_kernel_share_of_step": prof["relax_ms"] / max(prof["kernel_ms"], 1e-9),
+              "prev_pass_share_of_step": prof["prev_ms"] / max(prof["kernel_ms"], 1e-9)}
+    return roof, roof64, extras
+
+
+def same_config_check(rt, names=("annulus_180_50_20km", "annulus_180_50_5km")):
+    """GPU arm and CPU arm on the SAME problem: the mesh arrays are built once (oracle builder) and handed to both,
+    same AK135 velocity, same source; travel times compared bit for bit.  cpu = restated reference bfm (Jacobi,
+    OpenMP, all host threads); gpu = rt_bfm_solve_dev in both schedules (device-resident, median of 3)."""
+    import ctypes as C
+    import torch
+    from oracle import oracle as O
+    kr, kv = ak135()
+    cores = host_threads()
+    out = {}
+    for name in names:
+        w = WORKLOADS[name]
+        m = O.Annulus(w["ntheta"], w["nr"], w["spacing"])
+        U = O.interp_velocity(kr, kv, m.r)
+        src = O.closest_point(m.theta, m.r, 0.0, R)
+        t0 = time.perf_counter()
+        d_cpu, p_cpu, st_cpu = O.bfm(m, U, src, nthreads=cores)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        gr = rt.Grid2D(m.x, m.z, m.theta, m.r, m.e2n_off, m.e2n_idx, m.ntheta, m.nr, m.nel, m.n)
+        G = rt.SparseMatrixCSC(m.nel, m.n, m.G_colptr, m.G_rowval)
+        h = rt.mesh_from_arrays(gr, G, m.halo_matrix())
+        U_dev = torch.from_numpy(U).cuda()
+        dist = torch.empty(m.n, dtype=torch.float64, device="cuda")
+        prev = torch.empty(m.n, dtype=torch.int32, device="cuda")
+        srcs = np.array([src], np.int64)
+        rec = {"nodes": m.n, "graph_edges_per_source": st_cpu["graph_edges"], "cpu_ms": cpu_ms, "cpu_cores": cores,
+               "cpu_sweeps": st_cpu["sweeps"]}
+        for sched, key in ((1, "gpu_ms"), (0, "gpu_jacobi_ms")):
+            h.set_option("schedule", sched)
+            ts = []
+            for _ in range(4):
+                st = rt.RtStats()
+                t0 = time.perf_counter()
+                rt.api.check(rt.lib().rt_bfm_solve_dev(h.h, U_dev.data_ptr(), srcs, 1, 64, dist.data_ptr(),
+                                                       prev.data_ptr(), C.byref(st)))
+                ts.append((time.perf_counter() - t0) * 1e3)
+            rec[key] = float(np.median(ts[1:]))
+            eq = bool(np.array_equal(dist.cpu().numpy(), d_cpu))
+            rec["dist_bit_equal" if sched else "jacobi_dist_bit_equal"] = eq
+            if sched == 0:
+                rec["jacobi_prev_equal"] = bool(np.array_equal(prev.cpu().numpy().astype(np.int64) + 1, p_cpu))
+        rec["ratio"] = rec["cpu_ms"] / rec["gpu_ms"]
+        rec["ratio_same_schedule"] = rec["cpu_ms"] / rec["gpu_jacobi_ms"]
+        out[name] = rec
+        del h, gr, dist, prev, U_dev
+    return out
+
+
+def batch_cfg3(rt, torch, dist_mod, rank, world, nsrc=512):
+    """BASELINE configs[2]: 512 sources on annulus 720x200 (default spacing), AK135 == IASP91 file, full travel-time
+    tables, sources sharded round-robin over the ranks, one NCCL all_gather of the [512 x n] tables; rank 0 then
+    re-solves foreign sources one by one and compares them with the gathered rows."""
+    import ctypes as C
+    from raytracer_jl_b200 import sharded as sh
+    gr, G, halo = rt.init_annulus(720, 200, spacing=20.0, export=False)
+    h, n = gr._handle, gr.nnods
+    prof = rt.velocity_profile()
+    itp = rt.LinearInterpolation(prof.r, prof.Vp)
+    x_d, z_d, th_d, r_d = h.coords_dev()
+    U = torch.empty(n, dtype=torch.float64, device="cuda")
+    rt.api.check(rt.lib().rt_interp_velocity_dev(itp.knots, itp.values, len(itp.knots), r_d, n, -1.0, U.data_ptr()))
+    k = np.arange(nsrc)
+    sources = np.asarray(rt.closest_point(gr, 2 * np.pi * k / float(nsrc), np.full(nsrc, R), "polar"), np.int64)
+    h.set_option("schedule", 1)
+    stats = {}
+
+    def solve_fn(mine):
+        mine = np.ascontiguousarray(mine, np.int64)
+        d = torch.empty((len(mine), n), dtype=torch.float64, device="cuda")
+        p = torch.empty((len(mine), n), dtype=torch.int32, device="cuda")
+        st = rt.RtStats()
+        t0 = time.perf_counter()
+        rt.api.check(rt.lib().rt_bfm_solve_dev(h.h, U.data_ptr(), mine, len(mine), 64, d.data_ptr(), p.data_ptr(),
+                                               C.byref(st)))
+        torch.cuda.synchronize()
+        stats["solve_ms"] = (time.perf_counter() - t0) * 1e3
+        stats["st"] = st.as_dict()
+        return d, p
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist_mod.barrier()
+        torch.cuda.synchronize()
+
+    solve_fn(sources[rank::world][:8])  # warm-up: workspace allocation, kernels loaded
+    sync()
+    t0 = time.perf_counter()
+    d_all, p_all = sh.solve_sharded(solve_fn, sources, n, device="cuda")
+    sync()
+    total_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([total_ms, stats["solve_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+    total_ms, solve_ms = float(t[0]), float(t[1])
+    out = None
+    if rank == 0:
+        # verification: fresh single-source solves of sources owned by OTHER ranks (any at N = 1)
+        pick = [g for g in range(nsrc) if world == 1 or g % world != 0]
+        pick = [pick[(len(pick) * q) // 6] for q in range(6)]
+        d1 = torch.empty(n, dtype=torch.float64, device="cuda")
+        p1 = torch.empty(n, dtype=torch.int32, device="cuda")
+        ok_d, ok_p = True, True
+        for g in pick:
+            st = rt.RtStats()
+            rt.api.check(rt.lib().rt_bfm_solve_dev(h.h, U.data_ptr(), sources[g:g + 1].copy(), 1, 64, d1.data_ptr(),
+                                                   p1.data_ptr(), C.byref(st)))
+            ok_d = ok_d and bool(torch.equal(d1, d_all[g]))
+            ok_p = ok_p and bool(torch.equal(p1, p_all[g].to(torch.int32)))
+        rows_finite = bool(torch.isfinite(d_all).all())
+        src_zero = bool((d_all[torch.arange(nsrc, device="cuda"), torch.as_tensor(sources - 1, device="cuda")] == 0).all())
+        e_graph = stats["st"]["graph_edges"]
+        out = {"workload": "annulus_720_200_20km x %d sources (BASELINE configs[2])" % nsrc, "nodes": n,
+               "sources": nsrc, "ranks": world, "ms_total": total_ms, "ms_per_source": total_ms / nsrc,
+               "solve_ms_max_over_ranks": solve_ms, "gather_ms": max(total_ms - solve_ms, 0.0),
+               "gteps_graph": e_graph * nsrc / (total_ms * 1e-3) / 1e9,
+               "gathered_bytes": int(nsrc) * n * 12, "gather_verified": bool(ok_d and rows_finite and src_zero),
+               "verified_sources": [int(g) for g in pick], "prev_rows_equal": ok_p,
+               "rounds": stats["st"]["sweeps"], "launches_rank0": stats["st"]["total_launches"]}
+    del d_all, p_all, U, h, gr
+    torch.cuda.empty_cache()
+    return out
+
+
+def batch_cfg5(rt, torch, dist_mod, rank, world, per_rank=8, nrec=1000):
+    """BASELINE configs[4] with 8 sources per rank (64 at N = 8): 3-D 368^3 shell, star-1, near-far, travel-time and
+    predecessor tables gathered over NCCL, 1000-receiver recontruct_path sweep on the rank that owns the source."""
+    import ctypes as C
+    nn = (368, 368, 368)
+    g = rt.grid(SHELL_C0, SHELL_C1, nn, neighbour_levels=1, coord_system="spherical")
+    n = g.n
+    X, Y, Z = g.coordinates()
+    prof = rt.velocity_profile()
+    Uh = rt.interpolate_velocity(np.minimum(np.sqrt(X * X + Y * Y + Z * Z), R), rt.LinearInterpolation(prof.r, prof.Vp))
+    del X, Y, Z
+    U = torch.from_numpy(Uh).cuda()
+    nx, ny, nz = nn
+    nsrc = per_rank * world
+    # sources: regular lattice of surface nodes (k = nz); receivers: closest surface nodes to a 40 x 25 (theta, phi) lattice
+    lat = int(np.ceil(np.sqrt(nsrc)))
+    srcs = np.array([1 + (nx * (2 * (q % lat) + 1)) // (2 * lat) + nx * ((ny * (2 * (q // lat) + 1)) // (2 * lat) + ny * (nz - 1))
+                     for q in range(nsrc)], np.int64)
+    th = np.linspace(SHELL_C0[0], SHELL_C1[0], 40)
+    ph = np.linspace(SHELL_C0[1], SHELL_C1[1], nrec // 40)
+    TH, PH = np.meshgrid(th, ph, indexing="ij")
+    t0 = time.perf_counter()
+    recv = np.asarray(rt.closest_point(g, TH.reshape(-1), PH.reshape(-1), np.full(TH.size, R)), np.int64)
+    closest_ms = (time.perf_counter() - t0) * 1e3
+    g._handle.set_option("schedule", 1)
+    mine = np.ascontiguousarray(srcs[rank::world])
+    d = torch.empty((len(mine), n), dtype=torch.float64, device="cuda")
+    p = torch.empty((len(mine), n), dtype=torch.int32, device="cuda")
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist_mod.barrier()
+        torch.cuda.synchronize()
+
+    def solve(which, dd, pp):
+        st = rt.RtStats()
+        rt.api.check(rt.lib().rt_bfm_solve_dev(g._handle.h, U.data_ptr(), which, len(which), 64, dd.data_ptr(),
+                                               pp.data_ptr(), C.byref(st)))
+        return st.as_dict()
+
+    solve(mine[:1], d, p)  # warm-up
+    sync()
+    t0 = time.perf_counter()
+    st = solve(mine, d, p)
+    torch.cuda.synchronize()
+    solve_ms = (time.perf_counter() - t0) * 1e3
+    # receiver sweep on the owner: all paths of every owned source, straight from the device-resident prev table
+    tp = time.perf_counter()
+    npath = 0
+    for q in range(len(mine)):
+        off = np.zeros(len(recv) + 1, np.int64)
+        pq = p[q]
+        rt.api.check(rt.lib().rt_reconstruct_paths_dev(pq.data_ptr(), n, int(mine[q]), recv, len(recv), off, None, 0))
+        idx = np.zeros(int(off[-1]), np.int64)
+        rt.api.check(rt.lib().rt_reconstruct_paths_dev(pq.data_ptr(), n, int(mine[q]), recv, len(recv), off,
+                                                       idx.ctypes.data, len(idx)))
+        npath += int(off[-1])
+        if q == 0:
+            ends_ok = bool(np.all(idx[off[1:] - 1] == mine[q]) and np.all(idx[off[:-1]] == recv))
+    paths_ms = (time.perf_counter() - tp) * 1e3
+    tg = time.perf_counter()
+    if world > 1:
+        d_all = torch.empty((world * len(mine), n), dtype=torch.float64, device="cuda")
+        p_all = torch.empty((world * len(mine), n), dtype=torch.int32, device="cuda")
+        dist_mod.all_gather_into_tensor(d_all, d)
+        dist_mod.all_gather_into_tensor(p_all, p)
+    else:
+        d_all, p_all = d, p
+    sync()
+    gather_ms = (time.perf_counter() - tg) * 1e3
+    total_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([total_ms, solve_ms, paths_ms, gather_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        # gathered row r*k + q = source srcs[q*world + r]; verify one foreign source against a fresh solve
+        r_f, q_f = (1 % world), len(mine) - 1
+        g_src = srcs[q_f * world + r_f]
+        d1 = torch.empty((1, n), dtype=torch.float64, device="cuda")
+        p1 = torch.empty((1, n), dtype=torch.int32, device="cuda")
+        solve(np.array([g_src], np.int64), d1, p1)
+        row = r_f * len(mine) + q_f
+        ok = bool(torch.equal(d1[0], d_all[row])) and bool(torch.equal(p1[0], p_all[row]))
+        out = {"workload": "grid3d_368 star1 x %d sources, %d receivers (BASELINE configs[4], %d sources per rank)"
+                           % (nsrc, len(recv), per_rank), "nodes": n, "sources": nsrc, "ranks": world,
+               "ms_total": float(t[0]), "ms_per_source": float(t[0]) / nsrc, "solve_ms_max_over_ranks": float(t[1]),
+               "paths_ms": float(t[2]), "gather_ms": float(t[3]), "closest_point_ms_1000_queries": closest_ms,
+               "path_nodes_rank0": npath, "paths_end_at_source": ends_ok, "gathered_bytes": int(nsrc) * n * 12,
+               "gather_verified": ok, "gteps_graph": st["graph_edges"] * nsrc / (float(t[0]) * 1e-3) / 1e9}
+    del d_all, p_all, d, p, U, g
+    torch.cuda.empty_cache()
+    return out
+
+
+def other_workloads(rt, torch, peak, peak_src, sm_mhz):
+    """Driver-run numbers for the other BASELINE shapes (N = 1): device-resident single-source solves."""
+    out = {}
+    for name, scheds in (("grid3d_216", ("near-far", "jacobi")), ("annulus_180_50_1km", ("near-far",))):
+        for sched in scheds:
+            wl = GpuWorkload(name, rt, torch, sched, 1, pinned=False)
+            srcs = wl.sources[:5]
+            timed_solves(wl, srcs, 2)
+            ms, st = timed_solves(wl, srcs, 5)
+            roof, roof64, ex = roofline_pass(wl, srcs[0], 1, peak, peak_src, name, sm_mhz)
+            out["%s/%s" % (name, sched)] = {
+                "nodes": wl.n, "ms_per_source": ms, "teps_graph_gteps": st["graph_edges"] / (ms * 1e-3) / 1e9,
+                "sweeps": st["sweeps"], "relax_rate_gteps": ex["relax_rate_gteps"], "roofline_frac": roof["frac"],
+                "roofline_kernel": roof["kernel"], "roofline_fp64_frac": roof64["frac"],
+                "relax_kernel_share_of_step": ex["relax_kernel_share_of_step"]}
+            del wl
+            torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch
     import rt_loader
@@ -181,6 +499,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist_on = world > 1
+    dist = None
     if dist_on:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -191,6 +510,7 @@ def run_gpu(args):
     sps = args.sources_per_step
     n = wl.n
     gather_d = gather_p = None
+    gather_done = [None, None]
     if dist_on:
         gather_d = torch.empty(world * n * sps, dtype=torch.float64, device="cuda")
         gather_p = torch.empty(world * n * sps, dtype=torch.int32, device="cuda")
@@ -201,16 +521,24 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def pick(k):
+    def pick(k):  # every rank walks its own stride of the 65 sources -- at N = 1 too
         if sps == 1:
-            return wl.sources[(rank + k * world) % len(wl.sources)] if dist_on else wl.sources[0]
+            return wl.sources[(rank + k * world) % len(wl.sources)]
         return [wl.sources[(rank + (k * sps + q) * world) % len(wl.sources)] for q in range(sps)]
 
     def step(k):
-        st = wl.solve_dev(pick(k))
-        if dist_on:  # gather the travel-time tables of this step on every rank
-            dist.all_gather_into_tensor(gather_d, wl.dist_dev)
-            dist.all_gather_into_tensor(gather_p, wl.prev_dev)
+        buf = k & 1
+        if gather_done[buf] is not None:
+            # the library solves on its own stream: the gather (torch's NCCL stream) that last read this pair of
+            # tables must have finished before the solver overwrites them
+            gather_done[buf].synchronize()
+        st = wl.solve_dev(pick(k), buf)  # returns after the solver stream has drained: the tables are complete
+        if dist_on:  # gather the travel-time / predecessor tables of this step on every rank
+            dist.all_gather_into_tensor(gather_d, wl.dist_dev[buf])
+            dist.all_gather_into_tensor(gather_p, wl.prev_dev[buf])
+            ev = torch.cuda.Event()
+            ev.record()
+            gather_done[buf] = ev
         return st
 
     for k in range(args.warmup):
@@ -237,16 +565,11 @@ def run_gpu(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     wall_ms, dev_ms = float(times[0]), float(times[1])
 
-    # roofline pass: same step with per-launch CUDA-event timers around the relaxation kernel (the timers force a
-    # host sync per round, so they stay out of the timed region above)
-    wl.handle.set_option("profile_timers", 1)
-    prof = dict(relaxed_edges=0, vertex_updates=0, relax_ms=0.0, relax_launches=0, kernel_ms=0.0, prev_ms=0.0)
+    peak, peak_src = peaks()
+    sm_mhz = clocks["sm_mhz"] if clocks else None
     prof_steps = max(1, min(args.steps, 2))
-    for k in range(prof_steps):
-        st = wl.solve_dev(pick(0) if sps == 1 else wl.sources[0])
-        for key in prof:
-            prof[key] += st[key]
-    wl.handle.set_option("profile_timers", 0)
+    roof, roof64, ex = roofline_pass(wl, pick(0) if sps == 1 else wl.sources[0], prof_steps, peak, peak_src,
+                                     args.workload, sm_mhz)
 
     # end-to-end arm: same step through the host-buffer ABI call (H2D + D2H inside the timed region)
     e2e_steps = max(1, min(args.steps, 3))
@@ -261,14 +584,10 @@ def run_gpu(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms[0])
 
+    out = None
     if rank == 0:
-        peak, peak_src = peaks()
         nsolved = args.steps * world * sps
         value = e_graph * nsolved / (wall_ms * 1e-3) / 1e9
-        kname = ("relax%s_kernel" if wl.schedule == "jacobi" else "push%s_kernel") % ("3d" if wl.w["kind"] == "3d" else "2d")
-        bytes_alg = prof["relaxed_edges"] * 12 + prof["vertex_updates"] * wl.bv
-        relax_ms = max(prof["relax_ms"], 1e-9)
-        achieved = bytes_alg / (relax_ms * 1e-3) / 1e9
         out = {
             "metric": "sssp_relaxed_edges_per_s", "value": value, "unit": "GTEPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms / args.steps,
@@ -276,6 +595,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": args.workload, "nodes": n, "graph_edges_per_source": e_graph,
                        "sources_per_step_per_gpu": sps, "velocity": "AK135 Vp",
+                       "sources": "every rank walks its own stride of 65 surface sources (at N = 1 too)",
                        "schedule": "jacobi (reference sweeps)" if wl.schedule == "jacobi" else
                        "near-far push (dist bit-identical, prev exact except ties)",
                        "l2": "inputs larger than L2 (%.0f MB of node state per sweep set)" % (n * 48 / 1e6),
@@ -283,24 +603,37 @@ def run_gpu(args):
             "ms_per_source": wall_ms / args.steps / sps,
             "device_ms_per_step": dev_ms / args.steps,
             "teps_graph_gteps": value,
-            "relax_rate_gteps": (bytes_alg / 12.0) / (relax_ms * 1e-3) / 1e9,
-            "relaxed_edges_per_source": acc["relaxed_edges"] / args.steps,
+            "relax_rate_gteps": ex["relax_rate_gteps"],
+            "relaxed_edges_per_source": acc["relaxed_edges"] / args.steps / sps,
+            "E_relaxed_nominal_per_source": ex["E_relaxed_nominal_per_source"],
+            "E_evaluated_per_source": ex["E_evaluated_per_source"],
+            "E_exact_per_source": ex["E_exact_per_source"],
             "sweeps_per_source": acc["sweeps"] / args.steps,
-            "relax_kernel_share_of_step": relax_ms / max(prof["kernel_ms"], 1e-9),
-            "prev_pass_share_of_step": prof["prev_ms"] / max(prof["kernel_ms"], 1e-9),
+            "relax_kernel_share_of_step": ex["relax_kernel_share_of_step"],
+            "prev_pass_share_of_step": ex["prev_pass_share_of_step"],
             "gpu_launches": acc["total_launches"],
             "clocks": clocks,
             "e2e": {"value": e_graph * e2e_steps * world * sps / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS",
                     "ms_per_source": e2e_ms / e2e_steps / sps, "h2d_bytes_per_step": n * 8 + 8 * sps,
                     "d2h_bytes_per_step": n * 16 * sps},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(kname, args.workload),
-                         "peak_source": peak_src, "kernel": kname,
-                         "bytes_model": "12 B per relaxed candidate + %d B per active-vertex update" % wl.bv,
-                         "avg_launch_ms": relax_ms / max(prof["relax_launches"], 1)},
+            "roofline": roof, "roofline_fp64": roof64,
         }
+    # ---- blocks measured after the main metric (the big mesh is released first)
+    del wl, gather_d, gather_p
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        b3 = batch_cfg3(rt, torch, dist, rank, world)
+        b5 = batch_cfg5(rt, torch, dist, rank, world)
+        if rank == 0:
+            out["batch_cfg3"] = b3
+            out["batch_cfg5"] = b5
+            if world == 1:
+                out["other_workloads"] = other_workloads(rt, torch, peak, peak_src, sm_mhz)
+    if rank == 0:
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.workload, steps=1)
+            if not args.no_extras:
+                out["same_config_check"] = same_config_check(rt)
         print(json.dumps(out))
     if dist_on:
         dist.destroy_process_group()
@@ -319,14 +652,16 @@ def cpu_instance(workload):
         src = 1 + (nn[0] // 2) + nn[0] * ((nn[1] // 2) + nn[1] * (nn[2] - 1))
         run = lambda th: O.bfm3d(nn, 1, X, Y, Z, U, src, nthreads=th)
         desc = "3-D shell %dx%dx%d star1 (same grid family, reduced), full single-source solve" % nn
+        n = int(np.prod(nn))
     else:
         nt, nr, sp = w["cpu"]
         m = O.Annulus(nt, nr, sp)
         U = O.interp_velocity(kr, kv, m.r)
         src = O.closest_point(m.theta, m.r, 0.0, R)
         run = lambda th: O.bfm(m, U, src, nthreads=th)
-        desc = "annulus %dx%d spacing %g km (reduced spacing), full single-source solve" % (nt, nr, sp)
-    return run, desc
+        desc = "annulus %dx%d spacing %g km, full single-source solve" % (nt, nr, sp)
+        n = m.n
+    return run, desc, n
 
 
 def host_threads():
@@ -339,26 +674,32 @@ def host_threads():
 
 
 def cpu_baseline(workload, steps=1):
-    from oracle import oracle as O
-    run, desc = cpu_instance(workload)
+    run, desc, n = cpu_instance(workload)
     cores = host_threads()
     t0 = time.perf_counter()
     for _ in range(steps):
         d, p, st = run(cores)
     dt = (time.perf_counter() - t0) / steps
+    same = cpu_name(WORKLOADS[workload]) == workload
     return {"value": st["graph_edges"] / dt / 1e9, "unit": "GTEPS", "cores": cores, "kind": "port",
-            "sample": desc + "; TEPS_graph = E_graph / t; restated reference bfm (OpenMP, %d threads)" % cores,
+            "workload": cpu_name(WORKLOADS[workload]), "same_config": same, "nodes": n,
+            "graph_edges_per_source": st["graph_edges"],
+            "sample": desc + ("" if same else " -- a REDUCED instance of the GPU workload (the reference schedule needs "
+                              "hours on the full mesh): TEPS_graph is not size-invariant, see same_config_check for "
+                              "the like-for-like ratio") +
+                      "; TEPS_graph = E_graph / t; restated reference bfm (OpenMP, %d threads)" % cores,
             "ms_per_source": dt * 1e3, "relax_rate_gteps": st["relaxed_edges"] / dt / 1e9,
             "sweeps": st["sweeps"]}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (oracle port; Julia is not installed and the
-    reference has no compilable sources) on the host cores, same metric/unit, bounded sample per step."""
+    reference has no compilable sources) on the host cores, same metric/unit, bounded sample per step.  The record
+    names the mesh that was actually solved."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    run, desc = cpu_instance(args.workload)
+    run, desc, n = cpu_instance(args.workload)
     cores = host_threads()
     for _ in range(args.warmup):
         run(cores)
@@ -367,12 +708,21 @@ def run_reference(args):
         d, p, st = run(cores)
     dt = (time.perf_counter() - t0) / args.steps
     v = st["graph_edges"] / dt / 1e9
+    solved = cpu_name(WORKLOADS[args.workload])
+    same = solved == args.workload
     out = {"impl": "reference", "metric": "sssp_relaxed_edges_per_s", "value": v, "unit": "GTEPS",
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": args.workload, "graph_edges_per_source": st["graph_edges"]},
-           "cpu_baseline": {"value": v, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": desc},
+           "config": {"workload": solved, "requested_workload": args.workload, "same_config": same, "nodes": n,
+                      "graph_edges_per_source": st["graph_edges"], "schedule": "jacobi (reference sweeps)",
+                      "sweeps": st["sweeps"],
+                      "note": None if same else "bounded sample: the reference schedule on the requested mesh needs hours "
+                              "of CPU time, so a reduced-spacing instance of the same mesh family is solved; TEPS_graph "
+                              "is NOT size-invariant (sweeps grow with the mesh diameter): do not read value ratios "
+                              "across the two arms as a speed-up on one problem -- the GPU arm's same_config_check is"},
+           "cpu_baseline": {"value": v, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": desc,
+                            "workload": solved, "same_config": same},
            "e2e": {"value": v, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -384,7 +734,9 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / same_config_check legs")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="only the main metric (no batch_cfg3 / batch_cfg5 / other_workloads / same_config_check)")
     ap.add_argument("--schedule", default="near-far", choices=["jacobi", "near-far"])
     ap.add_argument("--sources-per-step", type=int, default=1,
                     help="sources solved per step and GPU (BASELINE config[2]: batches of earthquakes on one mesh)")

@@ -32,6 +32,8 @@ struct RtStats                                     # mirrors rt_stats (include/r
     relax_launches::Int64
     total_launches::Int64
     prev_ms::Float64
+    screened_edges::Int64
+    exact_edges::Int64
 end
 
 function check(rc::Cint)
@@ -162,7 +164,7 @@ function bfm_batch(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector
     n, ns = G.n, length(sources)
     dist = Matrix{Float64}(undef, n, ns)
     prev = Matrix{Int64}(undef, n, ns)
-    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0))
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0, 0, 0))
     check(ccall((:rt_bfm_solve, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
                 h.ptr, Vector{Float64}(U), sources, ns, precision, dist, prev, st))
@@ -177,7 +179,7 @@ function bfm_batch_multi(grids::Vector, sources::Vector{Int64}, U::AbstractArray
     n, ns = length(U), length(sources)
     dist = Matrix{Float64}(undef, n, ns)
     prev = Matrix{Int64}(undef, n, ns)
-    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0))
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0, 0, 0))
     check(ccall((:rt_bfm_solve_multi, LIB), Cint,
                 (Ptr{Ptr{Cvoid}}, Cint, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
                 hs, length(hs), Vector{Float64}(U), sources, ns, precision, dist, prev, st))
@@ -199,7 +201,7 @@ function bfm(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, source::Integer, gr, 
     n = G.n
     dist = Vector{Float64}(undef, n)
     prev = Vector{Int64}(undef, n)
-    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0))
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0, 0, 0))
     check(ccall((:rt_bfm_solve_dual, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
                 h.ptr, U, Int64[source], 1, dist, prev, st))
@@ -300,7 +302,7 @@ function BFM(gr::Grid3D, source::Integer, U::AbstractVector; precision::Integer 
     n = length(gr)
     dist = Vector{Float64}(undef, n)
     prev = Vector{Int64}(undef, n)
-    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0))
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0, 0, 0))
     check(ccall((:rt_bfm_solve, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
                 gr.handle.ptr, Vector{Float64}(U), Int64[source], 1, precision, dist, prev, st))

@@ -27,7 +27,7 @@ SYMBOLS = [
 class RtStats(C.Structure):
     _fields_ = [("sweeps", I64), ("relaxed_edges", I64), ("vertex_updates", I64), ("graph_edges", I64),
                 ("kernel_ms", C.c_double), ("relax_ms", C.c_double), ("relax_launches", I64),
-                ("total_launches", I64), ("prev_ms", C.c_double)]
+                ("total_launches", I64), ("prev_ms", C.c_double), ("screened_edges", I64), ("exact_edges", I64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

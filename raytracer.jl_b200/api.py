@@ -496,17 +496,21 @@ def _solve_dual(handle, n, U2, source):
 SCHEDULES = {"jacobi": 0, "near-far": 1}
 
 
-def bfm(G, halo, source, gr, U, schedule=None, delta=None, precision=64):
+def bfm(G, halo, source, gr, U, schedule=None, delta=None, precision=64, canonical_prev=None):
     """D = bfm(G, halo, source, gr, U) -- src/SSSP/bfm.jl:1-52.  `source` may be an array of sources, in which
     case D.dist / D.prev are [nsrc x n] tables (the batch API); a scalar gives vectors as in the reference.
 
     schedule (extension): "jacobi" = the reference's sweeps (dist and prev bit-identical, ties included);
     "near-far" = work-efficient push schedule (dist bit-identical, prev identical except on exact ties).
     precision=32: the Float32 arithmetic of bfm_gpu (src/SSSP/bfm_gpu.jl:170-205): x, z, U cast to Float32, travel
-    times relaxed in Float32; D.dist is a float32 array."""
+    times relaxed in Float32; D.dist is a float32 array.
+    canonical_prev=True (near-far): a post-pass rebuilds the reference's predecessors exactly, ties included
+    (rt_set_option "canonical_prev"; costs about one sweep over the graph)."""
     handle = mesh_from_arrays(gr, G, halo)
     if schedule is not None:
         handle.set_option("schedule", SCHEDULES[schedule])
+    if canonical_prev is not None:
+        handle.set_option("canonical_prev", 1 if canonical_prev else 0)
     if delta is not None:
         handle.set_option("delta", delta)
     if np.ndim(U) == 2:  # U::Matrix -> dual-velocity relax (bfm.jl:113-159)
@@ -519,9 +523,9 @@ def bfm(G, halo, source, gr, U, schedule=None, delta=None, precision=64):
     return BellmanFordMoore(prev, dist, st)
 
 
-def bfm_gpu(G, halo, source, gr, U, schedule=None):
+def bfm_gpu(G, halo, source, gr, U, schedule=None, canonical_prev=None):
     """bfm_gpu(G, halo, source, gr, U) src/SSSP/bfm_gpu.jl:212-250: the reference's Float32 device path."""
-    return bfm(G, halo, source, gr, U, schedule=schedule, precision=32)
+    return bfm(G, halo, source, gr, U, schedule=schedule, precision=32, canonical_prev=canonical_prev)
 
 
 def bfm3d(gr3, source, U, schedule=None, delta=None, precision=64):

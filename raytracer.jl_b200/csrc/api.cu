@@ -262,7 +262,10 @@ int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t ns
   cudaStream_t cs = m->stream;
   // sources go through in chunks so that small meshes can advance several sources in lock step while the
   // staging buffers stay bounded (<= 32 tables, <= ~2 GB)
-  i64 chunk = std::max<i64>(1, std::min<i64>(std::min<i64>(nsrc, 32), ((i64)1 << 28) / std::max<i64>(n, 1)));
+  // (2-D meshes of <= 4 M nodes advance up to 512 sources in lock step, see bfm2d_push.cu)
+  const bool wide = m->kind == 2 && n <= 4000000;
+  i64 chunk = std::max<i64>(1, std::min<i64>(std::min<i64>(nsrc, wide ? 512 : 32),
+                                             ((i64)1 << (wide ? 29 : 28)) / std::max<i64>(n, 1)));
   if (m->stage_U.n != (size_t)n) RT_TRY(m->stage_U.alloc(n));
   if (dist_out && m->stage_dist.n < (size_t)(chunk * n)) RT_TRY(m->stage_dist.alloc(chunk * n));
   if (prev_out && m->stage_prev.n < (size_t)(chunk * n)) {
@@ -289,6 +292,8 @@ int rt_bfm_solve(rt_mesh* m, const double* U, const int64_t* sources, int64_t ns
     total.relax_launches += st.relax_launches;
     total.total_launches += st.total_launches;
     total.prev_ms += st.prev_ms;
+    total.screened_edges += st.screened_edges;
+    total.exact_edges += st.exact_edges;
   }
   if (stats) *stats = total;
   return RT_OK;

@@ -70,7 +70,26 @@ struct PP {
   int warp_units;  // 1: short columns -> warp-per-item push (push2d_warp_body), 0: CTA per (item, element group)
   i64 n, n_items;
   const int* sources;  // [nb] 0-based
+  // flattened work of a batch round (written by round_begin): flat[0 .. nb] = exclusive prefix over the sources of
+  // the near-list slots of the sources that push this round, flat[FLAT_STRIDE + (0 .. nb)] = the same for the far-list
+  // slots of the sources whose threshold advances.  One launch then serves all sources with perfect load balance.
+  i64* flat;
 };
+constexpr int MAX_NB = 1024;          // sources advancing in lock step (one thread each in round_begin)
+constexpr int FLAT_STRIDE = MAX_NB + 1;
+
+// source that owns global slot g: largest b with base[b] <= g (sources without slots are skipped)
+__device__ __forceinline__ int flat_owner(const i64* __restrict__ base, int nb, i64 g) {
+  int lo = 0, hi = nb;  // invariant: base[lo] <= g < base[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (base[mid] <= g)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
 
 __device__ __forceinline__ i32* nq(const PP& p, int k) { return k ? p.nearq1 : p.nearq0; }
 __device__ __forceinline__ i32* fq(const PP& p, int k) { return k ? p.farq1 : p.farq0; }
@@ -366,7 +385,7 @@ __device__ __forceinline__ void push2d_body_t(const PP& p, const i32* near_cur, 
 // one warp owns one released item, no block barrier.  The element offsets of the column are fetched by the lanes
 // in parallel and prefix-summed, so the targets of ALL its elements form one flat index space that the lanes walk
 // with full utilisation (an element holds ~10 nodes there); sources sit in a warp-private shared-memory slab.
-template <bool PACKED, int MODE>
+template <bool PACKED, int MODE, bool COUNT = false>
 __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned mask, int cur, i32* near_next,
                                                  i32* far_list, int fcur, double tau, double2* sxz, double2* sUd, double2* sU2r,
                                                  int* s_id, int* s_pre, int* s_start) {
@@ -409,6 +428,7 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
   }
   const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
   u64 evals = 0;
+  unsigned n_scr = 0, n_ex = 0;  // COUNT: candidates that reached the screen / the exact evaluation (this lane)
   for (i64 cb0 = c0; cb0 < c1; cb0 += 32) {  // element batches of 32 (a column has <= 16 elements, the centre 2T)
     const int ne = (int)min((i64)32, c1 - cb0);
     int s_l = 0, m_l = 0;
@@ -454,6 +474,7 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
         const double2 ud = sUd[q];
         const double di = ud.y;
         if (!(di < best)) continue;
+        if (COUNT) ++n_scr;
         const double2 xz = sxz[q];
         double us = ud.x, ut = Uj;  // velocities of the source (head) and of the target (tail)
         if (DUAL) {
@@ -467,6 +488,7 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
           const double d2 = __fma_rn(dx, dx, dz * dz);
           if (screen_cannot_improve_t<F32>(best, di, d2, __dadd_rn(ut, us))) continue;
         }
+        if (COUNT) ++n_ex;
         const double delta = edge_delta<F32>(di, xz.x, xz.y, us, xj, zj, ut);
         if (PACKED) {
           const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
@@ -495,6 +517,16 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
     }
     __syncwarp();
   }
+  if (COUNT) {
+    for (int o = 16; o; o >>= 1) {
+      n_scr += __shfl_xor_sync(FULL, n_scr, o);
+      n_ex += __shfl_xor_sync(FULL, n_ex, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&p.counters[6], (u64)n_scr);
+      atomicAdd(&p.counters[7], (u64)n_ex);
+    }
+  }
   if (lane == 0) {
     atomicAdd(&p.counters[2], evals);
     atomicAdd(&p.counters[3], (u64)ns);
@@ -502,7 +534,7 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
 }
 
 // warp-level units of ONE source: slots of its near list
-template <int MODE>
+template <int MODE, bool COUNT = false>
 __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                                  i32* far_list, int fcur, i64 first_warp, i64 n_warps) {
   constexpr bool DUAL = MODE == MODE_DUAL;
@@ -516,11 +548,11 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
     if (mask == 0u) continue;
     if (p.ds == 2)
-      push2d_warp_unit<true, MODE>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
-                                   w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
+      push2d_warp_unit<true, MODE, COUNT>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
+                                          w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
     else
-      push2d_warp_unit<false, MODE>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
-                                    w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
+      push2d_warp_unit<false, MODE, COUNT>(p, it, mask, cur, near_next, far_list, fcur, tau, w_sxz[warp], w_sUd[warp],
+                                           w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
   }
 }
 
@@ -538,7 +570,7 @@ constexpr int FAR_EVERY = 3;  // the threshold-advance kernels are enqueued ever
 #endif
 constexpr int PUSH_SPLIT = RT_PUSH_SPLIT;     // max warps per (item, element) in sparse rounds
 constexpr int PUSH_FILL = RT_PUSH_FILL;  // warps the split aims to create (4 waves of resident warps; measured optimum is flat)
-template <bool PACKED, int MODE>
+template <bool PACKED, int MODE, bool COUNT = false>
 __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned mask, int e0, int sub, int kst, int cur,
                                                  i32* near_next,
                                                  i32* far_list, int fcur, double tau, double2* sxz, double2* sUd, double2* sU2r,
@@ -582,6 +614,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     }
   }
   u64 evals = 0;
+  unsigned n_scr = 0, n_ex = 0;  // COUNT: candidates that reached the screen / the exact evaluation (this lane)
   for (i64 c = c0 + e0; c < c1; c += PUSH_GE) {
     const int el = p.g_idx[c];
     const int s = p.e2n_off[el];
@@ -628,6 +661,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
           const double2 ud = sUd[q];
           const double di = ud.y;
           if (!(di < best)) continue;
+          if (COUNT) ++n_scr;
           const double2 xz = sxz[q];
           double us = ud.x, ut = Uj;  // velocities of the source (head) and of the target (tail)
           if (DUAL) {
@@ -641,6 +675,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
             const double d2 = __fma_rn(dx, dx, dz * dz);
             if (screen_cannot_improve_t<F32>(best, di, d2, __dadd_rn(ut, us))) continue;
           }
+          if (COUNT) ++n_ex;
           const double delta = edge_delta<F32>(di, xz.x, xz.y, us, xj, zj, ut);
           if (PACKED) {
             const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
@@ -680,12 +715,22 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     }
     if (sub == 0) evals += (u64)m * (u64)ns;
   }
+  if (COUNT) {
+    for (int o = 16; o; o >>= 1) {
+      n_scr += __shfl_xor_sync(FULL, n_scr, o);
+      n_ex += __shfl_xor_sync(FULL, n_ex, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&p.counters[6], (u64)n_scr);
+      atomicAdd(&p.counters[7], (u64)n_ex);
+    }
+  }
   if (lane == 0) {
     if (evals) atomicAdd(&p.counters[2], evals);
     if (e0 == 0 && sub == 0) atomicAdd(&p.counters[3], (u64)ns);
   }
 }
-template <int MODE>
+template <int MODE, bool COUNT = false>
 __device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                                  i32* far_list, int fcur, i64 first_warp, i64 n_warps) {
   constexpr bool DUAL = MODE == MODE_DUAL;
@@ -708,21 +753,21 @@ __device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cu
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
     if (mask == 0u) continue;
     if (p.ds == 2)
-      push2d_elem_unit<true, MODE>(p, it, mask, e0, sub, kst, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
-                                   e_sU2r[DUAL ? warp : 0], e_id[warp]);
+      push2d_elem_unit<true, MODE, COUNT>(p, it, mask, e0, sub, kst, cur, near_next, far_list, fcur, tau, e_sxz[warp],
+                                          e_sUd[warp], e_sU2r[DUAL ? warp : 0], e_id[warp]);
     else
-      push2d_elem_unit<false, MODE>(p, it, mask, e0, sub, kst, cur, near_next, far_list, fcur, tau, e_sxz[warp], e_sUd[warp],
-                                    e_sU2r[DUAL ? warp : 0], e_id[warp]);
+      push2d_elem_unit<false, MODE, COUNT>(p, it, mask, e0, sub, kst, cur, near_next, far_list, fcur, tau, e_sxz[warp],
+                                           e_sUd[warp], e_sU2r[DUAL ? warp : 0], e_id[warp]);
   }
 }
 
-template <bool WARP, int MODE>
+template <bool WARP, int MODE, bool COUNT = false>
 __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, int cur, i32* near_next,
                                             i32* far_list, int fcur) {
   if (WARP) {
     const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
-    push2d_warp_body<MODE>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
+    push2d_warp_body<MODE, COUNT>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
   } else if (p.cta_units) {
     if (p.ds == 2)
       push2d_body_t<true>(p, near_cur, cur, near_next, far_list, fcur);
@@ -731,14 +776,16 @@ __device__ __forceinline__ void push2d_body(const PP& p, const i32* near_cur, in
   } else {
     const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
-    push2d_elem_body<MODE>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
+    push2d_elem_body<MODE, COUNT>(p, near_cur, cur, near_next, far_list, fcur, gw, nw);
   }
 }
+// host-driven rounds with profiling timers (single source): also counts the candidates that reach the screen and the
+// exact evaluation (rt_stats.screened_edges / exact_edges) -- the counting costs a few percent, so only here
 template <bool WARP, int MODE>
 __global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_kernel(PP p, const i32* __restrict__ near_cur, int cur,
                                                            i32* __restrict__ near_next, i32* __restrict__ far_list,
                                                            int fcur) {
-  push2d_body<WARP, MODE>(p, near_cur, cur, near_next, far_list, fcur);
+  push2d_body<WARP, MODE, true>(p, near_cur, cur, near_next, far_list, fcur);
 }
 
 // threshold advance, step 1: smallest waiting value
@@ -949,85 +996,184 @@ __global__ void prev_halo_init_kernel(PP pb, const i32* __restrict__ hnode, cons
 // after_far: the far kernels were enqueued between the previous round_begin and this one.  They are only enqueued
 // every FAR_EVERY-th round (in most rounds they have nothing to do), so a source whose threshold advance has been
 // requested (mode 2) stays put -- prep / push return at once -- until a round_begin that follows them.
-__global__ void round_begin_kernel(PP pb, int after_far) {
-  if ((int)threadIdx.x >= pb.nb) return;
-  const PP p = pp_view(pb, threadIdx.x);
-  int* c = p.ctl;
-  if (c[3]) return;
-  if (c[2] == 2 && !after_far) return;
-  if (c[2] == 1)
-    c[0] ^= 1;
-  else if (c[2] == 2)
-    c[1] ^= 1;
-  const int cur = c[0], fcur = c[1];
-  const u64 n_near = p.counters[cur], n_far = p.counters[4 + fcur];
-  if (n_near == 0 && n_far == 0) {
-    c[2] = 0;
-    c[3] = 1;
-    return;
+template <int BS>
+__global__ void __launch_bounds__(BS) round_begin_kernel(PP pb, int after_far) {
+  const int b = threadIdx.x;
+  i64 cn = 0, cf = 0;  // this source's near slots to push / far slots to advance in the coming round
+  if (b < pb.nb) {
+    const PP p = pp_view(pb, b);
+    int* c = p.ctl;
+    if (!c[3] && !(c[2] == 2 && !after_far)) {
+      if (c[2] == 1)
+        c[0] ^= 1;
+      else if (c[2] == 2)
+        c[1] ^= 1;
+      const int cur = c[0], fcur = c[1];
+      const u64 n_near = p.counters[cur], n_far = p.counters[4 + fcur];
+      if (n_near == 0 && n_far == 0) {
+        c[2] = 0;
+        c[3] = 1;
+      } else {
+        c[4] += 1;
+        if (n_near > 0) {
+          c[2] = 1;
+          c[5] += 1;
+          p.counters[cur ^ 1] = 0;
+        } else {
+          c[2] = 2;
+          p.tau[2] = __longlong_as_double(-1LL);
+          p.counters[4 + (fcur ^ 1)] = 0;
+        }
+      }
+    }
+    if (!c[3]) {
+      if (c[2] == 1) cn = (i64)p.counters[c[0]];
+      if (c[2] == 2) cf = (i64)p.counters[4 + c[1]];
+    }
   }
-  c[4] += 1;
-  if (n_near > 0) {
-    c[2] = 1;
-    c[5] += 1;
-    p.counters[cur ^ 1] = 0;
+  if (BS == 32) {  // nb <= 32: warp scan
+    i64 in = cn, fi = cf;
+    for (int o = 1; o < 32; o <<= 1) {
+      const i64 a = __shfl_up_sync(FULL, in, o), f = __shfl_up_sync(FULL, fi, o);
+      if (b >= o) {
+        in += a;
+        fi += f;
+      }
+    }
+    if (b < pb.nb) {
+      pb.flat[b + 1] = in;
+      pb.flat[FLAT_STRIDE + b + 1] = fi;
+    }
+    if (b == 0) {
+      pb.flat[0] = 0;
+      pb.flat[FLAT_STRIDE] = 0;
+    }
   } else {
-    c[2] = 2;
-    p.tau[2] = __longlong_as_double(-1LL);
-    p.counters[4 + (fcur ^ 1)] = 0;
+    __shared__ i64 sn[BS], sf[BS];
+    sn[b] = cn;
+    sf[b] = cf;
+    __syncthreads();
+    for (int o = 1; o < BS; o <<= 1) {  // Hillis-Steele inclusive scan
+      const i64 a = b >= o ? sn[b - o] : 0, f = b >= o ? sf[b - o] : 0;
+      __syncthreads();
+      sn[b] += a;
+      sf[b] += f;
+      __syncthreads();
+    }
+    if (b < pb.nb) {
+      pb.flat[b + 1] = sn[b];
+      pb.flat[FLAT_STRIDE + b + 1] = sf[b];
+    }
+    if (b == 0) {
+      pb.flat[0] = 0;
+      pb.flat[FLAT_STRIDE] = 0;
+    }
   }
 }
 __global__ void prep_dc_kernel(PP pb) {
-  const PP p = pp_view(pb, blockIdx.y);
-  if (p.ctl[2] != 1) return;
-  const int cur = p.ctl[0];
-  const i32* near_cur = nq(p, cur);
-  const i64 n = (i64)p.counters[cur];
-  for (i64 slot = (i64)blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += (i64)gridDim.x * blockDim.x)
-    p.cur_mask[slot] = atomicExch(&p.pend_mask[near_cur[slot]], 0u);
+  const int nb = pb.nb;
+  const i64* base = pb.flat;
+  const i64 total = base[nb];
+  for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (i64)gridDim.x * blockDim.x) {
+    const int b = flat_owner(base, nb, g);
+    const i64 slot = g - base[b];
+    const i64 o = (i64)b * pb.n_items;
+    const i32* near_cur = (pb.ctl[b * 8] ? pb.nearq1 : pb.nearq0) + o;
+    pb.cur_mask[o + slot] = atomicExch(&pb.pend_mask[o + near_cur[slot]], 0u);
+  }
 }
 template <bool WARP, int MODE>
 __global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_dc_kernel(PP pb) {
-  const PP p = pp_view(pb, blockIdx.y);
-  if (p.ctl[2] != 1) return;
-  const int cur = p.ctl[0], fcur = p.ctl[1];
-  push2d_body<WARP, MODE>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
-}
-__global__ void far_min_dc_kernel(PP pb) {
-  const PP p = pp_view(pb, blockIdx.y);
-  if (p.ctl[2] != 2) return;
-  const int fcur = p.ctl[1];
-  const i32* far_cur = fq(p, fcur);
-  const i64 nslots = (i64)p.counters[4 + fcur];
-  const int lane = threadIdx.x & 31;
-  u64 best = ~0ull;
-  for (i64 slot = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < nslots;
-       slot += ((i64)gridDim.x * blockDim.x) >> 5) {
-    const int it = far_cur[slot];
-    const unsigned m = p.far_mask[it];
-    if ((m >> lane) & 1u) {
-      const u64 b = (u64)__double_as_longlong(p.dist[(i64)(p.item_first[it] + lane) * p.ds]);
-      best = b < best ? b : best;
+  if (WARP) {
+    // warp-level units of ALL sources in one flat index space (slot g of the concatenated near lists)
+    constexpr bool DUAL = MODE == MODE_DUAL;
+    __shared__ double2 w_sxz[PUSH_BLOCK / 32][32], w_sUd[PUSH_BLOCK / 32][32], w_sU2r[DUAL ? PUSH_BLOCK / 32 : 1][32];
+    __shared__ int w_id[PUSH_BLOCK / 32][32], w_pre[PUSH_BLOCK / 32][32], w_start[PUSH_BLOCK / 32][32];
+    const int warp = threadIdx.x >> 5;
+    const int nb = pb.nb;
+    const i64* base = pb.flat;
+    const i64 total = base[nb];
+    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 g = gw; g < total; g += nw) {
+      const int b = nb == 1 ? 0 : flat_owner(base, nb, g);
+      const i64 slot = g - base[b];
+      const PP p = pp_view(pb, b);
+      const int cur = p.ctl[0], fcur = p.ctl[1];
+      const int it = __ldcg(&nq(p, cur)[slot]);
+      const unsigned mask = __ldcg(&p.cur_mask[slot]);
+      if (mask == 0u) continue;
+      const double tau = __ldcg(&p.tau[0]);
+      if (p.ds == 2)
+        push2d_warp_unit<true, MODE>(p, it, mask, cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tau, w_sxz[warp], w_sUd[warp],
+                                     w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
+      else
+        push2d_warp_unit<false, MODE>(p, it, mask, cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tau, w_sxz[warp], w_sUd[warp],
+                                      w_sU2r[DUAL ? warp : 0], w_id[warp], w_pre[warp], w_start[warp]);
     }
+  } else {
+    const PP p = pp_view(pb, blockIdx.y);
+    if (p.ctl[2] != 1) return;
+    const int cur = p.ctl[0], fcur = p.ctl[1];
+    push2d_body<WARP, MODE>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
   }
-  for (int o = 16; o; o >>= 1) {
-    const u64 other = __shfl_xor_sync(FULL, best, o);
-    best = other < best ? other : best;
+}
+// threshold advance over the concatenated far lists of the advancing sources: warp per far-list slot
+__global__ void far_min_dc_kernel(PP pb) {
+  const int nb = pb.nb;
+  const i64* base = pb.flat + FLAT_STRIDE;
+  const i64 total = base[nb];
+  const int lane = threadIdx.x & 31;
+  const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+  // a warp takes a contiguous chunk of slots so that it usually stays inside one source (one atomic per chunk)
+  const i64 chunk = max((i64)1, min((i64)64, (total + nw - 1) / nw));
+  for (i64 g0 = gw * chunk; g0 < total; g0 += nw * chunk) {
+    int b = nb == 1 ? 0 : flat_owner(base, nb, g0);
+    u64 best = ~0ull;
+    const i64 g1 = min(total, g0 + chunk);
+    for (i64 g = g0; g < g1; ++g) {
+      while (g >= base[b + 1]) {  // crossed into the next source: flush
+        for (int o = 16; o; o >>= 1) {
+          const u64 other = __shfl_xor_sync(FULL, best, o);
+          best = other < best ? other : best;
+        }
+        if (lane == 0 && best != ~0ull) atomicMin((u64*)&pb.tau[(i64)b * 4 + 2], best);
+        best = ~0ull;
+        ++b;
+      }
+      const i64 o = (i64)b * pb.n_items;
+      const i32* far_cur = (pb.ctl[b * 8 + 1] ? pb.farq1 : pb.farq0) + o;
+      const int it = far_cur[g - base[b]];
+      const unsigned m = pb.far_mask[o + it];
+      if ((m >> lane) & 1u) {
+        const u64 v = (u64)__double_as_longlong(pb.dist[((i64)b * pb.n + pb.item_first[it] + lane) * pb.ds]);
+        best = v < best ? v : best;
+      }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const u64 other = __shfl_xor_sync(FULL, best, o);
+      best = other < best ? other : best;
+    }
+    if (lane == 0 && best != ~0ull) atomicMin((u64*)&pb.tau[(i64)b * 4 + 2], best);
   }
-  if (lane == 0 && best != ~0ull) atomicMin((u64*)&p.tau[2], best);
 }
 __global__ void far_release_dc_kernel(PP pb) {
-  const PP p = pp_view(pb, blockIdx.y);
-  if (p.ctl[2] != 2) return;
-  const int cur = p.ctl[0], fcur = p.ctl[1];
-  const i32* far_cur = fq(p, fcur);
-  i32* far_next = fq(p, fcur ^ 1);
-  i32* near_next = nq(p, cur);
-  const i64 nslots = (i64)p.counters[4 + fcur];
+  const int nb = pb.nb;
+  const i64* base = pb.flat + FLAT_STRIDE;
+  const i64 total = base[nb];
   const int lane = threadIdx.x & 31;
-  const double tau = __dadd_rn(p.tau[2], p.tau[1]);
-  for (i64 slot = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < nslots;
-       slot += ((i64)gridDim.x * blockDim.x) >> 5) {
+  const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
+  for (i64 g = gw; g < total; g += nw) {
+    const int b = nb == 1 ? 0 : flat_owner(base, nb, g);
+    const i64 slot = g - base[b];
+    const PP p = pp_view(pb, b);
+    const int cur = p.ctl[0], fcur = p.ctl[1];
+    const i32* far_cur = fq(p, fcur);
+    i32* far_next = fq(p, fcur ^ 1);
+    i32* near_next = nq(p, cur);
+    const double tau = __dadd_rn(p.tau[2], p.tau[1]);
     const int it = far_cur[slot];
     const unsigned m = p.far_mask[it];
     const bool mine = (m >> lane) & 1u;
@@ -1220,7 +1366,7 @@ __global__ void halo_prev_fix_kernel(PP pb, const i32* __restrict__ h2, i64 rows
     p.prev[b] = t;  // unresolved chain: the twin itself is a valid zero-weight predecessor
 }
 
-int ensure_push_workspace(rt_mesh* h, int nb, bool packed) {
+int ensure_push_workspace(rt_mesh* h, int nb, bool packed, bool need_bdist) {
   Mesh2D& m = *h->m2;
   cudaStream_t s = h->stream;
   if (!m.push_ready) {
@@ -1249,11 +1395,14 @@ int ensure_push_workspace(rt_mesh* h, int nb, bool packed) {
     RT_TRY(m.bcounters.alloc(B * 8));
     RT_TRY(m.bsources.alloc(B));
     RT_TRY(m.bprev.alloc(B * m.n));
-    RT_TRY(m.bdist.alloc(B * m.n));
+    m.bdist.release();
     m.dp.release();
     m.push_nb = nb;
   }
+  if (!m.flat.p) RT_TRY(m.flat.alloc(2 * FLAT_STRIDE));
   if (packed && !m.dp.p) RT_TRY(m.dp.alloc(2 * (size_t)m.n * (size_t)m.push_nb));
+  // plain travel-time tables: only the separate-pass mode keeps them here, or a caller that passes no dist buffer
+  if ((!packed || need_bdist) && !m.bdist.p) RT_TRY(m.bdist.alloc((size_t)m.push_nb * m.n));
   return RT_OK;
 }
 
@@ -1317,16 +1466,24 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   const i64 n = m.n;
   const bool timers = h->opts.profile_timers != 0;
   const bool packed = h->opts.packed_prev != 0;
-  // batch width: small meshes leave the GPU idle per round, so several sources advance in lock step
+  // batch width: small meshes leave the GPU idle per round, so many sources advance in lock step: every launch of a
+  // round serves the concatenated near / far lists of all of them (flat index space, see round_begin_kernel)
+  const int warp_units =
+      (h->opts.warp_units == 1 || (h->opts.warp_units < 0 && m.graph_edges / std::max<i64>(n, 1) < 1500)) ? 1 : 0;
   int nb = 1;
   if (!timers && packed && nsrc > 1 && n <= 4000000) {
     const i64 per_src = n * 32 + m.n_items * 40;
-    nb = (int)std::min<i64>(std::min<i64>(nsrc, h->opts.batch > 0 ? h->opts.batch : 32),
-                            std::max<i64>(1, ((i64)6 << 30) / per_src));
-    nb = std::max(1, std::min(nb, 32));
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const i64 budget = std::max<i64>((i64)6 << 30, (i64)(free_b / 3));
+    // the long-column units keep one grid row per source (<= 32); the warp-per-item units are flattened
+    const i64 cap = warp_units ? MAX_NB : 32;
+    nb = (int)std::min<i64>(std::min<i64>(nsrc, h->opts.batch > 0 ? std::min<i64>(h->opts.batch, cap) : (warp_units ? 512 : 32)),
+                            std::max<i64>(1, budget / per_src));
+    nb = std::max(1, nb);
   }
   if (timers || !packed) RT_TRY(bfm2d_ensure_workspace(h));  // pinned counter mirror of the host-driven paths
-  RT_TRY(ensure_push_workspace(h, nb, packed));
+  RT_TRY(ensure_push_workspace(h, nb, packed, dist_dev == nullptr));
   nb = std::min(nb, m.push_nb);
   PP p;
   p.x = f32 ? m.xf.p : m.x.p;
@@ -1363,7 +1520,8 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   p.farq1 = m.farq[1].p;
   p.ctl = m.ctl.p;
   p.nb = 1;
-  p.warp_units = (h->opts.warp_units == 1 || (h->opts.warp_units < 0 && m.graph_edges / std::max<i64>(n, 1) < 1500)) ? 1 : 0;
+  p.warp_units = warp_units;
+  p.flat = m.flat.p;
   p.cta_units = h->opts.cta_units;
   p.n = n;
   p.n_items = m.n_items;
@@ -1403,8 +1561,8 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   // persistent kernel wins while the frontier is small (few grid-wide barriers beat 5 launches per round); large
   // meshes are better served by hardware block scheduling of the batched launches
   const bool small_mesh = (i64)n * nb <= 1500000 || (nb > 1 && n <= 1500000);
-  const bool use_persistent =
-      !timers && coop_blocks > 0 && (h->opts.persistent == 1 || (h->opts.persistent < 0 && small_mesh));
+  const bool use_persistent = !timers && coop_blocks > 0 && nb <= 32 &&
+                              (h->opts.persistent == 1 || (h->opts.persistent < 0 && small_mesh));
   std::vector<int> hsrc(nb);
   std::vector<int> hctl((size_t)nb * 8);
   std::vector<u64> hcnt((size_t)nb * 8);
@@ -1455,20 +1613,24 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
       // device-controlled rounds, host sync every `check_every` rounds
       const int R = h->opts.check_every > 1 ? h->opts.check_every : 32;
       const unsigned gsmall = (unsigned)(sm_count * 2);
-      const unsigned gpush = (unsigned)std::max<i64>(sm_count, max_blocks / B);
+      // long-column units: one grid row per source; warp-per-item units: one flat grid over all sources
+      const dim3 gpush = p.warp_units ? dim3((unsigned)max_blocks, 1) : dim3((unsigned)std::max<i64>(sm_count, max_blocks / B), B);
       bool all_done = false;
       int after_far = 1;  // nothing is pending before the first round
       i64 enq_rounds = 0;
       while (!all_done) {
         for (int r = 0; r < R; ++r) {
-          round_begin_kernel<<<1, 32, 0, s>>>(p, after_far);
-          prep_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
-          launch_push_dc(p.warp_units != 0, mode, dim3(gpush, B), s, p);
+          if (B <= 32)
+            round_begin_kernel<32><<<1, 32, 0, s>>>(p, after_far);
+          else
+            round_begin_kernel<MAX_NB><<<1, MAX_NB, 0, s>>>(p, after_far);
+          prep_dc_kernel<<<gsmall, 256, 0, s>>>(p);
+          launch_push_dc(p.warp_units != 0, mode, gpush, s, p);
           st.total_launches += 3;
           after_far = 0;
           if (r % FAR_EVERY == FAR_EVERY - 1 || r == R - 1) {
-            far_min_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
-            far_release_dc_kernel<<<dim3(gsmall, B), 256, 0, s>>>(p);
+            far_min_dc_kernel<<<gsmall, 256, 0, s>>>(p);
+            far_release_dc_kernel<<<gsmall, 256, 0, s>>>(p);
             st.total_launches += 2;
             after_far = 1;
           }
@@ -1550,6 +1712,10 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
     for (int b = 0; b < B; ++b) {
       st.relaxed_edges += (i64)hcnt[b * 8 + 2];
       st.vertex_updates += (i64)hcnt[b * 8 + 3];
+      if (timers) {
+        st.screened_edges += (i64)hcnt[b * 8 + 6];
+        st.exact_edges += (i64)hcnt[b * 8 + 7];
+      }
     }
     // ---- predecessors
     cudaEventRecord(evr0, s);
@@ -1605,6 +1771,17 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
       if (rc != RT_OK) break;
       if (n_un > 0) prev_giveup_kernel<<<grid_for(n_un, 256), 256, 0, s>>>(p, m.unresolved[ucur].p, n_un);
       if (dist_dev) cudaMemcpyAsync(dist_out, m.bdist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    }
+    if (h->opts.canonical_prev) {
+      // reference predecessors, exact ties included (canonical_prev.cu); the travel-time tables are final here
+      for (int b = 0; b < B && rc == RT_OK; ++b) {
+        i64 launches = 0;
+        const double* dsrc = (packed || dist_dev) ? dist_out + (i64)b * n : m.bdist.p;
+        rc = canonical_prev_2d(h, p.x, p.z, p.U1, dual ? p.U2 : nullptr, mode, dsrc, hsrc[b], m.bprev.p + (i64)b * n,
+                               nullptr, &launches);
+        st.total_launches += launches;
+      }
+      if (rc != RT_OK) break;
     }
     cudaEventRecord(evr1, s);
     cudaEventRecord(ev1, s);

@@ -11,9 +11,18 @@
 
 namespace {
 
-__global__ void cvt_i64_i32_kernel(const i64* __restrict__ src, i32* __restrict__ dst, i64 count, i64 bias) {
+// narrowing happens only after the 64-bit value was range checked: an id such as 2^32 + 5 must not wrap into a valid one
+__global__ void cvt_i64_i32_kernel(const i64* __restrict__ src, i32* __restrict__ dst, i64 count, i64 bias, i64 lo,
+                                   i64 hi, int* bad) {
   i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) dst[i] = (i32)(src[i] + bias);
+  if (i >= count) return;
+  const i64 v = src[i] + bias;
+  if (v < lo || v >= hi) {
+    *bad = 1;
+    dst[i] = 0;
+  } else {
+    dst[i] = (i32)v;
+  }
 }
 __global__ void cvt_i64_i64_kernel(const i64* __restrict__ src, i64* __restrict__ dst, i64 count, i64 bias) {
   i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,19 +364,26 @@ int mesh2d_from_host(rt_mesh* h, i64 n, i64 nel, const i64* e2n_off, const i64* 
   }
   {
     DevBuf<i64> tmp;
+    DevBuf<int> bad;
+    RT_TRY(bad.alloc(1));
+    RT_TRY(bad.zero(s));
     RT_TRY(tmp.upload(e2n_off, nel + 1, s));
     RT_TRY(m.e2n_off.alloc(nel + 1));
-    cvt_i64_i32_kernel<<<grid_for(nel + 1, 256), 256, 0, s>>>(tmp.p, m.e2n_off.p, nel + 1, 0);
+    cvt_i64_i32_kernel<<<grid_for(nel + 1, 256), 256, 0, s>>>(tmp.p, m.e2n_off.p, nel + 1, 0, 0, m.sum_e2n + 1, bad.p);
     RT_TRY(tmp.upload(e2n_idx, m.sum_e2n, s));
     RT_TRY(m.e2n_idx.alloc(m.sum_e2n));
-    if (m.sum_e2n) cvt_i64_i32_kernel<<<grid_for(m.sum_e2n, 256), 256, 0, s>>>(tmp.p, m.e2n_idx.p, m.sum_e2n, -1);
+    if (m.sum_e2n)
+      cvt_i64_i32_kernel<<<grid_for(m.sum_e2n, 256), 256, 0, s>>>(tmp.p, m.e2n_idx.p, m.sum_e2n, -1, 0, n, bad.p);
     RT_TRY(tmp.upload(colptr, n + 1, s));
     RT_TRY(m.g_off.alloc(n + 1));
     cvt_i64_i64_kernel<<<grid_for(n + 1, 256), 256, 0, s>>>(tmp.p, m.g_off.p, n + 1, -1);
     RT_TRY(tmp.upload(rowval, m.nnzG, s));
     RT_TRY(m.g_idx.alloc(m.nnzG));
-    if (m.nnzG) cvt_i64_i32_kernel<<<grid_for(m.nnzG, 256), 256, 0, s>>>(tmp.p, m.g_idx.p, m.nnzG, -1);
+    if (m.nnzG) cvt_i64_i32_kernel<<<grid_for(m.nnzG, 256), 256, 0, s>>>(tmp.p, m.g_idx.p, m.nnzG, -1, 0, nel, bad.p);
+    int hb = 0;
+    RT_CUDA(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     RT_CUDA(cudaStreamSynchronize(s));
+    RT_ARG(hb == 0, "graph arrays hold ids outside 1..n / 1..nel (checked as 64-bit values before narrowing)");
   }
   return mesh2d_finalize(h, halo);
 }
@@ -437,6 +453,7 @@ int mesh2d_export(const rt_mesh* h, double* x, double* z, double* theta, double*
 void mesh2d_free(rt_mesh* h) {
   if (h->m2) {
     if (h->m2->counters_host) cudaFreeHost(h->m2->counters_host);
+    if (h->m2->canon) canon_ws_free(h->m2->canon);
     delete h->m2;
   }
   h->m2 = nullptr;

@@ -11,6 +11,9 @@
 #pragma once
 #include "common.cuh"
 
+struct CanonWs;  // workspace of the canonical-predecessor pass (canonical_prev.cu)
+void canon_ws_free(CanonWs* w);
+
 struct Mesh2D {
   i64 n = 0, nel = 0, sum_e2n = 0, nnzG = 0, halo_rows = 0, sum_nbr = 0, ntheta = 0, nr = 0;
   DevBuf<double> x, z, theta, r;
@@ -62,6 +65,8 @@ struct Mesh2D {
   DevBuf<int> bsources;
   DevBuf<i32> bprev;                   // [nb x n]
   DevBuf<double> bdist;                // [nb x n]
+  DevBuf<i64> flat;                    // flattened near / far slot prefixes of a batch round
+  CanonWs* canon = nullptr;
 };
 
 // Finishes a Mesh2D whose primary arrays (x,z,e2n_*,g_*) are already on the device: builds n2e, work items,
@@ -70,5 +75,8 @@ int mesh2d_finalize(rt_mesh* h, const i64* halo_host);
 int mesh2d_prepare_f32(rt_mesh* h);
 int bfm2d_solve_push_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 nsrc, double* dist_dev,
                           i32* prev_dev, rt_stats* stats);
+// reference predecessors (ties included) from converged travel times; see canonical_prev.cu
+int canonical_prev_2d(rt_mesh* h, const double* x, const double* z, const double* U1, const double* U2, int mode,
+                      const double* dist, int source, i32* prev, i64* levels_out, i64* launches_out);
 int bfm2d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                      rt_stats* stats);

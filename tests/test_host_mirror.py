@@ -55,8 +55,10 @@ def test_reorder_is_a_relabelling(rt, O, annulus, ak135):
     assert np.array_equal(halo3, halo)
 
 
+@pytest.mark.gpu
 def test_travel_times_and_csv(rt, tmp_path, monkeypatch):
-    """travel_times(D, gr, receivers; isave, flname) src/utils.jl:4-15."""
+    """travel_times(D, gr, receivers; isave, flname) src/utils.jl:4-15 (the gather runs on the device since round 2:
+    rt_travel_times, so this needs a GPU like every other compute call)."""
     n = 50
     theta = np.linspace(0.0, np.pi, n)
     gr = rt.Grid2D(np.zeros(n), np.zeros(n), theta, np.full(n, R), np.zeros(1, np.int64), np.zeros(0, np.int64), 1, 1,
