@@ -186,6 +186,16 @@ int rt_bfm_solve_dual(rt_mesh* m, const double* U2, const int64_t* sources, int6
 int rt_dual_velocity(const double* knots_r, const double* knots_v, int64_t nk, const double* r, int64_t n,
                      double buffer, double* out);
 
+/* ---- alternative solvers behind the Dijkstra / RadiusStepping result structs (src/SSSP/ssspm.jl:3-10) ------------- */
+/* algorithm 0: dijkstra(G::Dict, source, gr, U) src/SSSP/dijkstra.jl:68-136; algorithm 1: radius_stepping(Gsp, source,
+ * gr, U) src/SSSP/radius_stepping.jl:7-46.  Both work on the star-0 node graph nodal_incidence(gr) (src/GridAnnulus.jl:
+ * 763-804; rt_nodal_adjacency exports it) WITHOUT halo coupling, with the weight 2*distance/abs(U[i]+U[j]).  The travel
+ * times are the least fixed point of that graph (bit-identical to either reference loop); predecessors follow the settle
+ * order: the tight neighbour with the smallest (travel time, id), coincident duplicates at equal time resolved in the
+ * order they were fixed.  dist_out / prev_out: [n] host arrays (1-based ids, 0 = never set, Inf = unreachable). */
+int rt_sssp_nodal(rt_mesh* m, const double* U, int64_t source, int algorithm, double* dist_out, int64_t* prev_out,
+                  rt_stats* stats);
+
 /* Solver options: key/value, e.g. ("schedule", 0 = Jacobi sweeps exactly as the reference (default),
  * 1 = work-efficient near-far ordering; dist identical, prev may differ on exact ties),
  * ("profile_timers", 1) to fill rt_stats.relax_ms. */

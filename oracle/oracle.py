@@ -58,6 +58,9 @@ def lib():
         L.ora_bfm_dual.argtypes = [I64, I64, I64P, I64P, I64P, I64P, I64P, I64, F64P, F64P, F64P, F64P, F64P, I64, C.c_int,
                                    F64P, I64P, I64P]
         L.ora_dual_velocity.argtypes = [F64P, F64P, I64, F64P, I64, C.c_double, F64P]
+        L.ora_dijkstra_nodal.argtypes = [I64, I64P, I64P, F64P, F64P, F64P, I64, F64P, I64P]
+        L.ora_radius_stepping_nodal.restype = I64
+        L.ora_radius_stepping_nodal.argtypes = [I64, I64P, I64P, F64P, F64P, F64P, I64, F64P, I64P]
         L.ora_set_weight3d.argtypes = [C.c_int]
         L.ora_window3d.argtypes = [C.c_int]
         L.ora_nodal_incidence3d.argtypes = [I64P, C.c_int, I64P, C.c_void_p]
@@ -211,6 +214,29 @@ def dijkstra3d(nn, star_levels, X, Y, Z, U, source):
     dist = np.zeros(int(np.prod(nn)))
     lib().ora_dijkstra3d(nn, int(star_levels), X, Y, Z, np.ascontiguousarray(U, np.float64), int(source), dist)
     return dist
+
+
+def dijkstra_nodal(mesh, U, source, adjacency=None):
+    """dijkstra(G, source, gr, U) src/SSSP/dijkstra.jl:68-136 on nodal_incidence(gr) (star-0) -> (dist, prev)."""
+    deg, off, lst = adjacency if adjacency is not None else nodal_adjacency(mesh)
+    dist = np.zeros(mesh.n)
+    prev = np.zeros(mesh.n, np.int64)
+    if lib().ora_dijkstra_nodal(mesh.n, off, lst, mesh.x, mesh.z, np.ascontiguousarray(U, np.float64), int(source), dist,
+                                prev):
+        raise ValueError("bad source")
+    return dist, prev
+
+
+def radius_stepping_nodal(mesh, U, source, adjacency=None):
+    """radius_stepping(Gsp, source, gr, U) src/SSSP/radius_stepping.jl:7-46 on the same graph -> (dist, prev, it)."""
+    deg, off, lst = adjacency if adjacency is not None else nodal_adjacency(mesh)
+    dist = np.zeros(mesh.n)
+    prev = np.zeros(mesh.n, np.int64)
+    it = lib().ora_radius_stepping_nodal(mesh.n, off, lst, mesh.x, mesh.z, np.ascontiguousarray(U, np.float64),
+                                         int(source), dist, prev)
+    if it < 0:
+        raise ValueError("bad source")
+    return dist, prev, int(it)
 
 
 def set_weight3d(mode):

@@ -973,6 +973,102 @@ void ora_nodal_adjacency(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx,
   off[n] = o;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Alternative solvers of the reference on the star-0 node graph nodal_incidence(gr) (CSR: off[n+1] 0-based, list 1-based
+// neighbour ids).  Weight (both): 2 * distance(xi, zi, x[i], z[i]) / abs(U[i] + Ui) with the scalar distance
+// sqrt((ax-bx)^2 + (az-bz)^2) (src/GridAnnulus.jl:806).
+static inline double w_nodal(const double* x, const double* z, const double* U, i64 a, i64 b) {
+  const double dx = x[a] - x[b], dz = z[a] - z[b];
+  return 2 * std::sqrt(dx * dx + dz * dz) / std::fabs(U[b] + U[a]);
+}
+
+// dijkstra(G::Dict, source, gr, U) src/SSSP/dijkstra.jl:68-136, _relax_dijkstra! :138-162, min_distance :164-178,
+// literally: Q is a set scanned linearly for its minimum (O(|Q|) per settled node).  The reference's Q is a Julia Set,
+// whose iteration order decides between equal distances and is not reproducible: an ordered set stands in for it
+// (first minimum in ascending id).  prev: 0 = never set.
+int ora_dijkstra_nodal(i64 n, const i64* off, const i64* list, const double* x, const double* z, const double* U,
+                       i64 source, double* dist, i64* prev) {
+  if (source < 1 || source > n) return 1;
+  for (i64 i = 0; i < n; ++i) {
+    dist[i] = INF;
+    prev[i] = 0;
+  }
+  dist[source - 1] = 0.0;
+  std::set<i64> Q;
+  Q.insert(source - 1);
+  std::vector<uint8_t> settled(n, 0);
+  while (!Q.empty()) {
+    double d = INF;
+    i64 Qi = -1;
+    for (i64 q : Q)
+      if (dist[q] < d) {
+        d = dist[q];
+        Qi = q;
+      }
+    if (Qi < 0) break;  // only unreachable (Inf) entries cannot occur: nodes enter Q with a finite value
+    const double di = dist[Qi];
+    for (i64 e = off[Qi]; e < off[Qi + 1]; ++e) {
+      const i64 i = list[e] - 1;
+      if (settled[i]) continue;
+      const double delta = di + w_nodal(x, z, U, Qi, i);
+      if (delta < dist[i]) {
+        prev[i] = Qi + 1;
+        dist[i] = delta;
+        Q.insert(i);
+      }
+    }
+    Q.erase(Qi);
+    settled[Qi] = 1;
+  }
+  return 0;
+}
+
+// radius_stepping(Gsp, source, gr, U) src/SSSP/radius_stepping.jl:7-46 with relaxation! :58-71 (single thread: the
+// threaded loop races on dist / p), min_distance :73-84 and update! :48-56, literally.  Returns the iteration count.
+i64 ora_radius_stepping_nodal(i64 n, const i64* off, const i64* list, const double* x, const double* z,
+                              const double* U, i64 source, double* dist, i64* prev) {
+  if (source < 1 || source > n) return -1;
+  std::vector<uint8_t> Q(n, 1), F(n, 0);
+  Q[source - 1] = 0;
+  F[source - 1] = 1;
+  for (i64 i = 0; i < n; ++i) {
+    dist[i] = INF;
+    prev[i] = 0;
+  }
+  dist[source - 1] = 0.0;
+  i64 it = 1;
+  auto left = [&]() {
+    i64 c = 0;
+    for (i64 i = 0; i < n; ++i) c += Q[i];
+    return c;
+  };
+  while (left() != 0) {
+    for (i64 i = 0; i < n; ++i)  // relaxation!
+      if (F[i])
+        for (i64 e = off[i]; e < off[i + 1]; ++e) {
+          const i64 j = list[e] - 1;
+          if (!Q[j]) continue;
+          const double delta = dist[i] + w_nodal(x, z, U, i, j);
+          if (dist[j] > delta) {
+            dist[j] = delta;
+            prev[j] = i + 1;
+          }
+        }
+    double D = INF;  // min_distance(Q, dist)
+    for (i64 i = 0; i < n; ++i)
+      if (Q[i] && dist[i] < D) D = dist[i];
+    for (i64 i = 0; i < n; ++i) {  // update!
+      F[i] = 0;
+      if (Q[i] && dist[i] <= D) {
+        Q[i] = 0;
+        F[i] = 1;
+      }
+    }
+    ++it;
+  }
+  return it;
+}
+
 int ora_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -541,6 +541,32 @@ def bfm3d(gr3, source, U, schedule=None, delta=None, precision=64):
     return BellmanFordMoore(prev, dist, st)
 
 
+def _sssp_nodal(gr, source, U, algorithm, G=None, halo=None):
+    h = _handle_of(gr, G, halo)
+    n = gr.nnods
+    U = np.ascontiguousarray(U, np.float64)
+    if U.shape != (n,):
+        raise ValueError("U must have one entry per node (%d), got %s" % (n, U.shape))
+    dist = np.empty(n)
+    prev = np.empty(n, np.int64)
+    st = RtStats()
+    check(lib().rt_sssp_nodal(h.h, U, int(source), algorithm, dist, prev, C.byref(st)))
+    return prev, dist, st.as_dict()
+
+
+def dijkstra(G, source, gr, U):
+    """D = dijkstra(G, source, gr, U) -- src/SSSP/dijkstra.jl:68-136: G is the node graph nodal_incidence(gr) (star-0; the
+    reference passes it as a Dict, here it is implied by `gr`: pass None, or the SparseAdjencyList for symmetry).
+    Returns Dijkstra(prev, dist); unreachable nodes keep dist = Inf, prev = 0 (no halo coupling on this graph)."""
+    return Dijkstra(*_sssp_nodal(gr, source, U, 0))
+
+
+def radius_stepping(Gsp, source, gr, U):
+    """D = radius_stepping(Gsp, source, gr, U) -- src/SSSP/radius_stepping.jl:7-46 on the same node graph.
+    Returns RadiusStepping(prev, dist)."""
+    return RadiusStepping(*_sssp_nodal(gr, source, U, 1))
+
+
 # -------------------------------------------------------------------------------------------------- paths
 def recontruct_path(prev, source, receiver):
     """recontruct_path(prev::Vector, source, receiver) src/SSSP/ssspm.jl:30-40 -> [receiver, ..., source].

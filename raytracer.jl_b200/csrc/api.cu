@@ -185,6 +185,18 @@ int rt_rcm(rt_mesh* m, int64_t* perm_out) {
   return mesh2d_rcm(m, perm_out);
 }
 
+int rt_sssp_nodal(rt_mesh* m, const double* U, int64_t source, int algorithm, double* dist_out, int64_t* prev_out,
+                  rt_stats* stats) {
+  RT_ARG(m && m->kind == 2 && U, "rt_sssp_nodal needs a 2-D mesh and a velocity array");
+  RT_ARG(algorithm == 0 || algorithm == 1, "algorithm must be 0 (dijkstra) or 1 (radius_stepping)");
+  RT_CUDA(cudaSetDevice(m->device));
+  i64 sz[8];
+  mesh2d_sizes(m, sz);
+  DevBuf<double> dU;
+  RT_TRY(dU.upload(U, sz[0], m->stream));
+  return mesh2d_sssp_nodal(m, dU.p, source, algorithm, dist_out, prev_out, stats);
+}
+
 int rt_closest_point3d(const rt_mesh* m, const double* px, const double* py, const double* pz, int64_t npts,
                        int64_t* index_out) {
   RT_ARG(m && m->kind == 3, "rt_closest_point3d needs a 3-D grid");

@@ -135,6 +135,8 @@ int annulus_build_device(rt_mesh* h, i64 ntheta, i64 nr, double spacing);
 int mesh2d_interpolate_cells(rt_mesh* h, const int8_t* el_type_host, double* V_dev);
 int mesh2d_nodal_adjacency(rt_mesh* h, i64* deg_out, i64* list_off, i64* list_idx, i64 cap);
 int mesh2d_rcm(rt_mesh* h, i64* perm_out);
+int mesh2d_sssp_nodal(rt_mesh* h, const double* U_dev, i64 source1, int algorithm, double* dist_out, i64* prev_out,
+                      rt_stats* stats);
 int mesh2d_coords(const rt_mesh* h, const double** x, const double** z, const double** theta, const double** r);
 int grid3d_coords(const rt_mesh* h, const double** X, const double** Y, const double** Z, const double** none);
 

@@ -264,3 +264,251 @@ int mesh2d_rcm(rt_mesh* h, i64* perm_out) {
   RT_CUDA(cudaStreamSynchronize(s));
   return RT_OK;
 }
+
+// =========================================================================================================
+// Alternative solvers of the reference behind the Dijkstra / RadiusStepping result structs:
+//   dijkstra(G::Dict, source, gr, U)          src/SSSP/dijkstra.jl:68-136  (_relax_dijkstra! :138-162)
+//   radius_stepping(Gsp, source, gr, U)       src/SSSP/radius_stepping.jl:7-46 (relaxation! :58-71, update! :48-56)
+// Both run on the star-0 node graph nodal_incidence(gr) (no halo coupling) with the weight
+// 2 * distance(xi, zi, xj, zj) / abs(U[j] + U[i]) and settle nodes in order of travel time; their travel times are the
+// least fixed point of that graph, which a label-correcting frontier relaxation reaches bit for bit (fp `+` is monotone),
+// so the device never serialises on a priority queue.  Their predecessors follow from the settle order: a node keeps
+// the FIRST settled neighbour that gave it its final value (strict `<`), i.e. the tight predecessor with the smallest
+// (travel time, id); nodes whose only tight predecessors are coincident duplicates at EQUAL travel time (zero-weight
+// edges) take the duplicate that was resolved first.  (Ties in the reference's dijkstra are decided by the iteration order
+// of a Julia Set, which is not reproducible: ascending id stands in for it, as in radius_stepping's index loop.)
+namespace {
+
+struct SN {
+  TP t;
+  const double* __restrict__ x;
+  const double* __restrict__ z;
+  const double* __restrict__ U;
+  double* dist;
+  i32* prev;
+  i32* zl;  // pass in which the predecessor was fixed (0 = regular tight predecessor), -1 = open
+  i32* fr0;
+  i32* fr1;
+  unsigned* inq;
+  u64* cnt;  // [0],[1] frontier sizes (ping-pong) [2] open nodes [3] fixed in this pass [4] relaxations
+  int source;
+};
+
+__device__ __forceinline__ double w_nodal(const SN& p, int a, int b) {
+  const double dx = __dsub_rn(p.x[a], p.x[b]), dz = __dsub_rn(p.z[a], p.z[b]);
+  const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dz, dz)));
+  return __ddiv_rn(__dmul_rn(2.0, d), fabs(__dadd_rn(p.U[b], p.U[a])));
+}
+
+__global__ void sn_init_kernel(SN p) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.t.n) {
+    p.dist[i] = i == p.source ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+    p.prev[i] = -1;
+    p.zl[i] = -1;
+    p.inq[i] = 0u;
+  }
+  if (i == 0) {
+    p.fr0[0] = p.source;
+    p.cnt[0] = 1ull;
+    for (int k = 1; k < 8; ++k) p.cnt[k] = 0ull;
+  }
+}
+// one warp per frontier node: push dist + w to every star-0 neighbour
+__global__ void sn_relax_kernel(SN p, int cur) {
+  const i32* fr = cur ? p.fr1 : p.fr0;
+  i32* nx = cur ? p.fr0 : p.fr1;
+  const i64 nf = (i64)p.cnt[cur];
+  const int lane = threadIdx.x & 31;
+  for (i64 q = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nf; q += ((i64)gridDim.x * blockDim.x) >> 5) {
+    const int i = fr[q];
+    if (lane == 0) p.inq[i] = 0u;  // a later improvement of i queues it again
+    __syncwarp();
+    const double di = __ldcg(&p.dist[i]);
+    u64 nrel = 0;
+    for_each_neighbour(p.t, i, lane, [&](int u, int) {
+      ++nrel;
+      const double delta = __dadd_rn(di, w_nodal(p, i, u));
+      const u64 bits = (u64)__double_as_longlong(delta);
+      if (bits < (u64)__double_as_longlong(__ldcg(&p.dist[u]))) {
+        const u64 old = atomicMin((u64*)&p.dist[u], bits);
+        if (bits < old && atomicExch(&p.inq[u], 1u) == 0u) nx[atomicAdd(&p.cnt[cur ^ 1], 1ull)] = u;
+      }
+    });
+    for (int o = 16; o; o >>= 1) nrel += __shfl_xor_sync(FULL, nrel, o);
+    if (lane == 0) atomicAdd(&p.cnt[4], nrel);
+  }
+}
+// predecessor, regular case: tight neighbour with a strictly smaller travel time, smallest (time, id)
+__global__ void sn_prev_kernel(SN p, i32* __restrict__ open_list) {
+  const i64 i = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= p.t.n) return;
+  const double di = p.dist[i];
+  if (!(di < __longlong_as_double(0x7ff0000000000000LL)) || (int)i == p.source) return;  // warp-uniform
+  u64 bd = ~0ull;
+  int bj = 0x7fffffff;
+  for_each_neighbour(p.t, (int)i, lane, [&](int j, int) {
+    const double dj = p.dist[j];
+    if (!(dj < di)) return;
+    if (__dadd_rn(dj, w_nodal(p, j, (int)i)) != di) return;
+    const u64 b = (u64)__double_as_longlong(dj);
+    if (b < bd || (b == bd && j < bj)) {
+      bd = b;
+      bj = j;
+    }
+  });
+  for (int o = 16; o; o >>= 1) {
+    const u64 od = __shfl_xor_sync(FULL, bd, o);
+    const int oj = __shfl_xor_sync(FULL, bj, o);
+    if (od < bd || (od == bd && oj < bj)) {
+      bd = od;
+      bj = oj;
+    }
+  }
+  if (lane == 0) {
+    if (bd != ~0ull) {
+      p.prev[i] = bj;
+      p.zl[i] = 0;
+    } else {
+      open_list[atomicAdd(&p.cnt[2], 1ull)] = (i32)i;
+    }
+  }
+}
+// zero-weight case, pass k: among the equal-time tight neighbours fixed in an earlier pass, the one fixed first, then
+// the smallest id; decisions are applied after the kernel so that a pass sees a consistent state
+__global__ void sn_zero_kernel(SN p, const i32* __restrict__ open_list, i64 n_open, int pass, i32* __restrict__ pend) {
+  const i64 q = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= n_open) return;
+  const int i = open_list[q];
+  if (p.zl[i] >= 0) return;  // fixed in an earlier pass (warp-uniform)
+  const double di = p.dist[i];
+  int bl = 0x7fffffff, bj = 0x7fffffff;
+  for_each_neighbour(p.t, i, lane, [&](int j, int) {
+    if (p.dist[j] != di) return;
+    const int l = j == p.source ? 0 : p.zl[j];
+    if (l < 0 || l >= pass) return;
+    if (__dadd_rn(di, w_nodal(p, j, i)) != di) return;
+    if (l < bl || (l == bl && j < bj)) {
+      bl = l;
+      bj = j;
+    }
+  });
+  for (int o = 16; o; o >>= 1) {
+    const int ol = __shfl_xor_sync(FULL, bl, o), oj = __shfl_xor_sync(FULL, bj, o);
+    if (ol < bl || (ol == bl && oj < bj)) {
+      bl = ol;
+      bj = oj;
+    }
+  }
+  if (lane == 0) pend[q] = bl != 0x7fffffff ? bj : -1;
+}
+__global__ void sn_zero_apply_kernel(SN p, const i32* __restrict__ open_list, i64 n_open, int pass,
+                                     const i32* __restrict__ pend) {
+  const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_open) return;
+  const int i = open_list[q];
+  if (p.zl[i] >= 0 || pend[q] < 0) return;
+  p.prev[i] = pend[q];
+  p.zl[i] = pass;
+  atomicAdd(&p.cnt[3], 1ull);
+}
+
+}  // namespace
+
+// algorithm: 0 = dijkstra, 1 = radius_stepping (same tables; the caller wraps them in the matching result struct).
+int mesh2d_sssp_nodal(rt_mesh* h, const double* U_dev, i64 source1, int algorithm, double* dist_out, i64* prev_out,
+                      rt_stats* stats) {
+  (void)algorithm;
+  Mesh2D& m = *h->m2;
+  cudaStream_t s = h->stream;
+  const i64 n = m.n;
+  RT_ARG(source1 >= 1 && source1 <= n, "source out of range");
+  DevBuf<double> dist;
+  DevBuf<i32> prev, zl, fr0, fr1, open_list, pend;
+  DevBuf<unsigned> inq;
+  DevBuf<u64> cnt;
+  RT_TRY(dist.alloc(n));
+  RT_TRY(prev.alloc(n));
+  RT_TRY(zl.alloc(n));
+  RT_TRY(fr0.alloc(n));
+  RT_TRY(fr1.alloc(n));
+  RT_TRY(open_list.alloc(n));
+  RT_TRY(pend.alloc(n));
+  RT_TRY(inq.alloc(n));
+  RT_TRY(cnt.alloc(8));
+  SN p;
+  p.t = make_tp(m);
+  p.x = m.x.p;
+  p.z = m.z.p;
+  p.U = U_dev;
+  p.dist = dist.p;
+  p.prev = prev.p;
+  p.zl = zl.p;
+  p.fr0 = fr0.p;
+  p.fr1 = fr1.p;
+  p.inq = inq.p;
+  p.cnt = cnt.p;
+  p.source = (int)(source1 - 1);
+  cudaEvent_t ev0, ev1;
+  RT_CUDA(cudaEventCreate(&ev0));
+  RT_CUDA(cudaEventCreate(&ev1));
+  cudaEventRecord(ev0, s);
+  sn_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(p);
+  u64 hc[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  int cur = 0;
+  i64 rounds = 0, launches = 1;
+  int rc = RT_OK;
+  while (hc[cur] > 0) {
+    cudaMemsetAsync(cnt.p + (cur ^ 1), 0, sizeof(u64), s);
+    sn_relax_kernel<<<(unsigned)std::min<i64>(((i64)hc[cur] * 32 + 255) / 256, 148 * 16), 256, 0, s>>>(p, cur);
+    cudaMemcpyAsync(hc, cnt.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      rc = RT_ERR_CUDA;
+      break;
+    }
+    cur ^= 1;
+    ++rounds;
+    ++launches;
+    if (rounds > 4 * n + 64) {
+      rc = RT_ERR_CUDA;
+      break;
+    }
+  }
+  if (rc == RT_OK) {
+    sn_prev_kernel<<<grid_for(n * 32, 256), 256, 0, s>>>(p, open_list.p);
+    cudaMemcpyAsync(hc, cnt.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) rc = RT_ERR_CUDA;
+    ++launches;
+    const i64 n_open = (i64)hc[2];
+    for (int pass = 1; rc == RT_OK && n_open > 0 && pass < 64; ++pass) {
+      cudaMemsetAsync(cnt.p + 3, 0, sizeof(u64), s);
+      sn_zero_kernel<<<grid_for(n_open * 32, 256), 256, 0, s>>>(p, open_list.p, n_open, pass, pend.p);
+      sn_zero_apply_kernel<<<grid_for(n_open, 256), 256, 0, s>>>(p, open_list.p, n_open, pass, pend.p);
+      cudaMemcpyAsync(hc, cnt.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) rc = RT_ERR_CUDA;
+      launches += 2;
+      if (hc[3] == 0) break;  // nothing left that a fixed neighbour explains
+    }
+  }
+  cudaEventRecord(ev1, s);
+  if (rc == RT_OK && dist_out) {
+    if (cudaMemcpyAsync(dist_out, dist.p, n * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess) rc = RT_ERR_CUDA;
+  }
+  if (rc == RT_OK && prev_out) rc = prev_to_host_i64(prev.p, n, prev_out, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess) rc = RT_ERR_CUDA;
+  if (stats) {
+    *stats = rt_stats{};
+    stats->sweeps = rounds;
+    stats->relaxed_edges = (i64)hc[4];
+    stats->total_launches = launches;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    stats->kernel_ms = ms;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (rc != RT_OK) rt_set_error("CUDA failure in the nodal-graph solver: %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
+}
