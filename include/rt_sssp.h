@@ -186,6 +186,21 @@ int rt_bfm_solve_dual(rt_mesh* m, const double* U2, const int64_t* sources, int6
 int rt_dual_velocity(const double* knots_r, const double* knots_v, int64_t nk, const double* r, int64_t n,
                      double buffer, double* out);
 
+/* ---- multiphase / layer-restricted propagation (src/topology/topology.jl:150-206, src/SSSP/bfm_multiphase.jl) ------ */
+/* partition_grid(gr) topology.jl:183-206: id_out[n], k > 0 = "Layer_k" (find_layer_number :137-147, k = 1..8), -k =
+ * "Boundary_k" (k = 1..7: the discontinuity radii R - {20, 35, 210, 410, 660, 2740, 2891.5}); radii are rounded to two
+ * digits first, as the reference does. */
+int rt_partition_grid(const rt_mesh* m, int32_t* id_out);
+/* The inner loop of bfm_multiphase (bfm_multiphase.jl:118-150) on the graph of bfm: reference sweeps (Jacobi schedule)
+ * that CONTINUE from the caller's state dist_inout / prev_inout [n] and only relax, activate or halo-update nodes with
+ * allowed[i] != 0 (`ID[Gi] in current_level`; allowed == NULL: every node); the frontier starts as the allowed nodes of
+ * the star patches of seeds[0 .. nseeds).  Everything else of a phase loop (which layers, which boundary velocity,
+ * where to restart) stays with the caller: see bfm_multiphase in julia/RayTracerB200.jl and raytracer.jl_b200/api.py.
+ * The reference routine is unfinished (it calls the undefined _relax_bfm! / fillfalse!); the relax step used here is
+ * _relax!(U::Vector) of bfm.jl:161-210. */
+int rt_bfm_continue(rt_mesh* m, const double* U, const uint8_t* allowed, const int64_t* seeds, int64_t nseeds,
+                    double* dist_inout, int64_t* prev_inout, rt_stats* stats);
+
 /* ---- alternative solvers behind the Dijkstra / RadiusStepping result structs (src/SSSP/ssspm.jl:3-10) ------------- */
 /* algorithm 0: dijkstra(G::Dict, source, gr, U) src/SSSP/dijkstra.jl:68-136; algorithm 1: radius_stepping(Gsp, source,
  * gr, U) src/SSSP/radius_stepping.jl:7-46.  Both work on the star-0 node graph nodal_incidence(gr) (src/GridAnnulus.jl:

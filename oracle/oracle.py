@@ -61,6 +61,9 @@ def lib():
         L.ora_dijkstra_nodal.argtypes = [I64, I64P, I64P, F64P, F64P, F64P, I64, F64P, I64P]
         L.ora_radius_stepping_nodal.restype = I64
         L.ora_radius_stepping_nodal.argtypes = [I64, I64P, I64P, F64P, F64P, F64P, I64, F64P, I64P]
+        L.ora_partition_grid.argtypes = [F64P, I64, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
+        L.ora_bfm_continue.argtypes = [I64, I64, I64P, I64P, I64P, I64P, I64P, I64, F64P, F64P, F64P, C.c_void_p, I64P,
+                                       I64, C.c_int, F64P, I64P, I64P]
         L.ora_set_weight3d.argtypes = [C.c_int]
         L.ora_window3d.argtypes = [C.c_int]
         L.ora_nodal_incidence3d.argtypes = [I64P, C.c_int, I64P, C.c_void_p]
@@ -237,6 +240,32 @@ def radius_stepping_nodal(mesh, U, source, adjacency=None):
     if it < 0:
         raise ValueError("bad source")
     return dist, prev, int(it)
+
+
+def partition_grid(r):
+    """partition_grid(gr) src/topology/topology.jl:183-206 -> int32 ids: k > 0 = "Layer_k", -k = "Boundary_k"."""
+    r = np.ascontiguousarray(r, np.float64)
+    out = np.zeros(len(r), np.int32)
+    lib().ora_partition_grid(r, len(r), out)
+    return out
+
+
+def bfm_continue(mesh, U, allowed, seeds, dist, prev, nthreads=1):
+    """Restricted continuation (inner loop of bfm_multiphase, src/SSSP/bfm_multiphase.jl:118-150): returns new (dist,
+    prev, stats); the inputs are not modified."""
+    dist = np.array(dist, np.float64)
+    prev = np.array(prev, np.int64)
+    seeds = np.ascontiguousarray(np.atleast_1d(seeds), np.int64)
+    al = None if allowed is None else np.ascontiguousarray(allowed, np.uint8)
+    stats = np.zeros(4, np.int64)
+    halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
+    rc = lib().ora_bfm_continue(mesh.n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.G_colptr, mesh.G_rowval, halo,
+                                mesh.halo_rows, mesh.x, mesh.z, np.ascontiguousarray(U, np.float64),
+                                None if al is None else al.ctypes.data_as(C.c_void_p), seeds, len(seeds), int(nthreads),
+                                dist, prev, stats)
+    if rc:
+        raise ValueError("bad seed")
+    return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]))
 
 
 def set_weight3d(mode):

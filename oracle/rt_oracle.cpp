@@ -974,6 +974,123 @@ void ora_nodal_adjacency(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Multiphase / layer-restricted propagation.
+// partition_grid(gr) src/topology/topology.jl:183-206 with find_layer_number :137-147: id > 0 = "Layer_id",
+// id < 0 = "Boundary_(-id)"; the radius is rounded to 2 digits first (round(r; digits = 2) = round(r * 100) / 100).
+void ora_partition_grid(const double* r, i64 n, int32_t* id) {
+  for (i64 i = 0; i < n; ++i) {
+    const double ri = std::nearbyint(r[i] * 100.0) / 100.0;
+    int b = 0;
+    for (int k = 0; k < 7; ++k)
+      if (ri == RL[k]) {
+        b = k + 1;
+        break;
+      }
+    if (b) {
+      id[i] = -b;
+      continue;
+    }
+    int layer = 0;
+    if (ri > RL[0]) {
+      layer = 1;
+    } else if (ri < RL[6]) {
+      layer = 8;
+    } else {
+      for (int k = 0; k < 6; ++k)
+        if (RL[k] > ri && ri > RL[k + 1]) {
+          layer = k + 2;
+          break;
+        }
+    }
+    id[i] = layer;  // 0 = find_layer_number returned nothing (cannot happen for rounded radii off the boundaries)
+  }
+}
+
+// The inner loop of bfm_multiphase (src/SSSP/bfm_multiphase.jl:118-150) restated on the two-level graph of bfm: Jacobi
+// sweeps that CONTINUE from a given (dist, prev) state and only ever relax / activate nodes with allowed[i] != 0
+// (`ID[Gi] in current_level`, :121, :196); the frontier starts as the allowed nodes of the star patches of the seed
+// nodes; update_halo! acts on allowed targets only.  The reference routine itself is unfinished (it calls the undefined
+// _relax_bfm! and fillfalse!), so the relax step is _relax!(U::Vector) of bfm.jl:161-210.
+int ora_bfm_continue(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr, const i64* rowval,
+                     const i64* halo, i64 halo_rows, const double* x, const double* z, const double* U,
+                     const uint8_t* allowed, const i64* seeds, i64 nseeds, int nthreads, double* dist, i64* prev,
+                     i64* stats) {
+  Graph2D g{n, nel, e2n_off, e2n_idx, colptr, rowval, halo, halo_rows, x, z, U};
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  std::vector<double> dist0(dist, dist + n);
+  std::vector<uint8_t> Q(n, 0);
+  for (i64 k = 0; k < nseeds; ++k) {
+    const i64 s = seeds[k];
+    if (s < 1 || s > n) return 1;
+    for (i64 p = colptr[s - 1]; p < colptr[s]; ++p) {
+      const i64 el = rowval[p - 1];
+      for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q)
+        if (!allowed || allowed[e2n_idx[q] - 1]) Q[e2n_idx[q] - 1] = 1;
+    }
+  }
+  i64 sweeps = 0, evals = 0, updates = 0;
+  std::vector<i64> active;
+  while (true) {
+    active.clear();
+    for (i64 i = 0; i < n; ++i)
+      if (Q[i]) active.push_back(i);
+    if (active.empty()) break;
+    i64 ev = 0;
+    const i64 na = (i64)active.size();
+#pragma omp parallel for schedule(static) reduction(+ : ev)
+    for (i64 a = 0; a < na; ++a) {
+      const i64 i0 = active[a];
+      double di = dist0[i0];
+      for (i64 p = colptr[i0]; p < colptr[i0 + 1]; ++p) {
+        const i64 el = rowval[p - 1];
+        for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q) {
+          const i64 j0 = e2n_idx[q] - 1;
+          const double dj = dist0[j0];
+          const double delta = dj == INF ? INF : cand2d(g, dj, i0, j0);
+          if (di > delta) {
+            di = delta;
+            prev[i0] = j0 + 1;
+          }
+          ++ev;
+        }
+      }
+      dist[i0] = di;
+    }
+    evals += ev;
+    updates += na;
+    for (i64 k = 0; k < halo_rows; ++k) {
+      const i64 h1 = halo[k] - 1, h2 = halo[k + halo_rows] - 1;
+      if (allowed && !allowed[h2]) continue;
+      if (dist[h1] < dist0[h1] && dist[h2] > dist[h1]) {
+        dist[h2] = dist[h1];
+        prev[h2] = prev[h1];
+      }
+    }
+    std::fill(Q.begin(), Q.end(), 0);
+    for (i64 i = 0; i < n; ++i)
+      if (dist[i] < INF && dist[i] < dist0[i])
+        for (i64 p = colptr[i]; p < colptr[i + 1]; ++p) {
+          const i64 el = rowval[p - 1];
+          for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q) {
+            const i64 j0 = e2n_idx[q] - 1;
+            if (!allowed || allowed[j0]) Q[j0] = 1;
+          }
+        }
+    std::memcpy(dist0.data(), dist, sizeof(double) * n);
+    ++sweeps;
+  }
+  if (stats) {
+    stats[0] = sweeps;
+    stats[1] = evals;
+    stats[2] = updates;
+    stats[3] = 0;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Alternative solvers of the reference on the star-0 node graph nodal_incidence(gr) (CSR: off[n+1] 0-based, list 1-based
 // neighbour ids).  Weight (both): 2 * distance(xi, zi, x[i], z[i]) / abs(U[i] + Ui) with the scalar distance
 // sqrt((ax-bx)^2 + (az-bz)^2) (src/GridAnnulus.jl:806).

@@ -541,6 +541,129 @@ def bfm3d(gr3, source, U, schedule=None, delta=None, precision=64):
     return BellmanFordMoore(prev, dist, st)
 
 
+# ------------------------------------------------------------------------------------------------ multiphase
+RLAYER = tuple(R - d for d in (20.0, 35.0, 210.0, 410.0, 660.0, 2740.0, 2891.5))  # topology.jl:184-192
+
+
+class GridPartition:
+    """GridPartition of src/topology/topology.jl:150-181.  `code` holds the node ids as integers (k > 0 = "Layer_k",
+    -k = "Boundary_k"); `id` materialises the reference's Vector{String} on demand.  layers / boundaries / iterator are
+    the reference's name tuples and its LayerIterations dictionary (keys 1 .. 2 nlayers - 1)."""
+
+    def __init__(self, code, rboundaries=RLAYER):
+        self.code = np.ascontiguousarray(code, np.int32)
+        self.rboundaries = tuple(rboundaries)
+        self.nboundaries = len(self.rboundaries)
+        self.nlayers = self.nboundaries + 1
+        self.layers = tuple("Layer_%d" % (i + 1) for i in range(self.nlayers))
+        self.boundaries = tuple("Boundary_%d" % (i + 1) for i in range(self.nboundaries))
+        nl, nmax = self.nlayers, 2 * self.nlayers - 1
+        it = {1: (self.layers[0], self.boundaries[0]), nmax: (self.layers[0], self.boundaries[0])}
+        for i in range(2, nl):
+            it[i] = (self.layers[i - 1], self.boundaries[i - 2], self.boundaries[i - 1])
+            it[nmax - i + 1] = (self.layers[i - 1], self.boundaries[i - 2], self.boundaries[i - 1])
+        it[nl] = (self.layers[-1], self.boundaries[-1])
+        self.iterator = it
+
+    @property
+    def id(self):
+        return np.array([("Layer_%d" % c) if c > 0 else ("Boundary_%d" % -c) for c in self.code], dtype=object)
+
+    def code_of(self, name):
+        kind, k = name.split("_")
+        return int(k) if kind == "Layer" else -int(k)
+
+    def mask(self, names):
+        """allowed[i] = ID[i] in names (`ID[Gi] ∉ current_level && continue`, bfm_multiphase.jl:121)."""
+        return np.isin(self.code, [self.code_of(nm) for nm in names]).astype(np.uint8)
+
+
+def partition_grid(gr):
+    """partition_grid(gr) src/topology/topology.jl:183-206 (computed on the device from gr.r)."""
+    code = np.zeros(gr.nnods, np.int32)
+    check(lib().rt_partition_grid(_handle_of(gr).h, code))
+    return GridPartition(code)
+
+
+def directions(nlayers):
+    """directions(nlayers) src/SSSP/bfm_multiphase.jl:2-14."""
+    nmax = 2 * nlayers - 1
+    d = {1: ("above", "above"), nmax: ("above", "above")}
+    for i in range(2, nlayers):
+        d[i] = d[nmax - i + 1] = ("below", "above")
+    d[nlayers] = ("below", "below")
+    return d
+
+
+def bfm_continue(G, halo, gr, U, allowed, seeds, dist, prev):
+    """Restricted continuation (rt_bfm_continue): reference sweeps from the state (dist, prev) in which only nodes with
+    allowed != 0 change; the frontier starts as the allowed nodes of the seeds' star patches.  Returns a new
+    BellmanFordMoore; the inputs are not modified."""
+    handle = mesh_from_arrays(gr, G, halo)
+    n = int(G.n)
+    U = np.ascontiguousarray(U, np.float64)
+    d = np.array(dist, np.float64)
+    p = np.array(prev, np.int64)
+    if U.shape != (n,) or d.shape != (n,) or p.shape != (n,):
+        raise ValueError("U, dist and prev must have one entry per node (%d)" % n)
+    al = None if allowed is None else np.ascontiguousarray(allowed, np.uint8)
+    if al is not None and al.shape != (n,):
+        raise ValueError("allowed must have one entry per node")
+    sd = np.ascontiguousarray(np.atleast_1d(seeds), np.int64)
+    st = RtStats()
+    check(lib().rt_bfm_continue(handle.h, U, ptr(al), sd, len(sd), d, p, C.byref(st)))
+    return BellmanFordMoore(p, d, st.as_dict())
+
+
+def initial_state(halo, source, n):
+    """dist = fill(Inf, n); dist[source] = 0 and p after init_halo_path! (src/SSSP/bfm.jl:12-13, 21-22, 64-70)."""
+    dist = np.full(n, np.inf)
+    dist[source - 1] = 0.0
+    prev = np.zeros(n, np.int64)
+    if halo is not None:
+        for a, b in np.asarray(halo, np.int64):
+            prev[b - 1] = a
+            prev[a - 1] = b
+    return dist, prev
+
+
+def bfm_multiphase(G, halo, source, gr, U, partition, interpolant, nphases=3, buffer_zone=1.0):
+    """bfm_multiphase(Gsp, source, gr, U, partition, interpolant) -- src/SSSP/bfm_multiphase.jl:30-156, on the graph of
+    bfm.  The reference routine is an unfinished draft (undefined _relax_bfm! / fillfalse!, `for i in 1:3`, the restart
+    code commented out); this follows its structure and completes it where it says what it intends:
+      for phase i = 1 .. nphases: current_level = partition.iterator[i] (a layer and its one or two boundaries);
+        boundary_velocity! (:16-28): U at the nodes of each current boundary = interpolant(r_b -/+ buffer_zone) for the
+          ray direction :above / :below of directions(nlayers)[i] (the draft passes the whole tuple, so its comparison
+          with :above is never true; the per-boundary entry is what it evidently means);
+        frontier: phase 1 = the allowed nodes around `source` (:120-123); later phases restart from the nodes of the
+          first current boundary that have been reached (the commented-out find_new_source_min / restart block);
+        sweeps restricted to ID in current_level (:118-150), continuing from the running (dist, prev) state.
+    Returns BellmanFordMoore(prev, dist) like the reference; U is not modified (a copy is)."""
+    n = int(G.n)
+    U = np.array(U, np.float64)
+    rdir = directions(partition.nlayers)
+    rb = dict(zip(partition.boundaries, partition.rboundaries))
+    bnodes = {nm: np.flatnonzero(partition.code == partition.code_of(nm)) + 1 for nm in partition.boundaries}
+    kn, kv = interpolant.knots, interpolant.values
+    dist, prev = initial_state(halo, int(source), n)
+    D = BellmanFordMoore(prev, dist, {})
+    sweeps = []
+    for i in range(1, int(nphases) + 1):
+        level = partition.iterator[i]
+        for k, b in enumerate(level[1:]):
+            rq = rb[b] - buffer_zone if rdir[i][k] == "above" else rb[b] + buffer_zone
+            U[bnodes[b] - 1] = np.interp(rq, kn, kv)
+        if i == 1:
+            seeds = np.array([int(source)], np.int64)
+        else:
+            cand = bnodes[level[1]]
+            seeds = cand[np.isfinite(D.dist[cand - 1])]
+        D = bfm_continue(G, halo, gr, U, partition.mask(level), seeds, D.dist, D.prev)
+        sweeps.append(D.stats["sweeps"])
+    D.stats["phase_sweeps"] = sweeps
+    return D
+
+
 def _sssp_nodal(gr, source, U, algorithm, G=None, halo=None):
     h = _handle_of(gr, G, halo)
     n = gr.nnods

@@ -185,6 +185,25 @@ int rt_rcm(rt_mesh* m, int64_t* perm_out) {
   return mesh2d_rcm(m, perm_out);
 }
 
+int rt_partition_grid(const rt_mesh* m, int32_t* id_out) {
+  RT_ARG(m && m->kind == 2, "rt_partition_grid needs a 2-D mesh");
+  RT_CUDA(cudaSetDevice(m->device));
+  return mesh2d_partition(m, id_out);
+}
+
+int rt_bfm_continue(rt_mesh* m, const double* U, const uint8_t* allowed, const int64_t* seeds, int64_t nseeds,
+                    double* dist_inout, int64_t* prev_inout, rt_stats* stats) {
+  RT_ARG(m && m->kind == 2 && U && dist_inout && prev_inout && nseeds >= 0 && (nseeds == 0 || seeds),
+         "rt_bfm_continue needs a 2-D mesh, U, the (dist, prev) state and the seed nodes");
+  RT_CUDA(cudaSetDevice(m->device));
+  m->f32 = false;
+  i64 sz[8];
+  mesh2d_sizes(m, sz);
+  DevBuf<double> dU;
+  RT_TRY(dU.upload(U, sz[0], m->stream));
+  return bfm2d_continue(m, dU.p, allowed, seeds, nseeds, dist_inout, prev_inout, stats);
+}
+
 int rt_sssp_nodal(rt_mesh* m, const double* U, int64_t source, int algorithm, double* dist_out, int64_t* prev_out,
                   rt_stats* stats) {
   RT_ARG(m && m->kind == 2 && U, "rt_sssp_nodal needs a 2-D mesh and a velocity array");

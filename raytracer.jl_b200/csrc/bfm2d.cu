@@ -42,7 +42,9 @@ struct P2 {
   i32* prev;
   uint8_t* dirty;
   u64* counters;
+  const uint8_t* __restrict__ allowed;  // restricted continuation (rt_bfm_continue): only these nodes change; null = all
 };
+__device__ __forceinline__ bool node_allowed(const P2& p, int i) { return !p.allowed || p.allowed[i]; }
 
 // dGi + 2.0 * sqrt(0 + dx*dx + dz*dz) / (Ui + Uj)   (bfm.jl:186, GridAnnulus.jl:808-815), no contraction
 // exact_cand2<F32> (exact.h); F32 = the Float32 relax of src/SSSP/bfm_gpu.jl:487-526
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(RELAX_BLOCK) relax2d_kernel(P2 p, const i32* _
         bid = oi;
       }
     }
-    if (part == 0 && ti < t) {
+    if (part == 0 && ti < t && node_allowed(p, i)) {
       p.dist[i] = best;
       if (bpos >= 0) p.prev[i] = bid;
     }
@@ -148,7 +150,7 @@ __global__ void halo_phase1_kernel(P2 p, const i32* __restrict__ h1, const i32* 
   if (k >= H) return;
   const int a = h1[k], b = h2[k];
   const double da = p.dist[a];
-  if (da < p.dist0[a] && p.dist[b] > da) {
+  if (da < p.dist0[a] && p.dist[b] > da && node_allowed(p, b)) {
     p.dist[b] = da;
     p.prev[b] = p.prev[a];
   }
@@ -169,7 +171,7 @@ __global__ void halo_phase2_kernel(P2 p, const i32* __restrict__ orig, const i32
       p_o = p.prev[b];
     }
   }
-  if (p_o != -2) {
+  if (p_o != -2 && node_allowed(p, o)) {
     p.dist[o] = d_o;
     p.prev[o] = p_o;
   }
@@ -179,7 +181,7 @@ __global__ void halo_serial_kernel(P2 p, const i32* __restrict__ h1, const i32* 
   if (blockIdx.x || threadIdx.x) return;
   for (i64 k = 0; k < rows; ++k) {
     const int a = h1[k], b = h2[k];
-    if (p.dist[a] < p.dist0[a] && p.dist[b] > p.dist[a]) {
+    if (p.dist[a] < p.dist0[a] && p.dist[b] > p.dist[a] && node_allowed(p, b)) {
       p.dist[b] = p.dist[a];
       p.prev[b] = p.prev[a];
     }
@@ -230,11 +232,12 @@ __global__ void activate_kernel(P2 p, i64 n_items, i32* __restrict__ next_active
   bool act = false;
   if (lane < t) {
     const int v = v0 + lane;
-    for (int q = p.n2e_off[v]; q < p.n2e_off[v + 1]; ++q)
-      if (p.dirty[p.n2e_idx[q]]) {
-        act = true;
-        break;
-      }
+    if (node_allowed(p, v))
+      for (int q = p.n2e_off[v]; q < p.n2e_off[v + 1]; ++q)
+        if (p.dirty[p.n2e_idx[q]]) {
+          act = true;
+          break;
+        }
   }
   if (__any_sync(FULL, act) && lane == 0) {
     const u64 slot = atomicAdd(&p.counters[nxt], 1ull);
@@ -262,6 +265,16 @@ __global__ void init_source_kernel(P2 p, const i32* __restrict__ hnode, const i3
   }
 }
 
+// rt_bfm_continue: the frontier starts as the star patches of the seed nodes (init_Q! for every seed)
+__global__ void seed_touch_kernel(P2 p, const i32* __restrict__ seeds, i64 nseeds) {
+  const i64 k = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k < nseeds) touch_column(p, seeds[k], threadIdx.x & 31, 32);
+}
+__global__ void prev_from_i64_kernel(const i64* __restrict__ src, i32* __restrict__ dst, i64 n) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (i32)(src[i] - 1);
+}
+
 int ensure_workspace(rt_mesh* h) {
   Mesh2D& m = *h->m2;
   if (m.ws_ready) return RT_OK;
@@ -281,8 +294,14 @@ int ensure_workspace(rt_mesh* h) {
 
 int bfm2d_ensure_workspace(rt_mesh* h) { return ensure_workspace(h); }
 
+// cont != null: one continuation solve from the state already loaded into the workspace (rt_bfm_continue)
+struct Continuation {
+  const uint8_t* allowed_dev;
+  const i32* seeds_dev;
+  i64 nseeds;
+};
 int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sources, i64 nsrc, double* dist_dev,
-                     i32* prev_dev, rt_stats* stats);
+                     i32* prev_dev, rt_stats* stats, const Continuation* cont = nullptr);
 
 // precision = 32: Float32-rounded copies of the coordinates (Float32.(gr.x), bfm_gpu.jl:176-177), built once
 int mesh2d_prepare_f32(rt_mesh* h) {
@@ -314,7 +333,7 @@ int bfm2d_solve_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 n
 }
 
 int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sources, i64 nsrc, double* dist_dev,
-                     i32* prev_dev, rt_stats* stats) {
+                     i32* prev_dev, rt_stats* stats, const Continuation* cont) {
   Mesh2D& m = *h->m2;
   cudaStream_t s = h->stream;
   RT_TRY(ensure_workspace(h));
@@ -340,6 +359,7 @@ int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sour
   p.prev = m.prev.p;
   p.dirty = m.dirty.p;
   p.counters = m.counters.p;
+  p.allowed = cont ? cont->allowed_dev : nullptr;
 
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
@@ -356,18 +376,23 @@ int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sour
   int rc = RT_OK;
 
   for (i64 si = 0; si < nsrc && rc == RT_OK; ++si) {
-    const i64 src1 = sources[si];
+    const i64 src1 = cont ? 1 : sources[si];
     if (src1 < 1 || src1 > n) {
       rt_set_error("source %lld out of range 1..%lld", (long long)src1, (long long)n);
       rc = RT_ERR_ARG;
       break;
     }
     cudaEventRecord(ev0, s);
-    init_state_kernel<<<grid_for(n, 256), 256, 0, s>>>(p.dist, p.dist0, p.prev, n);
     cudaMemsetAsync(m.dirty.p, 0, m.nel, s);
     cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u64), s);
-    init_source_kernel<<<grid_for(std::max<i64>(m.n_hinit, 1), 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p,
-                                                                                 m.n_hinit, (int)(src1 - 1));
+    if (cont) {  // dist / prev were loaded by the caller; dist0 = copy; frontier = star patches of the seeds
+      cudaMemcpyAsync(p.dist0, p.dist, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+      if (cont->nseeds) seed_touch_kernel<<<grid_for(cont->nseeds * 32, 256), 256, 0, s>>>(p, cont->seeds_dev, cont->nseeds);
+    } else {
+      init_state_kernel<<<grid_for(n, 256), 256, 0, s>>>(p.dist, p.dist0, p.prev, n);
+      init_source_kernel<<<grid_for(std::max<i64>(m.n_hinit, 1), 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p,
+                                                                                   m.n_hinit, (int)(src1 - 1));
+    }
     int cur = 0;
     activate_kernel<<<grid_for(m.n_items * 32, 256), 256, 0, s>>>(p, m.n_items, m.act[cur].p, cur);
     cudaMemsetAsync(m.dirty.p, 0, m.nel, s);
@@ -450,4 +475,81 @@ int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sour
   cudaEventDestroy(evr1);
   if (stats) *stats = st;
   return rc;
+}
+
+// Restricted continuation -- the inner loop of bfm_multiphase (src/SSSP/bfm_multiphase.jl:118-150) on the graph of bfm:
+// Jacobi sweeps from the caller's (dist, prev) state in which only nodes with allowed[i] != 0 are relaxed, activated or
+// set by the halo rule; the frontier starts as the allowed nodes of the seeds' star patches.  Host arrays, 1-based ids.
+int bfm2d_continue(rt_mesh* h, const double* U_dev, const uint8_t* allowed, const i64* seeds, i64 nseeds,
+                   double* dist_io, i64* prev_io, rt_stats* stats) {
+  Mesh2D& m = *h->m2;
+  cudaStream_t s = h->stream;
+  RT_TRY(ensure_workspace(h));
+  const i64 n = m.n;
+  if (h->f32) {
+    rt_set_error("rt_bfm_continue is Float64 only");
+    return RT_ERR_UNSUPPORTED;
+  }
+  std::vector<i32> hs(nseeds);
+  for (i64 k = 0; k < nseeds; ++k) {
+    RT_ARG(seeds[k] >= 1 && seeds[k] <= n, "seed out of range");
+    hs[k] = (i32)(seeds[k] - 1);
+  }
+  DevBuf<uint8_t> dal;
+  DevBuf<i32> dseeds;
+  DevBuf<i64> dprev64;
+  if (allowed) RT_TRY(dal.upload(allowed, n, s));
+  RT_TRY(dseeds.upload(hs.data(), nseeds, s));
+  RT_TRY(dprev64.upload(prev_io, n, s));
+  RT_CUDA(cudaMemcpyAsync(m.dist.p, dist_io, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  prev_from_i64_kernel<<<grid_for(n, 256), 256, 0, s>>>(dprev64.p, m.prev.p, n);
+  RT_CUDA(cudaGetLastError());
+  Continuation c{allowed ? dal.p : nullptr, dseeds.p, nseeds};
+  DevBuf<double> dout;
+  DevBuf<i32> pout;
+  RT_TRY(dout.alloc(n));
+  RT_TRY(pout.alloc(n));
+  RT_TRY(bfm2d_solve_impl(h, U_dev, false, nullptr, 1, dout.p, pout.p, stats, &c));
+  RT_CUDA(cudaMemcpyAsync(dist_io, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  RT_TRY(prev_to_host_i64(pout.p, n, prev_io, s));
+  RT_CUDA(cudaStreamSynchronize(s));
+  return RT_OK;
+}
+
+// partition_grid(gr) src/topology/topology.jl:183-206, find_layer_number :137-147: id > 0 = "Layer_id", id < 0 =
+// "Boundary_(-id)"; the radius is rounded to two digits first (Julia: round(r; digits = 2) = round(r * 100) / 100, ties to even)
+namespace {
+__constant__ double c_rl[7] = {6371.0 - 20.0, 6371.0 - 35.0, 6371.0 - 210.0, 6371.0 - 410.0,
+                               6371.0 - 660.0, 6371.0 - 2740.0, 6371.0 - 2891.5};
+__global__ void partition_kernel(const double* __restrict__ r, i64 n, int* __restrict__ id) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ri = __ddiv_rn(rint(__dmul_rn(r[i], 100.0)), 100.0);
+  int out = 0;
+  for (int k = 0; k < 7; ++k)
+    if (ri == c_rl[k]) out = -(k + 1);
+  if (out == 0) {
+    if (ri > c_rl[0]) {
+      out = 1;
+    } else if (ri < c_rl[6]) {
+      out = 8;
+    } else {
+      for (int k = 0; k < 6; ++k)
+        if (c_rl[k] > ri && ri > c_rl[k + 1]) out = k + 2;
+    }
+  }
+  id[i] = out;
+}
+}  // namespace
+
+int mesh2d_partition(const rt_mesh* h, int32_t* id_out) {
+  const Mesh2D& m = *h->m2;
+  RT_ARG(m.has_polar && id_out, "partition_grid needs gr.r and an output array");
+  DevBuf<int> id;
+  RT_TRY(id.alloc(m.n));
+  partition_kernel<<<grid_for(m.n, 256), 256, 0, h->stream>>>(m.r.p, m.n, id.p);
+  RT_CUDA(cudaGetLastError());
+  RT_CUDA(cudaMemcpyAsync(id_out, id.p, m.n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  RT_CUDA(cudaStreamSynchronize(h->stream));
+  return RT_OK;
 }

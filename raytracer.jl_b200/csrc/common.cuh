@@ -130,6 +130,9 @@ int bfm2d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, d
                 rt_stats* stats);
 int bfm2d_solve_dual(rt_mesh* h, const double* U2_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                      rt_stats* stats);
+int bfm2d_continue(rt_mesh* h, const double* U_dev, const uint8_t* allowed, const i64* seeds, i64 nseeds,
+                   double* dist_io, i64* prev_io, rt_stats* stats);
+int mesh2d_partition(const rt_mesh* h, int32_t* id_out);
 int mesh2d_closest(const rt_mesh* h, const double* pa, const double* pb, i64 npts, int system, i64* out);
 int annulus_build_device(rt_mesh* h, i64 ntheta, i64 nr, double spacing);
 int mesh2d_interpolate_cells(rt_mesh* h, const int8_t* el_type_host, double* V_dev);
