@@ -45,14 +45,38 @@ def ray(p, r, eta, inv1mb):
     return 2 * delta, 2 * t, r[0]
 
 
+def rays(ps, r, eta, inv1mb):
+    """Vectorised `ray` for an array of ray parameters: (Delta, T) arrays."""
+    top, bot = eta[1:][::-1], eta[:-1][::-1]  # shells ordered from the surface downwards
+    c = inv1mb[::-1]
+    D = np.zeros(len(ps))
+    T = np.zeros(len(ps))
+    for a in range(0, len(ps), 256):
+        p = ps[a:a + 256, None]
+        stop = (top[None, :] <= p) | (bot[None, :] <= p)
+        first = np.where(stop.any(axis=1), stop.argmax(axis=1), len(top))
+        k = np.arange(len(top))[None, :]
+        above = k < first[:, None]  # shells crossed completely
+        with np.errstate(invalid="ignore"):
+            at, ab = np.arccos(np.minimum(p / top, 1.0)), np.arccos(np.minimum(p / bot, 1.0))
+            st, sb = np.sqrt(np.maximum(top * top - p * p, 0.0)), np.sqrt(np.maximum(bot * bot - p * p, 0.0))
+        D[a:a + 256] = np.sum(np.where(above, c * (at - ab), 0.0), axis=1)
+        T[a:a + 256] = np.sum(np.where(above, c * (st - sb), 0.0), axis=1)
+        # the shell in which the ray turns (top > p >= bot); a ray stopped by top <= p grazes that interface instead
+        rows = np.flatnonzero(first < len(top))
+        kk = first[rows]
+        turn = top[kk] > ps[a:a + 256][rows]
+        rr, kt = rows[turn], kk[turn]
+        D[a + rr] += c[kt] * at[rr, kt]
+        T[a + rr] += c[kt] * st[rr, kt]
+    return 2 * D, 2 * T
+
+
 def first_arrivals(r, v, deltas_rad, n_p=6000):
     """Lower envelope over all turning rays (mantle and core) plus the CMB-diffracted line.  Returns T [s] per Delta."""
     r, v, eta, c = shells(r, v)
     ps = np.linspace(eta[-1] * (1 - 1e-9), 1e-3, n_p)
-    D = np.zeros(n_p)
-    T = np.zeros(n_p)
-    for q, p in enumerate(ps):
-        D[q], T[q], _ = ray(p, r, eta, c)
+    D, T = rays(ps, r, eta, c)
     out = np.full(len(deltas_rad), np.inf)
     # every consecutive pair of rays spans a piece of a travel-time branch: linear interpolation inside it
     d0, d1, t0, t1 = D[:-1], D[1:], T[:-1], T[1:]
