@@ -338,10 +338,47 @@ def batch_cfg3(rt, torch, dist_mod, rank, world, nsrc=512):
 
     solve_fn(sources[rank::world][:8])  # warm-up: workspace allocation, kernels loaded
     sync()
+    # primary route: the library's own sharded solve (contiguous source blocks, ncclAllGather inside librt_sssp.so,
+    # rt_bfm_solve_sharded); if NCCL cannot be bound there, the torch.distributed route of sharded.py is used instead
+    route, comm = "librt_sssp rt_bfm_solve_sharded (ncclAllGather in the library)", None
+    try:
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = C.create_string_buffer(128)
+            rt.api.check(rt.lib().rt_comm_unique_id(raw))
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        if world > 1:
+            idc = idbuf.cuda()
+            dist_mod.broadcast(idc, 0)
+            idbuf = idc.cpu()
+        comm = C.c_void_p()
+        rt.api.check(rt.lib().rt_comm_init(bytes(idbuf.numpy().tobytes()), rank, world, C.byref(comm)))
+    except Exception as e:  # noqa: BLE001
+        route, comm = "torch.distributed all_gather_into_tensor (library route unavailable: %s)" % str(e)[:120], None
+    ok_all = torch.tensor([1 if comm is not None else 0], device="cuda")
+    if world > 1:
+        dist_mod.all_reduce(ok_all, op=dist_mod.ReduceOp.MIN)
+    if int(ok_all[0]) == 0 and comm is not None:
+        rt.lib().rt_comm_destroy(comm)
+        comm, route = None, "torch.distributed all_gather_into_tensor (library route unavailable on another rank)"
+    sync()
     t0 = time.perf_counter()
-    d_all, p_all = sh.solve_sharded(solve_fn, sources, n, device="cuda")
+    if comm is not None:
+        d_all = torch.empty((nsrc, n), dtype=torch.float64, device="cuda")
+        p_all = torch.empty((nsrc, n), dtype=torch.int32, device="cuda")
+        st = rt.RtStats()
+        rt.api.check(rt.lib().rt_bfm_solve_sharded(comm, h.h, U.data_ptr(), sources, nsrc, 64, d_all.data_ptr(),
+                                                   p_all.data_ptr(), C.byref(st)))
+        stats["st"] = st.as_dict()
+        stats["solve_ms"] = stats["st"]["kernel_ms"]
+        owner = lambda g: g // ((nsrc + world - 1) // world)
+    else:
+        d_all, p_all = sh.solve_sharded(solve_fn, sources, n, device="cuda")
+        owner = lambda g: g % world
     sync()
     total_ms = (time.perf_counter() - t0) * 1e3
+    if comm is not None:
+        rt.lib().rt_comm_destroy(comm)
     t = torch.tensor([total_ms, stats["solve_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
@@ -349,7 +386,7 @@ def batch_cfg3(rt, torch, dist_mod, rank, world, nsrc=512):
     out = None
     if rank == 0:
         # verification: fresh single-source solves of sources owned by OTHER ranks (any at N = 1)
-        pick = [g for g in range(nsrc) if world == 1 or g % world != 0]
+        pick = [g for g in range(nsrc) if world == 1 or owner(g) != 0]
         pick = [pick[(len(pick) * q) // 6] for q in range(6)]
         d1 = torch.empty(n, dtype=torch.float64, device="cuda")
         p1 = torch.empty(n, dtype=torch.int32, device="cuda")
@@ -364,7 +401,7 @@ def batch_cfg3(rt, torch, dist_mod, rank, world, nsrc=512):
         src_zero = bool((d_all[torch.arange(nsrc, device="cuda"), torch.as_tensor(sources - 1, device="cuda")] == 0).all())
         e_graph = stats["st"]["graph_edges"]
         out = {"workload": "annulus_720_200_20km x %d sources (BASELINE configs[2])" % nsrc, "nodes": n,
-               "sources": nsrc, "ranks": world, "ms_total": total_ms, "ms_per_source": total_ms / nsrc,
+               "sources": nsrc, "ranks": world, "route": route, "ms_total": total_ms, "ms_per_source": total_ms / nsrc,
                "solve_ms_max_over_ranks": solve_ms, "gather_ms": max(total_ms - solve_ms, 0.0),
                "gteps_graph": e_graph * nsrc / (total_ms * 1e-3) / 1e9,
                "gathered_bytes": int(nsrc) * n * 12, "gather_verified": bool(ok_d and rows_finite and src_zero),

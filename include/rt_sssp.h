@@ -174,6 +174,23 @@ int rt_bfm_solve_dev(rt_mesh* m, const double* U_dev, const int64_t* sources, in
 int rt_bfm_solve_multi(rt_mesh* const* meshes, int ndev, const double* U, const int64_t* sources, int64_t nsrc,
                        int precision, double* dist_out, int64_t* prev_out, rt_stats* stats);
 
+/* One process per GPU (torchrun, mpirun, Distributed.jl): the source batch is sharded over the ranks, every rank solves
+ * its contiguous block sources[first .. first+count) (rt_comm_shard) on its own replica of the mesh, and the
+ * travel-time / predecessor tables are gathered on EVERY rank with one ncclAllGather each over NVLink / NVSwitch
+ * (no collective inside the relaxation).  NCCL is bound at run time (dlopen libnccl.so.2); without it these entry points
+ * return RT_ERR_UNSUPPORTED.  rt_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId, the caller broadcasts it with
+ * whatever it already has (MPI, torch.distributed, a file), then every rank calls rt_comm_init after rt_set_device.
+ * U_dev [n] doubles, dist_dev [nsrc x n] doubles, prev_dev [nsrc x n] int32 (0-based, -1 = never set; may be NULL) are
+ * DEVICE pointers; the tables come back in the order of `sources` on every rank.  stats: the local solve's counters,
+ * prev_ms = device time of the gather. */
+typedef struct rt_comm rt_comm;
+int rt_comm_unique_id(unsigned char id[128]);
+int rt_comm_init(const unsigned char id[128], int rank, int world, rt_comm** out);
+int rt_comm_shard(int64_t nsrc, int rank, int world, int64_t* first, int64_t* count);
+int rt_bfm_solve_sharded(rt_comm* c, rt_mesh* m, const double* U_dev, const int64_t* sources, int64_t nsrc,
+                         int precision, double* dist_dev, int32_t* prev_dev, rt_stats* stats);
+int rt_comm_destroy(rt_comm* c);
+
 /* Dual-velocity variant: bfm with U::Matrix -> _relax!(..., U::Matrix) src/SSSP/bfm.jl:113-159.  U2 is the
  * [n x 2] matrix of dual_velocity (column-major: U[:,1] "below" values, then U[:,2] "above" values); for an edge
  * between node i and candidate j the pair is U[i, tail] + U[j, head] with head = (r_i > r_j) + 1, tail = 3 - head.

@@ -17,7 +17,9 @@ using SparseArrays
 
 export Grid2D, BellmanFordMoore, R, init_annulus, closest_point, interpolate_velocity, bfm, recontruct_path,
        LinearInterpolation, bfm_batch, bfm_batch_multi, set_device, bfm_gpu, interpolate!, symrcm, nodal_degree,
-       dual_velocity, SparseAdjencyList, sparse_adjacency_list, travel_times, set_schedule!, Grid3D, grid, coordinates, BFM
+       dual_velocity, SparseAdjencyList, sparse_adjacency_list, travel_times, set_schedule!, Grid3D, grid, coordinates, BFM,
+       AbstractSPM, Dijkstra, RadiusStepping, dijkstra, radius_stepping, Point, connectivity, CartesianIndex,
+       polardistance3D, set_option!, GridPartition, partition_grid, directions, bfm_continue, bfm_multiphase
 
 const R = 6371.0                                   # src/utils.jl:2
 const LIB = get(ENV, "RT_SSSP_LIB", joinpath(@__DIR__, "..", "raytracer.jl_b200", "librt_sssp.so"))
@@ -69,10 +71,16 @@ mutable struct Grid2D
 end
 Base.length(gr::Grid2D) = gr.nnods
 
-struct BellmanFordMoore{T,M}                       # src/SSSP/ssspm.jl:3-10
-    prev::T
-    dist::M
+abstract type AbstractSPM end                      # src/SSSP/ssspm.jl:1
+for algorithm in (:BellmanFordMoore, :Dijkstra, :RadiusStepping)   # src/SSSP/ssspm.jl:3-10
+    @eval begin
+        struct $(algorithm){T,M} <: AbstractSPM
+            prev::T
+            dist::M
+        end
+    end
 end
+Base.getindex(spm::AbstractSPM) = spm.prev         # src/SSSP/ssspm.jl:12
 
 struct LinearInterpolation                         # stand-in for Interpolations.LinearInterpolation (README.md:32)
     knots::Vector{Float64}
@@ -140,6 +148,20 @@ function closest_point(gr::Grid2D, px, pz; system = :cartesian)
     check(ccall((:rt_closest_point, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Cint, Ptr{Int64}),
                 gr.handle.ptr, [Float64(px)], [Float64(pz)], 1, system == :cartesian ? 0 : 1, out))
     return out[1]
+end
+
+# batched form (receiver sweeps): one device pass per query, any number of queries
+function closest_point(gr::Grid2D, px::AbstractVector, pz::AbstractVector; system = :cartesian)
+    out = zeros(Int64, length(px))
+    check(ccall((:rt_closest_point, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Cint, Ptr{Int64}),
+                gr.handle.ptr, Vector{Float64}(px), Vector{Float64}(pz), length(px), system == :cartesian ? 0 : 1, out))
+    return out
+end
+
+# generic solver / mesh option (include/rt_sssp.h: "schedule", "canonical_prev", "weight3d", "delta", ...)
+function set_option!(gr, key::AbstractString, value::Real)
+    check(ccall((:rt_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Cdouble), gr.handle.ptr, key, Float64(value)))
+    return gr
 end
 
 # bfm(G, halo, source, gr, U) -- src/SSSP/bfm.jl:1-52
@@ -248,11 +270,18 @@ function sparse_adjacency_list(gr::Grid2D)
     return SparseAdjencyList(Int32.(list), Int32.(deg), Int32.(off[1:n] .+ 1))
 end
 
-# travel_times(D, gr, receivers; isave, flname) -- src/utils.jl:4-15 (the CSV is written without DataFrames/CSV.jl)
+# travel_times(D, gr, receivers; isave, flname) -- src/utils.jl:4-15; the gather runs on the device (rt_travel_times), for
+# a batch result (dist :: Matrix n x nsrc) it returns nrec x nsrc.  The CSV is written without DataFrames / CSV.jl.
 function travel_times(D, gr, receivers; isave = false, flname = "")
-    travel_time = [D.dist[receiver] for receiver in receivers]
+    dist = D.dist
+    n, ns = size(dist, 1), size(dist, 2)
+    rec = Vector{Int64}(receivers)
+    out = Matrix{Float64}(undef, length(rec), ns)
+    check(ccall((:rt_travel_times, LIB), Cint, (Ptr{Float64}, Int64, Int64, Ptr{Int64}, Int64, Ptr{Float64}),
+                Array{Float64}(dist), n, ns, rec, length(rec), out))
+    travel_time = ns == 1 ? vec(out) : out
     if isave
-        θ = rad2deg.(gr.θ[receivers])
+        θ = rad2deg.(gr.θ[rec])
         open(joinpath(pwd(), flname), "w") do io
             println(io, "degree,travel_time")
             for (a, b) in zip(θ, travel_time)
@@ -323,6 +352,185 @@ function recontruct_path(prev::Vector, source, receiver)
                 p64, length(p64), source, rc, 1, off, path, length(path)))
     return Vector{Int}(path)
 end
-recontruct_path(D::BellmanFordMoore, source, receiver) = recontruct_path(D.prev, source, receiver)
+# recontruct_path(D, source, receiver) -- src/SSSP/ssspm.jl:14-28, the method on the result structs: the chase runs
+# `while ipath ∉ path` (until a node repeats), then `source` is appended; an unset predecessor throws like the reference
+function recontruct_path(D::AbstractSPM, source, receiver)
+    p64 = Vector{Int64}(D.prev)
+    off = zeros(Int64, 2)
+    rc = Int64[receiver]
+    st = ccall((:rt_reconstruct_paths_guarded, LIB), Cint,
+               (Ptr{Int64}, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Int64),
+               p64, length(p64), source, rc, 1, off, C_NULL, 0)
+    st == 4 && throw(BoundsError(D.prev, 0))
+    check(st)
+    path = zeros(Int64, off[2])
+    check(ccall((:rt_reconstruct_paths_guarded, LIB), Cint,
+                (Ptr{Int64}, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Int64),
+                p64, length(p64), source, rc, 1, off, path, length(path)))
+    return Vector{Int}(path)
+end
+
+# ---- the rest of the 3-D grid surface: src/StructuredGrid.jl:27-31, 57-104, 121-168, 245-270
+struct Point{T}
+    x::T
+    y::T
+    z::T
+end
+function axes3(gr::Grid3D)
+    x, y, z = zeros(gr.nnods[1]), zeros(gr.nnods[2]), zeros(gr.nnods[3])
+    check(ccall((:rt_grid3d_axes, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), gr.handle.ptr, x, y, z))
+    return x, y, z
+end
+function Base.getproperty(gr::Grid3D, s::Symbol)   # gr.x, gr.y, gr.z, gr.nels, gr.nxny like the reference's Grid
+    s === :x && return axes3(gr)[1]
+    s === :y && return axes3(gr)[2]
+    s === :z && return axes3(gr)[3]
+    s === :nels && return getfield(gr, :nnods) .- 1
+    s === :nxny && return getfield(gr, :nnods)[1] * getfield(gr, :nnods)[2]
+    return getfield(gr, s)
+end
+function Base.getindex(gr::Grid3D, I::Int)         # :77-81 (linear index, x fastest)
+    xyz = zeros(3)
+    st = ccall((:rt_grid3d_points, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Int64}),
+               gr.handle.ptr, Int64[I], 1, xyz, C_NULL)
+    st == 1 && throw(BoundsError(gr, I))
+    check(st)
+    return Point(xyz[1], xyz[2], xyz[3])
+end
+function Base.getindex(gr::Grid3D, I::Int, J::Int, K::Int)   # :57-62
+    @assert I <= gr.nnods[1]
+    @assert J <= gr.nnods[2]
+    @assert K <= gr.nnods[3]
+    x, y, z = axes3(gr)
+    return Point(x[I], y[J], z[K])
+end
+function CartesianIndex(gr::Grid3D, I::Int)        # :90-96
+    ijk = zeros(Int64, 3)
+    check(ccall((:rt_grid3d_points, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Int64}),
+                gr.handle.ptr, Int64[I], 1, C_NULL, ijk))
+    return (ijk[1], ijk[2], ijk[3])
+end
+function connectivity(gr::Grid3D)                  # :121-142 -> Vector{NTuple{8,Int64}}
+    nel = prod(gr.nels)
+    e2n = Matrix{Int64}(undef, 8, nel)
+    nel > 0 && check(ccall((:rt_grid3d_connectivity, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}), gr.handle.ptr, 1, nel, e2n))
+    return [ntuple(k -> e2n[k, i], 8) for i in 1:nel]
+end
+function connectivity(gr::Grid3D, iel::Int)        # :146-168
+    e = zeros(Int64, 8)
+    check(ccall((:rt_grid3d_connectivity, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}), gr.handle.ptr, iel, 1, e))
+    return ntuple(k -> e[k], 8)
+end
+function closest_point(gr::Grid3D, x::T, y::T, z::T) where {T}   # :257-270 (raw axis coordinates)
+    out = zeros(Int64, 1)
+    check(ccall((:rt_closest_point3d, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}),
+                gr.handle.ptr, [Float64(x)], [Float64(y)], [Float64(z)], 1, out))
+    return out[1]
+end
+function closest_point(gr::Grid3D, x::AbstractVector, y::AbstractVector, z::AbstractVector)   # receiver sweeps
+    out = zeros(Int64, length(x))
+    check(ccall((:rt_closest_point3d, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}),
+                gr.handle.ptr, Vector{Float64}(x), Vector{Float64}(y), Vector{Float64}(z), length(x), out))
+    return out
+end
+function polardistance3D(p1::Point, p2::Point)     # :245-249
+    out = zeros(1)
+    check(ccall((:rt_polardistance3d, LIB), Cint, (Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                Float64[p1.x, p1.y, p1.z], Float64[p2.x, p2.y, p2.z], 1, out))
+    return out[1]
+end
+
+# ---- alternative solvers behind the same structs: dijkstra(G, source, gr, U) src/SSSP/dijkstra.jl:68-136 and
+# radius_stepping(Gsp, source, gr, U) src/SSSP/radius_stepping.jl:7-46 on the star-0 node graph nodal_incidence(gr)
+# (the graph argument is implied by gr: pass `nothing` or the reference's own container)
+function sssp_nodal(gr::Grid2D, source::Integer, U::AbstractVector, algorithm::Integer)
+    n = gr.nnods
+    dist, prev = Vector{Float64}(undef, n), Vector{Int64}(undef, n)
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0, 0, 0))
+    check(ccall((:rt_sssp_nodal, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
+                gr.handle.ptr, Vector{Float64}(U), source, algorithm, dist, prev, st))
+    println("Converged in $(st[].sweeps + 1) iterations")
+    return prev, dist
+end
+dijkstra(G, source::Int, gr::Grid2D, U::Vector) = Dijkstra(sssp_nodal(gr, source, U, 0)...)
+radius_stepping(Gsp, source::Int, gr::Grid2D, U::Vector) = RadiusStepping(sssp_nodal(gr, source, U, 1)...)
+
+# ---- multiphase: partition_grid / GridPartition src/topology/topology.jl:150-206, bfm_multiphase
+# src/SSSP/bfm_multiphase.jl:30-156 (an unfinished draft in the reference: see rt_bfm_continue in include/rt_sssp.h)
+struct GridPartition
+    id::Vector{String}
+    code::Vector{Int32}                            # k > 0 = "Layer_k", -k = "Boundary_k"
+    rboundaries::NTuple{7,Float64}
+    layers::NTuple{8,String}
+    boundaries::NTuple{7,String}
+    nlayers::Int
+    nboundaries::Int
+    iterator::Dict{Int,Tuple}
+end
+function partition_grid(gr::Grid2D)
+    code = zeros(Int32, gr.nnods)
+    check(ccall((:rt_partition_grid, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), gr.handle.ptr, code))
+    rl = (R - 20.0, R - 35.0, R - 210.0, R - 410.0, R - 660.0, R - 2740.0, R - 2891.5)
+    layers = ntuple(i -> "Layer_$i", 8)
+    boundaries = ntuple(i -> "Boundary_$i", 7)
+    nl, nmax = 8, 15
+    it = Dict{Int,Tuple}()
+    it[1] = it[nmax] = (layers[1], boundaries[1])
+    for i in 2:(nl - 1)
+        it[i] = (layers[i], boundaries[i - 1], boundaries[i])
+        it[nmax - i + 1] = (layers[i], boundaries[i - 1], boundaries[i])
+    end
+    it[nl] = (layers[end], boundaries[end])
+    id = [c > 0 ? "Layer_$c" : "Boundary_$(-c)" for c in code]
+    return GridPartition(id, code, rl, layers, boundaries, 8, 7, it)
+end
+function directions(nlayers)                       # bfm_multiphase.jl:2-14
+    nmax = 2nlayers - 1
+    d = Dict{Int,NTuple{2,Symbol}}()
+    d[1] = d[nmax] = (:above, :above)
+    for i in 2:(nlayers - 1)
+        d[i] = d[nmax - i + 1] = (:below, :above)
+    end
+    d[nlayers] = (:below, :below)
+    return d
+end
+function bfm_continue(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, gr, U::Vector{Float64}, allowed, seeds::Vector{Int64},
+                      dist::Vector{Float64}, prev::Vector{Int64})
+    h = mesh_handle(G, halo, gr)
+    d, p = copy(dist), copy(prev)
+    al = allowed === nothing ? C_NULL : Vector{UInt8}(allowed)
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0, 0, 0))
+    check(ccall((:rt_bfm_continue, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
+                h.ptr, U, al, seeds, length(seeds), d, p, st))
+    return BellmanFordMoore(p, d), st[]
+end
+function bfm_multiphase(G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, source::Int, gr, U::Vector{Float64},
+                        partition::GridPartition, interpolant::LinearInterpolation; nphases = 3, buffer_zone = 1.0)
+    n = G.n
+    U = copy(U)
+    rdir = directions(partition.nlayers)
+    rb = Dict(a => b for (a, b) in zip(partition.boundaries, partition.rboundaries))
+    code_of(nm) = (s = split(nm, "_"); s[1] == "Layer" ? parse(Int, s[2]) : -parse(Int, s[2]))
+    bnodes = Dict(a => findall(partition.code .== code_of(a)) for a in partition.boundaries)
+    dist = fill(typemax(Float64), n); dist[source] = 0.0
+    prev = zeros(Int64, n)
+    for i in 1:size(halo, 1)                        # init_halo_path! (bfm.jl:64-70)
+        prev[halo[i, 2]] = halo[i, 1]; prev[halo[i, 1]] = halo[i, 2]
+    end
+    D = BellmanFordMoore(prev, dist)
+    for i in 1:nphases
+        level = partition.iterator[i]
+        for (k, b) in enumerate(level[2:end])       # boundary_velocity! (:16-28)
+            rq = rdir[i][k] == :above ? rb[b] - buffer_zone : rb[b] + buffer_zone
+            U[bnodes[b]] .= interpolate_velocity([rq], interpolant)[1]
+        end
+        seeds = i == 1 ? Int64[source] : Int64[j for j in bnodes[level[2]] if isfinite(D.dist[j])]
+        allowed = UInt8[partition.id[j] in level for j in 1:n]
+        D, st = bfm_continue(G, halo, gr, U, allowed, seeds, D.dist, D.prev)
+        println("Level $i converged in $(st.sweeps) iterations")
+    end
+    return D
+end
 
 end # module

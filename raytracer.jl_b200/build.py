@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode:
             raise RuntimeError("nvcc failed on " + src)
-    cmd = [nvcc, "-ccbin", ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs + ["-lcudart"]
+    cmd = [nvcc, "-ccbin", ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return SO
 

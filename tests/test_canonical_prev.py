@@ -142,3 +142,40 @@ def test_config0_readme_example_full_size_pinned(rt, O):
     assert np.array_equal(gr2.r, m.r) and np.array_equal(gr2.theta, m.theta)
     D2 = rt.bfm(G2, halo2, src, gr2, Vp, schedule="near-far", canonical_prev=False)
     assert np.allclose(D2.dist, D.dist, rtol=1e-12, atol=0)
+
+
+def test_library_sharded_solve_single_rank(rt, O, annulus, ak135):
+    """rt_comm_* / rt_bfm_solve_sharded (NCCL bound at run time inside the library) with a world of one rank: the gathered
+    tables equal the tables of rt_bfm_solve.  (The N > 1 exchange itself runs in bench.py's batch_cfg3 block.)"""
+    import ctypes as C
+    import torch
+    m = annulus(36, 10, 100.0)
+    gr, G, halo = adopt(rt, m)
+    Vp = rt.interpolate_velocity(gr.r, rt.LinearInterpolation(*ak135))
+    h = rt.mesh_from_arrays(gr, G, halo)
+    srcs = np.array([1, 57, 400, m.n, 9000], np.int64)
+    raw = C.create_string_buffer(128)
+    rt.api.check(rt.lib().rt_comm_unique_id(raw))
+    comm = C.c_void_p()
+    rt.api.check(rt.lib().rt_comm_init(raw.raw, 0, 1, C.byref(comm)))
+    first, count = C.c_int64(), C.c_int64()
+    for nsrc, world in ((5, 1), (10, 4), (3, 8)):
+        tot = 0
+        for r in range(world):
+            rt.api.check(rt.lib().rt_comm_shard(nsrc, r, world, C.byref(first), C.byref(count)))
+            assert first.value == tot and 0 <= count.value <= -(-nsrc // world)
+            tot += count.value
+        assert tot == nsrc
+    U = torch.from_numpy(Vp).cuda()
+    d = torch.empty((len(srcs), m.n), dtype=torch.float64, device="cuda")
+    p = torch.empty((len(srcs), m.n), dtype=torch.int32, device="cuda")
+    h.set_option("schedule", 1)
+    st = rt.RtStats()
+    rt.api.check(rt.lib().rt_bfm_solve_sharded(comm, h.h, U.data_ptr(), srcs, len(srcs), 64, d.data_ptr(), p.data_ptr(),
+                                               C.byref(st)))
+    rt.api.check(rt.lib().rt_comm_destroy(comm))
+    D = rt.bfm(G, halo, srcs, gr, Vp, schedule="near-far")
+    assert np.array_equal(d.cpu().numpy(), D.dist)
+    for k, s in enumerate(srcs):
+        assert np.array_equal(D.dist[k], O.bfm(m, Vp, int(s))[0])
+    h.set_option("schedule", 0)
