@@ -525,7 +525,52 @@ def other_workloads(rt, torch, peak, peak_src, sm_mhz):
                 "relax_kernel_share_of_step": ex["relax_kernel_share_of_step"]}
             del wl
             torch.cuda.empty_cache()
+    try:
+        out["annulus_180_50_1km/near-far/rcm_reordered"] = rcm_check(rt, torch)
+    except Exception as e:  # noqa: BLE001 -- an auxiliary measurement must not take the bench line down
+        out["annulus_180_50_1km/near-far/rcm_reordered"] = {"error": str(e)[:200]}
     return out
+
+
+def rcm_check(rt, torch, ntheta=180, nr=50, spacing=1.0):
+    """BASELINE configs[1] names Cuthill-McKee reordering (the reference measured ~2x from it on its thread-per-vertex
+    kernels).  Measured here on the README mesh: the same solve on the natural numbering of init_annulus and on the
+    symrcm-reordered mesh (reorder! of src/SSSP/rcm.jl:62-85, relabelled G and halo included)."""
+    import ctypes as C
+    gr, G, halo = rt.init_annulus(ntheta, nr, spacing=spacing)
+    prof = rt.velocity_profile()
+    Vp = rt.interpolate_velocity(gr.r, rt.LinearInterpolation(prof.r, prof.Vp))
+    src = int(rt.closest_point(gr, 0.0, R, system="polar"))
+    t0 = time.perf_counter()
+    prm = rt.symrcm(gr)
+    rcm_ms = (time.perf_counter() - t0) * 1e3
+    gr2, G2, halo2 = rt.reorder(gr, G, halo, prm)
+    inv = np.zeros(gr.nnods + 1, np.int64)
+    inv[prm] = np.arange(1, gr.nnods + 1)
+    res = {"nodes": gr.nnods, "symrcm_ms": rcm_ms}
+    ref = None
+    for key, (g_, G_, h_, U_, s_) in (("natural", (gr, G, halo, Vp, src)),
+                                      ("rcm", (gr2, G2, halo2, Vp[prm - 1], int(inv[src])))):
+        h = rt.mesh_from_arrays(g_, G_, h_) if key == "rcm" else g_._handle
+        h.set_option("schedule", 1)
+        Ud = torch.from_numpy(np.ascontiguousarray(U_)).cuda()
+        d = torch.empty(g_.nnods, dtype=torch.float64, device="cuda")
+        p = torch.empty(g_.nnods, dtype=torch.int32, device="cuda")
+        ts = []
+        for _ in range(4):
+            st = rt.RtStats()
+            t0 = time.perf_counter()
+            rt.api.check(rt.lib().rt_bfm_solve_dev(h.h, Ud.data_ptr(), np.array([s_], np.int64), 1, 64, d.data_ptr(),
+                                                   p.data_ptr(), C.byref(st)))
+            ts.append((time.perf_counter() - t0) * 1e3)
+        res[key + "_ms_per_source"] = float(np.median(ts[1:]))
+        dd = d.cpu().numpy()
+        if key == "natural":
+            ref = dd
+        else:
+            res["same_travel_times"] = bool(np.array_equal(dd, ref[prm - 1]))
+    res["rcm_over_natural"] = res["rcm_ms_per_source"] / res["natural_ms_per_source"]
+    return res
 
 
 def run_gpu(args):

@@ -528,11 +528,14 @@ def bfm_gpu(G, halo, source, gr, U, schedule=None, canonical_prev=None):
     return bfm(G, halo, source, gr, U, schedule=schedule, precision=32, canonical_prev=canonical_prev)
 
 
-def bfm3d(gr3, source, U, schedule=None, delta=None, precision=64):
+def bfm3d(gr3, source, U, schedule=None, delta=None, precision=64, canonical_prev=None):
     """BFM(G, source, gr, U, fw) of src/Dijsktra.jl:294-343 on the implicit star-L graph of a Grid3D with the
-    edge weight of src/SSSP/weights.jl:20."""
+    edge weight of src/SSSP/weights.jl:20 (option "weight3d" = 1: the expression inside foo!, Dijsktra.jl:388).
+    canonical_prev=True (near-far): predecessors of the reference schedule, ties included."""
     if schedule is not None:
         gr3._handle.set_option("schedule", SCHEDULES[schedule])
+    if canonical_prev is not None:
+        gr3._handle.set_option("canonical_prev", 1 if canonical_prev else 0)
     if delta is not None:
         gr3._handle.set_option("delta", delta)
     dist, prev, st = _solve(gr3._handle, gr3.n, U, source, precision=precision)

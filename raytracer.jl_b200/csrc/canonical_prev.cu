@@ -59,6 +59,11 @@ struct CP {
   // control block: [0] cur parity [1] level L [2] done [3] n overflow [4] queued groups; counts: cnt[0], cnt[1]
   int* ctl;
   unsigned long long* cnt;
+  // 3-D structured grid (implicit window adjacency, canonical scan order = ascending linear id); x, z unused there
+  const double* __restrict__ X3;
+  const double* __restrict__ Y3;
+  const double* __restrict__ Z3;
+  int nx, ny, nz, w3, self3, wmode3;
 };
 
 template <int MODE>
@@ -313,6 +318,84 @@ __global__ void cp_halo_kernel(CP p) {
   }
 }
 
+// ---- 3-D: tight predecessors of node I inside its clipped window, ascending linear id (thread per node)
+template <bool F32>
+__device__ __forceinline__ bool is_tight3(const CP& p, double di, double xi, double yi, double zi, double ui, i64 J) {
+  const double dj = p.dist[J];
+  if (!(dj <= di)) return false;
+  const double xj = p.X3[J], yj = p.Y3[J], zj = p.Z3[J], uj = p.U1[J];
+  const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  if (!screen_maybe_tight_t<F32>(di, dj, d2, screen_ssum3(fabs(__dadd_rn(ui, uj)), p.wmode3))) return false;
+  return exact_cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj, p.wmode3) == di;
+}
+template <bool F32>
+__global__ void __launch_bounds__(128) tight_build3_kernel(CP p) {
+  const i64 I = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= p.n) return;
+  const double di = p.dist[I];
+  int cnt = 0;
+  int b[KT];
+#pragma unroll
+  for (int q = 0; q < KT; ++q) b[q] = -1;
+  if (di < __longlong_as_double(0x7ff0000000000000LL) && (int)I != p.source) {
+    const int i = (int)(I % p.nx), j = (int)((I / p.nx) % p.ny), k = (int)(I / ((i64)p.nx * p.ny));
+    const double xi = p.X3[I], yi = p.Y3[I], zi = p.Z3[I], ui = p.U1[I];
+    const int w = p.w3;
+    for (int zz = max(0, k - w); zz <= min(p.nz - 1, k + w); ++zz)
+      for (int yy = max(0, j - w); yy <= min(p.ny - 1, j + w); ++yy)
+        for (int xx = max(0, i - w); xx <= min(p.nx - 1, i + w); ++xx) {
+          const i64 J = (i64)xx + (i64)p.nx * ((i64)yy + (i64)p.ny * zz);
+          if (J == I) continue;
+          if (!is_tight3<F32>(p, di, xi, yi, zi, ui, J)) continue;
+          if (cnt < KT) {
+#pragma unroll
+            for (int e = 0; e < KT; ++e)
+              if (e == cnt) b[e] = (int)J;
+          }
+          ++cnt;
+        }
+  }
+  p.tcnt[I] = cnt > KT ? KT + 1 : cnt;
+#pragma unroll
+  for (int e = 0; e < KT; ++e) p.tight[I * KT + e] = b[e];
+  if (cnt > KT) p.ovf[atomicAdd(&p.ctl[3], 1)] = (i32)I;
+}
+template <bool F32>
+__global__ void cp_overflow3_kernel(CP p) {
+  if (p.ctl[2]) return;
+  const int cur = p.ctl[0], L = p.ctl[1];
+  i32* nx = cur ? p.fr0 : p.fr1;
+  const int lane = threadIdx.x & 31;
+  const int no = p.ctl[3];
+  for (int wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wq < no; wq += (gridDim.x * blockDim.x) >> 5) {
+    const i64 I = p.ovf[wq];
+    if (p.level[I] != -1) continue;  // warp-uniform
+    const int i = (int)(I % p.nx), j = (int)((I / p.nx) % p.ny), k = (int)(I / ((i64)p.nx * p.ny));
+    const double di = p.dist[I], xi = p.X3[I], yi = p.Y3[I], zi = p.Z3[I], ui = p.U1[I];
+    const int w = p.w3;
+    const int x0 = max(0, i - w), x1 = min(p.nx - 1, i + w), y0 = max(0, j - w), y1 = min(p.ny - 1, j + w);
+    const int z0 = max(0, k - w), z1 = min(p.nz - 1, k + w);
+    const int cx = x1 - x0 + 1, cy = y1 - y0 + 1, total = cx * cy * (z1 - z0 + 1);
+    i64 best = 0x7fffffffffffffffLL;
+    for (int t = lane; t < total; t += 32) {  // window cells in ascending linear id
+      const int xx = x0 + t % cx, yy = y0 + (t / cx) % cy, zz = z0 + t / (cx * cy);
+      const i64 J = (i64)xx + (i64)p.nx * ((i64)yy + (i64)p.ny * zz);
+      if (J == I || J > best || p.level[J] != L - 1) continue;
+      if (is_tight3<F32>(p, di, xi, yi, zi, ui, J)) best = J;
+    }
+    for (int o = 16; o; o >>= 1) {
+      const i64 ob = __shfl_xor_sync(FULL, best, o);
+      best = ob < best ? ob : best;
+    }
+    if (lane == 0 && best != 0x7fffffffffffffffLL) {
+      p.level[I] = L;
+      p.prev[I] = (i32)best;
+      nx[atomicAdd(&p.cnt[cur ^ 1], 1ull)] = (i32)I;
+    }
+  }
+}
+
 template <int MODE>
 void launch_tight(const CP& p, unsigned grid, cudaStream_t s) {
   tight_build_kernel<MODE><<<grid, 128, 0, s>>>(p);
@@ -336,70 +419,30 @@ struct CanonWs {
 
 void canon_ws_free(CanonWs* w) { delete w; }
 
-// dist: converged travel times [n] (plain doubles); prev: [n] int32, overwritten for every reached node but the source.
-// mode: 0 fp64 (U1 = U), 1 dual velocity (U1, U2 = the two columns, needs gr.r), 2 Float32 arithmetic (x, z, U already rounded)
-int canonical_prev_2d(rt_mesh* h, const double* x, const double* z, const double* U1, const double* U2, int mode,
-                      const double* dist, int source, i32* prev, i64* levels_out, i64* launches_out) {
-  Mesh2D& m = *h->m2;
-  cudaStream_t s = h->stream;
-  const i64 n = m.n;
-  if (m.halo_rows > 0 && !m.halo_structured) {
-    rt_set_error("canonical_prev needs the halo matrix of init_annulus ((orig, twin) rows, then (twin, orig) rows)");
-    return RT_ERR_UNSUPPORTED;
-  }
-  if (!m.canon) m.canon = new CanonWs();
-  CanonWs& w = *m.canon;
-  const int n_groups = (int)m.n_h2_orig;
-  if (!w.ready) {
-    RT_TRY(w.tight.alloc((size_t)n * KT));
-    RT_TRY(w.tcnt.alloc(n));
-    RT_TRY(w.ovf.alloc(n));
-    RT_TRY(w.succ_cnt.alloc(n + 1));
-    RT_TRY(w.succ_cur.alloc(n));
-    RT_TRY(w.succ_idx.alloc((size_t)n * KT));
-    RT_TRY(w.level.alloc(n));
-    RT_TRY(w.fr0.alloc(n));
-    RT_TRY(w.fr1.alloc(n));
-    RT_TRY(w.ctl.alloc(8));
-    RT_TRY(w.cnt.alloc(2));
-    RT_TRY(w.g_stamp.alloc(std::max(n_groups, 1)));
-    RT_TRY(w.g_list.alloc(std::max(n_groups, 1)));
-    cub::DeviceScan::ExclusiveSum(nullptr, w.scan_bytes, w.succ_cnt.p, w.succ_cnt.p, n + 1, s);
-    RT_TRY(w.scan_tmp.alloc(w.scan_bytes));
-    // halo-node row -> group (orig and twins of one orig share a group)
-    if (m.n_hn > 0) {
-      std::vector<i32> hn(m.n_hn), go(std::max(n_groups, 1)), gt(std::max<i64>(m.H, 1)), goff(n_groups + 1);
-      RT_CUDA(cudaMemcpy(hn.data(), m.hn_node.p, m.n_hn * sizeof(i32), cudaMemcpyDeviceToHost));
-      std::vector<i32> grp(m.n_hn, -1);
-      if (n_groups > 0) {
-        RT_CUDA(cudaMemcpy(go.data(), m.h2_orig.p, n_groups * sizeof(i32), cudaMemcpyDeviceToHost));
-        RT_CUDA(cudaMemcpy(goff.data(), m.h2_off.p, (n_groups + 1) * sizeof(i32), cudaMemcpyDeviceToHost));
-        RT_CUDA(cudaMemcpy(gt.data(), m.h2_twin.p, m.H * sizeof(i32), cudaMemcpyDeviceToHost));
-        auto row_of = [&](i32 node) { return (i64)(std::lower_bound(hn.begin(), hn.end(), node) - hn.begin()); };
-        for (int g = 0; g < n_groups; ++g) {
-          grp[row_of(go[g])] = g;
-          for (int e = goff[g]; e < goff[g + 1]; ++e) grp[row_of(gt[e])] = g;
-        }
-      }
-      RT_TRY(w.hn_group.upload(grp.data(), grp.size()));
-    }
-    w.ready = true;
-  }
-  CP p;
-  p.x = x;
-  p.z = z;
-  p.U1 = U1;
-  p.U2 = U2 ? U2 : U1;
-  p.r = m.r.p;
-  p.e2n_off = m.e2n_off.p;
-  p.e2n_idx = m.e2n_idx.p;
-  p.g_off = m.g_off.p;
-  p.g_idx = m.g_idx.p;
-  p.item_first = m.item_first.p;
-  p.dist = dist;
-  p.n = n;
-  p.n_items = m.n_items;
-  p.source = source;
+namespace {
+
+int ensure_canon_ws(CanonWs& w, i64 n, int n_groups, cudaStream_t s) {
+  if (w.ready) return RT_OK;
+  RT_TRY(w.tight.alloc((size_t)n * KT));
+  RT_TRY(w.tcnt.alloc(n));
+  RT_TRY(w.ovf.alloc(n));
+  RT_TRY(w.succ_cnt.alloc(n + 1));
+  RT_TRY(w.succ_cur.alloc(n));
+  RT_TRY(w.succ_idx.alloc((size_t)n * KT));
+  RT_TRY(w.level.alloc(n));
+  RT_TRY(w.fr0.alloc(n));
+  RT_TRY(w.fr1.alloc(n));
+  RT_TRY(w.ctl.alloc(8));
+  RT_TRY(w.cnt.alloc(2));
+  RT_TRY(w.g_stamp.alloc(std::max(n_groups, 1)));
+  RT_TRY(w.g_list.alloc(std::max(n_groups, 1)));
+  cub::DeviceScan::ExclusiveSum(nullptr, w.scan_bytes, w.succ_cnt.p, w.succ_cnt.p, n + 1, s);
+  RT_TRY(w.scan_tmp.alloc(w.scan_bytes));
+  w.ready = true;
+  return RT_OK;
+}
+
+void bind_ws(CP& p, CanonWs& w) {
   p.tight = w.tight.p;
   p.tcnt = w.tcnt.p;
   p.ovf = w.ovf.p;
@@ -407,32 +450,37 @@ int canonical_prev_2d(rt_mesh* h, const double* x, const double* z, const double
   p.succ_cur = w.succ_cur.p;
   p.succ_idx = w.succ_idx.p;
   p.level = w.level.p;
-  p.prev = prev;
   p.fr0 = w.fr0.p;
   p.fr1 = w.fr1.p;
-  p.hn_index = m.hn_index.p;
   p.hn_group = w.hn_group.p;
-  p.g_orig = m.h2_orig.p;
-  p.g_toff = m.h2_off.p;
-  p.g_twin = m.h2_twin.p;
   p.g_stamp = w.g_stamp.p;
   p.g_list = w.g_list.p;
-  p.n_groups = n_groups;
   p.ctl = w.ctl.p;
   p.cnt = w.cnt.p;
+}
+
+// kind: 0..2 = 2-D relax modes (MODE_*), 3 = 3-D fp64, 4 = 3-D Float32
+int run_canonical(rt_mesh* h, CP& p, CanonWs& w, int kind, i64 n_items, i64* levels_out, i64* launches_out) {
+  cudaStream_t s = h->stream;
+  const i64 n = p.n;
+  const int n_groups = p.n_groups;
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
   const unsigned gfull = grid_for(std::max<i64>(n, n_groups), 256);
   RT_CUDA(cudaMemsetAsync(w.ctl.p, 0, 8 * sizeof(int), s));
   RT_CUDA(cudaMemsetAsync(w.succ_cnt.p, 0, (n + 1) * sizeof(i32), s));
   RT_CUDA(cudaMemsetAsync(w.succ_cur.p, 0, n * sizeof(i32), s));
-  const unsigned gt = (unsigned)std::min<i64>((m.n_items + 3) / 4, (i64)sm_count * 32);
-  if (mode == MODE_DUAL)
+  const unsigned gt = (unsigned)std::min<i64>((n_items + 3) / 4, (i64)sm_count * 32);
+  if (kind == MODE_DUAL)
     launch_tight<MODE_DUAL>(p, gt, s);
-  else if (mode == MODE_F32)
+  else if (kind == MODE_F32)
     launch_tight<MODE_F32>(p, gt, s);
-  else
+  else if (kind == MODE_F64)
     launch_tight<MODE_F64>(p, gt, s);
+  else if (kind == 3)
+    tight_build3_kernel<false><<<grid_for(n, 128), 128, 0, s>>>(p);
+  else
+    tight_build3_kernel<true><<<grid_for(n, 128), 128, 0, s>>>(p);
   succ_count_kernel<<<grid_for(n, 256), 256, 0, s>>>(p);
   cub::DeviceScan::ExclusiveSum(w.scan_tmp.p, w.scan_bytes, w.succ_cnt.p, w.succ_cnt.p, n + 1, s);
   succ_fill_kernel<<<grid_for(n, 256), 256, 0, s>>>(p);
@@ -449,12 +497,16 @@ int canonical_prev_2d(rt_mesh* h, const double* x, const double* z, const double
       cp_begin_kernel<<<1, 1, 0, s>>>(p);
       cp_expand_kernel<<<gsm, 256, 0, s>>>(p);
       if (has_ovf) {
-        if (mode == MODE_DUAL)
+        if (kind == MODE_DUAL)
           launch_overflow<MODE_DUAL>(p, gsm, s);
-        else if (mode == MODE_F32)
+        else if (kind == MODE_F32)
           launch_overflow<MODE_F32>(p, gsm, s);
-        else
+        else if (kind == MODE_F64)
           launch_overflow<MODE_F64>(p, gsm, s);
+        else if (kind == 3)
+          cp_overflow3_kernel<false><<<gsm, 128, 0, s>>>(p);
+        else
+          cp_overflow3_kernel<true><<<gsm, 128, 0, s>>>(p);
       }
       cp_select_kernel<<<gsm, 256, 0, s>>>(p);
       if (n_groups > 0) cp_halo_kernel<<<gsm, 256, 0, s>>>(p);
@@ -463,7 +515,7 @@ int canonical_prev_2d(rt_mesh* h, const double* x, const double* z, const double
     enq += 32;
     RT_CUDA(cudaMemcpyAsync(hctl, w.ctl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
     RT_CUDA(cudaStreamSynchronize(s));
-    if (enq > ((i64)1 << 22)) {
+    if (enq > n + 64) {
       rt_set_error("canonical_prev did not terminate");
       return RT_ERR_CUDA;
     }
@@ -472,4 +524,93 @@ int canonical_prev_2d(rt_mesh* h, const double* x, const double* z, const double
   if (levels_out) *levels_out = hctl[1];  // == the reference's sweep count
   if (launches_out) *launches_out = launches;
   return RT_OK;
+}
+
+}  // namespace
+
+// dist: converged travel times [n] (plain doubles); prev: [n] int32, overwritten for every reached node but the source.
+// mode: 0 fp64 (U1 = U), 1 dual velocity (U1, U2 = the two columns, needs gr.r), 2 Float32 arithmetic (x, z, U already rounded)
+int canonical_prev_2d(rt_mesh* h, const double* x, const double* z, const double* U1, const double* U2, int mode,
+                      const double* dist, int source, i32* prev, i64* levels_out, i64* launches_out) {
+  Mesh2D& m = *h->m2;
+  cudaStream_t s = h->stream;
+  const i64 n = m.n;
+  if (m.halo_rows > 0 && !m.halo_structured) {
+    rt_set_error("canonical_prev needs the halo matrix of init_annulus ((orig, twin) rows, then (twin, orig) rows)");
+    return RT_ERR_UNSUPPORTED;
+  }
+  if (!m.canon) m.canon = new CanonWs();
+  CanonWs& w = *m.canon;
+  const int n_groups = (int)m.n_h2_orig;
+  const bool first = !w.ready;
+  RT_TRY(ensure_canon_ws(w, n, n_groups, s));
+  if (first && m.n_hn > 0) {  // halo-node row -> group (orig and twins of one orig share a group)
+    std::vector<i32> hn(m.n_hn), go(std::max(n_groups, 1)), gt(std::max<i64>(m.H, 1)), goff(n_groups + 1);
+    RT_CUDA(cudaMemcpy(hn.data(), m.hn_node.p, m.n_hn * sizeof(i32), cudaMemcpyDeviceToHost));
+    std::vector<i32> grp(m.n_hn, -1);
+    if (n_groups > 0) {
+      RT_CUDA(cudaMemcpy(go.data(), m.h2_orig.p, n_groups * sizeof(i32), cudaMemcpyDeviceToHost));
+      RT_CUDA(cudaMemcpy(goff.data(), m.h2_off.p, (n_groups + 1) * sizeof(i32), cudaMemcpyDeviceToHost));
+      RT_CUDA(cudaMemcpy(gt.data(), m.h2_twin.p, m.H * sizeof(i32), cudaMemcpyDeviceToHost));
+      auto row_of = [&](i32 node) { return (i64)(std::lower_bound(hn.begin(), hn.end(), node) - hn.begin()); };
+      for (int g = 0; g < n_groups; ++g) {
+        grp[row_of(go[g])] = g;
+        for (int e = goff[g]; e < goff[g + 1]; ++e) grp[row_of(gt[e])] = g;
+      }
+    }
+    RT_TRY(w.hn_group.upload(grp.data(), grp.size()));
+  }
+  CP p = {};
+  p.x = x;
+  p.z = z;
+  p.U1 = U1;
+  p.U2 = U2 ? U2 : U1;
+  p.r = m.r.p;
+  p.e2n_off = m.e2n_off.p;
+  p.e2n_idx = m.e2n_idx.p;
+  p.g_off = m.g_off.p;
+  p.g_idx = m.g_idx.p;
+  p.item_first = m.item_first.p;
+  p.dist = dist;
+  p.n = n;
+  p.n_items = m.n_items;
+  p.source = source;
+  p.prev = prev;
+  bind_ws(p, w);
+  p.hn_index = m.hn_index.p;
+  p.g_orig = m.h2_orig.p;
+  p.g_toff = m.h2_off.p;
+  p.g_twin = m.h2_twin.p;
+  p.n_groups = n_groups;
+  return run_canonical(h, p, w, mode, m.n_items, levels_out, launches_out);
+}
+
+// 3-D structured grid: the same pass on the implicit window adjacency (canonical scan order = ascending linear id; no
+// halo).  X, Y, Z, U are the arrays the solve used (Float32-rounded copies when f32).
+int canonical_prev_3d(rt_mesh* h, CanonWs** ws, const Grid3Desc& g, const double* U, bool f32, const double* dist,
+                      i64 source, i32* prev, i64* launches_out) {
+  const i64 n = (i64)g.nx * g.ny * g.nz;
+  if (!*ws) *ws = new CanonWs();
+  CanonWs& w = **ws;
+  RT_TRY(ensure_canon_ws(w, n, 0, h->stream));
+  CP p = {};
+  p.U1 = U;
+  p.U2 = U;
+  p.dist = dist;
+  p.n = n;
+  p.n_items = 0;
+  p.source = (int)source;
+  p.prev = prev;
+  bind_ws(p, w);
+  p.n_groups = 0;
+  p.X3 = g.X;
+  p.Y3 = g.Y;
+  p.Z3 = g.Z;
+  p.nx = g.nx;
+  p.ny = g.ny;
+  p.nz = g.nz;
+  p.w3 = g.w;
+  p.self3 = g.self;
+  p.wmode3 = g.wmode;
+  return run_canonical(h, p, w, f32 ? 4 : 3, 0, nullptr, launches_out);
 }

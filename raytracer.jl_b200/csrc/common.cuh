@@ -118,6 +118,16 @@ struct rt_mesh {
   DevBuf<i64> stage_prev64;
 };
 
+// canonical-predecessor pass (canonical_prev.cu)
+struct CanonWs;
+void canon_ws_free(CanonWs* w);
+struct Grid3Desc {
+  const double *X, *Y, *Z;
+  int nx, ny, nz, w, self, wmode;
+};
+int canonical_prev_3d(rt_mesh* h, CanonWs** ws, const Grid3Desc& g, const double* U, bool f32, const double* dist,
+                      i64 source, i32* prev, i64* launches_out);
+
 // 2-D (mesh2d.cu / bfm2d.cu)
 int mesh2d_from_host(rt_mesh* h, i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, const i64* colptr,
                      const i64* rowval, const i64* halo, i64 halo_rows, const double* x, const double* z,

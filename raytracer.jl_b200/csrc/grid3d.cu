@@ -52,6 +52,7 @@ struct Grid3D {
   DevBuf<int> ctl;
   DevBuf<i32> unresolved;
   bool push_ready = false;
+  CanonWs* canon = nullptr;  // canonical-predecessor pass (option canonical_prev)
 };
 
 namespace {
@@ -353,6 +354,7 @@ int grid3d_export(const rt_mesh* h, double* X, double* Y, double* Z) {
 void grid3d_free(rt_mesh* h) {
   if (h->g3) {
     if (h->g3->counters_host) cudaFreeHost(h->g3->counters_host);
+    if (h->g3->canon) canon_ws_free(h->g3->canon);
     delete h->g3;
   }
   h->g3 = nullptr;
@@ -857,8 +859,15 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       prev_tight3_kernel<true><<<grid_for(n, 128), 128, 0, s>>>(p, n, src);
     else
       prev_tight3_kernel<false><<<grid_for(n, 128), 128, 0, s>>>(p, n, src);
-    cudaEventRecord(evr1, s);
     st.total_launches += 1;
+    if (h->opts.canonical_prev) {  // the reference schedule's predecessors, ties included (canonical_prev.cu)
+      Grid3Desc gd{p.X, p.Y, p.Z, p.nx, p.ny, p.nz, p.w, p.self, p.wmode};
+      i64 launches = 0;
+      rc = canonical_prev_3d(h, &g.canon, gd, U_dev, f32, g.dist.p, src, g.prev.p, &launches);
+      st.total_launches += launches;
+      if (rc != RT_OK) break;
+    }
+    cudaEventRecord(evr1, s);
     cudaMemcpyAsync(ch, g.counters.p, 8 * sizeof(u64), cudaMemcpyDeviceToHost, s);
     cudaEventRecord(ev1, s);
     if (dist_dev) cudaMemcpyAsync(dist_dev + si * n, g.dist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);

@@ -11,9 +11,6 @@
 #pragma once
 #include "common.cuh"
 
-struct CanonWs;  // workspace of the canonical-predecessor pass (canonical_prev.cu)
-void canon_ws_free(CanonWs* w);
-
 struct Mesh2D {
   i64 n = 0, nel = 0, sum_e2n = 0, nnzG = 0, halo_rows = 0, sum_nbr = 0, ntheta = 0, nr = 0;
   DevBuf<double> x, z, theta, r;

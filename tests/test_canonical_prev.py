@@ -179,3 +179,35 @@ def test_library_sharded_solve_single_rank(rt, O, annulus, ak135):
     for k, s in enumerate(srcs):
         assert np.array_equal(D.dist[k], O.bfm(m, Vp, int(s))[0])
     h.set_option("schedule", 0)
+
+
+@pytest.mark.parametrize("nn,lv,cs,wm", [((7, 6, 5), 1, "spherical", 0), ((11, 11, 11), 1, "cartesian", 0),
+                                         ((20, 9, 13), 0, "spherical", 1), ((33, 18, 10), 2, "cartesian", 0),
+                                         ((40, 40, 24), 1, "spherical", 0)])
+def test_near_far_3d_canonical_prev_equals_reference_schedule(rt, O, nn, lv, cs, wm):
+    """3-D: near-far + canonical pass == the Jacobi schedule's predecessors bit for bit (canonical scan order =
+    ascending linear id), including the homogeneous Cartesian grid where collinear exact ties are everywhere."""
+    if cs == "spherical":
+        c0 = (np.deg2rad(70.0), np.deg2rad(70.0), R - 2000.0)
+        c1 = (np.deg2rad(110.0), np.deg2rad(110.0), R)
+    else:
+        c0, c1 = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)
+    g = rt.grid(c0, c1, nn, neighbour_levels=lv, coord_system=cs)
+    X, Y, Z = g.coordinates()
+    n = g.n
+    g._handle.set_option("weight3d", wm)
+    O.set_weight3d(wm)
+    try:
+        for U in (4.0 + 6.0 * splitmix64(7 + n, n), np.ones(n)):
+            for src in (1, n // 2 + 3):
+                dist, prev, st = O.bfm3d(nn, lv, X, Y, Z, U, src)
+                D = rt.bfm3d(g, src, U, schedule="near-far", canonical_prev=True)
+                assert np.array_equal(D.dist, dist)
+                assert np.array_equal(D.prev, prev)
+        d32, p32, _ = O.bfm3d_f32(nn, lv, X, Y, Z, U, 1)
+        D32 = rt.bfm3d(g, 1, U, schedule="near-far", precision=32, canonical_prev=True)
+        assert np.array_equal(D32.dist.astype(np.float64), d32) and np.array_equal(D32.prev, p32)
+    finally:
+        O.set_weight3d(0)
+        g._handle.set_option("weight3d", 0)
+        g._handle.set_option("canonical_prev", 0)
