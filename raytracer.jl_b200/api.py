@@ -437,17 +437,22 @@ def dual_velocity(r, interpolant, buffer=1):
 
 
 # ------------------------------------------------------------------------------------------ closest_point
-def closest_point(gr, px, pz, pw=None, system="cartesian"):
-    """closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 -> 1-based node id (scalar or array).
+def closest_point(gr, px, pz, *rest, system=None):
+    """closest_point(gr, px, pz; system) src/GridAnnulus.jl:823-840 -> 1-based node id (scalar or array); `system`
+    may also be given as the fourth positional argument.
     With a Grid3D: closest_point(gr, x, y, z) of src/StructuredGrid.jl:257-270 (raw axis coordinates)."""
     if isinstance(gr, Grid3D):
-        if pw is None:
+        if len(rest) != 1 or system is not None:
             raise TypeError("closest_point(gr::Grid, x, y, z) needs three coordinates")
+        pw = rest[0]
         a, b, c = np.broadcast_arrays(*(np.atleast_1d(np.asarray(v, np.float64)) for v in (px, pz, pw)))
         a, b, c = (np.ascontiguousarray(v) for v in (a, b, c))
         out = np.zeros(len(a), np.int64)
         check(lib().rt_closest_point3d(gr._handle.h, a, b, c, len(a), out))
         return int(out[0]) if all(np.ndim(v) == 0 for v in (px, pz, pw)) else out
+    if len(rest) > 1 or (rest and system is not None):
+        raise TypeError("closest_point(gr, px, pz; system)")
+    system = rest[0] if rest else (system or "cartesian")
     handle = gr._handle
     if handle is None:
         raise ValueError("grid has no device handle; call mesh_from_arrays(gr, G, halo) or bfm(...) first")
