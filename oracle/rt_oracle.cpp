@@ -1019,12 +1019,30 @@ int ora_bfm_continue(i64 n, i64 nel, const i64* e2n_off, const i64* e2n_idx, con
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
+  // A restart treats the seeds as nodes that have just improved: their travel times first cross their halo rows
+  // (update_halo! with "is a seed" in place of "improved in this sweep", serial row order, allowed targets only; a
+  // node set this way counts as a seed for the rows after it), then the frontier is the allowed part of the star
+  // patches of all of them (update_Q! for the seeds).  Without this a phase that restarts on a discontinuity could
+  // never enter the layer below it: the twins of the boundary nodes only receive values through the halo rule.
+  std::vector<uint8_t> seeded(n, 0);
+  for (i64 k = 0; k < nseeds; ++k) {
+    if (seeds[k] < 1 || seeds[k] > n) return 1;
+    seeded[seeds[k] - 1] = 1;
+  }
+  for (i64 k = 0; k < halo_rows; ++k) {
+    const i64 h1 = halo[k] - 1, h2 = halo[k + halo_rows] - 1;
+    if (!seeded[h1] || (allowed && !allowed[h2])) continue;
+    if (dist[h2] > dist[h1]) {
+      dist[h2] = dist[h1];
+      prev[h2] = prev[h1];
+      seeded[h2] = 1;
+    }
+  }
   std::vector<double> dist0(dist, dist + n);
   std::vector<uint8_t> Q(n, 0);
-  for (i64 k = 0; k < nseeds; ++k) {
-    const i64 s = seeds[k];
-    if (s < 1 || s > n) return 1;
-    for (i64 p = colptr[s - 1]; p < colptr[s]; ++p) {
+  for (i64 s = 0; s < n; ++s) {
+    if (!seeded[s]) continue;
+    for (i64 p = colptr[s]; p < colptr[s + 1]; ++p) {
       const i64 el = rowval[p - 1];
       for (i64 q = e2n_off[el - 1]; q < e2n_off[el]; ++q)
         if (!allowed || allowed[e2n_idx[q] - 1]) Q[e2n_idx[q] - 1] = 1;

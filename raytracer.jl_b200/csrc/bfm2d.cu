@@ -265,10 +265,31 @@ __global__ void init_source_kernel(P2 p, const i32* __restrict__ hnode, const i3
   }
 }
 
-// rt_bfm_continue: the frontier starts as the star patches of the seed nodes (init_Q! for every seed)
-__global__ void seed_touch_kernel(P2 p, const i32* __restrict__ seeds, i64 nseeds) {
+// rt_bfm_continue: a restart treats the seeds as nodes that have just improved.  (1) their travel times cross their halo
+// rows (update_halo! with "is a seed" in place of "improved in this sweep": serial row order, allowed targets only, a node
+// set this way counts as a seed for the rows after it) -- without this a phase that restarts on a discontinuity never
+// enters the layer below, whose twins only receive values through the halo rule; (2) the frontier is the star patch of
+// every seeded node (update_Q! for the seeds).
+__global__ void seed_flag_kernel(const i32* __restrict__ seeds, i64 nseeds, uint8_t* __restrict__ seeded) {
+  const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nseeds) seeded[seeds[k]] = 1;
+}
+__global__ void seed_halo_serial_kernel(P2 p, const i32* __restrict__ h1, const i32* __restrict__ h2, i64 rows,
+                                        uint8_t* __restrict__ seeded) {
+  if (blockIdx.x || threadIdx.x) return;
+  for (i64 k = 0; k < rows; ++k) {
+    const int a = h1[k], b = h2[k];
+    if (!seeded[a] || !node_allowed(p, b)) continue;
+    if (p.dist[b] > p.dist[a]) {
+      p.dist[b] = p.dist[a];
+      p.prev[b] = p.prev[a];
+      seeded[b] = 1;
+    }
+  }
+}
+__global__ void seed_touch_kernel(P2 p, const uint8_t* __restrict__ seeded, i64 n) {
   const i64 k = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (k < nseeds) touch_column(p, seeds[k], threadIdx.x & 31, 32);
+  if (k < n && seeded[k]) touch_column(p, (int)k, threadIdx.x & 31, 32);
 }
 __global__ void prev_from_i64_kernel(const i64* __restrict__ src, i32* __restrict__ dst, i64 n) {
   const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,9 +406,19 @@ int bfm2d_solve_impl(rt_mesh* h, const double* U_dev, bool dual, const i64* sour
     cudaEventRecord(ev0, s);
     cudaMemsetAsync(m.dirty.p, 0, m.nel, s);
     cudaMemsetAsync(m.counters.p, 0, 8 * sizeof(u64), s);
-    if (cont) {  // dist / prev were loaded by the caller; dist0 = copy; frontier = star patches of the seeds
+    if (cont) {  // dist / prev were loaded by the caller; seeds cross their halo rows; dist0 = copy; frontier
+      DevBuf<uint8_t> seeded;
+      if (seeded.alloc(n) != RT_OK) {
+        rc = RT_ERR_CUDA;
+        break;
+      }
+      cudaMemsetAsync(seeded.p, 0, n, s);
+      if (cont->nseeds) seed_flag_kernel<<<grid_for(cont->nseeds, 256), 256, 0, s>>>(cont->seeds_dev, cont->nseeds, seeded.p);
+      if (m.halo_rows > 0)
+        seed_halo_serial_kernel<<<1, 32, 0, s>>>(p, m.halo_h1.p, m.halo_h2.p, m.halo_rows, seeded.p);
       cudaMemcpyAsync(p.dist0, p.dist, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
-      if (cont->nseeds) seed_touch_kernel<<<grid_for(cont->nseeds * 32, 256), 256, 0, s>>>(p, cont->seeds_dev, cont->nseeds);
+      seed_touch_kernel<<<grid_for(n * 32, 256), 256, 0, s>>>(p, seeded.p, n);
+      cudaStreamSynchronize(s);  // `seeded` goes out of scope
     } else {
       init_state_kernel<<<grid_for(n, 256), 256, 0, s>>>(p.dist, p.dist0, p.prev, n);
       init_source_kernel<<<grid_for(std::max<i64>(m.n_hinit, 1), 256), 256, 0, s>>>(p, m.hinit_node.p, m.hinit_val.p,

@@ -322,7 +322,10 @@ __global__ void sn_relax_kernel(SN p, int cur) {
   const int lane = threadIdx.x & 31;
   for (i64 q = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nf; q += ((i64)gridDim.x * blockDim.x) >> 5) {
     const int i = fr[q];
-    if (lane == 0) p.inq[i] = 0u;  // a later improvement of i queues it again
+    if (lane == 0) {
+      atomicExch(&p.inq[i], 0u);  // a later improvement of i queues it again ...
+      __threadfence();            // ... and the flag is down before the travel time is read
+    }
     __syncwarp();
     const double di = __ldcg(&p.dist[i]);
     u64 nrel = 0;

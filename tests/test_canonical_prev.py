@@ -51,14 +51,24 @@ def test_canonical_prev_random_velocity_special_sources_and_batch(rt, O, annulus
     hm = m.halo_matrix()
     H = m.halo_rows // 2
     srcs = [1, m.n, int(hm[0, 0]), int(hm[0, 1]), int(hm[H - 1, 1]), m.n // 2, int(hm[H // 2, 0])]
-    U = 4.0 + 6.0 * splitmix64(20261018, m.n)
-    D = rt.bfm(G, halo, np.array(srcs), gr, U, schedule="near-far", canonical_prev=True)  # one lock-step batch
-    for k, s in enumerate(srcs):
-        dist, prev, _ = O.bfm(m, U, s)
-        assert np.array_equal(D.dist[k], dist), s
-        assert np.array_equal(D.prev[k], prev), s
-        Ds = rt.bfm(G, halo, s, gr, U, schedule="near-far", canonical_prev=True)
-        assert np.array_equal(Ds.prev, prev), s
+    # random velocities: no ties at all; a CONSTANT velocity: dozens of exact ties per node (collinear nodes, duplicated
+    # radial edges: up to 29 distinct bit-exactly tight predecessors on this mesh), final values first reached through
+    # non-final values of a neighbour -- the case in which a breadth-first levelling of the tight edges is wrong
+    for U in (4.0 + 6.0 * splitmix64(20261018, m.n), np.full(m.n, 6.0)):
+        D = rt.bfm(G, halo, np.array(srcs), gr, U, schedule="near-far", canonical_prev=True)  # one lock-step batch
+        for k, s in enumerate(srcs):
+            dist, prev, _ = O.bfm(m, U, s)
+            assert np.array_equal(D.dist[k], dist), s
+            assert np.array_equal(D.prev[k], prev), s
+            Ds = rt.bfm(G, halo, s, gr, U, schedule="near-far", canonical_prev=True)
+            assert np.array_equal(Ds.prev, prev), s
+    m2 = annulus(24, 6, 300.0)
+    gr2, G2, halo2 = adopt(rt, m2)
+    U2 = np.full(m2.n, 8.0)
+    for s in (1, 17, m2.n // 2):
+        dist, prev, _ = O.bfm(m2, U2, s)
+        D2 = rt.bfm(G2, halo2, s, gr2, U2, schedule="near-far", canonical_prev=True)
+        assert np.array_equal(D2.dist, dist) and np.array_equal(D2.prev, prev), s
     rt.bfm(G, halo, 1, gr, U, schedule="jacobi", canonical_prev=False)
 
 
