@@ -441,7 +441,7 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
   } else if (!std::strcmp(key, "warp_units")) {
     m->opts.warp_units = value < 0.0 ? -1 : (value != 0.0);
   } else if (!std::strcmp(key, "batch")) {
-    RT_ARG(value >= 0.0 && value <= 32.0, "batch must be in 0..32");
+    RT_ARG(value >= 0.0 && value <= 1024.0, "batch must be in 0..1024");
     m->opts.batch = (int)value;
   } else if (!std::strcmp(key, "packed_prev")) {
     m->opts.packed_prev = value != 0.0;
