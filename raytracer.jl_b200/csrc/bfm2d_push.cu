@@ -19,6 +19,7 @@
 // zero-weight coupling (twins, coincident duplicates) inherit along that coupling.  This equals the
 // reference's prev except on exact ties (which are systematic on these meshes: every radial edge exists twice).
 #include <cooperative_groups.h>
+#include <cub/device/device_scan.cuh>
 
 #include "mesh2d.cuh"
 
@@ -74,6 +75,11 @@ struct PP {
   // the near-list slots of the sources that push this round, flat[FLAT_STRIDE + (0 .. nb)] = the same for the far-list
   // slots of the sources whose threshold advances.  One launch then serves all sources with perfect load balance.
   i64* flat;
+  // short-column meshes: de-duplicated target list per work item (first occurrences of the column's scan list, scan
+  // order kept): a node shared by several elements of the column is visited once per released item.  tgt_off == null:
+  // not built; an empty list = this item walks its elements (column too long for the builder).
+  const i64* __restrict__ tgt_off;
+  const i32* __restrict__ tgt_idx;
 };
 constexpr int MAX_NB = 1024;          // sources advancing in lock step (one thread each in round_begin)
 constexpr int FLAT_STRIDE = MAX_NB + 1;
@@ -149,6 +155,57 @@ __global__ void wdiag_kernel(PP p, i64 nel, double* __restrict__ sum) {
   }
   for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(FULL, wt, o);
   if ((threadIdx.x & 31) == 0 && wt > 0.0) atomicAdd(sum, wt);
+}
+
+// de-duplicated target lists (see PP::tgt_off): one warp per item gathers the ids of its column into shared memory and
+// keeps the first occurrence of every node; FILL = 0 counts, 1 writes.  Columns above TGT_CAP entries get no list.
+constexpr int TGT_CAP = 2048;
+template <int FILL>
+__global__ void __launch_bounds__(128) item_targets_kernel(PP p, i64* __restrict__ len_or_off, i32* __restrict__ out) {
+  __shared__ int buf[4][TGT_CAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (i64 it = (i64)blockIdx.x * 4 + warp; it < p.n_items; it += (i64)gridDim.x * 4) {
+    const int v0 = p.item_first[it];
+    const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
+    int m = 0;
+    bool fits = true;
+    __syncwarp();
+    for (i64 c = c0; c < c1 && fits; ++c) {
+      const int el = p.g_idx[c];
+      const int s = p.e2n_off[el], len = p.e2n_off[el + 1] - s;
+      if (m + len > TGT_CAP) {
+        fits = false;
+        break;
+      }
+      for (int k = lane; k < len; k += 32) buf[warp][m + k] = p.e2n_idx[s + k];
+      m += len;
+    }
+    __syncwarp();
+    if (!fits) {
+      if (!FILL && lane == 0) len_or_off[it] = 0;
+      continue;
+    }
+    int total = 0;
+    const i64 base = FILL ? len_or_off[it] : 0;
+    for (int k0 = 0; k0 < m; k0 += 32) {
+      const int k = k0 + lane;
+      bool uniq = false;
+      int id = -1;
+      if (k < m) {
+        id = buf[warp][k];
+        uniq = true;
+        for (int q = 0; q < k; ++q)
+          if (buf[warp][q] == id) {
+            uniq = false;
+            break;
+          }
+      }
+      const unsigned ball = __ballot_sync(FULL, uniq);
+      if (FILL && uniq) out[base + total + __popc(ball & ((1u << lane) - 1u))] = id;
+      total += __popc(ball);
+    }
+    if (!FILL && lane == 0) len_or_off[it] = total;
+  }
 }
 
 // flag node j (whose value just improved to d) for propagation: near list if d < tau, else far list
@@ -426,9 +483,9 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
       }
     }
   }
-  const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
   u64 evals = 0;
   unsigned n_scr = 0, n_ex = 0;  // COUNT: candidates that reached the screen / the exact evaluation (this lane)
+  const i64 c0 = p.g_off[v0], c1 = p.g_off[v0 + 1];
   for (i64 cb0 = c0; cb0 < c1; cb0 += 32) {  // element batches of 32 (a column has <= 16 elements, the centre 2T)
     const int ne = (int)min((i64)32, c1 - cb0);
     int s_l = 0, m_l = 0;
@@ -527,6 +584,155 @@ __device__ __forceinline__ void push2d_warp_unit(const PP& p, int it, unsigned m
       atomicAdd(&p.counters[7], (u64)n_ex);
     }
   }
+  if (lane == 0) {
+    atomicAdd(&p.counters[2], evals);
+    atomicAdd(&p.counters[3], (u64)ns);
+  }
+}
+
+// The same unit over the item's DE-DUPLICATED target list (PP::tgt_off): no element offsets, no prefix sums, every
+// node of the patch is visited once; the id of the next round and the gathers that hang on it are in flight while this
+// round's targets are evaluated.
+template <bool PACKED, int MODE>
+__device__ __forceinline__ void push2d_tgt_unit(const PP& p, int it, unsigned mask, i64 t0, i64 t1, int cur, i32* near_next,
+                                                i32* far_list, int fcur, double tau, double2* sxz, double2* sUd,
+                                                double2* sU2r, int* s_id) {
+  constexpr bool DUAL = MODE == MODE_DUAL, F32 = MODE == MODE_F32;
+  constexpr bool COUNT = false;
+  const int lane = threadIdx.x & 31;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const int v0 = p.item_first[it];
+  __syncwarp();
+  const bool on = (mask >> lane) & 1u;
+  const int pos = __popc(mask & ((1u << lane) - 1u));
+  double dmy = INF;
+  if (on) {
+    const int i = v0 + lane;
+    dmy = __ldcg(&p.dist[(i64)i * p.ds]);
+    sxz[pos] = make_double2(p.x[i], p.z[i]);
+    sUd[pos] = make_double2(DUAL ? p.U1[i] : p.U[i], dmy);
+    if (DUAL) sU2r[pos] = make_double2(p.U2[i], p.r[i]);
+    s_id[pos] = i;
+  }
+  double dmin = dmy;
+  for (int o = 16; o; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
+  const int ns = __popc(mask);
+  __syncwarp();
+  if (p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {  // zero-weight halo coupling
+    const int lo = p.hn_index[s_id[lane]];
+    if (lo >= 0) {
+      const double d = sUd[lane].y;
+      for (int q = p.hn_off[lo]; q < p.hn_off[lo + 1]; ++q) {
+        const int b = p.hn_part[q];
+        if (PACKED) {
+          const DP cb = dp_load(p, b);
+          if ((u64)__double_as_longlong(d) < cb.d && dp_update(p, b, cb, d, KEY_HALO | (u64)s_id[lane]))
+            enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+        } else if (d < __ldcg(&p.dist[(i64)b * p.ds]) && relax_to(p, b, d)) {
+          enqueue(p, b, d, tau, near_next, cur ^ 1, far_list, fcur);
+        }
+      }
+    }
+  }
+  u64 evals = 0;
+  unsigned n_scr = 0, n_ex = 0;
+  {
+    // de-duplicated targets of the item, one coalesced id load per 32 targets; the id of the next round and the
+    // gathers that hang on it are issued before this round's targets are evaluated
+    const int len = (int)(t1 - t0);
+    const i32* __restrict__ tg = p.tgt_idx + t0;
+    evals = (u64)len * (u64)ns;
+    int j = lane < len ? tg[lane] : -1;
+    double dj = 0.0, xj = 0.0, zj = 0.0, Uj = 0.0, U2j = 0.0, rj = 0.0;
+    u64 kj = KEY_NONE;
+    if (j >= 0) {
+      if (PACKED) kj = __ldcg(p.keys + 2 * (i64)j + 1);
+      dj = __ldcg(&p.dist[(i64)j * p.ds]);
+      xj = p.x[j];
+      zj = p.z[j];
+      Uj = DUAL ? p.U1[j] : p.U[j];
+      if (DUAL) {
+        U2j = p.U2[j];
+        rj = p.r[j];
+      }
+    }
+    for (int t = lane; t < len; t += 32) {
+      const int tn = t + 32;
+      const int jn = tn < len ? tg[tn] : -1;
+      double djn = 0.0, xjn = 0.0, zjn = 0.0, Ujn = 0.0, U2jn = 0.0, rjn = 0.0;
+      u64 kjn = KEY_NONE;
+      if (jn >= 0) {
+        if (PACKED) kjn = __ldcg(p.keys + 2 * (i64)jn + 1);
+        djn = __ldcg(&p.dist[(i64)jn * p.ds]);
+        xjn = p.x[jn];
+        zjn = p.z[jn];
+        Ujn = DUAL ? p.U1[jn] : p.U[jn];
+        if (DUAL) {
+          U2jn = p.U2[jn];
+          rjn = p.r[jn];
+        }
+      }
+      if (dmin < dj) {
+        double best = dj;
+        u64 bkey = kj;
+        bool changed = false;
+        for (int q = 0; q < ns; ++q) {
+          const double2 ud = sUd[q];
+          const double di = ud.y;
+          if (!(di < best)) continue;
+          if (COUNT) ++n_scr;
+          const double2 xz = sxz[q];
+          double us = ud.x, ut = Uj;
+          if (DUAL) {
+            const double2 u2r = sU2r[q];
+            const bool down = rj > u2r.y;
+            ut = down ? Uj : U2j;
+            us = down ? u2r.x : ud.x;
+          }
+          {
+            const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
+            const double d2 = __fma_rn(dx, dx, dz * dz);
+            if (screen_cannot_improve_t<F32>(best, di, d2, __dadd_rn(ut, us))) continue;
+          }
+          if (COUNT) ++n_ex;
+          const double delta = edge_delta<F32>(di, xz.x, xz.y, us, xj, zj, ut);
+          if (PACKED) {
+            const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
+            if (delta < best) {
+              best = delta;
+              bkey = key;
+              changed = true;
+            } else if (delta == best && !(key & KEY_ZMASK) && key < bkey) {
+              bkey = key;
+              changed = true;
+            }
+          } else {
+            best = delta < best ? delta : best;
+          }
+        }
+        if (PACKED) {
+          if (changed) {
+            DP cur_dp;
+            cur_dp.d = (u64)__double_as_longlong(dj);
+            cur_dp.k = kj;
+            if (dp_update(p, j, cur_dp, best, bkey)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+          }
+        } else if (best < dj && relax_to(p, j, best)) {
+          enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+        }
+      }
+      j = jn;
+      kj = kjn;
+      dj = djn;
+      xj = xjn;
+      zj = zjn;
+      Uj = Ujn;
+      U2j = U2jn;
+      rj = rjn;
+    }
+  }
+  (void)n_scr;
+  (void)n_ex;
   if (lane == 0) {
     atomicAdd(&p.counters[2], evals);
     atomicAdd(&p.counters[3], (u64)ns);
@@ -1103,6 +1309,7 @@ __global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_dc_kernel(PP pb) {
       const int it = __ldcg(&nq(p, cur)[slot]);
       const unsigned mask = __ldcg(&p.cur_mask[slot]);
       if (mask == 0u) continue;
+      if (p.tgt_off && p.tgt_off[it + 1] > p.tgt_off[it]) continue;  // served by push2d_tgt_dc_kernel
       const double tau = __ldcg(&p.tau[0]);
       if (p.ds == 2)
         push2d_warp_unit<true, MODE>(p, it, mask, cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tau, w_sxz[warp], w_sUd[warp],
@@ -1118,51 +1325,16 @@ __global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_dc_kernel(PP pb) {
     push2d_body<WARP, MODE>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
   }
 }
-// threshold advance over the concatenated far lists of the advancing sources: warp per far-list slot
-__global__ void far_min_dc_kernel(PP pb) {
+// warp-level units of ALL sources over the de-duplicated target lists (short-column meshes)
+template <int MODE>
+__global__ void __launch_bounds__(PUSH_BLOCK, 5) push2d_tgt_dc_kernel(PP pb) {
+  constexpr bool DUAL = MODE == MODE_DUAL;
+  __shared__ double2 w_sxz[PUSH_BLOCK / 32][32], w_sUd[PUSH_BLOCK / 32][32], w_sU2r[DUAL ? PUSH_BLOCK / 32 : 1][32];
+  __shared__ int w_id[PUSH_BLOCK / 32][32];
+  const int warp = threadIdx.x >> 5;
   const int nb = pb.nb;
-  const i64* base = pb.flat + FLAT_STRIDE;
+  const i64* base = pb.flat;
   const i64 total = base[nb];
-  const int lane = threadIdx.x & 31;
-  const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
-  // a warp takes a contiguous chunk of slots so that it usually stays inside one source (one atomic per chunk)
-  const i64 chunk = max((i64)1, min((i64)64, (total + nw - 1) / nw));
-  for (i64 g0 = gw * chunk; g0 < total; g0 += nw * chunk) {
-    int b = nb == 1 ? 0 : flat_owner(base, nb, g0);
-    u64 best = ~0ull;
-    const i64 g1 = min(total, g0 + chunk);
-    for (i64 g = g0; g < g1; ++g) {
-      while (g >= base[b + 1]) {  // crossed into the next source: flush
-        for (int o = 16; o; o >>= 1) {
-          const u64 other = __shfl_xor_sync(FULL, best, o);
-          best = other < best ? other : best;
-        }
-        if (lane == 0 && best != ~0ull) atomicMin((u64*)&pb.tau[(i64)b * 4 + 2], best);
-        best = ~0ull;
-        ++b;
-      }
-      const i64 o = (i64)b * pb.n_items;
-      const i32* far_cur = (pb.ctl[b * 8 + 1] ? pb.farq1 : pb.farq0) + o;
-      const int it = far_cur[g - base[b]];
-      const unsigned m = pb.far_mask[o + it];
-      if ((m >> lane) & 1u) {
-        const u64 v = (u64)__double_as_longlong(pb.dist[((i64)b * pb.n + pb.item_first[it] + lane) * pb.ds]);
-        best = v < best ? v : best;
-      }
-    }
-    for (int o = 16; o; o >>= 1) {
-      const u64 other = __shfl_xor_sync(FULL, best, o);
-      best = other < best ? other : best;
-    }
-    if (lane == 0 && best != ~0ull) atomicMin((u64*)&pb.tau[(i64)b * 4 + 2], best);
-  }
-}
-__global__ void far_release_dc_kernel(PP pb) {
-  const int nb = pb.nb;
-  const i64* base = pb.flat + FLAT_STRIDE;
-  const i64 total = base[nb];
-  const int lane = threadIdx.x & 31;
   const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
   for (i64 g = gw; g < total; g += nw) {
@@ -1170,27 +1342,113 @@ __global__ void far_release_dc_kernel(PP pb) {
     const i64 slot = g - base[b];
     const PP p = pp_view(pb, b);
     const int cur = p.ctl[0], fcur = p.ctl[1];
-    const i32* far_cur = fq(p, fcur);
-    i32* far_next = fq(p, fcur ^ 1);
-    i32* near_next = nq(p, cur);
-    const double tau = __dadd_rn(p.tau[2], p.tau[1]);
-    const int it = far_cur[slot];
-    const unsigned m = p.far_mask[it];
-    const bool mine = (m >> lane) & 1u;
-    const bool rel = mine && p.dist[(i64)(p.item_first[it] + lane) * p.ds] < tau;
-    const unsigned relm = __ballot_sync(FULL, rel);
-    if (lane == 0) {
-      const unsigned keep = m & ~relm;
-      p.far_mask[it] = keep;
-      if (keep)
-        far_next[atomicAdd(&p.counters[4 + (fcur ^ 1)], 1ull)] = it;
-      else
-        p.infar[it] = 0u;
-      if (relm) {
-        const unsigned old = atomicOr(&p.pend_mask[it], relm);
-        if (old == 0u) near_next[atomicAdd(&p.counters[cur], 1ull)] = it;
+    const int it = __ldcg(&nq(p, cur)[slot]);
+    const unsigned mask = __ldcg(&p.cur_mask[slot]);
+    if (mask == 0u) continue;
+    const i64 t0 = p.tgt_off[it], t1 = p.tgt_off[it + 1];
+    if (t1 <= t0) continue;  // no list: push2d_dc_kernel walks the elements of this item
+    const double tau = __ldcg(&p.tau[0]);
+    if (p.ds == 2)
+      push2d_tgt_unit<true, MODE>(p, it, mask, t0, t1, cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tau, w_sxz[warp], w_sUd[warp],
+                                  w_sU2r[DUAL ? warp : 0], w_id[warp]);
+    else
+      push2d_tgt_unit<false, MODE>(p, it, mask, t0, t1, cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tau, w_sxz[warp], w_sUd[warp],
+                                   w_sU2r[DUAL ? warp : 0], w_id[warp]);
+  }
+}
+
+// threshold advance over the concatenated far lists of the advancing sources: THREAD per far-list slot (an item of a
+// coarse mesh holds one or two nodes: a warp per slot would idle 30 lanes); warps that lie inside one source -- nearly
+// all of them -- reduce / append once per warp
+__global__ void far_min_dc_kernel(PP pb) {
+  const int nb = pb.nb;
+  const i64* base = pb.flat + FLAT_STRIDE;
+  const i64 total = base[nb];
+  const int lane = threadIdx.x & 31;
+  const i64 gsize = (i64)gridDim.x * blockDim.x;
+  for (i64 g0 = (i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31); g0 < total; g0 += gsize) {  // warp-uniform trip count
+    const i64 g = g0 + lane;
+    const bool valid = g < total;
+    int b = -1;
+    u64 best = ~0ull;
+    if (valid) {
+      b = nb == 1 ? 0 : flat_owner(base, nb, g);
+      const i64 o = (i64)b * pb.n_items;
+      const i32* far_cur = (pb.ctl[b * 8 + 1] ? pb.farq1 : pb.farq0) + o;
+      const int it = far_cur[g - base[b]];
+      unsigned m = pb.far_mask[o + it];
+      const i64 v0 = (i64)b * pb.n + pb.item_first[it];
+      while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1u;
+        const u64 v = (u64)__double_as_longlong(pb.dist[(v0 + k) * pb.ds]);
+        best = v < best ? v : best;
       }
-      if (slot == 0) p.tau[0] = tau;
+    }
+    const int b0 = __shfl_sync(FULL, b, 0);
+    if (__all_sync(FULL, !valid || b == b0)) {
+      for (int o = 16; o; o >>= 1) {
+        const u64 other = __shfl_xor_sync(FULL, best, o);
+        best = other < best ? other : best;
+      }
+      if (lane == 0 && best != ~0ull) atomicMin((u64*)&pb.tau[(i64)b0 * 4 + 2], best);
+    } else if (valid && best != ~0ull) {
+      atomicMin((u64*)&pb.tau[(i64)b * 4 + 2], best);
+    }
+  }
+}
+__global__ void far_release_dc_kernel(PP pb) {
+  const int nb = pb.nb;
+  const i64* base = pb.flat + FLAT_STRIDE;
+  const i64 total = base[nb];
+  const int lane = threadIdx.x & 31;
+  const i64 gsize = (i64)gridDim.x * blockDim.x;
+  for (i64 g0 = (i64)blockIdx.x * blockDim.x + (threadIdx.x & ~31); g0 < total; g0 += gsize) {
+    const i64 g = g0 + lane;
+    const bool valid = g < total;
+    int b = -1, it = 0, cur = 0, fcur = 0;
+    unsigned keep = 0u, relm = 0u;
+    bool first_pend = false;
+    if (valid) {
+      b = nb == 1 ? 0 : flat_owner(base, nb, g);
+      const i64 slot = g - base[b];
+      const i64 o = (i64)b * pb.n_items;
+      cur = pb.ctl[b * 8];
+      fcur = pb.ctl[b * 8 + 1];
+      const double tau = __dadd_rn(pb.tau[(i64)b * 4 + 2], pb.tau[(i64)b * 4 + 1]);
+      it = ((fcur ? pb.farq1 : pb.farq0) + o)[slot];
+      const unsigned m = pb.far_mask[o + it];
+      const i64 v0 = (i64)b * pb.n + pb.item_first[it];
+      unsigned mm = m;
+      while (mm) {
+        const int k = __ffs(mm) - 1;
+        mm &= mm - 1u;
+        if (pb.dist[(v0 + k) * pb.ds] < tau) relm |= 1u << k;
+      }
+      keep = m & ~relm;
+      pb.far_mask[o + it] = keep;
+      if (!keep) pb.infar[o + it] = 0u;
+      if (relm) first_pend = atomicOr(&pb.pend_mask[o + it], relm) == 0u;
+      if (slot == 0) pb.tau[(i64)b * 4] = tau;
+    }
+    const int b0 = __shfl_sync(FULL, b, 0);
+    if (__all_sync(FULL, !valid || b == b0)) {  // one source: one append per list and warp
+      const unsigned kb = __ballot_sync(FULL, valid && keep != 0u), pbm = __ballot_sync(FULL, first_pend);
+      const int cur0 = __shfl_sync(FULL, cur, 0), fcur0 = __shfl_sync(FULL, fcur, 0);
+      u64 base_k = 0, base_p = 0;
+      if (lane == 0 && b0 >= 0) {
+        if (kb) base_k = atomicAdd(&pb.counters[(i64)b0 * 8 + 4 + (fcur0 ^ 1)], (u64)__popc(kb));
+        if (pbm) base_p = atomicAdd(&pb.counters[(i64)b0 * 8 + cur0], (u64)__popc(pbm));
+      }
+      base_k = __shfl_sync(FULL, base_k, 0);
+      base_p = __shfl_sync(FULL, base_p, 0);
+      const i64 o = (i64)max(b0, 0) * pb.n_items;
+      if (valid && keep) ((fcur0 ? pb.farq0 : pb.farq1) + o)[base_k + __popc(kb & ((1u << lane) - 1u))] = it;
+      if (first_pend) ((cur0 ? pb.nearq1 : pb.nearq0) + o)[base_p + __popc(pbm & ((1u << lane) - 1u))] = it;
+    } else if (valid) {
+      const i64 o = (i64)b * pb.n_items;
+      if (keep) ((fcur ? pb.farq0 : pb.farq1) + o)[atomicAdd(&pb.counters[(i64)b * 8 + 4 + (fcur ^ 1)], 1ull)] = it;
+      if (first_pend) ((cur ? pb.nearq1 : pb.nearq0) + o)[atomicAdd(&pb.counters[(i64)b * 8 + cur], 1ull)] = it;
     }
   }
 }
@@ -1522,6 +1780,51 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   p.nb = 1;
   p.warp_units = warp_units;
   p.flat = m.flat.p;
+  p.tgt_off = nullptr;
+  p.tgt_idx = nullptr;
+  if (warp_units && !m.tgt_tried) {  // de-duplicated target lists of the work items, once per mesh
+    m.tgt_tried = true;
+    DevBuf<i64> off;
+    size_t sb = 0;
+    if (off.alloc(m.n_items + 1) == RT_OK) {
+      const unsigned gi = (unsigned)std::min<i64>((m.n_items + 3) / 4, 148 * 32);
+      item_targets_kernel<0><<<gi, 128, 0, s>>>(p, off.p, nullptr);
+      cudaMemsetAsync(off.p + m.n_items, 0, sizeof(i64), s);
+      cub::DeviceScan::ExclusiveSum(nullptr, sb, off.p, off.p, m.n_items + 1, s);
+      DevBuf<uint8_t> tmp;
+      i64 total = -1;
+      if (tmp.alloc(sb) == RT_OK) {
+        cub::DeviceScan::ExclusiveSum(tmp.p, sb, off.p, off.p, m.n_items + 1, s);
+        cudaMemcpyAsync(&total, off.p + m.n_items, sizeof(i64), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+      }
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      m.tgt_missing = true;  // refined below: are there items without a list (column longer than TGT_CAP)?
+      if (total > 0 && (size_t)total * sizeof(i32) < free_b / 8 && m.tgt_idx.alloc((size_t)total) == RT_OK) {
+        item_targets_kernel<1><<<gi, 128, 0, s>>>(p, off.p, m.tgt_idx.p);
+        if (m.tgt_off.alloc(m.n_items + 1) == RT_OK) {
+          cudaMemcpyAsync(m.tgt_off.p, off.p, (m.n_items + 1) * sizeof(i64), cudaMemcpyDeviceToDevice, s);
+          std::vector<i64> hoff(m.n_items + 1);
+          cudaMemcpyAsync(hoff.data(), off.p, (m.n_items + 1) * sizeof(i64), cudaMemcpyDeviceToHost, s);
+          cudaStreamSynchronize(s);
+          m.tgt_missing = false;
+          for (i64 q = 0; q < m.n_items; ++q)
+            if (hoff[q + 1] == hoff[q]) {
+              m.tgt_missing = true;
+              break;
+            }
+        } else {
+          m.tgt_idx.release();
+        }
+      }
+    }
+    RT_CUDA(cudaGetLastError());
+  }
+  if (warp_units && m.tgt_off.p && m.tgt_idx.p && h->opts.target_lists) {
+    p.tgt_off = m.tgt_off.p;
+    p.tgt_idx = m.tgt_idx.p;
+  }
   p.cta_units = h->opts.cta_units;
   p.n = n;
   p.n_items = m.n_items;
@@ -1613,6 +1916,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
       // device-controlled rounds, host sync every `check_every` rounds
       const int R = h->opts.check_every > 1 ? h->opts.check_every : 32;
       const unsigned gsmall = (unsigned)(sm_count * 2);
+      const unsigned gfar = (unsigned)(sm_count * (B > 32 ? 8 : 2));
       // long-column units: one grid row per source; warp-per-item units: one flat grid over all sources
       const dim3 gpush = p.warp_units ? dim3((unsigned)max_blocks, 1) : dim3((unsigned)std::max<i64>(sm_count, max_blocks / B), B);
       bool all_done = false;
@@ -1625,12 +1929,21 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
           else
             round_begin_kernel<MAX_NB><<<1, MAX_NB, 0, s>>>(p, after_far);
           prep_dc_kernel<<<gsmall, 256, 0, s>>>(p);
-          launch_push_dc(p.warp_units != 0, mode, gpush, s, p);
-          st.total_launches += 3;
+          if (p.tgt_off) {
+            if (mode == MODE_DUAL)
+              push2d_tgt_dc_kernel<MODE_DUAL><<<gpush, PUSH_BLOCK, 0, s>>>(p);
+            else if (mode == MODE_F32)
+              push2d_tgt_dc_kernel<MODE_F32><<<gpush, PUSH_BLOCK, 0, s>>>(p);
+            else
+              push2d_tgt_dc_kernel<MODE_F64><<<gpush, PUSH_BLOCK, 0, s>>>(p);
+            st.total_launches += 1;
+          }
+          if (!p.tgt_off || m.tgt_missing) launch_push_dc(p.warp_units != 0, mode, gpush, s, p);
+          st.total_launches += 3 - ((p.tgt_off && !m.tgt_missing) ? 1 : 0);
           after_far = 0;
           if (r % FAR_EVERY == FAR_EVERY - 1 || r == R - 1) {
-            far_min_dc_kernel<<<gsmall, 256, 0, s>>>(p);
-            far_release_dc_kernel<<<gsmall, 256, 0, s>>>(p);
+            far_min_dc_kernel<<<gfar, 256, 0, s>>>(p);
+            far_release_dc_kernel<<<gfar, 256, 0, s>>>(p);
             st.total_launches += 2;
             after_far = 1;
           }

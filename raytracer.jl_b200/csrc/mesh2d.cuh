@@ -64,6 +64,10 @@ struct Mesh2D {
   DevBuf<double> bdist;                // [nb x n]
   DevBuf<i64> flat;                    // flattened near / far slot prefixes of a batch round
   CanonWs* canon = nullptr;
+  DevBuf<i64> tgt_off;                 // de-duplicated target lists of the work items (short-column meshes)
+  DevBuf<i32> tgt_idx;
+  bool tgt_tried = false;
+  bool tgt_missing = true;             // some items have no list (column longer than the builder's cap)
 };
 
 // Finishes a Mesh2D whose primary arrays (x,z,e2n_*,g_*) are already on the device: builds n2e, work items,

@@ -27,8 +27,10 @@ p = torch.empty((nsrc, n), dtype=torch.int32, device="cuda")
 h.set_option("schedule", 1)
 once = os.environ.get("RT_PROBE_ONCE") == "1"
 ref = None
-for batch in ((512,) if once else (32, 128, 512)):
+factors = [float(v) for v in os.environ.get("RT_DELTA_FACTORS", "0").split(",")]
+for batch, fac in ([(512, factors[0])] if once else [(b, f) for f in factors for b in ((32, 128, 512) if len(factors) == 1 else (512,))]):
     h.set_option("batch", batch)
+    h.set_option("delta_factor", fac)
     st = rt.RtStats()
     for rep in range(1 if once else 2):
         torch.cuda.synchronize()
@@ -39,5 +41,5 @@ for batch in ((512,) if once else (32, 128, 512)):
     if ref is None:
         ref = d.clone()
     sd = st.as_dict()
-    print("batch %3d: %.2f ms/source  (%.1f sources/s, rounds %d, launches %d, same dist %s)" %
-          (batch, dt / nsrc * 1e3, nsrc / dt, sd["sweeps"], sd["total_launches"], bool(torch.equal(ref, d))), flush=True)
+    print("delta_factor %g batch %3d: %.2f ms/source  (%.1f sources/s, rounds %d, launches %d, same dist %s)" %
+          (fac, batch, dt / nsrc * 1e3, nsrc / dt, sd["sweeps"], sd["total_launches"], bool(torch.equal(ref, d))), flush=True)
