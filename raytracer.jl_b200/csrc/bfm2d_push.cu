@@ -1780,6 +1780,10 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   p.nb = 1;
   p.warp_units = warp_units;
   p.flat = m.flat.p;
+  p.cta_units = h->opts.cta_units;
+  p.n = n;
+  p.n_items = m.n_items;
+  p.sources = m.bsources.p;
   p.tgt_off = nullptr;
   p.tgt_idx = nullptr;
   if (warp_units && !m.tgt_tried) {  // de-duplicated target lists of the work items, once per mesh
@@ -1825,10 +1829,6 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
     p.tgt_off = m.tgt_off.p;
     p.tgt_idx = m.tgt_idx.p;
   }
-  p.cta_units = h->opts.cta_units;
-  p.n = n;
-  p.n_items = m.n_items;
-  p.sources = m.bsources.p;
 
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
