@@ -31,7 +31,32 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines):
+    """Kernel-variant A/B builds: build_variants/<name>/librt_sssp.so with extra -D flags (load it with RT_SSSP_LIB)."""
+    vdir = os.path.join(ROOT, "build_variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    so = os.path.join(vdir, "librt_sssp.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    objs, procs = [], []
+    for src in sources():
+        obj = os.path.join(vdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([nvcc, "-ccbin", ccbin] + NVCC_FLAGS + list(defines) + ["-c", src, "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode:
+            sys.stderr.write(out.decode())
+            raise RuntimeError("nvcc failed on " + src)
+    subprocess.check_call([nvcc, "-ccbin", ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs +
+                          ["-lcudart", "-ldl"])
+    return so
+
+
 def build(force=False, verbose=False):
+    if os.environ.get("RT_SSSP_LIB"):  # a prebuilt kernel variant is selected: leave the default library alone
+        return os.environ["RT_SSSP_LIB"]
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -80,6 +80,8 @@ struct PP {
   // not built; an empty list = this item walks its elements (column too long for the builder).
   const i64* __restrict__ tgt_off;
   const i32* __restrict__ tgt_idx;
+  i32* flat_b;   // owner source of the first flat_cap global near-list slots of this round (written by prep)
+  i64 flat_cap;
 };
 constexpr int MAX_NB = 1024;          // sources advancing in lock step (one thread each in round_begin)
 constexpr int FLAT_STRIDE = MAX_NB + 1;
@@ -1282,6 +1284,7 @@ __global__ void prep_dc_kernel(PP pb) {
   const i64 total = base[nb];
   for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (i64)gridDim.x * blockDim.x) {
     const int b = flat_owner(base, nb, g);
+    if (g < pb.flat_cap) pb.flat_b[g] = b;
     const i64 slot = g - base[b];
     const i64 o = (i64)b * pb.n_items;
     const i32* near_cur = (pb.ctl[b * 8] ? pb.nearq1 : pb.nearq0) + o;
@@ -1325,12 +1328,27 @@ __global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_dc_kernel(PP pb) {
     push2d_body<WARP, MODE>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
   }
 }
-// warp-level units of ALL sources over the de-duplicated target lists (short-column meshes)
+// rare path of the kernel below, kept out of line so that it does not cost the common path registers
 template <int MODE>
-__global__ void __launch_bounds__(PUSH_BLOCK, 5) push2d_tgt_dc_kernel(PP pb) {
+__device__ __noinline__ void push2d_walk_fallback(const PP& pb, int b, int it, unsigned mask, int cur, int fcur, double tau,
+                                                  double2* sxz, double2* sUd, double2* sU2r, int* s_id, int* s_pre,
+                                                  int* s_start) {
+  const PP p = pp_view(pb, b);
+  if (p.ds == 2)
+    push2d_warp_unit<true, MODE>(p, it, mask, cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tau, sxz, sUd, sU2r, s_id, s_pre, s_start);
+  else
+    push2d_warp_unit<false, MODE>(p, it, mask, cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tau, sxz, sUd, sU2r, s_id, s_pre, s_start);
+}
+
+// warp-level units of ALL sources over the de-duplicated target lists (short-column meshes)
+#ifndef RT_TGT_MINB
+#define RT_TGT_MINB 8
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(PUSH_BLOCK, RT_TGT_MINB) push2d_tgt_dc_kernel(PP pb) {
   constexpr bool DUAL = MODE == MODE_DUAL;
   __shared__ double2 w_sxz[PUSH_BLOCK / 32][32], w_sUd[PUSH_BLOCK / 32][32], w_sU2r[DUAL ? PUSH_BLOCK / 32 : 1][32];
-  __shared__ int w_id[PUSH_BLOCK / 32][32];
+  __shared__ int w_id[PUSH_BLOCK / 32][32], w_pre[PUSH_BLOCK / 32][32], w_start[PUSH_BLOCK / 32][32];
   const int warp = threadIdx.x >> 5;
   const int nb = pb.nb;
   const i64* base = pb.flat;
@@ -1338,7 +1356,7 @@ __global__ void __launch_bounds__(PUSH_BLOCK, 5) push2d_tgt_dc_kernel(PP pb) {
   const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const i64 nw = ((i64)gridDim.x * blockDim.x) >> 5;
   for (i64 g = gw; g < total; g += nw) {
-    const int b = nb == 1 ? 0 : flat_owner(base, nb, g);
+    const int b = nb == 1 ? 0 : (g < pb.flat_cap ? __ldcg(&pb.flat_b[g]) : flat_owner(base, nb, g));
     const i64 slot = g - base[b];
     const PP p = pp_view(pb, b);
     const int cur = p.ctl[0], fcur = p.ctl[1];
@@ -1346,8 +1364,12 @@ __global__ void __launch_bounds__(PUSH_BLOCK, 5) push2d_tgt_dc_kernel(PP pb) {
     const unsigned mask = __ldcg(&p.cur_mask[slot]);
     if (mask == 0u) continue;
     const i64 t0 = p.tgt_off[it], t1 = p.tgt_off[it + 1];
-    if (t1 <= t0) continue;  // no list: push2d_dc_kernel walks the elements of this item
     const double tau = __ldcg(&p.tau[0]);
+    if (t1 <= t0) {  // no list (a column longer than the builder's cap, e.g. the centre node): walk its elements
+      push2d_walk_fallback<MODE>(pb, b, it, mask, cur, fcur, tau, w_sxz[warp], w_sUd[warp], w_sU2r[DUAL ? warp : 0], w_id[warp],
+                                 w_pre[warp], w_start[warp]);
+      continue;
+    }
     if (p.ds == 2)
       push2d_tgt_unit<true, MODE>(p, it, mask, t0, t1, cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tau, w_sxz[warp], w_sUd[warp],
                                   w_sU2r[DUAL ? warp : 0], w_id[warp]);
@@ -1658,6 +1680,10 @@ int ensure_push_workspace(rt_mesh* h, int nb, bool packed, bool need_bdist) {
     m.push_nb = nb;
   }
   if (!m.flat.p) RT_TRY(m.flat.alloc(2 * FLAT_STRIDE));
+  {
+    const size_t want = m.push_nb > 1 ? (size_t)std::min<i64>((i64)m.push_nb * m.n_items, (i64)1 << 27) : 1;
+    if (m.flat_b.n < want) RT_TRY(m.flat_b.alloc(want));
+  }
   if (packed && !m.dp.p) RT_TRY(m.dp.alloc(2 * (size_t)m.n * (size_t)m.push_nb));
   // plain travel-time tables: only the separate-pass mode keeps them here, or a caller that passes no dist buffer
   if ((!packed || need_bdist) && !m.bdist.p) RT_TRY(m.bdist.alloc((size_t)m.push_nb * m.n));
@@ -1780,6 +1806,8 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   p.nb = 1;
   p.warp_units = warp_units;
   p.flat = m.flat.p;
+  p.flat_b = m.flat_b.p;
+  p.flat_cap = (i64)m.flat_b.n;
   p.cta_units = h->opts.cta_units;
   p.n = n;
   p.n_items = m.n_items;
@@ -1864,8 +1892,10 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   // persistent kernel wins while the frontier is small (few grid-wide barriers beat 5 launches per round); large
   // meshes are better served by hardware block scheduling of the batched launches
   const bool small_mesh = (i64)n * nb <= 1500000 || (nb > 1 && n <= 1500000);
+  // (measured on the 591 k-node mesh of BASELINE configs[2]: a persistent round costs ~17 us + 10 us per source, a
+  // launch-sequence round ~36 us + 1.5 us per source: the persistent kernel only wins for one to three sources)
   const bool use_persistent = !timers && coop_blocks > 0 && nb <= 32 &&
-                              (h->opts.persistent == 1 || (h->opts.persistent < 0 && small_mesh));
+                              (h->opts.persistent == 1 || (h->opts.persistent < 0 && small_mesh && nb <= 3));
   std::vector<int> hsrc(nb);
   std::vector<int> hctl((size_t)nb * 8);
   std::vector<u64> hcnt((size_t)nb * 8);
@@ -1929,7 +1959,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
           else
             round_begin_kernel<MAX_NB><<<1, MAX_NB, 0, s>>>(p, after_far);
           prep_dc_kernel<<<gsmall, 256, 0, s>>>(p);
-          if (p.tgt_off) {
+          if (p.tgt_off) {  // (items without a list are walked inside the same kernel, out of line)
             if (mode == MODE_DUAL)
               push2d_tgt_dc_kernel<MODE_DUAL><<<gpush, PUSH_BLOCK, 0, s>>>(p);
             else if (mode == MODE_F32)
@@ -1938,8 +1968,8 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
               push2d_tgt_dc_kernel<MODE_F64><<<gpush, PUSH_BLOCK, 0, s>>>(p);
             st.total_launches += 1;
           }
-          if (!p.tgt_off || m.tgt_missing) launch_push_dc(p.warp_units != 0, mode, gpush, s, p);
-          st.total_launches += 3 - ((p.tgt_off && !m.tgt_missing) ? 1 : 0);
+          if (!p.tgt_off) launch_push_dc(p.warp_units != 0, mode, gpush, s, p);
+          st.total_launches += 2;
           after_far = 0;
           if (r % FAR_EVERY == FAR_EVERY - 1 || r == R - 1) {
             far_min_dc_kernel<<<gfar, 256, 0, s>>>(p);

@@ -63,6 +63,7 @@ struct Mesh2D {
   DevBuf<i32> bprev;                   // [nb x n]
   DevBuf<double> bdist;                // [nb x n]
   DevBuf<i64> flat;                    // flattened near / far slot prefixes of a batch round
+  DevBuf<i32> flat_b;                  // owner source per global near-list slot of a batch round
   CanonWs* canon = nullptr;
   DevBuf<i64> tgt_off;                 // de-duplicated target lists of the work items (short-column meshes)
   DevBuf<i32> tgt_idx;
