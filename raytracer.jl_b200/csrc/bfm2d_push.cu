@@ -68,6 +68,7 @@ struct PP {
   // batch of sources solved in lock step (state arrays hold nb slices; pp_view() selects one)
   int nb;
   int cta_units;   // long columns: 1 = CTA per (item, element group) with block barriers, 0 = warp per (item, element)
+  int group_screen;  // 1: per (item, target) disc bound before the source loop (screen.h: group_cannot_improve_t)
   int warp_units;  // 1: short columns -> warp-per-item push (push2d_warp_body), 0: CTA per (item, element group)
   i64 n, n_items;
   const int* sources;  // [nb] 0-based
@@ -157,6 +158,29 @@ __global__ void wdiag_kernel(PP p, i64 nel, double* __restrict__ sum) {
   }
   for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(FULL, wt, o);
   if ((threadIdx.x & 31) == 0 && wt > 0.0) atomicAdd(sum, wt);
+}
+
+// disc around the released sources of an item and their largest velocity (screen.h: group_cannot_improve_t)
+struct GroupDisc {
+  double cx, cz, rho, umax;
+};
+__device__ __forceinline__ GroupDisc group_disc(bool on, double x, double z, double u) {
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  double xmn = on ? x : INF, xmx = on ? x : -INF, zmn = on ? z : INF, zmx = on ? z : -INF, um = on ? u : 0.0;
+  for (int o = 16; o; o >>= 1) {
+    xmn = fmin(xmn, __shfl_xor_sync(FULL, xmn, o));
+    xmx = fmax(xmx, __shfl_xor_sync(FULL, xmx, o));
+    zmn = fmin(zmn, __shfl_xor_sync(FULL, zmn, o));
+    zmx = fmax(zmx, __shfl_xor_sync(FULL, zmx, o));
+    um = fmax(um, __shfl_xor_sync(FULL, um, o));
+  }
+  GroupDisc g;
+  g.cx = 0.5 * (xmn + xmx);
+  g.cz = 0.5 * (zmn + zmx);
+  const double hx = xmx - xmn, hz = zmx - zmn;
+  g.rho = 0.5 * sqrt(hx * hx + hz * hz) * (1.0 + 1e-12) + 1e-300;
+  g.umax = um;
+  return g;
 }
 
 // de-duplicated target lists (see PP::tgt_off): one warp per item gathers the ids of its column into shared memory and
@@ -607,17 +631,25 @@ __device__ __forceinline__ void push2d_tgt_unit(const PP& p, int it, unsigned ma
   __syncwarp();
   const bool on = (mask >> lane) & 1u;
   const int pos = __popc(mask & ((1u << lane) - 1u));
-  double dmy = INF;
+  double dmy = INF, gx = 0.0, gz = 0.0, gu = 0.0;
   if (on) {
     const int i = v0 + lane;
     dmy = __ldcg(&p.dist[(i64)i * p.ds]);
-    sxz[pos] = make_double2(p.x[i], p.z[i]);
-    sUd[pos] = make_double2(DUAL ? p.U1[i] : p.U[i], dmy);
-    if (DUAL) sU2r[pos] = make_double2(p.U2[i], p.r[i]);
+    gx = p.x[i];
+    gz = p.z[i];
+    gu = DUAL ? p.U1[i] : p.U[i];
+    sxz[pos] = make_double2(gx, gz);
+    sUd[pos] = make_double2(gu, dmy);
+    if (DUAL) {
+      const double u2 = p.U2[i];
+      sU2r[pos] = make_double2(u2, p.r[i]);
+      gu = fmax(gu, u2);
+    }
     s_id[pos] = i;
   }
   double dmin = dmy;
   for (int o = 16; o; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
+  const GroupDisc gd = group_disc(on, gx, gz, gu);
   const int ns = __popc(mask);
   __syncwarp();
   if (p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {  // zero-weight halo coupling
@@ -674,7 +706,13 @@ __device__ __forceinline__ void push2d_tgt_unit(const PP& p, int it, unsigned ma
           rjn = p.r[jn];
         }
       }
-      if (dmin < dj) {
+      bool live = dmin < dj;
+      if (live) {  // no source of the item can reach this target in time: skip the whole source loop
+        const double dxc = __dsub_rn(xj, gd.cx), dzc = __dsub_rn(zj, gd.cz);
+        live = !group_cannot_improve_t<F32>(dj, dmin, __fma_rn(dxc, dxc, dzc * dzc), gd.rho,
+                                            __dadd_rn(DUAL ? fmax(Uj, U2j) : Uj, gd.umax));
+      }
+      if (live) {
         double best = dj;
         u64 bkey = kj;
         bool changed = false;
@@ -792,17 +830,25 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
   __syncwarp();
   const bool on = (mask >> lane) & 1u;
   const int pos = __popc(mask & ((1u << lane) - 1u));
-  double dmy = INF;
+  double dmy = INF, gx = 0.0, gz = 0.0, gu = 0.0;
   if (on) {
     const int i = v0 + lane;
     dmy = __ldcg(&p.dist[(i64)i * p.ds]);
-    sxz[pos] = make_double2(p.x[i], p.z[i]);
-    sUd[pos] = make_double2(DUAL ? p.U1[i] : p.U[i], dmy);
-    if (DUAL) sU2r[pos] = make_double2(p.U2[i], p.r[i]);
+    gx = p.x[i];
+    gz = p.z[i];
+    gu = DUAL ? p.U1[i] : p.U[i];
+    sxz[pos] = make_double2(gx, gz);
+    sUd[pos] = make_double2(gu, dmy);
+    if (DUAL) {
+      const double u2 = p.U2[i];
+      sU2r[pos] = make_double2(u2, p.r[i]);
+      gu = fmax(gu, u2);
+    }
     s_id[pos] = i;
   }
   double dmin = dmy;
   for (int o = 16; o; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
+  const GroupDisc gd = group_disc(on, gx, gz, gu);
   const int ns = __popc(mask);
   __syncwarp();
   if (e0 == 0 && sub == 0 && p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {  // zero-weight halo coupling
@@ -822,7 +868,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
     }
   }
   u64 evals = 0;
-  unsigned n_scr = 0, n_ex = 0;  // COUNT: candidates that reached the screen / the exact evaluation (this lane)
+  unsigned n_scr = 0, n_ex = 0, n_grp = 0;  // COUNT: candidates at the screen / exact evaluation; targets cut by the group screen
   for (i64 c = c0 + e0; c < c1; c += PUSH_GE) {
     const int el = p.g_idx[c];
     const int s = p.e2n_off[el];
@@ -861,7 +907,14 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
           rjn = p.r[jn];
         }
       }
-      if (dmin < dj) {
+      bool live = dmin < dj;
+      if (live && p.group_screen) {  // no source of the item can reach this target in time: skip the whole source loop
+        const double dxc = __dsub_rn(xj, gd.cx), dzc = __dsub_rn(zj, gd.cz);
+        live = !group_cannot_improve_t<F32>(dj, dmin, __fma_rn(dxc, dxc, dzc * dzc), gd.rho,
+                                            __dadd_rn(DUAL ? fmax(Uj, U2j) : Uj, gd.umax));
+        if (COUNT && !live) ++n_grp;
+      }
+      if (live) {
         double best = dj;
         u64 bkey = kj;
         bool changed = false;
@@ -1291,8 +1344,11 @@ __global__ void prep_dc_kernel(PP pb) {
     pb.cur_mask[o + slot] = atomicExch(&pb.pend_mask[o + near_cur[slot]], 0u);
   }
 }
+#ifndef RT_PUSH_MINB
+#define RT_PUSH_MINB 6
+#endif
 template <bool WARP, int MODE>
-__global__ void __launch_bounds__(PUSH_BLOCK, 6) push2d_dc_kernel(PP pb) {
+__global__ void __launch_bounds__(PUSH_BLOCK, RT_PUSH_MINB) push2d_dc_kernel(PP pb) {
   if (WARP) {
     // warp-level units of ALL sources in one flat index space (slot g of the concatenated near lists)
     constexpr bool DUAL = MODE == MODE_DUAL;
@@ -1809,6 +1865,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   p.flat_b = m.flat_b.p;
   p.flat_cap = (i64)m.flat_b.n;
   p.cta_units = h->opts.cta_units;
+  p.group_screen = h->opts.group_screen;
   p.n = n;
   p.n_items = m.n_items;
   p.sources = m.bsources.p;

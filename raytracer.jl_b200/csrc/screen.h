@@ -38,6 +38,19 @@ RT_HD bool screen_cannot_improve(double bound, double d_from, double d2, double 
   return screen_cannot_improve_t<false>(bound, d_from, d2, ssum);
 }
 
+// Group screen: can ANY source of a released group improve a target t whose incumbent is `bound`?  The group's sources
+// lie in the disc (centre c, radius rho), their travel times are >= dmin (callers guarantee dmin < bound) and their
+// velocities <= umax, so for every source s:  d_s + w(s, t) >= dmin + 2 (|t - c| - rho) / (u_t + umax).  That lower bound
+// is run through the same inequality as screen_cannot_improve_t, without the square root:
+//   |t - c| >= rho + (bound - dmin + slack) (u_t + umax) / 2   =>   no source can improve t.
+// d2c = |t - c|^2, ssum = u_t + umax (dual velocity: the larger of the two values on both sides).  `true` is exact-safe.
+template <bool F32>
+RT_HD bool group_cannot_improve_t(double bound, double dmin, double d2c, double rho, double ssum) {
+  const double tt = rt_fma(bound, F32 ? 1.3e-7 : 4e-15, bound - dmin);
+  const double rhs = rt_fma(tt * ssum, F32 ? 0.5 * (1.0 + 1e-6) : 0.5 * (1.0 + 1e-9), rho);
+  return (d2c > rhs * rhs * (1.0 + 1e-12)) && (ssum > 0.0);
+}
+
 // Can fl(d_from + w) == target hold?  false => certainly not tight.
 template <bool F32>
 RT_HD bool screen_maybe_tight_t(double target, double d_from, double d2, double ssum) {

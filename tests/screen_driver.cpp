@@ -76,4 +76,36 @@ void screen3d_batch(long n, int f32, const double* bound, const double* dj, cons
     }
   }
 }
+
+// group screen (screen.h: group_cannot_improve_t): ng groups of ns sources each, one target per group.  Outputs the
+// screen's answer and the smallest exact candidate over the group's sources (kernel arithmetic).
+void group2d_batch(long ng, int ns, int f32, const double* bound, const double* ds, const double* xs, const double* zs,
+                   const double* Us, const double* xt, const double* zt, const double* Ut, unsigned char* skip,
+                   double* best_exact) {
+  for (long g = 0; g < ng; ++g) {
+    double dmin = INFINITY, xmin = INFINITY, xmax = -INFINITY, zmin = INFINITY, zmax = -INFINITY, umax = 0.0;
+    double be = INFINITY;
+    for (int k = 0; k < ns; ++k) {
+      const long q = g * ns + k;
+      dmin = std::fmin(dmin, ds[q]);
+      xmin = std::fmin(xmin, xs[q]);
+      xmax = std::fmax(xmax, xs[q]);
+      zmin = std::fmin(zmin, zs[q]);
+      zmax = std::fmax(zmax, zs[q]);
+      umax = std::fmax(umax, Us[q]);
+      const double e = f32 ? exact_cand2<true>(ds[q], xs[q], zs[q], Us[q], xt[g], zt[g], Ut[g])
+                           : exact_cand2<false>(ds[q], xs[q], zs[q], Us[q], xt[g], zt[g], Ut[g]);
+      be = std::fmin(be, e);
+    }
+    // exactly what the kernels compute per released item
+    const double cx = 0.5 * (xmin + xmax), cz = 0.5 * (zmin + zmax);
+    const double hx = xmax - xmin, hz = zmax - zmin;
+    const double rho = 0.5 * std::sqrt(hx * hx + hz * hz) * (1.0 + 1e-12) + 1e-300;
+    const double dx = xt[g] - cx, dz = zt[g] - cz;
+    const double d2c = rt_fma(dx, dx, dz * dz);
+    skip[g] = dmin < bound[g] && (f32 ? group_cannot_improve_t<true>(bound[g], dmin, d2c, rho, Ut[g] + umax)
+                                      : group_cannot_improve_t<false>(bound[g], dmin, d2c, rho, Ut[g] + umax));
+    best_exact[g] = be;
+  }
+}
 }

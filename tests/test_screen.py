@@ -27,6 +27,7 @@ def drv():
     L = C.CDLL(so)
     L.screen2d_batch.argtypes = [C.c_long, C.c_int] + [F64P] * 9 + [U8P, U8P, F64P, F64P]
     L.screen3d_batch.argtypes = [C.c_long, C.c_int] + [F64P] * 11 + [U8P, U8P, F64P, F64P]
+    L.group2d_batch.argtypes = [C.c_long, C.c_int, C.c_int] + [F64P] * 8 + [U8P, F64P]
     return L
 
 
@@ -106,3 +107,50 @@ def test_screen_is_exact_safe(drv, dim, f32):
             far = ok & (d0 - dj > (1e-3 if f32 else 1e-6) * np.maximum(d0, 1.0))
             assert (tight[far] == 0).mean() > 0.999
     assert checked > n and skipped > 0
+
+
+@pytest.mark.parametrize("f32", [0, 1])
+def test_group_screen_is_exact_safe(drv, f32):
+    """group_cannot_improve_t (one test per released item and target in the push kernels): whenever it says "no source
+    of this group can improve the target", the smallest EXACT candidate over the group's sources is >= the incumbent.
+    Groups: up to 32 collinear-ish sources within a few km (nodes of one mesh edge); incumbents placed within a few ulp
+    of the best candidate, and exactly on the disc bound."""
+    rng = np.random.default_rng(20261018 + f32)
+    r = (lambda a: a.astype(np.float32).astype(np.float64)) if f32 else (lambda a: a)
+    ng, ns = 40000, 24
+    base = rng.uniform(-6371.0, 6371.0, (2, ng))
+    span = 10.0 ** rng.uniform(-2.0, 1.3, ng)                      # group extent 0.01 .. 20 km
+    dirv = rng.normal(size=(2, ng))
+    dirv /= np.linalg.norm(dirv, axis=0)
+    tpar = rng.uniform(-0.5, 0.5, (ns, ng))
+    xs = r((base[0] + dirv[0] * span * tpar + rng.normal(size=(ns, ng)) * span * 0.02).T.copy())
+    zs = r((base[1] + dirv[1] * span * tpar + rng.normal(size=(ns, ng)) * span * 0.02).T.copy())
+    Us = r(rng.uniform(1.0, 14.0, (ng, ns)))
+    d0 = rng.uniform(0.0, 2500.0, ng)
+    ds = r(d0[:, None] + rng.uniform(0.0, 3.0, (ng, ns)) * rng.random((ng, 1)))
+    dist_t = 10.0 ** rng.uniform(-2.0, 2.5, ng)
+    ang = rng.uniform(0, 2 * np.pi, ng)
+    xt, zt = r(base[0] + dist_t * np.cos(ang)), r(base[1] + dist_t * np.sin(ang))
+    Ut = r(rng.uniform(1.0, 14.0, ng))
+    skip = np.zeros(ng, np.uint8)
+    best = np.zeros(ng)
+    # pass 1: the best exact candidate of every group
+    drv.group2d_batch(ng, ns, f32, np.full(ng, 1e300), ds.reshape(-1), xs.reshape(-1), zs.reshape(-1), Us.reshape(-1), xt,
+                      zt, Ut, skip, best)
+    # pass 2: incumbents around that value (a few ulp either side, and generously above / below)
+    eps = 2.0 ** -23 if f32 else 2.0 ** -52
+    k = rng.integers(-4, 5, ng)
+    dmin0 = ds.min(axis=1)
+    sel = rng.random(ng)
+    bound = np.where(sel < 0.4, best * (1.0 + k * eps),
+                     np.where(sel < 0.7, best * rng.uniform(0.7, 1.3, ng), dmin0 + rng.random(ng) * (best - dmin0)))
+    bound = r(np.maximum(bound, 0.0))
+    drv.group2d_batch(ng, ns, f32, bound, ds.reshape(-1), xs.reshape(-1), zs.reshape(-1), Us.reshape(-1), xt, zt, Ut, skip,
+                      best)
+    wrong = (skip == 1) & (best < bound)
+    assert not wrong.any(), "the group screen hid an improvement"
+    # it is not vacuous: among the targets it is meant for (incumbent above the group's smallest travel time but below
+    # the best candidate by a margin) a good part is pruned without looking at a single source
+    dmin = ds.min(axis=1)
+    meant = (bound > dmin) & (bound < best * (1.0 - 1e-3))
+    assert meant.sum() > 1000 and skip[meant].mean() > 0.3

@@ -31,6 +31,7 @@ for (nt, nr, sp) in meshes:
     h.set_option("persistent", int(os.environ.get("RT_PERSISTENT", "-1")))
     h.set_option("cta_units", int(os.environ.get("RT_CTA_UNITS", "0")))
     h.set_option("check_every", int(os.environ.get("RT_CHECK_EVERY", "0")))
+    h.set_option("group_screen", int(os.environ.get("RT_GROUP_SCREEN", "1")))
     d = torch.empty(n, dtype=torch.float64, device="cuda")
     p = torch.empty(n, dtype=torch.int32, device="cuda")
     ref = None
@@ -52,6 +53,6 @@ for (nt, nr, sp) in meshes:
             ref = d.clone()
         print(json.dumps(dict(cfg=(nt, nr, sp), n=n, build_s=round(tb, 2), sched=sched, dfac=df, solve_s=round(ts, 4),
                               rounds=sd["sweeps"], relaxed=sd["relaxed_edges"], ratio=round(sd["relaxed_edges"] / sd["graph_edges"], 2),
-                              kernel_ms=round(sd["kernel_ms"], 1), relax_ms=round(sd["relax_ms"], 1), prev_ms=round(sd["prev_ms"], 1), launches=sd["total_launches"],
+                              screened=sd["screened_edges"], exact=sd["exact_edges"], kernel_ms=round(sd["kernel_ms"], 1), relax_ms=round(sd["relax_ms"], 1), prev_ms=round(sd["prev_ms"], 1), launches=sd["total_launches"],
                               teps_graph_G=round(sd["graph_edges"] / ts / 1e9, 2), same_dist=bool(torch.equal(ref, d)))), flush=True)
     del gr, G, h
