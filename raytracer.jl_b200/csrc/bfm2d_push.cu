@@ -68,6 +68,7 @@ struct PP {
   // batch of sources solved in lock step (state arrays hold nb slices; pp_view() selects one)
   int nb;
   int cta_units;   // long columns: 1 = CTA per (item, element group) with block barriers, 0 = warp per (item, element)
+  int compact;       // 1: long-column units park the targets that survive the group screen and evaluate full warps
   int group_screen;  // 1: per (item, target) disc bound before the source loop (screen.h: group_cannot_improve_t)
   int warp_units;  // 1: short columns -> warp-per-item push (push2d_warp_body), 0: CTA per (item, element group)
   i64 n, n_items;
@@ -802,6 +803,72 @@ __device__ __forceinline__ void push2d_warp_body(const PP& p, const i32* near_cu
   }
 }
 
+// One target against all released sources of an item (sources in the warp-private shared-memory slab).
+template <bool PACKED, int MODE, bool COUNT>
+__device__ __forceinline__ void push2d_eval_target(const PP& p, int ns, const double2* sxz, const double2* sUd,
+                                                   const double2* sU2r, const int* s_id, int j, double dj, u64 kj, double xj,
+                                                   double zj, double Uj, double U2j, double rj, double tau, i32* near_next,
+                                                   int cur, i32* far_list, int fcur, unsigned& n_scr, unsigned& n_ex) {
+  constexpr bool DUAL = MODE == MODE_DUAL, F32 = MODE == MODE_F32;
+  double best = dj;
+  u64 bkey = kj;
+  bool changed = false;
+  for (int q = 0; q < ns; ++q) {
+    const double2 ud = sUd[q];
+    const double di = ud.y;
+    if (!(di < best)) continue;
+    if (COUNT) ++n_scr;
+    const double2 xz = sxz[q];
+    double us = ud.x, ut = Uj;  // velocities of the source (head) and of the target (tail)
+    if (DUAL) {
+      const double2 u2r = sU2r[q];
+      const bool down = rj > u2r.y;  // head_idx = (r_i > r_Gi) + 1 with i = target, Gi = source
+      ut = down ? Uj : U2j;
+      us = down ? u2r.x : ud.x;
+    }
+    {
+      const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
+      const double d2 = __fma_rn(dx, dx, dz * dz);
+      if (screen_cannot_improve_t<F32>(best, di, d2, __dadd_rn(ut, us))) continue;
+    }
+    if (COUNT) ++n_ex;
+    const double delta = edge_delta<F32>(di, xz.x, xz.y, us, xj, zj, ut);
+    if (PACKED) {
+      const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
+      if (delta < best) {
+        best = delta;
+        bkey = key;
+        changed = true;
+      } else if (delta == best && !(key & KEY_ZMASK) && key < bkey) {
+        bkey = key;
+        changed = true;
+      }
+    } else {
+      best = delta < best ? delta : best;
+    }
+  }
+  if (PACKED) {
+    if (changed) {
+      DP cur_dp;
+      cur_dp.d = (u64)__double_as_longlong(dj);
+      cur_dp.k = kj;
+      if (dp_update(p, j, cur_dp, best, bkey)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+    }
+  } else if (best < dj && relax_to(p, j, best)) {
+    enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
+  }
+}
+
+// Warp-private buffer in which the lanes park the targets that survive the group screen; the source loop only runs on
+// full warps of survivors (lanes whose target was screened out would otherwise idle through the whole loop).
+struct LiveBuf {
+  double2 a[64];  // (dist, x) of the target
+  double2 b[64];  // (z, U)
+  double2 c[64];  // dual velocity: (U2, r)
+  u64 k[64];      // predecessor key
+  int j[64];
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // Barrier-free push for long columns: warp-level unit = (released item, element lane e): the warp keeps its own copy
 // of the released sources (warp-private smem slab) and walks the elements e, e + PUSH_GE, ... of the column with the
@@ -820,7 +887,7 @@ template <bool PACKED, int MODE, bool COUNT = false>
 __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned mask, int e0, int sub, int kst, int cur,
                                                  i32* near_next,
                                                  i32* far_list, int fcur, double tau, double2* sxz, double2* sUd, double2* sU2r,
-                                                 int* s_id) {
+                                                 int* s_id, LiveBuf* lb) {
   constexpr bool DUAL = MODE == MODE_DUAL, F32 = MODE == MODE_F32;
   const int lane = threadIdx.x & 31;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -869,6 +936,8 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
   }
   u64 evals = 0;
   unsigned n_scr = 0, n_ex = 0, n_grp = 0;  // COUNT: candidates at the screen / exact evaluation; targets cut by the group screen
+  const bool compact = p.compact != 0;
+  int nlive = 0;  // survivors parked in the warp's buffer (warp-uniform)
   for (i64 c = c0 + e0; c < c1; c += PUSH_GE) {
     const int el = p.g_idx[c];
     const int s = p.e2n_off[el];
@@ -892,7 +961,7 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
         rj = p.r[j];
       }
     }
-    while (k < m) {
+    while (k - lane < m) {  // warp-uniform trip count (the survivors are exchanged with warp-wide primitives)
       const int kn = k + kst;
       const int jnn = kn + kst < m ? p.e2n_idx[s + kn + kst] : -1;
       double djn = 0.0, xjn = 0.0, zjn = 0.0, Ujn = 0.0, U2jn = 0.0, rjn = 0.0;
@@ -907,61 +976,41 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
           rjn = p.r[jn];
         }
       }
-      bool live = dmin < dj;
+      bool live = j >= 0 && dmin < dj;
       if (live && p.group_screen) {  // no source of the item can reach this target in time: skip the whole source loop
         const double dxc = __dsub_rn(xj, gd.cx), dzc = __dsub_rn(zj, gd.cz);
         live = !group_cannot_improve_t<F32>(dj, dmin, __fma_rn(dxc, dxc, dzc * dzc), gd.rho,
                                             __dadd_rn(DUAL ? fmax(Uj, U2j) : Uj, gd.umax));
         if (COUNT && !live) ++n_grp;
       }
-      if (live) {
-        double best = dj;
-        u64 bkey = kj;
-        bool changed = false;
-        for (int q = 0; q < ns; ++q) {
-          const double2 ud = sUd[q];
-          const double di = ud.y;
-          if (!(di < best)) continue;
-          if (COUNT) ++n_scr;
-          const double2 xz = sxz[q];
-          double us = ud.x, ut = Uj;  // velocities of the source (head) and of the target (tail)
-          if (DUAL) {
-            const double2 u2r = sU2r[q];
-            const bool down = rj > u2r.y;  // head_idx = (r_i > r_Gi) + 1 with i = target, Gi = source
-            ut = down ? Uj : U2j;
-            us = down ? u2r.x : ud.x;
+      if (compact) {
+        const unsigned ball = __ballot_sync(FULL, live);
+        if (ball) {
+          if (live) {
+            const int w = nlive + __popc(ball & ((1u << lane) - 1u));
+            lb->a[w] = make_double2(dj, xj);
+            lb->b[w] = make_double2(zj, Uj);
+            if (DUAL) lb->c[w] = make_double2(U2j, rj);
+            lb->k[w] = kj;
+            lb->j[w] = j;
           }
-          {
-            const double dx = __dsub_rn(xz.x, xj), dz = __dsub_rn(xz.y, zj);
-            const double d2 = __fma_rn(dx, dx, dz * dz);
-            if (screen_cannot_improve_t<F32>(best, di, d2, __dadd_rn(ut, us))) continue;
-          }
-          if (COUNT) ++n_ex;
-          const double delta = edge_delta<F32>(di, xz.x, xz.y, us, xj, zj, ut);
-          if (PACKED) {
-            const u64 key = (delta == di ? KEY_ZW : 0ull) | (u64)s_id[q];
-            if (delta < best) {
-              best = delta;
-              bkey = key;
-              changed = true;
-            } else if (delta == best && !(key & KEY_ZMASK) && key < bkey) {
-              bkey = key;
-              changed = true;
-            }
-          } else {
-            best = delta < best ? delta : best;
+          nlive += __popc(ball);
+          __syncwarp();
+          if (nlive >= 32) {  // a full warp of survivors: evaluate the last 32
+            const int w = nlive - 32 + lane;
+            const double2 ta = lb->a[w], tb = lb->b[w];
+            const double2 tc = DUAL ? lb->c[w] : make_double2(0.0, 0.0);
+            const u64 tk = lb->k[w];
+            const int tj = lb->j[w];
+            __syncwarp();
+            nlive -= 32;
+            push2d_eval_target<PACKED, MODE, COUNT>(p, ns, sxz, sUd, sU2r, s_id, tj, ta.x, tk, ta.y, tb.x, tb.y, tc.x, tc.y, tau,
+                                                    near_next, cur, far_list, fcur, n_scr, n_ex);
           }
         }
-        if (PACKED) {
-          if (changed) {
-            DP cur_dp;
-            cur_dp.d = (u64)__double_as_longlong(dj);
-            cur_dp.k = kj;
-            if (dp_update(p, j, cur_dp, best, bkey)) enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
-          }
-        } else if (best < dj && relax_to(p, j, best)) {
-          enqueue(p, j, best, tau, near_next, cur ^ 1, far_list, fcur);
-        }
+      } else if (live) {
+        push2d_eval_target<PACKED, MODE, COUNT>(p, ns, sxz, sUd, sU2r, s_id, j, dj, kj, xj, zj, Uj, U2j, rj, tau, near_next, cur,
+                                                far_list, fcur, n_scr, n_ex);
       }
       k = kn;
       j = jn;
@@ -975,6 +1024,15 @@ __device__ __forceinline__ void push2d_elem_unit(const PP& p, int it, unsigned m
       rj = rjn;
     }
     if (sub == 0) evals += (u64)m * (u64)ns;
+  }
+  if (nlive > 0) {  // the last, partial warp of survivors
+    if (lane < nlive) {
+      const double2 ta = lb->a[lane], tb = lb->b[lane];
+      const double2 tc = DUAL ? lb->c[lane] : make_double2(0.0, 0.0);
+      push2d_eval_target<PACKED, MODE, COUNT>(p, ns, sxz, sUd, sU2r, s_id, lb->j[lane], ta.x, lb->k[lane], ta.y, tb.x, tb.y, tc.x,
+                                              tc.y, tau, near_next, cur, far_list, fcur, n_scr, n_ex);
+    }
+    __syncwarp();
   }
   if (COUNT) {
     for (int o = 16; o; o >>= 1) {
@@ -997,6 +1055,7 @@ __device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cu
   constexpr bool DUAL = MODE == MODE_DUAL;
   __shared__ double2 e_sxz[PUSH_BLOCK / 32][32], e_sUd[PUSH_BLOCK / 32][32], e_sU2r[DUAL ? PUSH_BLOCK / 32 : 1][32];
   __shared__ int e_id[PUSH_BLOCK / 32][32];
+  __shared__ LiveBuf e_lb[PUSH_BLOCK / 32];
   const int warp = threadIdx.x >> 5;
   const i64 n_near = (i64)__ldcg(&p.counters[cur]);
   const double tau = __ldcg(&p.tau[0]);
@@ -1015,10 +1074,10 @@ __device__ __forceinline__ void push2d_elem_body(const PP& p, const i32* near_cu
     if (mask == 0u) continue;
     if (p.ds == 2)
       push2d_elem_unit<true, MODE, COUNT>(p, it, mask, e0, sub, kst, cur, near_next, far_list, fcur, tau, e_sxz[warp],
-                                          e_sUd[warp], e_sU2r[DUAL ? warp : 0], e_id[warp]);
+                                          e_sUd[warp], e_sU2r[DUAL ? warp : 0], e_id[warp], &e_lb[warp]);
     else
       push2d_elem_unit<false, MODE, COUNT>(p, it, mask, e0, sub, kst, cur, near_next, far_list, fcur, tau, e_sxz[warp],
-                                           e_sUd[warp], e_sU2r[DUAL ? warp : 0], e_id[warp]);
+                                           e_sUd[warp], e_sU2r[DUAL ? warp : 0], e_id[warp], &e_lb[warp]);
   }
 }
 
@@ -1866,6 +1925,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   p.flat_cap = (i64)m.flat_b.n;
   p.cta_units = h->opts.cta_units;
   p.group_screen = h->opts.group_screen;
+  p.compact = h->opts.compact;
   p.n = n;
   p.n_items = m.n_items;
   p.sources = m.bsources.p;
