@@ -450,6 +450,8 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
   } else if (!std::strcmp(key, "weight3d")) {
     RT_ARG(value == 0.0 || value == 1.0, "weight3d must be 0 (weights.jl:20) or 1 (Dijsktra.jl:388)");
     m->opts.weight3d = (int)value;
+  } else if (!std::strcmp(key, "use_graph")) {
+    m->opts.use_graph = value != 0.0;
   } else if (!std::strcmp(key, "compact")) {
     m->opts.compact = value != 0.0;
   } else if (!std::strcmp(key, "group_screen")) {

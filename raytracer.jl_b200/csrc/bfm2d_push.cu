@@ -19,6 +19,8 @@
 // zero-weight coupling (twins, coincident duplicates) inherit along that coupling.  This equals the
 // reference's prev except on exact ties (which are systematic on these meshes: every radial edge exists twice).
 #include <cooperative_groups.h>
+
+#include <cstring>
 #include <cub/device/device_scan.cuh>
 
 #include "mesh2d.cuh"
@@ -632,25 +634,17 @@ __device__ __forceinline__ void push2d_tgt_unit(const PP& p, int it, unsigned ma
   __syncwarp();
   const bool on = (mask >> lane) & 1u;
   const int pos = __popc(mask & ((1u << lane) - 1u));
-  double dmy = INF, gx = 0.0, gz = 0.0, gu = 0.0;
+  double dmy = INF;
   if (on) {
     const int i = v0 + lane;
     dmy = __ldcg(&p.dist[(i64)i * p.ds]);
-    gx = p.x[i];
-    gz = p.z[i];
-    gu = DUAL ? p.U1[i] : p.U[i];
-    sxz[pos] = make_double2(gx, gz);
-    sUd[pos] = make_double2(gu, dmy);
-    if (DUAL) {
-      const double u2 = p.U2[i];
-      sU2r[pos] = make_double2(u2, p.r[i]);
-      gu = fmax(gu, u2);
-    }
+    sxz[pos] = make_double2(p.x[i], p.z[i]);
+    sUd[pos] = make_double2(DUAL ? p.U1[i] : p.U[i], dmy);
+    if (DUAL) sU2r[pos] = make_double2(p.U2[i], p.r[i]);
     s_id[pos] = i;
   }
   double dmin = dmy;
   for (int o = 16; o; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
-  const GroupDisc gd = group_disc(on, gx, gz, gu);
   const int ns = __popc(mask);
   __syncwarp();
   if (p.n_hn > 0 && lane < ns && s_id[lane] != p.source) {  // zero-weight halo coupling
@@ -707,13 +701,7 @@ __device__ __forceinline__ void push2d_tgt_unit(const PP& p, int it, unsigned ma
           rjn = p.r[jn];
         }
       }
-      bool live = dmin < dj;
-      if (live) {  // no source of the item can reach this target in time: skip the whole source loop
-        const double dxc = __dsub_rn(xj, gd.cx), dzc = __dsub_rn(zj, gd.cz);
-        live = !group_cannot_improve_t<F32>(dj, dmin, __fma_rn(dxc, dxc, dzc * dzc), gd.rho,
-                                            __dadd_rn(DUAL ? fmax(Uj, U2j) : Uj, gd.umax));
-      }
-      if (live) {
+      if (dmin < dj) {  // (items of a coarse mesh release one or two sources: no group screen here)
         double best = dj;
         u64 bkey = kj;
         bool changed = false;
@@ -1885,6 +1873,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   RT_TRY(ensure_push_workspace(h, nb, packed, dist_dev == nullptr));
   nb = std::min(nb, m.push_nb);
   PP p;
+  std::memset((void*)&p, 0, sizeof(p));  // (the struct is also the cache key of the captured round graph: no stray padding)
   p.x = f32 ? m.xf.p : m.x.p;
   p.z = f32 ? m.zf.p : m.z.p;
   p.U = U_dev;
@@ -2067,34 +2056,78 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
       // long-column units: one grid row per source; warp-per-item units: one flat grid over all sources
       const dim3 gpush = p.warp_units ? dim3((unsigned)max_blocks, 1) : dim3((unsigned)std::max<i64>(sm_count, max_blocks / B), B);
       bool all_done = false;
-      int after_far = 1;  // nothing is pending before the first round
       i64 enq_rounds = 0;
-      while (!all_done) {
+      // the R-round launch sequence is the same every time (which phase runs is decided on the device): it is captured
+      // once into a CUDA graph and replayed, which removes the per-launch host cost and most of the inter-kernel gaps
+      i64 seq_launches = 0;
+      auto enqueue_rounds = [&](cudaStream_t q) {
+        int af = 1;  // nothing is pending before the first round; the last round of a sequence always runs the far kernels
+        seq_launches = 0;
         for (int r = 0; r < R; ++r) {
           if (B <= 32)
-            round_begin_kernel<32><<<1, 32, 0, s>>>(p, after_far);
+            round_begin_kernel<32><<<1, 32, 0, q>>>(p, af);
           else
-            round_begin_kernel<MAX_NB><<<1, MAX_NB, 0, s>>>(p, after_far);
-          prep_dc_kernel<<<gsmall, 256, 0, s>>>(p);
+            round_begin_kernel<MAX_NB><<<1, MAX_NB, 0, q>>>(p, af);
+          prep_dc_kernel<<<gsmall, 256, 0, q>>>(p);
           if (p.tgt_off) {  // (items without a list are walked inside the same kernel, out of line)
             if (mode == MODE_DUAL)
-              push2d_tgt_dc_kernel<MODE_DUAL><<<gpush, PUSH_BLOCK, 0, s>>>(p);
+              push2d_tgt_dc_kernel<MODE_DUAL><<<gpush, PUSH_BLOCK, 0, q>>>(p);
             else if (mode == MODE_F32)
-              push2d_tgt_dc_kernel<MODE_F32><<<gpush, PUSH_BLOCK, 0, s>>>(p);
+              push2d_tgt_dc_kernel<MODE_F32><<<gpush, PUSH_BLOCK, 0, q>>>(p);
             else
-              push2d_tgt_dc_kernel<MODE_F64><<<gpush, PUSH_BLOCK, 0, s>>>(p);
-            st.total_launches += 1;
+              push2d_tgt_dc_kernel<MODE_F64><<<gpush, PUSH_BLOCK, 0, q>>>(p);
+          } else {
+            launch_push_dc(p.warp_units != 0, mode, gpush, q, p);
           }
-          if (!p.tgt_off) launch_push_dc(p.warp_units != 0, mode, gpush, s, p);
-          st.total_launches += 2;
-          after_far = 0;
+          seq_launches += 3;
+          af = 0;
           if (r % FAR_EVERY == FAR_EVERY - 1 || r == R - 1) {
-            far_min_dc_kernel<<<gfar, 256, 0, s>>>(p);
-            far_release_dc_kernel<<<gfar, 256, 0, s>>>(p);
-            st.total_launches += 2;
-            after_far = 1;
+            far_min_dc_kernel<<<gfar, 256, 0, q>>>(p);
+            far_release_dc_kernel<<<gfar, 256, 0, q>>>(p);
+            seq_launches += 2;
+            af = 1;
           }
         }
+      };
+      cudaGraphExec_t gexec = nullptr;
+      if (h->opts.use_graph) {
+        std::vector<char> key(sizeof(PP) + 4 * sizeof(int));
+        std::memcpy(key.data(), &p, sizeof(PP));
+        const int kv[4] = {B, mode, R, (int)gpush.x};
+        std::memcpy(key.data() + sizeof(PP), kv, sizeof(kv));
+        if (m.round_graph && key != m.round_graph_key) {
+          cudaGraphExecDestroy((cudaGraphExec_t)m.round_graph);
+          m.round_graph = nullptr;
+        }
+        if (!m.round_graph) {
+          cudaGraph_t g = nullptr;
+          if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            enqueue_rounds(s);
+            if (cudaStreamEndCapture(s, &g) == cudaSuccess && g) {
+              cudaGraphExec_t ge = nullptr;
+              if (cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+                m.round_graph = (void*)ge;
+                m.round_graph_key = key;
+                m.round_graph_launches = seq_launches;
+              }
+              cudaGraphDestroy(g);
+            }
+          }
+          cudaGetLastError();  // a failed capture falls back to plain launches
+        }
+        gexec = (cudaGraphExec_t)m.round_graph;
+        if (gexec) seq_launches = m.round_graph_launches;
+      }
+      while (!all_done) {
+        if (gexec) {
+          if (cudaGraphLaunch(gexec, s) != cudaSuccess) {
+            rc = RT_ERR_CUDA;
+            break;
+          }
+        } else {
+          enqueue_rounds(s);
+        }
+        st.total_launches += seq_launches;
         enq_rounds += R;
         if (enq_rounds > ((i64)1 << 22)) {  // a solve needs 1e3 - 1e5 rounds: never spin forever on a logic error
           rt_set_error("near-far schedule did not converge within %lld rounds", (long long)enq_rounds);

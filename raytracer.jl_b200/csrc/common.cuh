@@ -97,6 +97,7 @@ struct SolverOpts {
   int packed_prev = 1;     // near-far 2-D: 1 = 128-bit (time, predecessor) CAS, 0 = separate tightness pass
   double delta_factor = 0.0;  // automatic width = delta_factor x lightest edge (0 = default)
   int weight3d = 0;        // 3-D edge weight: 0 = weights.jl:20 (d * (1/|Ui+Uj|) * 2), 1 = Dijsktra.jl:388 (d / |Ui+Uj| * 0.5)
+  int use_graph = 1;       // near-far 2-D launch sequence: replay the rounds as a CUDA graph
   int compact = 1;         // near-far 2-D, long columns: evaluate full warps of the targets that survive the group screen
   int group_screen = 1;    // near-far 2-D: per (released item, target) disc bound before the source loop
   int target_lists = 1;    // near-far 2-D, short columns: 1 = de-duplicated target list per work item

@@ -454,6 +454,7 @@ void mesh2d_free(rt_mesh* h) {
   if (h->m2) {
     if (h->m2->counters_host) cudaFreeHost(h->m2->counters_host);
     if (h->m2->canon) canon_ws_free(h->m2->canon);
+    if (h->m2->round_graph) cudaGraphExecDestroy((cudaGraphExec_t)h->m2->round_graph);
     delete h->m2;
   }
   h->m2 = nullptr;

@@ -65,6 +65,9 @@ struct Mesh2D {
   DevBuf<i64> flat;                    // flattened near / far slot prefixes of a batch round
   DevBuf<i32> flat_b;                  // owner source per global near-list slot of a batch round
   CanonWs* canon = nullptr;
+  void* round_graph = nullptr;         // cudaGraphExec_t of the near-far round sequence (bfm2d_push.cu)
+  std::vector<char> round_graph_key;
+  i64 round_graph_launches = 0;
   DevBuf<i64> tgt_off;                 // de-duplicated target lists of the work items (short-column meshes)
   DevBuf<i32> tgt_idx;
   bool tgt_tried = false;
