@@ -862,7 +862,10 @@ struct LiveBuf {
 // of the released sources (warp-private smem slab) and walks the elements e, e + PUSH_GE, ... of the column with the
 // software-pipelined target loop.  (The CTA-level variant above spends a third of its stall time in __syncthreads.)
 constexpr int PUSH_GE = 16;
-constexpr int FAR_EVERY = 3;  // the threshold-advance kernels are enqueued every FAR_EVERY-th round
+#ifndef RT_FAR_EVERY
+#define RT_FAR_EVERY 3
+#endif
+constexpr int FAR_EVERY = RT_FAR_EVERY;  // the threshold-advance kernels are enqueued every FAR_EVERY-th round
 #ifndef RT_PUSH_SPLIT
 #define RT_PUSH_SPLIT 32
 #endif
