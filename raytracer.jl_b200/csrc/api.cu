@@ -460,6 +460,10 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
     m->opts.target_lists = value != 0.0;
   } else if (!std::strcmp(key, "canonical_prev")) {
     m->opts.canonical_prev = value != 0.0;
+  } else if (!std::strcmp(key, "early_advance")) {
+    m->opts.early_advance = value;
+  } else if (!std::strcmp(key, "tile_pull")) {
+    m->opts.tile_pull = value != 0.0;
   } else if (!std::strcmp(key, "delta_factor")) {
     RT_ARG(value >= 0.0, "delta_factor must be >= 0");
     m->opts.delta_factor = value;

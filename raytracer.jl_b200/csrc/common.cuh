@@ -102,6 +102,9 @@ struct SolverOpts {
   int group_screen = 1;    // near-far 2-D: per (released item, target) disc bound before the source loop
   int target_lists = 1;    // near-far 2-D, short columns: 1 = de-duplicated target list per work item
   int canonical_prev = 0;  // near-far: 1 = reproduce the reference's predecessors exactly, ties included
+  double early_advance = -1.0;  // near-far 3-D tile-pull: threshold advances early when a round releases fewer than
+                                // early_advance x n^(2/3) nodes (-1 = default, 0 = never)
+  int tile_pull = 1;       // near-far 3-D: 1 = tile-pull rounds (targets pull from released sources, no atomics), 0 = push units
 };
 
 struct Mesh2D;

@@ -11,6 +11,9 @@
 // shared memory once, and every thread scans its window in ascending linear id (the canonical scan order:
 // the reference iterates a Julia Set whose order is not reproducible).  Frontier = active tile list.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -52,6 +55,13 @@ struct Grid3D {
   DevBuf<int> ctl;
   DevBuf<i32> unresolved;
   bool push_ready = false;
+  // ---- near-far, tile-pull rounds (tile = the 8x4x4 block of the Jacobi kernel; 4 mask words per tile, word = z-plane)
+  DevBuf<unsigned> tpend, trel;    // [n_tiles * 4] improved since the last release / released in the current round
+  DevBuf<unsigned> tmark;          // [n_tiles] round stamp of the last activation as a target tile
+  DevBuf<unsigned> tmaxhi;         // [n_tiles] 1 + high word of the tile's largest travel time
+  bool pull_ready = false;
+  void* tp_graph = nullptr;        // cudaGraphExec_t of check_every rounds
+  std::vector<char> tp_graph_key;
   CanonWs* canon = nullptr;  // canonical-predecessor pass (option canonical_prev)
 };
 
@@ -285,8 +295,8 @@ int ensure_ws3(rt_mesh* h) {
   RT_TRY(g.improved.alloc(g.n_tiles));
   RT_TRY(g.act[0].alloc(g.n_tiles));
   RT_TRY(g.act[1].alloc(g.n_tiles));
-  RT_TRY(g.counters.alloc(8));
-  RT_CUDA(cudaMallocHost((void**)&g.counters_host, 8 * sizeof(u64)));
+  RT_TRY(g.counters.alloc(16));
+  RT_CUDA(cudaMallocHost((void**)&g.counters_host, 16 * sizeof(u64)));
   g.ws_ready = true;
   return RT_OK;
 }
@@ -355,6 +365,7 @@ void grid3d_free(rt_mesh* h) {
   if (h->g3) {
     if (h->g3->counters_host) cudaFreeHost(h->g3->counters_host);
     if (h->g3->canon) canon_ws_free(h->g3->canon);
+    if (h->g3->tp_graph) cudaGraphExecDestroy((cudaGraphExec_t)h->g3->tp_graph);
     delete h->g3;
   }
   h->g3 = nullptr;
@@ -534,6 +545,12 @@ __device__ __forceinline__ void push3d_body(const Q3& p, const i32* near_cur, in
 // after_far: the far kernels were enqueued since the previous round_begin (they only are every FAR3_EVERY-th
 // round); a requested threshold advance (mode 2) waits for them, prep / push return at once meanwhile
 constexpr int FAR3_EVERY = 3;
+#ifndef TP_DELTA_FACTOR
+#define TP_DELTA_FACTOR 8.0
+#endif
+#ifndef TP_EARLY
+#define TP_EARLY 0.0  // x n^(2/3) releases per round (measured on 216^3 / 368^3: no gain at 0.25 .. 4)
+#endif
 __global__ void round_begin3_kernel(Q3 p, int after_far) {
   int* c = p.ctl;
   if (c[3]) return;
@@ -897,8 +914,607 @@ int bfm3d_solve_push(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   return rc;
 }
 
+// =========================================================================================================
+// Near-far schedule as tile-pull rounds (option tile_pull = 1, the default for schedule 1 on 3-D grids).
+//
+// Same label-correcting scheme as the push units above (threshold tau, bucket width delta, every node that improved
+// and lies below tau is released in the next round), but the round is turned around: the TARGETS of a round pull from
+// the released sources.  Pending / released sets are 128-bit masks per tile (tile = the 8x4x4 block of the Jacobi
+// kernel; word = z-plane of the tile = warp of the CTA, bit = lane).  A tile within reach of a released node builds,
+// from the released words of the <= 27 tiles around it, one bit mask per x-row of tile + halo ("is this neighbour a
+// released source" becomes a shift and a mask), stages (travel time, X, Y, Z, U) of the released cells only, and every
+// thread relaxes its own node from the released sources of its window.  A node is written by exactly one thread of
+// one CTA: no atomics on the travel times, no per-node work lists; "improved" is one ballot per warp.  A source's
+// travel time is read from dist[] itself: any value it ever held is a valid label, and a source that improves during
+// the round is pending again.
+//
+// Pruning (all exact-safe: weights are >= 0): a tile whose largest travel time lies below the smallest released one
+// of a source tile is not visited for it (tmaxhi: high words, rounded up); a thread whose own travel time lies below
+// every released one of the staged block, or whose window holds no released source in a z-plane, skips the scan.
+//
+// Per round two launches: tp_release (scan the tile masks: nodes with pending improvement and dist < tau are released,
+// the tiles within reach stamped and appended to the target list) and tp_pull (the relaxation; its last CTA does the
+// round control: threshold advance to min(pending) + delta when nothing was released, termination).  The travel times
+// are the least fixed point of the same monotone relaxation, hence bit-identical to the other schedules; predecessors
+// come from the same tightness pass (prev_tight3_kernel / canonical_prev_3d).
+namespace {
+
+struct T3 {
+  const double* __restrict__ X;
+  const double* __restrict__ Y;
+  const double* __restrict__ Z;
+  const double* __restrict__ U;
+  double* dist;
+  unsigned* tpend;   // [n_tiles * 4] improved since the last release
+  unsigned* trel;    // [n_tiles * 4] released in the current round
+  unsigned* tmark;   // [n_tiles] round stamp of the last activation as a target tile
+  unsigned* tmaxhi;  // [n_tiles] 1 + high word of the largest travel time of the tile (0xffffffff: never visited)
+  i32* act;          // target tiles of the current round
+  // [0] target tiles [1] released this round [2] nominal candidates [3] releases (total) [4] finished pull CTAs
+  // [5] tile visits [7] min pending bits [8] screened [9] exact
+  u64* counters;
+  double* tau;  // [0] tau [1] delta
+  int* ctl;     // [0] round stamp [3] done [4] rounds [5] rounds with releases
+  int nx, ny, nz, tnx, tny, tnz;
+  i64 n_tiles;
+  int w, self, wmode, count;
+  u64 early;  // releases per round below which the threshold advances although the bucket is not empty
+  FastDiv fd_tnx, fd_tny, fd_SY;
+};
+
+constexpr int TPR_BLOCK = 256;
+static_assert(TX == 8 && TY == 4 && TZ == 4, "the tile masks assume 8 x 4 x 4 tiles (word = z-plane, byte = y-row)");
+
+__global__ void __launch_bounds__(TPR_BLOCK) tp_release_kernel(T3 p) {
+  if (p.ctl[3]) return;
+  __shared__ int s_list[TPR_BLOCK];
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  const i64 t = (i64)blockIdx.x * TPR_BLOCK + tid;
+  bool work = false;
+  if (t < p.n_tiles) {
+    const uint4 pw = __ldcg(reinterpret_cast<const uint4*>(p.tpend) + t);
+    const uint4 rw = __ldcg(reinterpret_cast<const uint4*>(p.trel) + t);
+    work = (pw.x | pw.y | pw.z | pw.w | rw.x | rw.y | rw.z | rw.w) != 0u;
+  }
+  const unsigned ball = __ballot_sync(FULL, work);
+  if (ball) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&s_cnt, __popc(ball));
+    base = __shfl_sync(FULL, base, 0);
+    if (work) s_list[base + __popc(ball & ((1u << lane) - 1u))] = (int)t;
+  }
+  __syncthreads();
+  const int cnt = s_cnt;
+  if (cnt == 0) return;
+  const unsigned stamp = (unsigned)__ldcg(&p.ctl[0]);
+  const double tau = __ldcg(&p.tau[0]);
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const int w = p.w;
+  u64 fmin = ~0ull, evals = 0;
+  unsigned nrel = 0;
+  for (int it = warp; it < cnt; it += TPR_BLOCK / 32) {
+    const int tile = s_list[it];
+    unsigned line, txu, tzu, tyu;
+    p.fd_tnx.divmod((unsigned)tile, line, txu);
+    p.fd_tny.divmod(line, tzu, tyu);
+    const int tx = (int)txu, ty = (int)tyu, tz = (int)tzu;
+    const uint4 pw = __ldcg(reinterpret_cast<const uint4*>(p.tpend) + tile);
+    const uint4 rw = __ldcg(reinterpret_cast<const uint4*>(p.trel) + tile);
+    const unsigned pk[4] = {pw.x, pw.y, pw.z, pw.w};
+    const int gx = tx * TX + (lane & 7), gy = ty * TY + (lane >> 3);
+    double d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // pending bits only exist for nodes of the grid
+      const i64 J = (i64)gx + (i64)p.nx * ((i64)gy + (i64)p.ny * (tz * TZ + k));
+      d[k] = ((pk[k] >> lane) & 1u) ? __ldcg(&p.dist[J]) : INF;
+    }
+    unsigned nk[4];
+    unsigned hmin = 0xffffffffu;
+    const int exy = (min(p.nx - 1, gx + w) - max(0, gx - w) + 1) * (min(p.ny - 1, gy + w) - max(0, gy - w) + 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool pend = (pk[k] >> lane) & 1u;
+      const bool near = pend && d[k] < tau;
+      nk[k] = __ballot_sync(FULL, near);
+      if (near) {
+        hmin = min(hmin, (unsigned)__double2hiint(d[k]));
+        const int gz = tz * TZ + k;
+        evals += (u64)(exy * (min(p.nz - 1, gz + w) - max(0, gz - w) + 1) - (p.self ? 0 : 1));
+      }
+      if (pend && !near) {
+        const u64 b = (u64)__double_as_longlong(d[k]);
+        fmin = b < fmin ? b : fmin;
+      }
+    }
+    const unsigned any = nk[0] | nk[1] | nk[2] | nk[3];
+    if (lane == 0) {
+      if (any | rw.x | rw.y | rw.z | rw.w) reinterpret_cast<uint4*>(p.trel)[tile] = make_uint4(nk[0], nk[1], nk[2], nk[3]);
+      if (any)
+        reinterpret_cast<uint4*>(p.tpend)[tile] = make_uint4(pk[0] & ~nk[0], pk[1] & ~nk[1], pk[2] & ~nk[2], pk[3] & ~nk[3]);
+      nrel += (unsigned)(__popc(nk[0]) + __popc(nk[1]) + __popc(nk[2]) + __popc(nk[3]));
+    }
+    if (any) {
+      const unsigned tminhi = __reduce_min_sync(FULL, hmin);  // high word of the smallest released travel time (>= 0)
+      if (lane < 27) {
+        // bounding box of the released nodes (tile-local), grown by the window half width, against the 27 tiles around
+        const unsigned fold = (any | (any >> 8) | (any >> 16) | (any >> 24)) & 0xffu;
+        const int bx0 = __ffs(fold) - 1, bx1 = 31 - __clz(fold);
+        const unsigned rows = ((any & 0xffu) ? 1u : 0u) | ((any & 0xff00u) ? 2u : 0u) | ((any & 0xff0000u) ? 4u : 0u) |
+                              ((any & 0xff000000u) ? 8u : 0u);
+        const int by0 = __ffs(rows) - 1, by1 = 31 - __clz(rows);
+        const int bz0 = nk[0] ? 0 : nk[1] ? 1 : nk[2] ? 2 : 3, bz1 = nk[3] ? 3 : nk[2] ? 2 : nk[1] ? 1 : 0;
+        const int ddx = lane % 3 - 1, ddy = (lane / 3) % 3 - 1, ddz = lane / 9 - 1;
+        const int ux = tx + ddx, uy = ty + ddy, uz = tz + ddz;
+        if (ux >= 0 && ux < p.tnx && uy >= 0 && uy < p.tny && uz >= 0 && uz < p.tnz) {
+          const int x0 = tx * TX + bx0 - w, x1 = tx * TX + bx1 + w;
+          const int y0 = ty * TY + by0 - w, y1 = ty * TY + by1 + w;
+          const int z0 = tz * TZ + bz0 - w, z1 = tz * TZ + bz1 + w;
+          if (x0 <= ux * TX + TX - 1 && x1 >= ux * TX && y0 <= uy * TY + TY - 1 && y1 >= uy * TY &&
+              z0 <= uz * TZ + TZ - 1 && z1 >= uz * TZ) {
+            const int nb = ux + p.tnx * (uy + p.tny * uz);
+            // every travel time of that tile already lies below every released one of this tile: nothing to improve
+            if (__ldcg(&p.tmaxhi[nb]) > tminhi)
+              if (atomicExch(&p.tmark[nb], stamp) != stamp) p.act[atomicAdd(&p.counters[0], 1ull)] = nb;
+          }
+        }
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const u64 other = __shfl_xor_sync(FULL, fmin, o);
+    fmin = other < fmin ? other : fmin;
+    evals += __shfl_xor_sync(FULL, evals, o);
+  }
+  if (lane == 0) {
+    if (fmin != ~0ull) atomicMin(&p.counters[7], fmin);
+    if (nrel) atomicAdd(&p.counters[1], (u64)nrel);
+    if (evals) atomicAdd(&p.counters[2], evals);
+  }
+}
+
+// dynamic smem: 5 * SN doubles (travel time, X, Y, Z, U of the released cells of tile + halo) + SY * SZ row masks +
+// SZ plane masks
+template <bool F32>
+__global__ void __launch_bounds__(TILE_THREADS) tp_pull_kernel(T3 p) {
+  extern __shared__ double sm[];
+  __shared__ unsigned s_bminhi;
+  if (p.ctl[3]) return;
+  const int w = p.w, W = 2 * w + 1;
+  const int SX = TX + 2 * w, SY = TY + 2 * w, SZ = TZ + 2 * w;
+  const int SN = SX * SY * SZ, NROW = SY * SZ;
+  double* sR = sm;
+  double* sX = sR + SN;
+  double* sY = sX + SN;
+  double* sZ = sY + SN;
+  double* sU = sZ + SN;
+  unsigned* rowm = reinterpret_cast<unsigned*>(sU + SN);
+  unsigned* planem = rowm + NROW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lx = tid % TX, ly = (tid / TX) % TY, lz = tid / (TX * TY);
+  const i64 n_act = (i64)__ldcg(&p.counters[0]);
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const unsigned wmask = (1u << W) - 1u, xmask = (1u << SX) - 1u;
+  u64 screened = 0, exact = 0;
+  for (i64 a = blockIdx.x; a < n_act; a += gridDim.x) {
+    const int tile = __ldcg(&p.act[a]);
+    unsigned line, txu, tzu, tyu;
+    p.fd_tnx.divmod((unsigned)tile, line, txu);
+    p.fd_tny.divmod(line, tzu, tyu);
+    const int tx = (int)txu, ty = (int)tyu, tz = (int)tzu;
+    const int ox = tx * TX - w, oy = ty * TY - w, oz = tz * TZ - w;  // grid coordinates of staged cell (0, 0, 0)
+    __syncthreads();  // the previous tile's readers are done
+    if (tid < SZ) planem[tid] = 0u;
+    if (tid == 0) {
+      s_bminhi = 0xffffffffu;
+      p.tmaxhi[tile] = 0u;
+    }
+    // own node
+    const int gx = tx * TX + lx, gy = ty * TY + ly, gz = tz * TZ + lz;
+    const bool inside = gx < p.nx && gy < p.ny && gz < p.nz;
+    const i64 I = (i64)gx + (i64)p.nx * ((i64)gy + (i64)p.ny * gz);
+    double di = INF, xi = 0.0, yi = 0.0, zi = 0.0, ui = 0.0;
+    if (inside) {
+      di = __ldcg(&p.dist[I]);
+      xi = p.X[I];
+      yi = p.Y[I];
+      zi = p.Z[I];
+      ui = p.U[I];
+    }
+    __syncthreads();
+    // phase 1: one mask per x-row of tile + halo from the released words of the (up to three) tiles the row crosses
+    for (int row = tid; row < NROW; row += TILE_THREADS) {
+      unsigned czu, cyu;
+      p.fd_SY.divmod((unsigned)row, czu, cyu);
+      const int gyy = oy + (int)cyu, gzz = oz + (int)czu;
+      unsigned m = 0u;
+      if (gyy >= 0 && gyy < p.ny && gzz >= 0 && gzz < p.nz) {
+        const i64 base = ((i64)(gzz / TZ) * p.tny + (gyy / TY)) * p.tnx;
+        const int word = gzz % TZ, sh8 = 8 * (gyy % TY);
+#pragma unroll
+        for (int dxx = -1; dxx <= 1; ++dxx) {
+          const int txx = tx + dxx;
+          if (txx < 0 || txx >= p.tnx) continue;
+          const unsigned byte = (__ldcg(&p.trel[(base + txx) * 4 + word]) >> sh8) & 0xffu;
+          const int sh = dxx * TX + w;  // staged x of that tile's first node
+          m |= sh >= 0 ? byte << sh : byte >> (-sh);
+        }
+        m &= xmask;
+      }
+      rowm[row] = m;
+      if (m) atomicOr(&planem[czu], m);
+    }
+    __syncthreads();
+    // phase 2: travel time and coordinates of the released cells (16 lanes per x-row, SX <= 16)
+    {
+      const int cx = tid & 15;
+      if (cx < SX) {
+        for (int row = tid >> 4; row < NROW; row += TILE_THREADS / 16) {
+          if (!((rowm[row] >> cx) & 1u)) continue;
+          unsigned czu, cyu;
+          p.fd_SY.divmod((unsigned)row, czu, cyu);
+          const i64 J = (i64)(ox + cx) + (i64)p.nx * ((i64)(oy + (int)cyu) + (i64)p.ny * (oz + (int)czu));
+          const int c = cx + SX * row;
+          const double r = __ldcg(&p.dist[J]);
+          sR[c] = r;
+          sX[c] = p.X[J];
+          sY[c] = p.Y[J];
+          sZ[c] = p.Z[J];
+          sU[c] = p.U[J];
+          atomicMin(&s_bminhi, (unsigned)__double2hiint(r));
+        }
+      }
+    }
+    __syncthreads();
+    bool improved = false;
+    double best = di;
+    // a travel time below every released one of the block cannot improve (high words: conservative)
+    if (inside && (unsigned)__double2hiint(di) >= s_bminhi) {
+      for (int zz = 0; zz < W; ++zz) {
+        if (!((planem[lz + zz] >> lx) & wmask)) continue;
+        const int row0 = ly + SY * (lz + zz);
+        for (int yy = 0; yy < W; ++yy) {
+          const int row = row0 + yy;
+          unsigned m = (rowm[row] >> lx) & wmask;
+          const int c0 = lx + SX * row;
+          while (m) {
+            const int c = c0 + __ffs(m) - 1;
+            m &= m - 1u;
+            const double dj = sR[c];
+            if (!(dj < best)) continue;  // also the node itself
+            const double xj = sX[c], yj = sY[c], zj = sZ[c], uj = sU[c];
+            const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
+            const double d2 = __fma_rn(dx, dx, __fma_rn(dy, dy, dz * dz));
+            if (p.count) screened += 1;
+            if (screen_cannot_improve_t<F32>(best, dj, d2, screen_ssum3(fabs(__dadd_rn(ui, uj)), p.wmode))) continue;
+            if (p.count) exact += 1;
+            const double delta = cand3<F32>(dj, xi, yi, zi, ui, xj, yj, zj, uj, p.wmode);
+            best = delta < best ? delta : best;
+          }
+        }
+      }
+      if (best < di) {
+        p.dist[I] = best;
+        improved = true;
+      }
+    }
+    const unsigned imp = __ballot_sync(FULL, improved);
+    const unsigned wmax = __reduce_max_sync(FULL, inside ? (unsigned)__double2hiint(best) : 0u);
+    if (lane == 0) {
+      if (imp) p.tpend[(i64)tile * 4 + warp] |= imp;  // this CTA is the only writer of the tile's words
+      atomicMax(&p.tmaxhi[tile], wmax + 1u);          // reset by thread 0 at the start of the visit (two barriers ago)
+    }
+  }
+  if (p.count) {
+    for (int o = 16; o; o >>= 1) {
+      screened += __shfl_xor_sync(FULL, screened, o);
+      exact += __shfl_xor_sync(FULL, exact, o);
+    }
+    if (lane == 0 && screened) {
+      atomicAdd(&p.counters[8], screened);
+      atomicAdd(&p.counters[9], exact);
+    }
+  }
+  // round control by the last CTA to finish
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const u64 ticket = atomicAdd(&p.counters[4], 1ull);
+    if (ticket == (u64)gridDim.x - 1ull) {
+      __threadfence();
+      const u64 n_rel = __ldcg(&p.counters[1]);
+      const u64 mp = __ldcg(&p.counters[7]);
+      p.ctl[4] += 1;
+      if (n_rel > 0) {
+        p.ctl[5] += 1;
+        p.counters[3] += n_rel;
+        p.counters[5] += __ldcg(&p.counters[0]);
+        // the tail of a bucket (a few stragglers per round) shares its rounds with the head of the next bucket: any
+        // release order reaches the same fixed point
+        if (n_rel < p.early && mp != ~0ull) {
+          const double t2 = __dadd_rn(__longlong_as_double((long long)mp), p.tau[1]);
+          if (t2 > p.tau[0]) p.tau[0] = t2;
+        }
+      } else if (mp != ~0ull) {
+        p.tau[0] = __dadd_rn(__longlong_as_double((long long)mp), p.tau[1]);
+      } else {
+        p.ctl[3] = 1;
+      }
+      p.ctl[0] += 1;
+      p.counters[0] = 0ull;
+      p.counters[1] = 0ull;
+      p.counters[4] = 0ull;
+      p.counters[7] = ~0ull;
+      __threadfence();
+    }
+  }
+}
+
+__global__ void tp_init_kernel(T3 p, i32* __restrict__ prev, i64 n, i64 source, double delta) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    p.dist[i] = (i == source) ? 0.0 : __longlong_as_double(0x7ff0000000000000LL);
+    prev[i] = -1;
+  }
+  if (i == 0) {
+    const int sx = (int)(source % p.nx), sy = (int)((source / p.nx) % p.ny), sz = (int)(source / ((i64)p.nx * p.ny));
+    const i64 tile = (sx / TX) + (i64)p.tnx * ((sy / TY) + (i64)p.tny * (sz / TZ));
+    p.tpend[tile * 4 + (sz % TZ)] = 1u << ((sx % TX) + TX * (sy % TY));
+    p.ctl[0] = 1;
+    p.tau[0] = delta;
+    p.tau[1] = delta;
+    p.counters[7] = ~0ull;
+  }
+}
+
+int ensure_pull3(rt_mesh* h) {
+  Grid3D& g = *h->g3;
+  if (g.pull_ready) return RT_OK;
+  RT_TRY(g.tpend.alloc(g.n_tiles * 4));
+  RT_TRY(g.trel.alloc(g.n_tiles * 4));
+  RT_TRY(g.tmark.alloc(g.n_tiles));
+  RT_TRY(g.tmaxhi.alloc(g.n_tiles));
+  RT_TRY(g.tau.alloc(4));
+  RT_TRY(g.ctl.alloc(8));
+  g.pull_ready = true;
+  return RT_OK;
+}
+
+}  // namespace
+
+int bfm3d_solve_pull(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                     rt_stats* stats) {
+  Grid3D& g = *h->g3;
+  cudaStream_t s = h->stream;
+  RT_TRY(ensure_ws3(h));
+  RT_TRY(ensure_pull3(h));
+  const i64 n = g.n;
+  const bool f32 = h->f32;
+  if (f32) RT_TRY(grid3d_prepare_f32(h));
+  T3 p;
+  p.X = f32 ? g.Xf.p : g.X.p;
+  p.Y = f32 ? g.Yf.p : g.Y.p;
+  p.Z = f32 ? g.Zf.p : g.Z.p;
+  p.U = U_dev;
+  p.dist = g.dist.p;
+  p.tpend = g.tpend.p;
+  p.trel = g.trel.p;
+  p.tmark = g.tmark.p;
+  p.tmaxhi = g.tmaxhi.p;
+  p.act = g.act[0].p;
+  p.counters = g.counters.p;
+  p.tau = g.tau.p;
+  p.ctl = g.ctl.p;
+  p.nx = (int)g.nn[0];
+  p.ny = (int)g.nn[1];
+  p.nz = (int)g.nn[2];
+  p.tnx = (int)g.tn[0];
+  p.tny = (int)g.tn[1];
+  p.tnz = (int)g.tn[2];
+  p.n_tiles = g.n_tiles;
+  p.w = g.w;
+  p.self = g.self;
+  p.wmode = h->opts.weight3d;
+  p.count = h->opts.profile_timers != 0;
+  p.early = (u64)((h->opts.early_advance >= 0.0 ? h->opts.early_advance : TP_EARLY) * std::pow((double)g.n, 2.0 / 3.0));
+  p.fd_tnx = FastDiv((unsigned)g.tn[0]);
+  p.fd_tny = FastDiv((unsigned)g.tn[1]);
+  p.fd_SY = FastDiv((unsigned)(TY + 2 * g.w));
+  RT_ARG(g.n_tiles < ((i64)1 << 31), "grid too large for the near-far schedule");
+  // the tightness pass and the bucket-width probe take the push schedule's parameter block
+  Q3 q = {};
+  q.X = p.X;
+  q.Y = p.Y;
+  q.Z = p.Z;
+  q.U = U_dev;
+  q.dist = g.dist.p;
+  q.prev = g.prev.p;
+  q.nx = p.nx;
+  q.ny = p.ny;
+  q.nz = p.nz;
+  q.w = g.w;
+  q.self = g.self;
+  q.wmode = p.wmode;
+  const int w = g.w;
+  const size_t SN = (size_t)(TX + 2 * w) * (TY + 2 * w) * (TZ + 2 * w);
+  const size_t smem = 5 * SN * sizeof(double) + (size_t)((TY + 2 * w) * (TZ + 2 * w) + (TZ + 2 * w)) * sizeof(unsigned);
+  RT_CUDA(cudaFuncSetAttribute(tp_pull_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RT_CUDA(cudaFuncSetAttribute(tp_pull_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+  int per_sm = 1;
+  if (f32)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tp_pull_kernel<true>, TILE_THREADS, smem);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tp_pull_kernel<false>, TILE_THREADS, smem);
+  const unsigned gpull = (unsigned)std::min<i64>(g.n_tiles, (i64)sm_count * std::max(per_sm, 1));
+  const unsigned grel = grid_for(g.n_tiles, TPR_BLOCK);
+  cudaEvent_t ev0, ev1, evr0, evr1;
+  RT_CUDA(cudaEventCreate(&ev0));
+  RT_CUDA(cudaEventCreate(&ev1));
+  RT_CUDA(cudaEventCreate(&evr0));
+  RT_CUDA(cudaEventCreate(&evr1));
+  rt_stats st = {};
+  st.graph_edges = g.graph_edges;
+  int rc = RT_OK;
+  const bool timers = h->opts.profile_timers != 0;
+  double delta = h->opts.delta;
+  if (!(delta > 0.0)) {
+    cudaMemsetAsync(g.tau.p + 3, 0, sizeof(double), s);
+    cudaMemsetAsync(g.counters.p + 7, 0, sizeof(u64), s);
+    wdiag3_kernel<<<grid_for((n + 6) / 7, 256), 256, 0, s>>>(q, g.tau.p + 3, g.counters.p + 7);
+    double wsum = 0.0;
+    u64 wc = 0;
+    cudaMemcpyAsync(&wsum, g.tau.p + 3, sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&wc, g.counters.p + 7, sizeof(u64), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) rc = RT_ERR_CUDA;
+    const double wmean = wc ? wsum / (double)wc : 1.0;
+    delta = wmean * (h->opts.delta_factor > 0.0 ? h->opts.delta_factor : TP_DELTA_FACTOR);
+  }
+  const int R = timers ? 1 : (h->opts.check_every > 1 ? h->opts.check_every : 32);
+  auto enqueue_rounds = [&](cudaStream_t qs) {
+    for (int r = 0; r < R; ++r) {
+      tp_release_kernel<<<grel, TPR_BLOCK, 0, qs>>>(p);
+      if (timers) cudaEventRecord(evr0, qs);
+      if (f32)
+        tp_pull_kernel<true><<<gpull, TILE_THREADS, smem, qs>>>(p);
+      else
+        tp_pull_kernel<false><<<gpull, TILE_THREADS, smem, qs>>>(p);
+      if (timers) cudaEventRecord(evr1, qs);
+    }
+  };
+  cudaGraphExec_t gexec = nullptr;
+  if (h->opts.use_graph && !timers && rc == RT_OK) {
+    std::vector<char> key(sizeof(T3) + 4 * sizeof(int));
+    std::memcpy(key.data(), &p, sizeof(T3));
+    const int kv[4] = {R, (int)gpull, (int)f32, (int)smem};
+    std::memcpy(key.data() + sizeof(T3), kv, sizeof(kv));
+    if (g.tp_graph && key != g.tp_graph_key) {
+      cudaGraphExecDestroy((cudaGraphExec_t)g.tp_graph);
+      g.tp_graph = nullptr;
+    }
+    if (!g.tp_graph) {
+      cudaGraph_t cg = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        enqueue_rounds(s);
+        if (cudaStreamEndCapture(s, &cg) == cudaSuccess && cg) {
+          cudaGraphExec_t ge = nullptr;
+          if (cudaGraphInstantiate(&ge, cg, 0) == cudaSuccess) {
+            g.tp_graph = (void*)ge;
+            g.tp_graph_key = key;
+          }
+          cudaGraphDestroy(cg);
+        }
+      }
+      cudaGetLastError();  // a failed capture falls back to plain launches
+    }
+    gexec = (cudaGraphExec_t)g.tp_graph;
+  }
+  u64* ch = g.counters_host;
+  for (i64 si = 0; si < nsrc && rc == RT_OK; ++si) {
+    const i64 src1 = sources[si];
+    if (src1 < 1 || src1 > n) {
+      rt_set_error("source %lld out of range 1..%lld", (long long)src1, (long long)n);
+      rc = RT_ERR_ARG;
+      break;
+    }
+    const i64 src = src1 - 1;
+    cudaEventRecord(ev0, s);
+    cudaMemsetAsync(g.counters.p, 0, 16 * sizeof(u64), s);
+    cudaMemsetAsync(g.tmaxhi.p, 0xff, g.n_tiles * sizeof(unsigned), s);
+    cudaMemsetAsync(g.tpend.p, 0, g.n_tiles * 4 * sizeof(unsigned), s);
+    cudaMemsetAsync(g.trel.p, 0, g.n_tiles * 4 * sizeof(unsigned), s);
+    cudaMemsetAsync(g.tmark.p, 0, g.n_tiles * sizeof(unsigned), s);
+    cudaMemsetAsync(g.ctl.p, 0, 8 * sizeof(int), s);
+    tp_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, g.prev.p, n, src, delta);
+    st.total_launches += 1;
+    int hctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    i64 enq_rounds = 0;
+    while (!hctl[3]) {
+      if (gexec) {
+        if (cudaGraphLaunch(gexec, s) != cudaSuccess) {
+          rc = RT_ERR_CUDA;
+          break;
+        }
+      } else {
+        enqueue_rounds(s);
+      }
+      st.total_launches += 2 * R;
+      enq_rounds += R;
+      if (enq_rounds > ((i64)1 << 22)) {  // a solve needs 1e2 - 1e4 rounds: never spin forever on a logic error
+        rt_set_error("near-far schedule did not converge within %lld rounds", (long long)enq_rounds);
+        rc = RT_ERR_CUDA;
+        break;
+      }
+      cudaMemcpyAsync(hctl, g.ctl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        rc = RT_ERR_CUDA;
+        break;
+      }
+      if (timers) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evr0, evr1);
+        st.relax_ms += ms;
+      }
+    }
+    if (rc != RT_OK) break;
+    st.sweeps += hctl[4];
+    st.relax_launches += hctl[5];
+
+    cudaEventRecord(evr0, s);
+    if (f32)
+      prev_tight3_kernel<true><<<grid_for(n, 128), 128, 0, s>>>(q, n, src);
+    else
+      prev_tight3_kernel<false><<<grid_for(n, 128), 128, 0, s>>>(q, n, src);
+    st.total_launches += 1;
+    if (h->opts.canonical_prev) {  // the reference schedule's predecessors, ties included (canonical_prev.cu)
+      Grid3Desc gd{p.X, p.Y, p.Z, p.nx, p.ny, p.nz, p.w, p.self, p.wmode};
+      i64 launches = 0;
+      rc = canonical_prev_3d(h, &g.canon, gd, U_dev, f32, g.dist.p, src, g.prev.p, &launches);
+      st.total_launches += launches;
+      if (rc != RT_OK) break;
+    }
+    cudaEventRecord(evr1, s);
+    cudaMemcpyAsync(ch, g.counters.p, 16 * sizeof(u64), cudaMemcpyDeviceToHost, s);
+    cudaEventRecord(ev1, s);
+    if (dist_dev) cudaMemcpyAsync(dist_dev + si * n, g.dist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (prev_dev) cudaMemcpyAsync(prev_dev + si * n, g.prev.p, n * sizeof(i32), cudaMemcpyDeviceToDevice, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) {
+      rc = RT_ERR_CUDA;
+      break;
+    }
+    st.relaxed_edges += (i64)ch[2];  // nominal: every (released source, target) pair; the tightness pass is in prev_ms
+    st.vertex_updates += (i64)ch[3];
+    st.screened_edges += (i64)ch[8];
+    st.exact_edges += (i64)ch[9];
+    if (std::getenv("RT_TP_DEBUG"))
+      std::fprintf(stderr, "tile-pull: %llu tile visits (%lld tiles), %llu releases, %d rounds\n", ch[5], (long long)g.n_tiles,
+                   ch[3], hctl[4]);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    st.kernel_ms += ms;
+    cudaEventElapsedTime(&ms, evr0, evr1);
+    st.prev_ms += ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (rc == RT_ERR_CUDA || e != cudaSuccess) {
+    rt_set_error("CUDA failure in bfm3d_solve_pull: %s", cudaGetErrorString(e));
+    rc = RT_ERR_CUDA;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  cudaEventDestroy(evr0);
+  cudaEventDestroy(evr1);
+  if (stats) *stats = st;
+  return rc;
+}
+
 int bfm3d_solve(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                 rt_stats* stats) {
+  if (h->opts.schedule == 1 && h->opts.tile_pull)
+    return bfm3d_solve_pull(h, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
   if (h->opts.schedule == 1) return bfm3d_solve_push(h, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
   Grid3D& g = *h->g3;
   cudaStream_t s = h->stream;
@@ -1087,64 +1703,41 @@ __global__ void connectivity3d_kernel(i64 nx, i64 ny, i64 ex, i64 ey, i64 first,
 }
 
 // closest_point(gr, x, y, z) (:257-270): argmin over the linear index of distance3D(gr[i], p) with strict `<`
-// (first index wins).  Pass 1: the minimum of the ROUNDED distances (the square root is only taken when the squared
-// distance undercuts the thread's best: sqrt is monotone, so a candidate with d2 >= best d2 can never be strictly
-// closer); pass 2: the first index attaining it (sqrt only for d2 within rounding reach of the target).
-__device__ __forceinline__ double d2_3(double a, double b, double c, double pa, double pb, double pc) {
-  const double da = __dsub_rn(a, pa), db = __dsub_rn(b, pb), dc = __dsub_rn(c, pc);
-  return __dadd_rn(__dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db)), __dmul_rn(dc, dc));
+// (first index wins).  The rounded distance fl(sqrt(fl(fl(a_i + b_j) + c_k))) with a_i = fl(fl(x_i - px)^2) (b_j, c_k
+// alike) is monotone in each of a_i, b_j, c_k, so its minimum D* is attained at the per-axis minima and the FIRST
+// linear index that attains it (z slowest, x fastest) is found axis by axis: the smallest k with
+// val(a_min, b_min, c_k) == D*, then the smallest j with val(a_min, b_j, c_k0) == D*, then the smallest i with
+// val(a_i, b_j0, c_k0) == D*.  O(nx + ny + nz) per query instead of a sweep over all nodes; one thread per query.
+__device__ __forceinline__ double sq_diff(double a, double pa) {
+  const double d = __dsub_rn(a, pa);
+  return __dmul_rn(d, d);
 }
-__global__ void closest3d_pass1_kernel(const double* __restrict__ ax, const double* __restrict__ ay,
-                                       const double* __restrict__ az, int nx, int ny, int nz, FastDiv fnx, FastDiv fny,
-                                       const double* __restrict__ pq, u64* __restrict__ best) {
-  const int q = blockIdx.y;
-  const double qa = pq[3 * q], qb = pq[3 * q + 1], qc = pq[3 * q + 2];
-  const i64 n = (i64)nx * ny * nz;
-  double bd2 = __longlong_as_double(0x7ff0000000000000LL);
-  u64 m = ~0ull;
-  for (i64 I = (i64)blockIdx.x * blockDim.x + threadIdx.x; I < n; I += (i64)gridDim.x * blockDim.x) {
-    unsigned line, i, k, j;
-    fnx.divmod((unsigned)I, line, i);
-    fny.divmod(line, k, j);
-    const double d2 = d2_3(ax[i], ay[j], az[k], qa, qb, qc);
-    if (d2 < bd2) {
-      bd2 = d2;
-      const u64 bits = (u64)__double_as_longlong(__dsqrt_rn(d2));
-      m = bits < m ? bits : m;
-    }
-  }
-  for (int o = 16; o; o >>= 1) {
-    const u64 other = __shfl_xor_sync(0xffffffffu, m, o);
-    m = other < m ? other : m;
-  }
-  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&best[q], m);
+__device__ __forceinline__ double dist_abc(double a, double b, double c) {
+  return __dsqrt_rn(__dadd_rn(__dadd_rn(a, b), c));
 }
-__global__ void closest3d_pass2_kernel(const double* __restrict__ ax, const double* __restrict__ ay,
-                                       const double* __restrict__ az, int nx, int ny, int nz, FastDiv fnx, FastDiv fny,
-                                       const double* __restrict__ pq, const u64* __restrict__ best,
-                                       u64* __restrict__ index) {
-  const int q = blockIdx.y;
+__global__ void closest3d_kernel(const double* __restrict__ ax, const double* __restrict__ ay,
+                                 const double* __restrict__ az, int nx, int ny, int nz, const double* __restrict__ pq,
+                                 i64 npts, i64* __restrict__ index) {
+  const i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= npts) return;
   const double qa = pq[3 * q], qb = pq[3 * q + 1], qc = pq[3 * q + 2];
-  const i64 n = (i64)nx * ny * nz;
-  const u64 target = best[q];
-  const double tv = __longlong_as_double((long long)target);
-  const double reach = tv * tv * (1.0 + 1e-15) + 1e-300;  // d2 above this cannot round to the target
-  u64 m = ~0ull;
-  for (i64 I = (i64)blockIdx.x * blockDim.x + threadIdx.x; I < n; I += (i64)gridDim.x * blockDim.x) {
-    unsigned line, i, k, j;
-    fnx.divmod((unsigned)I, line, i);
-    fny.divmod(line, k, j);
-    const double d2 = d2_3(ax[i], ay[j], az[k], qa, qb, qc);
-    if (d2 <= reach && (u64)__double_as_longlong(__dsqrt_rn(d2)) == target) {
-      m = (u64)I;
-      break;  // ascending per thread: the first hit is this thread's smallest
-    }
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  double amin = INF, bmin = INF, cmin = INF;
+  for (int i = 0; i < nx; ++i) amin = fmin(amin, sq_diff(ax[i], qa));  // fmin drops NaN: handled by the D test below
+  for (int j = 0; j < ny; ++j) bmin = fmin(bmin, sq_diff(ay[j], qb));
+  for (int k = 0; k < nz; ++k) cmin = fmin(cmin, sq_diff(az[k], qc));
+  const double D = dist_abc(amin, bmin, cmin);
+  i64 out = -1;  // no distance compares below Inf (NaN or infinite query): the reference returns its initial index
+  if (qa == qa && qb == qb && qc == qc && D < INF) {
+    int k0 = 0, j0 = 0, i0 = 0;
+    while (k0 < nz - 1 && dist_abc(amin, bmin, sq_diff(az[k0], qc)) != D) ++k0;
+    const double ck = sq_diff(az[k0], qc);
+    while (j0 < ny - 1 && dist_abc(amin, sq_diff(ay[j0], qb), ck) != D) ++j0;
+    const double bj = sq_diff(ay[j0], qb);
+    while (i0 < nx - 1 && dist_abc(sq_diff(ax[i0], qa), bj, ck) != D) ++i0;
+    out = (i64)i0 + (i64)nx * ((i64)j0 + (i64)ny * k0);
   }
-  for (int o = 16; o; o >>= 1) {
-    const u64 other = __shfl_xor_sync(0xffffffffu, m, o);
-    m = other < m ? other : m;
-  }
-  if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(&index[q], m);
+  index[q] = out;
 }
 
 int ensure_axes3(const rt_mesh* h) {
@@ -1221,26 +1814,15 @@ int grid3d_closest(const rt_mesh* h, const double* px, const double* py, const d
     pq[3 * q + 2] = pz[q];
   }
   DevBuf<double> dpq;
-  DevBuf<u64> best, index;
+  DevBuf<i64> index;
   RT_TRY(dpq.upload(pq.data(), 3 * npts, s));
-  RT_TRY(best.alloc(npts));
   RT_TRY(index.alloc(npts));
-  RT_CUDA(cudaMemsetAsync(best.p, 0xff, npts * sizeof(u64), s));
-  RT_CUDA(cudaMemsetAsync(index.p, 0xff, npts * sizeof(u64), s));
-  const FastDiv fnx((unsigned)g.nn[0]), fny((unsigned)g.nn[1]);
-  const unsigned bx = (unsigned)std::min<i64>(grid_for(g.n, 256), 592);
-  for (i64 q0 = 0; q0 < npts; q0 += 32768) {
-    const i64 nq = std::min<i64>(32768, npts - q0);
-    dim3 grid(bx, (unsigned)nq);
-    closest3d_pass1_kernel<<<grid, 256, 0, s>>>(g.ax.p, g.ay.p, g.az.p, (int)g.nn[0], (int)g.nn[1], (int)g.nn[2], fnx,
-                                                fny, dpq.p + 3 * q0, best.p + q0);
-    closest3d_pass2_kernel<<<grid, 256, 0, s>>>(g.ax.p, g.ay.p, g.az.p, (int)g.nn[0], (int)g.nn[1], (int)g.nn[2], fnx,
-                                                fny, dpq.p + 3 * q0, best.p + q0, index.p + q0);
-  }
+  closest3d_kernel<<<grid_for(npts, 64), 64, 0, s>>>(g.ax.p, g.ay.p, g.az.p, (int)g.nn[0], (int)g.nn[1], (int)g.nn[2],
+                                                     dpq.p, npts, index.p);
   RT_CUDA(cudaGetLastError());
-  std::vector<u64> hi(npts);
-  RT_CUDA(cudaMemcpyAsync(hi.data(), index.p, npts * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  std::vector<i64> hi(npts);
+  RT_CUDA(cudaMemcpyAsync(hi.data(), index.p, npts * sizeof(i64), cudaMemcpyDeviceToHost, s));
   RT_CUDA(cudaStreamSynchronize(s));
-  for (i64 q = 0; q < npts; ++q) out[q] = hi[q] == ~0ull ? -1 : (i64)hi[q] + 1;  // -1 as in the reference (NaN query)
+  for (i64 q = 0; q < npts; ++q) out[q] = hi[q] < 0 ? -1 : hi[q] + 1;  // -1 as in the reference (NaN query)
   return RT_OK;
 }

@@ -376,10 +376,16 @@ def test_bfm3d_near_far_schedule(rt, O, nn, lv, cs):
     n = int(np.prod(nn))
     U = 4.0 + 6.0 * splitmix64(11 + n, n)
     srcs = np.array([1, n, n // 2 + 3], np.int64)
-    for delta in (0.0, 1e-3, 1e9):
+    ref = [O.bfm3d(nn, lv, X, Y, Z, U, int(s)) for s in srcs]
+    # tile_pull = 1 (default): targets pull from the released sources tile by tile; 0: push units per released x-line
+    # early_advance > 0: the threshold moves on while stragglers of the bucket are still being released
+    for tile_pull, delta, early in ((1, 0.0, 0.0), (1, 1e-3, 0.0), (1, 1e9, 0.0), (1, 0.0, 2.0), (1, 1e-3, 50.0),
+                                    (0, 0.0, 0.0), (0, 1e-3, 0.0), (0, 1e9, 0.0)):
+        g._handle.set_option("tile_pull", tile_pull)
+        g._handle.set_option("early_advance", early)
         D = rt.bfm3d(g, srcs, U, schedule="near-far", delta=delta)
         for k, s in enumerate(srcs):
-            dist, prev, st = O.bfm3d(nn, lv, X, Y, Z, U, int(s))
+            dist, prev, st = ref[k]
             assert np.array_equal(D.dist[k], dist), "travel times must be bit-identical in any schedule"
             p = D.prev[k]
             i = np.nonzero(p > 0)[0]
@@ -389,6 +395,8 @@ def test_bfm3d_near_far_schedule(rt, O, nn, lv, cs):
             path = rt.recontruct_path(p, int(s), 1 if s != 1 else n)
             assert path[-1] == s and np.all(np.diff(dist[path - 1]) <= 0)
     assert D.stats["relaxed_edges"] > 0
+    g._handle.set_option("tile_pull", 1)
+    g._handle.set_option("early_advance", -1)
     rt.bfm3d(g, 1, U, schedule="jacobi")
 
 
