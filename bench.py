@@ -219,7 +219,10 @@ def roofline_pass(wl, source, steps, peak, peak_src, workload, sm_mhz):
         for key in prof:
             prof[key] += st[key]
     wl.handle.set_option("profile_timers", 0)
-    kname = ("relax%s_kernel" if wl.schedule == "jacobi" else "push%s_kernel") % ("3d" if wl.w["kind"] == "3d" else "2d")
+    if wl.w["kind"] == "3d":  # 3-D near-far = tile-pull rounds (option tile_pull = 1, the default)
+        kname = "relax3d_kernel" if wl.schedule == "jacobi" else "tp_pull_kernel"
+    else:
+        kname = "relax2d_kernel" if wl.schedule == "jacobi" else "push2d_kernel"
     bytes_alg = prof["relaxed_edges"] * 12 + prof["vertex_updates"] * wl.bv
     relax_s = max(prof["relax_ms"], 1e-9) * 1e-3
     achieved = bytes_alg / relax_s / 1e9

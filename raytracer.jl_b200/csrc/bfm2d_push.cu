@@ -1394,8 +1394,11 @@ __global__ void prep_dc_kernel(PP pb) {
     pb.cur_mask[o + slot] = atomicExch(&pb.pend_mask[o + near_cur[slot]], 0u);
   }
 }
+// resident CTAs per SM the register allocation aims at: 5 -> 96 registers (40 B of spills), 6 -> 80 (132 B), 4 -> 124
+// (none).  Measured on config[1] / annulus 180x50 @1 km (B200, r02p): 5: 1.137 s / 89 ms, 6: 1.178 s / 97 ms, 4: 1.187 s /
+// 91 ms, 7: 1.164 s, 8: 1.305 s, 3: 1.350 s / 99 ms.
 #ifndef RT_PUSH_MINB
-#define RT_PUSH_MINB 6
+#define RT_PUSH_MINB 5
 #endif
 template <bool WARP, int MODE>
 __global__ void __launch_bounds__(PUSH_BLOCK, RT_PUSH_MINB) push2d_dc_kernel(PP pb) {
