@@ -189,6 +189,10 @@ int rt_comm_init(const unsigned char id[128], int rank, int world, rt_comm** out
 int rt_comm_shard(int64_t nsrc, int rank, int world, int64_t* first, int64_t* count);
 int rt_bfm_solve_sharded(rt_comm* c, rt_mesh* m, const double* U_dev, const int64_t* sources, int64_t nsrc,
                          int precision, double* dist_dev, int32_t* prev_dev, rt_stats* stats);
+/* The same with HOST buffers (a caller without device memory of its own): U [n] in, dist_out [nsrc x n] doubles and
+ * prev_out [nsrc x n] 1-based int64 (0 = never set; may be NULL) out, as rt_bfm_solve returns them, on every rank. */
+int rt_bfm_solve_sharded_host(rt_comm* c, rt_mesh* m, const double* U, const int64_t* sources, int64_t nsrc,
+                              int precision, double* dist_out, int64_t* prev_out, rt_stats* stats);
 int rt_comm_destroy(rt_comm* c);
 
 /* Dual-velocity variant: bfm with U::Matrix -> _relax!(..., U::Matrix) src/SSSP/bfm.jl:113-159.  U2 is the

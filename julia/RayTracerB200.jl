@@ -19,7 +19,8 @@ export Grid2D, BellmanFordMoore, R, init_annulus, closest_point, interpolate_vel
        LinearInterpolation, bfm_batch, bfm_batch_multi, set_device, bfm_gpu, interpolate!, symrcm, nodal_degree,
        dual_velocity, SparseAdjencyList, sparse_adjacency_list, travel_times, set_schedule!, Grid3D, grid, coordinates, BFM,
        AbstractSPM, Dijkstra, RadiusStepping, dijkstra, radius_stepping, Point, connectivity, CartesianIndex,
-       polardistance3D, set_option!, GridPartition, partition_grid, directions, bfm_continue, bfm_multiphase
+       polardistance3D, set_option!, GridPartition, partition_grid, directions, bfm_continue, bfm_multiphase,
+       comm_unique_id, comm_init, comm_shard, comm_destroy, bfm_batch_sharded
 
 const R = 6371.0                                   # src/utils.jl:2
 const LIB = get(ENV, "RT_SSSP_LIB", joinpath(@__DIR__, "..", "raytracer.jl_b200", "librt_sssp.so"))
@@ -205,6 +206,44 @@ function bfm_batch_multi(grids::Vector, sources::Vector{Int64}, U::AbstractArray
     check(ccall((:rt_bfm_solve_multi, LIB), Cint,
                 (Ptr{Ptr{Cvoid}}, Cint, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
                 hs, length(hs), Vector{Float64}(U), sources, ns, precision, dist, prev, st))
+    return BellmanFordMoore(prev, dist), st[]
+end
+
+# many earthquakes with ONE PROCESS PER GPU (mpirun / Distributed.jl): rank 0 makes the 128-byte id with comm_unique_id()
+# and ships it to the other ranks by whatever the driver already has; every rank then calls
+#     set_device(local_rank); gr, G, halo = init_annulus(...); c = comm_init(id, rank, world)
+#     D, st = bfm_batch_sharded(c, G, halo, sources, gr, U)      # the full [n x nsrc] tables on every rank
+# rank r solves the contiguous block comm_shard(length(sources), r, world); the tables are gathered with one
+# ncclAllGather each over NVLink inside the library (rt_bfm_solve_sharded).
+mutable struct Comm
+    ptr::Ptr{Cvoid}
+end
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:rt_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    return id
+end
+function comm_init(id::Vector{UInt8}, rank::Integer, world::Integer)
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:rt_comm_init, LIB), Cint, (Ptr{UInt8}, Cint, Cint, Ref{Ptr{Cvoid}}), id, rank, world, c))
+    return Comm(c[])
+end
+function comm_shard(nsrc::Integer, rank::Integer, world::Integer)
+    first, count = Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:rt_comm_shard, LIB), Cint, (Int64, Cint, Cint, Ref{Int64}, Ref{Int64}), nsrc, rank, world, first, count))
+    return (first[] + 1):(first[] + count[])
+end
+comm_destroy(c::Comm) = (c.ptr != C_NULL && ccall((:rt_comm_destroy, LIB), Cint, (Ptr{Cvoid},), c.ptr); c.ptr = C_NULL; nothing)
+function bfm_batch_sharded(c::Comm, G::SparseMatrixCSC{Bool,Int64}, halo::Matrix, sources::Vector{Int64}, gr, U::AbstractArray;
+                           precision::Integer = 64)
+    h = mesh_handle(G, halo, gr)
+    n, ns = G.n, length(sources)
+    dist = Matrix{Float64}(undef, n, ns)
+    prev = Matrix{Int64}(undef, n, ns)
+    st = Ref(RtStats(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0.0, 0, 0))
+    check(ccall((:rt_bfm_solve_sharded_host, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Ptr{Int64}, Ref{RtStats}),
+                c.ptr, h.ptr, Vector{Float64}(U), sources, ns, precision, dist, prev, st))
     return BellmanFordMoore(prev, dist), st[]
 end
 

@@ -21,7 +21,7 @@ SYMBOLS = [
     "rt_bfm_solve_dev", "rt_bfm_solve_multi", "rt_bfm_solve_dual", "rt_dual_velocity", "rt_set_option", "rt_reconstruct_paths", "rt_reconstruct_paths_dev",
     "rt_grid3d_axes", "rt_grid3d_points", "rt_grid3d_connectivity", "rt_closest_point3d", "rt_polardistance3d",
     "rt_reconstruct_paths_guarded", "rt_travel_times", "rt_travel_times_dev", "rt_sssp_nodal", "rt_partition_grid", "rt_bfm_continue",
-    "rt_comm_unique_id", "rt_comm_init", "rt_comm_shard", "rt_bfm_solve_sharded", "rt_comm_destroy",
+    "rt_comm_unique_id", "rt_comm_init", "rt_comm_shard", "rt_bfm_solve_sharded", "rt_bfm_solve_sharded_host", "rt_comm_destroy",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
     L.rt_comm_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(VP)]
     L.rt_comm_shard.argtypes = [I64, C.c_int, C.c_int, C.POINTER(I64), C.POINTER(I64)]
     L.rt_bfm_solve_sharded.argtypes = [VP, VP, VP, I64P, I64, C.c_int, VP, VP, C.POINTER(RtStats)]
+    L.rt_bfm_solve_sharded_host.argtypes = [VP, VP, F64P, I64P, I64, C.c_int, VP, VP, C.POINTER(RtStats)]
     L.rt_comm_destroy.argtypes = [VP]
     L.rt_partition_grid.argtypes = [VP, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
     L.rt_bfm_continue.argtypes = [VP, F64P, VP, I64P, I64, F64P, I64P, C.POINTER(RtStats)]

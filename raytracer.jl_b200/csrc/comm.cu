@@ -77,6 +77,8 @@ struct rt_comm {
   int rank = 0, world = 1, device = 0;
   DevBuf<double> gd;  // padded gather buffers (only when nsrc is not a multiple of the world size)
   DevBuf<i32> gp;
+  DevBuf<double> hU, hd;  // staging of the host-buffer front (rt_bfm_solve_sharded_host)
+  DevBuf<i32> hp;
 };
 
 extern "C" {
@@ -187,6 +189,25 @@ int rt_bfm_solve_sharded(rt_comm* c, rt_mesh* m, const double* U_dev, const int6
     *stats = st;
     stats->prev_ms = gather_ms;  // this entry point reports the gather time here (the local solve's prev pass is in kernel_ms)
   }
+  return RT_OK;
+}
+
+// Host-buffer front of rt_bfm_solve_sharded for callers that hold no device memory (a plain Julia process): U in,
+// gathered tables out ([nsrc x n], 1-based int64 predecessors, 0 = never set, as rt_bfm_solve returns them).
+int rt_bfm_solve_sharded_host(rt_comm* c, rt_mesh* m, const double* U, const int64_t* sources, int64_t nsrc,
+                              int precision, double* dist_out, int64_t* prev_out, rt_stats* stats) {
+  RT_ARG(c && m && U && sources && nsrc >= 0 && dist_out, "null argument");
+  RT_CUDA(cudaSetDevice(m->device));
+  i64 sizes[8];
+  RT_TRY(rt_mesh_sizes(m, sizes));
+  const i64 n = sizes[0];
+  if (c->hU.n != (size_t)n) RT_TRY(c->hU.alloc(n));
+  if (c->hd.n < (size_t)(nsrc * n)) RT_TRY(c->hd.alloc(nsrc * n));
+  if (prev_out && c->hp.n < (size_t)(nsrc * n)) RT_TRY(c->hp.alloc(nsrc * n));
+  RT_CUDA(cudaMemcpy(c->hU.p, U, n * sizeof(double), cudaMemcpyHostToDevice));
+  RT_TRY(rt_bfm_solve_sharded(c, m, c->hU.p, sources, nsrc, precision, c->hd.p, prev_out ? c->hp.p : nullptr, stats));
+  RT_CUDA(cudaMemcpy(dist_out, c->hd.p, (size_t)nsrc * n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (prev_out) RT_TRY(prev_to_host_i64(c->hp.p, nsrc * n, prev_out, m->stream));
   return RT_OK;
 }
 

@@ -183,9 +183,15 @@ def test_library_sharded_solve_single_rank(rt, O, annulus, ak135):
     st = rt.RtStats()
     rt.api.check(rt.lib().rt_bfm_solve_sharded(comm, h.h, U.data_ptr(), srcs, len(srcs), 64, d.data_ptr(), p.data_ptr(),
                                                C.byref(st)))
+    # the host-buffer front (what a plain Julia process calls): 1-based int64 predecessors like rt_bfm_solve
+    dh = np.empty((len(srcs), m.n), np.float64)
+    ph = np.empty((len(srcs), m.n), np.int64)
+    rt.api.check(rt.lib().rt_bfm_solve_sharded_host(comm, h.h, np.ascontiguousarray(Vp), srcs, len(srcs), 64,
+                                                    dh.ctypes.data, ph.ctypes.data, C.byref(st)))
     rt.api.check(rt.lib().rt_comm_destroy(comm))
     D = rt.bfm(G, halo, srcs, gr, Vp, schedule="near-far")
     assert np.array_equal(d.cpu().numpy(), D.dist)
+    assert np.array_equal(dh, D.dist) and np.array_equal(ph, p.cpu().numpy().astype(np.int64) + 1)
     for k, s in enumerate(srcs):
         assert np.array_equal(D.dist[k], O.bfm(m, Vp, int(s))[0])
     h.set_option("schedule", 0)
