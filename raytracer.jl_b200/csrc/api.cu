@@ -462,6 +462,8 @@ int rt_set_option(rt_mesh* m, const char* key, double value) {
     m->opts.canonical_prev = value != 0.0;
   } else if (!std::strcmp(key, "early_advance")) {
     m->opts.early_advance = value;
+  } else if (!std::strcmp(key, "fuse_begin")) {
+    m->opts.fuse_begin = value != 0.0;
   } else if (!std::strcmp(key, "tile_pull")) {
     m->opts.tile_pull = value != 0.0;
   } else if (!std::strcmp(key, "delta_factor")) {

@@ -79,6 +79,7 @@ struct PP {
   // the near-list slots of the sources that push this round, flat[FLAT_STRIDE + (0 .. nb)] = the same for the far-list
   // slots of the sources whose threshold advances.  One launch then serves all sources with perfect load balance.
   i64* flat;
+  unsigned* ticket;  // finished CTAs of the kernel that carries the round control in its tail (round_tail)
   // short-column meshes: de-duplicated target list per work item (first occurrences of the column's scan list, scan
   // order kept): a node shared by several elements of the column is visited once per released item.  tgt_off == null:
   // not built; an empty list = this item walks its elements (column too long for the builder).
@@ -1307,6 +1308,80 @@ __global__ void prev_halo_init_kernel(PP pb, const i32* __restrict__ hnode, cons
 // after_far: the far kernels were enqueued between the previous round_begin and this one.  They are only enqueued
 // every FAR_EVERY-th round (in most rounds they have nothing to do), so a source whose threshold advance has been
 // requested (mode 2) stays put -- prep / push return at once -- until a round_begin that follows them.
+// The round control for nb <= 32 sources, executed by ONE full warp (lane = source).  Used by round_begin_kernel<32> and by
+// round_tail below; counters / tau are read past the L1 (the tail runs at the end of a kernel whose other CTAs updated
+// them with atomics).
+__device__ __forceinline__ void round_begin_warp(const PP& pb, int after_far) {
+  const int b = threadIdx.x & 31;
+  i64 cn = 0, cf = 0;
+  if (b < pb.nb) {
+    const PP p = pp_view(pb, b);
+    int* c = p.ctl;
+    if (!c[3] && !(c[2] == 2 && !after_far)) {
+      if (c[2] == 1)
+        c[0] ^= 1;
+      else if (c[2] == 2)
+        c[1] ^= 1;
+      const int cur = c[0], fcur = c[1];
+      const u64 n_near = __ldcg(&p.counters[cur]), n_far = __ldcg(&p.counters[4 + fcur]);
+      if (n_near == 0 && n_far == 0) {
+        c[2] = 0;
+        c[3] = 1;
+      } else {
+        c[4] += 1;
+        if (n_near > 0) {
+          c[2] = 1;
+          c[5] += 1;
+          p.counters[cur ^ 1] = 0;
+        } else {
+          c[2] = 2;
+          p.tau[2] = __longlong_as_double(-1LL);
+          p.counters[4 + (fcur ^ 1)] = 0;
+        }
+      }
+    }
+    if (!c[3]) {
+      if (c[2] == 1) cn = (i64)__ldcg(&p.counters[c[0]]);
+      if (c[2] == 2) cf = (i64)__ldcg(&p.counters[4 + c[1]]);
+    }
+  }
+  i64 in = cn, fi = cf;
+  for (int o = 1; o < 32; o <<= 1) {
+    const i64 a = __shfl_up_sync(FULL, in, o), f = __shfl_up_sync(FULL, fi, o);
+    if (b >= o) {
+      in += a;
+      fi += f;
+    }
+  }
+  if (b < pb.nb) {
+    pb.flat[b + 1] = in;
+    pb.flat[FLAT_STRIDE + b + 1] = fi;
+  }
+  if (b == 0) {
+    pb.flat[0] = 0;
+    pb.flat[FLAT_STRIDE] = 0;
+  }
+}
+// Round control folded into the tail of the kernel that precedes it (option fuse_begin, nb <= 32): the last CTA to finish
+// runs round_begin for the coming round, which saves one launch per round.  tail < 0: nothing; otherwise tail = the
+// after_far argument.  Every thread of every CTA must reach this call.  Measured (B200, graph replay): SLOWER than the
+// one-warp kernel of its own -- config[1] 1.159 s against 1.136 s per source, annulus 180x50 @1 km 91.5 against 88.8 ms:
+// the ticket atomics of ~2400 CTAs and the serial control at the very end of the push cost more than a launch inside
+// a graph.  Kept behind the option (default off).
+__device__ __forceinline__ void round_tail(const PP& pb, int tail) {
+  if (tail < 0) return;
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(pb.ticket, 1u) == gridDim.x * gridDim.y - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 32) round_begin_warp(pb, tail);
+  if (threadIdx.x == 0) *pb.ticket = 0u;
+}
 template <int BS>
 __global__ void __launch_bounds__(BS) round_begin_kernel(PP pb, int after_far) {
   const int b = threadIdx.x;
@@ -1401,7 +1476,7 @@ __global__ void prep_dc_kernel(PP pb) {
 #define RT_PUSH_MINB 5
 #endif
 template <bool WARP, int MODE>
-__global__ void __launch_bounds__(PUSH_BLOCK, RT_PUSH_MINB) push2d_dc_kernel(PP pb) {
+__global__ void __launch_bounds__(PUSH_BLOCK, RT_PUSH_MINB) push2d_dc_kernel(PP pb, int tail) {
   if (WARP) {
     // warp-level units of ALL sources in one flat index space (slot g of the concatenated near lists)
     constexpr bool DUAL = MODE == MODE_DUAL;
@@ -1432,10 +1507,12 @@ __global__ void __launch_bounds__(PUSH_BLOCK, RT_PUSH_MINB) push2d_dc_kernel(PP 
     }
   } else {
     const PP p = pp_view(pb, blockIdx.y);
-    if (p.ctl[2] != 1) return;
-    const int cur = p.ctl[0], fcur = p.ctl[1];
-    push2d_body<WARP, MODE>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
+    if (p.ctl[2] == 1) {
+      const int cur = p.ctl[0], fcur = p.ctl[1];
+      push2d_body<WARP, MODE>(p, nq(p, cur), cur, nq(p, cur ^ 1), fq(p, fcur), fcur);
+    }
   }
+  round_tail(pb, tail);
 }
 // rare path of the kernel below, kept out of line so that it does not cost the common path registers
 template <int MODE>
@@ -1454,7 +1531,7 @@ __device__ __noinline__ void push2d_walk_fallback(const PP& pb, int b, int it, u
 #define RT_TGT_MINB 8
 #endif
 template <int MODE>
-__global__ void __launch_bounds__(PUSH_BLOCK, RT_TGT_MINB) push2d_tgt_dc_kernel(PP pb) {
+__global__ void __launch_bounds__(PUSH_BLOCK, RT_TGT_MINB) push2d_tgt_dc_kernel(PP pb, int tail) {
   constexpr bool DUAL = MODE == MODE_DUAL;
   __shared__ double2 w_sxz[PUSH_BLOCK / 32][32], w_sUd[PUSH_BLOCK / 32][32], w_sU2r[DUAL ? PUSH_BLOCK / 32 : 1][32];
   __shared__ int w_id[PUSH_BLOCK / 32][32], w_pre[PUSH_BLOCK / 32][32], w_start[PUSH_BLOCK / 32][32];
@@ -1486,6 +1563,7 @@ __global__ void __launch_bounds__(PUSH_BLOCK, RT_TGT_MINB) push2d_tgt_dc_kernel(
       push2d_tgt_unit<false, MODE>(p, it, mask, t0, t1, cur, nq(p, cur ^ 1), fq(p, fcur), fcur, tau, w_sxz[warp], w_sUd[warp],
                                    w_sU2r[DUAL ? warp : 0], w_id[warp]);
   }
+  round_tail(pb, tail);
 }
 
 // threshold advance over the concatenated far lists of the advancing sources: THREAD per far-list slot (an item of a
@@ -1528,7 +1606,7 @@ __global__ void far_min_dc_kernel(PP pb) {
     }
   }
 }
-__global__ void far_release_dc_kernel(PP pb) {
+__global__ void far_release_dc_kernel(PP pb, int tail) {
   const int nb = pb.nb;
   const i64* base = pb.flat + FLAT_STRIDE;
   const i64 total = base[nb];
@@ -1582,6 +1660,7 @@ __global__ void far_release_dc_kernel(PP pb) {
       if (first_pend) ((cur ? pb.nearq1 : pb.nearq0) + o)[atomicAdd(&pb.counters[(i64)b * 8 + cur], 1ull)] = it;
     }
   }
+  round_tail(pb, tail);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1788,7 +1867,7 @@ int ensure_push_workspace(rt_mesh* h, int nb, bool packed, bool need_bdist) {
     m.dp.release();
     m.push_nb = nb;
   }
-  if (!m.flat.p) RT_TRY(m.flat.alloc(2 * FLAT_STRIDE));
+  if (!m.flat.p) RT_TRY(m.flat.alloc(2 * FLAT_STRIDE + 2));  // + the ticket word of round_tail
   {
     const size_t want = m.push_nb > 1 ? (size_t)std::min<i64>((i64)m.push_nb * m.n_items, (i64)1 << 27) : 1;
     if (m.flat_b.n < want) RT_TRY(m.flat_b.alloc(want));
@@ -1810,21 +1889,21 @@ const void* persistent_kernel_for(bool warp, int mode) {
   if (mode == MODE_F32) return (const void*)nearfar_persistent_kernel<false, MODE_F32>;
   return (const void*)nearfar_persistent_kernel<false, MODE_F64>;
 }
-void launch_push_dc(bool warp, int mode, dim3 grid, cudaStream_t s, const PP& p) {
+void launch_push_dc(bool warp, int mode, dim3 grid, cudaStream_t s, const PP& p, int tail) {
   if (warp) {
     if (mode == MODE_DUAL)
-      push2d_dc_kernel<true, MODE_DUAL><<<grid, PUSH_BLOCK, 0, s>>>(p);
+      push2d_dc_kernel<true, MODE_DUAL><<<grid, PUSH_BLOCK, 0, s>>>(p, tail);
     else if (mode == MODE_F32)
-      push2d_dc_kernel<true, MODE_F32><<<grid, PUSH_BLOCK, 0, s>>>(p);
+      push2d_dc_kernel<true, MODE_F32><<<grid, PUSH_BLOCK, 0, s>>>(p, tail);
     else
-      push2d_dc_kernel<true, MODE_F64><<<grid, PUSH_BLOCK, 0, s>>>(p);
+      push2d_dc_kernel<true, MODE_F64><<<grid, PUSH_BLOCK, 0, s>>>(p, tail);
   } else {
     if (mode == MODE_DUAL)
-      push2d_dc_kernel<false, MODE_DUAL><<<grid, PUSH_BLOCK, 0, s>>>(p);
+      push2d_dc_kernel<false, MODE_DUAL><<<grid, PUSH_BLOCK, 0, s>>>(p, tail);
     else if (mode == MODE_F32)
-      push2d_dc_kernel<false, MODE_F32><<<grid, PUSH_BLOCK, 0, s>>>(p);
+      push2d_dc_kernel<false, MODE_F32><<<grid, PUSH_BLOCK, 0, s>>>(p, tail);
     else
-      push2d_dc_kernel<false, MODE_F64><<<grid, PUSH_BLOCK, 0, s>>>(p);
+      push2d_dc_kernel<false, MODE_F64><<<grid, PUSH_BLOCK, 0, s>>>(p, tail);
   }
 }
 
@@ -1916,6 +1995,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
   p.nb = 1;
   p.warp_units = warp_units;
   p.flat = m.flat.p;
+  p.ticket = reinterpret_cast<unsigned*>(m.flat.p + 2 * FLAT_STRIDE);
   p.flat_b = m.flat_b.p;
   p.flat_cap = (i64)m.flat_b.n;
   p.cta_units = h->opts.cta_units;
@@ -2066,30 +2146,39 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
       // the R-round launch sequence is the same every time (which phase runs is decided on the device): it is captured
       // once into a CUDA graph and replayed, which removes the per-launch host cost and most of the inter-kernel gaps
       i64 seq_launches = 0;
+      const bool fused = h->opts.fuse_begin != 0 && B <= 32;
+      cudaMemsetAsync(p.ticket, 0, sizeof(unsigned), s);
       auto enqueue_rounds = [&](cudaStream_t q) {
         int af = 1;  // nothing is pending before the first round; the last round of a sequence always runs the far kernels
         seq_launches = 0;
         for (int r = 0; r < R; ++r) {
-          if (B <= 32)
-            round_begin_kernel<32><<<1, 32, 0, q>>>(p, af);
-          else
-            round_begin_kernel<MAX_NB><<<1, MAX_NB, 0, q>>>(p, af);
+          // fused: the round control of round r + 1 runs in the tail of the last kernel of round r (round_tail); only
+          // the first round of the sequence launches it as a kernel of its own
+          const bool far_now = r % FAR_EVERY == FAR_EVERY - 1 || r == R - 1;
+          if (!fused || r == 0) {
+            if (B <= 32)
+              round_begin_kernel<32><<<1, 32, 0, q>>>(p, af);
+            else
+              round_begin_kernel<MAX_NB><<<1, MAX_NB, 0, q>>>(p, af);
+            seq_launches += 1;
+          }
           prep_dc_kernel<<<gsmall, 256, 0, q>>>(p);
+          const int ptail = fused && !far_now ? 0 : -1;
           if (p.tgt_off) {  // (items without a list are walked inside the same kernel, out of line)
             if (mode == MODE_DUAL)
-              push2d_tgt_dc_kernel<MODE_DUAL><<<gpush, PUSH_BLOCK, 0, q>>>(p);
+              push2d_tgt_dc_kernel<MODE_DUAL><<<gpush, PUSH_BLOCK, 0, q>>>(p, ptail);
             else if (mode == MODE_F32)
-              push2d_tgt_dc_kernel<MODE_F32><<<gpush, PUSH_BLOCK, 0, q>>>(p);
+              push2d_tgt_dc_kernel<MODE_F32><<<gpush, PUSH_BLOCK, 0, q>>>(p, ptail);
             else
-              push2d_tgt_dc_kernel<MODE_F64><<<gpush, PUSH_BLOCK, 0, q>>>(p);
+              push2d_tgt_dc_kernel<MODE_F64><<<gpush, PUSH_BLOCK, 0, q>>>(p, ptail);
           } else {
-            launch_push_dc(p.warp_units != 0, mode, gpush, q, p);
+            launch_push_dc(p.warp_units != 0, mode, gpush, q, p, ptail);
           }
-          seq_launches += 3;
+          seq_launches += 2;
           af = 0;
-          if (r % FAR_EVERY == FAR_EVERY - 1 || r == R - 1) {
+          if (far_now) {
             far_min_dc_kernel<<<gfar, 256, 0, q>>>(p);
-            far_release_dc_kernel<<<gfar, 256, 0, q>>>(p);
+            far_release_dc_kernel<<<gfar, 256, 0, q>>>(p, fused && r < R - 1 ? 1 : -1);
             seq_launches += 2;
             af = 1;
           }
@@ -2099,7 +2188,7 @@ int bfm2d_solve_push_impl(rt_mesh* h, const double* U_dev, bool dual_arg, const 
       if (h->opts.use_graph) {
         std::vector<char> key(sizeof(PP) + 4 * sizeof(int));
         std::memcpy(key.data(), &p, sizeof(PP));
-        const int kv[4] = {B, mode, R, (int)gpush.x};
+        const int kv[4] = {B, mode, R + (fused ? 1 << 16 : 0), (int)gpush.x};
         std::memcpy(key.data() + sizeof(PP), kv, sizeof(kv));
         if (m.round_graph && key != m.round_graph_key) {
           cudaGraphExecDestroy((cudaGraphExec_t)m.round_graph);

@@ -873,12 +873,16 @@ def test_near_far_option_matrix(rt, O, annulus, ak135):
     srcs = [O.closest_point(m.theta, m.r, 0.0, R), m.n // 2, 5]
     want = [O.bfm(m, Vp, s) for s in srcs]
     defaults = dict(profile_timers=0, check_every=0, cta_units=0, warp_units=-1, batch=0, packed_prev=1, persistent=-1,
-                    delta_factor=0.0)
+                    delta_factor=0.0, fuse_begin=0, use_graph=1, target_lists=1)
     combos = [dict(persistent=1, warp_units=1), dict(persistent=1, warp_units=0), dict(persistent=0, warp_units=1),
               dict(persistent=0, warp_units=0), dict(persistent=0, warp_units=0, check_every=4),
               dict(persistent=0, warp_units=0, cta_units=1), dict(profile_timers=1, warp_units=0),
               dict(profile_timers=1, warp_units=1), dict(packed_prev=0), dict(packed_prev=0, persistent=0),
-              dict(batch=2), dict(batch=1), dict(delta_factor=0.25), dict(delta_factor=16.0)]
+              dict(batch=2), dict(batch=1), dict(delta_factor=0.25), dict(delta_factor=16.0),
+              # round control as a kernel of its own / in the tail of the preceding kernel, with and without graph replay
+              dict(persistent=0, fuse_begin=1), dict(persistent=0, fuse_begin=1, use_graph=0),
+              dict(persistent=0, warp_units=0, fuse_begin=1, check_every=5),
+              dict(persistent=0, target_lists=0, fuse_begin=1), dict(persistent=0, target_lists=0, use_graph=0)]
     try:
         for combo in combos:
             for k, v in {**defaults, **combo}.items():

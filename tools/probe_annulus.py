@@ -34,6 +34,7 @@ for (nt, nr, sp) in meshes:
     h.set_option("group_screen", int(os.environ.get("RT_GROUP_SCREEN", "1")))
     h.set_option("compact", int(os.environ.get("RT_COMPACT", "1")))
     h.set_option("use_graph", int(os.environ.get("RT_GRAPH", "1")))
+    h.set_option("fuse_begin", int(os.environ.get("RT_FUSE", "1")))
     d = torch.empty(n, dtype=torch.float64, device="cuda")
     p = torch.empty(n, dtype=torch.int32, device="cuda")
     ref = None
