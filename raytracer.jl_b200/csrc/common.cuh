@@ -105,7 +105,8 @@ struct SolverOpts {
   double early_advance = -1.0;  // near-far 3-D tile-pull: threshold advances early when a round releases fewer than
                                 // early_advance x n^(2/3) nodes (-1 = default, 0 = never)
   int fuse_begin = 0;      // near-far 2-D launch sequence (<= 32 sources): 1 = round control in the tail of the preceding
-                           // kernel instead of a launch of its own (measured slower: config[1] 1.159 s against 1.136 s)
+                           // kernel instead of a launch of its own (measured slower: config[1] 1.159 s against 1.136 s);
+                           // 3-D tile-pull rounds: 1 = the last CTA of tp_pull does the round control, 0 = tp_ctl_kernel
   int tile_pull = 1;       // near-far 3-D: 1 = tile-pull rounds (targets pull from released sources, no atomics), 0 = push units
 };
 

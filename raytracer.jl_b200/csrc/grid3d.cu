@@ -958,6 +958,7 @@ struct T3 {
   int nx, ny, nz, tnx, tny, tnz;
   i64 n_tiles;
   int w, self, wmode, count;
+  int ctl_tail;  // 1: the last CTA of tp_pull does the round control, 0: tp_ctl_kernel does
   u64 early;  // releases per round below which the threshold advances although the bucket is not empty
   FastDiv fd_tnx, fd_tny, fd_SY;
 };
@@ -1073,6 +1074,32 @@ __global__ void __launch_bounds__(TPR_BLOCK) tp_release_kernel(T3 p) {
     if (nrel) atomicAdd(&p.counters[1], (u64)nrel);
     if (evals) atomicAdd(&p.counters[2], evals);
   }
+}
+
+// end of a round: threshold advance to min(pending) + delta when nothing was released, termination, counters reset
+__device__ __forceinline__ void tp_round_control(const T3& p) {
+  const u64 n_rel = __ldcg(&p.counters[1]);
+  const u64 mp = __ldcg(&p.counters[7]);
+  p.ctl[4] += 1;
+  if (n_rel > 0) {
+    p.ctl[5] += 1;
+    p.counters[3] += n_rel;
+    p.counters[5] += __ldcg(&p.counters[0]);
+    // the tail of a bucket (a few stragglers per round) may share its rounds with the head of the next bucket: any
+    // release order reaches the same fixed point (option early_advance)
+    if (n_rel < p.early && mp != ~0ull) {
+      const double t2 = __dadd_rn(__longlong_as_double((long long)mp), p.tau[1]);
+      if (t2 > p.tau[0]) p.tau[0] = t2;
+    }
+  } else if (mp != ~0ull) {
+    p.tau[0] = __dadd_rn(__longlong_as_double((long long)mp), p.tau[1]);
+  } else {
+    p.ctl[3] = 1;
+  }
+  p.ctl[0] += 1;
+  p.counters[0] = 0ull;
+  p.counters[1] = 0ull;
+  p.counters[7] = ~0ull;
 }
 
 // dynamic smem: 5 * SN doubles (travel time, X, Y, Z, U of the released cells of tile + halo) + SY * SZ row masks +
@@ -1217,6 +1244,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tp_pull_kernel(T3 p) {
       atomicAdd(&p.counters[9], exact);
     }
   }
+  if (!p.ctl_tail) return;  // the round control runs as a kernel of its own (tp_ctl_kernel)
   // round control by the last CTA to finish
   __syncthreads();
   if (tid == 0) {
@@ -1224,32 +1252,17 @@ __global__ void __launch_bounds__(TILE_THREADS) tp_pull_kernel(T3 p) {
     const u64 ticket = atomicAdd(&p.counters[4], 1ull);
     if (ticket == (u64)gridDim.x - 1ull) {
       __threadfence();
-      const u64 n_rel = __ldcg(&p.counters[1]);
-      const u64 mp = __ldcg(&p.counters[7]);
-      p.ctl[4] += 1;
-      if (n_rel > 0) {
-        p.ctl[5] += 1;
-        p.counters[3] += n_rel;
-        p.counters[5] += __ldcg(&p.counters[0]);
-        // the tail of a bucket (a few stragglers per round) shares its rounds with the head of the next bucket: any
-        // release order reaches the same fixed point
-        if (n_rel < p.early && mp != ~0ull) {
-          const double t2 = __dadd_rn(__longlong_as_double((long long)mp), p.tau[1]);
-          if (t2 > p.tau[0]) p.tau[0] = t2;
-        }
-      } else if (mp != ~0ull) {
-        p.tau[0] = __dadd_rn(__longlong_as_double((long long)mp), p.tau[1]);
-      } else {
-        p.ctl[3] = 1;
-      }
-      p.ctl[0] += 1;
-      p.counters[0] = 0ull;
-      p.counters[1] = 0ull;
+      tp_round_control(p);
       p.counters[4] = 0ull;
-      p.counters[7] = ~0ull;
       __threadfence();
     }
   }
+}
+
+// the round control as a one-thread kernel (option ctl_tail = 0): no ticket atomics in the pull kernel
+__global__ void tp_ctl_kernel(T3 p) {
+  if (p.ctl[3]) return;
+  tp_round_control(p);
 }
 
 __global__ void tp_init_kernel(T3 p, i32* __restrict__ prev, i64 n, i64 source, double delta) {
@@ -1318,6 +1331,7 @@ int bfm3d_solve_pull(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   p.self = g.self;
   p.wmode = h->opts.weight3d;
   p.count = h->opts.profile_timers != 0;
+  p.ctl_tail = h->opts.fuse_begin != 0;
   p.early = (u64)((h->opts.early_advance >= 0.0 ? h->opts.early_advance : TP_EARLY) * std::pow((double)g.n, 2.0 / 3.0));
   p.fd_tnx = FastDiv((unsigned)g.tn[0]);
   p.fd_tny = FastDiv((unsigned)g.tn[1]);
@@ -1383,6 +1397,7 @@ int bfm3d_solve_pull(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       else
         tp_pull_kernel<false><<<gpull, TILE_THREADS, smem, qs>>>(p);
       if (timers) cudaEventRecord(evr1, qs);
+      if (!p.ctl_tail) tp_ctl_kernel<<<1, 1, 0, qs>>>(p);
     }
   };
   cudaGraphExec_t gexec = nullptr;
@@ -1441,7 +1456,7 @@ int bfm3d_solve_pull(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
       } else {
         enqueue_rounds(s);
       }
-      st.total_launches += 2 * R;
+      st.total_launches += (p.ctl_tail ? 2 : 3) * R;
       enq_rounds += R;
       if (enq_rounds > ((i64)1 << 22)) {  // a solve needs 1e2 - 1e4 rounds: never spin forever on a logic error
         rt_set_error("near-far schedule did not converge within %lld rounds", (long long)enq_rounds);

@@ -33,6 +33,7 @@ for nn in sizes:
     h.set_option("profile_timers", int(os.environ.get("RT_TIMERS", "0")))
     h.set_option("check_every", int(os.environ.get("RT_CHECK_EVERY", "0")))
     h.set_option("use_graph", int(os.environ.get("RT_GRAPH", "1")))
+    h.set_option("fuse_begin", int(os.environ.get("RT_FUSE", "0")))
     for mode in modes:
         name, _, df = mode.partition(":")
         df, _, ea = df.partition(":")
