@@ -360,6 +360,26 @@ int prev_to_host_i64_staged(const i32* prev_dev, i64 count, i64* out, i64* stage
 
 // prev_dev: 0-based int32 table on the device.  receivers: host, 1-based.  guarded = 1: the struct method
 // recontruct_path(D, source, receiver) (ssspm.jl:14-28) instead of the vector method (:30-40).
+// Scratch of the path sweeps, kept per host thread and device: a receiver sweep makes two calls per source, and four
+// cudaMalloc / cudaFree pairs per call cost more than the pointer chase itself (measured: up to 46 ms per call once other
+// libraries have grown the process's address space, against 0.3 ms of kernels).  The work stays on the legacy default
+// stream: a caller that filled prev_dev on its own (blocking) stream keeps the implicit ordering it had.
+namespace {
+struct PathScratch {
+  int device = -1;
+  DevBuf<i32> recv;
+  DevBuf<i64> len, off, out;
+};
+thread_local PathScratch g_paths;
+template <typename T>
+int grow(DevBuf<T>& b, size_t count) {
+  if (b.n >= count && b.p) return RT_OK;
+  size_t cap = 1024;
+  while (cap < count) cap *= 2;
+  return b.alloc(cap);
+}
+}  // namespace
+
 int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* receivers, i64 nrec,
                              i64* path_off, i64* path_idx, i64 cap, int guarded) {
   RT_ARG(prev_dev && receivers && path_off && nrec >= 0, "bad path arguments");
@@ -369,19 +389,30 @@ int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* 
     RT_ARG(receivers[k] >= 1 && receivers[k] <= n, "receiver out of range");
     r32[k] = (i32)(receivers[k] - 1);
   }
-  DevBuf<i32> recv;
-  DevBuf<i64> len;
-  RT_TRY(recv.upload(r32.data(), nrec));
-  RT_TRY(len.alloc(nrec));
+  PathScratch& ps = g_paths;
+  int dev = 0;
+  RT_CUDA(cudaGetDevice(&dev));
+  if (ps.device != dev) {  // another device is current on this thread: the scratch lives where the table lives
+    ps.recv.release();
+    ps.len.release();
+    ps.off.release();
+    ps.out.release();
+    ps.device = dev;
+  }
+  cudaStream_t s = cudaStreamLegacy;
+  RT_TRY(grow(ps.recv, (size_t)nrec));
+  RT_TRY(grow(ps.len, (size_t)nrec));
   if (nrec) {
+    RT_CUDA(cudaMemcpyAsync(ps.recv.p, r32.data(), nrec * sizeof(i32), cudaMemcpyHostToDevice, s));
     if (guarded)
-      path_len_guarded_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, n, recv.p, nrec, len.p);
+      path_len_guarded_kernel<<<grid_for(nrec, 128), 128, 0, s>>>(prev_dev, n, ps.recv.p, nrec, ps.len.p);
     else
-      path_len_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, n, (i32)(source - 1), recv.p, nrec, len.p);
+      path_len_kernel<<<grid_for(nrec, 128), 128, 0, s>>>(prev_dev, n, (i32)(source - 1), ps.recv.p, nrec, ps.len.p);
   }
   RT_CUDA(cudaGetLastError());
   std::vector<i64> hl(nrec);
-  RT_CUDA(cudaMemcpy(hl.data(), len.p, nrec * sizeof(i64), cudaMemcpyDeviceToHost));
+  if (nrec) RT_CUDA(cudaMemcpyAsync(hl.data(), ps.len.p, nrec * sizeof(i64), cudaMemcpyDeviceToHost, s));
+  RT_CUDA(cudaStreamSynchronize(s));
   path_off[0] = 0;
   for (i64 k = 0; k < nrec; ++k) {
     if (hl[k] < 0) {
@@ -395,15 +426,16 @@ int reconstruct_paths_device(const i32* prev_dev, i64 n, i64 source, const i64* 
   if (!path_idx) return RT_OK;
   RT_ARG(cap >= path_off[nrec], "path_idx capacity too small");
   if (nrec == 0) return RT_OK;
-  DevBuf<i64> off, out;
-  RT_TRY(off.upload(path_off, nrec + 1));
-  RT_TRY(out.alloc(path_off[nrec]));
+  RT_TRY(grow(ps.off, (size_t)nrec + 1));
+  RT_TRY(grow(ps.out, (size_t)std::max<i64>(path_off[nrec], 1)));
+  RT_CUDA(cudaMemcpyAsync(ps.off.p, path_off, (nrec + 1) * sizeof(i64), cudaMemcpyHostToDevice, s));
   if (guarded)
-    path_fill_guarded_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, (i32)(source - 1), recv.p, nrec, off.p, out.p);
+    path_fill_guarded_kernel<<<grid_for(nrec, 128), 128, 0, s>>>(prev_dev, (i32)(source - 1), ps.recv.p, nrec, ps.off.p, ps.out.p);
   else
-    path_fill_kernel<<<grid_for(nrec, 128), 128>>>(prev_dev, (i32)(source - 1), recv.p, nrec, off.p, out.p);
+    path_fill_kernel<<<grid_for(nrec, 128), 128, 0, s>>>(prev_dev, (i32)(source - 1), ps.recv.p, nrec, ps.off.p, ps.out.p);
   RT_CUDA(cudaGetLastError());
-  RT_CUDA(cudaMemcpy(path_idx, out.p, path_off[nrec] * sizeof(i64), cudaMemcpyDeviceToHost));
+  RT_CUDA(cudaMemcpyAsync(path_idx, ps.out.p, path_off[nrec] * sizeof(i64), cudaMemcpyDeviceToHost, s));
+  RT_CUDA(cudaStreamSynchronize(s));
   return RT_OK;
 }
 
