@@ -74,7 +74,12 @@ int rt_mesh_export(const rt_mesh* m, double* x, double* z, double* theta, double
 
 /* Adopt a graph that was built elsewhere (by the reference in Julia, or by a test):  the arrays that
  * bfm(G, halo, source, gr, U) reads -- G.colptr/G.rowval, gr.e2n (flattened), gr.x, gr.z, halo.
- * theta / r may be NULL (only needed by rt_mesh_export and rt_closest_point). */
+ * theta / r may be NULL (only needed by rt_mesh_export and rt_closest_point).
+ * Precondition: the node neighbourhood N(i) = union of e2n[e] over the column e of G[:, i] is SYMMETRIC (j in N(i) <=>
+ * i in N(j)), as every graph of init_annulus is.  The solver's frontier is element-granular (a superset of the
+ * reference's per-node queue) and the near-far schedule pushes i -> j along the same lists that the reference pulls
+ * j <- i; on an asymmetric graph sweeps, predecessors and even travel times could differ from the reference's queue
+ * semantics.  Ids must be in range (checked on the 64-bit values before narrowing); the symmetry is not checked. */
 int rt_mesh_from_arrays(int64_t n, int64_t nel, const int64_t* e2n_off, const int64_t* e2n_idx,
                         const int64_t* G_colptr, const int64_t* G_rowval, const int64_t* halo, int64_t halo_rows,
                         const double* x, const double* z, const double* theta, const double* r, rt_mesh** out);
