@@ -119,7 +119,7 @@ def closest_point(a, b, pa, pb):
                                        float(pb)))
 
 
-def bfm(mesh, U, source, nthreads=1, max_sweeps=0):
+def bfm(mesh, U, source, nthreads=None, max_sweeps=0):
     """bfm(G, halo, source, gr, U) (src/SSSP/bfm.jl:1-52). Returns dist, prev (1-based, 0 = never set), stats."""
     n = mesh.n
     dist = np.zeros(n)
@@ -128,14 +128,14 @@ def bfm(mesh, U, source, nthreads=1, max_sweeps=0):
     halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
     rc = lib().ora_bfm(n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.G_colptr, mesh.G_rowval, halo,
                        mesh.halo_rows, mesh.x, mesh.z, np.ascontiguousarray(U, np.float64), int(source),
-                       int(nthreads), int(max_sweeps), dist, prev, stats)
+                       _nt(nthreads), int(max_sweeps), dist, prev, stats)
     if rc:
         raise ValueError("bad source")
     return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
                             graph_edges=int(stats[3]))
 
 
-def bfm_f32(mesh, U, source, nthreads=1):
+def bfm_f32(mesh, U, source, nthreads=None):
     """Float32 comparison path (src/SSSP/bfm_gpu.jl:170-205, 487-526): x, z, U cast to Float32, travel times relaxed
     in Float32.  Returns the Float32 travel times widened to float64, prev, stats."""
     n = mesh.n
@@ -145,7 +145,7 @@ def bfm_f32(mesh, U, source, nthreads=1):
     halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
     rc = lib().ora_bfm_f32(n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.G_colptr, mesh.G_rowval, halo,
                            mesh.halo_rows, mesh.x, mesh.z, np.ascontiguousarray(U, np.float64), int(source),
-                           int(nthreads), dist, prev, stats)
+                           _nt(nthreads), dist, prev, stats)
     if rc:
         raise ValueError("bad source")
     return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
@@ -183,21 +183,21 @@ def grid3d_coords(c0, c1, nn, coord_system=0):
     return X, Y, Z
 
 
-def bfm3d(nn, star_levels, X, Y, Z, U, source, nthreads=1, max_sweeps=0):
+def bfm3d(nn, star_levels, X, Y, Z, U, source, nthreads=None, max_sweeps=0):
     nn = np.asarray(nn, np.int64)
     n = int(np.prod(nn))
     dist = np.zeros(n)
     prev = np.zeros(n, np.int64)
     stats = np.zeros(4, np.int64)
     rc = lib().ora_bfm3d(nn, int(star_levels), X, Y, Z, np.ascontiguousarray(U, np.float64), int(source),
-                         int(nthreads), int(max_sweeps), dist, prev, stats)
+                         _nt(nthreads), int(max_sweeps), dist, prev, stats)
     if rc:
         raise ValueError("bad source")
     return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
                             graph_edges=int(stats[3]))
 
 
-def bfm3d_f32(nn, star_levels, X, Y, Z, U, source, nthreads=1):
+def bfm3d_f32(nn, star_levels, X, Y, Z, U, source, nthreads=None):
     """3-D solve with coordinates, U and travel times in Float32 (benchmarks/cpu.jl:9-13 runs the grid in Float32)."""
     nn = np.asarray(nn, np.int64)
     n = int(np.prod(nn))
@@ -205,7 +205,7 @@ def bfm3d_f32(nn, star_levels, X, Y, Z, U, source, nthreads=1):
     prev = np.zeros(n, np.int64)
     stats = np.zeros(4, np.int64)
     rc = lib().ora_bfm3d_f32(nn, int(star_levels), X, Y, Z, np.ascontiguousarray(U, np.float64), int(source),
-                             int(nthreads), dist, prev, stats)
+                             _nt(nthreads), dist, prev, stats)
     if rc:
         raise ValueError("bad source")
     return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
@@ -250,7 +250,7 @@ def partition_grid(r):
     return out
 
 
-def bfm_continue(mesh, U, allowed, seeds, dist, prev, nthreads=1):
+def bfm_continue(mesh, U, allowed, seeds, dist, prev, nthreads=None):
     """Restricted continuation (inner loop of bfm_multiphase, src/SSSP/bfm_multiphase.jl:118-150): returns new (dist,
     prev, stats); the inputs are not modified."""
     dist = np.array(dist, np.float64)
@@ -261,7 +261,7 @@ def bfm_continue(mesh, U, allowed, seeds, dist, prev, nthreads=1):
     halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
     rc = lib().ora_bfm_continue(mesh.n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.G_colptr, mesh.G_rowval, halo,
                                 mesh.halo_rows, mesh.x, mesh.z, np.ascontiguousarray(U, np.float64),
-                                None if al is None else al.ctypes.data_as(C.c_void_p), seeds, len(seeds), int(nthreads),
+                                None if al is None else al.ctypes.data_as(C.c_void_p), seeds, len(seeds), _nt(nthreads),
                                 dist, prev, stats)
     if rc:
         raise ValueError("bad seed")
@@ -378,7 +378,7 @@ def dual_velocity(knots_r, knots_v, r, buffer=1.0):
     return out.reshape(2, len(r)).T.copy()
 
 
-def bfm_dual(mesh, U2, source, nthreads=1):
+def bfm_dual(mesh, U2, source, nthreads=None):
     """bfm(G, halo, source, gr, U::Matrix) -> _relax!(..., U::Matrix) src/SSSP/bfm.jl:113-159."""
     n = mesh.n
     U2 = np.asarray(U2, np.float64)
@@ -388,11 +388,16 @@ def bfm_dual(mesh, U2, source, nthreads=1):
     stats = np.zeros(4, np.int64)
     halo = mesh.halo if mesh.halo_rows else np.zeros(1, np.int64)
     rc = lib().ora_bfm_dual(n, mesh.nel, mesh.e2n_off, mesh.e2n_idx, mesh.G_colptr, mesh.G_rowval, halo,
-                            mesh.halo_rows, mesh.x, mesh.z, mesh.r, u1, u2, int(source), int(nthreads), dist, prev, stats)
+                            mesh.halo_rows, mesh.x, mesh.z, mesh.r, u1, u2, int(source), _nt(nthreads), dist, prev, stats)
     if rc:
         raise ValueError("bad source")
     return dist, prev, dict(sweeps=int(stats[0]), relaxed_edges=int(stats[1]), vertex_updates=int(stats[2]),
                             graph_edges=int(stats[3]))
+
+
+def _nt(nthreads):
+    """None = every host core: the sweeps are double-buffered, results do not depend on the thread count (tests/test_oracle.py)."""
+    return num_threads() if nthreads is None else int(nthreads)
 
 
 def num_threads():

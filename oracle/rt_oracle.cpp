@@ -1206,7 +1206,7 @@ i64 ora_radius_stepping_nodal(i64 n, const i64* off, const i64* list, const doub
 
 int ora_num_threads() {
 #ifdef _OPENMP
-  return omp_get_max_threads();
+  return omp_get_num_procs();  // not omp_get_max_threads(): an earlier solve's omp_set_num_threads(1) would stick
 #else
   return 1;
 #endif
