@@ -237,9 +237,21 @@ int rt_bfm_continue(rt_mesh* m, const double* U, const uint8_t* allowed, const i
 int rt_sssp_nodal(rt_mesh* m, const double* U, int64_t source, int algorithm, double* dist_out, int64_t* prev_out,
                   rt_stats* stats);
 
-/* Solver options: key/value, e.g. ("schedule", 0 = Jacobi sweeps exactly as the reference (default),
- * 1 = work-efficient near-far ordering; dist identical, prev may differ on exact ties),
- * ("profile_timers", 1) to fill rt_stats.relax_ms. */
+/* Solver options of one mesh handle, key / value.  Results-relevant:
+ *   "schedule"        0 = Jacobi sweeps exactly as the reference (default), 1 = work-efficient near-far ordering (travel
+ *                     times bit-identical; predecessors tight, identical to the reference except on exact ties)
+ *   "canonical_prev"  1 = the near-far schedule returns the reference's predecessors, exact ties included (about one
+ *                     extra sweep over the graph)
+ *   "weight3d"        3-D edge weight expression (see rt_grid3d_build)
+ * Execution strategy only (every combination gives the same bits; defaults are the measured best):
+ *   "delta" [s] / "delta_factor"  bucket width of the near-far schedule (0 = automatic)
+ *   "batch"           2-D: sources advanced in the same launches (0 = automatic, <= 1024)
+ *   "persistent", "warp_units", "cta_units", "packed_prev", "compact", "group_screen", "target_lists", "use_graph",
+ *   "fuse_begin"      2-D near-far kernel variants / launch sequence
+ *   "tile_pull"       3-D near-far: 1 = tile-pull rounds (default), 0 = push units;  "early_advance" (tile-pull rounds)
+ *   "check_every"     rounds between host convergence checks;  "profile_timers" 1 = fill rt_stats.relax_ms,
+ *                     screened_edges, exact_edges (adds a host synchronisation per round).
+ * An unknown key returns RT_ERR_ARG. */
 int rt_set_option(rt_mesh* m, const char* key, double value);
 
 /* ---- paths: recontruct_path(prev, source, receiver) src/SSSP/ssspm.jl:30-40 ------------------------------- */
