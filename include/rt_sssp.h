@@ -46,7 +46,7 @@ typedef struct rt_stats {
   int64_t total_launches;  /* all kernel launches issued by the solve(s)                                    */
   double prev_ms;          /* device time of the predecessor (tightness) pass of the near-far schedule      */
   int64_t screened_edges;  /* E_evaluated: candidates that reached the algebraic screen (not discarded by the   */
-                           /* d_from >= bound comparison); filled with profile_timers = 1 (2-D near-far), else 0 */
+                           /* d_from >= bound comparison); filled with profile_timers = 1 (2-D near-far, 3-D tile-pull), else 0 */
   int64_t exact_edges;     /* candidates that passed the screen and paid the exact sqrt/div evaluation (same)  */
 } rt_stats;
 
