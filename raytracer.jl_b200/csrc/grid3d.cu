@@ -25,6 +25,8 @@ constexpr unsigned FULL = 0xffffffffu;
 
 }  // namespace
 
+struct TpSlot;  // per-source state of a tile-pull solve running on its own stream (batches)
+
 struct Grid3D {
   i64 nn[3] = {0, 0, 0};
   i64 n = 0;
@@ -61,6 +63,7 @@ struct Grid3D {
   DevBuf<unsigned> tmaxhi;         // [n_tiles] 1 + high word of the tile's largest travel time
   bool pull_ready = false;
   void* tp_graph = nullptr;        // cudaGraphExec_t of check_every rounds
+  std::vector<TpSlot*> tp_slots;   // batches: several sources in flight, one slot + stream each
   std::vector<char> tp_graph_key;
   CanonWs* canon = nullptr;  // canonical-predecessor pass (option canonical_prev)
 };
@@ -361,8 +364,11 @@ int grid3d_export(const rt_mesh* h, double* X, double* Y, double* Z) {
   return RT_OK;
 }
 
+void tp_slots_free(Grid3D& g);
+
 void grid3d_free(rt_mesh* h) {
   if (h->g3) {
+    tp_slots_free(*h->g3);
     if (h->g3->counters_host) cudaFreeHost(h->g3->counters_host);
     if (h->g3->canon) canon_ws_free(h->g3->canon);
     if (h->g3->tp_graph) cudaGraphExecDestroy((cudaGraphExec_t)h->g3->tp_graph);
@@ -1297,8 +1303,14 @@ int ensure_pull3(rt_mesh* h) {
 
 }  // namespace
 
+int bfm3d_solve_pull_batch(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                           rt_stats* stats);
+
 int bfm3d_solve_pull(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
                      rt_stats* stats) {
+  // a batch keeps several sources in flight (option batch: 0 = automatic, 1 = one after the other, k = k slots)
+  if (nsrc >= 2 && !h->opts.profile_timers && h->opts.batch != 1)
+    return bfm3d_solve_pull_batch(h, U_dev, sources, nsrc, dist_dev, prev_dev, stats);
   Grid3D& g = *h->g3;
   cudaStream_t s = h->stream;
   RT_TRY(ensure_ws3(h));
@@ -1307,6 +1319,7 @@ int bfm3d_solve_pull(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   const bool f32 = h->f32;
   if (f32) RT_TRY(grid3d_prepare_f32(h));
   T3 p;
+  std::memset((void*)&p, 0, sizeof(T3));  // its bytes are the key of the cached graph
   p.X = f32 ? g.Xf.p : g.X.p;
   p.Y = f32 ? g.Yf.p : g.Y.p;
   p.Z = f32 ? g.Zf.p : g.Z.p;
@@ -1522,6 +1535,323 @@ int bfm3d_solve_pull(rt_mesh* h, const double* U_dev, const i64* sources, i64 ns
   cudaEventDestroy(ev1);
   cudaEventDestroy(evr0);
   cudaEventDestroy(evr1);
+  if (stats) *stats = st;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batches on the 3-D grid: up to TP_SLOTS sources in flight, each with its own solver state and stream.  A single solve
+// leaves the machine idle in its sparse rounds (latency-bound) and at ~0.6 of the issue rate in its dense ones; the
+// rounds of another source fill those gaps (measured with separate handles, tools/probe_concurrent3d.py: 22.7 -> 18.3 ms
+// per source at 216^3).  The kernels are the single-source ones; only the host loop differs: every running slot gets
+// one CUDA-graph replay (check_every rounds) per turn, a slot that has converged runs its tightness pass, copies its
+// tables out and takes the next source of the list.
+struct TpSlot {
+  DevBuf<double> dist, tau;
+  DevBuf<i32> prev, act;
+  DevBuf<unsigned> tpend, trel, tmark, tmaxhi;
+  DevBuf<u64> counters;
+  DevBuf<int> ctl;
+  int* hctl = nullptr;   // pinned
+  u64* hcnt = nullptr;   // pinned
+  cudaStream_t stream = nullptr;
+  cudaEvent_t evp0 = nullptr, evp1 = nullptr;
+  void* graph = nullptr;
+  std::vector<char> key;
+  i64 si = -1;           // index of the source this slot is solving, -1 = idle
+  i64 rounds_enq = 0;
+};
+
+void tp_slots_free(Grid3D& g) {
+  for (TpSlot* S : g.tp_slots) {
+    if (!S) continue;
+    if (S->graph) cudaGraphExecDestroy((cudaGraphExec_t)S->graph);
+    if (S->hctl) cudaFreeHost(S->hctl);
+    if (S->hcnt) cudaFreeHost(S->hcnt);
+    if (S->evp0) cudaEventDestroy(S->evp0);
+    if (S->evp1) cudaEventDestroy(S->evp1);
+    if (S->stream) cudaStreamDestroy(S->stream);
+    delete S;
+  }
+  g.tp_slots.clear();
+}
+
+#ifndef TP_SLOTS
+#define TP_SLOTS 4
+#endif
+
+namespace {
+int tp_slot_ensure(Grid3D& g, size_t k) {
+  while (g.tp_slots.size() <= k) g.tp_slots.push_back(nullptr);
+  if (g.tp_slots[k]) return RT_OK;
+  TpSlot* S = new TpSlot();
+  g.tp_slots[k] = S;
+  RT_TRY(S->dist.alloc(g.n));
+  RT_TRY(S->prev.alloc(g.n));
+  RT_TRY(S->tpend.alloc(g.n_tiles * 4));
+  RT_TRY(S->trel.alloc(g.n_tiles * 4));
+  RT_TRY(S->tmark.alloc(g.n_tiles));
+  RT_TRY(S->tmaxhi.alloc(g.n_tiles));
+  RT_TRY(S->act.alloc(g.n_tiles));
+  RT_TRY(S->counters.alloc(16));
+  RT_TRY(S->tau.alloc(4));
+  RT_TRY(S->ctl.alloc(8));
+  RT_CUDA(cudaMallocHost((void**)&S->hctl, 8 * sizeof(int)));
+  RT_CUDA(cudaMallocHost((void**)&S->hcnt, 16 * sizeof(u64)));
+  RT_CUDA(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+  RT_CUDA(cudaEventCreate(&S->evp0));
+  RT_CUDA(cudaEventCreate(&S->evp1));
+  return RT_OK;
+}
+}  // namespace
+
+int bfm3d_solve_pull_batch(rt_mesh* h, const double* U_dev, const i64* sources, i64 nsrc, double* dist_dev, i32* prev_dev,
+                           rt_stats* stats) {
+  Grid3D& g = *h->g3;
+  RT_TRY(ensure_ws3(h));
+  RT_TRY(ensure_pull3(h));
+  const i64 n = g.n;
+  const bool f32 = h->f32;
+  if (f32) RT_TRY(grid3d_prepare_f32(h));
+  for (i64 si = 0; si < nsrc; ++si)
+    if (sources[si] < 1 || sources[si] > n) {
+      rt_set_error("source %lld out of range 1..%lld", (long long)sources[si], (long long)n);
+      return RT_ERR_ARG;
+    }
+  RT_ARG(g.n_tiles < ((i64)1 << 31), "grid too large for the near-far schedule");
+  const int K = (int)std::min<i64>(nsrc, h->opts.batch >= 2 ? std::min(h->opts.batch, 8) : TP_SLOTS);
+  for (int k = 0; k < K; ++k) RT_TRY(tp_slot_ensure(g, (size_t)k));
+  // parameter block shared by the slots (zeroed: its bytes are the key of the cached graphs)
+  T3 p0;
+  std::memset((void*)&p0, 0, sizeof(T3));
+  p0.X = f32 ? g.Xf.p : g.X.p;
+  p0.Y = f32 ? g.Yf.p : g.Y.p;
+  p0.Z = f32 ? g.Zf.p : g.Z.p;
+  p0.U = U_dev;
+  p0.nx = (int)g.nn[0];
+  p0.ny = (int)g.nn[1];
+  p0.nz = (int)g.nn[2];
+  p0.tnx = (int)g.tn[0];
+  p0.tny = (int)g.tn[1];
+  p0.tnz = (int)g.tn[2];
+  p0.n_tiles = g.n_tiles;
+  p0.w = g.w;
+  p0.self = g.self;
+  p0.wmode = h->opts.weight3d;
+  p0.count = 0;
+  p0.ctl_tail = h->opts.fuse_begin != 0;
+  p0.early = (u64)((h->opts.early_advance >= 0.0 ? h->opts.early_advance : TP_EARLY) * std::pow((double)g.n, 2.0 / 3.0));
+  p0.fd_tnx = FastDiv((unsigned)g.tn[0]);
+  p0.fd_tny = FastDiv((unsigned)g.tn[1]);
+  p0.fd_SY = FastDiv((unsigned)(TY + 2 * g.w));
+  Q3 q0 = {};
+  q0.X = p0.X;
+  q0.Y = p0.Y;
+  q0.Z = p0.Z;
+  q0.U = U_dev;
+  q0.nx = p0.nx;
+  q0.ny = p0.ny;
+  q0.nz = p0.nz;
+  q0.w = g.w;
+  q0.self = g.self;
+  q0.wmode = p0.wmode;
+  const int w = g.w;
+  const size_t SN = (size_t)(TX + 2 * w) * (TY + 2 * w) * (TZ + 2 * w);
+  const size_t smem = 5 * SN * sizeof(double) + (size_t)((TY + 2 * w) * (TZ + 2 * w) + (TZ + 2 * w)) * sizeof(unsigned);
+  RT_CUDA(cudaFuncSetAttribute(tp_pull_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RT_CUDA(cudaFuncSetAttribute(tp_pull_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, h->device);
+  int per_sm = 1;
+  if (f32)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tp_pull_kernel<true>, TILE_THREADS, smem);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tp_pull_kernel<false>, TILE_THREADS, smem);
+  const unsigned gpull = (unsigned)std::min<i64>(g.n_tiles, (i64)sm_count * std::max(per_sm, 1));
+  const unsigned grel = grid_for(g.n_tiles, TPR_BLOCK);
+  // bucket width (same rule as the single-source path)
+  double delta = h->opts.delta;
+  if (!(delta > 0.0)) {
+    cudaStream_t s = h->stream;
+    cudaMemsetAsync(g.tau.p + 3, 0, sizeof(double), s);
+    cudaMemsetAsync(g.counters.p + 7, 0, sizeof(u64), s);
+    wdiag3_kernel<<<grid_for((n + 6) / 7, 256), 256, 0, s>>>(q0, g.tau.p + 3, g.counters.p + 7);
+    double wsum = 0.0;
+    u64 wc = 0;
+    cudaMemcpyAsync(&wsum, g.tau.p + 3, sizeof(double), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&wc, g.counters.p + 7, sizeof(u64), cudaMemcpyDeviceToHost, s);
+    RT_CUDA(cudaStreamSynchronize(s));
+    const double wmean = wc ? wsum / (double)wc : 1.0;
+    delta = wmean * (h->opts.delta_factor > 0.0 ? h->opts.delta_factor : TP_DELTA_FACTOR);
+  }
+  const int R = h->opts.check_every > 1 ? h->opts.check_every : 32;
+  const int launches_per_round = p0.ctl_tail ? 2 : 3;
+  std::vector<T3> P((size_t)K, p0);
+  auto enqueue_rounds = [&](const T3& p, cudaStream_t qs) {
+    for (int r = 0; r < R; ++r) {
+      tp_release_kernel<<<grel, TPR_BLOCK, 0, qs>>>(p);
+      if (f32)
+        tp_pull_kernel<true><<<gpull, TILE_THREADS, smem, qs>>>(p);
+      else
+        tp_pull_kernel<false><<<gpull, TILE_THREADS, smem, qs>>>(p);
+      if (!p.ctl_tail) tp_ctl_kernel<<<1, 1, 0, qs>>>(p);
+    }
+  };
+  for (int k = 0; k < K; ++k) {
+    TpSlot& S = *g.tp_slots[(size_t)k];
+    T3& p = P[(size_t)k];
+    p.dist = S.dist.p;
+    p.tpend = S.tpend.p;
+    p.trel = S.trel.p;
+    p.tmark = S.tmark.p;
+    p.tmaxhi = S.tmaxhi.p;
+    p.act = S.act.p;
+    p.counters = S.counters.p;
+    p.tau = S.tau.p;
+    p.ctl = S.ctl.p;
+    S.si = -1;
+    if (h->opts.use_graph) {
+      std::vector<char> key(sizeof(T3) + 4 * sizeof(int));
+      std::memcpy(key.data(), &p, sizeof(T3));
+      const int kv[4] = {R, (int)gpull, (int)f32, (int)smem};
+      std::memcpy(key.data() + sizeof(T3), kv, sizeof(kv));
+      if (S.graph && key != S.key) {
+        cudaGraphExecDestroy((cudaGraphExec_t)S.graph);
+        S.graph = nullptr;
+      }
+      if (!S.graph) {
+        cudaGraph_t cg = nullptr;
+        if (cudaStreamBeginCapture(S.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+          enqueue_rounds(p, S.stream);
+          if (cudaStreamEndCapture(S.stream, &cg) == cudaSuccess && cg) {
+            cudaGraphExec_t ge = nullptr;
+            if (cudaGraphInstantiate(&ge, cg, 0) == cudaSuccess) {
+              S.graph = (void*)ge;
+              S.key = key;
+            }
+            cudaGraphDestroy(cg);
+          }
+        }
+        cudaGetLastError();  // a failed capture falls back to plain launches
+      }
+    } else if (S.graph) {
+      cudaGraphExecDestroy((cudaGraphExec_t)S.graph);
+      S.graph = nullptr;
+    }
+  }
+  rt_stats st = {};
+  st.graph_edges = g.graph_edges;
+  int rc = RT_OK;
+  cudaEvent_t ev0, ev1;
+  RT_CUDA(cudaEventCreate(&ev0));
+  RT_CUDA(cudaEventCreate(&ev1));
+  cudaEventRecord(ev0, h->stream);
+  i64 next = 0, finished = 0;
+  auto start = [&](int k) {  // slot k takes source `next`
+    TpSlot& S = *g.tp_slots[(size_t)k];
+    const T3& p = P[(size_t)k];
+    cudaStream_t s = S.stream;
+    S.si = next++;
+    S.rounds_enq = 0;
+    cudaMemsetAsync(S.counters.p, 0, 16 * sizeof(u64), s);
+    cudaMemsetAsync(S.tmaxhi.p, 0xff, g.n_tiles * sizeof(unsigned), s);
+    cudaMemsetAsync(S.tpend.p, 0, g.n_tiles * 4 * sizeof(unsigned), s);
+    cudaMemsetAsync(S.trel.p, 0, g.n_tiles * 4 * sizeof(unsigned), s);
+    cudaMemsetAsync(S.tmark.p, 0, g.n_tiles * sizeof(unsigned), s);
+    cudaMemsetAsync(S.ctl.p, 0, 8 * sizeof(int), s);
+    tp_init_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, S.prev.p, n, sources[S.si] - 1, delta);
+    st.total_launches += 1;
+  };
+  for (int k = 0; k < K && next < nsrc; ++k) start(k);
+  while (finished < nsrc && rc == RT_OK) {
+    for (int k = 0; k < K; ++k) {  // one replay of R rounds for every running slot
+      TpSlot& S = *g.tp_slots[(size_t)k];
+      if (S.si < 0) continue;
+      if (S.graph) {
+        if (cudaGraphLaunch((cudaGraphExec_t)S.graph, S.stream) != cudaSuccess) rc = RT_ERR_CUDA;
+      } else {
+        enqueue_rounds(P[(size_t)k], S.stream);
+      }
+      st.total_launches += (i64)launches_per_round * R;
+      S.rounds_enq += R;
+      cudaMemcpyAsync(S.hctl, S.ctl.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, S.stream);
+    }
+    for (int k = 0; k < K && rc == RT_OK; ++k) {
+      TpSlot& S = *g.tp_slots[(size_t)k];
+      if (S.si < 0) continue;
+      if (cudaStreamSynchronize(S.stream) != cudaSuccess) {
+        rc = RT_ERR_CUDA;
+        break;
+      }
+      if (!S.hctl[3]) {
+        if (S.rounds_enq > ((i64)1 << 22)) {
+          rt_set_error("near-far schedule did not converge within %lld rounds", (long long)S.rounds_enq);
+          rc = RT_ERR_CUDA;
+        }
+        continue;
+      }
+      // converged: predecessors, tables out, counters; then the slot takes the next source
+      const i64 si = S.si;
+      const i64 src = sources[si] - 1;
+      Q3 q = q0;
+      q.dist = S.dist.p;
+      q.prev = S.prev.p;
+      cudaEventRecord(S.evp0, S.stream);
+      if (f32)
+        prev_tight3_kernel<true><<<grid_for(n, 128), 128, 0, S.stream>>>(q, n, src);
+      else
+        prev_tight3_kernel<false><<<grid_for(n, 128), 128, 0, S.stream>>>(q, n, src);
+      st.total_launches += 1;
+      if (h->opts.canonical_prev) {  // one workspace, the handle's stream: serialised
+        if (cudaStreamSynchronize(S.stream) != cudaSuccess) {
+          rc = RT_ERR_CUDA;
+          break;
+        }
+        Grid3Desc gd{q0.X, q0.Y, q0.Z, q0.nx, q0.ny, q0.nz, g.w, g.self, q0.wmode};
+        i64 launches = 0;
+        rc = canonical_prev_3d(h, &g.canon, gd, U_dev, f32, S.dist.p, src, S.prev.p, &launches);
+        st.total_launches += launches;
+        if (rc != RT_OK) break;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
+          rc = RT_ERR_CUDA;
+          break;
+        }
+      }
+      cudaEventRecord(S.evp1, S.stream);
+      cudaMemcpyAsync(S.hcnt, S.counters.p, 16 * sizeof(u64), cudaMemcpyDeviceToHost, S.stream);
+      if (dist_dev) cudaMemcpyAsync(dist_dev + si * n, S.dist.p, n * sizeof(double), cudaMemcpyDeviceToDevice, S.stream);
+      if (prev_dev) cudaMemcpyAsync(prev_dev + si * n, S.prev.p, n * sizeof(i32), cudaMemcpyDeviceToDevice, S.stream);
+      if (cudaStreamSynchronize(S.stream) != cudaSuccess) {
+        rc = RT_ERR_CUDA;
+        break;
+      }
+      st.sweeps += S.hctl[4];
+      st.relax_launches += S.hctl[5];
+      st.relaxed_edges += (i64)S.hcnt[2];
+      st.vertex_updates += (i64)S.hcnt[3];
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, S.evp0, S.evp1);
+      st.prev_ms += ms;
+      finished += 1;
+      S.si = -1;
+      if (next < nsrc) start(k);
+    }
+  }
+  for (int k = 0; k < K; ++k) cudaStreamSynchronize(g.tp_slots[(size_t)k]->stream);
+  cudaEventRecord(ev1, h->stream);  // the handle's stream was idle throughout: ev0 .. ev1 brackets the batch in host order
+  cudaStreamSynchronize(h->stream);
+  {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    st.kernel_ms = ms;
+  }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  cudaError_t e = cudaGetLastError();
+  if (rc == RT_ERR_CUDA || e != cudaSuccess) {
+    if (e != cudaSuccess) rt_set_error("CUDA failure in bfm3d_solve_pull_batch: %s", cudaGetErrorString(e));
+    rc = RT_ERR_CUDA;
+  }
   if (stats) *stats = st;
   return rc;
 }

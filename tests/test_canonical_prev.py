@@ -223,6 +223,12 @@ def test_near_far_3d_canonical_prev_equals_reference_schedule(rt, O, nn, lv, cs,
         d32, p32, _ = O.bfm3d_f32(nn, lv, X, Y, Z, U, 1)
         D32 = rt.bfm3d(g, 1, U, schedule="near-far", precision=32, canonical_prev=True)
         assert np.array_equal(D32.dist.astype(np.float64), d32) and np.array_equal(D32.prev, p32)
+        # a batch keeps its sources in flight in per-source slots: same tables, canonical predecessors included
+        srcs = np.array([1, n // 2 + 3, n, 2, n // 3 + 1], np.int64)
+        DB = rt.bfm3d(g, srcs, U, schedule="near-far", canonical_prev=True)
+        for k, sk in enumerate(srcs):
+            dist, prev, st = O.bfm3d(nn, lv, X, Y, Z, U, int(sk))
+            assert np.array_equal(DB.dist[k], dist) and np.array_equal(DB.prev[k], prev), "batch slot %d" % k
     finally:
         O.set_weight3d(0)
         g._handle.set_option("weight3d", 0)

@@ -379,10 +379,12 @@ def test_bfm3d_near_far_schedule(rt, O, nn, lv, cs):
     ref = [O.bfm3d(nn, lv, X, Y, Z, U, int(s)) for s in srcs]
     # tile_pull = 1 (default): targets pull from the released sources tile by tile; 0: push units per released x-line
     # early_advance > 0: the threshold moves on while stragglers of the bucket are still being released
-    for tile_pull, delta, early in ((1, 0.0, 0.0), (1, 1e-3, 0.0), (1, 1e9, 0.0), (1, 0.0, 2.0), (0, 0.0, 0.0),
-                                    (0, 1e9, 0.0)):
+    # batch: 0 = the sources of the call run concurrently in per-source slots (tile-pull), 1 = one after the other
+    for tile_pull, delta, early, batch in ((1, 0.0, 0.0, 0), (1, 1e-3, 0.0, 2), (1, 1e9, 0.0, 0), (1, 0.0, 2.0, 1),
+                                           (1, 0.0, 0.0, 1), (0, 0.0, 0.0, 0), (0, 1e9, 0.0, 0)):
         g._handle.set_option("tile_pull", tile_pull)
         g._handle.set_option("early_advance", early)
+        g._handle.set_option("batch", batch)
         D = rt.bfm3d(g, srcs, U, schedule="near-far", delta=delta)
         for k, s in enumerate(srcs):
             dist, prev, st = ref[k]
@@ -397,6 +399,7 @@ def test_bfm3d_near_far_schedule(rt, O, nn, lv, cs):
     assert D.stats["relaxed_edges"] > 0
     g._handle.set_option("tile_pull", 1)
     g._handle.set_option("early_advance", -1)
+    g._handle.set_option("batch", 0)
     rt.bfm3d(g, 1, U, schedule="jacobi")
 
 
