@@ -245,7 +245,9 @@ int rt_sssp_nodal(rt_mesh* m, const double* U, int64_t source, int algorithm, do
  *   "weight3d"        3-D edge weight expression (see rt_grid3d_build)
  * Execution strategy only (every combination gives the same bits; defaults are the measured best):
  *   "delta" [s] / "delta_factor"  bucket width of the near-far schedule (0 = automatic)
- *   "batch"           2-D: sources advanced in the same launches (0 = automatic, <= 1024)
+ *   "batch"           2-D: sources advanced in the same launches (0 = automatic, <= 1024); 3-D tile-pull rounds: sources
+ *                     of a call in flight at once, each in its own slot and stream (0 = automatic = 4, 1 = one after the
+ *                     other, k <= 8)
  *   "persistent", "warp_units", "cta_units", "packed_prev", "compact", "group_screen", "target_lists", "use_graph",
  *   "fuse_begin"      2-D near-far kernel variants / launch sequence
  *   "tile_pull"       3-D near-far: 1 = tile-pull rounds (default), 0 = push units;  "early_advance" (tile-pull rounds)
