@@ -536,7 +536,9 @@ def bfm_gpu(G, halo, source, gr, U, schedule=None, canonical_prev=None):
 def bfm3d(gr3, source, U, schedule=None, delta=None, precision=64, canonical_prev=None):
     """BFM(G, source, gr, U, fw) of src/Dijsktra.jl:294-343 on the implicit star-L graph of a Grid3D with the
     edge weight of src/SSSP/weights.jl:20 (option "weight3d" = 1: the expression inside foo!, Dijsktra.jl:388).
-    canonical_prev=True (near-far): predecessors of the reference schedule, ties included."""
+    canonical_prev=True (near-far): predecessors of the reference schedule, ties included.
+    schedule="near-far" runs tile-pull rounds (option "tile_pull" = 0: push units); a batch of sources keeps up to four
+    of them in flight in per-source slots (option "batch" = 1: one after the other)."""
     if schedule is not None:
         gr3._handle.set_option("schedule", SCHEDULES[schedule])
     if canonical_prev is not None:
